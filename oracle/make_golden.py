@@ -1,0 +1,234 @@
+#!/usr/bin/env python
+"""Pin the oracle against the UNMODIFIED reference and (re)generate tests/golden/*.npz.
+
+TEST INFRASTRUCTURE ONLY; runs only in the build container (needs /root/reference).
+
+    python oracle/make_golden.py            # check oracle == reference on every case, write fixtures
+    python oracle/make_golden.py --check    # check only
+
+For each seeded case it runs the reference's own ``smooth_fit`` (through ``oracle/ref_harness``)
+and the restatement in ``oracle/lssurf_oracle`` on identical inputs and requires
+  * G_data.toCSR() and Gc.toCSR(): indptr / indices / data identical bit for bit, Ec identical;
+  * the edit mask after every outer iteration identical; sigma_extra within 1e-5 absolute
+    (Brent's own xatol; the two CPU solvers differ at 1e-12);
+  * the final model within 1e-9 relative L2.
+The fixtures hold the inputs, sha256 digests of the reference CSR arrays and the per-iteration
+reference outputs, so the `-m "not gpu"` tests can re-check the oracle, and the GPU tests the
+CUDA product, where /root/reference does not exist.
+"""
+import argparse
+import hashlib
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import lssurf_oracle as O      # noqa: E402
+from oracle import ref_harness as H        # noqa: E402
+from lssurf_b200 import synthetic as S     # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def csr_digest(M):
+    M = M.tocsr()
+    assert M.has_canonical_format
+    return digest(M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64))
+
+
+def run_reference(pts, kw):
+    """Reference smooth_fit with taps on calc_sigma_extra (per-iteration residual/mask/sigma_extra)."""
+    L = H.load()
+    SF = H.smooth_fit_module()
+    D = H.point_data(**pts)
+    fo = L.smooth_fit(data=D.copy(), VERBOSE=False, return_fit_objects=True, **kw)
+    trace = []
+    orig = SF.calc_sigma_extra
+
+    def tap(r, sigma, mask, sigma_extra_masks=None):
+        out = orig(r, sigma, mask, sigma_extra_masks)
+        trace.append(dict(r=r.copy(), mask_in=mask.copy(), sigma_extra=out.copy()))
+        return out
+    SF.calc_sigma_extra = tap
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            out = L.smooth_fit(data=D.copy(), VERBOSE=False, **kw)
+    finally:
+        SF.calc_sigma_extra = orig
+    return fo, out, trace
+
+
+def case_fit(name, pts, kw, write):
+    print(f'== {name}: {pts["x"].size} points')
+    fo, out, trace = run_reference(pts, kw)
+    G_ref, C_ref = fo['G_data'].toCSR(), fo['Gc'].toCSR()
+    hist = []
+    bias = [pts[k] for k in kw['bias_params']] if kw.get('bias_params') else None
+    res = O.smooth_fit(pts['x'], pts['y'], pts['time'], pts['z'], pts['sigma'], kw['ctr'], kw['W'], kw['spacing'],
+                       kw['E_RMS'], reference_epoch=kw['reference_epoch'], max_iterations=kw['max_iterations'],
+                       bias_params=bias, sigma_corr=pts.get('sigma_corr'), history=hist)
+    s = res['sys']
+    n, ncol = s['n_data'], s['col_N']
+    # --- structure: bit exact
+    Gd = digest(*s['G'][:3])
+    Cd = digest(*s['C'][:3])
+    assert G_ref.shape == (n, ncol), (G_ref.shape, n, ncol)
+    assert Gd == csr_digest(G_ref), 'G_data CSR differs from reference'
+    assert C_ref.shape[1] == ncol and Cd == csr_digest(C_ref), 'Gc CSR differs from reference'
+    assert digest(s['Ec']) == digest(np.asarray(fo['Ec'], dtype=float)), 'Ec differs'
+    assert np.array_equal(res['valid'], out['valid_data'] | res['valid']) and res['valid'].sum() == n
+    # --- iterations
+    m_ref = out['m']['all']
+    n_it = len(trace)
+    assert n_it == sum('sigma_extra' in h for h in hist), (n_it, len(hist))
+    masks, sig_x, n_close = [], [], []
+    for k, tr in enumerate(trace):
+        assert np.array_equal(tr['mask_in'], hist[k]['mask_in']), f'mask into iteration {k} differs'
+        se_ref = tr['sigma_extra']
+        assert np.max(np.abs(se_ref - hist[k]['sigma_extra'])) < 1e-5, f'sigma_extra iteration {k}'
+        masks.append(np.packbits(hist[k]['mask_out']))
+        sig_x.append(float(np.median(se_ref)))
+        aug = np.sqrt(pts['sigma'][res['valid']] ** 2 + se_ref ** 2)
+        n_close.append(int(np.sum(np.abs(np.abs(tr['r'] / aug) - 3.0) < 1e-6)))
+    tse_ref = np.asarray(out['data'].three_sigma_edit, dtype=bool)
+    assert np.array_equal(tse_ref, res['in_TSE']), 'final edit mask differs'
+    rel = np.linalg.norm(res['m0'] - m_ref) / np.linalg.norm(m_ref)
+    print(f'   G {G_ref.shape} nnz={G_ref.nnz}  Gc {C_ref.shape} nnz={C_ref.nnz}  outer={len(hist)}'
+          f'  rel-L2(m0)={rel:.2e}  in_TSE={int(tse_ref.sum())}  near-threshold={n_close}')
+    assert rel < 1e-9, rel
+    if write:
+        fx = dict(G_digest=Gd, C_digest=Cd, Ec_digest=digest(s['Ec']), G_shape=np.array(G_ref.shape),
+                  C_shape=np.array(C_ref.shape), G_nnz=G_ref.nnz, C_nnz=C_ref.nnz, m0=m_ref,
+                  z_est=np.asarray(out['data'].z_est), in_TSE=np.packbits(tse_ref), n_data=n,
+                  sigma_extra=np.array(sig_x), masks=np.array(masks), n_outer=len(hist),
+                  near_threshold=np.array(n_close), kw=repr(kw),
+                  toc_rows=np.array([f'{k}:{len(np.unique(v))}' for k, v in fo['Gc'].TOC['rows'].items()]))
+        fx.update({'in_' + k: v for k, v in pts.items()})
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **fx)
+
+
+def case_lowlevel(write):
+    """interp_mtx / diff_op / toCSR on edge inputs (upper-bound points, on-node points, NaN,
+    out-of-bounds with bounds_error=False) in 1, 2 and 3 dimensions."""
+    print('== lowlevel')
+    L = H.load()
+    rng = np.random.default_rng(7)
+    fx = {}
+    specs = {'g1': ([[0., 10.]], [0.25]), 'g2': ([[-3., 5.], [100., 131.]], [0.5, 1.7]),
+             'g3': ([[-1e3, 1e3], [-2e3, 1e3], [-1., 1.]], [100., 100., 0.25])}
+    for gname, (bounds, deltas) in specs.items():
+        col_0 = 17 if gname == 'g3' else 0
+        gr = L.fd_grid(bounds, deltas, name=gname, col_0=col_0)
+        go = O.grid_geometry(bounds, deltas, col_0=col_0, name=gname)
+        assert np.array_equal(gr.shape, go['shape']) and np.array_equal(gr.stride, go['stride'])
+        m = 400
+        pts = [rng.uniform(b[0] - 0.05 * (b[1] - b[0]), b[1] + 0.05 * (b[1] - b[0]), m) for b in bounds]
+        for d in range(len(bounds)):
+            pts[d][:20] = gr.ctrs[d][rng.integers(0, gr.shape[d], 20)]       # exactly on nodes
+            pts[d][20:30] = gr.bds[d][1]                                      # on the upper bound
+            pts[d][30:40] = gr.bds[d][0]
+        pts[0][40:44] = np.nan
+        op = L.lin_op(gr, name='interp').interp_mtx(pts, bounds_error=False)
+        r, c, v = O.interp_triplets(go, pts, bounds_error=False)
+        assert np.array_equal(op.r, r) and np.array_equal(op.c, c) and digest(op.v) == digest(v), gname
+        M = op.toCSR(row_N=m)
+        ip, ix, dat, _ = O.coo_to_csr(r, c, v, n_rows=m, n_cols=gr.col_N)
+        assert csr_digest(M) == digest(ip, ix, dat), gname
+        try:
+            L.lin_op(gr).interp_mtx(pts)
+            raise AssertionError('reference did not raise')
+        except ValueError as e:
+            msg = str(e)
+        fx[gname + '_bounds'] = np.array(bounds)
+        fx[gname + '_deltas'] = np.array(deltas)
+        fx[gname + '_col0'] = col_0
+        fx[gname + '_pts'] = np.array(pts)
+        fx[gname + '_rcv'] = digest(op.r.astype(np.int64), op.c.astype(np.int64), op.v)
+        fx[gname + '_csr'] = csr_digest(M)
+        fx[gname + '_nvalid'] = op.N_eq
+        fx[gname + '_err'] = msg
+        print(f'   {gname}: shape={gr.shape} valid={op.N_eq}/{m} csr nnz={M.nnz} err="{msg}"')
+    # stencils: every built-in family + a custom 9-point template (aniso notebook style)
+    g2r = L.fd_grid(*specs['g2'], name='z0')
+    g3r = L.fd_grid(*specs['g3'], name='dz', col_0=g2r.N_nodes)
+    g2o = O.grid_geometry(*specs['g2'], name='z0')
+    g3o = O.grid_geometry(*specs['g3'], name='dz', col_0=g2o['n_nodes'])
+    fam_dig = []
+    for kind, gr_, go_, build in (('grad2_z0', g2r, g2o, lambda o: o.grad2(DOF='z0')),
+                                  ('grad_z0', g2r, g2o, lambda o: o.grad(DOF='z0')),
+                                  ('grad2_dzdt', g3r, g3o, lambda o: o.grad2_dzdt(DOF='z', t_lag=1)),
+                                  ('grad_dzdt', g3r, g3o, lambda o: o.grad_dzdt(DOF='z', t_lag=1)),
+                                  ('d2z_dt2', g3r, g3o, lambda o: o.d2z_dt2(DOF='z'))):
+        op = build(L.lin_op(gr_, name=kind))
+        row_0, rr, cc, vv, i0 = 0, [], [], [], []
+        for name, offs, coef in O.stencil_families(go_, kind):
+            r, c, v, ind0 = O.stencil_triplets(go_, offs, coef)
+            assert np.array_equal(op.TOC['rows'][name], np.arange(row_0, row_0 + r.shape[0])), name
+            rr.append(r.ravel() + row_0); cc.append(c.ravel()); vv.append(v.ravel()); i0.append(ind0)
+            row_0 += r.shape[0]
+        assert np.array_equal(op.r.ravel(), np.concatenate(rr)), kind
+        assert np.array_equal(op.c.ravel(), np.concatenate(cc)), kind
+        assert digest(op.v.ravel()) == digest(np.concatenate(vv)), kind
+        assert np.array_equal(op.ind0, np.concatenate(i0)), kind
+        d = digest(op.r.ravel().astype(np.int64), op.c.ravel().astype(np.int64), op.v.ravel(),
+                   np.asarray(op.ind0).astype(np.int64))
+        fam_dig.append(f'{kind}:{op.N_eq}:{d}')
+        print(f'   {kind}: N_eq={op.N_eq}')
+    offs = ([-1, -1, -1, 0, 0, 0, 1, 1, 1], [-1, 0, 1, -1, 0, 1, -1, 0, 1])
+    coef = np.array([0.5, -1.25, 0.5, 2., -3.5, 2., 0.5, -1.25, 0.5])
+    op = L.lin_op(g2r, name='custom').diff_op(offs, coef)
+    r, c, v, ind0 = O.stencil_triplets(g2o, offs, coef)
+    assert np.array_equal(op.r, r) and np.array_equal(op.c, c) and digest(op.v) == digest(v)
+    fam_dig.append('custom9:%d:%s' % (op.N_eq, digest(op.r.astype(np.int64), op.c.astype(np.int64), op.v,
+                                                      np.asarray(op.ind0).astype(np.int64))))
+    fx['stencils'] = np.array(fam_dig)
+    # RDE + sigma_extra known answers
+    x = rng.standard_t(3, 5001)
+    x[::97] = np.nan
+    sg = rng.uniform(0.05, 0.2, x.size)
+    msk = rng.random(x.size) < 0.9
+    fx['rde_x'], fx['rde_sigma'], fx['rde_mask'] = x, sg, msk
+    fx['rde'] = L.RDE(x)
+    assert fx['rde'] == O.rde(x) == O.rde_select(x)
+    xs = x.copy(); xs[~np.isfinite(xs)] = 0.
+    se_ref = L.calc_sigma_extra(xs, sg, msk)
+    se_or = O.sigma_extra(xs, sg, msk)
+    assert np.array_equal(se_ref, se_or), (se_ref[0], se_or[0])
+    fx['sigma_extra'] = se_ref[0]
+    print(f'   RDE={fx["rde"]:.6f} sigma_extra={se_ref[0]:.6f} (bit-identical to reference)')
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN, 'lowlevel.npz'), **fx)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--check', action='store_true')
+    a = ap.parse_args()
+    write = not a.check
+    os.makedirs(GOLDEN, exist_ok=True)
+    case_lowlevel(write)
+    case_fit('strip_nb', *S.notebook_strip(), write)
+    case_fit('strip_outliers', *S.notebook_strip(outliers=True, seed=0), write)
+    case_fit('uniform3d_small', *S.uniform_3d(n=6000, width=1.2e4, seed=1), write)
+    pts, kw = S.icesat2_tracks(n=8000, width=1.2e4, seed=2, t_span=3.)
+    case_fit('tracks_bias_small', pts, kw, write)
+    print('all cases: oracle == reference')
+
+
+if __name__ == '__main__':
+    main()
