@@ -1,0 +1,178 @@
+/*
+ * lssurf_b200 -- C ABI of the B200-native smooth_fit hot path.
+ *
+ * The reference (SmithB/LSsurf) is pure Python with no FFI layer; its boundary for this path is
+ * its Python API.  These entry points are what a ctypes binding inside the reference's
+ * lin_op.py / smooth_fit.py / calc_sigma_extra.py / RDE.py would call (INTEGRATION.md shows the
+ * stubs).  Each function cites the reference lines it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _h (host pointer);
+ *   - index arrays are int32, values fp64, sizes int64; `stream` is a cudaStream_t passed as void*;
+ *   - every function returns 0 on success, a negative LSS_E* code otherwise; lss_last_error()
+ *     returns a thread-local message for the last failure;
+ *   - functions with *_h outputs synchronise `stream` before returning, all others are
+ *     asynchronous on `stream`;
+ *   - nothing here falls back to the CPU: without a CUDA device every compute call fails.
+ */
+#ifndef LSSURF_B200_H
+#define LSSURF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSS_OK 0
+#define LSS_EINVAL -1   /* bad argument */
+#define LSS_ECUDA -2    /* CUDA runtime error */
+#define LSS_ENCCL -3    /* NCCL error / NCCL not loadable */
+#define LSS_EBOUNDS -4  /* points out of bounds with bounds_error set (lin_op.py:202-203) */
+#define LSS_ERANGE -5   /* size exceeds the int32 index range of the CSR format */
+
+#define LSS_MAX_DIMS 3
+
+/* Regular node grid: the hot-path subset of fd_grid (LSsurf/fd_grid.py:61-80). */
+typedef struct lss_grid {
+    int32_t ndim;                 /* 1..3, coordinate order (y, x, t)            fd_grid.py:25 */
+    int64_t shape[LSS_MAX_DIMS];  /* nodes per dimension                         fd_grid.py:61 */
+    int64_t stride[LSS_MAX_DIMS]; /* C-order strides in columns                  fd_grid.py:67 */
+    double lo[LSS_MAX_DIMS];      /* bds[d][0] = first node centre               fd_grid.py:63 */
+    double hi[LSS_MAX_DIMS];      /* bds[d][1] = last node centre                fd_grid.py:63 */
+    double delta[LSS_MAX_DIMS];   /* node spacing                                fd_grid.py:64 */
+    int64_t col_0;                /* first global column of the grid             fd_grid.py:68 */
+} lss_grid_t;
+
+int lss_version(void);
+const char *lss_last_error(void);
+/* Number of CUDA devices visible (0 => every compute entry point fails with LSS_ECUDA). */
+int lss_device_count(void);
+
+/* ------------------------------------------------------------------ design-matrix assembly */
+
+/* lin_op.interp_mtx (lin_op.py:163-247) with fd_grid.validate_pts / float_sub / cell_sub_for_pts /
+ * global_ind (fd_grid.py:90-145).  One row per input point i (row index = row_0 + i); 2^ndim
+ * triplets per row in np.mgrid corner order (dimension 0 slowest).  Weights are formed as
+ * 1.0 * prod_d (frac_d | 1 - frac_d) for ascending d with individually rounded fp64 operations
+ * (no FMA contraction), so they are bit-identical to NumPy's.  Points outside the closed grid
+ * bounds (or with a non-finite first coordinate) get valid[i] = 0, zero weights and column col_0.
+ * pts_h: host array of ndim device pointers (y, x[, t]).  n_invalid_h: host out. */
+int lss_interp_coo(const lss_grid_t *grid, const double *const *pts_h, int64_t n, int64_t row_0,
+                   int32_t *rows, int32_t *cols, double *vals, uint8_t *valid, int64_t *n_invalid_h,
+                   void *stream);
+
+/* Number of equations lin_op.diff_op produces (lin_op.py:88-103, 109).  Host-only helper.
+ * offsets_h: [ndim][n_off] int32 (row-major).  first_h/count_h (optional, [ndim]) receive the first
+ * valid centre subscript and the number of valid centres per dimension. */
+int lss_stencil_count(const lss_grid_t *grid, int32_t n_off, const int32_t *offsets_h, int32_t valid_only,
+                      int64_t *n_eq_h, int64_t *first_h, int64_t *count_h);
+
+/* lin_op.diff_op (lin_op.py:80-132): one row per valid centre node in C order, n_off triplets per
+ * row; ind0[i] = global column of the centre (lin_op.py:128).  With valid_only == 0 every node is a
+ * centre and out-of-grid offsets get column 0 and value 0 (lin_op.py:118-121). */
+int lss_stencil_coo(const lss_grid_t *grid, int32_t n_off, const int32_t *offsets_h, const double *coeffs_h,
+                    int64_t row_0, int32_t valid_only, int64_t n_eq, int32_t *rows, int32_t *cols,
+                    double *vals, int64_t *ind0, void *stream);
+
+/* max(r[v != 0]) (lin_op.py:750-752), -1 if there is none; and the count of v != 0. */
+int lss_coo_extent(int64_t nnz, const int32_t *rows, const double *vals, int64_t *max_row_h,
+                   int64_t *n_nonzero_h, void *stream);
+
+/* lin_op.toCSR (lin_op.py:745-753) == scipy coo_tocsr + sum_duplicates: drop v == 0, stable sort by
+ * (row, col), sum duplicates left to right, build indptr.  Output is canonical CSR (sorted
+ * indices, no duplicates).  indices/data must hold nnz entries; *nnz_out_h receives the CSR nnz. */
+int lss_coo_to_csr(int64_t nnz, const int32_t *rows, const int32_t *cols, const double *vals,
+                   int64_t n_rows, int64_t n_cols, int32_t *indptr, int32_t *indices, double *data,
+                   int64_t *nnz_out_h, void *stream);
+
+/* CSR of the transpose (scipy csr.T.tocsr(); used for G^T products, smooth_fit.py:142, 339-345).
+ * Entries of each output row keep ascending source-row order. */
+int lss_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *indptr,
+                      const int32_t *indices, const double *data, int32_t *t_indptr, int32_t *t_indices,
+                      double *t_data, void *stream);
+
+/* Stable argsort of int64 keys in [0, 2^key_bits) (used for the internal spatial ordering of points). */
+int lss_argsort_u64(int64_t n, const uint64_t *keys, int32_t key_bits, int32_t *order, void *stream);
+
+/* ------------------------------------------------------------------ CSR products */
+
+#define LSS_SPMV_PLAIN 0     /* y = A x                                                        */
+#define LSS_SPMV_SCALE 1     /* y = s .* (A x)        (row weights, smooth_fit.py:129, 142)     */
+#define LSS_SPMV_RESIDUAL 2  /* y = s - A x           (r_data = z - G m0, smooth_fit.py:146)    */
+
+/* scipy csr_matvec replacement (smooth_fit.py:142, 146, 326-345).  nnz-balanced tiles, deterministic
+ * (no atomics).  `s` is read only for modes 1 and 2.  rows [row_begin, row_end) only. */
+int lss_spmv(int64_t n_rows, int64_t n_cols, const int32_t *indptr, const int32_t *indices, const double *data,
+             const double *x, double *y, int32_t mode, const double *s, void *stream);
+
+/* ------------------------------------------------------------------ multi-GPU communicator */
+
+typedef struct lss_comm lss_comm_t;
+#define LSS_UNIQUE_ID_BYTES 128
+/* ncclGetUniqueId: rank 0 calls this and ships the bytes to the other ranks (any host transport). */
+int lss_comm_unique_id(char *id_h);
+int lss_comm_create(lss_comm_t **comm, const char *id_h, int32_t rank, int32_t n_ranks);
+int lss_comm_destroy(lss_comm_t *comm);
+int lss_comm_allreduce_f64(lss_comm_t *comm, double *buf, int64_t n, void *stream); /* in-place sum */
+
+/* ------------------------------------------------------------------ normal-equation PCG solve */
+
+typedef struct lss_solver lss_solver_t;
+
+/* Replaces sparseqr.solve on the row-selected, 1/sigma-scaled system (smooth_fit.py:123-142) by a
+ * matrix-free fp64 preconditioned CG on (A^T W A) x = A^T W b, where A = [G; C] is this rank's block
+ * of data rows stacked on its share of the constraint rows, W = diag(w), b = [z; prior].
+ * Columns listed in fixed_cols (the reference-epoch columns removed by Ip_c,
+ * constraint_functions.py:128-151) are held at exactly 0.  With a communicator the products
+ * A^T W (A p) and the dot products are summed over ranks with one NCCL all-reduce per iteration.
+ * The solver borrows every array (the caller keeps them alive until lss_solver_destroy). */
+int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, const int32_t *indptr,
+                      const int32_t *indices, const double *data, const int32_t *t_indptr,
+                      const int32_t *t_indices, const double *t_data, const double *rhs,
+                      const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm, void *stream);
+int lss_solver_destroy(lss_solver_t *solver);
+/* Row weights w (length n_rows): 1/sigma^2 for selected data rows, 0 for edited rows, 1/E_c^2 for
+ * constraint rows.  Recomputes the right-hand side A^T W b and the Jacobi diagonal. */
+int lss_solver_set_weights(lss_solver_t *solver, const double *w);
+/* Solve from the initial guess in x (length n_cols).  Stops when sqrt(r^T M^-1 r / b^T M^-1 b) <= rtol
+ * or after max_iter iterations.  iters_h / relres_h: host outputs. */
+int lss_solver_solve(lss_solver_t *solver, double *x, double rtol, int32_t max_iter, int32_t *iters_h,
+                     double *relres_h);
+/* Record CUDA-event pairs around every A and A^T product of the following solves (small overhead). */
+int lss_solver_set_profile(lss_solver_t *solver, int32_t on);
+/* Statistics of the last solve, timed with CUDA events on the solver's stream:
+ * stats_h[0] = total ms, [1] = ms in y = w.*(A p) products, [2] = ms in A^T u products (both 0 unless
+ * profiling is on), [3] = number of operator applications, [4] = kernels launched, [5] = nnz(A). */
+int lss_solver_stats(lss_solver_t *solver, double *stats_h);
+
+/* ------------------------------------------------------------------ robust statistics / editing */
+
+/* RDE(r / sqrt(s1^2 + sigma^2)) over points with mask != 0 and a finite value (RDE.py:10-18 inside
+ * calc_sigma_extra.py:36-39): exact selection of the four order statistics np.interp touches, then
+ * the same interpolation arithmetic.  sigma == NULL => RDE(r).  mask == NULL => all points.
+ * n_used_h receives the (global) number of points used; the result is NaN when it is < 2. */
+int lss_rde(const double *r, const double *sigma, const uint8_t *mask, double s1, int64_t n, lss_comm_t *comm,
+            double *rde_h, int64_t *n_used_h, void *stream);
+
+/* calc_sigma_extra for one mask group (calc_sigma_extra.py:34-41): bounded Brent minimisation of
+ * (RDE(r/sqrt(s^2+sigma^2)) - 1)^2 on [0, RDE(r)] with scipy's constants (xatol 1e-5, 500 calls).
+ * Returns 0 in *sigma_extra_h when fewer than 10 points are selected. */
+int lss_sigma_extra(const double *r, const double *sigma, const uint8_t *mask, int64_t n, lss_comm_t *comm,
+                    double *sigma_extra_h, int32_t *nfev_h, void *stream);
+
+/* in_TSE = |r / sqrt(sigma^2 + sigma_extra^2)| < n_sigma (smooth_fit.py:159-163) plus the statistics
+ * the convergence tests need: stats_h[0] = count(in_TSE), stats_h[1] = min sigma over in_TSE
+ * (smooth_fit.py:203), stats_h[2] = number of points with ||r/sigma_aug| - n_sigma| < 1e-6. */
+int lss_edit_mask(const double *r, const double *sigma, const double *sigma_extra, int64_t n, double n_sigma,
+                  uint8_t *in_TSE, double *stats_h, lss_comm_t *comm, void *stream);
+
+/* w[i] = mask[i] ? 1 / (sigma[i]^2 (+ sigma_extra[i]^2)) : 0   (smooth_fit.py:123-135). */
+int lss_data_weights(const double *sigma, const double *sigma_extra, const uint8_t *mask, int64_t n, double *w,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSSURF_B200_H */

@@ -1,0 +1,253 @@
+"""ctypes binding of liblssurf_b200.so (the C ABI declared in include/lssurf_b200.h).
+
+PyTorch is used only as the owner of device memory and streams: every call below takes raw device
+pointers (``tensor.data_ptr()``) and the current CUDA stream.  There is no CPU fallback: if the
+shared library is missing, or no CUDA device is visible, the compute entry points raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liblssurf_b200.so')
+_lib = None
+
+LSS_MAX_DIMS = 3
+SPMV_PLAIN, SPMV_SCALE, SPMV_RESIDUAL = 0, 1, 2
+
+
+class LssError(RuntimeError):
+    pass
+
+
+class lss_grid_t(C.Structure):
+    _fields_ = [('ndim', C.c_int32), ('shape', C.c_int64 * 3), ('stride', C.c_int64 * 3), ('lo', C.c_double * 3),
+                ('hi', C.c_double * 3), ('delta', C.c_double * 3), ('col_0', C.c_int64)]
+
+
+_vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+_pi64, _pi32, _pf64 = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)
+
+# name -> argtypes; every function returns int except where noted.  This table is also what the CPU
+# test suite checks against the header (tests/test_cabi_symbols.py).
+SIGNATURES = {
+    'lss_version': [],
+    'lss_device_count': [],
+    'lss_interp_coo': [C.POINTER(lss_grid_t), C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp, _pi64, _vp],
+    'lss_stencil_count': [C.POINTER(lss_grid_t), _i32, _pi32, _i32, _pi64, _pi64, _pi64],
+    'lss_stencil_coo': [C.POINTER(lss_grid_t), _i32, _pi32, _pf64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
+    'lss_coo_extent': [_i64, _vp, _vp, _pi64, _pi64, _vp],
+    'lss_coo_to_csr': [_i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _pi64, _vp],
+    'lss_csr_transpose': [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    'lss_argsort_u64': [_i64, _vp, _i32, _vp, _vp],
+    'lss_spmv': [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    'lss_comm_unique_id': [C.c_char_p],
+    'lss_comm_create': [C.POINTER(_vp), C.c_char_p, _i32, _i32],
+    'lss_comm_destroy': [_vp],
+    'lss_comm_allreduce_f64': [_vp, _vp, _i64, _vp],
+    'lss_solver_create': [C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    'lss_solver_destroy': [_vp],
+    'lss_solver_set_weights': [_vp, _vp],
+    'lss_solver_solve': [_vp, _vp, _f64, _i32, _pi32, _pf64],
+    'lss_solver_set_profile': [_vp, _i32],
+    'lss_solver_stats': [_vp, _pf64],
+    'lss_rde': [_vp, _vp, _vp, _f64, _i64, _vp, _pf64, _pi64, _vp],
+    'lss_sigma_extra': [_vp, _vp, _vp, _i64, _vp, _pf64, _pi32, _vp],
+    'lss_edit_mask': [_vp, _vp, _vp, _i64, _f64, _vp, _pf64, _vp, _vp],
+    'lss_data_weights': [_vp, _vp, _vp, _i64, _vp, _vp],
+}
+
+
+def load():
+    """Load the shared library (no CUDA call is made).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LssError(f'{LIB_PATH} not found: build it with `python -m lssurf_b200.csrc.build` '
+                       '(there is no CPU fallback)')
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.lss_last_error.argtypes = []
+    lib.lss_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def lib():
+    """The library, after checking that a CUDA device is usable.  No silent CPU path."""
+    L = load()
+    if not torch.cuda.is_available() or L.lss_device_count() < 1:
+        raise LssError('lssurf_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists')
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().lss_last_error().decode(errors='replace')
+        raise LssError(f'lssurf_b200 error {rc}: {msg}')
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), 'expected a contiguous CUDA tensor'
+    return C.c_void_p(t.data_ptr())
+
+
+def device():
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def to_dev(a, dtype=None):
+    """numpy / tensor -> contiguous CUDA tensor (tensor plumbing only)."""
+    if isinstance(a, torch.Tensor):
+        t = a.to(device())
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device())
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def grid_struct(shape, stride, lo, hi, delta, col_0):
+    g = lss_grid_t()
+    nd = len(shape)
+    g.ndim = nd
+    for d in range(3):
+        g.shape[d] = int(shape[d]) if d < nd else 1
+        g.stride[d] = int(stride[d]) if d < nd else 0
+        g.lo[d] = float(lo[d]) if d < nd else 0.0
+        g.hi[d] = float(hi[d]) if d < nd else 0.0
+        g.delta[d] = float(delta[d]) if d < nd else 1.0
+    g.col_0 = int(col_0)
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+# thin functional wrappers (device tensors in, device tensors out)
+# ---------------------------------------------------------------------------------------------
+
+def interp_coo(g, pts, row_0=0):
+    """-> rows[int32 n,2^d], cols[int32 n,2^d], vals[f64 n,2^d], valid[uint8 n], n_invalid"""
+    L = lib()
+    nd = g.ndim
+    n = int(pts[0].numel())
+    nc = 1 << nd
+    dev = device()
+    rows = torch.empty((n, nc), dtype=torch.int32, device=dev)
+    cols = torch.empty((n, nc), dtype=torch.int32, device=dev)
+    vals = torch.empty((n, nc), dtype=torch.float64, device=dev)
+    valid = torch.empty(n, dtype=torch.uint8, device=dev)
+    parr = (C.c_void_p * nd)(*[p.data_ptr() for p in pts[:nd]])
+    bad = C.c_int64(0)
+    check(L.lss_interp_coo(C.byref(g), parr, n, row_0, ptr(rows), ptr(cols), ptr(vals), ptr(valid), C.byref(bad), stream()))
+    return rows, cols, vals, valid, bad.value
+
+
+def stencil_coo(g, offsets, coeffs, row_0=0, valid_only=True):
+    L = lib()
+    offs = np.ascontiguousarray(np.asarray(offsets, dtype=np.int32).reshape(g.ndim, -1))
+    n_off = offs.shape[1]
+    coef = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float64).ravel())
+    if coef.size != n_off:
+        raise ValueError('one coefficient per offset is required')
+    n_eq = C.c_int64(0)
+    check(L.lss_stencil_count(C.byref(g), n_off, offs.ctypes.data_as(_pi32), int(valid_only), C.byref(n_eq), None, None))
+    n_eq = n_eq.value
+    dev = device()
+    rows = torch.empty((n_eq, n_off), dtype=torch.int32, device=dev)
+    cols = torch.empty((n_eq, n_off), dtype=torch.int32, device=dev)
+    vals = torch.empty((n_eq, n_off), dtype=torch.float64, device=dev)
+    ind0 = torch.empty(n_eq, dtype=torch.int64, device=dev)
+    check(L.lss_stencil_coo(C.byref(g), n_off, offs.ctypes.data_as(_pi32), coef.ctypes.data_as(_pf64), row_0,
+                            int(valid_only), n_eq, ptr(rows), ptr(cols), ptr(vals), ptr(ind0), stream()))
+    return rows, cols, vals, ind0
+
+
+def coo_extent(rows, vals):
+    L = lib()
+    mx, cnt = C.c_int64(-1), C.c_int64(0)
+    check(L.lss_coo_extent(int(vals.numel()), ptr(rows), ptr(vals), C.byref(mx), C.byref(cnt), stream()))
+    return mx.value, cnt.value
+
+
+def coo_to_csr(rows, cols, vals, n_rows, n_cols):
+    """Canonical CSR (device tensors indptr[int32], indices[int32], data[f64])."""
+    L = lib()
+    nnz = int(vals.numel())
+    dev = device()
+    indptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    data = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)
+    out = C.c_int64(0)
+    check(L.lss_coo_to_csr(nnz, ptr(rows), ptr(cols), ptr(vals), n_rows, n_cols, ptr(indptr), ptr(indices), ptr(data),
+                           C.byref(out), stream()))
+    k = out.value
+    return indptr, indices[:k].clone() if k < nnz else indices[:k], data[:k].clone() if k < nnz else data[:k]
+
+
+def csr_transpose(indptr, indices, data, n_rows, n_cols):
+    L = lib()
+    nnz = int(data.numel())
+    dev = device()
+    t_indptr = torch.empty(n_cols + 1, dtype=torch.int32, device=dev)
+    t_indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    t_data = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)
+    check(L.lss_csr_transpose(n_rows, n_cols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(t_indptr), ptr(t_indices),
+                              ptr(t_data), stream()))
+    return t_indptr, t_indices[:nnz], t_data[:nnz]
+
+
+def argsort_u64(keys, key_bits):
+    L = lib()
+    n = int(keys.numel())
+    order = torch.empty(n, dtype=torch.int32, device=device())
+    check(L.lss_argsort_u64(n, ptr(keys), int(key_bits), ptr(order), stream()))
+    return order
+
+
+def spmv(indptr, indices, data, x, n_rows, n_cols, mode=SPMV_PLAIN, s=None, out=None):
+    L = lib()
+    y = out if out is not None else torch.empty(n_rows, dtype=torch.float64, device=device())
+    check(L.lss_spmv(n_rows, n_cols, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), mode, ptr(s), stream()))
+    return y
+
+
+def rde(r, sigma=None, mask=None, s1=0.0, comm=None):
+    L = lib()
+    out, n_used = C.c_double(0.0), C.c_int64(0)
+    check(L.lss_rde(ptr(r), ptr(sigma), ptr(mask), float(s1), int(r.numel()), comm, C.byref(out), C.byref(n_used), stream()))
+    return out.value, n_used.value
+
+
+def sigma_extra(r, sigma, mask, comm=None):
+    L = lib()
+    out, nfev = C.c_double(0.0), C.c_int32(0)
+    check(L.lss_sigma_extra(ptr(r), ptr(sigma), ptr(mask), int(r.numel()), comm, C.byref(out), C.byref(nfev), stream()))
+    return out.value, nfev.value
+
+
+def edit_mask(r, sigma, sigma_extra_t, n_sigma=3.0, comm=None, out=None):
+    L = lib()
+    n = int(r.numel())
+    m = out if out is not None else torch.empty(n, dtype=torch.uint8, device=device())
+    stats = (C.c_double * 3)()
+    check(L.lss_edit_mask(ptr(r), ptr(sigma), ptr(sigma_extra_t), n, float(n_sigma), ptr(m), stats, comm, stream()))
+    return m, dict(count=int(stats[0]), min_sigma=float(stats[1]), near_threshold=int(stats[2]))
+
+
+def data_weights(sigma, sigma_extra_t, mask, out):
+    L = lib()
+    check(L.lss_data_weights(ptr(sigma), ptr(sigma_extra_t), ptr(mask), int(sigma.numel()), ptr(out), stream()))
+    return out

@@ -1,0 +1,105 @@
+// Shared helpers for the lssurf_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/lssurf_b200.h"
+
+namespace lss {
+
+extern thread_local char g_err[512];
+int fail(int code, const char *fmt, ...);
+
+#define LSS_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return lss::fail(LSS_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define LSS_TRY(call)                 \
+    do {                              \
+        int rc__ = (call);            \
+        if (rc__ != LSS_OK) return rc__; \
+    } while (0)
+
+#define LSS_LAUNCH_CHECK() LSS_CUDA(cudaGetLastError())
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids of grid-stride kernels are multiples of this
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Grid for a grid-stride kernel: enough CTAs to cover n once, capped at `waves` CTAs per SM.
+static inline int stride_grid(int64_t n, int block, int per_sm = 8) {
+    int64_t need = (n + block - 1) / block;
+    int64_t cap = (int64_t)kSMs * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// Stream-ordered scratch allocation (cudaMallocAsync pool); freed in stream order by the destructor.
+struct Scratch {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        s = stream;
+        if (bytes == 0) bytes = 16;
+        return cudaMallocAsync(&p, bytes, stream);
+    }
+    template <typename T>
+    T *as() { return reinterpret_cast<T *>(p); }
+    ~Scratch() {
+        if (p) cudaFreeAsync(p, s);
+    }
+};
+
+// ---- device-side helpers ------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Streaming (read-once) loads that do not allocate in L1: keeps L1 for the gathered vector.
+__device__ __forceinline__ double ldg_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_stream(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Exclusive prefix sum of uint32 (device, any n).  `total` (device, optional) receives the sum.
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total, cudaStream_t stream);
+
+// Stable LSD radix sort of (key, payload) pairs on key bits [bit_lo, bit_lo + n_bits).
+// keys_a/vals_a hold the input and are clobbered; the result lands in *keys_out/*vals_out, which
+// point to either the a or the b buffers.  With iota_first the input payload is not read: the first
+// pass writes the element's input position instead.
+int radix_sort_pairs(uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint32_t *vals_b, int64_t n, int bit_lo,
+                     int n_bits, int iota_first, uint64_t **keys_out, uint32_t **vals_out, cudaStream_t stream);
+
+// y = A x family (spmv.cu), rows [0, n_rows).
+int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data,
+                const double *x, double *y, int mode, const double *s, int64_t nnz, const double *stop,
+                cudaStream_t stream, int64_t *launches);
+
+}  // namespace lss
+
+// NCCL communicator wrapper (comm.cu)
+struct lss_comm {
+    void *nccl;  // ncclComm_t
+    int rank, n_ranks;
+};
+namespace lss {
+int comm_allreduce(lss_comm *c, void *buf, int64_t n, int dtype /*0 f64, 1 i64, 2 u64*/, int op /*0 sum,1 min,2 max*/,
+                   cudaStream_t stream);
+}

@@ -1,0 +1,432 @@
+// Matrix-free fp64 preconditioned conjugate gradients on the normal equations.
+//
+// Replaces `sparseqr.solve(Ip_r.dot(TCinv.dot(Gcoo)), Ip_r.dot(TCinv.dot(rhs)))`
+// (LSsurf/smooth_fit.py:123-142).  The row selection Ip_r and the 1/sigma scaling TCinv are never
+// materialised: they are the per-row weight vector w (0 for edited rows).  The column selection
+// Ip_c (reference epoch, constraint_functions.py:128-151) is a zero in the preconditioner, which
+// keeps those unknowns at exactly 0.
+//
+// One CG iteration =  u = w .* (A p)      CSR product, streams A once        (spmv.cu)
+//                     q = A^T u           CSR product, streams A^T once      (spmv.cu)
+//                     [q | p.q partials]  one NCCL all-reduce when row-sharded over GPUs
+//                     x, r, z, p updates  two fused vector kernels
+// All scalars (alpha, beta, r.z) stay on the device; the host only polls a convergence flag once
+// per batch of iterations, one batch ahead of the GPU, so the queue never drains.
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace lss {
+
+constexpr int VEC_BLOCK = 256;
+constexpr int VEC_GRID = 2 * kSMs;  // fixed: the per-block partial sums have a fixed length
+
+// slots of the device scalar block
+// S_RZ0/1 and S_DONE0/1 are double-buffered by iteration parity: kernels of iteration k read slot k&1 and only
+// block 0 of the last kernel of the iteration writes slot (k+1)&1, so no block can observe a value written
+// by a sibling block of the same launch.
+enum { S_RZ0 = 0, S_RZ1 = 1, S_BNORM = 2, S_TOL2 = 3, S_DONE0 = 4, S_DONE1 = 5, S_ITERS = 6, S_MAXIT = 7, S_RZ_LAST = 8, S_COUNT = 10 };
+
+__device__ __forceinline__ double block_sum(double v, double *sm /*[VEC_BLOCK/32]*/) {
+    v = warp_sum(v);
+    if (lane_id() == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < VEC_BLOCK / 32 ? sm[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+    }
+    __syncthreads();
+    return t;  // valid in warp 0
+}
+
+// Sum of the P per-block partials in a fixed order, identical in every block (deterministic).
+__device__ __forceinline__ double sum_partials(const double *__restrict__ part, int n_part, double *sm) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n_part; i += VEC_BLOCK) v += part[i];
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) sm[0] = v;
+    __syncthreads();
+    v = sm[0];
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(VEC_BLOCK)
+dot_partials_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ part,
+                    const double *__restrict__ stop) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    if (stop && *stop != 0.0) return;
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) v += a[i] * b[i];
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+// minv = free ? 1/diag : 0   and partial sums of g^T minv g
+__global__ void __launch_bounds__(VEC_BLOCK)
+jacobi_kernel(int64_t n, const double *__restrict__ diag, const unsigned char *__restrict__ fixed, const double *__restrict__ g,
+              double *__restrict__ minv, double *__restrict__ part) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) {
+        const double d = diag[i];
+        const double m = (!fixed[i] && d > 0.0) ? 1.0 / d : 0.0;
+        minv[i] = m;
+        v += g[i] * m * g[i];
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+// r = g - q (or r = g when q == nullptr); z = minv r; p = z; partials of r.z; x zeroed at fixed columns
+__global__ void __launch_bounds__(VEC_BLOCK)
+cg_init_kernel(int64_t n, const double *__restrict__ g, const double *__restrict__ q, const double *__restrict__ minv,
+               const unsigned char *__restrict__ fixed, double *__restrict__ x, double *__restrict__ r, double *__restrict__ p,
+               double *__restrict__ part) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) {
+        const double ri = q ? g[i] - q[i] : g[i];
+        const double zi = minv[i] * ri;
+        r[i] = ri;
+        p[i] = zi;
+        if (fixed[i]) x[i] = 0.0;
+        v += ri * zi;
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+// Folds the partial sums of a setup reduction into the scalar block (single block).
+__global__ void __launch_bounds__(VEC_BLOCK)
+cg_scalar_kernel(const double *__restrict__ part, int n_part, double *__restrict__ scal, int slot, double rtol, int max_iter) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    const double v = sum_partials(part, n_part, sm);
+    if (threadIdx.x == 0) {
+        scal[slot] = v;
+        if (slot == S_BNORM) scal[S_TOL2] = 0.0;
+        if (slot == S_RZ0) {  // start of a solve
+            scal[S_TOL2] = rtol * rtol * scal[S_BNORM];
+            scal[S_ITERS] = 0.0;
+            scal[S_MAXIT] = (double)max_iter;
+            scal[S_RZ_LAST] = v;
+            scal[S_DONE0] = scal[S_DONE1] = (v <= scal[S_TOL2] || max_iter <= 0 || !(v == v)) ? 1.0 : 0.0;
+        }
+    }
+}
+
+// alpha = rz / p.q;  x += alpha p;  r -= alpha q;  partials of r . (minv r)
+__global__ void __launch_bounds__(VEC_BLOCK)
+cg_update_kernel(int64_t n, const double *__restrict__ q, const double *__restrict__ pq_part, int n_part, const double *__restrict__ minv,
+                 const double *__restrict__ p, double *__restrict__ x, double *__restrict__ r, double *__restrict__ rz_part,
+                 const double *__restrict__ scal, int parity) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    if (scal[S_DONE0 + parity] != 0.0) return;
+    const double pq = sum_partials(pq_part, n_part, sm);
+    const double rz = scal[S_RZ0 + parity];
+    const double alpha = pq > 0.0 ? rz / pq : 0.0;
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) {
+        const double pi = p[i];
+        x[i] += alpha * pi;
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        v += ri * (minv[i] * ri);
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) rz_part[blockIdx.x] = v;
+}
+
+// beta = rz_new / rz_old;  p = minv r + beta p;  block 0 publishes rz_new, the iteration count and the stop flag
+__global__ void __launch_bounds__(VEC_BLOCK)
+cg_direction_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ minv, double *__restrict__ p,
+                    const double *__restrict__ rz_part, int n_part, double *__restrict__ scal, int parity) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    if (scal[S_DONE0 + parity] != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;   // stay stopped
+        return;
+    }
+    const double rz_new = sum_partials(rz_part, n_part, sm);
+    const double rz_old = scal[S_RZ0 + parity];
+    const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK)
+        p[i] = minv[i] * r[i] + beta * p[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[S_RZ0 + (parity ^ 1)] = rz_new;   // read by the NEXT iteration; this one reads slot `parity`
+        scal[S_RZ_LAST] = rz_new;
+        const double it = scal[S_ITERS] + 1.0;
+        scal[S_ITERS] = it;
+        scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(VEC_BLOCK)
+mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) out[i] = a[i] * b[i];
+}
+
+__global__ void __launch_bounds__(VEC_BLOCK)
+mark_fixed_kernel(int64_t n_fixed, const int *__restrict__ cols, unsigned char *__restrict__ fixed) {
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n_fixed; i += (int64_t)gridDim.x * VEC_BLOCK) fixed[cols[i]] = 1;
+}
+
+__global__ void __launch_bounds__(VEC_BLOCK)
+zero_fixed_kernel(int64_t n, const unsigned char *__restrict__ fixed, double *__restrict__ x) {
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK)
+        if (fixed[i]) x[i] = 0.0;
+}
+
+// diag_j = sum_k At.data[k]^2 * w[At.indices[k]] : one warp per row of A^T (a one-off per outer iteration)
+__global__ void __launch_bounds__(256)
+diag_kernel(int64_t n_cols, const int *__restrict__ t_indptr, const int *__restrict__ t_indices, const double *__restrict__ t_data,
+            const double *__restrict__ w, double *__restrict__ diag) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < n_cols; c += n_warps) {
+        const int b = t_indptr[c], e = t_indptr[c + 1];
+        double acc = 0.0;
+        for (int k = b + (int)lane_id(); k < e; k += 32) {
+            const double a = t_data[k];
+            acc += a * a * w[t_indices[k]];
+        }
+        acc = warp_sum(acc);
+        if (lane_id() == 0) diag[c] = acc;
+    }
+}
+
+}  // namespace lss
+
+using namespace lss;
+
+struct lss_solver {
+    int64_t n_rows, n_cols, nnz;
+    const int32_t *indptr, *indices, *t_indptr, *t_indices;
+    const double *data, *t_data, *rhs;
+    lss_comm_t *comm;
+    cudaStream_t stream;
+    // owned device memory
+    double *w, *u, *buf /* q[n_cols] | partials[VEC_GRID] */, *r, *p, *minv, *g, *diag, *part2, *scal;
+    unsigned char *fixed;
+    double *host_scal;  // pinned
+    cudaEvent_t ev0, ev1, ev_batch[2];
+    bool have_weights;
+    bool profile;
+    // stats of the last solve
+    double ms_total, ms_a, ms_at;
+    int64_t n_apply;
+    int64_t launches;
+    std::vector<cudaEvent_t> *prof_events;
+};
+
+static int dev_alloc(double **p, int64_t n) {
+    LSS_CUDA(cudaMalloc((void **)p, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_destroy(lss_solver_t *s) {
+    if (!s) return LSS_OK;
+    cudaStreamSynchronize(s->stream);
+    double **ptrs[] = {&s->w, &s->u, &s->buf, &s->r, &s->p, &s->minv, &s->g, &s->diag, &s->part2, &s->scal};
+    for (auto pp : ptrs)
+        if (*pp) cudaFree(*pp);
+    if (s->fixed) cudaFree(s->fixed);
+    if (s->host_scal) cudaFreeHost(s->host_scal);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (int i = 0; i < 2; ++i)
+        if (s->ev_batch[i]) cudaEventDestroy(s->ev_batch[i]);
+    if (s->prof_events) {
+        for (auto e : *s->prof_events) cudaEventDestroy(e);
+        delete s->prof_events;
+    }
+    delete s;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, const int32_t *indptr,
+                                 const int32_t *indices, const double *data, const int32_t *t_indptr,
+                                 const int32_t *t_indices, const double *t_data, const double *rhs,
+                                 const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm, void *stream) {
+    if (!solver || n_rows < 0 || n_cols <= 0) return fail(LSS_EINVAL, "solver_create: bad sizes");
+    lss_solver *s = new lss_solver();
+    memset(s, 0, sizeof(*s));
+    s->n_rows = n_rows; s->n_cols = n_cols;
+    s->indptr = indptr; s->indices = indices; s->data = data;
+    s->t_indptr = t_indptr; s->t_indices = t_indices; s->t_data = t_data;
+    s->rhs = rhs; s->comm = comm; s->stream = (cudaStream_t)stream;
+    s->prof_events = new std::vector<cudaEvent_t>();
+    int rc = LSS_OK;
+    auto chk = [&](int r) { if (rc == LSS_OK) rc = r; };
+    int nnz = 0;
+    if (n_rows > 0) {
+        if (cudaMemcpyAsync(&nnz, indptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+            cudaStreamSynchronize(s->stream) != cudaSuccess)
+            rc = fail(LSS_ECUDA, "solver_create: cannot read indptr: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    s->nnz = nnz;
+    chk(dev_alloc(&s->w, n_rows)); chk(dev_alloc(&s->u, n_rows));
+    chk(dev_alloc(&s->buf, n_cols + VEC_GRID)); chk(dev_alloc(&s->r, n_cols)); chk(dev_alloc(&s->p, n_cols));
+    chk(dev_alloc(&s->minv, n_cols)); chk(dev_alloc(&s->g, n_cols)); chk(dev_alloc(&s->diag, n_cols + VEC_GRID));
+    chk(dev_alloc(&s->part2, VEC_GRID)); chk(dev_alloc(&s->scal, S_COUNT));
+    if (rc == LSS_OK && cudaMalloc((void **)&s->fixed, (size_t)n_cols) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMalloc failed");
+    if (rc == LSS_OK && cudaMallocHost((void **)&s->host_scal, sizeof(double) * S_COUNT * 2) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMallocHost failed");
+    if (rc == LSS_OK) {
+        cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
+        cudaEventCreateWithFlags(&s->ev_batch[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->ev_batch[1], cudaEventDisableTiming);
+        cudaMemsetAsync(s->fixed, 0, (size_t)n_cols, s->stream);
+        cudaMemsetAsync(s->scal, 0, sizeof(double) * S_COUNT, s->stream);
+        if (n_fixed > 0) mark_fixed_kernel<<<stride_grid(n_fixed, VEC_BLOCK), VEC_BLOCK, 0, s->stream>>>(n_fixed, fixed_cols, s->fixed);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: launch failed");
+    }
+    if (rc != LSS_OK) { lss_solver_destroy(s); return rc; }
+    s->profile = getenv("LSS_PROFILE_SPMV") != nullptr;
+    *solver = s;
+    return LSS_OK;
+}
+
+// q(buf[0:n]) = A^T (w .* (A v)), partials of v.q appended at buf[n:], summed over ranks.
+static int apply_normal(lss_solver *s, const double *v, bool with_dot, const double *stop) {
+    cudaStream_t st = s->stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (s->profile) {
+        for (cudaEvent_t *e : {&e0, &e1, &e2}) {
+            LSS_CUDA(cudaEventCreate(e));
+            s->prof_events->push_back(*e);
+        }
+        LSS_CUDA(cudaEventRecord(e0, st));
+    }
+    LSS_TRY(spmv_launch(s->n_rows, s->indptr, s->indices, s->data, v, s->u, LSS_SPMV_SCALE, s->w, s->nnz, stop, st, &s->launches));
+    if (s->profile) LSS_CUDA(cudaEventRecord(e1, st));
+    LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->buf, LSS_SPMV_PLAIN, nullptr, s->nnz, stop, st, &s->launches));
+    if (s->profile) LSS_CUDA(cudaEventRecord(e2, st));
+    int64_t n_red = s->n_cols;
+    if (with_dot) {
+        dot_partials_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(s->n_cols, v, s->buf, s->buf + s->n_cols, stop);
+        LSS_LAUNCH_CHECK();
+        s->launches += 1;
+        n_red += VEC_GRID;
+    }
+    LSS_TRY(comm_allreduce(s->comm, s->buf, n_red, 0, 0, st));
+    s->n_apply += 1;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
+    if (!s || !w) return fail(LSS_EINVAL, "solver_set_weights: null argument");
+    cudaStream_t st = s->stream;
+    if (s->n_rows > 0) LSS_CUDA(cudaMemcpyAsync(s->w, w, sizeof(double) * s->n_rows, cudaMemcpyDeviceToDevice, st));
+    // g = A^T (w .* b)
+    if (s->n_rows > 0) {
+        mul_kernel<<<stride_grid(s->n_rows, VEC_BLOCK), VEC_BLOCK, 0, st>>>(s->n_rows, s->w, s->rhs, s->u);
+        LSS_LAUNCH_CHECK();
+    }
+    LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->g, LSS_SPMV_PLAIN, nullptr, s->nnz, nullptr, st, nullptr));
+    LSS_TRY(comm_allreduce(s->comm, s->g, s->n_cols, 0, 0, st));
+    // Jacobi preconditioner from diag(A^T W A)
+    diag_kernel<<<stride_grid(s->n_cols * 32, 256, 16), 256, 0, st>>>(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->w, s->diag);
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(comm_allreduce(s->comm, s->diag, s->n_cols, 0, 0, st));
+    jacobi_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(s->n_cols, s->diag, s->fixed, s->g, s->minv, s->part2);
+    LSS_LAUNCH_CHECK();
+    cg_scalar_kernel<<<1, VEC_BLOCK, 0, st>>>(s->part2, VEC_GRID, s->scal, S_BNORM, 0.0, 0);
+    LSS_LAUNCH_CHECK();
+    s->have_weights = true;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t max_iter, int32_t *iters_h, double *relres_h) {
+    if (!s || !x) return fail(LSS_EINVAL, "solver_solve: null argument");
+    if (!s->have_weights) return fail(LSS_EINVAL, "solver_solve: call lss_solver_set_weights first");
+    cudaStream_t st = s->stream;
+    const int64_t n = s->n_cols;
+    s->launches = 0;
+    s->n_apply = 0;
+    for (auto e : *s->prof_events) cudaEventDestroy(e);
+    s->prof_events->clear();
+    LSS_CUDA(cudaEventRecord(s->ev0, st));
+    // r = g - N x0
+    zero_fixed_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->fixed, x);
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(apply_normal(s, x, false, nullptr));
+    cg_init_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->g, s->buf, s->minv, s->fixed, x, s->r, s->p, s->part2);
+    LSS_LAUNCH_CHECK();
+    cg_scalar_kernel<<<1, VEC_BLOCK, 0, st>>>(s->part2, VEC_GRID, s->scal, S_RZ0, rtol, max_iter);
+    LSS_LAUNCH_CHECK();
+    s->launches += 3;
+    const int batch = 16;
+    int issued = 0, parity = 0, slot = 0;
+    bool done = false;
+    bool pending[2] = {false, false};
+    while (!done) {
+        // enqueue one batch, then look at the flag the PREVIOUS batch left behind
+        const int todo = (max_iter - issued) < batch ? (max_iter - issued) : batch;
+        for (int k = 0; k < todo; ++k) {
+            LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity));
+            cg_update_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->buf, s->buf + n, VEC_GRID, s->minv, s->p, x, s->r, s->part2, s->scal, parity);
+            LSS_LAUNCH_CHECK();
+            cg_direction_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->r, s->minv, s->p, s->part2, VEC_GRID, s->scal, parity);
+            LSS_LAUNCH_CHECK();
+            s->launches += 2;
+            parity ^= 1;
+        }
+        issued += todo;
+        LSS_CUDA(cudaMemcpyAsync(s->host_scal + slot * S_COUNT, s->scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaEventRecord(s->ev_batch[slot], st));
+        pending[slot] = true;
+        const int prev = slot ^ 1;
+        if (pending[prev]) {
+            LSS_CUDA(cudaEventSynchronize(s->ev_batch[prev]));
+            pending[prev] = false;
+            if (s->host_scal[prev * S_COUNT + S_DONE0] != 0.0 || s->host_scal[prev * S_COUNT + S_DONE1] != 0.0) done = true;
+        }
+        if (!done && (issued >= max_iter || todo == 0)) {
+            LSS_CUDA(cudaEventSynchronize(s->ev_batch[slot]));
+            pending[slot] = false;
+            done = true;
+        }
+        slot ^= 1;
+    }
+    LSS_CUDA(cudaMemcpyAsync(s->host_scal, s->scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
+    LSS_CUDA(cudaEventRecord(s->ev1, st));
+    LSS_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    s->ms_total = ms;
+    s->ms_a = s->ms_at = 0.0;
+    if (s->profile) {
+        const std::vector<cudaEvent_t> &ev = *s->prof_events;
+        for (size_t i = 0; i + 3 <= ev.size(); i += 3) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, ev[i], ev[i + 1]);
+            cudaEventElapsedTime(&b, ev[i + 1], ev[i + 2]);
+            s->ms_a += a;
+            s->ms_at += b;
+        }
+    }
+    const double bn = s->host_scal[S_BNORM], rzl = s->host_scal[S_RZ_LAST];
+    if (iters_h) *iters_h = (int32_t)s->host_scal[S_ITERS];
+    if (relres_h) *relres_h = bn > 0.0 ? sqrt(rzl / bn) : 0.0;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_set_profile(lss_solver_t *s, int32_t on) {
+    if (!s) return fail(LSS_EINVAL, "solver_set_profile: null solver");
+    s->profile = on != 0;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_stats(lss_solver_t *s, double *stats_h) {
+    if (!s || !stats_h) return fail(LSS_EINVAL, "solver_stats: null argument");
+    stats_h[0] = s->ms_total;
+    stats_h[1] = s->ms_a;
+    stats_h[2] = s->ms_at;
+    stats_h[3] = (double)s->n_apply;
+    stats_h[4] = (double)s->launches;
+    stats_h[5] = (double)s->nnz;
+    return LSS_OK;
+}

@@ -1,0 +1,434 @@
+// Device-wide exclusive scan, stable LSD radix sort, COO -> canonical CSR and CSR transpose.
+//
+// Replaces scipy's coo_tocsr + csr_sum_duplicates reached from lin_op.toCSR (LSsurf/lin_op.py:745-753)
+// and csr.T / tocsc used for G^T products (LSsurf/smooth_fit.py:142, 339-345).  All of it is
+// HBM-bound integer work: coalesced tile loads, warp-aggregated shared-memory histograms
+// (__match_any_sync), stable warp-level multi-split ranking, no global atomics on the data path.
+#include "common.cuh"
+
+namespace lss {
+
+// ============================================================================ exclusive scan
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total, uint32_t *smem /*[32]*/) {
+    // inclusive warp scan
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane_id() >= (unsigned)o) inc += t;
+    }
+    const int w = threadIdx.x >> 5;
+    if (lane_id() == 31) smem[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane_id() < (blockDim.x >> 5) ? smem[lane_id()] : 0;
+        uint32_t si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane_id() >= (unsigned)o) si += t;
+        }
+        smem[lane_id()] = si - s;  // exclusive warp offsets
+        if (lane_id() == 31) smem[32] = si;
+    }
+    __syncthreads();
+    uint32_t r = smem[w] + inc - v;
+    *total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+// pass 1: per-tile sums
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_reduce_kernel(const uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict__ sums) {
+    __shared__ uint32_t sm[33];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        int64_t i = base + k * SCAN_BLOCK + threadIdx.x;
+        if (i < n) acc += in[i];
+    }
+    uint32_t total;
+    block_exclusive_scan(acc, &total, sm);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// pass 3 (or only pass when one tile): scan inside the tile, add the tile offset
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_apply_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t n, const uint32_t *__restrict__ offsets,
+                  uint32_t *__restrict__ total_out) {
+    __shared__ uint32_t sm[33];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;  // blocked: thread owns 8 consecutive
+    uint32_t v[SCAN_ITEMS];
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        acc += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(acc, &total, sm) + (offsets ? offsets[blockIdx.x] : 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_BLOCK - 1) *total_out = ex;
+}
+
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total, cudaStream_t stream) {
+    if (n <= 0) {
+        if (total) LSS_CUDA(cudaMemsetAsync(total, 0, sizeof(uint32_t), stream));
+        return LSS_OK;
+    }
+    int tiles = ceil_div(n, SCAN_TILE);
+    if (tiles == 1) {
+        scan_apply_kernel<<<1, SCAN_BLOCK, 0, stream>>>(in, out, n, nullptr, total);
+        LSS_LAUNCH_CHECK();
+        return LSS_OK;
+    }
+    Scratch sums;
+    LSS_CUDA(sums.alloc(sizeof(uint32_t) * tiles, stream));
+    scan_reduce_kernel<<<tiles, SCAN_BLOCK, 0, stream>>>(in, n, sums.as<uint32_t>());
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(exclusive_scan_u32(sums.as<uint32_t>(), sums.as<uint32_t>(), tiles, nullptr, stream));
+    scan_apply_kernel<<<tiles, SCAN_BLOCK, 0, stream>>>(in, out, n, sums.as<uint32_t>(), total);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+// ============================================================================ radix sort
+constexpr int RS_BLOCK = 256;
+constexpr int RS_WARPS = RS_BLOCK / 32;
+constexpr int RS_ITEMS = 16;                     // keys per thread
+constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;     // 4096 keys per CTA
+constexpr int RS_BINS = 256;
+
+// Tile-local digit histogram -> counts[digit * n_tiles + tile].
+__global__ void __launch_bounds__(RS_BLOCK)
+rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t mask, uint32_t *__restrict__ counts, int n_tiles) {
+    __shared__ uint32_t h[RS_BINS];
+    for (int i = threadIdx.x; i < RS_BINS; i += RS_BLOCK) h[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        int64_t i = base + k * RS_BLOCK + threadIdx.x;
+        bool in = i < n;
+        uint32_t d = in ? (uint32_t)(keys[i] >> shift) & mask : 0xffffffffu;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (in && lane_id() == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RS_BINS; i += RS_BLOCK) counts[(int64_t)i * n_tiles + blockIdx.x] = h[i];
+}
+
+// Stable scatter.  Arrangement: warp w owns the contiguous chunk [w*512, (w+1)*512) of the tile and
+// reads it in 16 coalesced rounds of 32 keys, so tile order == (warp, round, lane) order.
+__global__ void __launch_bounds__(RS_BLOCK)
+rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t *__restrict__ keys_out,
+                  uint32_t *__restrict__ vals_out, int64_t n, int shift, uint32_t mask, const uint32_t *__restrict__ offsets,
+                  int n_tiles, int iota_vals) {
+    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];   // per-warp running digit counts -> exclusive warp offsets
+    __shared__ uint32_t gbase[RS_BINS];
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_BLOCK) (&cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < RS_BINS; i += RS_BLOCK) gbase[i] = offsets[(int64_t)i * n_tiles + blockIdx.x];
+    __syncthreads();
+    const int w = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (32 * RS_ITEMS);
+    uint64_t key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        int64_t i = base + k * 32 + lane_id();
+        bool in = i < n;
+        key[k] = in ? keys_in[i] : 0;
+        uint32_t d = in ? (uint32_t)(key[k] >> shift) & mask : 0xffffffffu;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (in && lane_id() == leader) {
+            old = cnt[w][d];
+            cnt[w][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[k] = old + __popc(peers & ((1u << lane_id()) - 1u));
+        __syncwarp();  // the next round's leader may be another lane: order the shared-memory counters
+    }
+    __syncthreads();
+    // exclusive scan over warps, per digit (256 threads == 256 digits)
+    {
+        uint32_t run = 0;
+        const int d = threadIdx.x;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            uint32_t c = cnt[ww][d];
+            cnt[ww][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        int64_t i = base + k * 32 + lane_id();
+        if (i < n) {
+            uint32_t d = (uint32_t)(key[k] >> shift) & mask;
+            uint32_t pos = gbase[d] + cnt[w][d] + rank[k];
+            keys_out[pos] = key[k];
+            vals_out[pos] = iota_vals ? (uint32_t)i : vals_in[i];
+        }
+    }
+}
+
+int radix_sort_pairs(uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint32_t *vals_b, int64_t n, int bit_lo,
+                     int n_bits, int iota_first, uint64_t **keys_out, uint32_t **vals_out, cudaStream_t stream) {
+    *keys_out = keys_a;
+    *vals_out = vals_a;
+    if (n <= 0 || n_bits <= 0) return LSS_OK;
+    if (n >= (1ll << 32)) return fail(LSS_ERANGE, "radix sort: more than 2^32 items");
+    const int n_tiles = ceil_div(n, RS_TILE);
+    Scratch counts;
+    LSS_CUDA(counts.alloc(sizeof(uint32_t) * (size_t)RS_BINS * n_tiles, stream));
+    const int passes = (n_bits + 7) / 8;
+    int done = 0;
+    uint64_t *ka = keys_a, *kb = keys_b;
+    uint32_t *va = vals_a, *vb = vals_b;
+    for (int p = 0; p < passes; ++p) {
+        int bits = (n_bits - done) / (passes - p);  // spread the bits evenly over the passes
+        if ((n_bits - done) % (passes - p)) ++bits;
+        const uint32_t mask = (1u << bits) - 1u;
+        rs_hist_kernel<<<n_tiles, RS_BLOCK, 0, stream>>>(ka, n, bit_lo + done, mask, counts.as<uint32_t>(), n_tiles);
+        LSS_LAUNCH_CHECK();
+        LSS_TRY(exclusive_scan_u32(counts.as<uint32_t>(), counts.as<uint32_t>(), (int64_t)RS_BINS * n_tiles, nullptr, stream));
+        rs_scatter_kernel<<<n_tiles, RS_BLOCK, 0, stream>>>(ka, va, kb, vb, n, bit_lo + done, mask, counts.as<uint32_t>(),
+                                                            n_tiles, iota_first && p == 0);
+        LSS_LAUNCH_CHECK();
+        done += bits;
+        uint64_t *tk = ka; ka = kb; kb = tk;
+        uint32_t *tv = va; va = vb; vb = tv;
+    }
+    *keys_out = ka;
+    *vals_out = va;
+    return LSS_OK;
+}
+
+// ============================================================================ COO -> CSR
+static int bits_for(int64_t max_value) {  // bits needed to represent values in [0, max_value]
+    int b = 1;
+    while (b < 63 && (max_value >> b)) ++b;
+    return b;
+}
+
+// key = row << 32 | col; entries with v == 0 get the sentinel row n_rows so they sort last.
+// stats[0] = number kept, stats[1] = max kept row, stats[2] = max kept col (as unsigned).
+__global__ void __launch_bounds__(256)
+coo_keys_kernel(int64_t nnz, const int *__restrict__ rows, const int *__restrict__ cols, const double *__restrict__ vals,
+                int64_t n_rows, uint64_t *__restrict__ keys, unsigned long long *__restrict__ stats) {
+    unsigned long long good = 0, mr = 0, mc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool keep = vals[i] != 0.0;   // NaN is kept, -0.0 dropped, as NumPy's v != 0 (lin_op.py:750)
+        const uint64_t r = keep ? (uint64_t)(uint32_t)rows[i] : (uint64_t)n_rows;
+        const uint64_t c = keep ? (uint64_t)(uint32_t)cols[i] : 0;
+        keys[i] = (r << 32) | c;
+        if (keep) {
+            ++good;
+            mr = r > mr ? r : mr;
+            mc = c > mc ? c : mc;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        good += __shfl_xor_sync(0xffffffffu, good, o);
+        unsigned long long a = __shfl_xor_sync(0xffffffffu, mr, o), b = __shfl_xor_sync(0xffffffffu, mc, o);
+        mr = a > mr ? a : mr;
+        mc = b > mc ? b : mc;
+    }
+    if (lane_id() == 0 && good) {
+        atomicAdd(stats, good);
+        atomicMax(stats + 1, mr);
+        atomicMax(stats + 2, mc);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+head_flags_kernel(const uint64_t *__restrict__ keys, int64_t n, uint32_t *__restrict__ flags) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// One thread per sorted entry; run heads sum their duplicates left to right (scipy csr_sum_duplicates
+// order after a stable sort) and write the CSR entry; row starts fill indptr for every row they open.
+__global__ void __launch_bounds__(256)
+csr_emit_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ idx, const double *__restrict__ vals,
+                int64_t n, const uint32_t *__restrict__ pos, int64_t n_rows, int *__restrict__ indptr,
+                int *__restrict__ indices, double *__restrict__ data, const uint32_t *__restrict__ n_out) {
+    const uint64_t cmask = 0xffffffffull;
+    const int col_bits = 32;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        const bool head = (i == 0) || (keys[i - 1] != k);
+        if (!head) continue;
+        double acc = vals[idx[i]];
+        int64_t j = i + 1;
+        for (; j < n && keys[j] == k; ++j) acc += vals[idx[j]];
+        const uint32_t p = pos[i];
+        indices[p] = (int)(k & cmask);
+        data[p] = acc;
+        const int64_t row = (int64_t)(k >> col_bits);
+        const int64_t prev_row = (i == 0) ? -1 : (int64_t)(keys[i - 1] >> col_bits);
+        for (int64_t r = prev_row + 1; r <= row; ++r) indptr[r] = (int)p;
+        if (j == n) {  // this run is the last one: close every remaining row
+            const int total = (int)(*n_out);
+            for (int64_t r = row + 1; r <= n_rows; ++r) indptr[r] = total;
+        }
+    }
+}
+
+__global__ void fill_i32_kernel(int *p, int64_t n, int v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ============================================================================ transpose
+__global__ void __launch_bounds__(256)
+csr_expand_keys_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__restrict__ indices,
+                       uint64_t *__restrict__ keys, uint32_t *__restrict__ src_row) {
+    // one warp per row: keys[k] = column of entry k, payload = source row
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        const int b = indptr[r], e = indptr[r + 1];
+        for (int k = b + (int)lane_id(); k < e; k += 32) {
+            keys[k] = (uint64_t)(uint32_t)indices[k];
+            src_row[k] = (uint32_t)r;
+        }
+    }
+}
+
+// After sorting entry ids by column: t_indices = source row, t_data = value, t_indptr from key changes.
+__global__ void __launch_bounds__(256)
+transpose_emit_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ ent, const uint32_t *__restrict__ src_row,
+                      const double *__restrict__ data, int64_t nnz, int64_t n_cols, int *__restrict__ t_indptr,
+                      int *__restrict__ t_indices, double *__restrict__ t_data) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t e = ent[i];
+        t_indices[i] = (int)src_row[e];
+        t_data[i] = data[e];
+        const int64_t c = (int64_t)keys[i];
+        const int64_t pc = (i == 0) ? -1 : (int64_t)keys[i - 1];
+        for (int64_t r = pc + 1; r <= c; ++r) t_indptr[r] = (int)i;
+        if (i == nnz - 1)
+            for (int64_t r = c + 1; r <= n_cols; ++r) t_indptr[r] = (int)nnz;
+    }
+}
+
+__global__ void __launch_bounds__(256) copy_order_kernel(const uint32_t *__restrict__ in, int *__restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int)in[i];
+}
+
+}  // namespace lss
+
+using namespace lss;
+
+extern "C" int lss_coo_to_csr(int64_t nnz, const int32_t *rows, const int32_t *cols, const double *vals, int64_t n_rows,
+                              int64_t n_cols, int32_t *indptr, int32_t *indices, double *data, int64_t *nnz_out_h,
+                              void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nnz < 0 || n_rows < 0 || n_cols < 0) return fail(LSS_EINVAL, "coo_to_csr: negative size");
+    if (nnz >= (1ll << 31) || n_rows >= (1ll << 31) - 1 || n_cols >= (1ll << 31)) return fail(LSS_ERANGE, "coo_to_csr: exceeds int32 index range");
+    if (nnz_out_h) *nnz_out_h = 0;
+    unsigned long long stats[3] = {0, 0, 0};
+    Scratch ka, kb, va, vb, cnt, flags;
+    if (nnz > 0) {
+        LSS_CUDA(ka.alloc(sizeof(uint64_t) * nnz, st));
+        LSS_CUDA(cnt.alloc(4 * sizeof(unsigned long long), st));
+        LSS_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(unsigned long long), st));
+        coo_keys_kernel<<<stride_grid(nnz, 256), 256, 0, st>>>(nnz, rows, cols, vals, n_rows, ka.as<uint64_t>(), cnt.as<unsigned long long>());
+        LSS_LAUNCH_CHECK();
+        LSS_CUDA(cudaMemcpyAsync(stats, cnt.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+    }
+    const int64_t n = (int64_t)stats[0];
+    if (n == 0) {
+        fill_i32_kernel<<<stride_grid(n_rows + 1, 256), 256, 0, st>>>(indptr, n_rows + 1, 0);
+        LSS_LAUNCH_CHECK();
+        LSS_CUDA(cudaStreamSynchronize(st));
+        return LSS_OK;
+    }
+    // scipy raises for indices outside the matrix (coo -> csr validation)
+    if ((int64_t)stats[1] >= n_rows) return fail(LSS_EINVAL, "coo_to_csr: row index %llu exceeds matrix dimension %lld", stats[1], (long long)n_rows);
+    if ((int64_t)stats[2] >= n_cols) return fail(LSS_EINVAL, "coo_to_csr: column index %llu exceeds matrix dimension %lld", stats[2], (long long)n_cols);
+    LSS_CUDA(kb.alloc(sizeof(uint64_t) * nnz, st));
+    LSS_CUDA(va.alloc(sizeof(uint32_t) * nnz, st));
+    LSS_CUDA(vb.alloc(sizeof(uint32_t) * nnz, st));
+    // LSD: column bits first (payload = original position, written by the first pass), then row bits
+    // (the sentinel row n_rows of dropped entries is included so they sort to the tail).
+    uint64_t *k1, *ks;
+    uint32_t *v1, *vs;
+    const int cbits = bits_for((int64_t)stats[2]);
+    const int rbits = bits_for(n_rows);
+    LSS_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), nnz, 0, cbits, 1, &k1, &v1, st));
+    uint64_t *k2 = (k1 == ka.as<uint64_t>()) ? kb.as<uint64_t>() : ka.as<uint64_t>();
+    uint32_t *v2 = (v1 == va.as<uint32_t>()) ? vb.as<uint32_t>() : va.as<uint32_t>();
+    LSS_TRY(radix_sort_pairs(k1, v1, k2, v2, nnz, 32, rbits, 0, &ks, &vs, st));
+    uint32_t *n_out_dev = reinterpret_cast<uint32_t *>(cnt.as<unsigned long long>() + 3);
+    LSS_CUDA(flags.alloc(sizeof(uint32_t) * n, st));
+    head_flags_kernel<<<stride_grid(n, 256), 256, 0, st>>>(ks, n, flags.as<uint32_t>());
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(exclusive_scan_u32(flags.as<uint32_t>(), flags.as<uint32_t>(), n, n_out_dev, st));
+    csr_emit_kernel<<<stride_grid(n, 256, 16), 256, 0, st>>>(ks, vs, vals, n, flags.as<uint32_t>(), n_rows, indptr, indices, data, n_out_dev);
+    LSS_LAUNCH_CHECK();
+    uint32_t n_out = 0;
+    LSS_CUDA(cudaMemcpyAsync(&n_out, n_out_dev, sizeof(n_out), cudaMemcpyDeviceToHost, st));
+    LSS_CUDA(cudaStreamSynchronize(st));
+    if (nnz_out_h) *nnz_out_h = (int64_t)n_out;
+    return LSS_OK;
+}
+
+extern "C" int lss_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *indptr, const int32_t *indices,
+                                 const double *data, int32_t *t_indptr, int32_t *t_indices, double *t_data, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nnz >= (1ll << 31) || n_rows >= (1ll << 31) || n_cols >= (1ll << 31) - 1) return fail(LSS_ERANGE, "csr_transpose: exceeds int32 index range");
+    if (nnz == 0) {
+        fill_i32_kernel<<<stride_grid(n_cols + 1, 256), 256, 0, st>>>(t_indptr, n_cols + 1, 0);
+        LSS_LAUNCH_CHECK();
+        return LSS_OK;
+    }
+    Scratch ka, kb, va, vb, src;
+    LSS_CUDA(ka.alloc(sizeof(uint64_t) * nnz, st));
+    LSS_CUDA(kb.alloc(sizeof(uint64_t) * nnz, st));
+    LSS_CUDA(va.alloc(sizeof(uint32_t) * nnz, st));
+    LSS_CUDA(vb.alloc(sizeof(uint32_t) * nnz, st));
+    LSS_CUDA(src.alloc(sizeof(uint32_t) * nnz, st));
+    csr_expand_keys_kernel<<<stride_grid(n_rows * 32, 256, 16), 256, 0, st>>>(n_rows, indptr, indices, ka.as<uint64_t>(), src.as<uint32_t>());
+    LSS_LAUNCH_CHECK();
+    uint64_t *ks;
+    uint32_t *vs;
+    LSS_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), nnz, 0,
+                             bits_for(n_cols > 0 ? n_cols - 1 : 0), 1, &ks, &vs, st));
+    transpose_emit_kernel<<<stride_grid(nnz, 256, 16), 256, 0, st>>>(ks, vs, src.as<uint32_t>(), data, nnz, n_cols, t_indptr, t_indices, t_data);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+extern "C" int lss_argsort_u64(int64_t n, const uint64_t *keys, int32_t key_bits, int32_t *order, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n >= (1ll << 31)) return fail(LSS_ERANGE, "argsort: exceeds int32 index range");
+    if (key_bits < 1 || key_bits > 64) return fail(LSS_EINVAL, "argsort: key_bits must be 1..64");
+    if (n == 0) return LSS_OK;
+    Scratch ka, kb, va, vb;
+    LSS_CUDA(ka.alloc(sizeof(uint64_t) * n, st));
+    LSS_CUDA(kb.alloc(sizeof(uint64_t) * n, st));
+    LSS_CUDA(va.alloc(sizeof(uint32_t) * n, st));
+    LSS_CUDA(vb.alloc(sizeof(uint32_t) * n, st));
+    LSS_CUDA(cudaMemcpyAsync(ka.p, keys, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, st));
+    uint64_t *ks;
+    uint32_t *vs;
+    LSS_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), n, 0, key_bits, 1, &ks, &vs, st));
+    copy_order_kernel<<<stride_grid(n, 256), 256, 0, st>>>(vs, order, n);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}

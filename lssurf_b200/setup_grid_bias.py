@@ -1,0 +1,35 @@
+"""Gridded bias proportional to a data parameter (API mirror of LSsurf/setup_grid_bias.py:4-43)."""
+import numpy as np
+import torch
+
+from . import _cabi
+from .lin_op import lin_op
+
+
+def setup_grid_bias(data, G_data, constraint_op_list, grids, name=None, param=None, grid=None, expected_rms=None,
+                    expected_value=None, expected_rms_grad=None):
+    """Columns = nodes of ``grid`` appended after G_data's; entries = interpolation weights x data.<param>.
+
+    Replicates the reference including its operator-precedence quirk: the curvature rows get
+    ``expected = expected_rms_grad`` (the division by sqrt(cell area) applies to a zero array,
+    setup_grid_bias.py:33).
+    """
+    if name is None:
+        name = param + '_bias'
+    grids[name] = grid
+    grid.col_0 = G_data.col_N
+    grid.col_N = grid.col_0 + grid.N_nodes
+    op = lin_op(grid=grid, name=name).interp_mtx(data.coords()[0:2])
+    scale = _cabi.to_dev(np.asarray(getattr(data, param), dtype=float), torch.float64)
+    r, c, v = op._device('r'), op._device('c'), op._device('v')
+    op._set_device(r, c, (v * scale[r.long()]).contiguous())
+    G_data.add(op)
+    if expected_rms_grad is not None:
+        curv = lin_op(grid, name='grad2_' + name).grad2(DOF=param)
+        curv.expected = expected_rms_grad + np.zeros(curv.N_eq) / np.sqrt(np.prod(grid.delta))
+        constraint_op_list.append(curv)
+    if expected_rms is not None:
+        mag = lin_op(grid, name='mag_' + name).data_bias(ind=np.arange(grid.N_nodes), col=np.arange(grid.col_0, grid.col_N))
+        mag.expected = expected_rms + np.zeros(mag.N_eq)
+        mag.expected_val = (0 if expected_value is None else expected_value) + np.zeros(mag.N_eq)
+        constraint_op_list.append(mag)

@@ -37,7 +37,7 @@ def grid_geometry(bounds, deltas, col_0=0, name=''):
     first/last centre), :67 (strides), :68/:76 (column range).
     """
     deltas = np.asarray(deltas, dtype=float)
-    shape = np.array([int((b[1] - b[0]) / d) + 1 for b, d in zip(bounds, deltas)], dtype=np.int64)
+    shape = np.array([((b[1] - b[0]) / d) + 1 for b, d in zip(bounds, deltas)]).astype(np.int64)
     ctrs = [b[0] + d * np.arange(n) for b, d, n in zip(bounds, deltas, shape)]
     lo = np.array([c[0] for c in ctrs])
     hi = np.array([c[-1] for c in ctrs])

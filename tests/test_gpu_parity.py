@@ -1,0 +1,245 @@
+"""GPU tier: the CUDA product (through the C ABI) against the oracle and the reference fixtures.
+
+Bit-exact for integer / index / structure work and for the fp64 assembly values; 1e-6 relative L2
+(BASELINE.json north_star) for solutions, written in each test; edit masks identical.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import lssurf_oracle as O
+from tests.util import FIT_CASES, GOLDEN, csr_digest, digest, load_case, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def L():
+    import lssurf_b200
+    lssurf_b200._cabi.lib()          # fails loudly if the .so or the GPU is missing
+    return lssurf_b200
+
+
+def make_data(L, pts):
+    return L.point_data.data().from_dict(pts)
+
+
+# ------------------------------------------------------------------------------------ assembly
+@pytest.mark.parametrize('g', ['g1', 'g2', 'g3'])
+def test_interp_mtx_edge_points(L, g):
+    fx = np.load(f'{GOLDEN}/lowlevel.npz')
+    bounds, deltas, col_0 = fx[g + '_bounds'], fx[g + '_deltas'], int(fx[g + '_col0'])
+    grid = L.fd_grid(bounds, deltas, name=g, col_0=col_0)
+    pts = list(fx[g + '_pts'])
+    op = L.lin_op(grid, name='interp').interp_mtx(pts, bounds_error=False)
+    assert op.N_eq == int(fx[g + '_nvalid'])
+    assert op.r.dtype == np.int64 and op.v.dtype == np.float64 and op.r.shape == (op.N_eq, 2 ** len(bounds))
+    assert digest(op.r, op.c, op.v) == str(fx[g + '_rcv'])               # reference triplets, bit for bit
+    M = op.toCSR(row_N=len(pts[0]))
+    assert M.has_canonical_format and csr_digest(M) == str(fx[g + '_csr'])
+    with pytest.raises(ValueError) as e:
+        L.lin_op(grid).interp_mtx(pts)
+    assert str(e.value) == str(fx[g + '_err'])
+
+
+def test_stencil_families(L):
+    fx = np.load(f'{GOLDEN}/lowlevel.npz')
+    g2 = L.fd_grid(fx['g2_bounds'], fx['g2_deltas'], name='z0')
+    g3 = L.fd_grid(fx['g3_bounds'], fx['g3_deltas'], name='dz', col_0=g2.N_nodes)
+    want = {s.split(':')[0]: s.split(':')[1:] for s in fx['stencils']}
+    builders = {'grad2_z0': lambda: L.lin_op(g2, name='grad2_z0').grad2(DOF='z0'),
+                'grad_z0': lambda: L.lin_op(g2, name='grad_z0').grad(DOF='z0'),
+                'grad2_dzdt': lambda: L.lin_op(g3, name='grad2_dzdt').grad2_dzdt(DOF='z', t_lag=1),
+                'grad_dzdt': lambda: L.lin_op(g3, name='grad_dzdt').grad_dzdt(DOF='z', t_lag=1),
+                'd2z_dt2': lambda: L.lin_op(g3, name='d2z_dt2').d2z_dt2(DOF='z')}
+    for kind, build in builders.items():
+        op = build()
+        d = digest(op.r.ravel(), op.c.ravel(), op.v.ravel(), np.asarray(op.ind0).astype(np.int64))
+        assert [str(op.N_eq), d] == want[kind], kind
+    offs = ([-1, -1, -1, 0, 0, 0, 1, 1, 1], [-1, 0, 1, -1, 0, 1, -1, 0, 1])
+    coef = np.array([0.5, -1.25, 0.5, 2., -3.5, 2., 0.5, -1.25, 0.5])
+    for op in (L.lin_op(g2, name='custom').diff_op(offs, coef), L.fd_op(g2, offs, coef, name='custom')):
+        d = digest(op.r, op.c, op.v, np.asarray(op.ind0).astype(np.int64))
+        assert [str(op.N_eq), d] == want['custom9']
+
+
+def test_stencil_invalid_equations_and_which_nodes(L):
+    g = L.fd_grid([[0., 6.], [0., 9.]], [1., 1.], name='z')
+    go = O.grid_geometry([[0., 6.], [0., 9.]], [1., 1.], name='z')
+    op = L.lin_op(g, name='a').diff_op(([-1, 0, 1], [0, 0, 2]), np.array([1., -2., 1.]), valid_equations_only=False)
+    assert op.N_eq == g.N_nodes
+    r, c, v = op.r, op.c, op.v
+    iy, ix = np.unravel_index(np.arange(g.N_nodes), g.shape)
+    for k, (dy, dx, w) in enumerate(zip([-1, 0, 1], [0, 0, 2], [1., -2., 1.])):
+        ok = (iy + dy >= 0) & (iy + dy < g.shape[0]) & (ix + dx >= 0) & (ix + dx < g.shape[1])
+        assert np.array_equal(v[:, k], w * ok) and np.array_equal(c[ok, k], (iy + dy)[ok] * g.shape[1] + (ix + dx)[ok])
+        assert np.all(c[~ok, k] == 0)
+    sel = np.array([0, 5, 17, 33])
+    op2 = L.lin_op(g, name='one').one(which_nodes=sel)
+    assert np.array_equal(op2.ind0, sel) and np.array_equal(op2.r.ravel(), np.arange(4)) and np.array_equal(op2.c.ravel(), sel)
+
+
+def test_coo_to_csr_random_duplicates_and_empty_rows(L):
+    rng = np.random.default_rng(11)
+    n = 200_000
+    r = rng.integers(0, 50_000, n); c = rng.integers(0, 3000, n); v = rng.normal(size=n)
+    v[rng.random(n) < 0.05] = 0.
+    r[:2000], c[:2000] = r[2000:4000], c[2000:4000]
+    r[r == 17] = 18                                         # an empty row in the middle
+    op = L.lin_op(col_N=3000)
+    op.r, op.c, op.v = r, c, v
+    M = op.toCSR(row_N=50_010)                              # trailing empty rows
+    ip, ix, dat, _ = O.coo_to_csr(r, c, v, n_rows=50_010, n_cols=3000)
+    assert np.array_equal(M.indptr, ip) and np.array_equal(M.indices, ix)
+    assert digest(M.data) == digest(dat)                    # <= 2 duplicates per entry here: sums are exact matches
+    # idempotence: CSR -> COO -> CSR is the identity
+    coo = M.tocoo()
+    op2 = L.lin_op(col_N=3000)
+    op2.r, op2.c, op2.v = coo.row, coo.col, coo.data
+    assert csr_digest(op2.toCSR(row_N=50_010)) == csr_digest(M)
+    # default row_N = last row holding a non-zero (lin_op.py:751-752)
+    assert op.toCSR().shape[0] == int(r[v != 0].max()) + 1
+    # all-zero operator
+    op3 = L.lin_op(col_N=5)
+    op3.r, op3.c, op3.v = np.array([0, 1]), np.array([1, 2]), np.zeros(2)
+    assert op3.toCSR(row_N=3).nnz == 0
+
+
+def test_transpose_and_spmv_modes(L):
+    rng = np.random.default_rng(12)
+    rows = 30_000
+    M = sp.random(rows, 4000, density=2e-3, random_state=5, format='csr')
+    M = sp.vstack([M, sp.csr_matrix(np.ones((1, 4000)))]).tocsr()          # one long row (warp path + carries)
+    M.sort_indices()
+    _c = L._cabi
+    A = L.DeviceCSR(_c.to_dev(M.indptr.astype(np.int32)), _c.to_dev(M.indices.astype(np.int32)), _c.to_dev(M.data), M.shape)
+    x = rng.normal(size=4000); s = rng.uniform(0.5, 2, M.shape[0])
+    xd, sd = _c.to_dev(x), _c.to_dev(s)
+    tol = 1e-13 * np.abs(M).dot(np.abs(x)).max()
+    assert np.max(np.abs(A.dot(xd).cpu().numpy() - M.dot(x))) <= tol
+    assert np.max(np.abs(A.dot(xd, mode=_c.SPMV_SCALE, s=sd).cpu().numpy() - s * M.dot(x))) <= tol * 2
+    assert np.max(np.abs(A.dot(xd, mode=_c.SPMV_RESIDUAL, s=sd).cpu().numpy() - (s - M.dot(x)))) <= tol
+    At = A.transpose()
+    Mt = M.T.tocsr(); Mt.sort_indices()
+    assert np.array_equal(At.indptr.cpu().numpy(), Mt.indptr) and np.array_equal(At.indices.cpu().numpy(), Mt.indices)
+    assert digest(At.data.cpu().numpy()) == digest(Mt.data)
+    y = rng.normal(size=M.shape[0])
+    # adjointness <A x, y> == <x, A^T y>
+    lhs = float(np.dot(A.dot(xd).cpu().numpy(), y)); rhs = float(np.dot(x, At.dot(_c.to_dev(y)).cpu().numpy()))
+    assert abs(lhs - rhs) <= 1e-12 * (abs(lhs) + 1)
+    # determinism: bitwise repeatable
+    assert digest(A.dot(xd).cpu().numpy()) == digest(A.dot(xd).cpu().numpy())
+
+
+def test_argsort(L):
+    rng = np.random.default_rng(13)
+    keys = rng.integers(0, 1 << 37, 300_001).astype(np.uint64)
+    keys[:1000] = keys[1000:2000]
+    order = L._cabi.argsort_u64(L._cabi.to_dev(keys.view(np.int64)).view(torch.int64), 37).cpu().numpy()
+    assert np.array_equal(order, np.argsort(keys, kind='stable'))
+
+
+# ------------------------------------------------------------------------------------ robust statistics
+def test_rde_and_sigma_extra_known_answers(L):
+    fx = np.load(f'{GOLDEN}/lowlevel.npz')
+    x = fx['rde_x']
+    assert L.RDE(x) == float(fx['rde'])                      # the reference's own RDE value, bit for bit
+    xs = x.copy(); xs[~np.isfinite(xs)] = 0.
+    se = L.calc_sigma_extra(xs, fx['rde_sigma'], fx['rde_mask'])
+    assert np.all(se == se[0]) and abs(se[0] - float(fx['sigma_extra'])) < 1e-12
+    assert np.isnan(L.RDE(np.array([1.0]))) and np.isnan(L.RDE(np.array([np.nan, np.inf, 2.0])))
+    rng = np.random.default_rng(14)
+    for n in (2, 3, 9, 10, 11, 1000, 100_003):
+        v = rng.standard_t(2, n) * 10 ** rng.uniform(-3, 3)
+        assert L.RDE(v) == O.rde(v), n
+    assert L.RDE(np.zeros(100)) == 0.0 and L.RDE(-np.ones(7)) == 0.0
+    # fewer than 10 selected points: sigma_extra stays 0 (calc_sigma_extra.py:34)
+    m = np.zeros(50, dtype=bool); m[:9] = True
+    assert np.all(L.calc_sigma_extra(rng.normal(size=50), np.ones(50), m) == 0)
+    # groups: each group gets its own value, assigned to all its members
+    r = rng.normal(0, 3, 4000); sg = np.full(4000, 0.5); msk = rng.random(4000) < 0.95
+    groups = {'a': np.arange(4000) < 1500, 'b': np.arange(4000) >= 1500}
+    got = L.calc_sigma_extra(r, sg, msk, groups)
+    want = O.sigma_extra(r, sg, msk, groups)
+    assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_edit_mask_kernel(L):
+    rng = np.random.default_rng(15)
+    n = 100_000
+    r = rng.normal(0, 1, n); sg = rng.uniform(0.2, 0.5, n); se = np.full(n, 0.3)
+    r[5] = np.nan
+    r[6] = 3.0 * np.sqrt(sg[6] ** 2 + 0.09)                  # exactly on the threshold -> excluded (strict <)
+    _c = L._cabi
+    m, st = _c.edit_mask(_c.to_dev(r), _c.to_dev(sg), _c.to_dev(se), 3.0)
+    want = np.abs(r / np.sqrt(sg ** 2 + se ** 2)) < 3.0
+    assert np.array_equal(m.cpu().numpy().astype(bool), want)
+    assert st['count'] == int(want.sum()) and st['min_sigma'] == sg[want].min() and st['near_threshold'] >= 1
+
+
+# ------------------------------------------------------------------------------------ whole fits
+@pytest.mark.parametrize('name', FIT_CASES)
+def test_smooth_fit_against_reference_fixture(L, name):
+    fx, pts, kw = load_case(name)
+    D = make_data(L, pts)
+    fo = L.smooth_fit(data=D.copy(), VERBOSE=False, return_fit_objects=True, **kw)
+    G, C = fo['G_data'].toCSR(), fo['Gc'].toCSR()
+    assert G.shape == tuple(fx['G_shape']) and C.shape == tuple(fx['C_shape'])
+    assert csr_digest(G) == str(fx['G_digest'])              # CSR structure + values: bit exact vs the reference
+    assert csr_digest(C) == str(fx['C_digest'])
+    assert digest(np.asarray(fo['Ec'], dtype=float)) == str(fx['Ec_digest'])
+    want_toc = {s.split(':')[0]: int(s.split(':')[1]) for s in fx['toc_rows']}
+    got_toc = {k: len(np.unique(v)) for k, v in fo['Gc'].TOC['rows'].items()}
+    assert got_toc == want_toc
+    hist = []
+    S = L.smooth_fit(data=D.copy(), VERBOSE=False, history=hist, **kw)
+    assert len(S['timing']['pcg']) == int(fx['n_outer'])
+    for k, packed in enumerate(fx['masks']):                 # identical edit mask after every outer iteration
+        assert np.array_equal(hist[k]['mask_out'], packed), f'mask after iteration {k}'
+        assert abs(hist[k]['sigma_extra']['all'] - fx['sigma_extra'][k]) < 2e-5
+    assert np.array_equal(np.packbits(S['data'].three_sigma_edit), fx['in_TSE'])
+    assert rel_l2(S['m']['all'], fx['m0']) < 1e-6            # north-star tolerance
+    assert rel_l2(S['m']['z0'].z0.ravel(), fx['m0'][:S['m']['z0'].z0.size]) < 1e-6
+    assert np.max(np.abs(S['data'].z_est - fx['z_est'])) < 1e-5
+    ref_cols = S['grids']['dz'].global_ind([*np.meshgrid(np.arange(S['grids']['dz'].shape[0]), np.arange(S['grids']['dz'].shape[1]),
+                                                         indexing='ij'), kw['reference_epoch'] + np.zeros(S['grids']['dz'].shape[:2], dtype=int)])
+    assert np.all(S['m']['all'][ref_cols.ravel()] == 0.0)    # reference epoch held at exactly zero
+    assert S['valid_data'].sum() == int(np.unpackbits(fx['in_TSE'])[:int(fx['n_data'])].sum())
+
+
+def test_smooth_fit_medium_against_oracle(L):
+    """1e5 uniform points, 3-D fit with outliers: CUDA path vs the oracle run here on the same inputs."""
+    from lssurf_b200 import synthetic
+    pts, kw = synthetic.uniform_3d(n=100_000, width=2.e4, seed=3)
+    hist_o, hist = [], []
+    res = O.smooth_fit(pts['x'], pts['y'], pts['time'], pts['z'], pts['sigma'], kw['ctr'], kw['W'], kw['spacing'],
+                       kw['E_RMS'], reference_epoch=kw['reference_epoch'], max_iterations=kw['max_iterations'], history=hist_o)
+    S = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, history=hist, **kw)
+    assert len(hist) == sum('mask_out' in h for h in hist_o)
+    for k, h in enumerate(hist):
+        assert np.array_equal(h['mask_out'], np.packbits(hist_o[k]['mask_out'])), f'mask after iteration {k}'
+    assert np.array_equal(S['data'].three_sigma_edit, res['in_TSE'])
+    assert rel_l2(S['m']['all'], res['m0']) < 1e-6
+    G = csr_digest(L.smooth_fit(data=make_data(L, pts), VERBOSE=False, return_fit_objects=True, **kw)['G_data'].toCSR())
+    assert G == digest(*res['sys']['G'][:3])
+
+
+def test_large_scale_properties(L):
+    """Full-size properties (cfg 3 shapes, 1e6 points) that need no oracle: row sums of the interpolation
+    matrix are exactly 1 up to rounding, CSR is canonical, G^T products are adjoint, the solve reduces the residual."""
+    from lssurf_b200 import synthetic
+    pts, kw = synthetic.uniform_3d(n=1_000_000, seed=0)
+    fo = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, return_fit_objects=True, **kw)
+    Gd = fo['G_data']._csr_device(row_N=1_000_000)
+    assert Gd.shape == (1_000_000, 254_622)
+    ip = Gd.indptr.cpu().numpy(); ix = Gd.indices.cpu().numpy()
+    assert ip[0] == 0 and np.all(np.diff(ip) >= 0) and ip[-1] == Gd.nnz
+    assert np.all((np.diff(ix) > 0) | np.isin(np.arange(1, ix.size), ip[1:-1]))      # sorted, no duplicates inside rows
+    ones = torch.ones(Gd.shape[1], dtype=torch.float64, device='cuda')
+    rs = Gd.dot(ones).cpu().numpy()
+    assert np.max(np.abs(rs - 2.0)) < 1e-12                                           # z0 weights + dz weights each sum to 1
+    rng = np.random.default_rng(0)
+    x = L._cabi.to_dev(rng.normal(size=Gd.shape[1])); y = L._cabi.to_dev(rng.normal(size=Gd.shape[0]))
+    lhs = float((Gd.dot(x) * y).sum().item()); rhs = float((x * Gd.transpose().dot(y)).sum().item())
+    assert abs(lhs - rhs) < 1e-10 * abs(lhs)

@@ -1,0 +1,99 @@
+"""CPU tier: host-side mirror of the reference interface (no kernels involved)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from lssurf_b200 import fd_grid, unique_by_rows
+from lssurf_b200.bias_functions import assign_bias_ID
+from lssurf_b200.parallel import DistContext
+from lssurf_b200.point_data import data as point_data
+from lssurf_b200.smooth_fit import DEFAULTS, smooth_fit
+from oracle import lssurf_oracle as O
+
+
+@pytest.mark.parametrize('bounds,deltas', [([[-5e4, 5e4], [-5e4, 5e4]], [250., 250.]),
+                                            ([[-3., 5.], [100., 131.]], [0.5, 1.7]),
+                                            ([[-1e3, 1e3], [-2e3, 1e3], [-1., 1.]], [100., 100., 0.25]),
+                                            ([[0., 0.3]], [0.1])])
+def test_fd_grid_geometry(bounds, deltas):
+    g = fd_grid(bounds, deltas, col_0=11)
+    o = O.grid_geometry(bounds, deltas, col_0=11)
+    assert np.array_equal(g.shape, o['shape']) and np.array_equal(g.stride, o['stride'])
+    assert g.col_N == o['col_N'] and g.N_nodes == o['n_nodes']
+    for d in range(len(bounds)):
+        assert np.array_equal(g.ctrs[d], o['ctrs'][d]) and g.bds[d][0] == o['lo'][d] and g.bds[d][1] == o['hi'][d]
+    s = g.as_struct()
+    assert s.ndim == len(bounds) and s.col_0 == 11 and s.shape[0] == g.shape[0]
+
+
+def test_fd_grid_point_helpers():
+    g = fd_grid([[0., 10.], [0., 20.]], [1., 2.], col_0=3)
+    pts = [np.array([0., 10., 10.0001, np.nan, 3.5]), np.array([0., 20., 1., 1., 7.])]
+    assert g.validate_pts(pts).tolist() == [True, True, False, False, True]
+    assert np.array_equal(g.global_ind([np.array([1.]), np.array([2.])]), [3 + 11 + 2])
+    ind, ok = g.global_ind([np.array([1, 11]), np.array([2, 0])], return_valid=True)
+    assert ok.tolist() == [True, False] and ind[1] == 0
+    sub = g.cell_sub_for_pts(pts)
+    assert sub[0][4] == 3 and sub[1][4] == 3 and np.isnan(sub[0][2])
+
+
+def test_unique_by_rows_and_bias_ids():
+    x = np.array([[2., 1.], [1., 5.], [2., 1.], [1., np.nan], [1., 5.]])
+    x2 = np.nan_to_num(x, nan=-9999)
+    u, d = unique_by_rows(x2, return_dict=True)
+    assert u.tolist() == [[1., -9999.], [1., 5.], [2., 1.]]
+    assert sorted(d[(2., 1.)].tolist()) == [0, 2]
+    D = point_data().from_dict({'rgt': x[:, 0], 'cycle': x[:, 1], 'sigma_corr': np.array([.1, .2, .3, .4, .6]), 'z': np.zeros(5)})
+    D, bm = assign_bias_ID(D, ['rgt', 'cycle'])
+    ids, _ = O.bias_ids([x[:, 0], x[:, 1]])
+    assert np.array_equal(D.bias_ID.astype(int), ids)
+    assert bm['E_bias'][1] == pytest.approx(0.4) and np.isnan(bm['bias_ID_dict'][0]['cycle'])
+
+
+def test_smooth_fit_argument_errors():
+    with pytest.raises(ValueError):
+        smooth_fit(data=point_data().from_dict({'z': np.zeros(3)}))
+    assert DEFAULTS['max_iterations'] == 10 and DEFAULTS['mask_scale'] == {0: 10, 1: 1}
+    assert DEFAULTS['converge_tol_dz'] == 0.05 and DEFAULTS['min_iterations'] == 2
+
+
+def test_shard_bounds():
+    for n in (0, 1, 7, 10_000_001):
+        for world in (1, 2, 4, 8):
+            cuts = [DistContext(r, world).shard(n) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    ctx = DistContext(rank, world, None)
+    lo, hi = ctx.shard(11)
+    out = ctx.gather_rows(np.arange(lo, hi, dtype=float) * 2)
+    # the data-path reduction every rank must agree on (what ncclAllReduce does on the GPU)
+    t = torch.tensor([float(hi - lo), float(rank)], dtype=torch.float64)
+    dist.all_reduce(t)
+    q.put((rank, out.tolist(), t.tolist()))
+    dist.destroy_process_group()
+
+
+def test_row_sharding_world2_gloo():
+    """World-size-2 host logic on CPU: shards tile the rows, gathers restore the row order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, gathered, red in res:
+        assert gathered == (np.arange(11.) * 2).tolist()
+        assert red == [11.0, 1.0]
