@@ -179,7 +179,13 @@ def coo_to_csr(r, c, v, n_rows=None, n_cols=None):
     head = np.ones(r.size, dtype=bool)
     head[1:] = (r[1:] != r[:-1]) | (c[1:] != c[:-1])
     starts = np.flatnonzero(head)
-    data = np.add.reduceat(v, starts) if v.size else v
+    # duplicates are summed left to right in input order (scipy's own order is unspecified for runs
+    # of three or more because csr_sort_indices uses an unstable sort; for one or two it is the same)
+    run = np.diff(np.append(starts, v.size))
+    data = v[starts].copy()
+    for k in range(1, int(run.max()) if run.size else 0):
+        more = run > k
+        data[more] = data[more] + v[starts[more] + k]
     indices = c[starts].astype(np.int32)
     counts = np.bincount(r[starts], minlength=n_rows)
     indptr = np.zeros(n_rows + 1, dtype=np.int32)

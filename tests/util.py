@@ -25,7 +25,7 @@ def csr_digest(M):
 
 def load_case(name):
     fx = np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False)
-    pts = {k[3:]: fx[k] for k in fx.files if k.startswith('in_')}
+    pts = {k[3:]: fx[k] for k in fx.files if k.startswith('in_') and k != 'in_TSE'}
     kw = eval(str(fx['kw']), {'np': np, 'array': np.array, 'float64': np.float64})   # repr() of plain dicts
     return fx, pts, kw
 
