@@ -49,6 +49,8 @@ int lss_version(void);
 const char *lss_last_error(void);
 /* Number of CUDA devices visible (0 => every compute entry point fails with LSS_ECUDA). */
 int lss_device_count(void);
+/* Kernels launched by this library in the calling process so far (for bench.py's gpu_launches). */
+int64_t lss_launch_count(void);
 
 /* ------------------------------------------------------------------ design-matrix assembly */
 
@@ -95,6 +97,16 @@ int lss_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t
 
 /* Stable argsort of int64 keys in [0, 2^key_bits) (used for the internal spatial ordering of points). */
 int lss_argsort_u64(int64_t n, const uint64_t *keys, int32_t key_bits, int32_t *order, void *stream);
+
+/* Dense rank of every value among the sorted distinct values of x (what np.unique(return_inverse=True)
+ * returns; NaN is first replaced by nan_value, as assign_bias_ID does with -9999, bias_functions.py:55-60).
+ * unique_h (host, optional, capacity unique_cap) receives the distinct values in ascending order. */
+int lss_dense_rank_f64(const double *x, int64_t n, double nan_value, int32_t *rank, double *unique_h,
+                       int64_t unique_cap, int64_t *n_unique_h, void *stream);
+
+/* out[g] = np.nanmedian(vals[ids == g]) for g in [0, n_groups) (bias_functions.py:79); NaN for an empty group. */
+int lss_group_median(const int32_t *ids, const double *vals, int64_t n, int32_t n_groups, double *out,
+                     void *stream);
 
 /* ------------------------------------------------------------------ CSR products */
 

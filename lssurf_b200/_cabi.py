@@ -35,6 +35,7 @@ _pi64, _pi32, _pf64 = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_
 SIGNATURES = {
     'lss_version': [],
     'lss_device_count': [],
+    'lss_launch_count': [],
     'lss_interp_coo': [C.POINTER(lss_grid_t), C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp, _pi64, _vp],
     'lss_stencil_count': [C.POINTER(lss_grid_t), _i32, _pi32, _i32, _pi64, _pi64, _pi64],
     'lss_stencil_coo': [C.POINTER(lss_grid_t), _i32, _pi32, _pf64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
@@ -42,6 +43,8 @@ SIGNATURES = {
     'lss_coo_to_csr': [_i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _pi64, _vp],
     'lss_csr_transpose': [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     'lss_argsort_u64': [_i64, _vp, _i32, _vp, _vp],
+    'lss_dense_rank_f64': [_vp, _i64, _f64, _vp, _pf64, _i64, _pi64, _vp],
+    'lss_group_median': [_vp, _vp, _i64, _i32, _vp, _vp],
     'lss_spmv': [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
     'lss_comm_unique_id': [C.c_char_p],
     'lss_comm_create': [C.POINTER(_vp), C.c_char_p, _i32, _i32],
@@ -73,6 +76,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.lss_launch_count.restype = C.c_int64
     lib.lss_last_error.argtypes = []
     lib.lss_last_error.restype = C.c_char_p
     _lib = lib
@@ -215,6 +219,29 @@ def argsort_u64(keys, key_bits):
     order = torch.empty(n, dtype=torch.int32, device=device())
     check(L.lss_argsort_u64(n, ptr(keys), int(key_bits), ptr(order), stream()))
     return order
+
+
+def dense_rank(x, nan_value=-9999.0, max_unique=1 << 20):
+    """-> (rank int32 tensor, ascending unique values as NumPy)   [np.unique(x, return_inverse=True)]"""
+    L = lib()
+    n = int(x.numel())
+    rank = torch.empty(n, dtype=torch.int32, device=device())
+    cap = min(max(n, 1), max_unique)
+    uniq = np.empty(cap, dtype=np.float64)
+    nu = C.c_int64(0)
+    check(L.lss_dense_rank_f64(ptr(x), n, float(nan_value), ptr(rank), uniq.ctypes.data_as(_pf64), cap, C.byref(nu), stream()))
+    return rank, uniq[:nu.value].copy()
+
+
+def group_median(ids, vals, n_groups):
+    L = lib()
+    out = torch.empty(int(n_groups), dtype=torch.float64, device=device())
+    check(L.lss_group_median(ptr(ids), ptr(vals), int(vals.numel()), int(n_groups), ptr(out), stream()))
+    return out
+
+
+def launch_count():
+    return int(load().lss_launch_count())
 
 
 def spmv(indptr, indices, data, x, n_rows, n_cols, mode=SPMV_PLAIN, s=None, out=None):

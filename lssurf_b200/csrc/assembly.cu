@@ -10,6 +10,7 @@
 namespace lss {
 
 thread_local char g_err[512] = "";
+long long g_launches = 0;
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -185,6 +186,7 @@ using namespace lss;
 
 extern "C" int lss_version(void) { return 100; }
 extern "C" const char *lss_last_error(void) { return lss::g_err; }
+extern "C" int64_t lss_launch_count(void) { return lss::g_launches; }
 extern "C" int lss_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {

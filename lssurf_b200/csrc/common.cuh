@@ -25,7 +25,14 @@ int fail(int code, const char *fmt, ...);
         if (rc__ != LSS_OK) return rc__; \
     } while (0)
 
-#define LSS_LAUNCH_CHECK() LSS_CUDA(cudaGetLastError())
+extern long long g_launches;
+}
+#define LSS_LAUNCH_CHECK()            \
+    do {                              \
+        ++lss::g_launches;            \
+        LSS_CUDA(cudaGetLastError()); \
+    } while (0)
+namespace lss {
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids of grid-stride kernels are multiples of this
 

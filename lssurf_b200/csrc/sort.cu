@@ -329,6 +329,64 @@ __global__ void __launch_bounds__(256) copy_order_kernel(const uint32_t *__restr
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int)in[i];
 }
 
+
+// ============================================================================ dense ranks / group medians
+__global__ void __launch_bounds__(256)
+rank_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ pos,
+                    int64_t n, int *__restrict__ rank, uint64_t *__restrict__ uniq) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool head = (i == 0) || (keys[i] != keys[i - 1]);
+        // pos = exclusive scan of the head flags: rank of a non-head is pos - 1
+        const uint32_t r = head ? pos[i] : pos[i] - 1;
+        rank[idx[i]] = (int)r;
+        if (head && uniq) uniq[r] = keys[i];
+    }
+}
+
+__device__ __forceinline__ unsigned long long f64_sort_key(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(256)
+f64_keys_kernel(const double *__restrict__ x, int64_t n, double nan_value, uint64_t *__restrict__ keys) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (v != v) v = nan_value;
+        if (v == 0.0) v = 0.0;               // -0.0 and +0.0 compare equal in NumPy
+        keys[i] = f64_sort_key(v);
+    }
+}
+
+// keys (id << 0) for the second, stable pass of the (id, value) sort
+__global__ void __launch_bounds__(256)
+gather_id_keys_kernel(const int *__restrict__ ids, const uint32_t *__restrict__ order, int64_t n, uint64_t *__restrict__ keys) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        keys[i] = (uint64_t)(uint32_t)ids[order[i]];
+}
+
+// one thread per group: [lo, hi) = its segment in the (id, value)-sorted order; NaNs sort last inside a group
+__global__ void __launch_bounds__(128)
+group_median_kernel(const uint64_t *__restrict__ id_keys, const uint32_t *__restrict__ order, const double *__restrict__ vals,
+                    int64_t n, int n_groups, double *__restrict__ out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    int64_t lo = 0, hi = n;                       // lower_bound(g), lower_bound(g + 1)
+    {
+        int64_t a = 0, b = n;
+        while (a < b) { int64_t m = (a + b) >> 1; if (id_keys[m] < (uint64_t)g) a = m + 1; else b = m; }
+        lo = a;
+        b = n;
+        while (a < b) { int64_t m = (a + b) >> 1; if (id_keys[m] < (uint64_t)g + 1) a = m + 1; else b = m; }
+        hi = a;
+    }
+    while (hi > lo && vals[order[hi - 1]] != vals[order[hi - 1]]) --hi;      // drop trailing NaNs (nanmedian)
+    const int64_t m = hi - lo;
+    if (m <= 0) { out[g] = nan(""); return; }
+    const double a = vals[order[lo + (m - 1) / 2]], b = vals[order[lo + m / 2]];
+    out[g] = (m & 1) ? a : (a + b) / 2.0;                                   // np.median: mean of the two middle values
+}
+
 }  // namespace lss
 
 using namespace lss;
@@ -429,6 +487,78 @@ extern "C" int lss_argsort_u64(int64_t n, const uint64_t *keys, int32_t key_bits
     uint32_t *vs;
     LSS_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), n, 0, key_bits, 1, &ks, &vs, st));
     copy_order_kernel<<<stride_grid(n, 256), 256, 0, st>>>(vs, order, n);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+extern "C" int lss_dense_rank_f64(const double *x, int64_t n, double nan_value, int32_t *rank, double *unique_h,
+                                  int64_t unique_cap, int64_t *n_unique_h, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n >= (1ll << 31)) return fail(LSS_ERANGE, "dense_rank: exceeds int32 index range");
+    if (n_unique_h) *n_unique_h = 0;
+    if (n == 0) return LSS_OK;
+    Scratch ka, kb, va, vb, flags, uniq, tot;
+    LSS_CUDA(ka.alloc(sizeof(uint64_t) * n, st));
+    LSS_CUDA(kb.alloc(sizeof(uint64_t) * n, st));
+    LSS_CUDA(va.alloc(sizeof(uint32_t) * n, st));
+    LSS_CUDA(vb.alloc(sizeof(uint32_t) * n, st));
+    LSS_CUDA(flags.alloc(sizeof(uint32_t) * n, st));
+    LSS_CUDA(uniq.alloc(sizeof(uint64_t) * n, st));
+    LSS_CUDA(tot.alloc(sizeof(uint32_t), st));
+    f64_keys_kernel<<<stride_grid(n, 256), 256, 0, st>>>(x, n, nan_value, ka.as<uint64_t>());
+    LSS_LAUNCH_CHECK();
+    uint64_t *ks;
+    uint32_t *vs;
+    LSS_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), n, 0, 64, 1, &ks, &vs, st));
+    head_flags_kernel<<<stride_grid(n, 256), 256, 0, st>>>(ks, n, flags.as<uint32_t>());
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(exclusive_scan_u32(flags.as<uint32_t>(), flags.as<uint32_t>(), n, tot.as<uint32_t>(), st));
+    rank_scatter_kernel<<<stride_grid(n, 256), 256, 0, st>>>(ks, vs, flags.as<uint32_t>(), n, rank, uniq.as<uint64_t>());
+    LSS_LAUNCH_CHECK();
+    uint32_t nu = 0;
+    LSS_CUDA(cudaMemcpyAsync(&nu, tot.p, sizeof(nu), cudaMemcpyDeviceToHost, st));
+    LSS_CUDA(cudaStreamSynchronize(st));
+    if (n_unique_h) *n_unique_h = nu;
+    if (unique_h) {
+        if ((int64_t)nu > unique_cap) return fail(LSS_EINVAL, "dense_rank: %u unique values exceed the capacity %lld", nu, (long long)unique_cap);
+        LSS_CUDA(cudaMemcpyAsync(unique_h, uniq.p, sizeof(uint64_t) * nu, cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < nu; ++i) {   // decode the order-preserving keys back to doubles
+            uint64_t k;
+            memcpy(&k, &unique_h[i], sizeof(k));
+            uint64_t u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+            memcpy(&unique_h[i], &u, sizeof(u));
+        }
+    }
+    return LSS_OK;
+}
+
+extern "C" int lss_group_median(const int32_t *ids, const double *vals, int64_t n, int32_t n_groups, double *out,
+                                void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n >= (1ll << 31)) return fail(LSS_ERANGE, "group_median: exceeds int32 index range");
+    if (n_groups <= 0) return LSS_OK;
+    Scratch ka, kb, va, vb;
+    LSS_CUDA(ka.alloc(sizeof(uint64_t) * (n + 1), st));
+    LSS_CUDA(kb.alloc(sizeof(uint64_t) * (n + 1), st));
+    LSS_CUDA(va.alloc(sizeof(uint32_t) * (n + 1), st));
+    LSS_CUDA(vb.alloc(sizeof(uint32_t) * (n + 1), st));
+    uint64_t *ks = ka.as<uint64_t>();
+    uint32_t *vs = va.as<uint32_t>();
+    if (n > 0) {
+        // sort by value (NaN last), then stably by group id
+        f64_keys_kernel<<<stride_grid(n, 256), 256, 0, st>>>(vals, n, nan(""), ka.as<uint64_t>());
+        LSS_LAUNCH_CHECK();
+        uint64_t *k1;
+        uint32_t *v1;
+        LSS_TRY(radix_sort_pairs(ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), n, 0, 64, 1, &k1, &v1, st));
+        uint64_t *k2 = (k1 == ka.as<uint64_t>()) ? kb.as<uint64_t>() : ka.as<uint64_t>();
+        uint32_t *v2 = (v1 == va.as<uint32_t>()) ? vb.as<uint32_t>() : va.as<uint32_t>();
+        gather_id_keys_kernel<<<stride_grid(n, 256), 256, 0, st>>>(ids, v1, n, k1);
+        LSS_LAUNCH_CHECK();
+        LSS_TRY(radix_sort_pairs(k1, v1, k2, v2, n, 0, bits_for(n_groups), 0, &ks, &vs, st));
+    }
+    group_median_kernel<<<ceil_div(n_groups, 128), 128, 0, st>>>(ks, vs, vals, n, n_groups, out);
     LSS_LAUNCH_CHECK();
     return LSS_OK;
 }

@@ -36,6 +36,14 @@ class DistContext(object):
         dist.all_gather_object(parts, arr)
         return np.concatenate(parts)
 
+    def allreduce_sum(self, t):
+        """In-place fp64 sum over ranks of a CUDA tensor through the library's NCCL communicator."""
+        if self.world == 1 or self.comm is None:
+            return t
+        t = t.contiguous()
+        _cabi.check(_cabi.lib().lss_comm_allreduce_f64(self.comm, _cabi.ptr(t), int(t.numel()), _cabi.stream()))
+        return t
+
     def destroy(self):
         if self.comm is not None:
             _cabi.load().lss_comm_destroy(self.comm)

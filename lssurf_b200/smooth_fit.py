@@ -57,8 +57,9 @@ class DiagonalOp(object):
     smooth_fit.py:613).  Only ``diagonal()`` / ``shape`` are needed by iterate_fit."""
 
     def __init__(self, d):
-        self._d = np.asarray(d, dtype=float)
-        self.shape = (self._d.size, self._d.size)
+        self._d = d if isinstance(d, torch.Tensor) else np.asarray(d, dtype=float)
+        n = int(self._d.numel()) if isinstance(d, torch.Tensor) else self._d.size
+        self.shape = (n, n)
 
     def diagonal(self):
         return self._d
@@ -115,12 +116,12 @@ def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, 
     comm = dist.comm if dist is not None else None
     n_data = int(G_data.N_eq)
     n_cols = int(Ip_c.shape[0])
-    E_all = 1. / np.asarray(TCinv.diagonal())
-    sigma_h, Ec_h = E_all[:n_data], E_all[n_data:]
     dev = _cabi.device()
     f64 = torch.float64
-    sigma = _cabi.to_dev(sigma_h, f64)
-    z = _cabi.to_dev(np.asarray(rhs[:n_data], dtype=float), f64)
+    E_all = 1. / _cabi.to_dev(TCinv.diagonal(), f64)          # row sigmas: data rows then constraint rows
+    rhs_d = _cabi.to_dev(rhs, f64)
+    sigma = E_all[:n_data].contiguous()
+    z = rhs_d[:n_data].contiguous()
     free_cols = np.unique(Ip_c.tocoo().row) if hasattr(Ip_c, 'tocoo') else np.asarray(Ip_c.free_cols)
     fixed_cols = np.setdiff1d(np.arange(n_cols), free_cols)
 
@@ -129,13 +130,16 @@ def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, 
     C_all = Gc._csr_device(col_N=n_cols, row_N=int(Gc.N_eq))
     c_lo, c_hi = (0, int(Gc.N_eq)) if dist is None else dist.shard(int(Gc.N_eq))
     C_loc = C_all if (c_lo, c_hi) == (0, int(Gc.N_eq)) else C_all.row_slice(c_lo, c_hi)
-    prior = _cabi.to_dev(np.asarray(rhs[n_data + c_lo:n_data + c_hi], dtype=float), f64)
-    Ec = _cabi.to_dev(Ec_h[c_lo:c_hi], f64)
+    prior = rhs_d[n_data + c_lo:n_data + c_hi].contiguous()
+    Ec = E_all[n_data + c_lo:n_data + c_hi].contiguous()
     solver = NormalSolver(G_csr, C_loc, z, prior, sigma, Ec, fixed_cols, dist)
     solver.set_profile(bool(args.get('profile_spmv')))
     stats = timing.setdefault('pcg', [])
 
-    in_TSE_d = _cabi.to_dev(np.asarray(in_TSE).astype(np.uint8), torch.uint8)
+    if isinstance(in_TSE, torch.Tensor):
+        in_TSE_d = _cabi.to_dev(in_TSE, torch.uint8).clone()
+    else:
+        in_TSE_d = _cabi.to_dev(np.asarray(in_TSE).astype(np.uint8), torch.uint8)
     if bias_model is None:
         bias_model = {}
     _edit_by_bias(data, np.zeros(n_cols), in_TSE_d, -1, bias_model, args)
@@ -231,16 +235,33 @@ def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, 
     return out
 
 
-def _grid_sums(Gt, cols, shape, vec):
-    """(G[:, cols]^T vec) reshaped to a grid -- the products parse_model takes (smooth_fit.py:339-345)."""
-    full = Gt.dot(vec)
-    return full[torch.as_tensor(cols, device=full.device)].cpu().numpy().reshape(shape)
+def _bias_statistics(b_dict, bias_id, r, tse, n_bias, dist):
+    """Per-bias residual statistics of parse_biases (bias_functions.py:140-155: nanstd of the residuals of
+    each bias group, raw and edited) as grouped two-pass reductions on the device instead of one masked pass
+    over all points per bias."""
+    ids = bias_id.to(torch.int64)
+    fin = torch.isfinite(r)
+    rr = torch.where(fin, r, torch.zeros_like(r))
+
+    def reduce(w):
+        t = torch.bincount(ids, weights=w, minlength=n_bias)[:n_bias]
+        return t if dist is None else dist.allreduce_sum(t)
+
+    for key_rms, key_n, wt in (('rms_data_raw', 'N_raw', torch.ones_like(r)), ('rms_data_edited', 'N_edited', tse.to(r.dtype))):
+        n_all = reduce(wt)                               # len(r[jj]) counts NaNs too
+        n_fin = reduce(wt * fin)
+        mean = reduce(wt * rr) / n_fin
+        dev = torch.where(fin, r - mean[ids], torch.zeros_like(r))
+        std = torch.sqrt(reduce(wt * dev * dev) / n_fin)
+        b_dict[key_n] = [int(v) for v in n_all.cpu().numpy()]
+        b_dict[key_rms] = [float(v) if c > 0 else np.nan for v, c in zip(std.cpu().numpy(), n_all.cpu().numpy())]
 
 
-def parse_model(m, m0, data, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args, dist=None):
-    """Reshape the solution into grids and compute per-node data counts / misfits and the constraint
-    residual summaries (smooth_fit.py:276-352).  The G^T products run on the GPU (lss_spmv on the
-    transposed CSR); with row sharding they are summed over ranks on the host."""
+def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args, dist=None):
+    """Reshape the solution into grids and compute per-node data counts / misfits, bias statistics and the
+    constraint residual summaries (smooth_fit.py:276-352).  ``dev_fields`` holds this rank's per-point
+    device arrays (z, sigma, z_est, three_sigma_edit, sigma_extra, bias_ID).  The G^T products run on the GPU
+    (lss_spmv on the transposed CSR); with row sharding the per-node sums are summed over ranks."""
     z0g, dzg = grids['z0'], grids['dz']
     m['z0'] = grid_data().from_dict({'x': z0g.ctrs[1], 'y': z0g.ctrs[0], 'cell_area': z0g.cell_area, 'mask': z0g.mask,
                                      'z0': np.reshape(m0[G_data.TOC['cols']['z0']], z0g.shape)})
@@ -251,8 +272,12 @@ def parse_model(m, m0, data, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_
         fields = {coord: ctr for coord, ctr in zip(op.dst_grid.coords, op.dst_grid.ctrs)}
         fields.update({'cell_area': op.dst_grid.cell_area, key: op.grid_prod(m0)})
         m[key] = grid_data().from_dict(fields)
+    f = dev_fields
+    tse = f['three_sigma_edit'].bool()
+    r = f['z'] - f['z_est']
     if len(bias_model.keys()) > 0:
-        m['bias'], m['slope_bias'] = parse_biases(m0, bias_model, args['bias_params'], data=data)
+        m['bias'], m['slope_bias'] = parse_biases(m0, bias_model, args['bias_params'])
+        _bias_statistics(m['bias'], f['bias_ID'], r, tse, len(bias_model['bias_ID_dict']), dist)
     m['all'] = m0
     m['extent'] = np.concatenate((z0g.bds[1], z0g.bds[0]))
     m['sensor_bias_grids'] = {}
@@ -267,32 +292,29 @@ def parse_model(m, m0, data, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_
             R[eq_type] = np.sum(rc[Gc.TOC['rows'][eq_type]] ** 2)
             RMS[eq_type] = np.sqrt(np.mean(ru[Gc.TOC['rows'][eq_type]] ** 2))
     # data counts and misfit maps: G^T applied to the edited-in indicator, r^2 and scaled r^2
-    tse = np.asarray(data.three_sigma_edit, dtype=bool)
-    r = np.where(tse, data.z - data.z_est, 0.)
+    r_in = torch.where(tse, r, torch.zeros_like(r))
     if args['sigma_extra_relax']:
-        rs = r / np.sqrt(data.sigma ** 2 + data.sigma_extra ** 2)
+        rs = r_in / torch.sqrt(f['sigma'] ** 2 + f['sigma_extra'] ** 2)
     else:
-        rs = r / data.sigma
-    Gt = G_data._csr_device(col_N=n_cols, row_N=int(data.size)).transpose()
-    vecs = {'count': tse.astype(float), 'misfit_scaled_rms': rs ** 2, 'misfit_rms': r ** 2}
+        rs = r_in / f['sigma']
+    Gt = G_data._csr_device(col_N=n_cols, row_N=int(r.numel())).transpose()
+    sums = {}
+    for key, vec in (('count', tse.to(torch.float64)), ('misfit_scaled_rms', rs * rs), ('misfit_rms', r_in * r_in)):
+        full = Gt.dot(vec.contiguous())
+        sums[key] = (full if dist is None else dist.allreduce_sum(full)).cpu().numpy()
     for ff in ['dz', 'z0']:
         cols = np.asarray(G_data.TOC['cols'][ff])
-        sums = {}
-        for key, vec in vecs.items():
-            part = _grid_sums(Gt, cols, grids[ff].shape, _cabi.to_dev(vec, torch.float64))
-            if dist is not None and dist.world > 1:
-                import torch.distributed as td
-                t = torch.from_numpy(part.copy())
-                t = t.cuda() if td.get_backend() == 'nccl' else t
-                td.all_reduce(t)
-                part = t.cpu().numpy()
-            sums[key] = part
-        count = sums['count']
+        count = sums['count'][cols].reshape(grids[ff].shape).copy()
         count[count == 0] = np.nan
         m[ff].assign({'count': count})
         with np.errstate(invalid='ignore'):
-            m[ff].assign({'misfit_scaled_rms': np.sqrt(sums['misfit_scaled_rms'] / count)})
-            m[ff].assign({'misfit_rms': np.sqrt(sums['misfit_rms'] / count)})
+            for key in ('misfit_scaled_rms', 'misfit_rms'):
+                m[ff].assign({key: np.sqrt(sums[key][cols].reshape(grids[ff].shape) / count)})
+    # chi^2 and RMS of the edited-in data residuals (smooth_fit.py:676-678)
+    tot = torch.stack([(rs * rs).sum(), (r_in * r_in).sum(), tse.sum().to(torch.float64)])
+    tot = (tot if dist is None else dist.allreduce_sum(tot)).cpu().numpy()
+    R['data'] = tot[0] if not args['sigma_extra_relax'] else float(((r_in / f['sigma']) ** 2).sum().item())
+    RMS['data'] = np.sqrt(tot[1] / tot[2]) if tot[2] > 0 else np.nan
 
 
 def _empty_result(m, E, data, grids, valid_data, timing, args):
@@ -300,13 +322,58 @@ def _empty_result(m, E, data, grids, valid_data, timing, args):
             'timing': timing, 'E_RMS': args['E_RMS']}
 
 
+def _field_dev(obj, name):
+    """A per-point field as a contiguous fp64 CUDA tensor (NumPy arrays are uploaded, CUDA tensors used as is)."""
+    v = getattr(obj, name)
+    if isinstance(v, torch.Tensor):
+        return _cabi.to_dev(v.reshape(-1), torch.float64)
+    return _cabi.to_dev(np.asarray(v, dtype=float).ravel(), torch.float64)
+
+
+def _assign_bias_ID_device(fields_d, bias_params, sigma_corr_d):
+    """assign_bias_ID (bias_functions.py:25-82) on device arrays.
+
+    Dense ranks of each parameter column (``lss_dense_rank_f64``: radix sort + head flags + scan, NaN -> -9999),
+    combined in mixed radix so that ascending combined rank == lexicographic order of the unique parameter rows,
+    ranked again to get consecutive IDs; E_bias = per-group nanmedian(sigma_corr) (``lss_group_median``).
+    Returns (bias_ID int32 CUDA tensor, bias_model dict as the reference builds it).
+    """
+    ranks, uniq = [], []
+    for p in bias_params:
+        r, u = _cabi.dense_rank(fields_d[p], nan_value=-9999.0)
+        ranks.append(r)
+        uniq.append(u)
+    comb = ranks[0].to(torch.int64)
+    for k in range(1, len(ranks)):
+        comb = comb * int(uniq[k].size) + ranks[k]
+    ids, ucomb = _cabi.dense_rank(comb.to(torch.float64), nan_value=-9999.0)
+    n_bias = int(ucomb.size)
+    e_bias = _cabi.group_median(ids, sigma_corr_d, n_bias).cpu().numpy()
+    model = {'E_bias': dict(), 'bias_param_dict': {p: list() for p in bias_params}, 'bias_ID_dict': dict()}
+    model['bias_param_dict']['ID'] = list()
+    for k, code in enumerate(ucomb.astype(np.int64)):
+        vals = []
+        for j in range(len(bias_params) - 1, -1, -1):
+            vals.append(uniq[j][code % uniq[j].size])
+            code //= uniq[j].size
+        vals = vals[::-1]
+        shown = [np.nan if v == -9999 else v for v in vals]
+        for j, p in enumerate(bias_params):
+            model['bias_param_dict'][p].append(vals[j])
+        model['bias_param_dict']['ID'].append(k)
+        model['bias_ID_dict'][k] = {p: shown[j] for j, p in enumerate(bias_params)}
+        model['E_bias'][k] = e_bias[k]
+    return ids, model
+
+
 def smooth_fit(**kwargs):
     """Fit z0(x, y) + dz(x, y, t) to point data with smoothness constraints and robust editing.
 
     Same call as the reference (smooth_fit.py:354-717).  ``data`` is any object with the
-    pointCollection.data interface (``lssurf_b200.point_data.data`` is provided).  Features outside
-    the hot-path scope (error propagation, mask files, priors, sensor / jitter grids,
-    averaging scales ...) raise NotImplementedError instead of being silently ignored.
+    pointCollection.data interface (``lssurf_b200.point_data.data`` is provided); its per-point fields may
+    be NumPy arrays (uploaded once) or CUDA tensors (used in place).  Features outside the hot-path scope
+    (error propagation, mask files, priors, sensor / jitter grids, averaging
+    scales ...) raise NotImplementedError instead of being silently ignored.
     """
     args = dict(DEFAULTS)
     args.update(kwargs)
@@ -322,7 +389,6 @@ def smooth_fit(**kwargs):
     verbose = args['VERBOSE'] and (dist is None or dist.rank == 0)
     args['VERBOSE'] = verbose
     data_in = args['data']
-    valid_data = np.isfinite(data_in.z)
     if 'sensor' not in data_in.fields:
         data_in.assign({'sensor': np.zeros(data_in.shape)})
     timing = dict()
@@ -330,33 +396,40 @@ def smooth_fit(**kwargs):
     tic = time()
     grids, bds = setup_grids(args)
 
-    # ---- host -> device: the point coordinates are uploaded once; validity comes from the
-    # interpolation kernel itself (fd_grid.validate_pts semantics, smooth_fit.py:423-425)
+    # ---- host -> device: every per-point field the fit needs is uploaded once; validity comes from the
+    # interpolation kernel itself (fd_grid.validate_pts semantics, smooth_fit.py:406, 423-425)
     f64 = torch.float64
-    coords = data_in.coords()
-    if len(coords) < 3:
+    if not all(f in data_in.fields for f in ('x', 'y', 'time')):
         raise ValueError('data must have x, y and time fields')
-    y_d, x_d, t_d = (_cabi.to_dev(np.asarray(c, dtype=float).ravel(), f64) for c in coords)
+    y_d, x_d, t_d, z_d, s_d = (_field_dev(data_in, f) for f in ('y', 'x', 'time', 'z', 'sigma'))
+    extra_d = {}
+    if args['bias_params'] is not None:
+        extra_d = {p: _field_dev(data_in, p) for p in list(args['bias_params']) + ['sigma_corr']}
+    tse_d = _field_dev(data_in, 'three_sigma_edit') if 'three_sigma_edit' in data_in.fields else None
     op_z0 = lin_op(grids['z0'], name='interp_z')
     op_dz = lin_op(grids['dz'], name='interp_dz')
     rz = _cabi.interp_coo(grids['z0'].as_struct(), [y_d, x_d])
     rd = _cabi.interp_coo(grids['dz'].as_struct(), [y_d, x_d, t_d])
-    if rz[4] or rd[4] or not np.all(valid_data):
-        valid_data = valid_data & rz[3].cpu().numpy().astype(bool) & rd[3].cpu().numpy().astype(bool)
+    finite = torch.isfinite(z_d)
+    if rz[4] or rd[4] or not bool(finite.all().item()):
+        keep = finite & rz[3].bool() & rd[3].bool()
+        valid_data = keep.cpu().numpy()
         if not np.any(valid_data):
             if verbose:
                 print("smooth_fit: no valid data")
             return _empty_result(m, E, None, grids, valid_data, timing, args)
         data = data_in.copy_subset(valid_data)
-        keep = _cabi.to_dev(valid_data)
-        y_d, x_d, t_d = y_d[keep].contiguous(), x_d[keep].contiguous(), t_d[keep].contiguous()
+        y_d, x_d, t_d, z_d, s_d = (a[keep].contiguous() for a in (y_d, x_d, t_d, z_d, s_d))
+        extra_d = {k: v[keep].contiguous() for k, v in extra_d.items()}
+        tse_d = None if tse_d is None else tse_d[keep].contiguous()
         rz = rd = None
     else:
+        valid_data = np.ones(int(z_d.numel()), dtype=bool)
         data = data_in.view() if hasattr(data_in, 'view') else data_in.copy_subset(valid_data)
-    if data.size == 0:
+    n_all = int(z_d.numel())
+    if n_all == 0:
         print("\tsmooth_fit.py: after masking, no data found")
         return _empty_result(m, E, data, grids, valid_data, timing, args)
-    n_all = int(data.size)
 
     # sigma_extra groups (smooth_fit.py:443-453)
     if args['sigma_extra_keys'] is not None:
@@ -371,15 +444,20 @@ def smooth_fit(**kwargs):
 
     # bias IDs are global (unique parameter combinations over ALL points), assigned before sharding
     bias_model = {}
+    bias_id_d = None
     if args['bias_params'] is not None:
-        data, bias_model = assign_bias_ID(data, args['bias_params'], bias_filter=args['bias_filter'])
+        if args['bias_filter'] is not None:
+            raise NotImplementedError('bias_filter is outside the GPU hot-path scope')
+        bias_id_d, bias_model = _assign_bias_ID_device(extra_d, args['bias_params'], extra_d['sigma_corr'])
+        data.assign({'bias_ID': bias_id_d.cpu().numpy().astype(float)})
         if args['bias_nsigma_edit']:
             bias_model['bias_param_dict']['edited'] = np.zeros_like(bias_model['bias_param_dict']['ID'], dtype=bool)
 
     # ---- this rank's block of points
     lo, hi = (0, n_all) if dist is None else dist.shard(n_all)
-    local = data if (lo, hi) == (0, n_all) else data.copy_subset(slice(lo, hi))
-    if rz is not None and (lo, hi) == (0, n_all):
+    whole = (lo, hi) == (0, n_all)
+    local = data if whole else data.copy_subset(slice(lo, hi))
+    if rz is not None and whole:
         # all points valid: the validity pass already produced the interpolation triplets
         for op, res, g in ((op_z0, rz, grids['z0']), (op_dz, rd, grids['dz'])):
             op._set_device(res[0], res[1], res[2])
@@ -390,27 +468,42 @@ def smooth_fit(**kwargs):
             op._update_shape()
     else:
         rz = rd = None
-        ys, xs, ts = y_d[lo:hi].contiguous(), x_d[lo:hi].contiguous(), t_d[lo:hi].contiguous()
-        op_z0.interp_mtx([ys, xs])
-        op_dz.interp_mtx([ys, xs, ts])
+        op_z0.interp_mtx([y_d[lo:hi].contiguous(), x_d[lo:hi].contiguous()])
+        op_dz.interp_mtx([y_d[lo:hi].contiguous(), x_d[lo:hi].contiguous(), t_d[lo:hi].contiguous()])
     G_data = op_z0
     G_data.add(op_dz)
     del rz, rd
+    z_loc, s_loc = z_d[lo:hi].contiguous(), s_d[lo:hi].contiguous()
 
     constraint_op_list = []
     if verbose:
         print(f"smooth_fit: E_RMS={args['E_RMS']}")
     setup_smoothness_constraints(grids, constraint_op_list, args['E_RMS'], args['mask_scale'])
     if args['bias_params'] is not None:
-        setup_bias_fit(local, bias_model, G_data, constraint_op_list, bias_param_name='bias_ID',
-                       n_bias=int(np.max(data.bias_ID)) + 1)
+        n_bias = len(bias_model['bias_ID_dict'])
+        col_0 = G_data.col_N
+        col_N = col_0 + n_bias
+        ids_loc = bias_id_d[lo:hi]
+        G_bias = lin_op(name='data_bias', col_0=col_0, col_N=col_N).data_bias(
+            torch.arange(hi - lo, dtype=torch.int32, device=ids_loc.device), col=(ids_loc + int(col_0)).contiguous())
+        ii = np.arange(n_bias, dtype=int)
+        Gc_bias = lin_op(name='constraint_data_bias', col_0=col_0, col_N=col_N).data_bias(ii, col=col_0 + ii)
+        for key in bias_model['bias_ID_dict']:
+            bias_model['bias_ID_dict'][key]['col'] = col_0 + key
+        Gc_bias.expected = np.array([bias_model['E_bias'][k] for k in ii])
+        if np.any(Gc_bias.expected == 0):
+            raise ValueError('found an zero value in the expected biases')
+        constraint_op_list.append(Gc_bias)
+        G_data.add(G_bias)
         if args['bias_edit_vals'] is not None:
             want = np.c_[[args['bias_edit_vals'][k] for k in args['bias_edit_vals']]].T.tolist()
             have = np.c_[[bias_model['bias_param_dict'][k] for k in args['bias_edit_vals']]].T.tolist()
             for row in want:
                 bias_model['bias_param_dict']['edited'][have.index(row)] = True
             bad = [bias_model['bias_param_dict']['ID'][i] for i in np.flatnonzero(bias_model['bias_param_dict']['edited'])]
-            local.three_sigma_edit[np.isin(local.bias_ID, bad)] = False
+            if tse_d is None:
+                tse_d = torch.ones(n_all, dtype=f64, device=z_d.device)
+            tse_d[torch.isin(bias_id_d, _cabi.to_dev(np.asarray(bad, dtype=np.int32)))] = 0.
     for op in constraint_op_list:
         if op.prior is None:
             op.prior = np.zeros_like(op.expected)
@@ -419,24 +512,24 @@ def smooth_fit(**kwargs):
     Ec = np.zeros(Gc.N_eq)
     for op in constraint_op_list:
         Ec[Gc.TOC['rows'][op.name]] = op.expected
-    Ed = np.asarray(local.sigma, dtype=float).ravel()
-    if np.any(Ed == 0):
+    if bool((s_loc == 0).any().item()):
         raise ValueError('zero value found in data sigma')
     if np.any(Ec == 0):
         raise ValueError('zero value found in constraint sigma')
-    TCinv = DiagonalOp(1. / np.concatenate((Ed, Ec)))
-    rhs = np.concatenate((np.asarray(local.z, dtype=float).ravel(), np.concatenate([op.prior for op in constraint_op_list])))
+    # TCinv and rhs stay on the device for the data rows (iterate_fit accepts tensors or NumPy)
+    TCinv = DiagonalOp(torch.cat((1. / s_loc, _cabi.to_dev(1. / Ec, f64))))
+    rhs = torch.cat((z_loc, _cabi.to_dev(np.concatenate([op.prior for op in constraint_op_list]), f64)))
     Ip_c = build_reference_epoch_matrix(G_data, Gc, grids, args['reference_epoch'])
     timing['setup'] = time() - tic
 
-    if "three_sigma_edit" in local.fields:
-        in_TSE = np.asarray(local.three_sigma_edit) > 0.01
+    if tse_d is not None:
+        in_TSE = (tse_d[lo:hi] > 0.01)
     else:
-        in_TSE = np.ones(G_data.N_eq, dtype=bool)
+        in_TSE = torch.ones(hi - lo, dtype=torch.bool, device=z_d.device)
     if verbose:
         print("initial: %d:" % (n_all - 1), flush=True)
     if args['return_fit_objects']:
-        return {'data': local, 'G_data': G_data, 'Gc': Gc, 'grids': grids, 'Ed': Ed, 'Ec': Ec}
+        return {'data': local, 'G_data': G_data, 'Gc': Gc, 'grids': grids, 'Ed': s_loc.cpu().numpy(), 'Ec': Ec}
 
     averaging_ops = {}
     if args['max_iterations'] > 0:
@@ -447,7 +540,8 @@ def smooth_fit(**kwargs):
                                                        {k: v[lo:hi] for k, v in args['sigma_extra_masks'].items()})
         timing['iteration'] = time() - tic_iteration
         # model estimate of every data point, G_data . m0 (smooth_fit.py:662); the CSR is already cached
-        z_est = G_data._csr_device(col_N=m0.size, row_N=int(local.size)).dot(_cabi.to_dev(m0, f64)).cpu().numpy()
+        z_est_d = G_data._csr_device(col_N=m0.size, row_N=hi - lo).dot(_cabi.to_dev(m0, f64))
+        z_est = z_est_d.cpu().numpy()
         if dist is not None and dist.world > 1:
             in_TSE_all, sigma_extra_all, z_est_all = (dist.gather_rows(a) for a in (in_TSE, sigma_extra, z_est))
         else:
@@ -456,15 +550,14 @@ def smooth_fit(**kwargs):
         data.assign({'three_sigma_edit': in_TSE_all})
         data.assign({'sigma_extra': sigma_extra_all})
         data.assign({'z_est': np.reshape(z_est_all, data.shape)})
-        local.assign({'three_sigma_edit': in_TSE, 'sigma_extra': sigma_extra, 'z_est': z_est})
+        if local is not data:
+            local.assign({'three_sigma_edit': in_TSE, 'sigma_extra': sigma_extra, 'z_est': z_est})
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
-        parse_model(m, m0, local, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args, dist=dist)
-        if 'bias' in m and local is not data:
-            m['bias'], m['slope_bias'] = parse_biases(m0, bias_model, args['bias_params'], data=data)
-        sel = data.three_sigma_edit == 1
-        r_sel = data.z_est[sel] - data.z[sel]
-        R['data'] = np.sum((r_sel / data.sigma[sel]) ** 2)
-        RMS['data'] = np.sqrt(np.mean(r_sel ** 2))
+        dev_fields = {'z': z_loc, 'sigma': s_loc, 'z_est': z_est_d, 'three_sigma_edit': _cabi.to_dev(in_TSE),
+                      'sigma_extra': _cabi.to_dev(sigma_extra, f64),
+                      'bias_ID': None if bias_id_d is None else bias_id_d[lo:hi]}
+        parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args,
+                    dist=dist if (dist is not None and dist.world > 1) else None)
     else:
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
     return {'m': m, 'E': E, 'data': data, 'grids': grids, 'valid_data': valid_data, 'TOC': Gc.TOC, 'R': R, 'RMS': RMS,

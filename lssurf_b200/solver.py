@@ -57,7 +57,7 @@ class NormalSolver(object):
         st = (C.c_double * 6)()
         _cabi.check(_cabi.lib().lss_solver_stats(self.handle, st))
         self.last = dict(iterations=it.value, relres=rel.value, ms=st[0], ms_A=st[1], ms_At=st[2], n_apply=int(st[3]),
-                         launches=int(st[4]), nnz=int(st[5]))
+                         launches=int(st[4]), nnz=int(st[5]), rows=int(self.A.shape[0]))
         return self.x
 
     def residual(self, x, z, out=None):
