@@ -94,10 +94,19 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *t
 int radix_sort_pairs(uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint32_t *vals_b, int64_t n, int bit_lo,
                      int n_bits, int iota_first, uint64_t **keys_out, uint32_t **vals_out, cudaStream_t stream);
 
-// y = A x family (spmv.cu), rows [0, n_rows).
+// y = A x family (spmv.cu), rows [0, n_rows).  A plan caches what depends only on the sparsity structure
+// (the first row of every non-zero tile) and the per-tile carry buffers; without one they are rebuilt per call.
+struct SpmvPlan {
+    int n_tiles;
+    int *bounds;
+    double *carry_val;
+    int *carry_row;
+};
+int spmv_plan_create(SpmvPlan *plan, int64_t n_rows, const int32_t *indptr, int64_t nnz, cudaStream_t stream);
+void spmv_plan_destroy(SpmvPlan *plan);
 int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data,
-                const double *x, double *y, int mode, const double *s, int64_t nnz, const double *stop,
-                cudaStream_t stream, int64_t *launches);
+                const double *x, double *y, int mode, const double *s, int64_t nnz, const SpmvPlan *plan,
+                const double *stop, cudaStream_t stream, int64_t *launches);
 
 }  // namespace lss
 

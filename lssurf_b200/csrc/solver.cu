@@ -220,6 +220,7 @@ struct lss_solver {
     int64_t n_apply;
     int64_t launches;
     std::vector<cudaEvent_t> *prof_events;
+    lss::SpmvPlan plan_a, plan_at;
 };
 
 static int dev_alloc(double **p, int64_t n) {
@@ -233,6 +234,8 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     double **ptrs[] = {&s->w, &s->u, &s->buf, &s->r, &s->p, &s->minv, &s->g, &s->diag, &s->part2, &s->scal};
     for (auto pp : ptrs)
         if (*pp) cudaFree(*pp);
+    lss::spmv_plan_destroy(&s->plan_a);
+    lss::spmv_plan_destroy(&s->plan_at);
     if (s->fixed) cudaFree(s->fixed);
     if (s->host_scal) cudaFreeHost(s->host_scal);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -283,6 +286,8 @@ extern "C" int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t 
         if (n_fixed > 0) mark_fixed_kernel<<<stride_grid(n_fixed, VEC_BLOCK), VEC_BLOCK, 0, s->stream>>>(n_fixed, fixed_cols, s->fixed);
         if (cudaGetLastError() != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: launch failed");
     }
+    if (rc == LSS_OK) rc = spmv_plan_create(&s->plan_a, n_rows, indptr, s->nnz, s->stream);
+    if (rc == LSS_OK) rc = spmv_plan_create(&s->plan_at, n_cols, t_indptr, s->nnz, s->stream);
     if (rc != LSS_OK) { lss_solver_destroy(s); return rc; }
     s->profile = getenv("LSS_PROFILE_SPMV") != nullptr;
     *solver = s;
@@ -300,9 +305,9 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
         }
         LSS_CUDA(cudaEventRecord(e0, st));
     }
-    LSS_TRY(spmv_launch(s->n_rows, s->indptr, s->indices, s->data, v, s->u, LSS_SPMV_SCALE, s->w, s->nnz, stop, st, &s->launches));
+    LSS_TRY(spmv_launch(s->n_rows, s->indptr, s->indices, s->data, v, s->u, LSS_SPMV_SCALE, s->w, s->nnz, &s->plan_a, stop, st, &s->launches));
     if (s->profile) LSS_CUDA(cudaEventRecord(e1, st));
-    LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->buf, LSS_SPMV_PLAIN, nullptr, s->nnz, stop, st, &s->launches));
+    LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->buf, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, stop, st, &s->launches));
     if (s->profile) LSS_CUDA(cudaEventRecord(e2, st));
     int64_t n_red = s->n_cols;
     if (with_dot) {
@@ -325,7 +330,7 @@ extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
         mul_kernel<<<stride_grid(s->n_rows, VEC_BLOCK), VEC_BLOCK, 0, st>>>(s->n_rows, s->w, s->rhs, s->u);
         LSS_LAUNCH_CHECK();
     }
-    LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->g, LSS_SPMV_PLAIN, nullptr, s->nnz, nullptr, st, nullptr));
+    LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->g, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, nullptr, st, nullptr));
     LSS_TRY(comm_allreduce(s->comm, s->g, s->n_cols, 0, 0, st));
     // Jacobi preconditioner from diag(A^T W A)
     diag_kernel<<<stride_grid(s->n_cols * 32, 256, 16), 256, 0, st>>>(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->w, s->diag);

@@ -35,18 +35,26 @@ __device__ __forceinline__ int64_t lower_bound_i32(const int *__restrict__ a, in
     return lo;
 }
 
+// bounds[t] = first row whose entries start at or after non-zero t*TILE (bounds[n_tiles] = n_rows): the rows a
+// tile owns are [bounds[t], bounds[t+1]).  Depends only on the sparsity structure: computed once per matrix.
+__global__ void __launch_bounds__(256)
+spmv_tile_bounds_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, int n_tiles, int *__restrict__ bounds) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    bounds[t] = (t == n_tiles) ? (int)n_rows : (int)lower_bound_i32(indptr, n_rows, (int64_t)t * SPMV_TILE);
+}
+
 __global__ void __launch_bounds__(SPMV_BLOCK)
 spmv_tile_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, const int *__restrict__ indices,
                  const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y, int mode,
                  const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row,
-                 const double *__restrict__ stop) {
-    if (stop && *stop != 0.0) return;   // solver converged: the queued tail of the batch is a no-op
+                 const int *__restrict__ tile_bounds, const double *__restrict__ stop) {
     __shared__ double prod[SPMV_TILE];
-    __shared__ int64_t sh_rows[2];
     const int64_t k0 = (int64_t)blockIdx.x * SPMV_TILE;
     const int64_t k1 = (k0 + SPMV_TILE < nnz) ? k0 + SPMV_TILE : nnz;
-    if (threadIdx.x == 0) sh_rows[0] = lower_bound_i32(indptr, n_rows, k0);
-    if (threadIdx.x == 32) sh_rows[1] = (k1 == nnz) ? n_rows : lower_bound_i32(indptr, n_rows, k1);
+    // issued first, consumed after the staging loads are in flight (no serialised round trip per CTA)
+    const double stop_v = stop ? *reinterpret_cast<const volatile double *>(stop) : 0.0;
+    const int64_t r_lo = tile_bounds[blockIdx.x], r_hi = tile_bounds[blockIdx.x + 1];
     // stage the products: coalesced streaming loads of the matrix, gathered loads of x
 #pragma unroll
     for (int j = 0; j < SPMV_IPT; ++j) {
@@ -55,8 +63,8 @@ spmv_tile_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, co
         if (k < k1) p = ldg_stream(data + k) * __ldg(x + ldg_stream(indices + k));
         prod[j * SPMV_BLOCK + threadIdx.x] = p;
     }
+    if (stop_v != 0.0) return;   // solver converged: the queued tail of the batch is a no-op (uniform per launch)
     __syncthreads();
-    const int64_t r_lo = sh_rows[0], r_hi = sh_rows[1];
     // carry-in: the row that started in an earlier tile and still has entries here
     const bool has_carry = r_lo > 0 && (int64_t)indptr[r_lo] > k0;   // r_lo <= n_rows always
     const int64_t n_virtual = (r_hi - r_lo) + 1;                      // virtual row 0 is the carry-in
@@ -127,8 +135,32 @@ spmv_empty_kernel(int64_t n_rows, double *__restrict__ y, int mode, const double
         y[r] = epilogue(0.0, mode, s, r);
 }
 
+int spmv_plan_create(SpmvPlan *plan, int64_t n_rows, const int32_t *indptr, int64_t nnz, cudaStream_t stream) {
+    plan->n_tiles = nnz > 0 ? ceil_div(nnz, SPMV_TILE) : 0;
+    plan->bounds = nullptr;
+    plan->carry_val = nullptr;
+    plan->carry_row = nullptr;
+    if (plan->n_tiles == 0) return LSS_OK;
+    LSS_CUDA(cudaMalloc((void **)&plan->bounds, sizeof(int) * (plan->n_tiles + 1)));
+    LSS_CUDA(cudaMalloc((void **)&plan->carry_val, sizeof(double) * plan->n_tiles));
+    LSS_CUDA(cudaMalloc((void **)&plan->carry_row, sizeof(int) * plan->n_tiles));
+    spmv_tile_bounds_kernel<<<ceil_div(plan->n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, plan->n_tiles, plan->bounds);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+void spmv_plan_destroy(SpmvPlan *plan) {
+    if (plan->bounds) cudaFree(plan->bounds);
+    if (plan->carry_val) cudaFree(plan->carry_val);
+    if (plan->carry_row) cudaFree(plan->carry_row);
+    plan->bounds = nullptr;
+    plan->carry_val = nullptr;
+    plan->carry_row = nullptr;
+}
+
 int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x,
-                double *y, int mode, const double *s, int64_t nnz, const double *stop, cudaStream_t stream, int64_t *launches) {
+                double *y, int mode, const double *s, int64_t nnz, const SpmvPlan *plan, const double *stop,
+                cudaStream_t stream, int64_t *launches) {
     if (n_rows <= 0) return LSS_OK;
     if (nnz == 0) {
         spmv_empty_kernel<<<stride_grid(n_rows, 256), 256, 0, stream>>>(n_rows, y, mode, s);
@@ -137,12 +169,23 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
         return LSS_OK;
     }
     const int n_tiles = ceil_div(nnz, SPMV_TILE);
-    Scratch cv, cr;
-    LSS_CUDA(cv.alloc(sizeof(double) * n_tiles, stream));
-    LSS_CUDA(cr.alloc(sizeof(int) * n_tiles, stream));
-    spmv_tile_kernel<<<n_tiles, SPMV_BLOCK, 0, stream>>>(n_rows, nnz, indptr, indices, data, x, y, mode, s, cv.as<double>(), cr.as<int>(), stop);
+    Scratch cv, cr, tb;
+    double *carry_val;
+    int *carry_row, *bounds;
+    if (plan && plan->bounds) {
+        carry_val = plan->carry_val; carry_row = plan->carry_row; bounds = plan->bounds;
+    } else {
+        LSS_CUDA(cv.alloc(sizeof(double) * n_tiles, stream));
+        LSS_CUDA(cr.alloc(sizeof(int) * n_tiles, stream));
+        LSS_CUDA(tb.alloc(sizeof(int) * (n_tiles + 1), stream));
+        carry_val = cv.as<double>(); carry_row = cr.as<int>(); bounds = tb.as<int>();
+        spmv_tile_bounds_kernel<<<ceil_div(n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, n_tiles, bounds);
+        LSS_LAUNCH_CHECK();
+        if (launches) *launches += 1;
+    }
+    spmv_tile_kernel<<<n_tiles, SPMV_BLOCK, 0, stream>>>(n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop);
     LSS_LAUNCH_CHECK();
-    spmv_fixup_kernel<<<ceil_div(n_tiles, 256), 256, 0, stream>>>(n_tiles, cv.as<double>(), cr.as<int>(), y, mode, s, stop);
+    spmv_fixup_kernel<<<ceil_div(n_tiles, 256), 256, 0, stream>>>(n_tiles, carry_val, carry_row, y, mode, s, stop);
     LSS_LAUNCH_CHECK();
     if (launches) *launches += 2;
     return LSS_OK;
@@ -162,5 +205,5 @@ extern "C" int lss_spmv(int64_t n_rows, int64_t n_cols, const int32_t *indptr, c
     int nnz = 0;
     LSS_CUDA(cudaMemcpyAsync(&nnz, indptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
     LSS_CUDA(cudaStreamSynchronize(st));
-    return spmv_launch(n_rows, indptr, indices, data, x, y, mode, s, nnz, nullptr, st, nullptr);
+    return spmv_launch(n_rows, indptr, indices, data, x, y, mode, s, nnz, nullptr, nullptr, st, nullptr);
 }

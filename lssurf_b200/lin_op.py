@@ -222,7 +222,7 @@ class lin_op(object):
         self._update_shape()
         return self
 
-    def data_bias(self, ind=None, val=None, col=None, DOF=None):
+    def data_bias(self, ind=None, val=None, col=None, DOF=None, _toc=None):
         """One entry per listed row: picks (or adds) a single model parameter (lin_op.py:504-522)."""
         if col is None:
             col = self.col_N
@@ -238,8 +238,11 @@ class lin_op(object):
         else:
             val_d = _cabi.to_dev(np.asarray(val).ravel(), torch.float64) if not isinstance(val, torch.Tensor) else val
         self._set_device(ind_d.contiguous(), col_d.contiguous(), val_d.contiguous())
-        self.TOC['rows'] = {self.name: torch.unique(ind_d).cpu().numpy().astype(int)}
-        self.TOC['cols'] = {self.name: torch.unique(col_d).cpu().numpy().astype(int)}
+        if _toc is not None:       # caller already knows the distinct rows / columns (avoids sorting 1e7 indices)
+            self.TOC['rows'], self.TOC['cols'] = {self.name: _toc[0]}, {self.name: _toc[1]}
+        else:
+            self.TOC['rows'] = {self.name: torch.unique(ind_d).cpu().numpy().astype(int)}
+            self.TOC['cols'] = {self.name: torch.unique(col_d).cpu().numpy().astype(int)}
         self.N_eq = int(ind_d.max().item()) + 1 if ind_d.numel() else 0
         self._update_shape()
         return self

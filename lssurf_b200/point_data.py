@@ -10,6 +10,20 @@ import copy as _copy
 import numpy as np
 
 
+def _as_field(val):
+    """NumPy array for host data; CUDA / CPU torch tensors are kept as they are (device-resident inputs)."""
+    if type(val).__module__.startswith('torch'):
+        return val
+    return np.asarray(val)
+
+
+def _shape_size(val):
+    if type(val).__module__.startswith('torch'):
+        return tuple(val.shape), int(val.numel())
+    a = np.asarray(val)
+    return a.shape, a.size
+
+
 class data(object):
     def __init__(self, fields=None, **kw):
         self.fields = [] if fields is None else list(fields)
@@ -18,15 +32,14 @@ class data(object):
 
     def __update_size_and_shape__(self):
         if self.fields:
-            first = np.asarray(getattr(self, self.fields[0]))
-            self.shape, self.size = first.shape, first.size
+            self.shape, self.size = _shape_size(getattr(self, self.fields[0]))
         else:
             self.shape, self.size = (0,), 0
         return self
 
     def from_dict(self, fields_dict, **kw):
         for key, val in fields_dict.items():
-            setattr(self, key, np.asarray(val))
+            setattr(self, key, _as_field(val))
             if key not in self.fields:
                 self.fields.append(key)
         return self.__update_size_and_shape__()
@@ -60,7 +73,8 @@ class data(object):
     def copy_subset(self, index, datasets=None, **kw):
         out = data()
         for f in (self.fields if datasets is None else datasets):
-            out.assign({f: np.asarray(getattr(self, f))[index].copy()})
+            v = _as_field(getattr(self, f))[index]
+            out.assign({f: v.clone() if hasattr(v, 'clone') else v.copy()})
         return out
 
     def view(self):
@@ -72,7 +86,7 @@ class data(object):
 
     def index(self, index, **kw):
         for f in self.fields:
-            setattr(self, f, np.asarray(getattr(self, f))[index])
+            setattr(self, f, _as_field(getattr(self, f))[index])
         return self.__update_size_and_shape__()
 
     def __getitem__(self, index):

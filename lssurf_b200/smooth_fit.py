@@ -485,7 +485,8 @@ def smooth_fit(**kwargs):
         col_N = col_0 + n_bias
         ids_loc = bias_id_d[lo:hi]
         G_bias = lin_op(name='data_bias', col_0=col_0, col_N=col_N).data_bias(
-            torch.arange(hi - lo, dtype=torch.int32, device=ids_loc.device), col=(ids_loc + int(col_0)).contiguous())
+            torch.arange(hi - lo, dtype=torch.int32, device=ids_loc.device), col=(ids_loc + int(col_0)).contiguous(),
+            _toc=(np.arange(hi - lo, dtype=int), np.arange(col_0, col_N, dtype=int)))
         ii = np.arange(n_bias, dtype=int)
         Gc_bias = lin_op(name='constraint_data_bias', col_0=col_0, col_N=col_N).data_bias(ii, col=col_0 + ii)
         for key in bias_model['bias_ID_dict']:
