@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument('--max-outer', type=int, default=None, help='profiling only: cap the edit iterations')
     ap.add_argument('--cg-maxiter', type=int, default=None, help='profiling only: cap the CG iterations per solve')
     ap.add_argument('--skip-e2e', action='store_true', help='profiling only: no host-input pass')
+    ap.add_argument('--stages', action='store_true', help='add an untimed pass reporting wall time per stage')
     return ap.parse_args()
 
 
@@ -190,10 +191,10 @@ def run_b200(a):
     h2d = sum(host[f].numel() * 8 for f in fields)
     dist_arg = dist if world > 1 else None
 
-    def fit(inputs, profile):
+    def fit(inputs, profile, stages=False):
         D = L.point_data.data().from_dict({f: (inputs[f] if isinstance(inputs[f], torch.Tensor) and inputs[f].is_cuda
                                                else inputs[f].numpy()) for f in fields})
-        return L.smooth_fit(data=D, VERBOSE=False, dist=dist_arg, profile_spmv=profile, **kw)
+        return L.smooth_fit(data=D, VERBOSE=False, dist=dist_arg, profile_spmv=profile, time_stages=stages, **kw)
 
     # ---- warm-up (device-resident steps, plus one host-input step)
     for _ in range(a.warmup):
@@ -228,6 +229,10 @@ def run_b200(a):
     t_e2e = max(time.perf_counter() - w0, 1e-9)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    stage_times = None
+    if a.stages:                                   # untimed diagnostic pass: wall time per stage with device syncs
+        Sd = fit(host, False, stages=True)
+        stage_times = {k: round(v, 4) for k, v in Sd['timing']['stages'].items()}
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -274,7 +279,9 @@ def run_b200(a):
                 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
                 'solve': {'outer_iterations': outer, 'cg_iterations_per_step': iters, 'pcg_ms_per_step': solve_ms,
                           'ms_per_cg_iteration': solve_ms / max(iters, 1), 'cg_rtol': kw.get('cg_rtol', 1e-12),
-                          'in_TSE': int(np.sum(S['data'].three_sigma_edit)), 'unknowns': n_cols, 'nnz_A_per_rank': nnz}}
+                          'in_TSE': int(np.sum(S['data'].three_sigma_edit)), 'unknowns': n_cols, 'nnz_A_per_rank': nnz,
+                          'cg_iterations': [p['iterations'] for p in pcg[:int(outer)]]},
+                'stages_s': stage_times}
         print(json.dumps(line), flush=True)
     dist.destroy()
     if world > 1:

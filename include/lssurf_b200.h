@@ -119,6 +119,18 @@ int lss_group_median(const int32_t *ids, const double *vals, int64_t n, int32_t 
 int lss_spmv(int64_t n_rows, int64_t n_cols, const int32_t *indptr, const int32_t *indices, const double *data,
              const double *x, double *y, int32_t mode, const double *s, void *stream);
 
+/* Same product with the structure-dependent set-up (first row of every non-zero tile, carry buffers) done
+ * once: for matrices that are multiplied many times (the edit loop's residual and G^T products). */
+typedef struct lss_spmv_plan lss_spmv_plan_t;
+int lss_spmv_plan_create(lss_spmv_plan_t **plan, int64_t n_rows, const int32_t *indptr, void *stream);
+int lss_spmv_plan_destroy(lss_spmv_plan_t *plan);
+int lss_spmv_planned(lss_spmv_plan_t *plan, int64_t n_rows, const int32_t *indptr, const int32_t *indices,
+                     const double *data, const double *x, double *y, int32_t mode, const double *s, void *stream);
+
+/* Tuning knobs.  "spmv_variant": CTA shape of the CSR product kernel (index into a fixed table of
+ * (threads, non-zeros per thread) pairs); affects speed only, never results. */
+int lss_set_option(const char *name, int32_t value);
+
 /* ------------------------------------------------------------------ multi-GPU communicator */
 
 typedef struct lss_comm lss_comm_t;

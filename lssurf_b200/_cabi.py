@@ -46,6 +46,10 @@ SIGNATURES = {
     'lss_dense_rank_f64': [_vp, _i64, _f64, _vp, _pf64, _i64, _pi64, _vp],
     'lss_group_median': [_vp, _vp, _i64, _i32, _vp, _vp],
     'lss_spmv': [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    'lss_spmv_plan_create': [C.POINTER(_vp), _i64, _vp, _vp],
+    'lss_spmv_plan_destroy': [_vp],
+    'lss_spmv_planned': [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    'lss_set_option': [C.c_char_p, _i32],
     'lss_comm_unique_id': [C.c_char_p],
     'lss_comm_create': [C.POINTER(_vp), C.c_char_p, _i32, _i32],
     'lss_comm_destroy': [_vp],
@@ -122,6 +126,27 @@ def to_dev(a, dtype=None):
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.contiguous()
+
+
+_pinned = {}
+
+
+def to_host(t):
+    """CUDA tensor -> fresh NumPy array through a cached pinned staging buffer (DMA at PCIe speed instead
+    of a pageable copy); the staging buffer is reused, the returned array is owned by the caller."""
+    if not t.is_cuda:
+        return t.numpy().copy()
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes < (1 << 20):
+        return t.cpu().numpy()
+    buf = _pinned.get('buf')
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 26), dtype=torch.uint8, pin_memory=True)
+        _pinned['buf'] = buf
+    view = buf[:nbytes].view(t.dtype).reshape(t.shape)
+    view.copy_(t, non_blocking=False)
+    return view.numpy().copy()
 
 
 def grid_struct(shape, stride, lo, hi, delta, col_0):
@@ -240,6 +265,10 @@ def group_median(ids, vals, n_groups):
     return out
 
 
+def set_option(name, value):
+    check(load().lss_set_option(name.encode(), int(value)))
+
+
 def launch_count():
     return int(load().lss_launch_count())
 
@@ -248,6 +277,29 @@ def spmv(indptr, indices, data, x, n_rows, n_cols, mode=SPMV_PLAIN, s=None, out=
     L = lib()
     y = out if out is not None else torch.empty(n_rows, dtype=torch.float64, device=device())
     check(L.lss_spmv(n_rows, n_cols, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), mode, ptr(s), stream()))
+    return y
+
+
+class SpmvPlan(object):
+    """Owner of an lss_spmv_plan (structure-dependent set-up of the tiled CSR product)."""
+
+    def __init__(self, indptr, n_rows):
+        self.h = C.c_void_p(0)
+        check(lib().lss_spmv_plan_create(C.byref(self.h), int(n_rows), ptr(indptr), stream()))
+
+    def __del__(self):
+        try:
+            if self.h:
+                load().lss_spmv_plan_destroy(self.h)
+                self.h = C.c_void_p(0)
+        except Exception:
+            pass
+
+
+def spmv_planned(plan, indptr, indices, data, x, n_rows, mode=SPMV_PLAIN, s=None, out=None):
+    L = lib()
+    y = out if out is not None else torch.empty(n_rows, dtype=torch.float64, device=device())
+    check(L.lss_spmv_planned(plan.h, n_rows, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), mode, ptr(s), stream()))
     return y
 
 

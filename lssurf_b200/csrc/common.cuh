@@ -53,7 +53,21 @@ struct Scratch {
     cudaError_t alloc(size_t bytes, cudaStream_t stream) {
         s = stream;
         if (bytes == 0) bytes = 16;
+        configure_pool();
         return cudaMallocAsync(&p, bytes, stream);
+    }
+    // Keep freed scratch in the stream-ordered pool across synchronisations (the default threshold of 0
+    // returns it to the driver at every sync, which makes each later allocation a real cudaMalloc).
+    static void configure_pool() {
+        static int done_for = -1;
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        done_for = dev;
     }
     template <typename T>
     T *as() { return reinterpret_cast<T *>(p); }
@@ -98,6 +112,7 @@ int radix_sort_pairs(uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint3
 // (the first row of every non-zero tile) and the per-tile carry buffers; without one they are rebuilt per call.
 struct SpmvPlan {
     int n_tiles;
+    int tile;
     int *bounds;
     double *carry_val;
     int *carry_row;

@@ -219,7 +219,8 @@ struct lss_solver {
     double ms_total, ms_a, ms_at;
     int64_t n_apply;
     int64_t launches;
-    std::vector<cudaEvent_t> *prof_events;
+    std::vector<cudaEvent_t> *prof_events;   // fixed pool: 3 events per operator application, 2 batches deep
+    int64_t n_prof;
     lss::SpmvPlan plan_a, plan_at;
 };
 
@@ -295,20 +296,27 @@ extern "C" int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t 
 }
 
 // q(buf[0:n]) = A^T (w .* (A v)), partials of v.q appended at buf[n:], summed over ranks.
-static int apply_normal(lss_solver *s, const double *v, bool with_dot, const double *stop) {
+constexpr int kBatch = 16;   // CG iterations enqueued between two looks at the convergence flag
+
+static int apply_normal(lss_solver *s, const double *v, bool with_dot, const double *stop, int prof_slot = -1) {
     cudaStream_t st = s->stream;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-    if (s->profile) {
-        for (cudaEvent_t *e : {&e0, &e1, &e2}) {
-            LSS_CUDA(cudaEventCreate(e));
-            s->prof_events->push_back(*e);
+    const bool timed = s->profile && prof_slot >= 0;
+    if (timed) {
+        while ((int)s->prof_events->size() < 3 * 2 * kBatch) {   // created once, reused for every batch
+            cudaEvent_t e;
+            LSS_CUDA(cudaEventCreate(&e));
+            s->prof_events->push_back(e);
         }
+        e0 = (*s->prof_events)[3 * prof_slot];
+        e1 = (*s->prof_events)[3 * prof_slot + 1];
+        e2 = (*s->prof_events)[3 * prof_slot + 2];
         LSS_CUDA(cudaEventRecord(e0, st));
     }
     LSS_TRY(spmv_launch(s->n_rows, s->indptr, s->indices, s->data, v, s->u, LSS_SPMV_SCALE, s->w, s->nnz, &s->plan_a, stop, st, &s->launches));
-    if (s->profile) LSS_CUDA(cudaEventRecord(e1, st));
+    if (timed) LSS_CUDA(cudaEventRecord(e1, st));
     LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->buf, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, stop, st, &s->launches));
-    if (s->profile) LSS_CUDA(cudaEventRecord(e2, st));
+    if (timed) LSS_CUDA(cudaEventRecord(e2, st));
     int64_t n_red = s->n_cols;
     if (with_dot) {
         dot_partials_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(s->n_cols, v, s->buf, s->buf + s->n_cols, stop);
@@ -351,8 +359,8 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     const int64_t n = s->n_cols;
     s->launches = 0;
     s->n_apply = 0;
-    for (auto e : *s->prof_events) cudaEventDestroy(e);
-    s->prof_events->clear();
+    s->ms_a = s->ms_at = 0.0;
+    s->n_prof = 0;
     LSS_CUDA(cudaEventRecord(s->ev0, st));
     // r = g - N x0
     zero_fixed_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->fixed, x);
@@ -363,15 +371,30 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     cg_scalar_kernel<<<1, VEC_BLOCK, 0, st>>>(s->part2, VEC_GRID, s->scal, S_RZ0, rtol, max_iter);
     LSS_LAUNCH_CHECK();
     s->launches += 3;
-    const int batch = 16;
+    const int batch = kBatch;
     int issued = 0, parity = 0, slot = 0;
     bool done = false;
     bool pending[2] = {false, false};
+    int in_slot[2] = {0, 0}, base_it[2] = {0, 0};
+    auto harvest = [&](int sl) {     // the batch's completion event has been waited for: its timing events are final
+        // iterations enqueued after convergence are no-ops on the device: leave them out of the averages
+        const int real = (int)s->host_scal[sl * S_COUNT + S_ITERS] - base_it[sl];
+        for (int k = 0; k < in_slot[sl] && k < real && s->profile; ++k) {
+            float a = 0.f, b = 0.f;
+            const int e = 3 * (sl * kBatch + k);
+            cudaEventElapsedTime(&a, (*s->prof_events)[e], (*s->prof_events)[e + 1]);
+            cudaEventElapsedTime(&b, (*s->prof_events)[e + 1], (*s->prof_events)[e + 2]);
+            s->ms_a += a;
+            s->ms_at += b;
+            s->n_prof += 1;
+        }
+        in_slot[sl] = 0;
+    };
     while (!done) {
         // enqueue one batch, then look at the flag the PREVIOUS batch left behind
         const int todo = (max_iter - issued) < batch ? (max_iter - issued) : batch;
         for (int k = 0; k < todo; ++k) {
-            LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity));
+            LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity, slot * kBatch + k));
             cg_update_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->buf, s->buf + n, VEC_GRID, s->minv, s->p, x, s->r, s->part2, s->scal, parity);
             LSS_LAUNCH_CHECK();
             cg_direction_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->r, s->minv, s->p, s->part2, VEC_GRID, s->scal, parity);
@@ -379,7 +402,9 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
             s->launches += 2;
             parity ^= 1;
         }
+        base_it[slot] = issued;
         issued += todo;
+        in_slot[slot] = todo;
         LSS_CUDA(cudaMemcpyAsync(s->host_scal + slot * S_COUNT, s->scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
         LSS_CUDA(cudaEventRecord(s->ev_batch[slot], st));
         pending[slot] = true;
@@ -387,6 +412,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
         if (pending[prev]) {
             LSS_CUDA(cudaEventSynchronize(s->ev_batch[prev]));
             pending[prev] = false;
+            harvest(prev);
             if (s->host_scal[prev * S_COUNT + S_DONE0] != 0.0 || s->host_scal[prev * S_COUNT + S_DONE1] != 0.0) done = true;
         }
         if (!done && (issued >= max_iter || todo == 0)) {
@@ -402,17 +428,8 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->ms_total = ms;
-    s->ms_a = s->ms_at = 0.0;
-    if (s->profile) {
-        const std::vector<cudaEvent_t> &ev = *s->prof_events;
-        for (size_t i = 0; i + 3 <= ev.size(); i += 3) {
-            float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, ev[i], ev[i + 1]);
-            cudaEventElapsedTime(&b, ev[i + 1], ev[i + 2]);
-            s->ms_a += a;
-            s->ms_at += b;
-        }
-    }
+    harvest(0);
+    harvest(1);
     const double bn = s->host_scal[S_BNORM], rzl = s->host_scal[S_RZ_LAST];
     if (iters_h) *iters_h = (int32_t)s->host_scal[S_ITERS];
     if (relres_h) *relres_h = bn > 0.0 ? sqrt(rzl / bn) : 0.0;
@@ -430,7 +447,7 @@ extern "C" int lss_solver_stats(lss_solver_t *s, double *stats_h) {
     stats_h[0] = s->ms_total;
     stats_h[1] = s->ms_a;
     stats_h[2] = s->ms_at;
-    stats_h[3] = (double)s->n_apply;
+    stats_h[3] = (double)(s->profile ? s->n_prof : s->n_apply);   // applications behind stats_h[1], [2] when profiling
     stats_h[4] = (double)s->launches;
     stats_h[5] = (double)s->nnz;
     return LSS_OK;

@@ -6,18 +6,37 @@
 //
 // Work decomposition is by NON-ZEROS, not rows: CTA t owns non-zeros [t*TILE, (t+1)*TILE), so the
 // same kernel is balanced for G (12-13 entries per row), for the constraint stencils (2-8 per
-// row) and for G^T, whose rows range from empty (63 % of the grid columns see no data) to
+// row) and for G^T, whose rows range from empty (most grid columns between tracks see no data) to
 // >10^4 entries (bias columns).  Products are staged in shared memory, rows are then reduced
 // from shared memory by one thread (short rows) or one warp (long rows) each.  Rows cut by a tile
 // boundary are completed by a tiny fix-up kernel from per-tile carries, so the result is
-// deterministic (no atomics).
+// deterministic (no atomics).  The first row of every tile depends only on the sparsity structure
+// and is computed once per matrix (SpmvPlan), not searched for by every CTA of every product.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lss {
 
-constexpr int SPMV_BLOCK = 256;
-constexpr int SPMV_IPT = 8;
-constexpr int SPMV_TILE = SPMV_BLOCK * SPMV_IPT;  // 2048 non-zeros, 16 KB of staged products
+// (threads per CTA, non-zeros per thread); selectable at run time for tuning (lss_set_option("spmv_variant")).
+struct SpmvShape { int block, ipt; };
+static const SpmvShape kShapes[] = {{256, 8}, {128, 8}, {128, 16}, {256, 4}, {512, 4}, {256, 16}, {128, 4},
+                                    {128, 8}, {128, 8}, {256, 8}, {128, 4}};   // 7..10: persistent kernels
+constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
+static int g_variant = -1;
+
+static int current_variant() {
+    if (g_variant < 0) {
+        const char *e = getenv("LSS_SPMV_VARIANT");
+        g_variant = e ? atoi(e) : 7;   // persistent 128 x 8 (tools/spmv_bench.py, profiles/spmv_variants_r01.md)
+        if (g_variant < 0 || g_variant >= kNumShapes) g_variant = 0;
+    }
+    return g_variant;
+}
+int spmv_tile_size() {
+    const SpmvShape &s = kShapes[current_variant()];
+    return s.block * s.ipt;
+}
 
 __device__ __forceinline__ double epilogue(double v, int mode, const double *__restrict__ s, int64_t r) {
     if (mode == LSS_SPMV_SCALE) return s[r] * v;
@@ -25,7 +44,7 @@ __device__ __forceinline__ double epilogue(double v, int mode, const double *__r
     return v;
 }
 
-// first r in [0, n] with a[r] >= key  (a is non-decreasing, length n + 1 is assumed readable up to a[n])
+// first r in [0, n] with a[r] >= key  (a is non-decreasing and readable up to a[n])
 __device__ __forceinline__ int64_t lower_bound_i32(const int *__restrict__ a, int64_t n, int64_t key) {
     int64_t lo = 0, hi = n + 1;
     while (lo < hi) {
@@ -35,43 +54,26 @@ __device__ __forceinline__ int64_t lower_bound_i32(const int *__restrict__ a, in
     return lo;
 }
 
-// bounds[t] = first row whose entries start at or after non-zero t*TILE (bounds[n_tiles] = n_rows): the rows a
-// tile owns are [bounds[t], bounds[t+1]).  Depends only on the sparsity structure: computed once per matrix.
+// bounds[t] = first row whose entries start at or after non-zero t*tile (bounds[n_tiles] = n_rows): the rows a
+// tile owns are [bounds[t], bounds[t+1]).
 __global__ void __launch_bounds__(256)
-spmv_tile_bounds_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, int n_tiles, int *__restrict__ bounds) {
+spmv_tile_bounds_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, int n_tiles, int tile, int *__restrict__ bounds) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
-    bounds[t] = (t == n_tiles) ? (int)n_rows : (int)lower_bound_i32(indptr, n_rows, (int64_t)t * SPMV_TILE);
+    bounds[t] = (t == n_tiles) ? (int)n_rows : (int)lower_bound_i32(indptr, n_rows, (int64_t)t * tile);
 }
 
-__global__ void __launch_bounds__(SPMV_BLOCK)
-spmv_tile_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, const int *__restrict__ indices,
-                 const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y, int mode,
-                 const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row,
-                 const int *__restrict__ tile_bounds, const double *__restrict__ stop) {
-    __shared__ double prod[SPMV_TILE];
-    const int64_t k0 = (int64_t)blockIdx.x * SPMV_TILE;
-    const int64_t k1 = (k0 + SPMV_TILE < nnz) ? k0 + SPMV_TILE : nnz;
-    // issued first, consumed after the staging loads are in flight (no serialised round trip per CTA)
-    const double stop_v = stop ? *reinterpret_cast<const volatile double *>(stop) : 0.0;
-    const int64_t r_lo = tile_bounds[blockIdx.x], r_hi = tile_bounds[blockIdx.x + 1];
-    // stage the products: coalesced streaming loads of the matrix, gathered loads of x
-#pragma unroll
-    for (int j = 0; j < SPMV_IPT; ++j) {
-        const int64_t k = k0 + j * SPMV_BLOCK + threadIdx.x;
-        double p = 0.0;
-        if (k < k1) p = ldg_stream(data + k) * __ldg(x + ldg_stream(indices + k));
-        prod[j * SPMV_BLOCK + threadIdx.x] = p;
-    }
-    if (stop_v != 0.0) return;   // solver converged: the queued tail of the batch is a no-op (uniform per launch)
-    __syncthreads();
+template <int BLOCK>
+__device__ __forceinline__ void reduce_rows(const double *__restrict__ prod, int tile, int64_t k0, int64_t k1, int64_t r_lo, int64_t r_hi,
+                                            const int *__restrict__ indptr, double *__restrict__ y, int mode,
+                                            const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row) {
     // carry-in: the row that started in an earlier tile and still has entries here
-    const bool has_carry = r_lo > 0 && (int64_t)indptr[r_lo] > k0;   // r_lo <= n_rows always
+    const bool has_carry = r_lo > 0 && (int64_t)indptr[r_lo] > k0;
     const int64_t n_virtual = (r_hi - r_lo) + 1;                      // virtual row 0 is the carry-in
-    if (n_virtual <= 2 * (SPMV_BLOCK / 32)) {
+    if (n_virtual <= 2 * (BLOCK / 32)) {
         // few, long rows: one warp per row
         const int w = threadIdx.x >> 5;
-        for (int64_t v = w; v < n_virtual; v += SPMV_BLOCK / 32) {
+        for (int64_t v = w; v < n_virtual; v += BLOCK / 32) {
             int64_t b, e, r = r_lo + v - 1;
             if (v == 0) {
                 if (!has_carry) continue;
@@ -87,12 +89,12 @@ spmv_tile_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, co
             for (int64_t k = b - k0 + lane_id(); k < e - k0; k += 32) acc += prod[k];
             acc = warp_sum(acc);
             if (lane_id() == 0) {
-                if (v == 0) carry_val[blockIdx.x] = acc;
+                if (v == 0) carry_val[tile] = acc;
                 else y[r] = open ? acc : epilogue(acc, mode, s, r);
             }
         }
     } else {
-        for (int64_t v = threadIdx.x; v < n_virtual; v += SPMV_BLOCK) {
+        for (int64_t v = threadIdx.x; v < n_virtual; v += BLOCK) {
             int64_t b, e, r = r_lo + v - 1;
             if (v == 0) {
                 if (!has_carry) continue;
@@ -106,11 +108,90 @@ spmv_tile_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, co
             if (open) e = k1;
             double acc = 0.0;
             for (int64_t k = b - k0; k < e - k0; ++k) acc += prod[k];
-            if (v == 0) carry_val[blockIdx.x] = acc;
+            if (v == 0) carry_val[tile] = acc;
             else y[r] = open ? acc : epilogue(acc, mode, s, r);
         }
     }
-    if (threadIdx.x == 0) carry_row[blockIdx.x] = has_carry ? (int)(r_lo - 1) : -1;
+    if (threadIdx.x == 0) carry_row[tile] = has_carry ? (int)(r_lo - 1) : -1;
+}
+
+template <int BLOCK, int IPT>
+__global__ void __launch_bounds__(BLOCK)
+spmv_tile_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, const int *__restrict__ indices,
+                 const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y, int mode,
+                 const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row,
+                 const int *__restrict__ tile_bounds, const double *__restrict__ stop) {
+    constexpr int TILE = BLOCK * IPT;
+    __shared__ double prod[TILE];
+    const int64_t k0 = (int64_t)blockIdx.x * TILE;
+    const int64_t k1 = (k0 + TILE < nnz) ? k0 + TILE : nnz;
+    // issued first, consumed after the staging loads are in flight (no serialised round trip per CTA)
+    const double stop_v = stop ? *reinterpret_cast<const volatile double *>(stop) : 0.0;
+    const int64_t r_lo = tile_bounds[blockIdx.x], r_hi = tile_bounds[blockIdx.x + 1];
+    // stage the products: coalesced streaming loads of the matrix, gathered loads of x
+    {
+        int col[IPT];
+        double val[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int64_t k = k0 + j * BLOCK + threadIdx.x;
+            const bool in = k < k1;
+            col[j] = in ? ldg_stream(indices + k) : 0;
+            val[j] = in ? ldg_stream(data + k) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) prod[j * BLOCK + threadIdx.x] = val[j] * __ldg(x + col[j]);
+    }
+    if (stop_v != 0.0) return;   // solver converged: the queued tail of the batch is a no-op (uniform per launch)
+    __syncthreads();
+    reduce_rows<BLOCK>(prod, blockIdx.x, k0, k1, r_lo, r_hi, indptr, y, mode, s, carry_val, carry_row);
+}
+
+// Persistent variant: CTAs loop over tiles (static round robin) and prefetch the NEXT tile's matrix stream
+// (column indices + values, the HBM traffic) into registers before reducing the current tile's rows, so the
+// DRAM pipe stays busy during the shared-memory phase.  DBUF double-buffers the staged products (one barrier
+// per tile instead of two).
+template <int BLOCK, int IPT, bool DBUF>
+__global__ void __launch_bounds__(BLOCK)
+spmv_persistent_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__restrict__ indptr, const int *__restrict__ indices,
+                       const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y, int mode,
+                       const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row,
+                       const int *__restrict__ tile_bounds, const double *__restrict__ stop) {
+    constexpr int TILE = BLOCK * IPT;
+    __shared__ double prod_s[DBUF ? 2 : 1][TILE];
+    if (stop && *stop != 0.0) return;
+    int col[IPT];
+    double val[IPT];
+    int t = blockIdx.x;
+    if (t >= n_tiles) return;
+    auto fetch = [&](int tile) {
+        const int64_t k0 = (int64_t)tile * TILE;
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int64_t k = k0 + j * BLOCK + threadIdx.x;
+            const bool in = k < nnz;
+            col[j] = in ? ldg_stream(indices + k) : 0;
+            val[j] = in ? ldg_stream(data + k) : 0.0;
+        }
+    };
+    fetch(t);
+    int buf = 0;
+    for (; t < n_tiles; t += gridDim.x) {
+        const int64_t k0 = (int64_t)t * TILE;
+        const int64_t k1 = (k0 + TILE < nnz) ? k0 + TILE : nnz;
+        const int64_t r_lo = tile_bounds[t], r_hi = tile_bounds[t + 1];
+        double *prod = prod_s[buf];
+        double xg[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) xg[j] = __ldg(x + col[j]);
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) prod[j * BLOCK + threadIdx.x] = val[j] * xg[j];
+        const int nt = t + gridDim.x;
+        if (nt < n_tiles) fetch(nt);            // in flight during the barrier and the row reduction below
+        __syncthreads();
+        reduce_rows<BLOCK>(prod, t, k0, k1, r_lo, r_hi, indptr, y, mode, s, carry_val, carry_row);
+        if (DBUF) buf ^= 1; else __syncthreads();
+    }
 }
 
 // Completes rows cut by tile boundaries: the first carry tile of each such row adds the carries of
@@ -136,7 +217,8 @@ spmv_empty_kernel(int64_t n_rows, double *__restrict__ y, int mode, const double
 }
 
 int spmv_plan_create(SpmvPlan *plan, int64_t n_rows, const int32_t *indptr, int64_t nnz, cudaStream_t stream) {
-    plan->n_tiles = nnz > 0 ? ceil_div(nnz, SPMV_TILE) : 0;
+    plan->tile = spmv_tile_size();
+    plan->n_tiles = nnz > 0 ? ceil_div(nnz, plan->tile) : 0;
     plan->bounds = nullptr;
     plan->carry_val = nullptr;
     plan->carry_row = nullptr;
@@ -144,7 +226,7 @@ int spmv_plan_create(SpmvPlan *plan, int64_t n_rows, const int32_t *indptr, int6
     LSS_CUDA(cudaMalloc((void **)&plan->bounds, sizeof(int) * (plan->n_tiles + 1)));
     LSS_CUDA(cudaMalloc((void **)&plan->carry_val, sizeof(double) * plan->n_tiles));
     LSS_CUDA(cudaMalloc((void **)&plan->carry_row, sizeof(int) * plan->n_tiles));
-    spmv_tile_bounds_kernel<<<ceil_div(plan->n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, plan->n_tiles, plan->bounds);
+    spmv_tile_bounds_kernel<<<ceil_div(plan->n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, plan->n_tiles, plan->tile, plan->bounds);
     LSS_LAUNCH_CHECK();
     return LSS_OK;
 }
@@ -158,6 +240,27 @@ void spmv_plan_destroy(SpmvPlan *plan) {
     plan->carry_row = nullptr;
 }
 
+template <int BLOCK, int IPT>
+static void launch_tile(int n_tiles, cudaStream_t stream, int64_t n_rows, int64_t nnz, const int *indptr, const int *indices,
+                        const double *data, const double *x, double *y, int mode, const double *s, double *cv, int *cr,
+                        const int *bounds, const double *stop) {
+    spmv_tile_kernel<BLOCK, IPT><<<n_tiles, BLOCK, 0, stream>>>(n_rows, nnz, indptr, indices, data, x, y, mode, s, cv, cr, bounds, stop);
+}
+
+template <int BLOCK, int IPT, bool DBUF>
+static void launch_persistent(int n_tiles, cudaStream_t stream, int64_t n_rows, int64_t nnz, const int *indptr, const int *indices,
+                              const double *data, const double *x, double *y, int mode, const double *s, double *cv, int *cr,
+                              const int *bounds, const double *stop) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_persistent_kernel<BLOCK, IPT, DBUF>, BLOCK, 0);
+        if (per_sm < 1) per_sm = 1;
+    }
+    const int grid = n_tiles < kSMs * per_sm ? n_tiles : kSMs * per_sm;   // one resident wave: a multiple of the SM count
+    spmv_persistent_kernel<BLOCK, IPT, DBUF><<<grid, BLOCK, 0, stream>>>(n_rows, nnz, n_tiles, indptr, indices, data, x, y, mode, s,
+                                                                         cv, cr, bounds, stop);
+}
+
 int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x,
                 double *y, int mode, const double *s, int64_t nnz, const SpmvPlan *plan, const double *stop,
                 cudaStream_t stream, int64_t *launches) {
@@ -168,22 +271,39 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
         if (launches) *launches += 1;
         return LSS_OK;
     }
-    const int n_tiles = ceil_div(nnz, SPMV_TILE);
+    const int variant = current_variant();
+    const int tile = kShapes[variant].block * kShapes[variant].ipt;
+    const int n_tiles = ceil_div(nnz, tile);
     Scratch cv, cr, tb;
     double *carry_val;
     int *carry_row, *bounds;
-    if (plan && plan->bounds) {
+    if (plan && plan->bounds && plan->tile == tile) {
         carry_val = plan->carry_val; carry_row = plan->carry_row; bounds = plan->bounds;
     } else {
         LSS_CUDA(cv.alloc(sizeof(double) * n_tiles, stream));
         LSS_CUDA(cr.alloc(sizeof(int) * n_tiles, stream));
         LSS_CUDA(tb.alloc(sizeof(int) * (n_tiles + 1), stream));
         carry_val = cv.as<double>(); carry_row = cr.as<int>(); bounds = tb.as<int>();
-        spmv_tile_bounds_kernel<<<ceil_div(n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, n_tiles, bounds);
+        spmv_tile_bounds_kernel<<<ceil_div(n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, n_tiles, tile, bounds);
         LSS_LAUNCH_CHECK();
         if (launches) *launches += 1;
     }
-    spmv_tile_kernel<<<n_tiles, SPMV_BLOCK, 0, stream>>>(n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop);
+#define LSS_SPMV_CASE(V, B, I)                                                                                     \
+    case V: launch_tile<B, I>(n_tiles, stream, n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop); break;
+    switch (variant) {
+        LSS_SPMV_CASE(0, 256, 8)
+        LSS_SPMV_CASE(1, 128, 8)
+        LSS_SPMV_CASE(2, 128, 16)
+        LSS_SPMV_CASE(3, 256, 4)
+        LSS_SPMV_CASE(4, 512, 4)
+        LSS_SPMV_CASE(5, 256, 16)
+        case 6: launch_tile<128, 4>(n_tiles, stream, n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop); break;
+        case 7: launch_persistent<128, 8, false>(n_tiles, stream, n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop); break;
+        case 8: launch_persistent<128, 8, true>(n_tiles, stream, n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop); break;
+        case 9: launch_persistent<256, 8, false>(n_tiles, stream, n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop); break;
+        default: launch_persistent<128, 4, true>(n_tiles, stream, n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop); break;
+    }
+#undef LSS_SPMV_CASE
     LSS_LAUNCH_CHECK();
     spmv_fixup_kernel<<<ceil_div(n_tiles, 256), 256, 0, stream>>>(n_tiles, carry_val, carry_row, y, mode, s, stop);
     LSS_LAUNCH_CHECK();
@@ -194,6 +314,51 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
 }  // namespace lss
 
 using namespace lss;
+
+extern "C" int lss_set_option(const char *name, int32_t value) {
+    if (name && strcmp(name, "spmv_variant") == 0) {
+        if (value < 0 || value >= kNumShapes) return fail(LSS_EINVAL, "spmv_variant must be in [0, %d)", kNumShapes);
+        g_variant = value;
+        return LSS_OK;
+    }
+    return fail(LSS_EINVAL, "unknown option %s", name ? name : "(null)");
+}
+
+struct lss_spmv_plan {
+    lss::SpmvPlan p;
+    int64_t nnz;
+};
+
+extern "C" int lss_spmv_plan_create(lss_spmv_plan **plan, int64_t n_rows, const int32_t *indptr, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!plan || n_rows < 0) return fail(LSS_EINVAL, "spmv_plan_create: bad arguments");
+    int nnz = 0;
+    if (n_rows > 0) {
+        LSS_CUDA(cudaMemcpyAsync(&nnz, indptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+    }
+    lss_spmv_plan *pl = new lss_spmv_plan();
+    pl->nnz = nnz;
+    int rc = spmv_plan_create(&pl->p, n_rows, indptr, nnz, st);
+    if (rc != LSS_OK) { delete pl; return rc; }
+    *plan = pl;
+    return LSS_OK;
+}
+
+extern "C" int lss_spmv_plan_destroy(lss_spmv_plan *plan) {
+    if (!plan) return LSS_OK;
+    spmv_plan_destroy(&plan->p);
+    delete plan;
+    return LSS_OK;
+}
+
+extern "C" int lss_spmv_planned(lss_spmv_plan *plan, int64_t n_rows, const int32_t *indptr, const int32_t *indices,
+                                const double *data, const double *x, double *y, int32_t mode, const double *s, void *stream) {
+    if (!plan) return fail(LSS_EINVAL, "spmv_planned: null plan");
+    if (mode < 0 || mode > 2) return fail(LSS_EINVAL, "spmv: unknown mode %d", mode);
+    if (mode != LSS_SPMV_PLAIN && !s) return fail(LSS_EINVAL, "spmv: mode %d needs the vector s", mode);
+    return spmv_launch(n_rows, indptr, indices, data, x, y, mode, s, plan->nnz, &plan->p, nullptr, (cudaStream_t)stream, nullptr);
+}
 
 extern "C" int lss_spmv(int64_t n_rows, int64_t n_cols, const int32_t *indptr, const int32_t *indices, const double *data,
                         const double *x, double *y, int32_t mode, const double *s, void *stream) {

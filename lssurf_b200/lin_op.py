@@ -34,6 +34,7 @@ class DeviceCSR(object):
         self.indptr, self.indices, self.data = indptr, indices, data
         self.shape = (int(shape[0]), int(shape[1]))
         self._T = None
+        self._plan = None
 
     @property
     def nnz(self):
@@ -48,7 +49,9 @@ class DeviceCSR(object):
 
     def dot(self, x, mode=_cabi.SPMV_PLAIN, s=None, out=None):
         """y = A x on the device (x: CUDA fp64 tensor)."""
-        return _cabi.spmv(self.indptr, self.indices, self.data, x, self.shape[0], self.shape[1], mode, s, out)
+        if self._plan is None:
+            self._plan = _cabi.SpmvPlan(self.indptr, self.shape[0])
+        return _cabi.spmv_planned(self._plan, self.indptr, self.indices, self.data, x, self.shape[0], mode, s, out)
 
     def row_slice(self, lo, hi):
         """Rows [lo, hi) as a new DeviceCSR (used to shard rows over ranks)."""

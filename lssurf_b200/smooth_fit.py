@@ -45,11 +45,30 @@ DEFAULTS = {
     'VERBOSE': True, 'DEBUG': False,
     # solver controls (new; defaults chosen for 1e-6 relative-L2 parity with a direct solve)
     'cg_rtol': 1e-12, 'cg_maxiter': 50000, 'dist': None, 'profile_spmv': False, 'history': None,
+    'time_stages': False,
 }
 
 _UNSUPPORTED = ('compute_E', 'mask_file', 'mask_update_function', 'sigma_extra_bin_spacing', 'prior_args',
                 'prior_edge_args', 'data_slope_sensors', 'sensor_grid_bias_params', 'lagrangian_coords',
                 'constraint_scaling_maps', 'avg_masks', 'z0_average_scale', 'DEM_tol')
+
+
+class _Stages(object):
+    """Optional per-stage wall times with a device synchronise at each boundary (``time_stages=True``)."""
+
+    def __init__(self, on, sink):
+        self.on, self.sink, self.t = on, sink, time()
+        if on:
+            torch.cuda.synchronize()
+            self.t = time()
+
+    def mark(self, name):
+        if not self.on:
+            return
+        torch.cuda.synchronize()
+        now = time()
+        self.sink[name] = self.sink.get(name, 0.) + (now - self.t)
+        self.t = now
 
 
 class DiagonalOp(object):
@@ -132,9 +151,14 @@ def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, 
     C_loc = C_all if (c_lo, c_hi) == (0, int(Gc.N_eq)) else C_all.row_slice(c_lo, c_hi)
     prior = rhs_d[n_data + c_lo:n_data + c_hi].contiguous()
     Ec = E_all[n_data + c_lo:n_data + c_hi].contiguous()
+    st = _Stages(bool(args.get('time_stages')), timing.setdefault('stages', {}))
+    st.mark('it:prep')
+    G_csr = G_csr
+    st.mark('it:csr')
     solver = NormalSolver(G_csr, C_loc, z, prior, sigma, Ec, fixed_cols, dist)
     solver.set_profile(bool(args.get('profile_spmv')))
     stats = timing.setdefault('pcg', [])
+    st.mark('it:solver_setup(vstack+transpose)')
 
     if isinstance(in_TSE, torch.Tensor):
         in_TSE_d = _cabi.to_dev(in_TSE, torch.uint8).clone()
@@ -162,6 +186,7 @@ def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, 
         if relax and args['VERBOSE']:
             print('smooth_fit.iterate_fit: relaxing errors by sigma_extra')
         solver.set_rows(in_TSE_d, sigma_extra if relax else None)
+        st.mark('it:set_weights')
         if args['VERBOSE']:
             print("starting qr solve for iteration %d at %s" % (iteration, ctime()), flush=True)
         tic = time()
@@ -174,12 +199,16 @@ def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, 
             print('\tpcg: %d iterations, relres=%.2e, %.1f ms' % (solver.last['iterations'], solver.last['relres'],
                                                                   solver.last['ms']), flush=True)
         # residual over ALL data rows, edited or not (smooth_fit.py:146)
+        st.mark('it:pcg')
         solver.residual(x, z, out=r_data)
+        st.mark('it:residual')
         if last_iteration:
             break
         sigma_extra, se_values = sigma_extra_device(r_data, sigma, in_TSE_d, groups, comm, out=sigma_extra)
+        st.mark('it:sigma_extra')
         in_TSE_last = in_TSE_d
         in_TSE_d, est = _cabi.edit_mask(r_data, sigma, sigma_extra, 3.0, comm)
+        st.mark('it:edit_mask')
         timing.setdefault('near_threshold', []).append(est['near_threshold'])
         if args.get('history') is not None:      # per-iteration tap for parity tests
             args['history'].append(dict(iteration=iteration, m0=m0.copy(), sigma_extra=dict(se_values),
@@ -229,9 +258,11 @@ def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, 
                 last_iteration = True
         if iteration == args['max_iterations'] - 2:
             last_iteration = True
-    rs_data = (r_data / sigma).cpu().numpy()
-    out = (m0, sigma_extra.cpu().numpy(), in_TSE_d.cpu().numpy().astype(bool), rs_data)
+    st.mark('it:other')
+    rs_data = _cabi.to_host(r_data / sigma)
+    out = (m0, _cabi.to_host(sigma_extra), _cabi.to_host(in_TSE_d).astype(bool), rs_data)
     solver.close()
+    st.mark('it:outputs_d2h')
     return out
 
 
@@ -394,7 +425,9 @@ def smooth_fit(**kwargs):
     timing = dict()
     m, E, R, RMS = {}, {}, {}, {}
     tic = time()
+    stages = _Stages(args['time_stages'], timing.setdefault('stages', {}))
     grids, bds = setup_grids(args)
+    stages.mark('setup_grids')
 
     # ---- host -> device: every per-point field the fit needs is uploaded once; validity comes from the
     # interpolation kernel itself (fd_grid.validate_pts semantics, smooth_fit.py:406, 423-425)
@@ -406,6 +439,7 @@ def smooth_fit(**kwargs):
     if args['bias_params'] is not None:
         extra_d = {p: _field_dev(data_in, p) for p in list(args['bias_params']) + ['sigma_corr']}
     tse_d = _field_dev(data_in, 'three_sigma_edit') if 'three_sigma_edit' in data_in.fields else None
+    stages.mark('upload')
     op_z0 = lin_op(grids['z0'], name='interp_z')
     op_dz = lin_op(grids['dz'], name='interp_dz')
     rz = _cabi.interp_coo(grids['z0'].as_struct(), [y_d, x_d])
@@ -431,6 +465,7 @@ def smooth_fit(**kwargs):
         print("\tsmooth_fit.py: after masking, no data found")
         return _empty_result(m, E, data, grids, valid_data, timing, args)
 
+    stages.mark('interp+valid')
     # sigma_extra groups (smooth_fit.py:443-453)
     if args['sigma_extra_keys'] is not None:
         args['sigma_extra_masks'] = {}
@@ -449,10 +484,11 @@ def smooth_fit(**kwargs):
         if args['bias_filter'] is not None:
             raise NotImplementedError('bias_filter is outside the GPU hot-path scope')
         bias_id_d, bias_model = _assign_bias_ID_device(extra_d, args['bias_params'], extra_d['sigma_corr'])
-        data.assign({'bias_ID': bias_id_d.cpu().numpy().astype(float)})
+        data.assign({'bias_ID': _cabi.to_host(bias_id_d).astype(float)})
         if args['bias_nsigma_edit']:
             bias_model['bias_param_dict']['edited'] = np.zeros_like(bias_model['bias_param_dict']['ID'], dtype=bool)
 
+    stages.mark('bias_ids')
     # ---- this rank's block of points
     lo, hi = (0, n_all) if dist is None else dist.shard(n_all)
     whole = (lo, hi) == (0, n_all)
@@ -475,6 +511,7 @@ def smooth_fit(**kwargs):
     del rz, rd
     z_loc, s_loc = z_d[lo:hi].contiguous(), s_d[lo:hi].contiguous()
 
+    stages.mark('G_data')
     constraint_op_list = []
     if verbose:
         print(f"smooth_fit: E_RMS={args['E_RMS']}")
@@ -521,6 +558,7 @@ def smooth_fit(**kwargs):
     TCinv = DiagonalOp(torch.cat((1. / s_loc, _cabi.to_dev(1. / Ec, f64))))
     rhs = torch.cat((z_loc, _cabi.to_dev(np.concatenate([op.prior for op in constraint_op_list]), f64)))
     Ip_c = build_reference_epoch_matrix(G_data, Gc, grids, args['reference_epoch'])
+    stages.mark('constraints')
     timing['setup'] = time() - tic
 
     if tse_d is not None:
@@ -540,9 +578,10 @@ def smooth_fit(**kwargs):
                                                        sigma_extra_masks=None if args['sigma_extra_masks'] is None else
                                                        {k: v[lo:hi] for k, v in args['sigma_extra_masks'].items()})
         timing['iteration'] = time() - tic_iteration
+        stages.mark('iterate_fit')
         # model estimate of every data point, G_data . m0 (smooth_fit.py:662); the CSR is already cached
         z_est_d = G_data._csr_device(col_N=m0.size, row_N=hi - lo).dot(_cabi.to_dev(m0, f64))
-        z_est = z_est_d.cpu().numpy()
+        z_est = _cabi.to_host(z_est_d)
         if dist is not None and dist.world > 1:
             in_TSE_all, sigma_extra_all, z_est_all = (dist.gather_rows(a) for a in (in_TSE, sigma_extra, z_est))
         else:
@@ -557,8 +596,10 @@ def smooth_fit(**kwargs):
         dev_fields = {'z': z_loc, 'sigma': s_loc, 'z_est': z_est_d, 'three_sigma_edit': _cabi.to_dev(in_TSE),
                       'sigma_extra': _cabi.to_dev(sigma_extra, f64),
                       'bias_ID': None if bias_id_d is None else bias_id_d[lo:hi]}
+        stages.mark('outputs_d2h')
         parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args,
                     dist=dist if (dist is not None and dist.world > 1) else None)
+        stages.mark('parse_model')
     else:
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
     return {'m': m, 'E': E, 'data': data, 'grids': grids, 'valid_data': valid_data, 'TOC': Gc.TOC, 'R': R, 'RMS': RMS,
