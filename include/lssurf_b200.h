@@ -157,6 +157,12 @@ int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, con
                       const int32_t *t_indices, const double *t_data, const double *rhs,
                       const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm, void *stream);
 int lss_solver_destroy(lss_solver_t *solver);
+/* Optional layout hint for the product y = w .* (A p): the first n_lead rows of A (the data block G, whose rows
+ * all hold at most row_len <= 16 entries: 4 z0 + 8 dz corners + bias columns) are additionally kept column-major
+ * (ELL) and applied one thread per row; the remaining rows (constraints) are applied from the stand-alone CSR
+ * (c_indptr rebased to 0, borrowed).  Row sums are taken left to right; results are deterministic. */
+int lss_solver_split_rows(lss_solver_t *solver, int64_t n_lead, int32_t row_len, const int32_t *c_indptr,
+                          const int32_t *c_indices, const double *c_data);
 /* Row weights w (length n_rows): 1/sigma^2 for selected data rows, 0 for edited rows, 1/E_c^2 for
  * constraint rows.  Recomputes the right-hand side A^T W b and the Jacobi diagonal. */
 int lss_solver_set_weights(lss_solver_t *solver, const double *w);

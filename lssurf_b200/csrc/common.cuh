@@ -123,6 +123,12 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
                 const double *x, double *y, int mode, const double *s, int64_t nnz, const SpmvPlan *plan,
                 const double *stop, cudaStream_t stream, int64_t *launches);
 
+// Column-major fixed-row-length ("ELL") copy of the leading rows of a CSR matrix and its product (spmv.cu).
+int ell_build(int64_t n_rows, int K, const int32_t *indptr, const int32_t *indices, const double *data, int32_t *ell_col,
+              double *ell_val, int64_t n_pad, cudaStream_t stream);
+int ell_spmv_launch(int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val, const double *x, double *y,
+                    int mode, const double *s, const double *stop, cudaStream_t stream);
+
 }  // namespace lss
 
 // NCCL communicator wrapper (comm.cu)

@@ -221,7 +221,15 @@ struct lss_solver {
     int64_t launches;
     std::vector<cudaEvent_t> *prof_events;   // fixed pool: 3 events per operator application, 2 batches deep
     int64_t n_prof;
-    lss::SpmvPlan plan_a, plan_at;
+    lss::SpmvPlan plan_a, plan_at, plan_c;
+    // optional split of the A product: leading rows in ELL form, the remaining rows as a stand-alone CSR
+    int64_t ell_rows, ell_pad;
+    int ell_k;
+    int32_t *ell_col;
+    double *ell_val;
+    const int32_t *c_indptr, *c_indices;
+    const double *c_data;
+    int64_t c_nnz;
 };
 
 static int dev_alloc(double **p, int64_t n) {
@@ -237,6 +245,9 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
         if (*pp) cudaFree(*pp);
     lss::spmv_plan_destroy(&s->plan_a);
     lss::spmv_plan_destroy(&s->plan_at);
+    lss::spmv_plan_destroy(&s->plan_c);
+    if (s->ell_col) cudaFree(s->ell_col);
+    if (s->ell_val) cudaFree(s->ell_val);
     if (s->fixed) cudaFree(s->fixed);
     if (s->host_scal) cudaFreeHost(s->host_scal);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -313,7 +324,14 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
         e2 = (*s->prof_events)[3 * prof_slot + 2];
         LSS_CUDA(cudaEventRecord(e0, st));
     }
-    LSS_TRY(spmv_launch(s->n_rows, s->indptr, s->indices, s->data, v, s->u, LSS_SPMV_SCALE, s->w, s->nnz, &s->plan_a, stop, st, &s->launches));
+    if (s->ell_rows > 0) {
+        LSS_TRY(ell_spmv_launch(s->ell_rows, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, v, s->u, LSS_SPMV_SCALE, s->w, stop, st));
+        s->launches += 1;
+        LSS_TRY(spmv_launch(s->n_rows - s->ell_rows, s->c_indptr, s->c_indices, s->c_data, v, s->u + s->ell_rows, LSS_SPMV_SCALE,
+                            s->w + s->ell_rows, s->c_nnz, &s->plan_c, stop, st, &s->launches));
+    } else {
+        LSS_TRY(spmv_launch(s->n_rows, s->indptr, s->indices, s->data, v, s->u, LSS_SPMV_SCALE, s->w, s->nnz, &s->plan_a, stop, st, &s->launches));
+    }
     if (timed) LSS_CUDA(cudaEventRecord(e1, st));
     LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->buf, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, stop, st, &s->launches));
     if (timed) LSS_CUDA(cudaEventRecord(e2, st));
@@ -326,6 +344,33 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     }
     LSS_TRY(comm_allreduce(s->comm, s->buf, n_red, 0, 0, st));
     s->n_apply += 1;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_split_rows(lss_solver_t *s, int64_t n_lead, int32_t row_len, const int32_t *c_indptr,
+                                     const int32_t *c_indices, const double *c_data) {
+    if (!s || n_lead < 0 || n_lead > s->n_rows) return fail(LSS_EINVAL, "solver_split_rows: bad row count");
+    if (row_len < 1 || row_len > 16) return fail(LSS_EINVAL, "solver_split_rows: row length must be 1..16");
+    cudaStream_t st = s->stream;
+    const int64_t n_rest = s->n_rows - n_lead;
+    int c_nnz = 0;
+    if (n_rest > 0) {
+        if (!c_indptr) return fail(LSS_EINVAL, "solver_split_rows: the trailing rows need their own CSR");
+        LSS_CUDA(cudaMemcpyAsync(&c_nnz, c_indptr + n_rest, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+    }
+    if (s->ell_col) { cudaFree(s->ell_col); s->ell_col = nullptr; }
+    if (s->ell_val) { cudaFree(s->ell_val); s->ell_val = nullptr; }
+    s->ell_rows = 0;
+    if (n_lead == 0) return LSS_OK;
+    const int64_t n_pad = (n_lead + 31) / 32 * 32;           // keeps every column 256-byte aligned
+    LSS_CUDA(cudaMalloc((void **)&s->ell_col, sizeof(int32_t) * n_pad * row_len));
+    LSS_CUDA(cudaMalloc((void **)&s->ell_val, sizeof(double) * n_pad * row_len));
+    LSS_TRY(ell_build(n_lead, row_len, s->indptr, s->indices, s->data, s->ell_col, s->ell_val, n_pad, st));
+    spmv_plan_destroy(&s->plan_c);
+    if (n_rest > 0) LSS_TRY(spmv_plan_create(&s->plan_c, n_rest, c_indptr, c_nnz, st));
+    s->c_indptr = c_indptr; s->c_indices = c_indices; s->c_data = c_data; s->c_nnz = c_nnz;
+    s->ell_pad = n_pad; s->ell_k = row_len; s->ell_rows = n_lead;
     return LSS_OK;
 }
 

@@ -311,6 +311,72 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
     return LSS_OK;
 }
 
+
+// ============================================================================ ELL (fixed row length) product
+// The data block G has the same number of entries in every row (2^2 z0 corners + 2^3 dz corners + bias columns),
+// so it is also kept column-major ("ELL"): entry k of row r at [k * n_pad + r].  One thread per row then reads
+// perfectly coalesced index / value streams (1 + 2 L1 wavefronts per warp instruction) and gathers x for 32
+// CONSECUTIVE rows at a time -- points that are neighbours on the ground and share grid nodes -- instead of
+// 32 consecutive non-zeros of 2-3 rows.  The nnz-tiled CSR kernel is L1TEX-wavefront bound on those gathers
+// (ncu: l1tex 75 %, DRAM 59-64 %); this layout needs ~2.5x fewer wavefronts per byte streamed.
+__global__ void __launch_bounds__(256)
+ell_build_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict__ indptr, const int *__restrict__ indices,
+                 const double *__restrict__ data, int *__restrict__ ell_col, double *__restrict__ ell_val) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int b = indptr[r], e = indptr[r + 1];
+    for (int k = 0; k < K; ++k) {
+        const bool in = b + k < e;
+        ell_col[(int64_t)k * n_pad + r] = in ? indices[b + k] : 0;
+        ell_val[(int64_t)k * n_pad + r] = in ? data[b + k] : 0.0;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+ell_spmv_kernel(int64_t n_rows, int64_t n_pad, const int *__restrict__ ell_col, const double *__restrict__ ell_val,
+                const double *__restrict__ x, double *__restrict__ y, int mode, const double *__restrict__ s,
+                const double *__restrict__ stop) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const double stop_v = stop ? *reinterpret_cast<const volatile double *>(stop) : 0.0;
+    int c[K];
+    double v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        c[k] = ldg_stream(ell_col + (int64_t)k * n_pad + r);
+        v[k] = ldg_stream(ell_val + (int64_t)k * n_pad + r);
+    }
+    if (stop_v != 0.0) return;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc += v[k] * __ldg(x + c[k]);     // same left-to-right order as the CSR row sum
+    y[r] = epilogue(acc, mode, s, r);
+}
+
+int ell_build(int64_t n_rows, int K, const int32_t *indptr, const int32_t *indices, const double *data, int32_t *ell_col,
+              double *ell_val, int64_t n_pad, cudaStream_t stream) {
+    if (n_rows <= 0) return LSS_OK;
+    ell_build_kernel<<<ceil_div(n_rows, 256), 256, 0, stream>>>(n_rows, n_pad, K, indptr, indices, data, ell_col, ell_val);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+int ell_spmv_launch(int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val, const double *x, double *y,
+                    int mode, const double *s, const double *stop, cudaStream_t stream) {
+    if (n_rows <= 0) return LSS_OK;
+    const int grid = ceil_div(n_rows, 256);
+#define LSS_ELL_CASE(KK) case KK: ell_spmv_kernel<KK><<<grid, 256, 0, stream>>>(n_rows, n_pad, ell_col, ell_val, x, y, mode, s, stop); break;
+    switch (K) {
+        LSS_ELL_CASE(1) LSS_ELL_CASE(2) LSS_ELL_CASE(3) LSS_ELL_CASE(4) LSS_ELL_CASE(5) LSS_ELL_CASE(6) LSS_ELL_CASE(7) LSS_ELL_CASE(8)
+        LSS_ELL_CASE(9) LSS_ELL_CASE(10) LSS_ELL_CASE(11) LSS_ELL_CASE(12) LSS_ELL_CASE(13) LSS_ELL_CASE(14) LSS_ELL_CASE(15) LSS_ELL_CASE(16)
+        default: return fail(LSS_EINVAL, "ELL product: row length %d not in 1..16", K);
+    }
+#undef LSS_ELL_CASE
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
 }  // namespace lss
 
 using namespace lss;

@@ -5,6 +5,7 @@ Stands in for the single line ``m0 = Ip_c.dot(sparseqr.solve(Ip_r.dot(TCinv.dot(
 memory for the whole edit loop; only the row-weight vector changes between outer iterations.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -14,7 +15,7 @@ from .lin_op import DeviceCSR
 
 
 class NormalSolver(object):
-    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None):
+    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, ell=True):
         """G: DeviceCSR of this rank's data rows; Cn: DeviceCSR of this rank's constraint rows;
         z / sigma: data values and errors (CUDA fp64); prior / Ec: constraint right-hand side and sigma;
         fixed_cols: columns held at zero (reference epoch)."""
@@ -37,6 +38,14 @@ class NormalSolver(object):
                                         _cabi.ptr(self.A.indices), _cabi.ptr(self.A.data), _cabi.ptr(self.At.indptr),
                                         _cabi.ptr(self.At.indices), _cabi.ptr(self.At.data), _cabi.ptr(self.rhs),
                                         _cabi.ptr(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
+        # data rows have a fixed, short row length: apply them in column-major (ELL) form
+        self.C = Cn
+        row_len = int((G.indptr[1:] - G.indptr[:-1]).max().item()) if self.n_data > 0 else 0
+        self.ell = bool(ell) and 1 <= row_len <= 16 and not os.environ.get('LSS_NO_ELL')
+        if self.ell:
+            has_c = Cn.shape[0] > 0
+            _cabi.check(L.lss_solver_split_rows(self.handle, self.n_data, row_len, _cabi.ptr(Cn.indptr) if has_c else None,
+                                                _cabi.ptr(Cn.indices) if has_c else None, _cabi.ptr(Cn.data) if has_c else None))
         self.x = torch.zeros(self.n_cols, dtype=torch.float64, device=z.device)
         self.last = {}
 
