@@ -95,6 +95,12 @@ int lss_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t
                       const int32_t *indices, const double *data, int32_t *t_indptr, int32_t *t_indices,
                       double *t_data, void *stream);
 
+/* Spatial sort keys (coarse (y, x) cell, fine (y, x) cell, coarse time cell; row-major) for the solver's INTERNAL
+ * ordering of the points: neighbours on the ground become neighbours in memory.  pts_h: host array of device
+ * pointers (y, x[, t]).  *key_bits_h receives the number of significant key bits (for lss_argsort_u64). */
+int lss_cell_keys(const lss_grid_t *fine, const lss_grid_t *coarse, const double *const *pts_h, int64_t n,
+                  uint64_t *keys, int32_t *key_bits_h, void *stream);
+
 /* Stable argsort of int64 keys in [0, 2^key_bits) (used for the internal spatial ordering of points). */
 int lss_argsort_u64(int64_t n, const uint64_t *keys, int32_t key_bits, int32_t *order, void *stream);
 

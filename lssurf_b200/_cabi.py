@@ -42,6 +42,7 @@ SIGNATURES = {
     'lss_coo_extent': [_i64, _vp, _vp, _pi64, _pi64, _vp],
     'lss_coo_to_csr': [_i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _pi64, _vp],
     'lss_csr_transpose': [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    'lss_cell_keys': [C.POINTER(lss_grid_t), C.POINTER(lss_grid_t), C.POINTER(_vp), _i64, _vp, _pi32, _vp],
     'lss_argsort_u64': [_i64, _vp, _i32, _vp, _vp],
     'lss_dense_rank_f64': [_vp, _i64, _f64, _vp, _pf64, _i64, _pi64, _vp],
     'lss_group_median': [_vp, _vp, _i64, _i32, _vp, _vp],
@@ -237,6 +238,18 @@ def csr_transpose(indptr, indices, data, n_rows, n_cols):
     check(L.lss_csr_transpose(n_rows, n_cols, nnz, ptr(indptr), ptr(indices), ptr(data), ptr(t_indptr), ptr(t_indices),
                               ptr(t_data), stream()))
     return t_indptr, t_indices[:nnz], t_data[:nnz]
+
+
+def spatial_order(fine, coarse, pts):
+    """Permutation (int64 CUDA tensor) that sorts points by (coarse cell, fine cell, time cell)."""
+    L = lib()
+    n = int(pts[0].numel())
+    keys = torch.empty(n, dtype=torch.int64, device=device())
+    nd = coarse.ndim
+    parr = (C.c_void_p * nd)(*[p.data_ptr() for p in pts[:nd]])
+    bits = C.c_int32(0)
+    check(L.lss_cell_keys(C.byref(fine), C.byref(coarse), parr, n, ptr(keys), C.byref(bits), stream()))
+    return argsort_u64(keys, bits.value).to(torch.int64)
 
 
 def argsort_u64(keys, key_bits):

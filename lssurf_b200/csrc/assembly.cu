@@ -157,6 +157,30 @@ stencil_coo_kernel(GridDev g, StencilDev st, int n_off, const int *__restrict__ 
     }
 }
 
+// Spatial sort key of a point: (coarse cell, fine cell, time cell), row-major, so that points sharing grid
+// nodes become neighbours in memory (gather locality of the CSR / ELL products).  Internal ordering only.
+__global__ void __launch_bounds__(256)
+cell_key_kernel(GridDev fine, GridDev coarse, PtsDev pts, long long n, unsigned long long *__restrict__ keys) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long key = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const GridDev &g = pass == 0 ? coarse : fine;
+        const int nd = pass == 0 ? 2 : fine.ndim < 2 ? fine.ndim : 2;
+        for (int d = 0; d < nd; ++d) {
+            long long c = (long long)floor((pts.p[d][i] - g.lo[d]) / g.delta[d]);
+            c = c < 0 ? 0 : (c >= g.shape[d] ? g.shape[d] - 1 : c);
+            key = key * (unsigned long long)g.shape[d] + (unsigned long long)c;
+        }
+    }
+    if (coarse.ndim > 2) {
+        long long c = (long long)floor((pts.p[2][i] - coarse.lo[2]) / coarse.delta[2]);
+        c = c < 0 ? 0 : (c >= coarse.shape[2] ? coarse.shape[2] - 1 : c);
+        key = key * (unsigned long long)coarse.shape[2] + (unsigned long long)c;
+    }
+    keys[i] = key;
+}
+
 __global__ void __launch_bounds__(256)
 coo_extent_kernel(long long nnz, const int *__restrict__ rows, const double *__restrict__ vals,
                   long long *__restrict__ out /* [0]=max_row, [1]=count */) {
@@ -306,5 +330,26 @@ extern "C" int lss_coo_extent(int64_t nnz, const int32_t *rows, const double *va
     }
     if (max_row_h) *max_row_h = h[0];
     if (n_nonzero_h) *n_nonzero_h = h[1];
+    return LSS_OK;
+}
+
+extern "C" int lss_cell_keys(const lss_grid_t *fine, const lss_grid_t *coarse, const double *const *pts_h, int64_t n,
+                             uint64_t *keys, int32_t *key_bits_h, void *stream) {
+    LSS_TRY(check_grid(fine));
+    LSS_TRY(check_grid(coarse));
+    if (fine->ndim < 2 || coarse->ndim < 2) return fail(LSS_EINVAL, "cell_keys: grids need at least 2 dimensions");
+    double span = 1.0;
+    for (int d = 0; d < 2; ++d) span *= (double)fine->shape[d] * (double)coarse->shape[d];
+    if (coarse->ndim > 2) span *= (double)coarse->shape[2];
+    int bits = 1;
+    while (bits < 63 && span > (double)(1ull << bits)) ++bits;
+    if (bits >= 63) return fail(LSS_ERANGE, "cell_keys: key does not fit in 63 bits");
+    if (key_bits_h) *key_bits_h = bits;
+    if (n <= 0) return LSS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    PtsDev p{};
+    for (int d = 0; d < coarse->ndim && d < 3; ++d) p.p[d] = pts_h[d];
+    cell_key_kernel<<<ceil_div(n, 256), 256, 0, st>>>(to_dev(fine), to_dev(coarse), p, n, (unsigned long long *)keys);
+    LSS_LAUNCH_CHECK();
     return LSS_OK;
 }

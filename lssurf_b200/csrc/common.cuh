@@ -113,6 +113,7 @@ int radix_sort_pairs(uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint3
 struct SpmvPlan {
     int n_tiles;
     int tile;
+    cudaStream_t stream;
     int *bounds;
     double *carry_val;
     int *carry_row;

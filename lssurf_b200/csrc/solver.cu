@@ -232,8 +232,11 @@ struct lss_solver {
     int64_t c_nnz;
 };
 
-static int dev_alloc(double **p, int64_t n) {
-    LSS_CUDA(cudaMalloc((void **)p, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+// Stream-ordered pool allocations: a solver is created and destroyed once per smooth_fit call, and cudaFree of
+// GB-sized blocks costs up to a second; freed pool memory is simply reused by the next solver.
+static int dev_alloc(double **p, int64_t n, cudaStream_t st) {
+    lss::Scratch::configure_pool();
+    LSS_CUDA(cudaMallocAsync((void **)p, sizeof(double) * (size_t)(n > 0 ? n : 1), st));
     return LSS_OK;
 }
 
@@ -246,8 +249,8 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     lss::spmv_plan_destroy(&s->plan_a);
     lss::spmv_plan_destroy(&s->plan_at);
     lss::spmv_plan_destroy(&s->plan_c);
-    if (s->ell_col) cudaFree(s->ell_col);
-    if (s->ell_val) cudaFree(s->ell_val);
+    if (s->ell_col) cudaFreeAsync(s->ell_col, s->stream);
+    if (s->ell_val) cudaFreeAsync(s->ell_val, s->stream);
     if (s->fixed) cudaFree(s->fixed);
     if (s->host_scal) cudaFreeHost(s->host_scal);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -283,11 +286,11 @@ extern "C" int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t 
             rc = fail(LSS_ECUDA, "solver_create: cannot read indptr: %s", cudaGetErrorString(cudaGetLastError()));
     }
     s->nnz = nnz;
-    chk(dev_alloc(&s->w, n_rows)); chk(dev_alloc(&s->u, n_rows));
-    chk(dev_alloc(&s->buf, n_cols + VEC_GRID)); chk(dev_alloc(&s->r, n_cols)); chk(dev_alloc(&s->p, n_cols));
-    chk(dev_alloc(&s->minv, n_cols)); chk(dev_alloc(&s->g, n_cols)); chk(dev_alloc(&s->diag, n_cols + VEC_GRID));
-    chk(dev_alloc(&s->part2, VEC_GRID)); chk(dev_alloc(&s->scal, S_COUNT));
-    if (rc == LSS_OK && cudaMalloc((void **)&s->fixed, (size_t)n_cols) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMalloc failed");
+    chk(dev_alloc(&s->w, n_rows, s->stream)); chk(dev_alloc(&s->u, n_rows, s->stream));
+    chk(dev_alloc(&s->buf, n_cols + VEC_GRID, s->stream)); chk(dev_alloc(&s->r, n_cols, s->stream)); chk(dev_alloc(&s->p, n_cols, s->stream));
+    chk(dev_alloc(&s->minv, n_cols, s->stream)); chk(dev_alloc(&s->g, n_cols, s->stream)); chk(dev_alloc(&s->diag, n_cols + VEC_GRID, s->stream));
+    chk(dev_alloc(&s->part2, VEC_GRID, s->stream)); chk(dev_alloc(&s->scal, S_COUNT, s->stream));
+    if (rc == LSS_OK && cudaMallocAsync((void **)&s->fixed, (size_t)n_cols, s->stream) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMalloc failed");
     if (rc == LSS_OK && cudaMallocHost((void **)&s->host_scal, sizeof(double) * S_COUNT * 2) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMallocHost failed");
     if (rc == LSS_OK) {
         cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
@@ -359,13 +362,13 @@ extern "C" int lss_solver_split_rows(lss_solver_t *s, int64_t n_lead, int32_t ro
         LSS_CUDA(cudaMemcpyAsync(&c_nnz, c_indptr + n_rest, sizeof(int), cudaMemcpyDeviceToHost, st));
         LSS_CUDA(cudaStreamSynchronize(st));
     }
-    if (s->ell_col) { cudaFree(s->ell_col); s->ell_col = nullptr; }
-    if (s->ell_val) { cudaFree(s->ell_val); s->ell_val = nullptr; }
+    if (s->ell_col) { cudaFreeAsync(s->ell_col, st); s->ell_col = nullptr; }
+    if (s->ell_val) { cudaFreeAsync(s->ell_val, st); s->ell_val = nullptr; }
     s->ell_rows = 0;
     if (n_lead == 0) return LSS_OK;
     const int64_t n_pad = (n_lead + 31) / 32 * 32;           // keeps every column 256-byte aligned
-    LSS_CUDA(cudaMalloc((void **)&s->ell_col, sizeof(int32_t) * n_pad * row_len));
-    LSS_CUDA(cudaMalloc((void **)&s->ell_val, sizeof(double) * n_pad * row_len));
+    LSS_CUDA(cudaMallocAsync((void **)&s->ell_col, sizeof(int32_t) * n_pad * row_len, st));
+    LSS_CUDA(cudaMallocAsync((void **)&s->ell_val, sizeof(double) * n_pad * row_len, st));
     LSS_TRY(ell_build(n_lead, row_len, s->indptr, s->indices, s->data, s->ell_col, s->ell_val, n_pad, st));
     spmv_plan_destroy(&s->plan_c);
     if (n_rest > 0) LSS_TRY(spmv_plan_create(&s->plan_c, n_rest, c_indptr, c_nnz, st));

@@ -223,18 +223,20 @@ int spmv_plan_create(SpmvPlan *plan, int64_t n_rows, const int32_t *indptr, int6
     plan->carry_val = nullptr;
     plan->carry_row = nullptr;
     if (plan->n_tiles == 0) return LSS_OK;
-    LSS_CUDA(cudaMalloc((void **)&plan->bounds, sizeof(int) * (plan->n_tiles + 1)));
-    LSS_CUDA(cudaMalloc((void **)&plan->carry_val, sizeof(double) * plan->n_tiles));
-    LSS_CUDA(cudaMalloc((void **)&plan->carry_row, sizeof(int) * plan->n_tiles));
+    plan->stream = stream;
+    Scratch::configure_pool();
+    LSS_CUDA(cudaMallocAsync((void **)&plan->bounds, sizeof(int) * (plan->n_tiles + 1), stream));
+    LSS_CUDA(cudaMallocAsync((void **)&plan->carry_val, sizeof(double) * plan->n_tiles, stream));
+    LSS_CUDA(cudaMallocAsync((void **)&plan->carry_row, sizeof(int) * plan->n_tiles, stream));
     spmv_tile_bounds_kernel<<<ceil_div(plan->n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, plan->n_tiles, plan->tile, plan->bounds);
     LSS_LAUNCH_CHECK();
     return LSS_OK;
 }
 
 void spmv_plan_destroy(SpmvPlan *plan) {
-    if (plan->bounds) cudaFree(plan->bounds);
-    if (plan->carry_val) cudaFree(plan->carry_val);
-    if (plan->carry_row) cudaFree(plan->carry_row);
+    if (plan->bounds) cudaFreeAsync(plan->bounds, plan->stream);
+    if (plan->carry_val) cudaFreeAsync(plan->carry_val, plan->stream);
+    if (plan->carry_row) cudaFreeAsync(plan->carry_row, plan->stream);
     plan->bounds = nullptr;
     plan->carry_val = nullptr;
     plan->carry_row = nullptr;

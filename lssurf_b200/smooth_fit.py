@@ -15,6 +15,7 @@ the weight vector), the column selection ``Ip_c`` is a set of unknowns held at z
 keywords (defaults keep existing calls unchanged): ``cg_rtol``, ``cg_maxiter``, ``dist`` (a
 ``parallel.DistContext`` for row-sharded multi-GPU solves), ``profile_spmv``.
 """
+import os
 from time import time, ctime
 
 import numpy as np
@@ -45,7 +46,7 @@ DEFAULTS = {
     'VERBOSE': True, 'DEBUG': False,
     # solver controls (new; defaults chosen for 1e-6 relative-L2 parity with a direct solve)
     'cg_rtol': 1e-12, 'cg_maxiter': 50000, 'dist': None, 'profile_spmv': False, 'history': None,
-    'time_stages': False,
+    'time_stages': False, 'sort_points': True,
 }
 
 _UNSUPPORTED = ('compute_E', 'mask_file', 'mask_update_function', 'sigma_extra_bin_spacing', 'prior_args',
@@ -122,12 +123,21 @@ def _value_set(mask):
 
 def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, grids,
                 bias_model=None, sigma_extra_masks=None):
+    """Reference signature (smooth_fit.py:100-101, 210): returns ``m0, sigma_extra, in_TSE, rs_data`` as NumPy
+    arrays.  The work is done by ``iterate_fit_device`` on device arrays."""
+    m0, se, tse, r_data, sigma = iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, grids,
+                                                    bias_model=bias_model, sigma_extra_masks=sigma_extra_masks)
+    return m0, _cabi.to_host(se), _cabi.to_host(tse).astype(bool), _cabi.to_host(r_data / sigma)
+
+
+def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, grids,
+                       bias_model=None, sigma_extra_masks=None):
     """The edit / reweight loop (smooth_fit.py:100-210) on device arrays.
 
     ``Gcoo`` is accepted for signature compatibility and ignored: the operator is taken from the
     ``G_data`` / ``Gc`` lin_ops (device CSR).  ``TCinv`` only needs ``diagonal()`` (1/sigma for the
     data rows then the constraint rows); ``Ip_c`` (col_N x n_free selection) only tells which columns
-    are solved for.  Returns ``m0, sigma_extra, in_TSE, rs_data`` as NumPy arrays like the reference.
+    are solved for.  Returns ``m0`` (NumPy) and the CUDA tensors ``sigma_extra, in_TSE (uint8), r_data, sigma``.
     With ``args['dist']`` the data rows of this rank are its shard; m0 is identical on every rank.
     """
     args = dict(DEFAULTS, **args) if not all(k in args for k in ('cg_rtol', 'cg_maxiter', 'dist')) else args
@@ -259,11 +269,9 @@ def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, 
         if iteration == args['max_iterations'] - 2:
             last_iteration = True
     st.mark('it:other')
-    rs_data = _cabi.to_host(r_data / sigma)
-    out = (m0, _cabi.to_host(sigma_extra), _cabi.to_host(in_TSE_d).astype(bool), rs_data)
     solver.close()
-    st.mark('it:outputs_d2h')
-    return out
+    st.mark('it:close')
+    return m0, sigma_extra, in_TSE_d, r_data, sigma
 
 
 def _bias_statistics(b_dict, bias_id, r, tse, n_bias, dist):
@@ -489,10 +497,28 @@ def smooth_fit(**kwargs):
             bias_model['bias_param_dict']['edited'] = np.zeros_like(bias_model['bias_param_dict']['ID'], dtype=bool)
 
     stages.mark('bias_ids')
+    # ---- internal spatial ordering: rows of G are built for points sorted by (dz cell, z0 cell, epoch) so that the
+    # gathers of the CSR / ELL products hit neighbouring grid nodes; every per-point output is returned in the
+    # caller's order.  Skipped where the caller sees operator rows (return_fit_objects) or per-point host logic
+    # addresses rows (bias editing, `editable`).
+    order = None
+    if (args['sort_points'] and os.environ.get('LSS_SORT_POINTS', '1') != '0' and not args['return_fit_objects'] and args['bias_nsigma_edit'] is None
+            and args['bias_edit_vals'] is None and 'editable' not in data.fields and args['sigma_extra_masks'] is None
+            and n_all > 1):
+        order = _cabi.spatial_order(grids['z0'].as_struct(), grids['dz'].as_struct(), [y_d, x_d, t_d])
+        y_d, x_d, t_d, z_d, s_d = (a[order].contiguous() for a in (y_d, x_d, t_d, z_d, s_d))
+        tse_d = None if tse_d is None else tse_d[order].contiguous()
+        bias_id_d = None if bias_id_d is None else bias_id_d[order].contiguous()
+        rz = rd = None
+        stages.mark('spatial_sort')
     # ---- this rank's block of points
     lo, hi = (0, n_all) if dist is None else dist.shard(n_all)
     whole = (lo, hi) == (0, n_all)
-    local = data if whole else data.copy_subset(slice(lo, hi))
+    if order is not None:
+        # rows are in the internal order: the loop only needs the row count from the point container
+        local = point_data().from_dict({'row': np.empty(hi - lo, dtype=np.uint8)})
+    else:
+        local = data if whole else data.copy_subset(slice(lo, hi))
     if rz is not None and whole:
         # all points valid: the validity pass already produced the interpolation triplets
         for op, res, g in ((op_z0, rz, grids['z0']), (op_dz, rd, grids['dz'])):
@@ -573,28 +599,43 @@ def smooth_fit(**kwargs):
     averaging_ops = {}
     if args['max_iterations'] > 0:
         tic_iteration = time()
-        m0, sigma_extra, in_TSE, rs_data = iterate_fit(local, None, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args,
-                                                       grids, bias_model=bias_model,
-                                                       sigma_extra_masks=None if args['sigma_extra_masks'] is None else
-                                                       {k: v[lo:hi] for k, v in args['sigma_extra_masks'].items()})
+        m0, se_d, tse_out_d, r_d, _ = iterate_fit_device(local, None, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args,
+                                                        grids, bias_model=bias_model,
+                                                        sigma_extra_masks=None if args['sigma_extra_masks'] is None else
+                                                        {k: v[lo:hi] for k, v in args['sigma_extra_masks'].items()})
         timing['iteration'] = time() - tic_iteration
         stages.mark('iterate_fit')
         # model estimate of every data point, G_data . m0 (smooth_fit.py:662); the CSR is already cached
         z_est_d = G_data._csr_device(col_N=m0.size, row_N=hi - lo).dot(_cabi.to_dev(m0, f64))
-        z_est = _cabi.to_host(z_est_d)
-        if dist is not None and dist.world > 1:
-            in_TSE_all, sigma_extra_all, z_est_all = (dist.gather_rows(a) for a in (in_TSE, sigma_extra, z_est))
-        else:
-            in_TSE_all, sigma_extra_all, z_est_all = in_TSE, sigma_extra, z_est
+        multi = dist is not None and dist.world > 1
+
+        def to_caller(t):
+            """device rows of this rank -> NumPy over all points in the caller's order"""
+            if multi:
+                a = dist.gather_rows(_cabi.to_host(t))
+                if order is None:
+                    return a
+                t = _cabi.to_dev(a)
+            if order is not None:
+                out = torch.empty_like(t)
+                out[order] = t                    # undo the internal spatial ordering on the device
+                t = out
+            return _cabi.to_host(t)
+
+        in_TSE_all = to_caller(tse_out_d).astype(bool)
+        sigma_extra_all = to_caller(se_d)
+        z_est_all = to_caller(z_est_d)
+        if args.get('history') is not None and order is not None and not multi:
+            for h in args['history']:             # per-iteration masks were recorded in the internal order
+                mk = torch.empty(n_all, dtype=torch.uint8, device=z_d.device)
+                mk[order] = _cabi.to_dev(np.unpackbits(h['mask_out'])[:n_all])
+                h['mask_out'] = np.packbits(_cabi.to_host(mk))
         valid_data[valid_data] = in_TSE_all
         data.assign({'three_sigma_edit': in_TSE_all})
         data.assign({'sigma_extra': sigma_extra_all})
         data.assign({'z_est': np.reshape(z_est_all, data.shape)})
-        if local is not data:
-            local.assign({'three_sigma_edit': in_TSE, 'sigma_extra': sigma_extra, 'z_est': z_est})
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
-        dev_fields = {'z': z_loc, 'sigma': s_loc, 'z_est': z_est_d, 'three_sigma_edit': _cabi.to_dev(in_TSE),
-                      'sigma_extra': _cabi.to_dev(sigma_extra, f64),
+        dev_fields = {'z': z_loc, 'sigma': s_loc, 'z_est': z_est_d, 'three_sigma_edit': tse_out_d, 'sigma_extra': se_d,
                       'bias_ID': None if bias_id_d is None else bias_id_d[lo:hi]}
         stages.mark('outputs_d2h')
         parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args,
