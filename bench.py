@@ -242,22 +242,37 @@ def run_b200(a):
     # ---- roofline of the dominant kernel from the solver's own event pairs (this rank's launches)
     n_apply = sum(p['n_apply'] for p in pcg)
     ms_a, ms_at = sum(p['ms_A'] for p in pcg), sum(p['ms_At'] for p in pcg)
-    nnz = pcg[0]['nnz']
+    p0 = pcg[0]
+    nnz = p0['nnz']
     n_cols = int(S['m']['all'].size)
-    rows_loc = pcg[0]['rows']
-    b_a = spmv_bytes(rows_loc, n_cols, nnz, True)
-    b_at = spmv_bytes(n_cols, rows_loc, nnz, False)
     peak, peak_src = measured_peak()
-    ach = (b_a + b_at) * n_apply / ((ms_a + ms_at) / 1e3) / 1e9 if (ms_a + ms_at) > 0 else None
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'spmv_traffic.json')
     if os.path.exists(prof):
         traffic = json.load(open(prof)).get('dram_bytes_per_launch')
-    roofline = {'bound': 'hbm', 'kernel': 'lss::spmv_tile_kernel (y = w.*(A p) and q = A^T u)', 'achieved': ach, 'peak': peak,
-                'unit': 'GB/s', 'frac': None if ach is None else ach / peak, 'peak_source': peak_src, 'traffic': traffic,
-                'bytes_per_launch': {'A': b_a, 'At': b_at}, 'launch_ms': {'A': ms_a / n_apply, 'At': ms_at / n_apply},
-                'gbs': {'A': b_a / (ms_a / n_apply / 1e3) / 1e9, 'At': b_at / (ms_at / n_apply / 1e3) / 1e9},
-                'frac_of_nominal_8TBs': None if ach is None else ach / 8000.0}
+    if p0.get('fused'):
+        # block form: ONE pass over the ELL copy of G does q += G^T (w .* (G p)): 12 B per entry, the row weights,
+        # x read once and q read-modify-written once (compulsory); the constraint pair (C, C^T) is the small rest
+        b_dom = 12 * p0['nnz_G'] + 8 * p0['n_data'] + 24 * n_cols
+        b_con = spmv_bytes(p0['n_con'], n_cols, p0['nnz_C'], True) + spmv_bytes(n_cols, p0['n_con'], p0['nnz_C'], False)
+        ms_dom, ms_con = ms_at / n_apply, ms_a / n_apply
+        ach = b_dom / (ms_dom / 1e3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': 'lss::ell_normal_kernel<13,0> (fused q += G^T (w .* (G p)), one pass over G)',
+                    'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peak_src,
+                    'traffic': traffic, 'bytes_per_launch': {'fused_G': b_dom, 'C_and_Ct': b_con},
+                    'launch_ms': {'fused_G': ms_dom, 'C_and_Ct': ms_con},
+                    'gbs': {'fused_G': ach, 'C_and_Ct': b_con / (ms_con / 1e3) / 1e9 if ms_con > 0 else None},
+                    'frac_of_nominal_8TBs': ach / 8000.0}
+    else:
+        rows_loc = p0['rows']
+        b_a = spmv_bytes(rows_loc, n_cols, nnz, True)
+        b_at = spmv_bytes(n_cols, rows_loc, nnz, False)
+        ach = (b_a + b_at) * n_apply / ((ms_a + ms_at) / 1e3) / 1e9 if (ms_a + ms_at) > 0 else None
+        roofline = {'bound': 'hbm', 'kernel': 'lss::spmv_persistent_kernel (y = w.*(A p) and q = A^T u)', 'achieved': ach, 'peak': peak,
+                    'unit': 'GB/s', 'frac': None if ach is None else ach / peak, 'peak_source': peak_src, 'traffic': traffic,
+                    'bytes_per_launch': {'A': b_a, 'At': b_at}, 'launch_ms': {'A': ms_a / n_apply, 'At': ms_at / n_apply},
+                    'gbs': {'A': b_a / (ms_a / n_apply / 1e3) / 1e9, 'At': b_at / (ms_at / n_apply / 1e3) / 1e9},
+                    'frac_of_nominal_8TBs': None if ach is None else ach / 8000.0}
     outer = len(pcg) / a.steps
     iters = sum(p['iterations'] for p in pcg) / a.steps
     solve_ms = sum(p['ms'] for p in pcg) / a.steps

@@ -163,12 +163,20 @@ int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, con
                       const int32_t *t_indices, const double *t_data, const double *rhs,
                       const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm, void *stream);
 int lss_solver_destroy(lss_solver_t *solver);
-/* Optional layout hint for the product y = w .* (A p): the first n_lead rows of A (the data block G, whose rows
- * all hold at most row_len <= 16 entries: 4 z0 + 8 dz corners + bias columns) are additionally kept column-major
- * (ELL) and applied one thread per row; the remaining rows (constraints) are applied from the stand-alone CSR
- * (c_indptr rebased to 0, borrowed).  Row sums are taken left to right; results are deterministic. */
-int lss_solver_split_rows(lss_solver_t *solver, int64_t n_lead, int32_t row_len, const int32_t *c_indptr,
-                          const int32_t *c_indices, const double *c_data);
+/* Block form of the same solver, the one smooth_fit uses: A = [G; C] is given as its two row blocks.
+ *   G (n_data rows): every row holds at most row_len <= 16 entries (4 z0 + 8 dz corners + bias columns).  It is copied
+ *     column-major (ELL) and applied by ONE fused kernel q += G^T (w .* (G p)) -- a single pass over G per CG
+ *     iteration, contributions of neighbouring rows combined with warp shuffles before fp64 RED atomics -- so no
+ *     transpose of G is ever built.  The CSR arrays of G are only read during this call.
+ *   C (n_con rows) and its transpose C^T (n_cols rows), both canonical CSR (borrowed): applied with the tiled
+ *     CSR kernel.
+ * rhs has n_data + n_con entries.  The atomics make the summation order of q run-dependent (last-bit differences). */
+int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, int64_t n_con, int64_t n_cols, int32_t row_len,
+                             const int32_t *g_indptr, const int32_t *g_indices, const double *g_data,
+                             const int32_t *c_indptr, const int32_t *c_indices, const double *c_data,
+                             const int32_t *ct_indptr, const int32_t *ct_indices, const double *ct_data,
+                             const double *rhs, const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm,
+                             void *stream);
 /* Row weights w (length n_rows): 1/sigma^2 for selected data rows, 0 for edited rows, 1/E_c^2 for
  * constraint rows.  Recomputes the right-hand side A^T W b and the Jacobi diagonal. */
 int lss_solver_set_weights(lss_solver_t *solver, const double *w);
@@ -179,8 +187,9 @@ int lss_solver_solve(lss_solver_t *solver, double *x, double rtol, int32_t max_i
 /* Record CUDA-event pairs around every A and A^T product of the following solves (small overhead). */
 int lss_solver_set_profile(lss_solver_t *solver, int32_t on);
 /* Statistics of the last solve, timed with CUDA events on the solver's stream:
- * stats_h[0] = total ms, [1] = ms in y = w.*(A p) products, [2] = ms in A^T u products (both 0 unless
- * profiling is on), [3] = number of operator applications, [4] = kernels launched, [5] = nnz(A). */
+ * stats_h[0] = total ms; [1], [2] = ms in the two halves of the operator (generic form: y = w.*(A p), then A^T u;
+ * block form: the constraint products C, C^T, then the fused data-block kernel), 0 unless profiling is on;
+ * [3] = number of operator applications behind [1], [2]; [4] = kernels launched; [5] = nnz(A). */
 int lss_solver_stats(lss_solver_t *solver, double *stats_h);
 
 /* ------------------------------------------------------------------ robust statistics / editing */

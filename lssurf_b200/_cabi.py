@@ -57,7 +57,7 @@ SIGNATURES = {
     'lss_comm_allreduce_f64': [_vp, _vp, _i64, _vp],
     'lss_solver_create': [C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     'lss_solver_destroy': [_vp],
-    'lss_solver_split_rows': [_vp, _i64, _i32, _vp, _vp, _vp],
+    'lss_solver_create_blocks': [C.POINTER(_vp), _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     'lss_solver_set_weights': [_vp, _vp],
     'lss_solver_solve': [_vp, _vp, _f64, _i32, _pi32, _pf64],
     'lss_solver_set_profile': [_vp, _i32],

@@ -221,16 +221,19 @@ struct lss_solver {
     int64_t launches;
     std::vector<cudaEvent_t> *prof_events;   // fixed pool: 3 events per operator application, 2 batches deep
     int64_t n_prof;
-    lss::SpmvPlan plan_a, plan_at, plan_c;
-    // optional split of the A product: leading rows in ELL form, the remaining rows as a stand-alone CSR
-    int64_t ell_rows, ell_pad;
+    lss::SpmvPlan plan_a, plan_at, plan_c, plan_ct;
+    // block form (lss_solver_create_blocks): data rows as an ELL copy applied by the fused G^T W G kernel,
+    // constraint rows as a CSR pair (C, C^T); the A / A^T arrays above are then unused
+    bool blocks;
+    int64_t n_data, n_con, ell_pad;
     int ell_k;
     int32_t *ell_col;
     double *ell_val;
-    const int32_t *c_indptr, *c_indices;
-    const double *c_data;
+    const int32_t *c_indptr, *c_indices, *ct_indptr, *ct_indices;
+    const double *c_data, *ct_data;
     int64_t c_nnz;
 };
+
 
 // Stream-ordered pool allocations: a solver is created and destroyed once per smooth_fit call, and cudaFree of
 // GB-sized blocks costs up to a second; freed pool memory is simply reused by the next solver.
@@ -245,13 +248,14 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     cudaStreamSynchronize(s->stream);
     double **ptrs[] = {&s->w, &s->u, &s->buf, &s->r, &s->p, &s->minv, &s->g, &s->diag, &s->part2, &s->scal};
     for (auto pp : ptrs)
-        if (*pp) cudaFree(*pp);
+        if (*pp) cudaFreeAsync(*pp, s->stream);
     lss::spmv_plan_destroy(&s->plan_a);
     lss::spmv_plan_destroy(&s->plan_at);
     lss::spmv_plan_destroy(&s->plan_c);
+    lss::spmv_plan_destroy(&s->plan_ct);
     if (s->ell_col) cudaFreeAsync(s->ell_col, s->stream);
     if (s->ell_val) cudaFreeAsync(s->ell_val, s->stream);
-    if (s->fixed) cudaFree(s->fixed);
+    if (s->fixed) cudaFreeAsync(s->fixed, s->stream);
     if (s->host_scal) cudaFreeHost(s->host_scal);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -265,27 +269,14 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     return LSS_OK;
 }
 
-extern "C" int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, const int32_t *indptr,
-                                 const int32_t *indices, const double *data, const int32_t *t_indptr,
-                                 const int32_t *t_indices, const double *t_data, const double *rhs,
-                                 const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm, void *stream) {
-    if (!solver || n_rows < 0 || n_cols <= 0) return fail(LSS_EINVAL, "solver_create: bad sizes");
-    lss_solver *s = new lss_solver();
+static int solver_init_common(lss_solver *s, int64_t n_rows, int64_t n_cols, const double *rhs, const int32_t *fixed_cols,
+                              int64_t n_fixed, lss_comm_t *comm, void *stream) {
     memset(s, 0, sizeof(*s));
     s->n_rows = n_rows; s->n_cols = n_cols;
-    s->indptr = indptr; s->indices = indices; s->data = data;
-    s->t_indptr = t_indptr; s->t_indices = t_indices; s->t_data = t_data;
     s->rhs = rhs; s->comm = comm; s->stream = (cudaStream_t)stream;
     s->prof_events = new std::vector<cudaEvent_t>();
     int rc = LSS_OK;
     auto chk = [&](int r) { if (rc == LSS_OK) rc = r; };
-    int nnz = 0;
-    if (n_rows > 0) {
-        if (cudaMemcpyAsync(&nnz, indptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
-            cudaStreamSynchronize(s->stream) != cudaSuccess)
-            rc = fail(LSS_ECUDA, "solver_create: cannot read indptr: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    s->nnz = nnz;
     chk(dev_alloc(&s->w, n_rows, s->stream)); chk(dev_alloc(&s->u, n_rows, s->stream));
     chk(dev_alloc(&s->buf, n_cols + VEC_GRID, s->stream)); chk(dev_alloc(&s->r, n_cols, s->stream)); chk(dev_alloc(&s->p, n_cols, s->stream));
     chk(dev_alloc(&s->minv, n_cols, s->stream)); chk(dev_alloc(&s->g, n_cols, s->stream)); chk(dev_alloc(&s->diag, n_cols + VEC_GRID, s->stream));
@@ -301,10 +292,67 @@ extern "C" int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t 
         if (n_fixed > 0) mark_fixed_kernel<<<stride_grid(n_fixed, VEC_BLOCK), VEC_BLOCK, 0, s->stream>>>(n_fixed, fixed_cols, s->fixed);
         if (cudaGetLastError() != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: launch failed");
     }
+    s->profile = getenv("LSS_PROFILE_SPMV") != nullptr;
+    return rc;
+}
+
+static int read_nnz(const int32_t *indptr, int64_t n_rows, cudaStream_t st, int64_t *nnz) {
+    int v = 0;
+    if (n_rows > 0) {
+        LSS_CUDA(cudaMemcpyAsync(&v, indptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+    }
+    *nnz = v;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, const int32_t *indptr,
+                                 const int32_t *indices, const double *data, const int32_t *t_indptr,
+                                 const int32_t *t_indices, const double *t_data, const double *rhs,
+                                 const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm, void *stream) {
+    if (!solver || n_rows < 0 || n_cols <= 0) return fail(LSS_EINVAL, "solver_create: bad sizes");
+    lss_solver *s = new lss_solver();
+    int rc = solver_init_common(s, n_rows, n_cols, rhs, fixed_cols, n_fixed, comm, stream);
+    s->indptr = indptr; s->indices = indices; s->data = data;
+    s->t_indptr = t_indptr; s->t_indices = t_indices; s->t_data = t_data;
+    if (rc == LSS_OK) rc = read_nnz(indptr, n_rows, s->stream, &s->nnz);
     if (rc == LSS_OK) rc = spmv_plan_create(&s->plan_a, n_rows, indptr, s->nnz, s->stream);
     if (rc == LSS_OK) rc = spmv_plan_create(&s->plan_at, n_cols, t_indptr, s->nnz, s->stream);
     if (rc != LSS_OK) { lss_solver_destroy(s); return rc; }
-    s->profile = getenv("LSS_PROFILE_SPMV") != nullptr;
+    *solver = s;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, int64_t n_con, int64_t n_cols, int32_t row_len,
+                                        const int32_t *g_indptr, const int32_t *g_indices, const double *g_data,
+                                        const int32_t *c_indptr, const int32_t *c_indices, const double *c_data,
+                                        const int32_t *ct_indptr, const int32_t *ct_indices, const double *ct_data,
+                                        const double *rhs, const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm,
+                                        void *stream) {
+    if (!solver || n_data < 0 || n_con < 0 || n_cols <= 0) return fail(LSS_EINVAL, "solver_create_blocks: bad sizes");
+    if (n_data > 0 && (row_len < 1 || row_len > 16)) return fail(LSS_EINVAL, "solver_create_blocks: data rows must hold 1..16 entries");
+    lss_solver *s = new lss_solver();
+    int rc = solver_init_common(s, n_data + n_con, n_cols, rhs, fixed_cols, n_fixed, comm, stream);
+    cudaStream_t st = s->stream;
+    s->blocks = true;
+    s->n_data = n_data; s->n_con = n_con;
+    s->c_indptr = c_indptr; s->c_indices = c_indices; s->c_data = c_data;
+    s->ct_indptr = ct_indptr; s->ct_indices = ct_indices; s->ct_data = ct_data;
+    int64_t g_nnz = 0;
+    if (rc == LSS_OK) rc = read_nnz(g_indptr, n_data, st, &g_nnz);
+    if (rc == LSS_OK && n_con > 0) rc = read_nnz(c_indptr, n_con, st, &s->c_nnz);
+    s->nnz = g_nnz + s->c_nnz;
+    if (rc == LSS_OK && n_data > 0) {
+        s->ell_k = row_len;
+        s->ell_pad = (n_data + 31) / 32 * 32;          // every ELL column stays 256-byte aligned
+        if (cudaMallocAsync((void **)&s->ell_col, sizeof(int32_t) * s->ell_pad * row_len, st) != cudaSuccess ||
+            cudaMallocAsync((void **)&s->ell_val, sizeof(double) * s->ell_pad * row_len, st) != cudaSuccess)
+            rc = fail(LSS_ECUDA, "solver_create_blocks: cudaMallocAsync failed");
+        if (rc == LSS_OK) rc = ell_build(n_data, row_len, g_indptr, g_indices, g_data, s->ell_col, s->ell_val, s->ell_pad, st);
+    }
+    if (rc == LSS_OK && n_con > 0) rc = spmv_plan_create(&s->plan_c, n_con, c_indptr, s->c_nnz, st);
+    if (rc == LSS_OK && n_con > 0) rc = spmv_plan_create(&s->plan_ct, n_cols, ct_indptr, s->c_nnz, st);
+    if (rc != LSS_OK) { lss_solver_destroy(s); return rc; }
     *solver = s;
     return LSS_OK;
 }
@@ -327,16 +375,25 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
         e2 = (*s->prof_events)[3 * prof_slot + 2];
         LSS_CUDA(cudaEventRecord(e0, st));
     }
-    if (s->ell_rows > 0) {
-        LSS_TRY(ell_spmv_launch(s->ell_rows, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, v, s->u, LSS_SPMV_SCALE, s->w, stop, st));
-        s->launches += 1;
-        LSS_TRY(spmv_launch(s->n_rows - s->ell_rows, s->c_indptr, s->c_indices, s->c_data, v, s->u + s->ell_rows, LSS_SPMV_SCALE,
-                            s->w + s->ell_rows, s->c_nnz, &s->plan_c, stop, st, &s->launches));
+    if (s->blocks) {
+        // constraint rows: q = C^T (w_c .* (C v)) with the tiled CSR kernel (writes every entry of q) ...
+        if (s->n_con > 0) {
+            LSS_TRY(spmv_launch(s->n_con, s->c_indptr, s->c_indices, s->c_data, v, s->u + s->n_data, LSS_SPMV_SCALE,
+                                s->w + s->n_data, s->c_nnz, &s->plan_c, stop, st, &s->launches));
+            LSS_TRY(spmv_launch(s->n_cols, s->ct_indptr, s->ct_indices, s->ct_data, s->u + s->n_data, s->buf, LSS_SPMV_PLAIN, nullptr,
+                                s->c_nnz, &s->plan_ct, stop, st, &s->launches));
+        } else {
+            LSS_CUDA(cudaMemsetAsync(s->buf, 0, sizeof(double) * s->n_cols, st));
+        }
+        if (timed) LSS_CUDA(cudaEventRecord(e1, st));
+        // ... data rows: q += G^T (w .* (G v)), one fused pass over the ELL copy of G
+        LSS_TRY(ell_normal_launch(0, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, v, s->w, nullptr, s->buf, stop, st));
+        if (s->n_data > 0) s->launches += 1;
     } else {
         LSS_TRY(spmv_launch(s->n_rows, s->indptr, s->indices, s->data, v, s->u, LSS_SPMV_SCALE, s->w, s->nnz, &s->plan_a, stop, st, &s->launches));
+        if (timed) LSS_CUDA(cudaEventRecord(e1, st));
+        LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->buf, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, stop, st, &s->launches));
     }
-    if (timed) LSS_CUDA(cudaEventRecord(e1, st));
-    LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->buf, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, stop, st, &s->launches));
     if (timed) LSS_CUDA(cudaEventRecord(e2, st));
     int64_t n_red = s->n_cols;
     if (with_dot) {
@@ -350,47 +407,34 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     return LSS_OK;
 }
 
-extern "C" int lss_solver_split_rows(lss_solver_t *s, int64_t n_lead, int32_t row_len, const int32_t *c_indptr,
-                                     const int32_t *c_indices, const double *c_data) {
-    if (!s || n_lead < 0 || n_lead > s->n_rows) return fail(LSS_EINVAL, "solver_split_rows: bad row count");
-    if (row_len < 1 || row_len > 16) return fail(LSS_EINVAL, "solver_split_rows: row length must be 1..16");
-    cudaStream_t st = s->stream;
-    const int64_t n_rest = s->n_rows - n_lead;
-    int c_nnz = 0;
-    if (n_rest > 0) {
-        if (!c_indptr) return fail(LSS_EINVAL, "solver_split_rows: the trailing rows need their own CSR");
-        LSS_CUDA(cudaMemcpyAsync(&c_nnz, c_indptr + n_rest, sizeof(int), cudaMemcpyDeviceToHost, st));
-        LSS_CUDA(cudaStreamSynchronize(st));
-    }
-    if (s->ell_col) { cudaFreeAsync(s->ell_col, st); s->ell_col = nullptr; }
-    if (s->ell_val) { cudaFreeAsync(s->ell_val, st); s->ell_val = nullptr; }
-    s->ell_rows = 0;
-    if (n_lead == 0) return LSS_OK;
-    const int64_t n_pad = (n_lead + 31) / 32 * 32;           // keeps every column 256-byte aligned
-    LSS_CUDA(cudaMallocAsync((void **)&s->ell_col, sizeof(int32_t) * n_pad * row_len, st));
-    LSS_CUDA(cudaMallocAsync((void **)&s->ell_val, sizeof(double) * n_pad * row_len, st));
-    LSS_TRY(ell_build(n_lead, row_len, s->indptr, s->indices, s->data, s->ell_col, s->ell_val, n_pad, st));
-    spmv_plan_destroy(&s->plan_c);
-    if (n_rest > 0) LSS_TRY(spmv_plan_create(&s->plan_c, n_rest, c_indptr, c_nnz, st));
-    s->c_indptr = c_indptr; s->c_indices = c_indices; s->c_data = c_data; s->c_nnz = c_nnz;
-    s->ell_pad = n_pad; s->ell_k = row_len; s->ell_rows = n_lead;
-    return LSS_OK;
-}
-
 extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
     if (!s || !w) return fail(LSS_EINVAL, "solver_set_weights: null argument");
     cudaStream_t st = s->stream;
     if (s->n_rows > 0) LSS_CUDA(cudaMemcpyAsync(s->w, w, sizeof(double) * s->n_rows, cudaMemcpyDeviceToDevice, st));
-    // g = A^T (w .* b)
+    // g = A^T (w .* b)  and the Jacobi diagonal diag(A^T W A)
     if (s->n_rows > 0) {
         mul_kernel<<<stride_grid(s->n_rows, VEC_BLOCK), VEC_BLOCK, 0, st>>>(s->n_rows, s->w, s->rhs, s->u);
         LSS_LAUNCH_CHECK();
     }
-    LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->g, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, nullptr, st, nullptr));
+    if (s->blocks) {
+        if (s->n_con > 0) {
+            LSS_TRY(spmv_launch(s->n_cols, s->ct_indptr, s->ct_indices, s->ct_data, s->u + s->n_data, s->g, LSS_SPMV_PLAIN, nullptr,
+                                s->c_nnz, &s->plan_ct, nullptr, st, nullptr));
+            diag_kernel<<<stride_grid(s->n_cols * 32, 256, 16), 256, 0, st>>>(s->n_cols, s->ct_indptr, s->ct_indices, s->ct_data,
+                                                                              s->w + s->n_data, s->diag);
+            LSS_LAUNCH_CHECK();
+        } else {
+            LSS_CUDA(cudaMemsetAsync(s->g, 0, sizeof(double) * s->n_cols, st));
+            LSS_CUDA(cudaMemsetAsync(s->diag, 0, sizeof(double) * s->n_cols, st));
+        }
+        LSS_TRY(ell_normal_launch(1, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, s->rhs, s->g, nullptr, st));
+        LSS_TRY(ell_normal_launch(2, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, nullptr, s->diag, nullptr, st));
+    } else {
+        LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->g, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, nullptr, st, nullptr));
+        diag_kernel<<<stride_grid(s->n_cols * 32, 256, 16), 256, 0, st>>>(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->w, s->diag);
+        LSS_LAUNCH_CHECK();
+    }
     LSS_TRY(comm_allreduce(s->comm, s->g, s->n_cols, 0, 0, st));
-    // Jacobi preconditioner from diag(A^T W A)
-    diag_kernel<<<stride_grid(s->n_cols * 32, 256, 16), 256, 0, st>>>(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->w, s->diag);
-    LSS_LAUNCH_CHECK();
     LSS_TRY(comm_allreduce(s->comm, s->diag, s->n_cols, 0, 0, st));
     jacobi_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(s->n_cols, s->diag, s->fixed, s->g, s->minv, s->part2);
     LSS_LAUNCH_CHECK();

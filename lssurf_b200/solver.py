@@ -1,8 +1,15 @@
 """Python handle on the matrix-free normal-equation PCG solver (``lss_solver_*`` in the C ABI).
 
 Stands in for the single line ``m0 = Ip_c.dot(sparseqr.solve(Ip_r.dot(TCinv.dot(Gcoo)), Ip_r.dot(TCinv.dot(rhs))))``
-(LSsurf/smooth_fit.py:142).  The operator A = [G_local; C_local] and its transpose stay in GPU
-memory for the whole edit loop; only the row-weight vector changes between outer iterations.
+(LSsurf/smooth_fit.py:142).  The operator stays in GPU memory for the whole edit loop; only the row-weight vector
+changes between outer iterations.
+
+Two forms (include/lssurf_b200.h):
+  * block form (default when every data row holds <= 16 entries, which is always the case for interpolation rows):
+    G as an ELL copy applied by the fused ``q += G^T (w .* (G p))`` kernel, the constraint rows as a CSR pair
+    (C, C^T) -- one pass over G per CG iteration, no transpose of G;
+  * generic form: A = [G; C] and an explicit A^T as CSR, two tiled CSR products per iteration (deterministic;
+    selected with ``fused=False`` or ``LSS_NO_FUSED=1``).
 """
 import ctypes as C
 import os
@@ -15,37 +22,41 @@ from .lin_op import DeviceCSR
 
 
 class NormalSolver(object):
-    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, ell=True):
+    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True):
         """G: DeviceCSR of this rank's data rows; Cn: DeviceCSR of this rank's constraint rows;
         z / sigma: data values and errors (CUDA fp64); prior / Ec: constraint right-hand side and sigma;
         fixed_cols: columns held at zero (reference epoch)."""
         L = _cabi.lib()
-        self.n_data = G.shape[0]
-        self.n_cols = G.shape[1]
-        self.A = DeviceCSR.vstack([G, Cn]) if Cn.shape[0] > 0 else G
-        # the data rows are the leading rows of A: a view, no second copy of G
-        self.G = DeviceCSR(self.A.indptr[:self.n_data + 1], self.A.indices, self.A.data, (self.n_data, self.n_cols))
-        self.At = self.A.transpose()
+        self.n_data, self.n_con, self.n_cols = G.shape[0], Cn.shape[0], G.shape[1]
+        self.G, self.C = G, Cn
         self.rhs = torch.cat([z, prior]).contiguous()
         self.sigma = sigma
-        self.w = torch.empty(self.A.shape[0], dtype=torch.float64, device=z.device)
+        self.w = torch.empty(self.n_data + self.n_con, dtype=torch.float64, device=z.device)
         self.w[self.n_data:] = 1. / (Ec * Ec)                       # constraint rows: fixed weight 1/E_c^2
         self.fixed = _cabi.to_dev(np.asarray(fixed_cols), torch.int32)
         self.dist = dist
         self.handle = C.c_void_p(0)
         comm = dist.comm if dist is not None else None
-        _cabi.check(L.lss_solver_create(C.byref(self.handle), self.A.shape[0], self.n_cols, _cabi.ptr(self.A.indptr),
-                                        _cabi.ptr(self.A.indices), _cabi.ptr(self.A.data), _cabi.ptr(self.At.indptr),
-                                        _cabi.ptr(self.At.indices), _cabi.ptr(self.At.data), _cabi.ptr(self.rhs),
-                                        _cabi.ptr(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
-        # data rows have a fixed, short row length: apply them in column-major (ELL) form
-        self.C = Cn
-        row_len = int((G.indptr[1:] - G.indptr[:-1]).max().item()) if self.n_data > 0 else 0
-        self.ell = bool(ell) and 1 <= row_len <= 16 and not os.environ.get('LSS_NO_ELL')
-        if self.ell:
-            has_c = Cn.shape[0] > 0
-            _cabi.check(L.lss_solver_split_rows(self.handle, self.n_data, row_len, _cabi.ptr(Cn.indptr) if has_c else None,
-                                                _cabi.ptr(Cn.indices) if has_c else None, _cabi.ptr(Cn.data) if has_c else None))
+        row_len = int((G.indptr[1:] - G.indptr[:-1]).max().item()) if self.n_data > 0 else 1
+        self.fused = bool(fused) and row_len <= 16 and not os.environ.get('LSS_NO_FUSED')
+        if self.fused:
+            self.Ct = Cn.transpose() if self.n_con > 0 else None
+            p = _cabi.ptr
+            nul = C.c_void_p(0)
+            _cabi.check(L.lss_solver_create_blocks(
+                C.byref(self.handle), self.n_data, self.n_con, self.n_cols, max(row_len, 1),
+                p(G.indptr), p(G.indices), p(G.data),
+                p(Cn.indptr) if self.n_con else nul, p(Cn.indices) if self.n_con else nul, p(Cn.data) if self.n_con else nul,
+                p(self.Ct.indptr) if self.n_con else nul, p(self.Ct.indices) if self.n_con else nul,
+                p(self.Ct.data) if self.n_con else nul,
+                p(self.rhs), p(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
+        else:
+            self.A = DeviceCSR.vstack([G, Cn]) if self.n_con > 0 else G
+            self.At = self.A.transpose()
+            _cabi.check(L.lss_solver_create(C.byref(self.handle), self.A.shape[0], self.n_cols, _cabi.ptr(self.A.indptr),
+                                            _cabi.ptr(self.A.indices), _cabi.ptr(self.A.data), _cabi.ptr(self.At.indptr),
+                                            _cabi.ptr(self.At.indices), _cabi.ptr(self.At.data), _cabi.ptr(self.rhs),
+                                            _cabi.ptr(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
         self.x = torch.zeros(self.n_cols, dtype=torch.float64, device=z.device)
         self.last = {}
 
@@ -66,7 +77,8 @@ class NormalSolver(object):
         st = (C.c_double * 6)()
         _cabi.check(_cabi.lib().lss_solver_stats(self.handle, st))
         self.last = dict(iterations=it.value, relres=rel.value, ms=st[0], ms_A=st[1], ms_At=st[2], n_apply=int(st[3]),
-                         launches=int(st[4]), nnz=int(st[5]), rows=int(self.A.shape[0]))
+                         launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused,
+                         n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz)
         return self.x
 
     def residual(self, x, z, out=None):

@@ -225,6 +225,24 @@ def test_smooth_fit_medium_against_oracle(L):
     assert G == digest(*res['sys']['G'][:3])
 
 
+def test_fused_and_generic_solver_agree(L):
+    """Block form (fused ELL kernel with RED atomics) vs generic form (two deterministic CSR products): same system,
+    same solution to solver tolerance, same masks."""
+    import os
+    from lssurf_b200 import synthetic
+    pts, kw = synthetic.icesat2_tracks(n=150_000, width=2.e4, seed=6)
+    S1 = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, **kw)
+    os.environ['LSS_NO_FUSED'] = '1'
+    try:
+        S2 = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, **kw)
+    finally:
+        del os.environ['LSS_NO_FUSED']
+    assert S1['timing']['pcg'][0]['fused'] and not S2['timing']['pcg'][0]['fused']
+    assert rel_l2(S1['m']['all'], S2['m']['all']) < 1e-9
+    assert np.array_equal(S1['data'].three_sigma_edit, S2['data'].three_sigma_edit)
+    assert np.allclose(S1['m']['bias']['val'], S2['m']['bias']['val'], rtol=0, atol=1e-9)
+
+
 def test_large_scale_properties(L):
     """Full-size properties (cfg 3 shapes, 1e6 points) that need no oracle: row sums of the interpolation
     matrix are exactly 1 up to rounding, CSR is canonical, G^T products are adjoint, the solve reduces the residual."""
