@@ -125,6 +125,12 @@ int lss_group_median(const int32_t *ids, const double *vals, int64_t n, int32_t 
 int lss_spmv(int64_t n_rows, int64_t n_cols, const int32_t *indptr, const int32_t *indices, const double *data,
              const double *x, double *y, int32_t mode, const double *s, void *stream);
 
+/* q = A^T u computed from the CSR rows of A by scattering (fp64 RED atomics; summation order is run dependent).
+ * For occasional transpose products (parse_model's count / misfit maps, smooth_fit.py:339-345) where building
+ * A^T with lss_csr_transpose is not worth it. */
+int lss_csr_rmatvec(int64_t n_rows, int64_t n_cols, const int32_t *indptr, const int32_t *indices, const double *data,
+                    const double *u, double *q, void *stream);
+
 /* Same product with the structure-dependent set-up (first row of every non-zero tile, carry buffers) done
  * once: for matrices that are multiplied many times (the edit loop's residual and G^T products). */
 typedef struct lss_spmv_plan lss_spmv_plan_t;

@@ -47,6 +47,7 @@ SIGNATURES = {
     'lss_dense_rank_f64': [_vp, _i64, _f64, _vp, _pf64, _i64, _pi64, _vp],
     'lss_group_median': [_vp, _vp, _i64, _i32, _vp, _vp],
     'lss_spmv': [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    'lss_csr_rmatvec': [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     'lss_spmv_plan_create': [C.POINTER(_vp), _i64, _vp, _vp],
     'lss_spmv_plan_destroy': [_vp],
     'lss_spmv_planned': [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
@@ -292,6 +293,13 @@ def spmv(indptr, indices, data, x, n_rows, n_cols, mode=SPMV_PLAIN, s=None, out=
     y = out if out is not None else torch.empty(n_rows, dtype=torch.float64, device=device())
     check(L.lss_spmv(n_rows, n_cols, ptr(indptr), ptr(indices), ptr(data), ptr(x), ptr(y), mode, ptr(s), stream()))
     return y
+
+
+def csr_rmatvec(indptr, indices, data, u, n_rows, n_cols):
+    """q = A^T u from the CSR rows of A (scatter with atomics)."""
+    q = torch.empty(n_cols, dtype=torch.float64, device=device())
+    check(lib().lss_csr_rmatvec(n_rows, n_cols, ptr(indptr), ptr(indices), ptr(data), ptr(u), ptr(q), stream()))
+    return q
 
 
 class SpmvPlan(object):

@@ -356,6 +356,18 @@ ell_spmv_kernel(int64_t n_rows, int64_t n_pad, const int *__restrict__ ell_col, 
     y[r] = epilogue(acc, mode, s, r);
 }
 
+// q += A^T u straight from the CSR rows of A (one thread per row, one RED.ADD.F64 per entry): for the handful of
+// transpose products per fit that do not justify building and storing A^T (parse_model's per-node sums).
+__global__ void __launch_bounds__(256)
+csr_rmatvec_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ data,
+                   const double *__restrict__ u, double *__restrict__ q) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const double ur = u[r];
+    if (ur == 0.0) return;
+    for (int k = indptr[r]; k < indptr[r + 1]; ++k) atomicAdd(q + indices[k], data[k] * ur);
+}
+
 // Fused normal-equation product of the data block:  q += G^T (w .* (G x))  in ONE pass over the ELL copy of G.
 // Thread r forms t = sum_k v[k] x[c[k]], u = w[r] t and scatters v[k] u into q[c[k]].  Neighbouring rows (points that
 // are neighbours on the ground) hit the same grid nodes, so contributions are first summed over runs of equal
@@ -502,6 +514,16 @@ extern "C" int lss_spmv_planned(lss_spmv_plan *plan, int64_t n_rows, const int32
     if (mode < 0 || mode > 2) return fail(LSS_EINVAL, "spmv: unknown mode %d", mode);
     if (mode != LSS_SPMV_PLAIN && !s) return fail(LSS_EINVAL, "spmv: mode %d needs the vector s", mode);
     return spmv_launch(n_rows, indptr, indices, data, x, y, mode, s, plan->nnz, &plan->p, nullptr, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int lss_csr_rmatvec(int64_t n_rows, int64_t n_cols, const int32_t *indptr, const int32_t *indices, const double *data,
+                               const double *u, double *q, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_cols > 0) LSS_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * n_cols, st));
+    if (n_rows <= 0) return LSS_OK;
+    csr_rmatvec_kernel<<<ceil_div(n_rows, 256), 256, 0, st>>>(n_rows, indptr, indices, data, u, q);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
 }
 
 extern "C" int lss_spmv(int64_t n_rows, int64_t n_cols, const int32_t *indptr, const int32_t *indices, const double *data,

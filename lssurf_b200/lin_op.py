@@ -27,6 +27,30 @@ _DEV_DTYPE = {'r': torch.int32, 'c': torch.int32, 'v': torch.float64}
 _HOST_DTYPE = {'r': np.int64, 'c': np.int64, 'v': np.float64}
 
 
+def _union_of_columns(arrays):
+    """np.unique(np.concatenate(arrays)); column lists are almost always contiguous ranges, whose union is merged
+    as intervals instead of sorting millions of integers."""
+    if not arrays:
+        return np.array([], dtype=int)
+    spans = []
+    for a in arrays:
+        a = np.asarray(a)
+        if a.size == 0:
+            continue
+        if a[-1] - a[0] == a.size - 1 and (a.size < 3 or (a[1] - a[0] == 1 and a[a.size // 2] - a[0] == a.size // 2)):
+            spans.append((int(a[0]), int(a[-1]) + 1))
+        else:
+            return np.unique(np.concatenate(arrays))
+    spans.sort()
+    merged = []
+    for lo, hi in spans:
+        if merged and lo <= merged[-1][1]:
+            merged[-1][1] = max(merged[-1][1], hi)
+        else:
+            merged.append([lo, hi])
+    return np.concatenate([np.arange(lo, hi) for lo, hi in merged]) if merged else np.array([], dtype=int)
+
+
 class DeviceCSR(object):
     """Canonical CSR on the GPU (int32 indptr / indices, fp64 data) plus a lazily built transpose."""
 
@@ -52,6 +76,10 @@ class DeviceCSR(object):
         if self._plan is None:
             self._plan = _cabi.SpmvPlan(self.indptr, self.shape[0])
         return _cabi.spmv_planned(self._plan, self.indptr, self.indices, self.data, x, self.shape[0], mode, s, out)
+
+    def rdot(self, u):
+        """A^T u without building the transpose (scatter kernel; use transpose().dot for repeated products)."""
+        return _cabi.csr_rmatvec(self.indptr, self.indices, self.data, u, self.shape[0], self.shape[1])
 
     def row_slice(self, lo, hi):
         """Rows [lo, hi) as a new DeviceCSR (used to shard rows over ranks)."""
@@ -95,7 +123,7 @@ class lin_op(object):
         self._host = {'r': np.array([], dtype=int), 'c': np.array([], dtype=int), 'v': np.array([], dtype=float)}
         self._dev = {'r': None, 'c': None, 'v': None}
         self._csr_cache = {}
-        self.ind0 = np.zeros([0], dtype=int)
+        self._ind0 = np.zeros([0], dtype=int)      # or a list of parts: ('arange', n) / ndarray, joined on demand
         self.TOC = {'rows': dict(), 'cols': dict()}
         self.grid = grid
         self.dst_grid = None
@@ -104,6 +132,21 @@ class lin_op(object):
         self.prior = None
         self.shape = None
         self.size = None
+
+    # ------------------------------------------------------------------ ind0 (lazy: interpolation ops index 1e7 points)
+    @property
+    def ind0(self):
+        if isinstance(self._ind0, list):
+            self._ind0 = np.concatenate([np.arange(0, p[1], dtype='int') if isinstance(p, tuple) else np.asarray(p)
+                                         for p in self._ind0]) if self._ind0 else np.zeros([0], dtype=int)
+        return self._ind0
+
+    @ind0.setter
+    def ind0(self, value):
+        self._ind0 = value
+
+    def _ind0_parts(self):
+        return list(self._ind0) if isinstance(self._ind0, list) else [self._ind0]
 
     # ------------------------------------------------------------------ triplet storage
     def _get_host(self, f):
@@ -196,8 +239,8 @@ class lin_op(object):
         self._set_device(rows, cols, vals)
         self._valid_pts = valid if n_bad > 0 else None
         self.N_eq = n_pts
-        self.ind0 = np.arange(0, n_pts, dtype='int')
-        self.TOC['rows'] = {self.name: np.arange(self.N_eq, dtype='int')}
+        self._ind0 = [('arange', n_pts)]                       # np.arange(n_pts), materialised on access
+        self.TOC['rows'] = {self.name: range(self.N_eq)}
         self.TOC['cols'] = {self.grid.name: np.arange(self.grid.col_0, self.grid.col_0 + self.grid.N_nodes)}
         self._update_shape()
         return self
@@ -325,7 +368,7 @@ class lin_op(object):
         else:
             for f in _FIELDS:
                 self._set_host(f, np.append(getattr(self, f), getattr(op, f)))
-        self.ind0 = np.append(self.ind0, op.ind0)
+        self._ind0 = self._ind0_parts() + op._ind0_parts()
         for key in op.TOC['cols'].keys():
             self.TOC['cols'][key] = op.TOC['cols'][key]
         self.col_N = np.maximum(self.col_N, op.col_N)
@@ -348,7 +391,7 @@ class lin_op(object):
                     TOC_cols[key] = val
                     all_cols.append(np.asarray(val).ravel())
             if self.name is not None:
-                TOC_cols[self.name] = np.unique(np.concatenate(all_cols)) if all_cols else np.array([], dtype=int)
+                TOC_cols[self.name] = _union_of_columns(all_cols)
         if self.col_N is None:
             self.col_N = np.max(np.array([op.col_N for op in ops]))
         self.TOC['cols'] = TOC_cols

@@ -336,10 +336,10 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
         rs = r_in / torch.sqrt(f['sigma'] ** 2 + f['sigma_extra'] ** 2)
     else:
         rs = r_in / f['sigma']
-    Gt = G_data._csr_device(col_N=n_cols, row_N=int(r.numel())).transpose()
+    Gd = G_data._csr_device(col_N=n_cols, row_N=int(r.numel()))
     sums = {}
     for key, vec in (('count', tse.to(torch.float64)), ('misfit_scaled_rms', rs * rs), ('misfit_rms', r_in * r_in)):
-        full = Gt.dot(vec.contiguous())
+        full = Gd.rdot(vec.contiguous())                 # G^T vec by scatter: three products do not pay for a transpose
         sums[key] = (full if dist is None else dist.allreduce_sum(full)).cpu().numpy()
     for ff in ['dz', 'z0']:
         cols = np.asarray(G_data.TOC['cols'][ff])
@@ -524,8 +524,8 @@ def smooth_fit(**kwargs):
         for op, res, g in ((op_z0, rz, grids['z0']), (op_dz, rd, grids['dz'])):
             op._set_device(res[0], res[1], res[2])
             op.N_eq = n_all
-            op.ind0 = np.arange(0, n_all, dtype='int')
-            op.TOC['rows'] = {op.name: np.arange(n_all, dtype='int')}
+            op._ind0 = [('arange', n_all)]
+            op.TOC['rows'] = {op.name: range(n_all)}
             op.TOC['cols'] = {g.name: np.arange(g.col_0, g.col_0 + g.N_nodes)}
             op._update_shape()
     else:
@@ -643,5 +643,6 @@ def smooth_fit(**kwargs):
         stages.mark('parse_model')
     else:
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
+    stages.mark('epilogue')
     return {'m': m, 'E': E, 'data': data, 'grids': grids, 'valid_data': valid_data, 'TOC': Gc.TOC, 'R': R, 'RMS': RMS,
             'timing': timing, 'E_RMS': args['E_RMS'], 'dzdt_lags': args['dzdt_lags']}
