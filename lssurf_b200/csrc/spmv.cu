@@ -406,18 +406,19 @@ ell_normal_kernel(int64_t n_rows, int64_t n_pad, const int *__restrict__ ell_col
     for (int k = 0; k < K; ++k) {
         const int col = active ? c[k] : -1 - (int)lane;
         double sum = (MODE == 2) ? v[k] * v[k] * u : v[k] * u;
+        // runs of equal columns inside each 8-lane group: heads from one shuffle + one ballot, the segmented scan
+        // then needs only the value shuffles (distance to the run head comes from the ballot bits)
         const int prev = __shfl_up_sync(0xffffffffu, col, 1);
-        bool head = sub == 0 || prev != col;
-        const int next_head = __shfl_down_sync(0xffffffffu, (int)head, 1);   // every lane must take part: no short-circuit
-        const bool tail = sub == 7 || next_head != 0;
-        bool flag = head;
+        const bool head = sub == 0 || prev != col;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned grp = (heads >> (lane & 24u)) & 0xffu;
+        const int dist = (int)sub - (31 - __clz((int)(grp & ((2u << sub) - 1u))));
+        const bool tail = sub == 7 || ((grp >> (sub + 1)) & 1u);
+        if (heads != 0xffffffffu) {          // warp-uniform: some neighbouring rows share this column
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            const double s2 = __shfl_up_sync(0xffffffffu, sum, o);
-            const int f2 = __shfl_up_sync(0xffffffffu, (int)flag, o);
-            if (sub >= (unsigned)o && !flag) {
-                sum += s2;
-                flag = f2 != 0;
+            for (int o = 1; o < 8; o <<= 1) {
+                const double s2 = __shfl_up_sync(0xffffffffu, sum, o);
+                if (dist >= o) sum += s2;
             }
         }
         if (tail && col >= 0 && sum != 0.0) atomicAdd(q + col, sum);
