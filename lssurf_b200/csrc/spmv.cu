@@ -54,13 +54,19 @@ __device__ __forceinline__ int64_t lower_bound_i32(const int *__restrict__ a, in
     return lo;
 }
 
-// bounds[t] = first row whose entries start at or after non-zero t*tile (bounds[n_tiles] = n_rows): the rows a
-// tile owns are [bounds[t], bounds[t+1]).
+// Row range touched by tile t (non-zeros [t*tile, min((t+1)*tile, nnz))): bounds[2t] = the row holding non-zero t*tile
+// (first row whose end lies beyond it), bounds[2t+1] = one past the row holding the tile's last non-zero.  Empty rows
+// before / after that range belong to no tile (they are pre-filled), so a tile never walks a long block of empty rows
+// (A^T of a row shard has >10^5 consecutive empty rows).
 __global__ void __launch_bounds__(256)
 spmv_tile_bounds_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, int n_tiles, int tile, int *__restrict__ bounds) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    bounds[t] = (t == n_tiles) ? (int)n_rows : (int)lower_bound_i32(indptr, n_rows, (int64_t)t * tile);
+    if (t >= n_tiles) return;
+    const int64_t k0 = (int64_t)t * tile;
+    const int64_t k1 = (k0 + tile < nnz) ? k0 + tile : nnz;
+    // first r in [0, n_rows) with indptr[r + 1] > k0   /   first r with indptr[r + 1] >= k1
+    bounds[2 * t] = (int)lower_bound_i32(indptr + 1, n_rows - 1, k0 + 1);
+    bounds[2 * t + 1] = (int)lower_bound_i32(indptr + 1, n_rows - 1, k1) + 1;
 }
 
 template <int BLOCK>
@@ -68,17 +74,18 @@ __device__ __forceinline__ void reduce_rows(const double *__restrict__ prod, int
                                             const int *__restrict__ indptr, double *__restrict__ y, int mode,
                                             const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row) {
     // carry-in: the row that started in an earlier tile and still has entries here
-    const bool has_carry = r_lo > 0 && (int64_t)indptr[r_lo] > k0;
-    const int64_t n_virtual = (r_hi - r_lo) + 1;                      // virtual row 0 is the carry-in
+    const bool has_carry = (int64_t)indptr[r_lo] < k0;                // r_lo itself started in an earlier tile
+    const int64_t first = r_lo + (has_carry ? 1 : 0);                 // first row that starts in this tile
+    const int64_t n_virtual = (r_hi - first) + 1;                     // virtual row 0 is the carry-in
     if (n_virtual <= 2 * (BLOCK / 32)) {
         // few, long rows: one warp per row
         const int w = threadIdx.x >> 5;
         for (int64_t v = w; v < n_virtual; v += BLOCK / 32) {
-            int64_t b, e, r = r_lo + v - 1;
+            int64_t b, e, r = first + v - 1;
             if (v == 0) {
                 if (!has_carry) continue;
                 b = k0;
-                e = (int64_t)indptr[r_lo];
+                e = (int64_t)indptr[r_lo + 1];
             } else {
                 b = indptr[r];
                 e = indptr[r + 1];
@@ -95,11 +102,11 @@ __device__ __forceinline__ void reduce_rows(const double *__restrict__ prod, int
         }
     } else {
         for (int64_t v = threadIdx.x; v < n_virtual; v += BLOCK) {
-            int64_t b, e, r = r_lo + v - 1;
+            int64_t b, e, r = first + v - 1;
             if (v == 0) {
                 if (!has_carry) continue;
                 b = k0;
-                e = (int64_t)indptr[r_lo];
+                e = (int64_t)indptr[r_lo + 1];
             } else {
                 b = indptr[r];
                 e = indptr[r + 1];
@@ -112,7 +119,7 @@ __device__ __forceinline__ void reduce_rows(const double *__restrict__ prod, int
             else y[r] = open ? acc : epilogue(acc, mode, s, r);
         }
     }
-    if (threadIdx.x == 0) carry_row[tile] = has_carry ? (int)(r_lo - 1) : -1;
+    if (threadIdx.x == 0) carry_row[tile] = has_carry ? (int)r_lo : -1;
 }
 
 template <int BLOCK, int IPT>
@@ -127,7 +134,7 @@ spmv_tile_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, co
     const int64_t k1 = (k0 + TILE < nnz) ? k0 + TILE : nnz;
     // issued first, consumed after the staging loads are in flight (no serialised round trip per CTA)
     const double stop_v = stop ? *reinterpret_cast<const volatile double *>(stop) : 0.0;
-    const int64_t r_lo = tile_bounds[blockIdx.x], r_hi = tile_bounds[blockIdx.x + 1];
+    const int64_t r_lo = tile_bounds[2 * blockIdx.x], r_hi = tile_bounds[2 * blockIdx.x + 1];
     // stage the products: coalesced streaming loads of the matrix, gathered loads of x
     {
         int col[IPT];
@@ -179,7 +186,7 @@ spmv_persistent_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__re
     for (; t < n_tiles; t += gridDim.x) {
         const int64_t k0 = (int64_t)t * TILE;
         const int64_t k1 = (k0 + TILE < nnz) ? k0 + TILE : nnz;
-        const int64_t r_lo = tile_bounds[t], r_hi = tile_bounds[t + 1];
+        const int64_t r_lo = tile_bounds[2 * t], r_hi = tile_bounds[2 * t + 1];
         double *prod = prod_s[buf];
         double xg[IPT];
 #pragma unroll
@@ -211,7 +218,8 @@ spmv_fixup_kernel(int n_tiles, const double *__restrict__ carry_val, const int *
 }
 
 __global__ void __launch_bounds__(256)
-spmv_empty_kernel(int64_t n_rows, double *__restrict__ y, int mode, const double *__restrict__ s) {
+spmv_empty_kernel(int64_t n_rows, double *__restrict__ y, int mode, const double *__restrict__ s, const double *__restrict__ stop) {
+    if (stop && *stop != 0.0) return;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
         y[r] = epilogue(0.0, mode, s, r);
 }
@@ -225,10 +233,10 @@ int spmv_plan_create(SpmvPlan *plan, int64_t n_rows, const int32_t *indptr, int6
     if (plan->n_tiles == 0) return LSS_OK;
     plan->stream = stream;
     Scratch::configure_pool();
-    LSS_CUDA(cudaMallocAsync((void **)&plan->bounds, sizeof(int) * (plan->n_tiles + 1), stream));
+    LSS_CUDA(cudaMallocAsync((void **)&plan->bounds, sizeof(int) * 2 * plan->n_tiles, stream));
     LSS_CUDA(cudaMallocAsync((void **)&plan->carry_val, sizeof(double) * plan->n_tiles, stream));
     LSS_CUDA(cudaMallocAsync((void **)&plan->carry_row, sizeof(int) * plan->n_tiles, stream));
-    spmv_tile_bounds_kernel<<<ceil_div(plan->n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, plan->n_tiles, plan->tile, plan->bounds);
+    spmv_tile_bounds_kernel<<<ceil_div(plan->n_tiles, 256), 256, 0, stream>>>(n_rows, nnz, indptr, plan->n_tiles, plan->tile, plan->bounds);
     LSS_LAUNCH_CHECK();
     return LSS_OK;
 }
@@ -268,7 +276,7 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
                 cudaStream_t stream, int64_t *launches) {
     if (n_rows <= 0) return LSS_OK;
     if (nnz == 0) {
-        spmv_empty_kernel<<<stride_grid(n_rows, 256), 256, 0, stream>>>(n_rows, y, mode, s);
+        spmv_empty_kernel<<<stride_grid(n_rows, 256), 256, 0, stream>>>(n_rows, y, mode, s, nullptr);
         LSS_LAUNCH_CHECK();
         if (launches) *launches += 1;
         return LSS_OK;
@@ -284,12 +292,16 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
     } else {
         LSS_CUDA(cv.alloc(sizeof(double) * n_tiles, stream));
         LSS_CUDA(cr.alloc(sizeof(int) * n_tiles, stream));
-        LSS_CUDA(tb.alloc(sizeof(int) * (n_tiles + 1), stream));
+        LSS_CUDA(tb.alloc(sizeof(int) * 2 * n_tiles, stream));
         carry_val = cv.as<double>(); carry_row = cr.as<int>(); bounds = tb.as<int>();
-        spmv_tile_bounds_kernel<<<ceil_div(n_tiles + 1, 256), 256, 0, stream>>>(n_rows, nnz, indptr, n_tiles, tile, bounds);
+        spmv_tile_bounds_kernel<<<ceil_div(n_tiles, 256), 256, 0, stream>>>(n_rows, nnz, indptr, n_tiles, tile, bounds);
         LSS_LAUNCH_CHECK();
         if (launches) *launches += 1;
     }
+    // rows without entries (and nothing else) keep this value: y = epilogue(0)
+    spmv_empty_kernel<<<stride_grid(n_rows, 256), 256, 0, stream>>>(n_rows, y, mode, s, stop);
+    LSS_LAUNCH_CHECK();
+    if (launches) *launches += 1;
 #define LSS_SPMV_CASE(V, B, I)                                                                                     \
     case V: launch_tile<B, I>(n_tiles, stream, n_rows, nnz, indptr, indices, data, x, y, mode, s, carry_val, carry_row, bounds, stop); break;
     switch (variant) {

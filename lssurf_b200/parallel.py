@@ -36,6 +36,23 @@ class DistContext(object):
         dist.all_gather_object(parts, arr)
         return np.concatenate(parts)
 
+    def gather_rows_device(self, t, n_total):
+        """Concatenate the per-rank row blocks of a 1-D CUDA tensor in rank order on every rank (NCCL all-gather
+        of equal-size padded blocks; the block sizes follow from shard()).  Falls back to the host transport
+        when torch.distributed is not running on NCCL."""
+        if self.world == 1:
+            return t
+        import torch.distributed as dist
+        if dist.get_backend() != 'nccl':
+            return _cabi.to_dev(self.gather_rows(_cabi.to_host(t)))
+        sizes = [((r + 1) * n_total) // self.world - (r * n_total) // self.world for r in range(self.world)]
+        m = max(sizes)
+        pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+        pad[:t.numel()] = t
+        out = torch.empty(m * self.world, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad)
+        return torch.cat([out[i * m:i * m + sizes[i]] for i in range(self.world)])
+
     def allreduce_sum(self, t):
         """In-place fp64 sum over ranks of a CUDA tensor through the library's NCCL communicator."""
         if self.world == 1 or self.comm is None:

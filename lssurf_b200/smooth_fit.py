@@ -612,10 +612,7 @@ def smooth_fit(**kwargs):
         def to_caller(t):
             """device rows of this rank -> NumPy over all points in the caller's order"""
             if multi:
-                a = dist.gather_rows(_cabi.to_host(t))
-                if order is None:
-                    return a
-                t = _cabi.to_dev(a)
+                t = dist.gather_rows_device(t, n_all)
             if order is not None:
                 out = torch.empty_like(t)
                 out[order] = t                    # undo the internal spatial ordering on the device
