@@ -253,11 +253,15 @@ def run_b200(a):
     if p0.get('fused'):
         # block form: ONE pass over the ELL copy of G does q += G^T (w .* (G p)): 12 B per entry, the row weights,
         # x read once and q read-modify-written once (compulsory); the constraint pair (C, C^T) is the small rest
-        b_dom = 12 * p0['nnz_G'] + 8 * p0['n_data'] + 24 * n_cols
-        b_con = spmv_bytes(p0['n_con'], n_cols, p0['nnz_C'], True) + spmv_bytes(n_cols, p0['n_con'], p0['nnz_C'], False)
+        if p0.get('all_ell'):      # constraint rows ride in the same ELL block: one kernel per operator application
+            b_dom = 12 * (p0['nnz_G'] + p0['nnz_C']) + 8 * (p0['n_data'] + p0['n_con']) + 24 * n_cols
+            b_con = 0
+        else:
+            b_dom = 12 * p0['nnz_G'] + 8 * p0['n_data'] + 24 * n_cols
+            b_con = spmv_bytes(p0['n_con'], n_cols, p0['nnz_C'], True) + spmv_bytes(n_cols, p0['n_con'], p0['nnz_C'], False)
         ms_dom, ms_con = ms_at / n_apply, ms_a / n_apply
         ach = b_dom / (ms_dom / 1e3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'lss::ell_normal_kernel<13,0> (fused q += G^T (w .* (G p)), one pass over G)',
+        roofline = {'bound': 'hbm', 'kernel': 'lss::ell_normal_kernel<13,0> (fused q += A^T (w .* (A p)), one pass over the ELL rows)',
                     'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peak_src,
                     'traffic': traffic, 'bytes_per_launch': {'fused_G': b_dom, 'C_and_Ct': b_con},
                     'launch_ms': {'fused_G': ms_dom, 'C_and_Ct': ms_con},

@@ -38,18 +38,30 @@ class NormalSolver(object):
         self.handle = C.c_void_p(0)
         comm = dist.comm if dist is not None else None
         row_len = int((G.indptr[1:] - G.indptr[:-1]).max().item()) if self.n_data > 0 else 1
+        con_len = int((Cn.indptr[1:] - Cn.indptr[:-1]).max().item()) if self.n_con > 0 else 0
         self.fused = bool(fused) and row_len <= 16 and not os.environ.get('LSS_NO_FUSED')
+        self.all_ell = False
         if self.fused:
-            self.Ct = Cn.transpose() if self.n_con > 0 else None
             p = _cabi.ptr
             nul = C.c_void_p(0)
-            _cabi.check(L.lss_solver_create_blocks(
-                C.byref(self.handle), self.n_data, self.n_con, self.n_cols, max(row_len, 1),
-                p(G.indptr), p(G.indices), p(G.data),
-                p(Cn.indptr) if self.n_con else nul, p(Cn.indices) if self.n_con else nul, p(Cn.data) if self.n_con else nul,
-                p(self.Ct.indptr) if self.n_con else nul, p(self.Ct.indices) if self.n_con else nul,
-                p(self.Ct.data) if self.n_con else nul,
-                p(self.rhs), p(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
+            self.all_ell = con_len <= 16 and not os.environ.get('LSS_CSR_CONSTRAINTS')
+            if self.all_ell:
+                # constraint stencils are short rows too (<= 9 entries): one ELL block [G; C], one kernel per product
+                self.A = DeviceCSR.vstack([G, Cn]) if self.n_con > 0 else G
+                _cabi.check(L.lss_solver_create_blocks(
+                    C.byref(self.handle), self.n_data + self.n_con, 0, self.n_cols, max(row_len, con_len, 1),
+                    p(self.A.indptr), p(self.A.indices), p(self.A.data), nul, nul, nul, nul, nul, nul,
+                    p(self.rhs), p(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
+                self.A = None                      # the solver keeps its own ELL copy
+            else:
+                self.Ct = Cn.transpose() if self.n_con > 0 else None
+                _cabi.check(L.lss_solver_create_blocks(
+                    C.byref(self.handle), self.n_data, self.n_con, self.n_cols, max(row_len, 1),
+                    p(G.indptr), p(G.indices), p(G.data),
+                    p(Cn.indptr) if self.n_con else nul, p(Cn.indices) if self.n_con else nul, p(Cn.data) if self.n_con else nul,
+                    p(self.Ct.indptr) if self.n_con else nul, p(self.Ct.indices) if self.n_con else nul,
+                    p(self.Ct.data) if self.n_con else nul,
+                    p(self.rhs), p(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
         else:
             self.A = DeviceCSR.vstack([G, Cn]) if self.n_con > 0 else G
             self.At = self.A.transpose()
@@ -77,7 +89,7 @@ class NormalSolver(object):
         st = (C.c_double * 6)()
         _cabi.check(_cabi.lib().lss_solver_stats(self.handle, st))
         self.last = dict(iterations=it.value, relres=rel.value, ms=st[0], ms_A=st[1], ms_At=st[2], n_apply=int(st[3]),
-                         launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused,
+                         launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused, all_ell=self.all_ell,
                          n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz)
         return self.x
 
