@@ -132,7 +132,7 @@ int ell_spmv_launch(int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col
 
 // q += G^T (w .* (G x)) (mode 0), q += G^T (w .* b) (mode 1), q += diag(G^T W G) (mode 2) from the ELL copy of G.
 int ell_normal_launch(int mode, int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val, const double *x,
-                      const double *w, const double *b, double *q, const double *stop, cudaStream_t stream);
+                      const double *w, const double *b, double *q, double *pq_slots, const double *stop, cudaStream_t stream);
 
 }  // namespace lss
 

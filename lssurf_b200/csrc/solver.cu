@@ -17,9 +17,14 @@
 
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lss {
+
+namespace cgx = cooperative_groups;
+constexpr int PQ_SLOTS = 64;   // p.q partial sums written by the fused operator kernel
 
 constexpr int VEC_BLOCK = 256;
 constexpr int VEC_GRID = 2 * kSMs;  // fixed: the per-block partial sums have a fixed length
@@ -164,6 +169,46 @@ cg_direction_kernel(int64_t n, const double *__restrict__ r, const double *__res
     }
 }
 
+// update + direction in ONE cooperative launch (grid-wide barrier in between) for the block form of the solver;
+// also clears q and the p.q slots for the next operator application, which accumulates into them with atomics.
+__global__ void __launch_bounds__(VEC_BLOCK)
+cg_step_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots, const double *__restrict__ minv, double *__restrict__ p,
+               double *__restrict__ x, double *__restrict__ r, double *__restrict__ rz_part, double *__restrict__ scal, int parity) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    if (scal[S_DONE0 + parity] != 0.0) {          // uniform over the grid: nobody reaches the barrier
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
+        return;
+    }
+    const double pq = sum_partials(pq_slots, PQ_SLOTS, sm);
+    const double rz_old = scal[S_RZ0 + parity];
+    const double alpha = pq > 0.0 ? rz_old / pq : 0.0;
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        q[i] = 0.0;
+        v += ri * (minv[i] * ri);
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) rz_part[blockIdx.x] = v;
+    cgx::this_grid().sync();
+    const double rz_new = sum_partials(rz_part, (int)gridDim.x, sm);
+    const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK)
+        p[i] = minv[i] * r[i] + beta * p[i];
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < PQ_SLOTS) pq_slots[threadIdx.x] = 0.0;     // every block read them before the barrier
+        if (threadIdx.x == 0) {
+            scal[S_RZ0 + (parity ^ 1)] = rz_new;
+            scal[S_RZ_LAST] = rz_new;
+            const double it = scal[S_ITERS] + 1.0;
+            scal[S_ITERS] = it;
+            scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(VEC_BLOCK)
 mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) out[i] = a[i] * b[i];
@@ -225,6 +270,7 @@ struct lss_solver {
     // block form (lss_solver_create_blocks): data rows as an ELL copy applied by the fused G^T W G kernel,
     // constraint rows as a CSR pair (C, C^T); the A / A^T arrays above are then unused
     bool blocks;
+    bool q_clean;          // q and the p.q slots were zeroed by the last cg_step_kernel
     int64_t n_data, n_con, ell_pad;
     int ell_k;
     int32_t *ell_col;
@@ -382,13 +428,16 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
                                 s->w + s->n_data, s->c_nnz, &s->plan_c, stop, st, &s->launches));
             LSS_TRY(spmv_launch(s->n_cols, s->ct_indptr, s->ct_indices, s->ct_data, s->u + s->n_data, s->buf, LSS_SPMV_PLAIN, nullptr,
                                 s->c_nnz, &s->plan_ct, stop, st, &s->launches));
-        } else {
-            LSS_CUDA(cudaMemsetAsync(s->buf, 0, sizeof(double) * s->n_cols, st));
+            LSS_CUDA(cudaMemsetAsync(s->buf + s->n_cols, 0, sizeof(double) * PQ_SLOTS, st));
+        } else if (!s->q_clean) {
+            LSS_CUDA(cudaMemsetAsync(s->buf, 0, sizeof(double) * (s->n_cols + PQ_SLOTS), st));
         }
         if (timed) LSS_CUDA(cudaEventRecord(e1, st));
-        // ... data rows: q += G^T (w .* (G v)), one fused pass over the ELL copy of G
-        LSS_TRY(ell_normal_launch(0, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, v, s->w, nullptr, s->buf, stop, st));
+        // ... data rows: q += G^T (w .* (G v)) and the p.q partials, one fused pass over the ELL copy of G
+        LSS_TRY(ell_normal_launch(0, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, v, s->w, nullptr, s->buf,
+                                  s->buf + s->n_cols, stop, st));
         if (s->n_data > 0) s->launches += 1;
+        s->q_clean = false;
     } else {
         LSS_TRY(spmv_launch(s->n_rows, s->indptr, s->indices, s->data, v, s->u, LSS_SPMV_SCALE, s->w, s->nnz, &s->plan_a, stop, st, &s->launches));
         if (timed) LSS_CUDA(cudaEventRecord(e1, st));
@@ -396,7 +445,9 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     }
     if (timed) LSS_CUDA(cudaEventRecord(e2, st));
     int64_t n_red = s->n_cols;
-    if (with_dot) {
+    if (s->blocks) {
+        n_red += PQ_SLOTS;              // the fused kernel already left the p.q partials behind q
+    } else if (with_dot) {
         dot_partials_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(s->n_cols, v, s->buf, s->buf + s->n_cols, stop);
         LSS_LAUNCH_CHECK();
         s->launches += 1;
@@ -427,8 +478,8 @@ extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
             LSS_CUDA(cudaMemsetAsync(s->g, 0, sizeof(double) * s->n_cols, st));
             LSS_CUDA(cudaMemsetAsync(s->diag, 0, sizeof(double) * s->n_cols, st));
         }
-        LSS_TRY(ell_normal_launch(1, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, s->rhs, s->g, nullptr, st));
-        LSS_TRY(ell_normal_launch(2, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, nullptr, s->diag, nullptr, st));
+        LSS_TRY(ell_normal_launch(1, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, s->rhs, s->g, nullptr, nullptr, st));
+        LSS_TRY(ell_normal_launch(2, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, nullptr, s->diag, nullptr, nullptr, st));
     } else {
         LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->g, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, nullptr, st, nullptr));
         diag_kernel<<<stride_grid(s->n_cols * 32, 256, 16), 256, 0, st>>>(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->w, s->diag);
@@ -454,6 +505,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     s->ms_a = s->ms_at = 0.0;
     s->n_prof = 0;
     LSS_CUDA(cudaEventRecord(s->ev0, st));
+    s->q_clean = false;
     // r = g - N x0
     zero_fixed_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->fixed, x);
     LSS_LAUNCH_CHECK();
@@ -487,11 +539,23 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
         const int todo = (max_iter - issued) < batch ? (max_iter - issued) : batch;
         for (int k = 0; k < todo; ++k) {
             LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity, slot * kBatch + k));
-            cg_update_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->buf, s->buf + n, VEC_GRID, s->minv, s->p, x, s->r, s->part2, s->scal, parity);
-            LSS_LAUNCH_CHECK();
-            cg_direction_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->r, s->minv, s->p, s->part2, VEC_GRID, s->scal, parity);
-            LSS_LAUNCH_CHECK();
-            s->launches += 2;
+            if (s->blocks && s->n_con == 0) {
+                double *qv = s->buf, *slots = s->buf + n, *minv = s->minv, *pv = s->p, *rv = s->r, *part = s->part2, *scal = s->scal;
+                int64_t nn = n;
+                int par = parity;
+                void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &rv, &part, &scal, &par};
+                LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_kernel, dim3(VEC_GRID), dim3(VEC_BLOCK), args, 0, st));
+                ++lss::g_launches;
+                s->launches += 1;
+                s->q_clean = true;
+            } else {
+                cg_update_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->buf, s->buf + n, s->blocks ? PQ_SLOTS : VEC_GRID, s->minv, s->p, x,
+                                                                 s->r, s->part2, s->scal, parity);
+                LSS_LAUNCH_CHECK();
+                cg_direction_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->r, s->minv, s->p, s->part2, VEC_GRID, s->scal, parity);
+                LSS_LAUNCH_CHECK();
+                s->launches += 2;
+            }
             parity ^= 1;
         }
         base_it[slot] = issued;

@@ -391,7 +391,7 @@ template <int K, int MODE>
 __global__ void __launch_bounds__(256)
 ell_normal_kernel(int64_t n_rows, int64_t n_pad, const int *__restrict__ ell_col, const double *__restrict__ ell_val,
                   const double *__restrict__ x, const double *__restrict__ w, const double *__restrict__ b,
-                  double *__restrict__ q, const double *__restrict__ stop) {
+                  double *__restrict__ q, double *__restrict__ pq_slots, const double *__restrict__ stop) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = r < n_rows;
     const int64_t rr = active ? r : n_rows - 1;
@@ -410,6 +410,19 @@ ell_normal_kernel(int64_t n_rows, int64_t n_pad, const int *__restrict__ ell_col
 #pragma unroll
         for (int k = 0; k < K; ++k) t += v[k] * __ldg(x + c[k]);
         u *= t;
+        if (pq_slots) {
+            // x . (A^T W A x) = sum_r w_r t_r^2 comes for free here: block sum, one RED per CTA spread over 64 slots
+            __shared__ double red[8];
+            const double part = warp_sum(u * t);
+            if (lane_id() == 0) red[threadIdx.x >> 5] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tot += red[i];
+                if (tot != 0.0) atomicAdd(pq_slots + (blockIdx.x & 63), tot);
+            }
+        }
     } else if (MODE == 1) {
         u *= b[rr];
     }
@@ -461,14 +474,14 @@ int ell_spmv_launch(int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col
 }
 
 int ell_normal_launch(int mode, int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val, const double *x,
-                      const double *w, const double *b, double *q, const double *stop, cudaStream_t stream) {
+                      const double *w, const double *b, double *q, double *pq_slots, const double *stop, cudaStream_t stream) {
     if (n_rows <= 0) return LSS_OK;
     const int grid = ceil_div(n_rows, 256);
 #define LSS_ELLN_CASE(KK)                                                                                                         \
     case KK:                                                                                                                      \
-        if (mode == 0) ell_normal_kernel<KK, 0><<<grid, 256, 0, stream>>>(n_rows, n_pad, ell_col, ell_val, x, w, b, q, stop);      \
-        else if (mode == 1) ell_normal_kernel<KK, 1><<<grid, 256, 0, stream>>>(n_rows, n_pad, ell_col, ell_val, x, w, b, q, stop); \
-        else ell_normal_kernel<KK, 2><<<grid, 256, 0, stream>>>(n_rows, n_pad, ell_col, ell_val, x, w, b, q, stop);                \
+        if (mode == 0) ell_normal_kernel<KK, 0><<<grid, 256, 0, stream>>>(n_rows, n_pad, ell_col, ell_val, x, w, b, q, pq_slots, stop); \
+        else if (mode == 1) ell_normal_kernel<KK, 1><<<grid, 256, 0, stream>>>(n_rows, n_pad, ell_col, ell_val, x, w, b, q, pq_slots, stop); \
+        else ell_normal_kernel<KK, 2><<<grid, 256, 0, stream>>>(n_rows, n_pad, ell_col, ell_val, x, w, b, q, pq_slots, stop); \
         break;
     switch (K) {
         LSS_ELLN_CASE(1) LSS_ELLN_CASE(2) LSS_ELLN_CASE(3) LSS_ELLN_CASE(4) LSS_ELLN_CASE(5) LSS_ELLN_CASE(6) LSS_ELLN_CASE(7) LSS_ELLN_CASE(8)

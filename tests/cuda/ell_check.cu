@@ -10,7 +10,7 @@ namespace lss {
 int ell_build(int64_t n_rows, int K, const int32_t *indptr, const int32_t *indices, const double *data, int32_t *ell_col,
               double *ell_val, int64_t n_pad, cudaStream_t stream);
 int ell_normal_launch(int mode, int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val, const double *x,
-                      const double *w, const double *b, double *q, const double *stop, cudaStream_t stream);
+                      const double *w, const double *b, double *q, double *pq_slots, const double *stop, cudaStream_t stream);
 }
 extern "C" const char *lss_last_error(void);
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
@@ -40,10 +40,11 @@ int main(int argc, char **argv) {
     CK(cudaMemcpy(d_w, w.data(), 8 * n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_b, b.data(), 8 * n, cudaMemcpyHostToDevice));
     if (lss::ell_build(n, K, d_ip, d_ix, d_v, d_ec, d_ev, n_pad, 0)) { printf("build: %s\n", lss_last_error()); return 1; }
     CK(cudaDeviceSynchronize());
+    double *d_pq; CK(cudaMalloc(&d_pq, 8 * 64)); CK(cudaMemset(d_pq, 0, 8 * 64));
     int bad = 0;
     for (int mode = 0; mode < 3; ++mode) {
         CK(cudaMemset(d_q, 0, 8 * ncols));
-        if (lss::ell_normal_launch(mode, n, n_pad, K, d_ec, d_ev, d_x, d_w, d_b, d_q, nullptr, 0)) { printf("launch: %s\n", lss_last_error()); return 1; }
+        if (lss::ell_normal_launch(mode, n, n_pad, K, d_ec, d_ev, d_x, d_w, d_b, d_q, mode == 0 ? d_pq : nullptr, nullptr, 0)) { printf("launch: %s\n", lss_last_error()); return 1; }
         CK(cudaDeviceSynchronize());
         std::vector<double> q(ncols), ref(ncols, 0.0);
         CK(cudaMemcpy(q.data(), d_q, 8 * ncols, cudaMemcpyDeviceToHost));
@@ -56,6 +57,14 @@ int main(int argc, char **argv) {
         double err = 0, mx = 0;
         for (int j = 0; j < ncols; ++j) { err = fmax(err, fabs(q[j] - ref[j])); mx = fmax(mx, fabs(ref[j])); }
         printf("mode %d: max |q - ref| = %.3e (max |ref| %.3e)\n", mode, err, mx);
+        if (mode == 0) {          // x . q must equal the sum of the 64 p.q slots
+            double slots[64], pq = 0, want = 0;
+            CK(cudaMemcpy(slots, d_pq, sizeof(slots), cudaMemcpyDeviceToHost));
+            for (double v : slots) pq += v;
+            for (int j = 0; j < ncols; ++j) want += x[j] * ref[j];
+            printf("        x.q from slots %.12e, from q %.12e\n", pq, want);
+            if (!(fabs(pq - want) <= 1e-11 * fabs(want))) bad = 1;
+        }
         if (!(err <= 1e-11 * mx)) bad = 1;
     }
     printf(bad ? "FAIL\n" : "PASS\n");
