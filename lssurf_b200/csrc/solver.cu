@@ -24,7 +24,7 @@
 namespace lss {
 
 namespace cgx = cooperative_groups;
-constexpr int PQ_SLOTS = 64;   // p.q partial sums written by the fused operator kernel
+constexpr int PQ_SLOTS = 256;   // p.q partial sums written by the fused operator kernel
 
 constexpr int VEC_BLOCK = 256;
 constexpr int VEC_GRID = 2 * kSMs;  // fixed: the per-block partial sums have a fixed length
@@ -198,7 +198,7 @@ cg_step_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots,
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK)
         p[i] = minv[i] * r[i] + beta * p[i];
     if (blockIdx.x == 0) {
-        if (threadIdx.x < PQ_SLOTS) pq_slots[threadIdx.x] = 0.0;     // every block read them before the barrier
+        for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;     // every block read them before the barrier
         if (threadIdx.x == 0) {
             scal[S_RZ0 + (parity ^ 1)] = rz_new;
             scal[S_RZ_LAST] = rz_new;

@@ -411,17 +411,11 @@ ell_normal_kernel(int64_t n_rows, int64_t n_pad, const int *__restrict__ ell_col
         for (int k = 0; k < K; ++k) t += v[k] * __ldg(x + c[k]);
         u *= t;
         if (pq_slots) {
-            // x . (A^T W A x) = sum_r w_r t_r^2 comes for free here: block sum, one RED per CTA spread over 64 slots
-            __shared__ double red[8];
+            // x . (A^T W A x) = sum_r w_r t_r^2 comes for free here: warp sum, one RED per warp spread over 256 slots
+            // (no block barrier: warps must not wait for each other's gathers)
             const double part = warp_sum(u * t);
-            if (lane_id() == 0) red[threadIdx.x >> 5] = part;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double tot = 0.0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) tot += red[i];
-                if (tot != 0.0) atomicAdd(pq_slots + (blockIdx.x & 63), tot);
-            }
+            if (lane_id() == 0 && part != 0.0)
+                atomicAdd(pq_slots + (((unsigned)blockIdx.x * 8u + (threadIdx.x >> 5)) & 255u), part);
         }
     } else if (MODE == 1) {
         u *= b[rr];

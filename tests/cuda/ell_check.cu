@@ -40,7 +40,7 @@ int main(int argc, char **argv) {
     CK(cudaMemcpy(d_w, w.data(), 8 * n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_b, b.data(), 8 * n, cudaMemcpyHostToDevice));
     if (lss::ell_build(n, K, d_ip, d_ix, d_v, d_ec, d_ev, n_pad, 0)) { printf("build: %s\n", lss_last_error()); return 1; }
     CK(cudaDeviceSynchronize());
-    double *d_pq; CK(cudaMalloc(&d_pq, 8 * 64)); CK(cudaMemset(d_pq, 0, 8 * 64));
+    double *d_pq; CK(cudaMalloc(&d_pq, 8 * 256)); CK(cudaMemset(d_pq, 0, 8 * 256));
     int bad = 0;
     for (int mode = 0; mode < 3; ++mode) {
         CK(cudaMemset(d_q, 0, 8 * ncols));
@@ -58,7 +58,7 @@ int main(int argc, char **argv) {
         for (int j = 0; j < ncols; ++j) { err = fmax(err, fabs(q[j] - ref[j])); mx = fmax(mx, fabs(ref[j])); }
         printf("mode %d: max |q - ref| = %.3e (max |ref| %.3e)\n", mode, err, mx);
         if (mode == 0) {          // x . q must equal the sum of the 64 p.q slots
-            double slots[64], pq = 0, want = 0;
+            double slots[256], pq = 0, want = 0;
             CK(cudaMemcpy(slots, d_pq, sizeof(slots), cudaMemcpyDeviceToHost));
             for (double v : slots) pq += v;
             for (int j = 0; j < ncols; ++j) want += x[j] * ref[j];
