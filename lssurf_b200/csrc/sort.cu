@@ -354,7 +354,8 @@ f64_keys_kernel(const double *__restrict__ x, int64_t n, double nan_value, uint6
         double v = x[i];
         if (v != v) v = nan_value;
         if (v == 0.0) v = 0.0;               // -0.0 and +0.0 compare equal in NumPy
-        keys[i] = f64_sort_key(v);
+        // a NaN that is still a NaN sorts last whatever its sign bit (NumPy's order); its payload is not kept
+        keys[i] = (v != v) ? 0xfff8000000000000ull : f64_sort_key(v);
     }
 }
 

@@ -27,6 +27,13 @@ _DEV_DTYPE = {'r': torch.int32, 'c': torch.int32, 'v': torch.float64}
 _HOST_DTYPE = {'r': np.int64, 'c': np.int64, 'v': np.float64}
 
 
+def _index_array(rows):
+    """TOC row lists as an int array; ``range`` objects (what diff_op / interp_mtx store) without a Python loop."""
+    if isinstance(rows, range):
+        return np.arange(rows.start, rows.stop, rows.step, dtype='int')
+    return np.array(rows, dtype='int')
+
+
 def _union_of_columns(arrays):
     """np.unique(np.concatenate(arrays)); column lists are almost always contiguous ranges, whose union is merged
     as intervals instead of sorting millions of integers."""
@@ -420,7 +427,7 @@ class lin_op(object):
             label = candidate
             shifted = []
             for key, rows in op.TOC['rows'].items():
-                these = np.array(rows, dtype='int') + next_row
+                these = _index_array(rows) + next_row
                 self.TOC['rows'][key] = these
                 shifted.append(these.ravel())
             if label not in self.TOC['rows']:

@@ -140,6 +140,65 @@ def test_argsort(L):
     assert np.array_equal(order, np.argsort(keys, kind='stable'))
 
 
+def test_dense_rank_group_median_and_bias_ids(L):
+    """Device bias bookkeeping (lss_dense_rank_f64 / lss_group_median) vs np.unique / np.nanmedian and vs the host
+    assign_bias_ID mirror of bias_functions.py:25-82."""
+    rng = np.random.default_rng(21)
+    n = 200_003
+    x = rng.integers(-5, 40, n).astype(float)
+    x[rng.random(n) < 0.01] = np.nan
+    x[:3] = [0.0, -0.0, 1e-300]
+    _c = L._cabi
+    rank, uniq = _c.dense_rank(_c.to_dev(x), nan_value=-9999.0)
+    u, inv = np.unique(np.nan_to_num(x, nan=-9999.0), return_inverse=True)
+    assert np.array_equal(uniq, u) and np.array_equal(rank.cpu().numpy(), inv)
+    ids = rng.integers(0, 37, n).astype(np.int32)
+    vals = rng.normal(size=n)
+    vals[rng.random(n) < 0.02] = np.nan
+    ids[ids == 5] = 6                                            # an empty group
+    med = _c.group_median(_c.to_dev(ids), _c.to_dev(vals), 37).cpu().numpy()
+    with np.errstate(all='ignore'):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            want = np.array([np.nanmedian(vals[ids == g]) if np.any(ids == g) else np.nan for g in range(37)])
+    assert np.array_equal(np.isnan(med), np.isnan(want)) and np.array_equal(med[~np.isnan(med)], want[~np.isnan(want)])
+    # the device bias model equals the host mirror of the reference routine
+    from lssurf_b200.smooth_fit import _assign_bias_ID_device
+    from lssurf_b200.bias_functions import assign_bias_ID
+    m = 50_000
+    rgt = rng.integers(0, 12, m).astype(float); cyc = rng.integers(1, 9, m).astype(float); cyc[rng.random(m) < 0.01] = np.nan
+    sc = rng.uniform(0.01, 0.1, m)
+    D = L.point_data.data().from_dict({'rgt': rgt, 'cycle': cyc, 'sigma_corr': sc, 'z': np.zeros(m)})
+    D, bm = assign_bias_ID(D, ['rgt', 'cycle'])
+    ids_d, bm_d = _assign_bias_ID_device({'rgt': _c.to_dev(rgt), 'cycle': _c.to_dev(cyc)}, ['rgt', 'cycle'], _c.to_dev(sc))
+    assert np.array_equal(ids_d.cpu().numpy(), D.bias_ID.astype(int))
+    assert bm_d['bias_param_dict']['ID'] == bm['bias_param_dict']['ID']
+    assert all(bm_d['E_bias'][k] == bm['E_bias'][k] for k in bm['E_bias'])
+    for k in bm['bias_ID_dict']:
+        a, b = bm['bias_ID_dict'][k], bm_d['bias_ID_dict'][k]
+        assert all((np.isnan(a[f]) and np.isnan(b[f])) or a[f] == b[f] for f in ('rgt', 'cycle'))
+
+
+def test_rmatvec_and_spatial_order(L):
+    rng = np.random.default_rng(22)
+    M = sp.random(20_000, 3000, density=3e-3, random_state=7, format='csr'); M.sort_indices()
+    _c = L._cabi
+    A = L.DeviceCSR(_c.to_dev(M.indptr.astype(np.int32)), _c.to_dev(M.indices.astype(np.int32)), _c.to_dev(M.data), M.shape)
+    u = rng.normal(size=M.shape[0]); u[::7] = 0.
+    got = A.rdot(_c.to_dev(u)).cpu().numpy()
+    want = M.T.dot(u)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.abs(M).T.dot(np.abs(u)).max()
+    fine = L.fd_grid([[0., 100.], [0., 100.]], [1., 1.], name='z0')
+    coarse = L.fd_grid([[0., 100.], [0., 100.], [0., 2.]], [4., 4., 0.5], name='dz')
+    y, x, t = rng.uniform(0, 100, 5000), rng.uniform(0, 100, 5000), rng.uniform(0, 2, 5000)
+    order = _c.spatial_order(fine.as_struct(), coarse.as_struct(), [_c.to_dev(y), _c.to_dev(x), _c.to_dev(t)]).cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(5000))           # a permutation
+    key = ((np.floor(y / 4) * 26 + np.floor(x / 4)) * 101 + np.floor(y)) * 101 + np.floor(x)
+    key = key * 5 + np.floor(t / 0.5)
+    assert np.all(np.diff(key[order]) >= 0)                           # sorted by (coarse cell, fine cell, epoch)
+
+
 # ------------------------------------------------------------------------------------ robust statistics
 def test_rde_and_sigma_extra_known_answers(L):
     fx = np.load(f'{GOLDEN}/lowlevel.npz')
