@@ -63,7 +63,7 @@ def workload_config(a):
     return {'workload': 'cfg4: ICESat-2-shaped tracks, %d points, %.0f x %.0f km, z0 250 m, dz 1 km x 0.25 yr, '
                         "bias_params=['rgt','cycle'], max_iterations=10" % (a.points, a.width / 1e3, a.width / 1e3),
             'points': a.points, 'parallelism': 'row-sharded dp%d' % a.gpus,
-            'l2_policy': 'inputs larger than L2 (A and A^T are ~1.7 GB each per rank at N=1)'}
+            'l2_policy': 'inputs larger than L2 (the normal matrix streamed per CG iteration is ~0.75 GB per rank at N=1, A is 1.7 GB)'}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
@@ -248,9 +248,26 @@ def run_b200(a):
     peak, peak_src = measured_peak()
     traffic = None
     prof = os.path.join(ROOT, 'profiles', 'spmv_traffic.json')
-    if os.path.exists(prof):
-        traffic = json.load(open(prof)).get('dram_bytes_per_launch')
-    if p0.get('fused'):
+    if os.path.exists(prof):       # ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by operator form
+        traffic = json.load(open(prof)).get(p0.get('form', ''), {}).get('dram_bytes_per_launch')
+    if p0.get('form') == 'explicit_normal':
+        # explicit form: q = N p with the tiled CSR kernel over N = A^T W A: 12 B per non-zero of N, row pointers,
+        # q written and p read once (SURVEY 8(d) formula applied to N).  The two-product CSR form of the same
+        # operator (what SURVEY 8(d) budgets per CG iteration) is reported alongside for comparison.
+        nnzN = p0['nnz_N']
+        b_dom = spmv_bytes(n_cols, n_cols, nnzN, False)
+        ms_dom = ms_at / n_apply
+        ach = b_dom / (ms_dom / 1e3) / 1e9
+        b_two = spmv_bytes(p0['rows'], n_cols, nnz, True) + spmv_bytes(n_cols, p0['rows'], nnz, False)
+        roofline = {'bound': 'hbm', 'kernel': 'lss::spmv_persistent_kernel<128,8> on the explicit normal matrix (q = N p, N = A^T W A)',
+                    'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peak_src,
+                    'traffic': traffic, 'bytes_per_launch': {'N': b_dom}, 'launch_ms': {'N': ms_dom},
+                    'nnz_N': nnzN, 'nnz_A': nnz,
+                    'csr_pair_equivalent': {'bytes': b_two, 'gbs': b_two / (ms_dom / 1e3) / 1e9,
+                                            'note': 'bytes the A / A^T two-product form of the same operator would stream, '
+                                                    'divided by the time of the N product (not a bandwidth claim)'},
+                    'frac_of_nominal_8TBs': ach / 8000.0}
+    elif p0.get('fused'):
         # block form: ONE pass over the ELL copy of G does q += G^T (w .* (G p)): 12 B per entry, the row weights,
         # x read once and q read-modify-written once (compulsory); the constraint pair (C, C^T) is the small rest
         if p0.get('all_ell'):      # constraint rows ride in the same ELL block: one kernel per operator application

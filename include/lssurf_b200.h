@@ -140,8 +140,29 @@ int lss_spmv_planned(lss_spmv_plan_t *plan, int64_t n_rows, const int32_t *indpt
                      const double *data, const double *x, double *y, int32_t mode, const double *s, void *stream);
 
 /* Tuning knobs.  "spmv_variant": CTA shape of the CSR product kernel (index into a fixed table of
- * (threads, non-zeros per thread) pairs); affects speed only, never results. */
+ * (threads, non-zeros per thread) pairs); affects speed only, never results.  "explicit_normal" (default 1):
+ * lss_solver_create_blocks forms N = A^T W A explicitly (see lss_normal_create) instead of applying A twice. */
 int lss_set_option(const char *name, int32_t value);
+
+/* ------------------------------------------------------------------ explicit normal matrix */
+
+/* N = A^T diag(w) A for a matrix A whose rows hold at most row_len <= 16 entries (canonical CSR in; the interpolation
+ * rows of lin_op.interp_mtx and the stencil rows of lin_op.diff_op all qualify).  This is the matrix SuiteSparseQR
+ * factorises implicitly in sparseqr.solve (smooth_fit.py:142); the PCG solver multiplies by it instead.
+ * lss_normal_create computes the sparsity pattern (row i of N = union of the column sets of the rows of A holding
+ * column i; rows / columns listed in fixed_cols are left empty) with all values zero; *nnz_h receives nnz(N).
+ * lss_normal_update(w) adds A^T diag(w - w_prev) A, where w_prev is the weight vector of the previous call (zero at
+ * first): only rows whose weight changed are touched.  Values are accumulated with fp64 RED atomics (summation
+ * order, hence the last bits, are run dependent).  lss_normal_export copies canonical CSR arrays (sorted indices)
+ * out: indptr[n_cols + 1], indices[nnz], data[nnz].  lss_normal_apply: y = N x with the tiled CSR kernel. */
+typedef struct lss_normal lss_normal_t;
+int lss_normal_create(lss_normal_t **normal, int64_t n_rows, int64_t n_cols, int32_t row_len, const int32_t *indptr,
+                      const int32_t *indices, const double *data, const int32_t *fixed_cols, int64_t n_fixed,
+                      int64_t *nnz_h, void *stream);
+int lss_normal_update(lss_normal_t *normal, const double *w);
+int lss_normal_export(lss_normal_t *normal, int32_t *indptr, int32_t *indices, double *data);
+int lss_normal_apply(lss_normal_t *normal, const double *x, double *y);
+int lss_normal_destroy(lss_normal_t *normal);
 
 /* ------------------------------------------------------------------ multi-GPU communicator */
 
@@ -183,6 +204,10 @@ int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, int64_t n_co
                              const int32_t *ct_indptr, const int32_t *ct_indices, const double *ct_data,
                              const double *rhs, const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm,
                              void *stream);
+/* Which operator form the solver uses and its size: info_h[0] = 0 generic CSR pair (A, A^T), 1 fused ELL pass,
+ * 2 explicit normal matrix; info_h[1] = nnz of the explicit normal matrix (0 otherwise); info_h[2] = column pairs
+ * sorted by its symbolic phase; info_h[3] = rows of A held in ELL form. */
+int lss_solver_info(lss_solver_t *solver, int64_t *info_h);
 /* Row weights w (length n_rows): 1/sigma^2 for selected data rows, 0 for edited rows, 1/E_c^2 for
  * constraint rows.  Recomputes the right-hand side A^T W b and the Jacobi diagonal. */
 int lss_solver_set_weights(lss_solver_t *solver, const double *w);

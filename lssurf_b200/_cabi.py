@@ -63,6 +63,12 @@ SIGNATURES = {
     'lss_solver_solve': [_vp, _vp, _f64, _i32, _pi32, _pf64],
     'lss_solver_set_profile': [_vp, _i32],
     'lss_solver_stats': [_vp, _pf64],
+    'lss_solver_info': [_vp, _pi64],
+    'lss_normal_create': [C.POINTER(_vp), _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _pi64, _vp],
+    'lss_normal_update': [_vp, _vp],
+    'lss_normal_export': [_vp, _vp, _vp, _vp],
+    'lss_normal_apply': [_vp, _vp, _vp],
+    'lss_normal_destroy': [_vp],
     'lss_rde': [_vp, _vp, _vp, _f64, _i64, _vp, _pf64, _pi64, _vp],
     'lss_sigma_extra': [_vp, _vp, _vp, _i64, _vp, _pf64, _pi32, _vp],
     'lss_edit_mask': [_vp, _vp, _vp, _i64, _f64, _vp, _pf64, _vp, _vp],

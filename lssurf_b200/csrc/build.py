@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ['assembly.cu', 'sort.cu', 'spmv.cu', 'comm.cu', 'solver.cu', 'robust.cu']
+SOURCES = ['assembly.cu', 'sort.cu', 'spmv.cu', 'comm.cu', 'normal.cu', 'solver.cu', 'robust.cu']
 LIB = os.path.join(PKG, 'liblssurf_b200.so')
 NVCC_FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default']

@@ -134,6 +134,28 @@ int ell_spmv_launch(int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col
 int ell_normal_launch(int mode, int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val, const double *x,
                       const double *w, const double *b, double *q, double *pq_slots, const double *stop, cudaStream_t stream);
 
+// Explicit normal matrix N = A^T W A built from the ELL rows of A (normal.cu).  The ELL arrays and the fixed-column
+// flags are borrowed; indptr / indices / data / w_cur are owned.
+struct NormalMatrix {
+    int64_t n_rows, n_pad, n_cols, nnz, n_pairs;
+    int K;
+    const int32_t *ell_col;
+    const double *ell_val;
+    const unsigned char *fixed;
+    int32_t *indptr, *indices;
+    double *data, *w_cur;
+    unsigned long long *missing;
+    SpmvPlan plan;
+    cudaStream_t stream;
+};
+extern int g_opt_explicit_normal;   // -1: unset (environment LSS_NO_EXPLICIT_N decides), 0 / 1: lss_set_option
+int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val,
+                  int64_t n_cols, const unsigned char *fixed, cudaStream_t stream);
+int normal_destroy(NormalMatrix *m);
+int normal_update(NormalMatrix *m, const double *w);                 // N += A^T diag(w - w_cur) A ; w_cur <- w
+int normal_diag(NormalMatrix *m, double *diag);
+int normal_apply(NormalMatrix *m, const double *x, double *y, const double *stop, int64_t *launches);
+
 }  // namespace lss
 
 // NCCL communicator wrapper (comm.cu)

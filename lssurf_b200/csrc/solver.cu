@@ -209,6 +209,49 @@ cg_step_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots,
     }
 }
 
+// Whole vector part of one CG iteration for the explicit-normal-matrix form, where q = N p comes from a gather
+// product (no p.q by-product): p.q, grid barrier, alpha / x / r update and r.M^-1 r, grid barrier, beta / p update.
+// part holds 2 * gridDim.x partial sums.
+__global__ void __launch_bounds__(VEC_BLOCK)
+cg_step_n_kernel(int64_t n, const double *__restrict__ q, const double *__restrict__ minv, double *__restrict__ p,
+                 double *__restrict__ x, double *__restrict__ r, double *__restrict__ part, double *__restrict__ scal, int parity) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    if (scal[S_DONE0 + parity] != 0.0) {          // uniform over the grid: nobody reaches the barriers
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
+        return;
+    }
+    cgx::grid_group grid = cgx::this_grid();
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) v += p[i] * q[i];
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    grid.sync();
+    const double pq = sum_partials(part, (int)gridDim.x, sm);
+    const double rz_old = scal[S_RZ0 + parity];
+    const double alpha = pq > 0.0 ? rz_old / pq : 0.0;
+    v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        v += ri * (minv[i] * ri);
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[gridDim.x + blockIdx.x] = v;
+    grid.sync();
+    const double rz_new = sum_partials(part + gridDim.x, (int)gridDim.x, sm);
+    const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK)
+        p[i] = minv[i] * r[i] + beta * p[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[S_RZ0 + (parity ^ 1)] = rz_new;
+        scal[S_RZ_LAST] = rz_new;
+        const double it = scal[S_ITERS] + 1.0;
+        scal[S_ITERS] = it;
+        scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(VEC_BLOCK)
 mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) out[i] = a[i] * b[i];
@@ -278,6 +321,8 @@ struct lss_solver {
     const int32_t *c_indptr, *c_indices, *ct_indptr, *ct_indices;
     const double *c_data, *ct_data;
     int64_t c_nnz;
+    // explicit form: N = A^T W A (normal.cu), built from the ELL rows; the ELL copy stays for the right-hand side
+    lss::NormalMatrix *nm;
 };
 
 
@@ -299,6 +344,7 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     lss::spmv_plan_destroy(&s->plan_at);
     lss::spmv_plan_destroy(&s->plan_c);
     lss::spmv_plan_destroy(&s->plan_ct);
+    if (s->nm) lss::normal_destroy(s->nm);
     if (s->ell_col) cudaFreeAsync(s->ell_col, s->stream);
     if (s->ell_val) cudaFreeAsync(s->ell_val, s->stream);
     if (s->fixed) cudaFreeAsync(s->fixed, s->stream);
@@ -326,7 +372,7 @@ static int solver_init_common(lss_solver *s, int64_t n_rows, int64_t n_cols, con
     chk(dev_alloc(&s->w, n_rows, s->stream)); chk(dev_alloc(&s->u, n_rows, s->stream));
     chk(dev_alloc(&s->buf, n_cols + VEC_GRID, s->stream)); chk(dev_alloc(&s->r, n_cols, s->stream)); chk(dev_alloc(&s->p, n_cols, s->stream));
     chk(dev_alloc(&s->minv, n_cols, s->stream)); chk(dev_alloc(&s->g, n_cols, s->stream)); chk(dev_alloc(&s->diag, n_cols + VEC_GRID, s->stream));
-    chk(dev_alloc(&s->part2, VEC_GRID, s->stream)); chk(dev_alloc(&s->scal, S_COUNT, s->stream));
+    chk(dev_alloc(&s->part2, 2 * VEC_GRID, s->stream)); chk(dev_alloc(&s->scal, S_COUNT, s->stream));
     if (rc == LSS_OK && cudaMallocAsync((void **)&s->fixed, (size_t)n_cols, s->stream) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMalloc failed");
     if (rc == LSS_OK && cudaMallocHost((void **)&s->host_scal, sizeof(double) * S_COUNT * 2) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMallocHost failed");
     if (rc == LSS_OK) {
@@ -396,6 +442,14 @@ extern "C" int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, i
             rc = fail(LSS_ECUDA, "solver_create_blocks: cudaMallocAsync failed");
         if (rc == LSS_OK) rc = ell_build(n_data, row_len, g_indptr, g_indices, g_data, s->ell_col, s->ell_val, s->ell_pad, st);
     }
+    if (rc == LSS_OK && n_data > 0 && n_con == 0) {
+        int want = lss::g_opt_explicit_normal;
+        if (want < 0) want = getenv("LSS_NO_EXPLICIT_N") ? 0 : 1;
+        if (want) {
+            rc = normal_create(&s->nm, n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, n_cols, s->fixed, st);
+            if (rc == LSS_ERANGE) { s->nm = nullptr; rc = LSS_OK; }   // too many column pairs for the 32-bit sort: fused ELL form
+        }
+    }
     if (rc == LSS_OK && n_con > 0) rc = spmv_plan_create(&s->plan_c, n_con, c_indptr, s->c_nnz, st);
     if (rc == LSS_OK && n_con > 0) rc = spmv_plan_create(&s->plan_ct, n_cols, ct_indptr, s->c_nnz, st);
     if (rc != LSS_OK) { lss_solver_destroy(s); return rc; }
@@ -421,7 +475,10 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
         e2 = (*s->prof_events)[3 * prof_slot + 2];
         LSS_CUDA(cudaEventRecord(e0, st));
     }
-    if (s->blocks) {
+    if (s->nm) {
+        if (timed) LSS_CUDA(cudaEventRecord(e1, st));
+        LSS_TRY(normal_apply(s->nm, v, s->buf, stop, &s->launches));      // q = N v : one gather product
+    } else if (s->blocks) {
         // constraint rows: q = C^T (w_c .* (C v)) with the tiled CSR kernel (writes every entry of q) ...
         if (s->n_con > 0) {
             LSS_TRY(spmv_launch(s->n_con, s->c_indptr, s->c_indices, s->c_data, v, s->u + s->n_data, LSS_SPMV_SCALE,
@@ -445,7 +502,9 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     }
     if (timed) LSS_CUDA(cudaEventRecord(e2, st));
     int64_t n_red = s->n_cols;
-    if (s->blocks) {
+    if (s->nm) {
+        // p.q is formed from the reduced q by cg_step_n_kernel on every rank
+    } else if (s->blocks) {
         n_red += PQ_SLOTS;              // the fused kernel already left the p.q partials behind q
     } else if (with_dot) {
         dot_partials_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(s->n_cols, v, s->buf, s->buf + s->n_cols, stop);
@@ -479,7 +538,12 @@ extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
             LSS_CUDA(cudaMemsetAsync(s->diag, 0, sizeof(double) * s->n_cols, st));
         }
         LSS_TRY(ell_normal_launch(1, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, s->rhs, s->g, nullptr, nullptr, st));
-        LSS_TRY(ell_normal_launch(2, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, nullptr, s->diag, nullptr, nullptr, st));
+        if (s->nm) {
+            LSS_TRY(normal_update(s->nm, s->w));       // N += A^T diag(w - w_prev) A : only rows whose weight changed
+            LSS_TRY(normal_diag(s->nm, s->diag));
+        } else {
+            LSS_TRY(ell_normal_launch(2, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, nullptr, s->diag, nullptr, nullptr, st));
+        }
     } else {
         LSS_TRY(spmv_launch(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->u, s->g, LSS_SPMV_PLAIN, nullptr, s->nnz, &s->plan_at, nullptr, st, nullptr));
         diag_kernel<<<stride_grid(s->n_cols * 32, 256, 16), 256, 0, st>>>(s->n_cols, s->t_indptr, s->t_indices, s->t_data, s->w, s->diag);
@@ -539,7 +603,15 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
         const int todo = (max_iter - issued) < batch ? (max_iter - issued) : batch;
         for (int k = 0; k < todo; ++k) {
             LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity, slot * kBatch + k));
-            if (s->blocks && s->n_con == 0) {
+            if (s->nm) {
+                double *qv = s->buf, *minv = s->minv, *pv = s->p, *rv = s->r, *part = s->part2, *scal = s->scal;
+                int64_t nn = n;
+                int par = parity;
+                void *args[] = {&nn, &qv, &minv, &pv, &x, &rv, &part, &scal, &par};
+                LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_n_kernel, dim3(VEC_GRID), dim3(VEC_BLOCK), args, 0, st));
+                ++lss::g_launches;
+                s->launches += 1;
+            } else if (s->blocks && s->n_con == 0) {
                 double *qv = s->buf, *slots = s->buf + n, *minv = s->minv, *pv = s->p, *rv = s->r, *part = s->part2, *scal = s->scal;
                 int64_t nn = n;
                 int par = parity;
@@ -595,6 +667,15 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
 extern "C" int lss_solver_set_profile(lss_solver_t *s, int32_t on) {
     if (!s) return fail(LSS_EINVAL, "solver_set_profile: null solver");
     s->profile = on != 0;
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_info(lss_solver_t *s, int64_t *info_h) {
+    if (!s || !info_h) return fail(LSS_EINVAL, "solver_info: null argument");
+    info_h[0] = s->nm ? 2 : (s->blocks ? 1 : 0);
+    info_h[1] = s->nm ? s->nm->nnz : 0;
+    info_h[2] = s->nm ? s->nm->n_pairs : 0;
+    info_h[3] = s->blocks ? s->n_data : 0;
     return LSS_OK;
 }
 

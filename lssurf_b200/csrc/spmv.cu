@@ -491,7 +491,13 @@ int ell_normal_launch(int mode, int64_t n_rows, int64_t n_pad, int K, const int3
 
 using namespace lss;
 
+namespace lss { int g_opt_explicit_normal = -1; }
+
 extern "C" int lss_set_option(const char *name, int32_t value) {
+    if (name && strcmp(name, "explicit_normal") == 0) {
+        lss::g_opt_explicit_normal = value != 0;
+        return LSS_OK;
+    }
     if (name && strcmp(name, "spmv_variant") == 0) {
         if (value < 0 || value >= kNumShapes) return fail(LSS_EINVAL, "spmv_variant must be in [0, %d)", kNumShapes);
         g_variant = value;

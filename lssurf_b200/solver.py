@@ -4,7 +4,10 @@ Stands in for the single line ``m0 = Ip_c.dot(sparseqr.solve(Ip_r.dot(TCinv.dot(
 (LSsurf/smooth_fit.py:142).  The operator stays in GPU memory for the whole edit loop; only the row-weight vector
 changes between outer iterations.
 
-Two forms (include/lssurf_b200.h):
+Three forms (include/lssurf_b200.h):
+  * explicit normal matrix (default): N = A^T W A is formed on the device from the ELL rows of A = [G; C] (it has fewer
+    non-zeros than A) and CG multiplies by it with one gather product per iteration; N is updated incrementally when
+    the edit mask changes (``LSS_NO_EXPLICIT_N=1`` or ``lss_set_option('explicit_normal', 0)`` selects the next form);
   * block form (default when every data row holds <= 16 entries, which is always the case for interpolation rows):
     G as an ELL copy applied by the fused ``q += G^T (w .* (G p))`` kernel, the constraint rows as a CSR pair
     (C, C^T) -- one pass over G per CG iteration, no transpose of G;
@@ -19,6 +22,49 @@ import torch
 
 from . import _cabi
 from .lin_op import DeviceCSR
+
+
+class NormalMatrix(object):
+    """N = A^T diag(w) A on the device for a DeviceCSR A with short rows (``lss_normal_*``)."""
+
+    def __init__(self, A, fixed_cols=None):
+        L = _cabi.lib()
+        self.n_cols = A.shape[1]
+        row_len = int((A.indptr[1:] - A.indptr[:-1]).max().item()) if A.shape[0] > 0 else 1
+        fixed = _cabi.to_dev(np.asarray(fixed_cols if fixed_cols is not None else [], dtype=np.int32), torch.int32)
+        self.handle = C.c_void_p(0)
+        nnz = C.c_int64(0)
+        _cabi.check(L.lss_normal_create(C.byref(self.handle), A.shape[0], self.n_cols, max(row_len, 1), _cabi.ptr(A.indptr),
+                                        _cabi.ptr(A.indices), _cabi.ptr(A.data), _cabi.ptr(fixed), int(fixed.numel()),
+                                        C.byref(nnz), _cabi.stream()))
+        self.nnz = int(nnz.value)
+
+    def update(self, w):
+        _cabi.check(_cabi.lib().lss_normal_update(self.handle, _cabi.ptr(w)))
+
+    def export(self):
+        dev = _cabi.device()
+        indptr = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
+        indices = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        data = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=dev)
+        _cabi.check(_cabi.lib().lss_normal_export(self.handle, _cabi.ptr(indptr), _cabi.ptr(indices), _cabi.ptr(data)))
+        return indptr, indices[:self.nnz], data[:self.nnz]
+
+    def dot(self, x):
+        y = torch.empty(self.n_cols, dtype=torch.float64, device=x.device)
+        _cabi.check(_cabi.lib().lss_normal_apply(self.handle, _cabi.ptr(x), _cabi.ptr(y)))
+        return y
+
+    def close(self):
+        if self.handle:
+            _cabi.load().lss_normal_destroy(self.handle)
+            self.handle = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class NormalSolver(object):
@@ -71,6 +117,10 @@ class NormalSolver(object):
                                             _cabi.ptr(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
         self.x = torch.zeros(self.n_cols, dtype=torch.float64, device=z.device)
         self.last = {}
+        info = (C.c_int64 * 4)()
+        _cabi.check(L.lss_solver_info(self.handle, info))
+        self.form = ('csr_pair', 'fused_ell', 'explicit_normal')[int(info[0])]
+        self.nnz_N, self.n_pairs = int(info[1]), int(info[2])
 
     def set_rows(self, in_TSE, sigma_extra=None):
         """Select data rows (uint8 mask) and, on the relaxed last pass, inflate their errors."""
@@ -90,7 +140,8 @@ class NormalSolver(object):
         _cabi.check(_cabi.lib().lss_solver_stats(self.handle, st))
         self.last = dict(iterations=it.value, relres=rel.value, ms=st[0], ms_A=st[1], ms_At=st[2], n_apply=int(st[3]),
                          launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused, all_ell=self.all_ell,
-                         n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz)
+                         n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz,
+                         form=self.form, nnz_N=self.nnz_N, n_cols=self.n_cols)
         return self.x
 
     def residual(self, x, z, out=None):

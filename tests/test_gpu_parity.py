@@ -302,6 +302,78 @@ def test_fused_and_generic_solver_agree(L):
     assert np.allclose(S1['m']['bias']['val'], S2['m']['bias']['val'], rtol=0, atol=1e-9)
 
 
+def test_explicit_normal_matrix_against_scipy(L):
+    """lss_normal_*: pattern and values of N = A^T W A against scipy's (A^T W A) on the oracle's assembly of a small
+    ICESat-2-shaped case ([G; C] rows, reference-epoch columns left out), then an incremental re-weighting."""
+    from lssurf_b200 import synthetic
+    from lssurf_b200.lin_op import DeviceCSR
+    from lssurf_b200.solver import NormalMatrix
+    pts, kw = synthetic.icesat2_tracks(n=40_000, width=1.e4, seed=2)
+    s = O.assemble(pts['x'], pts['y'], pts['time'], pts['z'], pts['sigma'], kw['ctr'], kw['W'], kw['spacing'], kw['E_RMS'],
+                   kw['reference_epoch'], bias_params=[pts['rgt'], pts['cycle']], sigma_corr=pts['sigma_corr'])
+    G = O.csr_matrix(*s['G'][:3], shape=(s['n_data'], s['col_N']))
+    Cm = O.csr_matrix(*s['C'][:3], shape=(s['Ec'].size, s['col_N']))
+    A = sp.vstack([G, Cm]).tocsr()
+    A.sort_indices()
+    fixed = np.setdiff1d(np.arange(s['col_N']), s['keep_cols'])
+    keep = np.zeros(s['col_N']); keep[s['keep_cols']] = 1.0
+    dev = lambda a, dt: L._cabi.to_dev(np.asarray(a), dt)
+    Ad = DeviceCSR(dev(A.indptr, torch.int32), dev(A.indices, torch.int32), dev(A.data, torch.float64), A.shape)
+    Nm = NormalMatrix(Ad, fixed_cols=fixed)
+    rng = np.random.default_rng(0)
+    w = np.r_[1. / s['Ed'] ** 2, 1. / s['Ec'] ** 2]
+    K = sp.diags(keep)
+
+    def check(w):
+        Nm.update(dev(w, torch.float64))
+        ip, ix, dat = [t.cpu().numpy() for t in Nm.export()]
+        got = sp.csr_matrix((dat, ix, ip), shape=(A.shape[1],) * 2)
+        assert got.has_sorted_indices
+        want = (K @ (A.T @ sp.diags(w) @ A) @ K).tocsr()
+        want.eliminate_zeros()
+        # the pattern is weight independent: it must cover the exact product's pattern, values agree to rounding
+        d = (got - want).tocsr()
+        scale = np.abs(want.data).max()
+        assert (np.abs(d.data).max() if d.nnz else 0.0) < 1e-12 * scale
+        P = got.copy(); P.data[:] = 1.0
+        Pw = (K @ (abs(A).T @ abs(A)) @ K).tocsr(); Pw.eliminate_zeros(); Pw.data[:] = 1.0
+        assert (P - Pw).nnz == 0 and got.nnz == Nm.nnz
+        x = rng.normal(size=A.shape[1])
+        y = Nm.dot(dev(x, torch.float64)).cpu().numpy()
+        assert np.allclose(y, want @ x, rtol=0, atol=1e-11 * np.abs(want @ x).max())
+
+    check(w)
+    w2 = w.copy()
+    off = rng.choice(s['n_data'], 900, replace=False)
+    w2[off] = 0.0                                                   # 3-sigma edit switches rows off ...
+    check(w2)
+    w2[off[:300]] = w[off[:300]] * 0.25                             # ... and a relaxed pass re-weights some
+    check(w2)
+    Nm.close()
+
+
+def test_three_operator_forms_agree(L):
+    """Explicit normal matrix (default) vs fused ELL pass vs generic CSR pair: same masks, same solution."""
+    import os
+    from lssurf_b200 import synthetic
+    pts, kw = synthetic.icesat2_tracks(n=150_000, width=2.e4, seed=7)
+    out = {}
+    for name, env in (('explicit_normal', None), ('fused_ell', 'LSS_NO_EXPLICIT_N'), ('csr_pair', 'LSS_NO_FUSED')):
+        if env:
+            os.environ[env] = '1'
+        try:
+            out[name] = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, **kw)
+        finally:
+            if env:
+                del os.environ[env]
+        assert out[name]['timing']['pcg'][0]['form'] == name
+    ref = out['csr_pair']
+    for name in ('explicit_normal', 'fused_ell'):
+        assert rel_l2(out[name]['m']['all'], ref['m']['all']) < 1e-9
+        assert np.array_equal(out[name]['data'].three_sigma_edit, ref['data'].three_sigma_edit)
+    assert out['explicit_normal']['timing']['pcg'][0]['nnz_N'] > 0
+
+
 def test_large_scale_properties(L):
     """Full-size properties (cfg 3 shapes, 1e6 points) that need no oracle: row sums of the interpolation
     matrix are exactly 1 up to rounding, CSR is canonical, G^T products are adjoint, the solve reduces the residual."""
