@@ -206,8 +206,22 @@ int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, int64_t n_co
                              void *stream);
 /* Which operator form the solver uses and its size: info_h[0] = 0 generic CSR pair (A, A^T), 1 fused ELL pass,
  * 2 explicit normal matrix; info_h[1] = nnz of the explicit normal matrix (0 otherwise); info_h[2] = column pairs
- * sorted by its symbolic phase; info_h[3] = rows of A held in ELL form. */
+ * sorted by its symbolic phase; info_h[3] = rows of A held in ELL form; info_h[4] = preconditioner blocks;
+ * info_h[5] = eliminated columns; info_h[6] = blocks that were not positive definite in the last set_weights
+ * (they fall back to their diagonal).  info_h has 8 entries. */
 int lss_solver_info(lss_solver_t *solver, int64_t *info_h);
+/* Optional structure of the unknowns for the explicit-normal form (ignored by the other forms); call once, before
+ * lss_solver_set_weights.
+ *   blocks: n_blocks disjoint groups of at most 64 columns, block b = block_cols[block_ptr[b] .. block_ptr[b+1])
+ *     (device arrays, copied): block-Jacobi preconditioner -- the diagonal blocks of A^T W A are inverted exactly.
+ *     smooth_fit groups every dz node's epochs with the z0 nodes around it (each data point couples z0 to dz(t) at
+ *     one place; scalar Jacobi ignores exactly that).  Columns outside all blocks keep scalar Jacobi.
+ *   [elim_begin, elim_end): a column range whose diagonal block of A^T W A is diagonal (every row of A holds at most
+ *     one of them: the per-(rgt, cycle) bias columns of assign_bias_ID, bias_functions.py:25-82).  They are eliminated
+ *     exactly (CG runs on the Schur complement and back-substitutes); LSS_EINVAL if the block is not diagonal.
+ *     Ignored on more than one rank. */
+int lss_solver_set_structure(lss_solver_t *solver, int32_t n_blocks, const int32_t *block_ptr, const int32_t *block_cols,
+                             int32_t max_block, int64_t elim_begin, int64_t elim_end);
 /* Row weights w (length n_rows): 1/sigma^2 for selected data rows, 0 for edited rows, 1/E_c^2 for
  * constraint rows.  Recomputes the right-hand side A^T W b and the Jacobi diagonal. */
 int lss_solver_set_weights(lss_solver_t *solver, const double *w);

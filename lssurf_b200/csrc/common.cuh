@@ -98,6 +98,34 @@ __device__ __forceinline__ int ldg_stream(const int *p) {
     return v;
 }
 
+// L2 eviction policies: the matrix stream of a product is read once per CG iteration and is larger than L2
+// (evict_first), while the vectors and the preconditioner blocks are re-read every iteration (evict_last).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double ldg_stream(const double *p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ldg_stream(const int *p, uint64_t pol) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ldg_keep(const float *p, uint64_t pol) {
+    float v;
+    asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 // Exclusive prefix sum of uint32 (device, any n).  `total` (device, optional) receives the sum.
 int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total, cudaStream_t stream);
 

@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "precond.cuh"
 
 namespace lss {
 
@@ -252,6 +253,161 @@ cg_step_n_kernel(int64_t n, const double *__restrict__ q, const double *__restri
     }
 }
 
+// ---- structured form of the explicit-normal solver: block-Jacobi preconditioner and / or an exactly eliminated
+// diagonal block E = [e0, e1) (the per-(rgt, cycle) bias columns: every data row holds one of them, so N_EE is
+// diagonal).  CG then runs on the Schur complement in full-length vectors: the E part of every direction is slaved to
+// its grid part, p_E = -N_EE^-1 N_Eg p_g, which makes (N p)_E = 0 and (N p)_g = S p_g.
+
+// Number of entries of rows [e0, e1) of N that sit inside [e0, e1) off the diagonal (must be zero).
+__global__ void __launch_bounds__(256)
+elim_check_kernel(int64_t e0, int64_t e1, const int *__restrict__ indptr, const int *__restrict__ indices, unsigned long long *__restrict__ bad) {
+    const int64_t row = e0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= e1) return;
+    unsigned long long c = 0;
+    for (int k = indptr[row] + (int)lane_id(); k < indptr[row + 1]; k += 32) {
+        const int j = indices[k];
+        if (j >= e0 && j < e1 && j != row) ++c;
+    }
+    if (c) atomicAdd(bad, c);
+}
+
+// einv = 1 / N_ii over E, and no preconditioner action there (z_E = 0)
+__global__ void __launch_bounds__(256)
+elim_setup_kernel(int64_t e0, int64_t e1, const double *__restrict__ diag, double *__restrict__ einv, double *__restrict__ minv) {
+    const int64_t i = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e1) return;
+    const double d = diag[i];
+    einv[i - e0] = d > 0.0 ? 1.0 / d : 0.0;
+    minv[i] = 0.0;
+}
+
+// out_i = einv_i * (c_i - sum_{j not in E} N_ij v_j)  for i in E; one CTA per row (bias rows hold thousands of entries),
+// every thread's loads issued before the first use.  out may alias v (only entries outside E are read).
+constexpr int ELIM_BLOCK = 512, ELIM_IPT = 4;
+__global__ void __launch_bounds__(ELIM_BLOCK)
+elim_solve_kernel(int64_t e0, int64_t e1, const int *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ data,
+                  const double *v, const double *__restrict__ c, const double *__restrict__ einv, double *out,
+                  const double *__restrict__ stop) {
+    __shared__ double sm[ELIM_BLOCK / 32];
+    const double stop_v = stop ? *reinterpret_cast<const volatile double *>(stop) : 0.0;
+    const int64_t row = e0 + blockIdx.x;
+    const int kb = indptr[row], ke = indptr[row + 1];
+    double acc = 0.0;
+    for (int k0 = kb; k0 < ke; k0 += ELIM_BLOCK * ELIM_IPT) {
+        int j[ELIM_IPT];
+        double a[ELIM_IPT];
+#pragma unroll
+        for (int t = 0; t < ELIM_IPT; ++t) {
+            const int k = k0 + t * ELIM_BLOCK + (int)threadIdx.x;
+            j[t] = k < ke ? __ldg(indices + k) : -1;
+            a[t] = k < ke ? __ldg(data + k) : 0.0;
+        }
+        double x[ELIM_IPT];
+#pragma unroll
+        for (int t = 0; t < ELIM_IPT; ++t) x[t] = (j[t] >= 0 && (j[t] < e0 || j[t] >= e1)) ? v[j[t]] : 0.0;
+#pragma unroll
+        for (int t = 0; t < ELIM_IPT; ++t) acc += a[t] * x[t];
+    }
+    if (stop_v != 0.0) return;
+    acc = warp_sum(acc);
+    if (lane_id() == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < ELIM_BLOCK / 32 ? sm[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) out[row] = einv[row - e0] * ((c ? c[row] : 0.0) - t);
+    }
+}
+
+// r = g - q (q may be null), r_E = 0, x = 0 at fixed columns
+__global__ void __launch_bounds__(VEC_BLOCK)
+resid_kernel(int64_t n, const double *__restrict__ g, const double *__restrict__ q, const unsigned char *__restrict__ fixed,
+             int64_t e0, int64_t e1, double *__restrict__ x, double *__restrict__ r) {
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) {
+        r[i] = (i >= e0 && i < e1) ? 0.0 : (q ? g[i] - q[i] : g[i]);
+        if (x && fixed[i]) x[i] = 0.0;
+    }
+}
+
+// p = z and the partial sums of r.z
+__global__ void __launch_bounds__(VEC_BLOCK)
+init_p_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ z, double *__restrict__ p, double *__restrict__ part) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) {
+        if (p) p[i] = z[i];
+        v += r[i] * z[i];
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+// One CG iteration's vector work with the block preconditioner (cooperative launch, as many CTAs as fit):
+// p.q | alpha, x, r, z = M^-1 r (warp per block), r.z | beta, p.
+__global__ void __launch_bounds__(VEC_BLOCK)
+cg_step_p_kernel(int64_t n, const double *__restrict__ q, const double *__restrict__ minv, double *__restrict__ p,
+                 double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *__restrict__ part,
+                 double *__restrict__ scal, int parity, int n_blocks, int bs, const int *__restrict__ bcols,
+                 const int *__restrict__ col_block, const float *__restrict__ binv) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    if (scal[S_DONE0 + parity] != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
+        return;
+    }
+    cgx::grid_group grid = cgx::this_grid();
+    const int64_t tid = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x, nth = (int64_t)gridDim.x * VEC_BLOCK;
+    double v = 0.0;
+    for (int64_t i = tid; i < n; i += nth) v += p[i] * q[i];
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    grid.sync();
+    const double pq = sum_partials(part, (int)gridDim.x, sm);
+    const double rz_old = scal[S_RZ0 + parity];
+    const double alpha = pq > 0.0 ? rz_old / pq : 0.0;
+    v = 0.0;
+    const unsigned lane = lane_id();
+    const uint64_t keep = l2_policy_evict_last();
+    for (int b = (int)(tid >> 5); b < n_blocks; b += (int)(nth >> 5)) {
+        // padded member table: nothing here waits for a block pointer; the first rows of the inverse are requested
+        // before the vector entries they will multiply
+        const int c0 = (int)lane < bs ? __ldg(bcols + (size_t)b * bs + lane) : -1;
+        const int c1 = (int)lane + 32 < bs ? __ldg(bcols + (size_t)b * bs + 32 + lane) : -1;
+        const float *inv = binv + (size_t)b * bs * bs;
+        BlockRows first;
+        block_rows_load(first, inv, bs, 0, keep);
+        double r0 = 0.0, r1 = 0.0;
+        if (c0 >= 0) { x[c0] += alpha * p[c0]; r0 = r[c0] - alpha * q[c0]; r[c0] = r0; }
+        if (c1 >= 0) { x[c1] += alpha * p[c1]; r1 = r[c1] - alpha * q[c1]; r[c1] = r1; }
+        double z0, z1;
+        block_apply_warp(inv, bs, first, r0, r1, z0, z1, keep);
+        if (c0 >= 0) z[c0] = z0;
+        if (c1 >= 0) z[c1] = z1;
+        v += r0 * z0 + r1 * z1;
+    }
+    for (int64_t i = tid; i < n; i += nth) {
+        if (col_block && col_block[i] >= 0) continue;
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        const double zi = minv[i] * ri;
+        z[i] = zi;
+        v += ri * zi;
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[gridDim.x + blockIdx.x] = v;
+    grid.sync();
+    const double rz_new = sum_partials(part + gridDim.x, (int)gridDim.x, sm);
+    const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
+    for (int64_t i = tid; i < n; i += nth) p[i] = z[i] + beta * p[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[S_RZ0 + (parity ^ 1)] = rz_new;
+        scal[S_RZ_LAST] = rz_new;
+        const double it = scal[S_ITERS] + 1.0;
+        scal[S_ITERS] = it;
+        scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(VEC_BLOCK)
 mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) out[i] = a[i] * b[i];
@@ -323,6 +479,11 @@ struct lss_solver {
     int64_t c_nnz;
     // explicit form: N = A^T W A (normal.cu), built from the ELL rows; the ELL copy stays for the right-hand side
     lss::NormalMatrix *nm;
+    // structured form (lss_solver_set_structure): block-Jacobi preconditioner and / or eliminated diagonal block
+    lss::BlockPrecond *bp;
+    int64_t e0, e1;          // eliminated columns [e0, e1); e0 == e1: none
+    double *einv, *z;
+    int step_grid;           // CTAs of the cooperative step kernel
 };
 
 
@@ -344,6 +505,9 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     lss::spmv_plan_destroy(&s->plan_at);
     lss::spmv_plan_destroy(&s->plan_c);
     lss::spmv_plan_destroy(&s->plan_ct);
+    if (s->bp) lss::block_precond_destroy(s->bp);
+    if (s->einv) cudaFreeAsync(s->einv, s->stream);
+    if (s->z) cudaFreeAsync(s->z, s->stream);
     if (s->nm) lss::normal_destroy(s->nm);
     if (s->ell_col) cudaFreeAsync(s->ell_col, s->stream);
     if (s->ell_val) cudaFreeAsync(s->ell_val, s->stream);
@@ -372,7 +536,7 @@ static int solver_init_common(lss_solver *s, int64_t n_rows, int64_t n_cols, con
     chk(dev_alloc(&s->w, n_rows, s->stream)); chk(dev_alloc(&s->u, n_rows, s->stream));
     chk(dev_alloc(&s->buf, n_cols + VEC_GRID, s->stream)); chk(dev_alloc(&s->r, n_cols, s->stream)); chk(dev_alloc(&s->p, n_cols, s->stream));
     chk(dev_alloc(&s->minv, n_cols, s->stream)); chk(dev_alloc(&s->g, n_cols, s->stream)); chk(dev_alloc(&s->diag, n_cols + VEC_GRID, s->stream));
-    chk(dev_alloc(&s->part2, 2 * VEC_GRID, s->stream)); chk(dev_alloc(&s->scal, S_COUNT, s->stream));
+    chk(dev_alloc(&s->part2, 2 * kSMs * 8, s->stream)); chk(dev_alloc(&s->scal, S_COUNT, s->stream));
     if (rc == LSS_OK && cudaMallocAsync((void **)&s->fixed, (size_t)n_cols, s->stream) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMalloc failed");
     if (rc == LSS_OK && cudaMallocHost((void **)&s->host_scal, sizeof(double) * S_COUNT * 2) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create: cudaMallocHost failed");
     if (rc == LSS_OK) {
@@ -457,6 +621,41 @@ extern "C" int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, i
     return LSS_OK;
 }
 
+extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const int32_t *block_ptr, const int32_t *block_cols,
+                                        int32_t max_block, int64_t elim_begin, int64_t elim_end) {
+    if (!s) return fail(LSS_EINVAL, "solver_set_structure: null solver");
+    if (!s->nm) return LSS_OK;          // only the explicit-normal form has the matrix entries these need
+    cudaStream_t st = s->stream;
+    const bool want_elim = elim_end > elim_begin && !(s->comm && s->comm->n_ranks > 1);   // N_Eg rows are rank-local sums
+    if (want_elim) {
+        if (elim_begin < 0 || elim_end > s->n_cols) return fail(LSS_EINVAL, "solver_set_structure: eliminated range outside the columns");
+        Scratch bad;
+        LSS_CUDA(bad.alloc(sizeof(unsigned long long), st));
+        LSS_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(unsigned long long), st));
+        elim_check_kernel<<<ceil_div((elim_end - elim_begin) * 32, 256), 256, 0, st>>>(elim_begin, elim_end, s->nm->indptr, s->nm->indices,
+                                                                                     bad.as<unsigned long long>());
+        LSS_LAUNCH_CHECK();
+        unsigned long long nb = 0;
+        LSS_CUDA(cudaMemcpyAsync(&nb, bad.p, sizeof(nb), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+        if (nb) return fail(LSS_EINVAL, "solver_set_structure: columns [%lld, %lld) are coupled to each other (%llu entries): not a diagonal block",
+                            (long long)elim_begin, (long long)elim_end, nb);
+        s->e0 = elim_begin; s->e1 = elim_end;
+        LSS_TRY(dev_alloc(&s->einv, elim_end - elim_begin, st));
+    }
+    if (n_blocks > 0) LSS_TRY(block_precond_create(&s->bp, s->n_cols, n_blocks, block_ptr, block_cols, max_block, st));
+    if (s->bp || s->e1 > s->e0) {
+        LSS_TRY(dev_alloc(&s->z, s->n_cols, st));
+        int per_sm = 0;
+        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_step_p_kernel, VEC_BLOCK, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        s->step_grid = kSMs * per_sm;
+    }
+    s->have_weights = false;
+    return LSS_OK;
+}
+
 // q(buf[0:n]) = A^T (w .* (A v)), partials of v.q appended at buf[n:], summed over ranks.
 constexpr int kBatch = 16;   // CG iterations enqueued between two looks at the convergence flag
 
@@ -517,6 +716,14 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     return LSS_OK;
 }
 
+// z = M^-1 r for the structured form
+static int apply_precond(lss_solver *s, const double *r, double *z) {
+    if (s->bp) return block_precond_apply(s->bp, s->n_cols, r, s->minv, z, s->stream);
+    mul_kernel<<<VEC_GRID, VEC_BLOCK, 0, s->stream>>>(s->n_cols, s->minv, r, z);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
 extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
     if (!s || !w) return fail(LSS_EINVAL, "solver_set_weights: null argument");
     cudaStream_t st = s->stream;
@@ -553,6 +760,27 @@ extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
     LSS_TRY(comm_allreduce(s->comm, s->diag, s->n_cols, 0, 0, st));
     jacobi_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(s->n_cols, s->diag, s->fixed, s->g, s->minv, s->part2);
     LSS_LAUNCH_CHECK();
+    if (s->z) {
+        // structured form: ||b||^2 = g'^T M^-1 g' with g' the right-hand side of the reduced (Schur) system
+        const int64_t n = s->n_cols;
+        if (s->bp) LSS_TRY(block_precond_factor(s->bp, s->nm, s->comm));
+        const double *gq = nullptr;
+        if (s->e1 > s->e0) {
+            elim_setup_kernel<<<ceil_div(s->e1 - s->e0, 256), 256, 0, st>>>(s->e0, s->e1, s->diag, s->einv, s->minv);
+            LSS_LAUNCH_CHECK();
+            LSS_CUDA(cudaMemsetAsync(s->p, 0, sizeof(double) * n, st));
+            elim_solve_kernel<<<(int)(s->e1 - s->e0), ELIM_BLOCK, 0, st>>>(s->e0, s->e1, s->nm->indptr, s->nm->indices, s->nm->data, s->p, s->g,
+                                                                   s->einv, s->p, nullptr);
+            LSS_LAUNCH_CHECK();
+            LSS_TRY(normal_apply(s->nm, s->p, s->buf, nullptr, nullptr));
+            gq = s->buf;
+        }
+        resid_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->g, gq, s->fixed, s->e0, s->e1, nullptr, s->r);
+        LSS_LAUNCH_CHECK();
+        LSS_TRY(apply_precond(s, s->r, s->z));
+        init_p_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->r, s->z, nullptr, s->part2);
+        LSS_LAUNCH_CHECK();
+    }
     cg_scalar_kernel<<<1, VEC_BLOCK, 0, st>>>(s->part2, VEC_GRID, s->scal, S_BNORM, 0.0, 0);
     LSS_LAUNCH_CHECK();
     s->have_weights = true;
@@ -573,9 +801,29 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     // r = g - N x0
     zero_fixed_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->fixed, x);
     LSS_LAUNCH_CHECK();
-    LSS_TRY(apply_normal(s, x, false, nullptr));
-    cg_init_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->g, s->buf, s->minv, s->fixed, x, s->r, s->p, s->part2);
-    LSS_LAUNCH_CHECK();
+    const bool structured = s->z != nullptr;
+    const bool elim = s->e1 > s->e0;
+    auto slave = [&](double *v, const double *c, const double *stop) -> int {      // v_E = N_EE^-1 (c_E - N_Eg v_g)
+        elim_solve_kernel<<<(int)(s->e1 - s->e0), ELIM_BLOCK, 0, st>>>(s->e0, s->e1, s->nm->indptr, s->nm->indices, s->nm->data, v, c, s->einv, v, stop);
+        LSS_LAUNCH_CHECK();
+        s->launches += 1;
+        return LSS_OK;
+    };
+    if (structured) {
+        if (elim) LSS_TRY(slave(x, s->g, nullptr));
+        LSS_TRY(apply_normal(s, x, false, nullptr));
+        resid_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->g, s->buf, s->fixed, s->e0, s->e1, x, s->r);
+        LSS_LAUNCH_CHECK();
+        LSS_TRY(apply_precond(s, s->r, s->z));
+        init_p_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->r, s->z, s->p, s->part2);
+        LSS_LAUNCH_CHECK();
+        if (elim) LSS_TRY(slave(s->p, nullptr, nullptr));
+        s->launches += 2;
+    } else {
+        LSS_TRY(apply_normal(s, x, false, nullptr));
+        cg_init_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->g, s->buf, s->minv, s->fixed, x, s->r, s->p, s->part2);
+        LSS_LAUNCH_CHECK();
+    }
     cg_scalar_kernel<<<1, VEC_BLOCK, 0, st>>>(s->part2, VEC_GRID, s->scal, S_RZ0, rtol, max_iter);
     LSS_LAUNCH_CHECK();
     s->launches += 3;
@@ -603,7 +851,18 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
         const int todo = (max_iter - issued) < batch ? (max_iter - issued) : batch;
         for (int k = 0; k < todo; ++k) {
             LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity, slot * kBatch + k));
-            if (s->nm) {
+            if (structured) {
+                double *qv = s->buf, *minv = s->minv, *pv = s->p, *rv = s->r, *zv = s->z, *part = s->part2, *scal = s->scal;
+                int64_t nn = n;
+                int par = parity, nb = s->bp ? s->bp->n_blocks : 0, bs = s->bp ? s->bp->bs : 0;
+                const int *bcols = s->bp ? s->bp->cols_pad : nullptr, *cblk = s->bp ? s->bp->col_block : nullptr;
+                const float *binv = s->bp ? s->bp->inv : nullptr;
+                void *args[] = {&nn, &qv, &minv, &pv, &x, &rv, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv};
+                LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_p_kernel, dim3(s->step_grid), dim3(VEC_BLOCK), args, 0, st));
+                ++lss::g_launches;
+                s->launches += 1;
+                if (elim) LSS_TRY(slave(s->p, nullptr, s->scal + S_DONE0 + (parity ^ 1)));
+            } else if (s->nm) {
                 double *qv = s->buf, *minv = s->minv, *pv = s->p, *rv = s->r, *part = s->part2, *scal = s->scal;
                 int64_t nn = n;
                 int par = parity;
@@ -650,6 +909,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
         }
         slot ^= 1;
     }
+    if (structured && elim) LSS_TRY(slave(x, s->g, nullptr));       // back-substitution from the final grid part
     LSS_CUDA(cudaMemcpyAsync(s->host_scal, s->scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
     LSS_CUDA(cudaEventRecord(s->ev1, st));
     LSS_CUDA(cudaStreamSynchronize(st));
@@ -676,6 +936,15 @@ extern "C" int lss_solver_info(lss_solver_t *s, int64_t *info_h) {
     info_h[1] = s->nm ? s->nm->nnz : 0;
     info_h[2] = s->nm ? s->nm->n_pairs : 0;
     info_h[3] = s->blocks ? s->n_data : 0;
+    info_h[4] = s->bp ? s->bp->n_blocks : 0;
+    info_h[5] = s->e1 - s->e0;
+    info_h[6] = 0;
+    if (s->bp) {
+        unsigned int nb = 0;
+        cudaMemcpyAsync(&nb, s->bp->n_bad, sizeof(nb), cudaMemcpyDeviceToHost, s->stream);
+        cudaStreamSynchronize(s->stream);
+        info_h[6] = nb;
+    }
     return LSS_OK;
 }
 

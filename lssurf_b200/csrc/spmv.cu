@@ -171,14 +171,15 @@ spmv_persistent_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__re
     double val[IPT];
     int t = blockIdx.x;
     if (t >= n_tiles) return;
+    const uint64_t once = l2_policy_evict_first();     // the matrix does not fit in L2: leave L2 to x, y and the preconditioner
     auto fetch = [&](int tile) {
         const int64_t k0 = (int64_t)tile * TILE;
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int64_t k = k0 + j * BLOCK + threadIdx.x;
             const bool in = k < nnz;
-            col[j] = in ? ldg_stream(indices + k) : 0;
-            val[j] = in ? ldg_stream(data + k) : 0.0;
+            col[j] = in ? ldg_stream(indices + k, once) : 0;
+            val[j] = in ? ldg_stream(data + k, once) : 0.0;
         }
     };
     fetch(t);

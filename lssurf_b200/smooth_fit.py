@@ -28,7 +28,7 @@ from .constraint_functions import setup_smoothness_constraints, build_reference_
 from .grid_functions import setup_grids, setup_averaging_ops
 from .lin_op import lin_op, DeviceCSR
 from .point_data import data as point_data, grid_data
-from .solver import NormalSolver
+from .solver import NormalSolver, grid_structure
 
 REQUIRED = ('data', 'W', 'ctr', 'spacing', 'E_RMS')
 
@@ -165,7 +165,9 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
     st.mark('it:prep')
     G_csr = G_csr
     st.mark('it:csr')
-    solver = NormalSolver(G_csr, C_loc, z, prior, sigma, Ec, fixed_cols, dist)
+    # structure of the unknowns for the preconditioner: (dz node epochs + nearest z0 nodes) blocks, bias columns eliminated
+    structure = grid_structure(grids, fixed_cols, bias_cols=G_data.TOC['cols'].get('data_bias')) if isinstance(grids, dict) else None
+    solver = NormalSolver(G_csr, C_loc, z, prior, sigma, Ec, fixed_cols, dist, structure=structure)
     solver.set_profile(bool(args.get('profile_spmv')))
     stats = timing.setdefault('pcg', [])
     st.mark('it:solver_setup(vstack+transpose)')

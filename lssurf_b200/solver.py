@@ -67,8 +67,39 @@ class NormalMatrix(object):
             pass
 
 
+def grid_structure(grids, fixed_cols, bias_cols=None, max_block=64):
+    """Column structure handed to ``lss_solver_set_structure``: one preconditioner block per dz node (its free epochs
+    plus the z0 nodes nearest to it), and the bias column range to eliminate.  ``grids``: the dict of fd_grid objects
+    smooth_fit builds (needs 'z0' with 2 and 'dz' with 3 dimensions, same extent); returns None without them."""
+    out = {}
+    z0, dz = grids.get('z0'), grids.get('dz')
+    if z0 is not None and dz is not None and len(z0.shape) == 2 and len(dz.shape) == 3:
+        ny, nx, nt = [int(v) for v in dz.shape]
+        k = np.arange(int(z0.N_nodes))
+        iy, ix = np.divmod(k, int(z0.shape[1]))
+        jy = np.clip(np.floor((z0.ctrs[0][iy] - dz.ctrs[0][0]) / dz.delta[0] + 0.5), 0, ny - 1).astype(np.int64)
+        jx = np.clip(np.floor((z0.ctrs[1][ix] - dz.ctrs[1][0]) / dz.delta[1] + 0.5), 0, nx - 1).astype(np.int64)
+        cols = np.concatenate([z0.col_0 + k, dz.col_0 + np.arange(int(dz.N_nodes))])
+        blk = np.concatenate([jy * nx + jx, np.arange(int(dz.N_nodes)) // nt])
+        free = np.ones(int(cols.max()) + 1, dtype=bool)
+        free[np.asarray(fixed_cols, dtype=np.int64)] = False
+        sel = free[cols]
+        cols, blk = cols[sel], blk[sel]
+        order = np.argsort(blk, kind='stable')
+        counts = np.bincount(blk, minlength=ny * nx)
+        counts = counts[counts > 0]
+        if counts.size and counts.max() <= max_block:
+            out.update(block_ptr=np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), block_cols=cols[order].astype(np.int32),
+                       max_block=int(counts.max()))
+    if bias_cols is not None and len(bias_cols) > 0:
+        b = np.asarray(bias_cols, dtype=np.int64)
+        if b.max() - b.min() + 1 == b.size:
+            out['elim'] = (int(b.min()), int(b.max()) + 1)
+    return out or None
+
+
 class NormalSolver(object):
-    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True):
+    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None):
         """G: DeviceCSR of this rank's data rows; Cn: DeviceCSR of this rank's constraint rows;
         z / sigma: data values and errors (CUDA fp64); prior / Ec: constraint right-hand side and sigma;
         fixed_cols: columns held at zero (reference epoch)."""
@@ -117,10 +148,27 @@ class NormalSolver(object):
                                             _cabi.ptr(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
         self.x = torch.zeros(self.n_cols, dtype=torch.float64, device=z.device)
         self.last = {}
-        info = (C.c_int64 * 4)()
+        info = (C.c_int64 * 8)()
         _cabi.check(L.lss_solver_info(self.handle, info))
         self.form = ('csr_pair', 'fused_ell', 'explicit_normal')[int(info[0])]
         self.nnz_N, self.n_pairs = int(info[1]), int(info[2])
+        self.n_blocks = self.n_elim = 0
+        if structure is not None and self.form == 'explicit_normal' and not os.environ.get('LSS_NO_STRUCTURE'):
+            bp, bc = structure.get('block_ptr'), structure.get('block_cols')
+            e0, e1 = structure.get('elim', (0, 0))
+            if os.environ.get('LSS_NO_ELIM'):
+                e0 = e1 = 0
+            nb = 0 if bp is None or os.environ.get('LSS_NO_BLOCKS') else int(bp.size) - 1
+            self._bp = _cabi.to_dev(np.asarray(bp if nb else [0], dtype=np.int32), torch.int32)
+            self._bc = _cabi.to_dev(np.asarray(bc if nb else [0], dtype=np.int32), torch.int32)
+            rc = L.lss_solver_set_structure(self.handle, nb, _cabi.ptr(self._bp), _cabi.ptr(self._bc),
+                                            int(structure.get('max_block', 1)), int(e0), int(e1))
+            if rc == -1 and e1 > e0:         # LSS_EINVAL: the candidate block is not diagonal -> keep those columns in the solve
+                rc = L.lss_solver_set_structure(self.handle, nb, _cabi.ptr(self._bp), _cabi.ptr(self._bc),
+                                                int(structure.get('max_block', 1)), 0, 0)
+            _cabi.check(rc)
+            _cabi.check(L.lss_solver_info(self.handle, info))
+            self.n_blocks, self.n_elim = int(info[4]), int(info[5])
 
     def set_rows(self, in_TSE, sigma_extra=None):
         """Select data rows (uint8 mask) and, on the relaxed last pass, inflate their errors."""
@@ -141,7 +189,7 @@ class NormalSolver(object):
         self.last = dict(iterations=it.value, relres=rel.value, ms=st[0], ms_A=st[1], ms_At=st[2], n_apply=int(st[3]),
                          launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused, all_ell=self.all_ell,
                          n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz,
-                         form=self.form, nnz_N=self.nnz_N, n_cols=self.n_cols)
+                         form=self.form, nnz_N=self.nnz_N, n_cols=self.n_cols, precond_blocks=self.n_blocks, eliminated=self.n_elim)
         return self.x
 
     def residual(self, x, z, out=None):
