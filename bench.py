@@ -314,7 +314,10 @@ def run_b200(a):
                         'ms_per_step': 1e3 * t_e2e / a.steps},
                 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
                 'solve': {'outer_iterations': outer, 'cg_iterations_per_step': iters, 'pcg_ms_per_step': solve_ms,
-                          'ms_per_cg_iteration': solve_ms / max(iters, 1), 'cg_rtol': kw.get('cg_rtol', 1e-12),
+                          'ms_per_cg_iteration': solve_ms / max(iters, 1),
+                          'ms_product_per_iteration': ms_at / max(n_apply, 1), 'ms_vector_step_per_iteration': sum(p.get('ms_step', 0.) for p in pcg) / max(n_apply, 1),
+                          'preconditioner': {'blocks': p0.get('precond_blocks', 0), 'eliminated_columns': p0.get('eliminated', 0)},
+                          'cg_rtol': kw.get('cg_rtol', 1e-12),
                           'in_TSE': int(np.sum(S['data'].three_sigma_edit)), 'unknowns': n_cols, 'nnz_A_per_rank': nnz,
                           'cg_iterations': [p['iterations'] for p in pcg[:int(outer)]]},
                 'stages_s': stage_times}

@@ -234,7 +234,8 @@ int lss_solver_set_profile(lss_solver_t *solver, int32_t on);
 /* Statistics of the last solve, timed with CUDA events on the solver's stream:
  * stats_h[0] = total ms; [1], [2] = ms in the two halves of the operator (generic form: y = w.*(A p), then A^T u;
  * block form: the constraint products C, C^T, then the fused data-block kernel), 0 unless profiling is on;
- * [3] = number of operator applications behind [1], [2]; [4] = kernels launched; [5] = nnz(A). */
+ * [3] = number of operator applications behind [1], [2]; [4] = kernels launched; [5] = nnz(A); [6] = ms in the vector
+ * step of the iterations (+ collective, + elimination) when profiling; [7] reserved.  stats_h has 8 entries. */
 int lss_solver_stats(lss_solver_t *solver, double *stats_h);
 
 /* ------------------------------------------------------------------ robust statistics / editing */

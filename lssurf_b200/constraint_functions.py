@@ -75,6 +75,8 @@ def build_reference_epoch_matrix(G_data, Gc, grids, reference_epoch, dz_mask=Non
     held at zero inside the PCG (they are recovered here from the matrix' empty rows)."""
     if dz_mask is not None:
         raise NotImplementedError('dz_mask column rejection is outside the hot-path scope')
-    cols = np.arange(G_data.col_N, dtype='int')
-    keep = np.setdiff1d(cols, reference_epoch_columns(grids, reference_epoch))
-    return sp.coo_matrix((np.ones_like(keep), (keep, np.arange(keep.size))), shape=(Gc.col_N, keep.size)).tocsc()
+    is_kept = np.ones(G_data.col_N, dtype=bool)
+    is_kept[reference_epoch_columns(grids, reference_epoch)] = False
+    keep = np.flatnonzero(is_kept)                      # ascending, as setdiff1d returns it
+    # one entry per column: the CSC arrays can be written down directly
+    return sp.csc_matrix((np.ones_like(keep), keep, np.arange(keep.size + 1)), shape=(Gc.col_N, keep.size))

@@ -152,6 +152,10 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
                 const double *x, double *y, int mode, const double *s, int64_t nnz, const SpmvPlan *plan,
                 const double *stop, cudaStream_t stream, int64_t *launches);
 
+int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
+                       int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches,
+                       double *dot_slots = nullptr);   // y pre-zeroed; dot_slots[256] += partial sums of x . (A x)
+
 // Column-major fixed-row-length ("ELL") copy of the leading rows of a CSR matrix and its product (spmv.cu).
 int ell_build(int64_t n_rows, int K, const int32_t *indptr, const int32_t *indices, const double *data, int32_t *ell_col,
               double *ell_val, int64_t n_pad, cudaStream_t stream);
@@ -174,6 +178,8 @@ struct NormalMatrix {
     double *data, *w_cur;
     unsigned long long *missing;
     SpmvPlan plan;
+    SpmvPlan plan_part;        // plan of the leading rows [0, part_rows) (an eliminated trailing block is left out of the product)
+    int64_t part_rows, part_nnz;
     cudaStream_t stream;
 };
 extern int g_opt_explicit_normal;   // -1: unset (environment LSS_NO_EXPLICIT_N decides), 0 / 1: lss_set_option
@@ -183,6 +189,9 @@ int normal_destroy(NormalMatrix *m);
 int normal_update(NormalMatrix *m, const double *w);                 // N += A^T diag(w - w_cur) A ; w_cur <- w
 int normal_diag(NormalMatrix *m, double *diag);
 int normal_apply(NormalMatrix *m, const double *x, double *y, const double *stop, int64_t *launches);
+// same product in one launch (atomic carries) over the leading n_rows rows; y must hold zeros (y_is_zero) or is cleared first
+int normal_apply_fast(NormalMatrix *m, int64_t n_rows, const double *x, double *y, bool y_is_zero, const double *stop, int64_t *launches,
+                      double *dot_slots = nullptr);
 
 }  // namespace lss
 

@@ -187,6 +187,7 @@ int normal_destroy(NormalMatrix *m) {
     if (m->w_cur) cudaFreeAsync(m->w_cur, st);
     if (m->missing) cudaFreeAsync(m->missing, st);
     spmv_plan_destroy(&m->plan);
+    spmv_plan_destroy(&m->plan_part);
     delete m;
     return LSS_OK;
 }
@@ -199,6 +200,7 @@ int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, cons
     memset(m, 0, sizeof(*m));
     m->n_rows = n_rows; m->n_pad = n_pad; m->K = K; m->n_cols = n_cols;
     m->ell_col = ell_col; m->ell_val = ell_val; m->fixed = fixed; m->stream = st;
+    m->part_rows = -1;
     Scratch::configure_pool();
     int rc = LSS_OK;
     auto bail = [&](int code) { normal_destroy(m); return code; };
@@ -295,6 +297,25 @@ int normal_diag(NormalMatrix *m, double *diag) {
 
 int normal_apply(NormalMatrix *m, const double *x, double *y, const double *stop, int64_t *launches) {
     return spmv_launch(m->n_cols, m->indptr, m->indices, m->data, x, y, LSS_SPMV_PLAIN, nullptr, m->nnz, &m->plan, stop, m->stream, launches);
+}
+
+int normal_apply_fast(NormalMatrix *m, int64_t n_rows, const double *x, double *y, bool y_is_zero, const double *stop, int64_t *launches,
+                      double *dot_slots) {
+    if (m->plan.n_tiles > 0 && m->plan.tile != 1024)
+        return fail(LSS_EINVAL, "normal matrix product: the single-launch kernel needs the default spmv_variant (1024-entry tiles)");
+    if (!y_is_zero) LSS_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * m->n_cols, m->stream));
+    if (n_rows >= m->n_cols)
+        return spmv_launch_atomic(m->n_cols, m->indptr, m->indices, m->data, x, y, m->nnz, &m->plan, stop, m->stream, launches, dot_slots);
+    if (m->part_rows != n_rows) {          // first use with this row count: plan of the leading block
+        spmv_plan_destroy(&m->plan_part);
+        int nz = 0;
+        LSS_CUDA(cudaMemcpyAsync(&nz, m->indptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        LSS_CUDA(cudaStreamSynchronize(m->stream));
+        m->part_nnz = nz;
+        LSS_TRY(spmv_plan_create(&m->plan_part, n_rows, m->indptr, nz, m->stream));
+        m->part_rows = n_rows;
+    }
+    return spmv_launch_atomic(n_rows, m->indptr, m->indices, m->data, x, y, m->part_nnz, &m->plan_part, stop, m->stream, launches, dot_slots);
 }
 
 __global__ void __launch_bounds__(256)

@@ -103,9 +103,9 @@ bp_apply_kernel(int n_blocks, int bs, const int *__restrict__ ptr, const int *__
         const int c0 = (int)lane < m ? cols[b0 + lane] : -1, c1 = (int)lane + 32 < m ? cols[b0 + 32 + lane] : -1;
         const double r0 = c0 >= 0 ? r[c0] : 0.0, r1 = c1 >= 0 ? r[c1] : 0.0;
         double z0, z1;
-        BlockRows first;
-        block_rows_load(first, inv + (size_t)b * bs * bs, bs, 0, keep);
-        block_apply_warp(inv + (size_t)b * bs * bs, bs, first, r0, r1, z0, z1, keep);
+        BlockRegs R;
+        block_regs_load(R, inv + (size_t)b * bs * bs, bs, keep);
+        block_apply_warp(inv + (size_t)b * bs * bs, bs, R, r0, r1, z0, z1, keep);
         if (c0 >= 0) z[c0] = z0;
         if (c1 >= 0) z[c1] = z1;
     }

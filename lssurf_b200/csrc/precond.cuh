@@ -31,38 +31,50 @@ int block_precond_factor(BlockPrecond *bp, const NormalMatrix *nm, lss_comm *com
 int block_precond_apply(const BlockPrecond *bp, int64_t n_cols, const double *r, const double *minv, double *z, cudaStream_t stream);
 
 // Warp-cooperative z = Binv r over one block.  Lane l holds members l and l + 32 (r0, r1) and receives z for the same
-// members.  The stored block is bs x bs with zero padding, so the loop bound does not depend on the member count and
-// every load address is known up front: BP_CH rows of the (symmetric) inverse are requested at a time, the first
-// group by the caller before it touches anything else.
-constexpr int BP_CH = 12;
-struct BlockRows { float a0[BP_CH], a1[BP_CH]; };
+// members.  The stored block is bs x bs with zero padding and symmetric, so nothing depends on the member count and
+// every address is known before any vector entry is: the caller requests the block (BlockRegs) first, then gathers
+// the vector entries, then calls block_apply_warp -- one memory round trip per block.
+//   members 0..31 : z_l = sum_j inv[j][l] r_j           lane l keeps column l of rows 0..BP_ROWS-1 in registers
+//   members >= 32 : z_i = <inv[i][:], r>                  a warp reduction per member, BP_TAIL rows in registers
+constexpr int BP_ROWS = 40, BP_TAIL = 4;
+struct BlockRegs { float a[BP_ROWS], t0[BP_TAIL], t1[BP_TAIL]; };
 
-__device__ __forceinline__ void block_rows_load(BlockRows &R, const float *__restrict__ inv, int bs, int j0, uint64_t keep) {
+__device__ __forceinline__ void block_regs_load(BlockRegs &R, const float *__restrict__ inv, int bs, uint64_t keep) {
     const unsigned lane = threadIdx.x & 31u;
     const bool h0 = (int)lane < bs, h1 = (int)lane + 32 < bs;
 #pragma unroll
-    for (int t = 0; t < BP_CH; ++t) {
-        const bool in = j0 + t < bs;
-        R.a0[t] = (in && h0) ? ldg_keep(inv + (j0 + t) * bs + lane, keep) : 0.f;
-        R.a1[t] = (in && h1) ? ldg_keep(inv + (j0 + t) * bs + 32 + lane, keep) : 0.f;
+    for (int t = 0; t < BP_ROWS; ++t) R.a[t] = (t < bs && h0) ? ldg_keep(inv + t * bs + lane, keep) : 0.f;
+#pragma unroll
+    for (int t = 0; t < BP_TAIL; ++t) {
+        R.t0[t] = (32 + t < bs && h0) ? ldg_keep(inv + (32 + t) * bs + lane, keep) : 0.f;
+        R.t1[t] = (32 + t < bs && h1) ? ldg_keep(inv + (32 + t) * bs + 32 + lane, keep) : 0.f;
     }
 }
 
-__device__ __forceinline__ void block_apply_warp(const float *__restrict__ inv, int bs, BlockRows &R, double r0, double r1, double &z0,
-                                                 double &z1, uint64_t keep) {
+__device__ __forceinline__ void block_apply_warp(const float *__restrict__ inv, int bs, const BlockRegs &R, double r0, double r1,
+                                                 double &z0, double &z1, uint64_t keep) {
+    const unsigned lane = threadIdx.x & 31u;
     z0 = 0.0;
     z1 = 0.0;
-    for (int j0 = 0; j0 < bs; j0 += BP_CH) {
-        BlockRows nxt;
-        if (j0 + BP_CH < bs) block_rows_load(nxt, inv, bs, j0 + BP_CH, keep);      // in flight during the sums below
 #pragma unroll
-        for (int t = 0; t < BP_CH; ++t) {
-            const int j = j0 + t;
-            const double rj = __shfl_sync(0xffffffffu, (j < 32) ? r0 : r1, j & 31);
-            z0 += (double)R.a0[t] * rj;
-            z1 += (double)R.a1[t] * rj;
-        }
-        if (j0 + BP_CH < bs) R = nxt;
+    for (int j = 0; j < BP_ROWS; ++j) {
+        const double rj = __shfl_sync(0xffffffffu, (j < 32) ? r0 : r1, j & 31);
+        z0 += (double)R.a[j] * rj;
+    }
+    for (int j = BP_ROWS; j < bs; ++j) {            // blocks beyond BP_ROWS members: remaining rows straight from memory
+        const double rj = __shfl_sync(0xffffffffu, r1, j & 31);
+        z0 += (double)((int)lane < bs ? ldg_keep(inv + j * bs + lane, keep) : 0.f) * rj;
+    }
+#pragma unroll
+    for (int t = 0; t < BP_TAIL; ++t) {
+        const double d = warp_sum((double)R.t0[t] * r0 + (double)R.t1[t] * r1);
+        if ((int)lane == t) z1 = d;
+    }
+    for (int i = 32 + BP_TAIL; i < bs; ++i) {
+        const float b0 = (int)lane < bs ? ldg_keep(inv + i * bs + lane, keep) : 0.f;
+        const float b1 = (int)lane + 32 < bs ? ldg_keep(inv + i * bs + 32 + lane, keep) : 0.f;
+        const double d = warp_sum((double)b0 * r0 + (double)b1 * r1);
+        if ((int)lane == i - 32) z1 = d;
     }
 }
 

@@ -199,7 +199,8 @@ cg_step_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots,
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK)
         p[i] = minv[i] * r[i] + beta * p[i];
     if (blockIdx.x == 0) {
-        for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;     // every block read them before the barrier
+        if (pq_slots)
+            for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;     // every block read them before the barrier
         if (threadIdx.x == 0) {
             scal[S_RZ0 + (parity ^ 1)] = rz_new;
             scal[S_RZ_LAST] = rz_new;
@@ -214,7 +215,7 @@ cg_step_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots,
 // product (no p.q by-product): p.q, grid barrier, alpha / x / r update and r.M^-1 r, grid barrier, beta / p update.
 // part holds 2 * gridDim.x partial sums.
 __global__ void __launch_bounds__(VEC_BLOCK)
-cg_step_n_kernel(int64_t n, const double *__restrict__ q, const double *__restrict__ minv, double *__restrict__ p,
+cg_step_n_kernel(int64_t n, double *__restrict__ q, const double *__restrict__ minv, double *__restrict__ p,
                  double *__restrict__ x, double *__restrict__ r, double *__restrict__ part, double *__restrict__ scal, int parity) {
     __shared__ double sm[VEC_BLOCK / 32];
     if (scal[S_DONE0 + parity] != 0.0) {          // uniform over the grid: nobody reaches the barriers
@@ -235,6 +236,7 @@ cg_step_n_kernel(int64_t n, const double *__restrict__ q, const double *__restri
         x[i] += alpha * p[i];
         const double ri = r[i] - alpha * q[i];
         r[i] = ri;
+        q[i] = 0.0;                       // the next product accumulates its cut rows into a clean q
         v += ri * (minv[i] * ri);
     }
     v = block_sum(v, sm);
@@ -342,10 +344,12 @@ init_p_kernel(int64_t n, const double *__restrict__ r, const double *__restrict_
     if (threadIdx.x == 0) part[blockIdx.x] = v;
 }
 
-// One CG iteration's vector work with the block preconditioner (cooperative launch, as many CTAs as fit):
-// p.q | alpha, x, r, z = M^-1 r (warp per block), r.z | beta, p.
-__global__ void __launch_bounds__(VEC_BLOCK)
-cg_step_p_kernel(int64_t n, const double *__restrict__ q, const double *__restrict__ minv, double *__restrict__ p,
+// One CG iteration's vector work with the block preconditioner (cooperative launch, 3 CTAs per SM):
+// alpha from the p.q slots the product left behind | x, r, z = M^-1 r (warp per block), r.z | grid barrier | beta, p.
+// Clears q and the slots for the next product.
+constexpr int STEP_PER_SM = 3;
+__global__ void __launch_bounds__(VEC_BLOCK, STEP_PER_SM)
+cg_step_p_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots, const double *__restrict__ minv, double *__restrict__ p,
                  double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *__restrict__ part,
                  double *__restrict__ scal, int parity, int n_blocks, int bs, const int *__restrict__ bcols,
                  const int *__restrict__ col_block, const float *__restrict__ binv) {
@@ -354,57 +358,73 @@ cg_step_p_kernel(int64_t n, const double *__restrict__ q, const double *__restri
         if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
         return;
     }
-    cgx::grid_group grid = cgx::this_grid();
     const int64_t tid = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x, nth = (int64_t)gridDim.x * VEC_BLOCK;
-    double v = 0.0;
-    for (int64_t i = tid; i < n; i += nth) v += p[i] * q[i];
-    v = block_sum(v, sm);
-    if (threadIdx.x == 0) part[blockIdx.x] = v;
-    grid.sync();
-    const double pq = sum_partials(part, (int)gridDim.x, sm);
-    const double rz_old = scal[S_RZ0 + parity];
-    const double alpha = pq > 0.0 ? rz_old / pq : 0.0;
-    v = 0.0;
     const unsigned lane = lane_id();
     const uint64_t keep = l2_policy_evict_last();
-    for (int b = (int)(tid >> 5); b < n_blocks; b += (int)(nth >> 5)) {
-        // padded member table: nothing here waits for a block pointer; the first rows of the inverse are requested
-        // before the vector entries they will multiply
-        const int c0 = (int)lane < bs ? __ldg(bcols + (size_t)b * bs + lane) : -1;
-        const int c1 = (int)lane + 32 < bs ? __ldg(bcols + (size_t)b * bs + 32 + lane) : -1;
-        const float *inv = binv + (size_t)b * bs * bs;
-        BlockRows first;
-        block_rows_load(first, inv, bs, 0, keep);
+    // the first block's inverse and members are requested before anything else
+    int b = (int)(tid >> 5);
+    BlockRegs R;
+    int c0 = -1, c1 = -1;
+    if (b < n_blocks) {
+        block_regs_load(R, binv + (size_t)b * bs * bs, bs, keep);
+        c0 = (int)lane < bs ? __ldg(bcols + (size_t)b * bs + lane) : -1;
+        c1 = (int)lane + 32 < bs ? __ldg(bcols + (size_t)b * bs + 32 + lane) : -1;
+    }
+    double pq;
+    if (pq_slots) {
+        pq = sum_partials(pq_slots, PQ_SLOTS, sm);
+    } else {                                   // p.q formed here (one more grid barrier)
+        double d = 0.0;
+        for (int64_t i = tid; i < n; i += nth) d += p[i] * q[i];
+        d = block_sum(d, sm);
+        if (threadIdx.x == 0) part[gridDim.x + blockIdx.x] = d;
+        cgx::this_grid().sync();
+        pq = sum_partials(part + gridDim.x, (int)gridDim.x, sm);
+    }
+    const double rz_old = scal[S_RZ0 + parity];
+    const double alpha = pq > 0.0 ? rz_old / pq : 0.0;
+    double v = 0.0;
+    for (; b < n_blocks; b += (int)(nth >> 5)) {
         double r0 = 0.0, r1 = 0.0;
-        if (c0 >= 0) { x[c0] += alpha * p[c0]; r0 = r[c0] - alpha * q[c0]; r[c0] = r0; }
-        if (c1 >= 0) { x[c1] += alpha * p[c1]; r1 = r[c1] - alpha * q[c1]; r[c1] = r1; }
+        if (c0 >= 0) { x[c0] += alpha * p[c0]; r0 = r[c0] - alpha * q[c0]; r[c0] = r0; q[c0] = 0.0; }
+        if (c1 >= 0) { x[c1] += alpha * p[c1]; r1 = r[c1] - alpha * q[c1]; r[c1] = r1; q[c1] = 0.0; }
         double z0, z1;
-        block_apply_warp(inv, bs, first, r0, r1, z0, z1, keep);
+        block_apply_warp(binv + (size_t)b * bs * bs, bs, R, r0, r1, z0, z1, keep);
         if (c0 >= 0) z[c0] = z0;
         if (c1 >= 0) z[c1] = z1;
         v += r0 * z0 + r1 * z1;
+        const int nb = b + (int)(nth >> 5);
+        if (nb < n_blocks) {
+            block_regs_load(R, binv + (size_t)nb * bs * bs, bs, keep);
+            c0 = (int)lane < bs ? __ldg(bcols + (size_t)nb * bs + lane) : -1;
+            c1 = (int)lane + 32 < bs ? __ldg(bcols + (size_t)nb * bs + 32 + lane) : -1;
+        }
     }
     for (int64_t i = tid; i < n; i += nth) {
         if (col_block && col_block[i] >= 0) continue;
         x[i] += alpha * p[i];
         const double ri = r[i] - alpha * q[i];
         r[i] = ri;
+        q[i] = 0.0;
         const double zi = minv[i] * ri;
         z[i] = zi;
         v += ri * zi;
     }
     v = block_sum(v, sm);
-    if (threadIdx.x == 0) part[gridDim.x + blockIdx.x] = v;
-    grid.sync();
-    const double rz_new = sum_partials(part + gridDim.x, (int)gridDim.x, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    cgx::this_grid().sync();
+    const double rz_new = sum_partials(part, (int)gridDim.x, sm);
     const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
     for (int64_t i = tid; i < n; i += nth) p[i] = z[i] + beta * p[i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        scal[S_RZ0 + (parity ^ 1)] = rz_new;
-        scal[S_RZ_LAST] = rz_new;
-        const double it = scal[S_ITERS] + 1.0;
-        scal[S_ITERS] = it;
-        scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;     // every block read them before the barrier
+        if (threadIdx.x == 0) {
+            scal[S_RZ0 + (parity ^ 1)] = rz_new;
+            scal[S_RZ_LAST] = rz_new;
+            const double it = scal[S_ITERS] + 1.0;
+            scal[S_ITERS] = it;
+            scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+        }
     }
 }
 
@@ -460,7 +480,7 @@ struct lss_solver {
     bool have_weights;
     bool profile;
     // stats of the last solve
-    double ms_total, ms_a, ms_at;
+    double ms_total, ms_a, ms_at, ms_step;
     int64_t n_apply;
     int64_t launches;
     std::vector<cudaEvent_t> *prof_events;   // fixed pool: 3 events per operator application, 2 batches deep
@@ -484,6 +504,8 @@ struct lss_solver {
     int64_t e0, e1;          // eliminated columns [e0, e1); e0 == e1: none
     double *einv, *z;
     int step_grid;           // CTAs of the cooperative step kernel
+    bool l2_window;          // an L2 persisting window on the preconditioner blocks is installed on the stream
+    bool pq_in_step;         // the step kernel forms p.q itself instead of taking it from the product kernel
 };
 
 
@@ -505,6 +527,13 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     lss::spmv_plan_destroy(&s->plan_at);
     lss::spmv_plan_destroy(&s->plan_c);
     lss::spmv_plan_destroy(&s->plan_ct);
+    if (s->l2_window) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr);     // num_bytes = 0: no window
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
     if (s->bp) lss::block_precond_destroy(s->bp);
     if (s->einv) cudaFreeAsync(s->einv, s->stream);
     if (s->z) cudaFreeAsync(s->z, s->stream);
@@ -644,14 +673,38 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
         LSS_TRY(dev_alloc(&s->einv, elim_end - elim_begin, st));
     }
     if (n_blocks > 0) LSS_TRY(block_precond_create(&s->bp, s->n_cols, n_blocks, block_ptr, block_cols, max_block, st));
+    if (s->bp && !getenv("LSS_NO_L2_WINDOW")) {
+        // keep the block inverses (re-read every CG iteration, ~50 MB at 10^4 blocks) in the persisting part of L2
+        // while the normal matrix streams through the rest
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const size_t bytes = sizeof(float) * (size_t)s->bp->n_blocks * s->bp->bs * s->bp->bs;
+            size_t carve = bytes + (8u << 20);
+            if (carve > (size_t)prop.persistingL2CacheMaxSize) carve = prop.persistingL2CacheMaxSize;
+            size_t win = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                cudaStreamAttrValue attr;
+                memset(&attr, 0, sizeof(attr));
+                attr.accessPolicyWindow.base_ptr = s->bp->inv;
+                attr.accessPolicyWindow.num_bytes = win;
+                attr.accessPolicyWindow.hitRatio = carve >= win ? 1.0f : (float)((double)carve / (double)win);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) s->l2_window = true;
+            }
+            cudaGetLastError();     // the window is an optimisation: never fail the solve over it
+        }
+    }
     if (s->bp || s->e1 > s->e0) {
         LSS_TRY(dev_alloc(&s->z, s->n_cols, st));
         int per_sm = 0;
         LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_step_p_kernel, VEC_BLOCK, 0));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 8) per_sm = 8;
+        if (per_sm > STEP_PER_SM) per_sm = STEP_PER_SM;
         s->step_grid = kSMs * per_sm;
     }
+    s->pq_in_step = getenv("LSS_PQ_IN_STEP") != nullptr;
     s->have_weights = false;
     return LSS_OK;
 }
@@ -664,19 +717,24 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     const bool timed = s->profile && prof_slot >= 0;
     if (timed) {
-        while ((int)s->prof_events->size() < 3 * 2 * kBatch) {   // created once, reused for every batch
+        while ((int)s->prof_events->size() < 4 * 2 * kBatch) {   // created once, reused for every batch
             cudaEvent_t e;
             LSS_CUDA(cudaEventCreate(&e));
             s->prof_events->push_back(e);
         }
-        e0 = (*s->prof_events)[3 * prof_slot];
-        e1 = (*s->prof_events)[3 * prof_slot + 1];
-        e2 = (*s->prof_events)[3 * prof_slot + 2];
+        e0 = (*s->prof_events)[4 * prof_slot];
+        e1 = (*s->prof_events)[4 * prof_slot + 1];
+        e2 = (*s->prof_events)[4 * prof_slot + 2];
         LSS_CUDA(cudaEventRecord(e0, st));
     }
     if (s->nm) {
         if (timed) LSS_CUDA(cudaEventRecord(e1, st));
-        LSS_TRY(normal_apply(s->nm, v, s->buf, stop, &s->launches));      // q = N v : one gather product
+        // q = N v : one gather product, one launch (rows of an eliminated trailing block are left out: (N p)_E = 0)
+        const int64_t rows = (s->e1 > s->e0 && s->e1 == s->n_cols) ? s->e0 : s->n_cols;
+        double *slots = (s->z && with_dot && !s->pq_in_step) ? s->buf + s->n_cols : nullptr;      // p.q by-product for the structured step kernel
+        if (slots && !s->q_clean) LSS_CUDA(cudaMemsetAsync(slots, 0, sizeof(double) * PQ_SLOTS, st));
+        LSS_TRY(normal_apply_fast(s->nm, rows, v, s->buf, s->q_clean, stop, &s->launches, slots));
+        s->q_clean = false;
     } else if (s->blocks) {
         // constraint rows: q = C^T (w_c .* (C v)) with the tiled CSR kernel (writes every entry of q) ...
         if (s->n_con > 0) {
@@ -702,7 +760,8 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     if (timed) LSS_CUDA(cudaEventRecord(e2, st));
     int64_t n_red = s->n_cols;
     if (s->nm) {
-        // p.q is formed from the reduced q by cg_step_n_kernel on every rank
+        if (s->z && with_dot && !s->pq_in_step) n_red += PQ_SLOTS;   // structured form: the product left its p.q partials behind q
+        // plain form: p.q is formed from the reduced q by cg_step_n_kernel on every rank
     } else if (s->blocks) {
         n_red += PQ_SLOTS;              // the fused kernel already left the p.q partials behind q
     } else if (with_dot) {
@@ -794,7 +853,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     const int64_t n = s->n_cols;
     s->launches = 0;
     s->n_apply = 0;
-    s->ms_a = s->ms_at = 0.0;
+    s->ms_a = s->ms_at = s->ms_step = 0.0;
     s->n_prof = 0;
     LSS_CUDA(cudaEventRecord(s->ev0, st));
     s->q_clean = false;
@@ -837,11 +896,14 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
         const int real = (int)s->host_scal[sl * S_COUNT + S_ITERS] - base_it[sl];
         for (int k = 0; k < in_slot[sl] && k < real && s->profile; ++k) {
             float a = 0.f, b = 0.f;
-            const int e = 3 * (sl * kBatch + k);
+            const int e = 4 * (sl * kBatch + k);
+            float c = 0.f;
             cudaEventElapsedTime(&a, (*s->prof_events)[e], (*s->prof_events)[e + 1]);
             cudaEventElapsedTime(&b, (*s->prof_events)[e + 1], (*s->prof_events)[e + 2]);
+            cudaEventElapsedTime(&c, (*s->prof_events)[e + 2], (*s->prof_events)[e + 3]);
             s->ms_a += a;
             s->ms_at += b;
+            s->ms_step += c;
             s->n_prof += 1;
         }
         in_slot[sl] = 0;
@@ -857,10 +919,12 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
                 int par = parity, nb = s->bp ? s->bp->n_blocks : 0, bs = s->bp ? s->bp->bs : 0;
                 const int *bcols = s->bp ? s->bp->cols_pad : nullptr, *cblk = s->bp ? s->bp->col_block : nullptr;
                 const float *binv = s->bp ? s->bp->inv : nullptr;
-                void *args[] = {&nn, &qv, &minv, &pv, &x, &rv, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv};
+                double *slots = s->pq_in_step ? nullptr : s->buf + n;
+                void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &rv, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv};
                 LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_p_kernel, dim3(s->step_grid), dim3(VEC_BLOCK), args, 0, st));
                 ++lss::g_launches;
                 s->launches += 1;
+                s->q_clean = true;
                 if (elim) LSS_TRY(slave(s->p, nullptr, s->scal + S_DONE0 + (parity ^ 1)));
             } else if (s->nm) {
                 double *qv = s->buf, *minv = s->minv, *pv = s->p, *rv = s->r, *part = s->part2, *scal = s->scal;
@@ -870,6 +934,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
                 LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_n_kernel, dim3(VEC_GRID), dim3(VEC_BLOCK), args, 0, st));
                 ++lss::g_launches;
                 s->launches += 1;
+                s->q_clean = true;
             } else if (s->blocks && s->n_con == 0) {
                 double *qv = s->buf, *slots = s->buf + n, *minv = s->minv, *pv = s->p, *rv = s->r, *part = s->part2, *scal = s->scal;
                 int64_t nn = n;
@@ -887,6 +952,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
                 LSS_LAUNCH_CHECK();
                 s->launches += 2;
             }
+            if (s->profile) LSS_CUDA(cudaEventRecord((*s->prof_events)[4 * (slot * kBatch + k) + 3], st));   // after the vector step
             parity ^= 1;
         }
         base_it[slot] = issued;
@@ -956,5 +1022,7 @@ extern "C" int lss_solver_stats(lss_solver_t *s, double *stats_h) {
     stats_h[3] = (double)(s->profile ? s->n_prof : s->n_apply);   // applications behind stats_h[1], [2] when profiling
     stats_h[4] = (double)s->launches;
     stats_h[5] = (double)s->nnz;
+    stats_h[6] = s->ms_step;
+    stats_h[7] = 0.0;
     return LSS_OK;
 }

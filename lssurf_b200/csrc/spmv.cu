@@ -69,57 +69,58 @@ spmv_tile_bounds_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ ind
     bounds[2 * t + 1] = (int)lower_bound_i32(indptr + 1, n_rows - 1, k1) + 1;
 }
 
-template <int BLOCK>
+// ATOMIC (plain products into a pre-zeroed y only): partial sums of rows cut by a tile boundary are added with RED
+// atomics instead of going through the carry buffers and the fix-up kernel; complete rows are stored.
+template <int BLOCK, bool ATOMIC = false>
 __device__ __forceinline__ void reduce_rows(const double *__restrict__ prod, int tile, int64_t k0, int64_t k1, int64_t r_lo, int64_t r_hi,
                                             const int *__restrict__ indptr, double *__restrict__ y, int mode,
-                                            const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row) {
+                                            const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row,
+                                            const double *__restrict__ xdot = nullptr, double *__restrict__ dot_slots = nullptr) {
+    double dot = 0.0;      // ATOMIC only: this thread's share of x . (A x), summed per warp into dot_slots
     // carry-in: the row that started in an earlier tile and still has entries here
     const bool has_carry = (int64_t)indptr[r_lo] < k0;                // r_lo itself started in an earlier tile
     const int64_t first = r_lo + (has_carry ? 1 : 0);                 // first row that starts in this tile
     const int64_t n_virtual = (r_hi - first) + 1;                     // virtual row 0 is the carry-in
-    if (n_virtual <= 2 * (BLOCK / 32)) {
-        // few, long rows: one warp per row
-        const int w = threadIdx.x >> 5;
-        for (int64_t v = w; v < n_virtual; v += BLOCK / 32) {
-            int64_t b, e, r = first + v - 1;
+    // g lanes per row, g the largest power of two with n_virtual * g <= BLOCK: one thread per row for the 13-entry rows
+    // of G (~80 rows per tile), 8 lanes per row for the ~90-entry rows of the explicit normal matrix, a warp per row
+    // for the long rows of A^T.  Lanes of a group stride the row's staged products, then fold with g-wide shuffles.
+    int g = 1;
+    while (g < 32 && n_virtual * (2 * g) <= BLOCK) g <<= 1;
+    const int gl = threadIdx.x & (g - 1), rows_per_pass = BLOCK / g;
+    for (int64_t base = 0; base < n_virtual; base += rows_per_pass) {
+        const int64_t v = base + threadIdx.x / g;
+        const bool valid = v < n_virtual && !(v == 0 && !has_carry);
+        int64_t b = 0, e = 0;
+        const int64_t r = first + v - 1, rr = v == 0 ? r_lo : r;
+        if (valid) {
             if (v == 0) {
-                if (!has_carry) continue;
                 b = k0;
                 e = (int64_t)indptr[r_lo + 1];
             } else {
                 b = indptr[r];
                 e = indptr[r + 1];
-            }
-            const bool open = e > k1;   // continues in the next tile
-            if (open) e = k1;
-            double acc = 0.0;
-            for (int64_t k = b - k0 + lane_id(); k < e - k0; k += 32) acc += prod[k];
-            acc = warp_sum(acc);
-            if (lane_id() == 0) {
-                if (v == 0) carry_val[tile] = acc;
-                else y[r] = open ? acc : epilogue(acc, mode, s, r);
             }
         }
-    } else {
-        for (int64_t v = threadIdx.x; v < n_virtual; v += BLOCK) {
-            int64_t b, e, r = first + v - 1;
-            if (v == 0) {
-                if (!has_carry) continue;
-                b = k0;
-                e = (int64_t)indptr[r_lo + 1];
-            } else {
-                b = indptr[r];
-                e = indptr[r + 1];
-            }
-            const bool open = e > k1;
-            if (open) e = k1;
-            double acc = 0.0;
-            for (int64_t k = b - k0; k < e - k0; ++k) acc += prod[k];
-            if (v == 0) carry_val[tile] = acc;
+        const bool open = e > k1;   // continues in the next tile
+        if (open) e = k1;
+        const double xr = (ATOMIC && xdot && valid && gl == 0) ? __ldg(xdot + rr) : 0.0;   // in flight during the sum
+        double acc = 0.0;
+        for (int64_t k = b - k0 + gl; k < e - k0; k += g) acc += prod[k];
+        for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (valid && gl == 0) {
+            if (ATOMIC) {
+                if (v == 0 || open) atomicAdd(y + rr, acc);
+                else y[rr] = acc;
+                dot += acc * xr;
+            } else if (v == 0) carry_val[tile] = acc;
             else y[r] = open ? acc : epilogue(acc, mode, s, r);
         }
     }
-    if (threadIdx.x == 0) carry_row[tile] = has_carry ? (int)r_lo : -1;
+    if (ATOMIC && xdot) {          // x . (A x) as a by-product (partial sums of cut rows add up by linearity)
+        dot = warp_sum(dot);
+        if (lane_id() == 0 && dot != 0.0) atomicAdd(dot_slots + (((unsigned)tile * (BLOCK / 32) + (threadIdx.x >> 5)) & 255u), dot);
+    }
+    if (!ATOMIC && threadIdx.x == 0) carry_row[tile] = has_carry ? (int)r_lo : -1;
 }
 
 template <int BLOCK, int IPT>
@@ -158,12 +159,12 @@ spmv_tile_kernel(int64_t n_rows, int64_t nnz, const int *__restrict__ indptr, co
 // (column indices + values, the HBM traffic) into registers before reducing the current tile's rows, so the
 // DRAM pipe stays busy during the shared-memory phase.  DBUF double-buffers the staged products (one barrier
 // per tile instead of two).
-template <int BLOCK, int IPT, bool DBUF>
+template <int BLOCK, int IPT, bool DBUF, bool ATOMIC = false>
 __global__ void __launch_bounds__(BLOCK)
 spmv_persistent_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__restrict__ indptr, const int *__restrict__ indices,
                        const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y, int mode,
                        const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row,
-                       const int *__restrict__ tile_bounds, const double *__restrict__ stop) {
+                       const int *__restrict__ tile_bounds, const double *__restrict__ stop, double *__restrict__ dot_slots = nullptr) {
     constexpr int TILE = BLOCK * IPT;
     __shared__ double prod_s[DBUF ? 2 : 1][TILE];
     if (stop && *stop != 0.0) return;
@@ -197,7 +198,7 @@ spmv_persistent_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__re
         const int nt = t + gridDim.x;
         if (nt < n_tiles) fetch(nt);            // in flight during the barrier and the row reduction below
         __syncthreads();
-        reduce_rows<BLOCK>(prod, t, k0, k1, r_lo, r_hi, indptr, y, mode, s, carry_val, carry_row);
+        reduce_rows<BLOCK, ATOMIC>(prod, t, k0, k1, r_lo, r_hi, indptr, y, mode, s, carry_val, carry_row, dot_slots ? x : nullptr, dot_slots);
         if (DBUF) buf ^= 1; else __syncthreads();
     }
 }
@@ -326,6 +327,29 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
     return LSS_OK;
 }
 
+
+// dot_slots (optional, 256 doubles, accumulated into): x . (A x) as a by-product, one RED per warp and tile.
+// y += A x in ONE launch for a y that holds zeros (at least in the rows cut by tile boundaries and the empty rows):
+// the persistent kernel with atomic carries.  Used for the explicit normal matrix inside CG, where the vector step
+// that consumes q clears it for the next product.
+int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
+                       int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots) {
+    if (n_rows <= 0 || nnz == 0) return LSS_OK;
+    constexpr int BLOCK = 128, IPT = 8;
+    if (!plan || !plan->bounds || plan->tile != BLOCK * IPT) return fail(LSS_EINVAL, "spmv_launch_atomic: needs a plan with %d-entry tiles", BLOCK * IPT);
+    const int n_tiles = ceil_div(nnz, BLOCK * IPT);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_persistent_kernel<BLOCK, IPT, false, true>, BLOCK, 0);
+        if (per_sm < 1) per_sm = 1;
+    }
+    const int grid = n_tiles < kSMs * per_sm ? n_tiles : kSMs * per_sm;
+    spmv_persistent_kernel<BLOCK, IPT, false, true><<<grid, BLOCK, 0, stream>>>(n_rows, nnz, n_tiles, indptr, indices, data, x, y, LSS_SPMV_PLAIN,
+                                                                                nullptr, nullptr, nullptr, plan->bounds, stop, dot_slots);
+    LSS_LAUNCH_CHECK();
+    if (launches) *launches += 1;
+    return LSS_OK;
+}
 
 // ============================================================================ ELL (fixed row length) product
 // The data block G has the same number of entries in every row (2^2 z0 corners + 2^3 dz corners + bias columns),

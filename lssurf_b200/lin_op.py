@@ -455,6 +455,8 @@ class lin_op(object):
             mask = self.grid.mask
         if mask is None:
             return np.ones_like(self.ind0, dtype=float)
+        if mask_scale is None and mask.dtype == bool and mask.all():
+            return np.ones(np.shape(self.ind0), dtype=bool)       # default all-True mask: nothing to sample
         local = self.ind0 - self.grid.col_0
         if len(self.grid.shape) > len(mask.shape):
             full = np.unravel_index(local, self.grid.shape)

@@ -19,6 +19,7 @@ import os
 from time import time, ctime
 
 import numpy as np
+import scipy.sparse as sp
 import torch
 
 from . import _cabi
@@ -151,8 +152,14 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
     rhs_d = _cabi.to_dev(rhs, f64)
     sigma = E_all[:n_data].contiguous()
     z = rhs_d[:n_data].contiguous()
-    free_cols = np.unique(Ip_c.tocoo().row) if hasattr(Ip_c, 'tocoo') else np.asarray(Ip_c.free_cols)
-    fixed_cols = np.setdiff1d(np.arange(n_cols), free_cols)
+    # rows of the selection matrix that hold an entry are the free columns (boolean mask instead of unique / setdiff1d)
+    is_free = np.zeros(n_cols, dtype=bool)
+    if sp.issparse(Ip_c):
+        Ipc = Ip_c if Ip_c.format in ('csc', 'coo') else Ip_c.tocoo()
+        is_free[Ipc.indices if Ipc.format == 'csc' else Ipc.row] = True
+    else:
+        is_free[np.asarray(Ip_c.free_cols)] = True
+    fixed_cols = np.flatnonzero(~is_free)
 
     # device operator: this rank's data rows + its share of the constraint rows
     G_csr = G_data._csr_device(col_N=n_cols, row_N=n_data)

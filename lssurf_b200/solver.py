@@ -184,9 +184,9 @@ class NormalSolver(object):
         it, rel = C.c_int32(0), C.c_double(0.0)
         _cabi.check(_cabi.lib().lss_solver_solve(self.handle, _cabi.ptr(self.x), float(rtol), int(max_iter),
                                                  C.byref(it), C.byref(rel)))
-        st = (C.c_double * 6)()
+        st = (C.c_double * 8)()
         _cabi.check(_cabi.lib().lss_solver_stats(self.handle, st))
-        self.last = dict(iterations=it.value, relres=rel.value, ms=st[0], ms_A=st[1], ms_At=st[2], n_apply=int(st[3]),
+        self.last = dict(iterations=it.value, relres=rel.value, ms=st[0], ms_A=st[1], ms_At=st[2], ms_step=st[6], n_apply=int(st[3]),
                          launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused, all_ell=self.all_ell,
                          n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz,
                          form=self.form, nnz_N=self.nnz_N, n_cols=self.n_cols, precond_blocks=self.n_blocks, eliminated=self.n_elim)
