@@ -255,14 +255,16 @@ def run_b200(a):
         # q written and p read once (SURVEY 8(d) formula applied to N).  The two-product CSR form of the same
         # operator (what SURVEY 8(d) budgets per CG iteration) is reported alongside for comparison.
         nnzN = p0['nnz_N']
-        b_dom = spmv_bytes(n_cols, n_cols, nnzN, False)
+        nnzP = p0.get('nnz_product') or nnzN          # the rows of the eliminated bias block are not part of the CG product
+        b_dom = spmv_bytes(n_cols - p0.get('eliminated', 0), n_cols, nnzP, False)
         ms_dom = ms_at / n_apply
         ach = b_dom / (ms_dom / 1e3) / 1e9
         b_two = spmv_bytes(p0['rows'], n_cols, nnz, True) + spmv_bytes(n_cols, p0['rows'], nnz, False)
-        roofline = {'bound': 'hbm', 'kernel': 'lss::spmv_persistent_kernel<128,8> on the explicit normal matrix (q = N p, N = A^T W A)',
+        roofline = {'bound': 'hbm', 'kernel': 'lss::spmv_persistent_kernel<128,8,false,true> on the explicit normal matrix (q = N p, N = A^T W A; one launch, '
+                              'atomic carries, p.q by-product)',
                     'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peak_src,
                     'traffic': traffic, 'bytes_per_launch': {'N': b_dom}, 'launch_ms': {'N': ms_dom},
-                    'nnz_N': nnzN, 'nnz_A': nnz,
+                    'nnz_N': nnzN, 'nnz_streamed_per_product': nnzP, 'nnz_A': nnz,
                     'csr_pair_equivalent': {'bytes': b_two, 'gbs': b_two / (ms_dom / 1e3) / 1e9,
                                             'note': 'bytes the A / A^T two-product form of the same operator would stream, '
                                                     'divided by the time of the N product (not a bandwidth claim)'},

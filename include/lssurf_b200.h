@@ -208,7 +208,8 @@ int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, int64_t n_co
  * 2 explicit normal matrix; info_h[1] = nnz of the explicit normal matrix (0 otherwise); info_h[2] = column pairs
  * sorted by its symbolic phase; info_h[3] = rows of A held in ELL form; info_h[4] = preconditioner blocks;
  * info_h[5] = eliminated columns; info_h[6] = blocks that were not positive definite in the last set_weights
- * (they fall back to their diagonal).  info_h has 8 entries. */
+ * (they fall back to their diagonal); info_h[7] = non-zeros of N streamed per CG product (rows of an eliminated
+ * trailing block are left out; valid after the first solve).  info_h has 8 entries. */
 int lss_solver_info(lss_solver_t *solver, int64_t *info_h);
 /* Optional structure of the unknowns for the explicit-normal form (ignored by the other forms); call once, before
  * lss_solver_set_weights.
@@ -219,7 +220,8 @@ int lss_solver_info(lss_solver_t *solver, int64_t *info_h);
  *   [elim_begin, elim_end): a column range whose diagonal block of A^T W A is diagonal (every row of A holds at most
  *     one of them: the per-(rgt, cycle) bias columns of assign_bias_ID, bias_functions.py:25-82).  They are eliminated
  *     exactly (CG runs on the Schur complement and back-substitutes); LSS_EINVAL if the block is not diagonal.
- *     Ignored on more than one rank. */
+ *     With row-sharded ranks the slaved entries cost one extra small all-reduce (elim_end - elim_begin doubles)
+ *     per CG iteration. */
 int lss_solver_set_structure(lss_solver_t *solver, int32_t n_blocks, const int32_t *block_ptr, const int32_t *block_cols,
                              int32_t max_block, int64_t elim_begin, int64_t elim_end);
 /* Row weights w (length n_rows): 1/sigma^2 for selected data rows, 0 for edited rows, 1/E_c^2 for

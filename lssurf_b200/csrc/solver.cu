@@ -199,8 +199,7 @@ cg_step_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots,
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK)
         p[i] = minv[i] * r[i] + beta * p[i];
     if (blockIdx.x == 0) {
-        if (pq_slots)
-            for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;     // every block read them before the barrier
+        for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;     // every block read them before the barrier
         if (threadIdx.x == 0) {
             scal[S_RZ0 + (parity ^ 1)] = rz_new;
             scal[S_RZ_LAST] = rz_new;
@@ -289,7 +288,7 @@ constexpr int ELIM_BLOCK = 512, ELIM_IPT = 4;
 __global__ void __launch_bounds__(ELIM_BLOCK)
 elim_solve_kernel(int64_t e0, int64_t e1, const int *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ data,
                   const double *v, const double *__restrict__ c, const double *__restrict__ einv, double *out,
-                  const double *__restrict__ stop) {
+                  const double *__restrict__ stop, double *__restrict__ raw) {
     __shared__ double sm[ELIM_BLOCK / 32];
     const double stop_v = stop ? *reinterpret_cast<const volatile double *>(stop) : 0.0;
     const int64_t row = e0 + blockIdx.x;
@@ -317,8 +316,19 @@ elim_solve_kernel(int64_t e0, int64_t e1, const int *__restrict__ indptr, const 
     if (threadIdx.x < 32) {
         double t = threadIdx.x < ELIM_BLOCK / 32 ? sm[threadIdx.x] : 0.0;
         t = warp_sum(t);
-        if (threadIdx.x == 0) out[row] = einv[row - e0] * ((c ? c[row] : 0.0) - t);
+        if (threadIdx.x == 0) {
+            if (raw) raw[row - e0] = t;        // row-sharded N: the sums are completed over ranks first (elim_finish_kernel)
+            else out[row] = einv[row - e0] * ((c ? c[row] : 0.0) - t);
+        }
     }
+}
+
+__global__ void __launch_bounds__(256)
+elim_finish_kernel(int64_t e0, int64_t e1, const double *__restrict__ t, const double *__restrict__ c, const double *__restrict__ einv,
+                   double *__restrict__ out, const double *__restrict__ stop) {
+    if (stop && *stop != 0.0) return;
+    const int64_t i = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e1) out[i] = einv[i - e0] * ((c ? c[i] : 0.0) - t[i - e0]);
 }
 
 // r = g - q (q may be null), r_E = 0, x = 0 at fixed columns
@@ -370,17 +380,7 @@ cg_step_p_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slot
         c0 = (int)lane < bs ? __ldg(bcols + (size_t)b * bs + lane) : -1;
         c1 = (int)lane + 32 < bs ? __ldg(bcols + (size_t)b * bs + 32 + lane) : -1;
     }
-    double pq;
-    if (pq_slots) {
-        pq = sum_partials(pq_slots, PQ_SLOTS, sm);
-    } else {                                   // p.q formed here (one more grid barrier)
-        double d = 0.0;
-        for (int64_t i = tid; i < n; i += nth) d += p[i] * q[i];
-        d = block_sum(d, sm);
-        if (threadIdx.x == 0) part[gridDim.x + blockIdx.x] = d;
-        cgx::this_grid().sync();
-        pq = sum_partials(part + gridDim.x, (int)gridDim.x, sm);
-    }
+    const double pq = sum_partials(pq_slots, PQ_SLOTS, sm);
     const double rz_old = scal[S_RZ0 + parity];
     const double alpha = pq > 0.0 ? rz_old / pq : 0.0;
     double v = 0.0;
@@ -502,10 +502,9 @@ struct lss_solver {
     // structured form (lss_solver_set_structure): block-Jacobi preconditioner and / or eliminated diagonal block
     lss::BlockPrecond *bp;
     int64_t e0, e1;          // eliminated columns [e0, e1); e0 == e1: none
-    double *einv, *z;
+    double *einv, *z, *eraw;   // eraw: rank-local N_Eg v sums (multi-rank only)
     int step_grid;           // CTAs of the cooperative step kernel
     bool l2_window;          // an L2 persisting window on the preconditioner blocks is installed on the stream
-    bool pq_in_step;         // the step kernel forms p.q itself instead of taking it from the product kernel
 };
 
 
@@ -536,6 +535,7 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     }
     if (s->bp) lss::block_precond_destroy(s->bp);
     if (s->einv) cudaFreeAsync(s->einv, s->stream);
+    if (s->eraw) cudaFreeAsync(s->eraw, s->stream);
     if (s->z) cudaFreeAsync(s->z, s->stream);
     if (s->nm) lss::normal_destroy(s->nm);
     if (s->ell_col) cudaFreeAsync(s->ell_col, s->stream);
@@ -655,7 +655,8 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
     if (!s) return fail(LSS_EINVAL, "solver_set_structure: null solver");
     if (!s->nm) return LSS_OK;          // only the explicit-normal form has the matrix entries these need
     cudaStream_t st = s->stream;
-    const bool want_elim = elim_end > elim_begin && !(s->comm && s->comm->n_ranks > 1);   // N_Eg rows are rank-local sums
+    const bool multi = s->comm && s->comm->n_ranks > 1;
+    const bool want_elim = elim_end > elim_begin;
     if (want_elim) {
         if (elim_begin < 0 || elim_end > s->n_cols) return fail(LSS_EINVAL, "solver_set_structure: eliminated range outside the columns");
         Scratch bad;
@@ -664,6 +665,7 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
         elim_check_kernel<<<ceil_div((elim_end - elim_begin) * 32, 256), 256, 0, st>>>(elim_begin, elim_end, s->nm->indptr, s->nm->indices,
                                                                                      bad.as<unsigned long long>());
         LSS_LAUNCH_CHECK();
+        LSS_TRY(comm_allreduce(s->comm, bad.p, 1, 2, 0, st));      // the block must be diagonal on every rank
         unsigned long long nb = 0;
         LSS_CUDA(cudaMemcpyAsync(&nb, bad.p, sizeof(nb), cudaMemcpyDeviceToHost, st));
         LSS_CUDA(cudaStreamSynchronize(st));
@@ -671,6 +673,7 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
                             (long long)elim_begin, (long long)elim_end, nb);
         s->e0 = elim_begin; s->e1 = elim_end;
         LSS_TRY(dev_alloc(&s->einv, elim_end - elim_begin, st));
+        if (multi) LSS_TRY(dev_alloc(&s->eraw, elim_end - elim_begin, st));
     }
     if (n_blocks > 0) LSS_TRY(block_precond_create(&s->bp, s->n_cols, n_blocks, block_ptr, block_cols, max_block, st));
     if (s->bp && !getenv("LSS_NO_L2_WINDOW")) {
@@ -704,7 +707,6 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
         if (per_sm > STEP_PER_SM) per_sm = STEP_PER_SM;
         s->step_grid = kSMs * per_sm;
     }
-    s->pq_in_step = getenv("LSS_PQ_IN_STEP") != nullptr;
     s->have_weights = false;
     return LSS_OK;
 }
@@ -731,7 +733,7 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
         if (timed) LSS_CUDA(cudaEventRecord(e1, st));
         // q = N v : one gather product, one launch (rows of an eliminated trailing block are left out: (N p)_E = 0)
         const int64_t rows = (s->e1 > s->e0 && s->e1 == s->n_cols) ? s->e0 : s->n_cols;
-        double *slots = (s->z && with_dot && !s->pq_in_step) ? s->buf + s->n_cols : nullptr;      // p.q by-product for the structured step kernel
+        double *slots = (s->z && with_dot) ? s->buf + s->n_cols : nullptr;      // p.q by-product for the structured step kernel
         if (slots && !s->q_clean) LSS_CUDA(cudaMemsetAsync(slots, 0, sizeof(double) * PQ_SLOTS, st));
         LSS_TRY(normal_apply_fast(s->nm, rows, v, s->buf, s->q_clean, stop, &s->launches, slots));
         s->q_clean = false;
@@ -760,7 +762,7 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     if (timed) LSS_CUDA(cudaEventRecord(e2, st));
     int64_t n_red = s->n_cols;
     if (s->nm) {
-        if (s->z && with_dot && !s->pq_in_step) n_red += PQ_SLOTS;   // structured form: the product left its p.q partials behind q
+        if (s->z && with_dot) n_red += PQ_SLOTS;   // structured form: the product left its p.q partials behind q
         // plain form: p.q is formed from the reduced q by cg_step_n_kernel on every rank
     } else if (s->blocks) {
         n_red += PQ_SLOTS;              // the fused kernel already left the p.q partials behind q
@@ -772,6 +774,22 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
     }
     LSS_TRY(comm_allreduce(s->comm, s->buf, n_red, 0, 0, st));
     s->n_apply += 1;
+    return LSS_OK;
+}
+
+// v_E = N_EE^-1 (c_E - N_Eg v_g): one kernel on one rank; local sums, all-reduce, finish when the rows of N are sharded
+static int elim_slave(lss_solver *s, double *v, const double *c, const double *stop) {
+    cudaStream_t st = s->stream;
+    const int n_e = (int)(s->e1 - s->e0);
+    elim_solve_kernel<<<n_e, ELIM_BLOCK, 0, st>>>(s->e0, s->e1, s->nm->indptr, s->nm->indices, s->nm->data, v, c, s->einv, v, stop, s->eraw);
+    LSS_LAUNCH_CHECK();
+    s->launches += 1;
+    if (s->eraw) {
+        LSS_TRY(comm_allreduce(s->comm, s->eraw, n_e, 0, 0, st));
+        elim_finish_kernel<<<ceil_div(n_e, 256), 256, 0, st>>>(s->e0, s->e1, s->eraw, c, s->einv, v, stop);
+        LSS_LAUNCH_CHECK();
+        s->launches += 1;
+    }
     return LSS_OK;
 }
 
@@ -828,10 +846,9 @@ extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
             elim_setup_kernel<<<ceil_div(s->e1 - s->e0, 256), 256, 0, st>>>(s->e0, s->e1, s->diag, s->einv, s->minv);
             LSS_LAUNCH_CHECK();
             LSS_CUDA(cudaMemsetAsync(s->p, 0, sizeof(double) * n, st));
-            elim_solve_kernel<<<(int)(s->e1 - s->e0), ELIM_BLOCK, 0, st>>>(s->e0, s->e1, s->nm->indptr, s->nm->indices, s->nm->data, s->p, s->g,
-                                                                   s->einv, s->p, nullptr);
-            LSS_LAUNCH_CHECK();
+            LSS_TRY(elim_slave(s, s->p, s->g, nullptr));
             LSS_TRY(normal_apply(s->nm, s->p, s->buf, nullptr, nullptr));
+            LSS_TRY(comm_allreduce(s->comm, s->buf, n, 0, 0, st));
             gq = s->buf;
         }
         resid_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->g, gq, s->fixed, s->e0, s->e1, nullptr, s->r);
@@ -862,12 +879,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     LSS_LAUNCH_CHECK();
     const bool structured = s->z != nullptr;
     const bool elim = s->e1 > s->e0;
-    auto slave = [&](double *v, const double *c, const double *stop) -> int {      // v_E = N_EE^-1 (c_E - N_Eg v_g)
-        elim_solve_kernel<<<(int)(s->e1 - s->e0), ELIM_BLOCK, 0, st>>>(s->e0, s->e1, s->nm->indptr, s->nm->indices, s->nm->data, v, c, s->einv, v, stop);
-        LSS_LAUNCH_CHECK();
-        s->launches += 1;
-        return LSS_OK;
-    };
+    auto slave = [&](double *v, const double *c, const double *stop) -> int { return elim_slave(s, v, c, stop); };
     if (structured) {
         if (elim) LSS_TRY(slave(x, s->g, nullptr));
         LSS_TRY(apply_normal(s, x, false, nullptr));
@@ -919,7 +931,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
                 int par = parity, nb = s->bp ? s->bp->n_blocks : 0, bs = s->bp ? s->bp->bs : 0;
                 const int *bcols = s->bp ? s->bp->cols_pad : nullptr, *cblk = s->bp ? s->bp->col_block : nullptr;
                 const float *binv = s->bp ? s->bp->inv : nullptr;
-                double *slots = s->pq_in_step ? nullptr : s->buf + n;
+                double *slots = s->buf + n;
                 void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &rv, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv};
                 LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_p_kernel, dim3(s->step_grid), dim3(VEC_BLOCK), args, 0, st));
                 ++lss::g_launches;
@@ -1005,6 +1017,8 @@ extern "C" int lss_solver_info(lss_solver_t *s, int64_t *info_h) {
     info_h[4] = s->bp ? s->bp->n_blocks : 0;
     info_h[5] = s->e1 - s->e0;
     info_h[6] = 0;
+    // non-zeros the CG product streams per application (the rows of an eliminated trailing block are left out)
+    info_h[7] = s->nm ? ((s->e1 > s->e0 && s->e1 == s->n_cols && s->nm->part_rows == s->e0) ? s->nm->part_nnz : s->nm->nnz) : 0;
     if (s->bp) {
         unsigned int nb = 0;
         cudaMemcpyAsync(&nb, s->bp->n_bad, sizeof(nb), cudaMemcpyDeviceToHost, s->stream);

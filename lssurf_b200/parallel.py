@@ -1,12 +1,18 @@
 """Row-sharded data parallelism over the GPUs of one node: one process per GPU.
 
 The reference is single-process.  Here each rank owns a contiguous block of data
-rows of G plus a 1/P share of the constraint rows; the grid unknowns are replicated.  The only
-data-path collective is one NCCL all-reduce (fp64 sum) of A^T W (A p) plus the dot-product partials
-per CG iteration, issued from the C++ solver loop through the communicator created here
-(``lss_comm_create`` -> ncclCommInitRank, NVLink 5 / NVSwitch).  torch.distributed (any backend,
-gloo on CPU works) is used ONLY as the host transport for the 128-byte NCCL unique id and for
-gathering per-point outputs at the end.
+rows: it assembles its rows of G and does all per-point work (residuals, order statistics, edit masks) on them.
+Two ways to run the solve:
+  * replicated solve (default): the assembled rows are all-gathered once (NCCL all-gather over NVLink, ~2 GB at 10^7
+    points), every rank forms the same normal matrix and runs the same PCG with NO collective inside the iteration
+    (one CG iteration is ~150 us of work on one B200 -- less than one 8-rank all-reduce costs); the solution is
+    broadcast from rank 0 after every solve so all ranks continue from identical bits;
+  * row-sharded solve (``LSS_SHARDED_SOLVE=1``): each rank keeps only its rows plus a 1/P share of the constraint
+    rows and the products are summed with one NCCL all-reduce (fp64) per CG iteration, issued from the C++ solver
+    loop through the communicator created here (``lss_comm_create`` -> ncclCommInitRank) -- for problems whose
+    iteration is long compared with the collective.
+torch.distributed is plumbing only: the host transport for the 128-byte NCCL unique id (any backend, gloo on CPU
+works), the all-gathers of assembled rows / masks / per-point outputs and the broadcast of the solution.
 """
 import ctypes as C
 import os
@@ -52,6 +58,48 @@ class DistContext(object):
         out = torch.empty(m * self.world, dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, pad)
         return torch.cat([out[i * m:i * m + sizes[i]] for i in range(self.world)])
+
+    def gather_counts(self, n):
+        """Every rank's value of the integer n, in rank order (host transport)."""
+        if self.world == 1:
+            return [int(n)]
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, int(n))
+        return [int(v) for v in parts]
+
+    def gather_var_device(self, t, counts):
+        """Concatenate 1-D CUDA tensors of different lengths (counts[r] on rank r) in rank order on every rank."""
+        if self.world == 1:
+            return t
+        import torch.distributed as dist
+        if dist.get_backend() != 'nccl':        # host transport (CPU tests under gloo)
+            return torch.from_numpy(self.gather_rows(t.cpu().numpy())).to(t.device)
+        m = max(max(counts), 1)
+        pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+        pad[:t.numel()] = t
+        out = torch.empty(m * self.world, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad)
+        return torch.cat([out[i * m:i * m + counts[i]] for i in range(self.world)])
+
+    def gather_csr(self, A):
+        """Stack the per-rank row blocks of a DeviceCSR in rank order on every rank (NCCL all-gather over NVLink)."""
+        from .lin_op import DeviceCSR
+        if self.world == 1:
+            return A
+        rows = self.gather_counts(A.shape[0])
+        nnzs = self.gather_counts(A.nnz)
+        lens = self.gather_var_device((A.indptr[1:] - A.indptr[:-1]).contiguous(), rows)
+        indptr = torch.zeros(sum(rows) + 1, dtype=torch.int32, device=lens.device)
+        indptr[1:] = torch.cumsum(lens, 0)
+        return DeviceCSR(indptr, self.gather_var_device(A.indices, nnzs), self.gather_var_device(A.data, nnzs), (sum(rows), A.shape[1]))
+
+    def broadcast(self, t, src=0):
+        """In-place broadcast of a CUDA tensor from rank src (keeps replicated solves bit-identical across ranks)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(t, src=src)
+        return t
 
     def allreduce_sum(self, t):
         """In-place fp64 sum over ranks of a CUDA tensor through the library's NCCL communicator."""

@@ -161,20 +161,32 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         is_free[np.asarray(Ip_c.free_cols)] = True
     fixed_cols = np.flatnonzero(~is_free)
 
-    # device operator: this rank's data rows + its share of the constraint rows
+    # device operator
     G_csr = G_data._csr_device(col_N=n_cols, row_N=n_data)
     C_all = Gc._csr_device(col_N=n_cols, row_N=int(Gc.N_eq))
-    c_lo, c_hi = (0, int(Gc.N_eq)) if dist is None else dist.shard(int(Gc.N_eq))
-    C_loc = C_all if (c_lo, c_hi) == (0, int(Gc.N_eq)) else C_all.row_slice(c_lo, c_hi)
-    prior = rhs_d[n_data + c_lo:n_data + c_hi].contiguous()
-    Ec = E_all[n_data + c_lo:n_data + c_hi].contiguous()
+    multi = dist is not None and dist.world > 1
+    replicate = multi and not os.environ.get('LSS_SHARDED_SOLVE')
     st = _Stages(bool(args.get('time_stages')), timing.setdefault('stages', {}))
     st.mark('it:prep')
-    G_csr = G_csr
-    st.mark('it:csr')
-    # structure of the unknowns for the preconditioner: (dz node epochs + nearest z0 nodes) blocks, bias columns eliminated
     structure = grid_structure(grids, fixed_cols, bias_cols=G_data.TOC['cols'].get('data_bias')) if isinstance(grids, dict) else None
-    solver = NormalSolver(G_csr, C_loc, z, prior, sigma, Ec, fixed_cols, dist, structure=structure)
+    if replicate:
+        # replicated solve: every rank gets all assembled rows once and runs the same PCG with no collective inside the
+        # iteration; per-point work (residuals, sigma_extra, edit masks) stays on the rank's own rows
+        row_counts = dist.gather_counts(n_data)
+        G_full = dist.gather_csr(G_csr)
+        z_full, sigma_full = dist.gather_var_device(z, row_counts), dist.gather_var_device(sigma, row_counts)
+        st.mark('it:csr')
+        solver = NormalSolver(G_full, C_all, z_full, rhs_d[n_data:].contiguous(), sigma_full, E_all[n_data:].contiguous(),
+                              fixed_cols, None, structure=structure, G_local=G_csr)
+        del G_full
+    else:
+        # row-sharded solve: this rank's data rows + its share of the constraint rows, one all-reduce per CG iteration
+        c_lo, c_hi = (0, int(Gc.N_eq)) if dist is None else dist.shard(int(Gc.N_eq))
+        C_loc = C_all if (c_lo, c_hi) == (0, int(Gc.N_eq)) else C_all.row_slice(c_lo, c_hi)
+        prior = rhs_d[n_data + c_lo:n_data + c_hi].contiguous()
+        Ec = E_all[n_data + c_lo:n_data + c_hi].contiguous()
+        st.mark('it:csr')
+        solver = NormalSolver(G_csr, C_loc, z, prior, sigma, Ec, fixed_cols, dist, structure=structure)
     solver.set_profile(bool(args.get('profile_spmv')))
     stats = timing.setdefault('pcg', [])
     st.mark('it:solver_setup(vstack+transpose)')
@@ -204,13 +216,19 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         relax = last_iteration and args['sigma_extra_relax']
         if relax and args['VERBOSE']:
             print('smooth_fit.iterate_fit: relaxing errors by sigma_extra')
-        solver.set_rows(in_TSE_d, sigma_extra if relax else None)
+        if replicate:
+            solver.set_rows(dist.gather_var_device(in_TSE_d, row_counts),
+                            dist.gather_var_device(sigma_extra, row_counts) if relax else None)
+        else:
+            solver.set_rows(in_TSE_d, sigma_extra if relax else None)
         st.mark('it:set_weights')
         if args['VERBOSE']:
             print("starting qr solve for iteration %d at %s" % (iteration, ctime()), flush=True)
         tic = time()
         m0_last = m0
         x = solver.solve(rtol=args['cg_rtol'], max_iter=args['cg_maxiter'], warm_start=True)
+        if replicate:
+            dist.broadcast(x, src=0)          # every rank continues from rank 0's bits
         m0 = x.cpu().numpy().copy()
         timing['sparseqr_solve'] = time() - tic
         stats.append(dict(solver.last, iteration=iteration, wall_s=timing['sparseqr_solve']))

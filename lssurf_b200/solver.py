@@ -99,13 +99,14 @@ def grid_structure(grids, fixed_cols, bias_cols=None, max_block=64):
 
 
 class NormalSolver(object):
-    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None):
+    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None, G_local=None):
         """G: DeviceCSR of this rank's data rows; Cn: DeviceCSR of this rank's constraint rows;
         z / sigma: data values and errors (CUDA fp64); prior / Ec: constraint right-hand side and sigma;
         fixed_cols: columns held at zero (reference epoch)."""
         L = _cabi.lib()
         self.n_data, self.n_con, self.n_cols = G.shape[0], Cn.shape[0], G.shape[1]
         self.G, self.C = G, Cn
+        self.G_local = G if G_local is None else G_local      # rows whose residual this rank owns (replicated solve: its shard)
         self.rhs = torch.cat([z, prior]).contiguous()
         self.sigma = sigma
         self.w = torch.empty(self.n_data + self.n_con, dtype=torch.float64, device=z.device)
@@ -186,15 +187,18 @@ class NormalSolver(object):
                                                  C.byref(it), C.byref(rel)))
         st = (C.c_double * 8)()
         _cabi.check(_cabi.lib().lss_solver_stats(self.handle, st))
+        info = (C.c_int64 * 8)()
+        _cabi.check(_cabi.lib().lss_solver_info(self.handle, info))
         self.last = dict(iterations=it.value, relres=rel.value, ms=st[0], ms_A=st[1], ms_At=st[2], ms_step=st[6], n_apply=int(st[3]),
                          launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused, all_ell=self.all_ell,
                          n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz,
-                         form=self.form, nnz_N=self.nnz_N, n_cols=self.n_cols, precond_blocks=self.n_blocks, eliminated=self.n_elim)
+                         form=self.form, nnz_N=self.nnz_N, n_cols=self.n_cols, precond_blocks=self.n_blocks, eliminated=self.n_elim,
+                         nnz_product=int(info[7]), bad_blocks=int(info[6]))
         return self.x
 
     def residual(self, x, z, out=None):
         """r = z - G x over this rank's data rows (LSsurf/smooth_fit.py:146)."""
-        return self.G.dot(x, mode=_cabi.SPMV_RESIDUAL, s=z, out=out)
+        return self.G_local.dot(x, mode=_cabi.SPMV_RESIDUAL, s=z, out=out)
 
     def close(self):
         if self.handle:

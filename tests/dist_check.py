@@ -2,9 +2,10 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
 
-Every rank runs the row-sharded smooth_fit; rank 0 then repeats the fit on one GPU and requires the same
-edit masks after every outer iteration and the same model to 1e-9 relative L2 (all-reduce summation order
-differs from the single-GPU order).
+Every rank runs the multi-GPU smooth_fit in both solve modes (replicated solve: rows all-gathered once, no collective
+inside CG; row-sharded solve, LSS_SHARDED_SOLVE=1: one all-reduce per CG iteration); rank 0 then repeats the fit on one
+GPU and requires the same edit masks after every outer iteration and the same model to 1e-9 relative L2 (summation
+order differs from the single-GPU order).
 """
 import os
 import sys
@@ -22,10 +23,15 @@ def main():
     cases = [('uniform_3d', synthetic.uniform_3d(n=200_000, width=3.e4, seed=4)),
              ('tracks_bias', synthetic.icesat2_tracks(n=300_000, width=2.e4, seed=4))]
     ok = True
-    for name, (pts, kw) in cases:
+    for name, (pts, kw), mode in [(c[0], c[1], m) for c in cases for m in ('replicated', 'sharded')]:
         hist = []
+        if mode == 'sharded':
+            os.environ['LSS_SHARDED_SOLVE'] = '1'
+        else:
+            os.environ.pop('LSS_SHARDED_SOLVE', None)
         S = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, dist=ctx if ctx.world > 1 else None,
                          history=hist, **kw)
+        name = name + '/' + mode
         if ctx.rank == 0:
             hist1 = []
             S1 = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, history=hist1, **kw)

@@ -78,7 +78,19 @@ def _gloo_worker(rank, world, port, q):
     # the data-path reduction every rank must agree on (what ncclAllReduce does on the GPU)
     t = torch.tensor([float(hi - lo), float(rank)], dtype=torch.float64)
     dist.all_reduce(t)
-    q.put((rank, out.tolist(), t.tolist()))
+    # replicated solve plumbing: per-rank CSR row blocks (different sizes) stacked in rank order on every rank
+    import scipy.sparse as sp
+    from lssurf_b200.lin_op import DeviceCSR
+    M = sp.random(11, 6, density=0.4, random_state=3, format='csr')
+    blk = M[lo:hi].tocsr()
+    A = DeviceCSR(torch.from_numpy(blk.indptr.astype(np.int32)), torch.from_numpy(blk.indices.astype(np.int32)),
+                  torch.from_numpy(blk.data), blk.shape)
+    F = ctx.gather_csr(A)
+    same = (F.shape == M.shape and np.array_equal(F.indptr.numpy(), M.indptr) and np.array_equal(F.indices.numpy(), M.indices)
+            and np.array_equal(F.data.numpy(), M.data) and ctx.gather_counts(hi - lo) == [5, 6])
+    x = torch.full((3,), float(rank + 1), dtype=torch.float64)
+    ctx.broadcast(x, src=0)
+    q.put((rank, out.tolist(), t.tolist() + [float(same), float(x.sum())]))
     dist.destroy_process_group()
 
 
@@ -96,4 +108,35 @@ def test_row_sharding_world2_gloo():
         p.join(timeout=60)
     for rank, gathered, red in res:
         assert gathered == (np.arange(11.) * 2).tolist()
-        assert red == [11.0, 1.0]
+        assert red == [11.0, 1.0, 1.0, 3.0]
+
+
+def test_grid_structure_partition():
+    """Preconditioner blocks handed to lss_solver_set_structure: every free z0 / dz column sits in exactly one block,
+    a block is one dz node's free epochs plus the z0 nodes nearest to it, the bias range is passed through."""
+    from lssurf_b200.solver import grid_structure
+    from lssurf_b200.constraint_functions import reference_epoch_columns
+    by, bx, bt = [-3000., 3000.], [-4000., 4000.], [-1., 1.]
+    z0 = fd_grid([by, bx], [250., 250.], name='z0')
+    dz = fd_grid([by, bx, bt], [1000., 1000., 0.25], name='dz', col_0=z0.N_nodes)
+    grids = {'z0': z0, 'dz': dz}
+    fixed = reference_epoch_columns(grids, 3)
+    bias = np.arange(dz.col_N, dz.col_N + 7)
+    st = grid_structure(grids, fixed, bias_cols=bias)
+    ptr, cols = st['block_ptr'], st['block_cols']
+    assert st['elim'] == (dz.col_N, dz.col_N + 7)
+    assert ptr[0] == 0 and ptr[-1] == cols.size and np.all(np.diff(ptr) > 0) and np.diff(ptr).max() == st['max_block'] <= 64
+    free = np.setdiff1d(np.arange(dz.col_N), fixed)
+    assert np.array_equal(np.sort(cols), free)                        # a partition of the free grid columns
+    ny, nx, nt = dz.shape
+    assert ptr.size - 1 == ny * nx
+    for b in (0, nx + 1, ny * nx - 1):
+        members = cols[ptr[b]:ptr[b + 1]]
+        dz_part = members[members >= dz.col_0] - dz.col_0
+        assert np.all(dz_part // nt == b) and dz_part.size == nt - 1   # all free epochs of one dz node
+        z0_part = members[members < dz.col_0]
+        iy, ix = np.divmod(z0_part, z0.shape[1])
+        jy, jx = divmod(b, nx)
+        assert np.all(np.abs(z0.ctrs[0][iy] - dz.ctrs[0][jy]) <= dz.delta[0] / 2)
+        assert np.all(np.abs(z0.ctrs[1][ix] - dz.ctrs[1][jx]) <= dz.delta[1] / 2)
+    assert grid_structure({'z0': z0}, fixed) is None                  # no dz grid: scalar Jacobi
