@@ -138,25 +138,43 @@ def to_dev(a, dtype=None):
     return t.contiguous()
 
 
-_pinned = {}
+class _PinnedPool(object):
+    """Page-locked host blocks handed out as NumPy arrays and taken back when the array is garbage collected.
+    Two blocks are created the first time a size is asked for: a caller that still holds the previous fit's outputs
+    while the next fit runs (the usual pattern) then never waits for cudaHostAlloc again."""
+
+    def __init__(self):
+        self.free = {}
+
+    def take(self, nbytes):
+        import weakref
+        key = (nbytes + (1 << 20) - 1) >> 20
+        blocks = self.free.setdefault(key, None)
+        if blocks is None:
+            blocks = self.free[key] = [torch.empty(key << 20, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        buf = blocks.pop() if blocks else torch.empty(key << 20, dtype=torch.uint8, pin_memory=True)
+        return buf, (lambda b=buf, bl=blocks: bl.append(b))
+
+
+_pool = _PinnedPool()
 
 
 def to_host(t):
-    """CUDA tensor -> fresh NumPy array through a cached pinned staging buffer (DMA at PCIe speed instead
-    of a pageable copy); the staging buffer is reused, the returned array is owned by the caller."""
+    """CUDA tensor -> NumPy array owned by the caller.  Large tensors are copied by DMA into a page-locked block of
+    their own (no second host copy); the block goes back to a pool when the array is released."""
+    import weakref
     if not t.is_cuda:
         return t.numpy().copy()
     t = t.contiguous()
     nbytes = t.numel() * t.element_size()
     if nbytes < (1 << 20):
         return t.cpu().numpy()
-    buf = _pinned.get('buf')
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 26), dtype=torch.uint8, pin_memory=True)
-        _pinned['buf'] = buf
+    buf, give_back = _pool.take(nbytes)
     view = buf[:nbytes].view(t.dtype).reshape(t.shape)
     view.copy_(t, non_blocking=False)
-    return view.numpy().copy()
+    arr = view.numpy()
+    weakref.finalize(arr, give_back)
+    return arr
 
 
 def grid_struct(shape, stride, lo, hi, delta, col_0):

@@ -354,29 +354,48 @@ init_p_kernel(int64_t n, const double *__restrict__ r, const double *__restrict_
     if (threadIdx.x == 0) part[blockIdx.x] = v;
 }
 
-// One CG iteration's vector work with the block preconditioner (cooperative launch, 3 CTAs per SM):
+// One CG iteration's vector work with the block preconditioner (cooperative launch, 2 CTAs per SM):
 // alpha from the p.q slots the product left behind | x, r, z = M^-1 r (warp per block), r.z | grid barrier | beta, p.
 // Clears q and the slots for the next product.
-constexpr int STEP_PER_SM = 3;
+// The block inverses (bs x bs fp32, contiguous) are staged through shared memory with cp.async, double buffered per
+// warp: while a warp multiplies block b its copy of block b + stride is already in flight, so the phase runs at memory
+// bandwidth instead of one latency per block.
+constexpr int STEP_PER_SM = 2;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(VEC_BLOCK, STEP_PER_SM)
 cg_step_p_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots, const double *__restrict__ minv, double *__restrict__ p,
                  double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *__restrict__ part,
                  double *__restrict__ scal, int parity, int n_blocks, int bs, const int *__restrict__ bcols,
-                 const int *__restrict__ col_block, const float *__restrict__ binv) {
+                 const int *__restrict__ col_block, const float *__restrict__ binv, int n_stage) {
     __shared__ double sm[VEC_BLOCK / 32];
+    extern __shared__ __align__(16) float stage_buf[];      // [warp][n_stage][bs * bs]
     if (scal[S_DONE0 + parity] != 0.0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
         return;
     }
     const int64_t tid = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x, nth = (int64_t)gridDim.x * VEC_BLOCK;
     const unsigned lane = lane_id();
-    const uint64_t keep = l2_policy_evict_last();
-    // the first block's inverse and members are requested before anything else
+    const int bs2 = bs * bs, n16 = bs2 / 4;                 // bs is a multiple of 4: whole 16-byte pieces
+    const int stride = (int)(nth >> 5);
+    float *mine = stage_buf + (size_t)(threadIdx.x >> 5) * n_stage * bs2;
+    auto fetch = [&](int blk, int st) {
+        const float4 *src = reinterpret_cast<const float4 *>(binv + (size_t)blk * bs2);
+        float4 *dst = reinterpret_cast<float4 *>(mine + (size_t)st * bs2);
+        for (int i = (int)lane; i < n16; i += 32) cp_async16(dst + i, src + i);
+    };
     int b = (int)(tid >> 5);
-    BlockRegs R;
+    if (b < n_blocks) fetch(b, 0);
+    cp_async_commit();
     int c0 = -1, c1 = -1;
     if (b < n_blocks) {
-        block_regs_load(R, binv + (size_t)b * bs * bs, bs, keep);
         c0 = (int)lane < bs ? __ldg(bcols + (size_t)b * bs + lane) : -1;
         c1 = (int)lane + 32 < bs ? __ldg(bcols + (size_t)b * bs + 32 + lane) : -1;
     }
@@ -384,22 +403,48 @@ cg_step_p_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slot
     const double rz_old = scal[S_RZ0 + parity];
     const double alpha = pq > 0.0 ? rz_old / pq : 0.0;
     double v = 0.0;
-    for (; b < n_blocks; b += (int)(nth >> 5)) {
+    int st = 0;
+    for (; b < n_blocks; b += stride) {
+        const int nb = b + stride;
+        int d0 = -1, d1 = -1;
+        if (n_stage > 1) {
+            if (nb < n_blocks) {
+                fetch(nb, st ^ 1);
+                d0 = (int)lane < bs ? __ldg(bcols + (size_t)nb * bs + lane) : -1;
+                d1 = (int)lane + 32 < bs ? __ldg(bcols + (size_t)nb * bs + 32 + lane) : -1;
+            }
+            cp_async_commit();
+        }
         double r0 = 0.0, r1 = 0.0;
         if (c0 >= 0) { x[c0] += alpha * p[c0]; r0 = r[c0] - alpha * q[c0]; r[c0] = r0; q[c0] = 0.0; }
         if (c1 >= 0) { x[c1] += alpha * p[c1]; r1 = r[c1] - alpha * q[c1]; r[c1] = r1; q[c1] = 0.0; }
-        double z0, z1;
-        block_apply_warp(binv + (size_t)b * bs * bs, bs, R, r0, r1, z0, z1, keep);
+        if (n_stage > 1) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
+        const float *S = mine + (size_t)st * bs2;
+        double z0 = 0.0, z1 = 0.0;
+        const bool h0 = (int)lane < bs, h1 = (int)lane + 32 < bs;
+#pragma unroll 4
+        for (int j = 0; j < bs; ++j) {                      // the stored inverse is symmetric: column l == row l
+            const double rj = __shfl_sync(0xffffffffu, (j < 32) ? r0 : r1, j & 31);
+            if (h0) z0 += (double)S[j * bs + lane] * rj;
+            if (h1) z1 += (double)S[j * bs + 32 + lane] * rj;
+        }
         if (c0 >= 0) z[c0] = z0;
         if (c1 >= 0) z[c1] = z1;
         v += r0 * z0 + r1 * z1;
-        const int nb = b + (int)(nth >> 5);
-        if (nb < n_blocks) {
-            block_regs_load(R, binv + (size_t)nb * bs * bs, bs, keep);
+        __syncwarp();                                        // all lanes are done with this stage before it is refilled
+        if (n_stage > 1) {
+            st ^= 1;
+            c0 = d0;
+            c1 = d1;
+        } else if (nb < n_blocks) {
+            fetch(nb, 0);
+            cp_async_commit();
             c0 = (int)lane < bs ? __ldg(bcols + (size_t)nb * bs + lane) : -1;
             c1 = (int)lane + 32 < bs ? __ldg(bcols + (size_t)nb * bs + 32 + lane) : -1;
         }
     }
+    cp_async_wait<0>();
     for (int64_t i = tid; i < n; i += nth) {
         if (col_block && col_block[i] >= 0) continue;
         x[i] += alpha * p[i];
@@ -504,6 +549,8 @@ struct lss_solver {
     int64_t e0, e1;          // eliminated columns [e0, e1); e0 == e1: none
     double *einv, *z, *eraw;   // eraw: rank-local N_Eg v sums (multi-rank only)
     int step_grid;           // CTAs of the cooperative step kernel
+    int step_stages;         // shared-memory stages per warp for the block inverses
+    size_t step_smem;
     bool l2_window;          // an L2 persisting window on the preconditioner blocks is installed on the stream
 };
 
@@ -701,9 +748,15 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
     }
     if (s->bp || s->e1 > s->e0) {
         LSS_TRY(dev_alloc(&s->z, s->n_cols, st));
+        // shared-memory staging of the block inverses: two stages per warp when they fit next to a second CTA
+        const size_t one = s->bp ? sizeof(float) * (size_t)s->bp->bs * s->bp->bs * (VEC_BLOCK / 32) : 0;
+        s->step_stages = (2 * one <= 100 * 1024) ? 2 : 1;
+        s->step_smem = one * s->step_stages;
+        if (s->step_smem > 48 * 1024)
+            LSS_CUDA(cudaFuncSetAttribute(cg_step_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->step_smem));
         int per_sm = 0;
-        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_step_p_kernel, VEC_BLOCK, 0));
-        if (per_sm < 1) per_sm = 1;
+        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_step_p_kernel, VEC_BLOCK, s->step_smem));
+        if (per_sm < 1) return fail(LSS_EINVAL, "solver_set_structure: %zu bytes of staging memory per CTA do not fit", s->step_smem);
         if (per_sm > STEP_PER_SM) per_sm = STEP_PER_SM;
         s->step_grid = kSMs * per_sm;
     }
@@ -932,8 +985,9 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
                 const int *bcols = s->bp ? s->bp->cols_pad : nullptr, *cblk = s->bp ? s->bp->col_block : nullptr;
                 const float *binv = s->bp ? s->bp->inv : nullptr;
                 double *slots = s->buf + n;
-                void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &rv, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv};
-                LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_p_kernel, dim3(s->step_grid), dim3(VEC_BLOCK), args, 0, st));
+                int n_stage = s->step_stages;
+                void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &rv, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv, &n_stage};
+                LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_p_kernel, dim3(s->step_grid), dim3(VEC_BLOCK), args, s->step_smem, st));
                 ++lss::g_launches;
                 s->launches += 1;
                 s->q_clean = true;

@@ -144,8 +144,13 @@ class lin_op(object):
     @property
     def ind0(self):
         if isinstance(self._ind0, list):
-            self._ind0 = np.concatenate([np.arange(0, p[1], dtype='int') if isinstance(p, tuple) else np.asarray(p)
-                                         for p in self._ind0]) if self._ind0 else np.zeros([0], dtype=int)
+            def part(p):
+                if isinstance(p, tuple) and p[0] == 'arange':
+                    return np.arange(0, p[1], dtype='int')
+                if isinstance(p, tuple) and p[0] == 'dev':        # centre nodes still on the device (diff_op)
+                    return p[1].cpu().numpy().astype(int)
+                return np.asarray(p)
+            self._ind0 = np.concatenate([part(p) for p in self._ind0]) if self._ind0 else np.zeros([0], dtype=int)
         return self._ind0
 
     @ind0.setter
@@ -258,6 +263,15 @@ class lin_op(object):
         offs = np.array([np.asarray(d).ravel() for d in delta_subs], dtype=np.int64)
         coef = np.array([np.asarray(vals[k]).ravel()[0] for k in range(offs.shape[1])], dtype=float)
         rows, cols, v, ind0 = _cabi.stencil_coo(self.grid.as_struct(), offs, coef, self.row_0, bool(valid_equations_only))
+        if which_nodes is None:
+            # the centre nodes stay on the device until somebody reads .ind0 (no 16 MB copy and sync per stencil)
+            self._set_device(rows, cols, v)
+            self.N_eq = int(ind0.numel())
+            self._ind0 = [('dev', ind0)]
+            self.TOC['rows'] = {self.name: range(self.N_eq)}
+            self.TOC['cols'] = {self.grid.name: np.arange(self.grid.col_0, self.grid.col_0 + self.grid.N_nodes)}
+            self._update_shape()
+            return self
         ind0 = ind0.cpu().numpy()
         if which_nodes is not None:
             # keep only centres listed in which_nodes (lin_op.py:104-106), rows renumbered consecutively
@@ -442,7 +456,7 @@ class lin_op(object):
                 self._set_host(f, np.concatenate(parts[f]))
         if expected:
             self.expected = np.concatenate(expected)
-        self.ind0 = np.concatenate([op.ind0 for op in ops])
+        self._ind0 = [p for op in ops for p in op._ind0_parts()]        # joined on demand
         if self.name is not None and len(self.name) > 0:
             self.TOC['rows'][self.name] = np.arange(0, next_row)
         self._update_shape()
@@ -456,7 +470,7 @@ class lin_op(object):
         if mask is None:
             return np.ones_like(self.ind0, dtype=float)
         if mask_scale is None and mask.dtype == bool and mask.all():
-            return np.ones(np.shape(self.ind0), dtype=bool)       # default all-True mask: nothing to sample
+            return np.ones(int(self.N_eq), dtype=bool)            # default all-True mask: nothing to sample
         local = self.ind0 - self.grid.col_0
         if len(self.grid.shape) > len(mask.shape):
             full = np.unravel_index(local, self.grid.shape)

@@ -162,8 +162,12 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
     fixed_cols = np.flatnonzero(~is_free)
 
     # device operator
+    st0 = _Stages(bool(args.get('time_stages')), timing.setdefault('stages', {}))
+    st0.mark('it:entry')
     G_csr = G_data._csr_device(col_N=n_cols, row_N=n_data)
+    st0.mark('it:G_csr(sort)')
     C_all = Gc._csr_device(col_N=n_cols, row_N=int(Gc.N_eq))
+    st0.mark('it:C_csr(sort)')
     multi = dist is not None and dist.world > 1
     replicate = multi and not os.environ.get('LSS_SHARDED_SOLVE')
     st = _Stages(bool(args.get('time_stages')), timing.setdefault('stages', {}))
@@ -177,7 +181,7 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         z_full, sigma_full = dist.gather_var_device(z, row_counts), dist.gather_var_device(sigma, row_counts)
         st.mark('it:csr')
         solver = NormalSolver(G_full, C_all, z_full, rhs_d[n_data:].contiguous(), sigma_full, E_all[n_data:].contiguous(),
-                              fixed_cols, None, structure=structure, G_local=G_csr)
+                              fixed_cols, None, structure=structure, G_local=G_csr, stages=st)
         del G_full
     else:
         # row-sharded solve: this rank's data rows + its share of the constraint rows, one all-reduce per CG iteration
@@ -186,10 +190,10 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         prior = rhs_d[n_data + c_lo:n_data + c_hi].contiguous()
         Ec = E_all[n_data + c_lo:n_data + c_hi].contiguous()
         st.mark('it:csr')
-        solver = NormalSolver(G_csr, C_loc, z, prior, sigma, Ec, fixed_cols, dist, structure=structure)
+        solver = NormalSolver(G_csr, C_loc, z, prior, sigma, Ec, fixed_cols, dist, structure=structure, stages=st)
     solver.set_profile(bool(args.get('profile_spmv')))
     stats = timing.setdefault('pcg', [])
-    st.mark('it:solver_setup(vstack+transpose)')
+    st.mark('it:solver_structure')
 
     if isinstance(in_TSE, torch.Tensor):
         in_TSE_d = _cabi.to_dev(in_TSE, torch.uint8).clone()
@@ -569,6 +573,7 @@ def smooth_fit(**kwargs):
     if verbose:
         print(f"smooth_fit: E_RMS={args['E_RMS']}")
     setup_smoothness_constraints(grids, constraint_op_list, args['E_RMS'], args['mask_scale'])
+    stages.mark('c:smoothness_ops')
     if args['bias_params'] is not None:
         n_bias = len(bias_model['bias_ID_dict'])
         col_0 = G_data.col_N
@@ -599,7 +604,9 @@ def smooth_fit(**kwargs):
         if op.prior is None:
             op.prior = np.zeros_like(op.expected)
 
+    stages.mark('c:bias_ops')
     Gc = lin_op(None, name='constraints').vstack(constraint_op_list)
+    stages.mark('c:vstack')
     Ec = np.zeros(Gc.N_eq)
     for op in constraint_op_list:
         Ec[Gc.TOC['rows'][op.name]] = op.expected
@@ -610,8 +617,9 @@ def smooth_fit(**kwargs):
     # TCinv and rhs stay on the device for the data rows (iterate_fit accepts tensors or NumPy)
     TCinv = DiagonalOp(torch.cat((1. / s_loc, _cabi.to_dev(1. / Ec, f64))))
     rhs = torch.cat((z_loc, _cabi.to_dev(np.concatenate([op.prior for op in constraint_op_list]), f64)))
+    stages.mark('c:Ec_rhs')
     Ip_c = build_reference_epoch_matrix(G_data, Gc, grids, args['reference_epoch'])
-    stages.mark('constraints')
+    stages.mark('c:Ip_c')
     timing['setup'] = time() - tic
 
     if tse_d is not None:

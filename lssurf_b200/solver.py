@@ -99,7 +99,7 @@ def grid_structure(grids, fixed_cols, bias_cols=None, max_block=64):
 
 
 class NormalSolver(object):
-    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None, G_local=None):
+    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None, G_local=None, stages=None):
         """G: DeviceCSR of this rank's data rows; Cn: DeviceCSR of this rank's constraint rows;
         z / sigma: data values and errors (CUDA fp64); prior / Ec: constraint right-hand side and sigma;
         fixed_cols: columns held at zero (reference epoch)."""
@@ -126,11 +126,15 @@ class NormalSolver(object):
             if self.all_ell:
                 # constraint stencils are short rows too (<= 9 entries): one ELL block [G; C], one kernel per product
                 self.A = DeviceCSR.vstack([G, Cn]) if self.n_con > 0 else G
+                if stages is not None:
+                    stages.mark('it:solver_vstack')
                 _cabi.check(L.lss_solver_create_blocks(
                     C.byref(self.handle), self.n_data + self.n_con, 0, self.n_cols, max(row_len, con_len, 1),
                     p(self.A.indptr), p(self.A.indices), p(self.A.data), nul, nul, nul, nul, nul, nul,
                     p(self.rhs), p(self.fixed), int(self.fixed.numel()), comm, _cabi.stream()))
                 self.A = None                      # the solver keeps its own ELL copy
+                if stages is not None:
+                    stages.mark('it:solver_create(ELL+symbolic N)')
             else:
                 self.Ct = Cn.transpose() if self.n_con > 0 else None
                 _cabi.check(L.lss_solver_create_blocks(
