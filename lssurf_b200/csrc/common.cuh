@@ -156,6 +156,30 @@ int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *ind
                        int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches,
                        double *dot_slots = nullptr);   // y pre-zeroed; dot_slots[256] += partial sums of x . (A x)
 
+// Products specialised for the explicit normal matrix (long overlapping rows); variant 0 is spmv_launch_atomic.
+int normal_product_variant();
+void set_normal_product_variant(int v);
+int spmv_launch_normal(int variant, int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x,
+                       double *y, int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches,
+                       double *dot_slots = nullptr);
+
+// variant 10: row-aligned tiles streamed through shared memory by TMA bulk copies (plan per row count)
+struct SpmvTmaPlan {
+    int64_t n_rows;
+    int n_tiles, cap;          // cap: entries a ring stage must hold
+    int *tile_row, *tile_k;    // [n_tiles + 1]
+    cudaStream_t stream;
+};
+int spmv_tma_plan_create(SpmvTmaPlan *plan, int64_t n_rows, const int32_t *indptr, int64_t nnz, cudaStream_t stream);
+void spmv_tma_plan_destroy(SpmvTmaPlan *plan);
+bool spmv_tma_fits(const SpmvTmaPlan *plan);
+int spmv_launch_tma(const SpmvTmaPlan *plan, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
+                    const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots = nullptr);
+
+// variants 7..9: product from the chunk-of-8 padded copy (U = 4, 6, 8 loads per lane)
+int spmv_launch_chunk8(int variant, int64_t n_chunks, const int32_t *chunk_row, const int32_t *cols, const double *vals, const double *x,
+                       double *y, const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots = nullptr);
+
 // Column-major fixed-row-length ("ELL") copy of the leading rows of a CSR matrix and its product (spmv.cu).
 int ell_build(int64_t n_rows, int K, const int32_t *indptr, const int32_t *indices, const double *data, int32_t *ell_col,
               double *ell_val, int64_t n_pad, cudaStream_t stream);
@@ -177,11 +201,19 @@ struct NormalMatrix {
     int32_t *indptr, *indices;
     double *data, *w_cur;
     unsigned long long *missing;
+    // chunk-of-8 padded copy for the CG product (built at the first fast product, values refreshed after every update)
+    int32_t *c8_ptr, *c8_row, *c8_cols;     // chunk start per row [n_cols + 1], row per chunk, padded columns [8 * n_chunks]
+    double *c8_vals;
+    int64_t n_chunks, c8_part_rows, c8_part_chunks, c8_part_nnz;
+    bool c8_dirty;
+    SpmvTmaPlan tma_plan;      // built at the first fast product for the row count it is asked for
+    int64_t tma_nnz;           // entries of the rows the plan covers
     SpmvPlan plan;
     SpmvPlan plan_part;        // plan of the leading rows [0, part_rows) (an eliminated trailing block is left out of the product)
     int64_t part_rows, part_nnz;
     cudaStream_t stream;
 };
+extern int g_opt_step_kernel;       // -1: unset (environment LSS_STEP_KERNEL decides, default 2), 0: warp per block, 1: thread per block row, 2: CTA tile
 extern int g_opt_explicit_normal;   // -1: unset (environment LSS_NO_EXPLICIT_N decides), 0 / 1: lss_set_option
 int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val,
                   int64_t n_cols, const unsigned char *fixed, cudaStream_t stream);

@@ -172,6 +172,68 @@ normal_diag_kernel(int64_t n_cols, const int *__restrict__ indptr, const int *__
 __global__ void sum_u32_kernel(const uint32_t *__restrict__ in, int64_t n, unsigned long long *__restrict__ out);
 static int sum_u32_to_u64(const uint32_t *in, int64_t n, unsigned long long *out, cudaStream_t st);
 
+// ---- chunk-of-8 padded copy of N for the CG product (spmv_chunk8_kernel) ----
+__global__ void __launch_bounds__(256)
+c8_count_kernel(int64_t n_cols, const int *__restrict__ indptr, uint32_t *__restrict__ n_chunks) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_cols; r += (int64_t)gridDim.x * blockDim.x)
+        n_chunks[r] = (uint32_t)((indptr[r + 1] - indptr[r] + 7) >> 3);
+}
+
+// one warp per row: row id of each of its chunks, padded columns (padding repeats the row's last column, value 0)
+__global__ void __launch_bounds__(256)
+c8_structure_kernel(int64_t n_cols, const int *__restrict__ indptr, const int *__restrict__ indices, const int *__restrict__ c8_ptr,
+                    int *__restrict__ c8_row, int *__restrict__ c8_cols) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_cols; r += n_warps) {
+        const int b = indptr[r], len = indptr[r + 1] - b;
+        const int cb = c8_ptr[r], nc = c8_ptr[r + 1] - cb;
+        for (int c = (int)lane_id(); c < nc; c += 32) c8_row[cb + c] = (int)r;
+        for (int k = (int)lane_id(); k < nc * 8; k += 32) c8_cols[(int64_t)cb * 8 + k] = indices[b + (k < len ? k : len - 1)];
+    }
+}
+
+// values of the padded copy: one thread per padded slot
+__global__ void __launch_bounds__(256)
+c8_values_kernel(int64_t n_slots, const int *__restrict__ indptr, const double *__restrict__ data, const int *__restrict__ c8_ptr,
+                 const int *__restrict__ c8_row, double *__restrict__ c8_vals) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += (int64_t)gridDim.x * blockDim.x) {
+        const int r = c8_row[s >> 3];
+        const int k = (int)(s - (int64_t)c8_ptr[r] * 8);
+        const int b = indptr[r], len = indptr[r + 1] - b;
+        c8_vals[s] = k < len ? data[b + k] : 0.0;
+    }
+}
+
+static int c8_build(NormalMatrix *m) {
+    cudaStream_t st = m->stream;
+    const int64_t n = m->n_cols;
+    Scratch cnt, tot;
+    LSS_CUDA(cnt.alloc(sizeof(uint32_t) * (n + 1), st));
+    LSS_CUDA(tot.alloc(sizeof(uint32_t), st));
+    c8_count_kernel<<<stride_grid(n, 256), 256, 0, st>>>(n, m->indptr, cnt.as<uint32_t>());
+    LSS_LAUNCH_CHECK();
+    LSS_CUDA(cudaMallocAsync((void **)&m->c8_ptr, sizeof(int) * (n + 1), st));
+    LSS_TRY(exclusive_scan_u32(cnt.as<uint32_t>(), reinterpret_cast<uint32_t *>(m->c8_ptr), n, tot.as<uint32_t>(), st));
+    uint32_t total = 0;
+    LSS_CUDA(cudaMemcpyAsync(&total, tot.p, sizeof(total), cudaMemcpyDeviceToHost, st));
+    LSS_CUDA(cudaStreamSynchronize(st));
+    if ((uint64_t)total * 8 >= (1ull << 31)) return fail(LSS_ERANGE, "normal matrix: padded copy exceeds 2^31 entries");
+    LSS_CUDA(cudaMemcpyAsync(m->c8_ptr + n, &total, sizeof(int), cudaMemcpyHostToDevice, st));
+    m->n_chunks = total;
+    const size_t nc = total > 0 ? total : 1;
+    LSS_CUDA(cudaMallocAsync((void **)&m->c8_row, sizeof(int) * nc, st));
+    LSS_CUDA(cudaMallocAsync((void **)&m->c8_cols, sizeof(int) * nc * 8, st));
+    LSS_CUDA(cudaMallocAsync((void **)&m->c8_vals, sizeof(double) * nc * 8, st));
+    if (total > 0) {
+        c8_structure_kernel<<<stride_grid(n * 32, 256, 16), 256, 0, st>>>(n, m->indptr, m->indices, m->c8_ptr, m->c8_row, m->c8_cols);
+        LSS_LAUNCH_CHECK();
+    }
+    LSS_CUDA(cudaStreamSynchronize(st));        // `total` (host stack) was the source of an async copy
+    m->c8_dirty = true;
+    m->c8_part_rows = -1;
+    return LSS_OK;
+}
+
 static int bits_for_cols(int64_t n_cols) {
     int b = 1;
     while (b < 31 && ((n_cols - 1) >> b)) ++b;
@@ -186,6 +248,11 @@ int normal_destroy(NormalMatrix *m) {
     if (m->data) cudaFreeAsync(m->data, st);
     if (m->w_cur) cudaFreeAsync(m->w_cur, st);
     if (m->missing) cudaFreeAsync(m->missing, st);
+    if (m->c8_ptr) cudaFreeAsync(m->c8_ptr, st);
+    if (m->c8_row) cudaFreeAsync(m->c8_row, st);
+    if (m->c8_cols) cudaFreeAsync(m->c8_cols, st);
+    if (m->c8_vals) cudaFreeAsync(m->c8_vals, st);
+    spmv_tma_plan_destroy(&m->tma_plan);
     spmv_plan_destroy(&m->plan);
     spmv_plan_destroy(&m->plan_part);
     delete m;
@@ -201,10 +268,12 @@ int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, cons
     m->n_rows = n_rows; m->n_pad = n_pad; m->K = K; m->n_cols = n_cols;
     m->ell_col = ell_col; m->ell_val = ell_val; m->fixed = fixed; m->stream = st;
     m->part_rows = -1;
+    m->c8_part_rows = -1;
+    m->c8_dirty = true;
     Scratch::configure_pool();
     int rc = LSS_OK;
     auto bail = [&](int code) { normal_destroy(m); return code; };
-    if (cudaMallocAsync((void **)&m->indptr, sizeof(int) * (n_cols + 1), st) != cudaSuccess ||
+    if (cudaMallocAsync((void **)&m->indptr, sizeof(int) * (n_cols + 1 + 8), st) != cudaSuccess ||
         cudaMallocAsync((void **)&m->w_cur, sizeof(double) * (n_rows > 0 ? n_rows : 1), st) != cudaSuccess ||
         cudaMallocAsync((void **)&m->missing, sizeof(unsigned long long), st) != cudaSuccess)
         return bail(fail(LSS_ECUDA, "normal matrix: cudaMallocAsync failed"));
@@ -258,8 +327,9 @@ int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, cons
             if (cudaStreamSynchronize(st) != cudaSuccess) return bail(fail(LSS_ECUDA, "normal matrix: symbolic phase failed: %s", cudaGetErrorString(cudaGetLastError())));
             if (n_unique >= (1u << 31)) return bail(fail(LSS_ERANGE, "normal matrix: more than 2^31 non-zeros"));
             m->nnz = n_unique;
-            if (cudaMallocAsync((void **)&m->indices, sizeof(int) * (size_t)n_unique, st) != cudaSuccess ||
-                cudaMallocAsync((void **)&m->data, sizeof(double) * (size_t)n_unique, st) != cudaSuccess)
+            // + 8: the TMA product reads whole 16-byte pieces, up to 3 entries past the end of a tile
+            if (cudaMallocAsync((void **)&m->indices, sizeof(int) * ((size_t)n_unique + 8), st) != cudaSuccess ||
+                cudaMallocAsync((void **)&m->data, sizeof(double) * ((size_t)n_unique + 8), st) != cudaSuccess)
                 return bail(fail(LSS_ECUDA, "normal matrix: cudaMallocAsync failed"));
             cudaMemsetAsync(m->data, 0, sizeof(double) * (size_t)n_unique, st);
             normal_pattern_kernel<<<stride_grid(np, 256, 16), 256, 0, st>>>(ks, np, fl, cbits, n_cols, m->indptr, m->indices, tot.as<uint32_t>() + 1);
@@ -279,6 +349,7 @@ int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, cons
 
 int normal_update(NormalMatrix *m, const double *w) {
     if (m->n_rows <= 0 || m->nnz == 0) return LSS_OK;
+    m->c8_dirty = true;
     const int64_t n_chunks = (m->n_rows + 31) / 32;
     int64_t need = (n_chunks + NU_WARPS - 1) / NU_WARPS;
     const int64_t cap = (int64_t)kSMs * 16;
@@ -304,8 +375,48 @@ int normal_apply_fast(NormalMatrix *m, int64_t n_rows, const double *x, double *
     if (m->plan.n_tiles > 0 && m->plan.tile != 1024)
         return fail(LSS_EINVAL, "normal matrix product: the single-launch kernel needs the default spmv_variant (1024-entry tiles)");
     if (!y_is_zero) LSS_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * m->n_cols, m->stream));
+    int variant = normal_product_variant();
+    if (variant == 10 && m->nnz > 0) {
+        const int64_t rows = n_rows < m->n_cols ? n_rows : m->n_cols;
+        if (!m->tma_plan.tile_row || m->tma_plan.n_rows != rows) {
+            spmv_tma_plan_destroy(&m->tma_plan);
+            int nz = 0;
+            LSS_CUDA(cudaMemcpyAsync(&nz, m->indptr + rows, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+            LSS_CUDA(cudaStreamSynchronize(m->stream));
+            m->tma_nnz = nz;
+            LSS_TRY(spmv_tma_plan_create(&m->tma_plan, rows, m->indptr, nz, m->stream));
+        }
+        if (spmv_tma_fits(&m->tma_plan))
+            return spmv_launch_tma(&m->tma_plan, m->indptr, m->indices, m->data, x, y, stop, m->stream, launches, dot_slots);
+        variant = 0;                     // rows too long for a ring stage (e.g. bias rows that were not eliminated)
+    }
+    if (variant >= 7 && m->nnz > 0) {
+        if (!m->c8_ptr) LSS_TRY(c8_build(m));
+        if (m->c8_dirty) {
+            const int64_t n_slots = m->n_chunks * 8;
+            if (n_slots > 0) {
+                c8_values_kernel<<<stride_grid(n_slots, 256, 16), 256, 0, m->stream>>>(n_slots, m->indptr, m->data, m->c8_ptr, m->c8_row, m->c8_vals);
+                LSS_LAUNCH_CHECK();
+            }
+            m->c8_dirty = false;
+        }
+        int64_t chunks = m->n_chunks;
+        if (n_rows < m->n_cols) {
+            if (m->c8_part_rows != n_rows) {
+                int pc = 0, nz = 0;
+                LSS_CUDA(cudaMemcpyAsync(&pc, m->c8_ptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+                LSS_CUDA(cudaMemcpyAsync(&nz, m->indptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+                LSS_CUDA(cudaStreamSynchronize(m->stream));
+                m->c8_part_chunks = pc;
+                m->c8_part_nnz = nz;
+                m->c8_part_rows = n_rows;
+            }
+            chunks = m->c8_part_chunks;
+        }
+        return spmv_launch_chunk8(variant, chunks, m->c8_row, m->c8_cols, m->c8_vals, x, y, stop, m->stream, launches, dot_slots);
+    }
     if (n_rows >= m->n_cols)
-        return spmv_launch_atomic(m->n_cols, m->indptr, m->indices, m->data, x, y, m->nnz, &m->plan, stop, m->stream, launches, dot_slots);
+        return spmv_launch_normal(variant, m->n_cols, m->indptr, m->indices, m->data, x, y, m->nnz, &m->plan, stop, m->stream, launches, dot_slots);
     if (m->part_rows != n_rows) {          // first use with this row count: plan of the leading block
         spmv_plan_destroy(&m->plan_part);
         int nz = 0;
@@ -315,7 +426,8 @@ int normal_apply_fast(NormalMatrix *m, int64_t n_rows, const double *x, double *
         LSS_TRY(spmv_plan_create(&m->plan_part, n_rows, m->indptr, nz, m->stream));
         m->part_rows = n_rows;
     }
-    return spmv_launch_atomic(n_rows, m->indptr, m->indices, m->data, x, y, m->part_nnz, &m->plan_part, stop, m->stream, launches, dot_slots);
+    return spmv_launch_normal(variant, n_rows, m->indptr, m->indices, m->data, x, y, m->part_nnz, &m->plan_part, stop, m->stream, launches,
+                              dot_slots);
 }
 
 __global__ void __launch_bounds__(256)

@@ -473,6 +473,227 @@ cg_step_p_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slot
     }
 }
 
+// The same CG vector step with ONE THREAD PER BLOCK ROW instead of a warp per block (the default; LSS_STEP_KERNEL=0 or
+// lss_set_option("step_kernel", 0) selects the kernel above).  Thread (b, l) forms z_l = sum_j inv_b[j][l] r'_j with
+// r'_j = r_j - alpha q_j recomputed from the old residual: the 36 loads of a column of the (symmetric) inverse are
+// independent and coalesced across l, the member / residual loads are warp-uniform broadcasts, and nothing is exchanged
+// between threads -- no shuffles, no shared-memory staging, every thread of every resident warp has bs loads in flight.
+// The updated residual goes to a second buffer (r_in / r_out swap with the parity) so that no thread reads an entry a
+// neighbour has already overwritten; q is cleared after the grid barrier for the same reason.
+constexpr int STEP2_PER_SM = 4;
+__global__ void __launch_bounds__(VEC_BLOCK, STEP2_PER_SM)
+cg_step_rows_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots, const double *__restrict__ minv, double *__restrict__ p,
+                    double *__restrict__ x, const double *__restrict__ r_in, double *__restrict__ r_out, double *__restrict__ z,
+                    double *__restrict__ part, double *__restrict__ scal, int parity, int n_blocks, int bs, const int *__restrict__ bcols,
+                    const int *__restrict__ col_block, const float *__restrict__ binv) {
+    __shared__ double sm[VEC_BLOCK / 32];
+    if (scal[S_DONE0 + parity] != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
+        return;
+    }
+    const int64_t tid = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x, nth = (int64_t)gridDim.x * VEC_BLOCK;
+    static_assert(PQ_SLOTS == VEC_BLOCK, "one p.q slot per thread");
+    const double slot_v = pq_slots[threadIdx.x];              // in flight while the first block row is accumulated
+    const double rz_old = scal[S_RZ0 + parity];
+    const int total = n_blocks * bs;
+    // z_l = sum_j S_jl (r_j - alpha q_j) = zr - alpha zq: nothing below depends on alpha until the row is finished, so the
+    // loads of the first row (the bulk of this kernel's traffic) are issued before the p.q reduction has been waited for
+    auto accumulate = [&](int t, double &zr, double &zq) -> int {
+        const int b = t / bs, l = t - b * bs;
+        const int *bc = bcols + (size_t)b * bs;
+        const int c = __ldg(bc + l);
+        zr = 0.0;
+        zq = 0.0;
+        if (c < 0) return c;                                  // padding row of a short block
+        const float *S = binv + (size_t)b * bs * bs + l;      // column l == row l of the symmetric inverse
+#pragma unroll 6
+        for (int j = 0; j < bs; ++j) {
+            const int cj = __ldg(bc + j);
+            const double sj = (double)__ldg(S + j * bs);
+            if (cj >= 0) {
+                zr += sj * r_in[cj];
+                zq += sj * q[cj];
+            }
+        }
+        return c;
+    };
+    int t = (int)tid;
+    double zr0 = 0.0, zq0 = 0.0;
+    const int c_first = t < total ? accumulate(t, zr0, zq0) : -1;
+    double pq = block_sum(slot_v, sm);
+    if (threadIdx.x == 0) sm[0] = pq;
+    __syncthreads();
+    pq = sm[0];
+    __syncthreads();
+    const double alpha = pq > 0.0 ? rz_old / pq : 0.0;
+    double v = 0.0;
+    auto finish = [&](int c, double zr, double zq) {
+        const double zl = zr - alpha * zq;
+        const double rl = r_in[c] - alpha * q[c];
+        x[c] += alpha * p[c];
+        r_out[c] = rl;
+        z[c] = zl;
+        v += rl * zl;
+    };
+    if (c_first >= 0) finish(c_first, zr0, zq0);
+    for (t += (int)nth; t < total; t += (int)nth) {
+        double zr, zq;
+        const int c = accumulate(t, zr, zq);
+        if (c >= 0) finish(c, zr, zq);
+    }
+    for (int64_t i = tid; i < n; i += nth) {
+        if (col_block && col_block[i] >= 0) continue;
+        x[i] += alpha * p[i];
+        const double ri = r_in[i] - alpha * q[i];
+        r_out[i] = ri;
+        const double zi = minv[i] * ri;
+        z[i] = zi;
+        v += ri * zi;
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    cgx::this_grid().sync();
+    const double rz_new = sum_partials(part, (int)gridDim.x, sm);
+    const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
+    for (int64_t i = tid; i < n; i += nth) {
+        p[i] = z[i] + beta * p[i];
+        q[i] = 0.0;
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;     // every block read them before the barrier
+        if (threadIdx.x == 0) {
+            scal[S_RZ0 + (parity ^ 1)] = rz_new;
+            scal[S_RZ_LAST] = rz_new;
+            const double it = scal[S_ITERS] + 1.0;
+            scal[S_ITERS] = it;
+            scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+        }
+    }
+}
+
+// Third form of the same step (the default when the block stride is one of the instantiated sizes; step_kernel = 2):
+// a CTA takes 256 / BS whole blocks at a time.  Every thread first issues the BS loads of its column of the inverse
+// (addresses known from the thread index alone, coalesced, all in flight at once), then gathers r, q of its own
+// member into shared memory; after one barrier the products run from registers and shared-memory broadcasts.  The
+// thread-per-row kernel above needs the member list before it can gather (two dependent levels, six times per row).
+constexpr int STEP3_PER_SM = 3;
+template <int BS>
+__global__ void __launch_bounds__(VEC_BLOCK, STEP3_PER_SM)
+cg_step_tile_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots, const double *__restrict__ minv, double *__restrict__ p,
+                    double *__restrict__ x, const double *__restrict__ r_in, double *__restrict__ r_out, double *__restrict__ z,
+                    double *__restrict__ part, double *__restrict__ scal, int parity, int n_blocks, const int *__restrict__ bcols,
+                    const int *__restrict__ col_block, const float *__restrict__ binv) {
+    constexpr int NBLK = VEC_BLOCK / BS, ROWS = NBLK * BS;
+    __shared__ double sm[VEC_BLOCK / 32];
+    __shared__ double rs[ROWS], qs[ROWS];
+    if (scal[S_DONE0 + parity] != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
+        return;
+    }
+    const int64_t tid = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x, nth = (int64_t)gridDim.x * VEC_BLOCK;
+    static_assert(PQ_SLOTS == VEC_BLOCK, "one p.q slot per thread");
+    const double slot_v = pq_slots[threadIdx.x];
+    const double rz_old = scal[S_RZ0 + parity];
+    const int n_groups = (n_blocks + NBLK - 1) / NBLK;
+    const int bl = threadIdx.x / BS, l = threadIdx.x - bl * BS;       // block inside the group, member inside the block
+    double alpha = 0.0, v = 0.0;
+    bool have_alpha = false;
+    auto get_alpha = [&]() {                                            // all threads of the CTA call this together
+        double pq = block_sum(slot_v, sm);
+        if (threadIdx.x == 0) sm[0] = pq;
+        __syncthreads();
+        pq = sm[0];
+        __syncthreads();
+        alpha = pq > 0.0 ? rz_old / pq : 0.0;
+        have_alpha = true;
+    };
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int b = g * NBLK + bl;
+        const bool active = threadIdx.x < ROWS && b < n_blocks;
+        float sv[BS];
+        int c = -1;
+        if (active) {
+            const float *S = binv + (size_t)b * BS * BS + l;              // column l == row l of the symmetric inverse
+#pragma unroll
+            for (int j = 0; j < BS; ++j) sv[j] = __ldg(S + j * BS);
+            c = __ldg(bcols + (size_t)b * BS + l);
+        } else {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) sv[j] = 0.f;
+        }
+        double r_own = 0.0, q_own = 0.0, p_own = 0.0, x_own = 0.0;
+        if (c >= 0) {
+            r_own = r_in[c];
+            q_own = q[c];
+            p_own = p[c];
+            x_own = x[c];
+        }
+        if (threadIdx.x < ROWS) {
+            rs[threadIdx.x] = r_own;
+            qs[threadIdx.x] = q_own;
+        }
+        __syncthreads();
+        double zr = 0.0, zq = 0.0;
+        const double *rb = rs + bl * BS, *qb = qs + bl * BS;
+        if (threadIdx.x < ROWS) {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+                const double sj = (double)sv[j];
+                zr += sj * rb[j];
+                zq += sj * qb[j];
+            }
+        }
+        if (!have_alpha) get_alpha();                                       // contains barriers: rs / qs are free afterwards
+        else __syncthreads();
+        if (c >= 0) {
+            const double zl = zr - alpha * zq;
+            const double rl = r_own - alpha * q_own;
+            x[c] = x_own + alpha * p_own;
+            r_out[c] = rl;
+            z[c] = zl;
+            v += rl * zl;
+        }
+    }
+    if (!have_alpha) get_alpha();
+    for (int64_t i = tid; i < n; i += nth) {
+        if (col_block && col_block[i] >= 0) continue;
+        x[i] += alpha * p[i];
+        const double ri = r_in[i] - alpha * q[i];
+        r_out[i] = ri;
+        const double zi = minv[i] * ri;
+        z[i] = zi;
+        v += ri * zi;
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    cgx::this_grid().sync();
+    const double rz_new = sum_partials(part, (int)gridDim.x, sm);
+    const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
+    for (int64_t i = tid; i < n; i += nth) {
+        p[i] = z[i] + beta * p[i];
+        q[i] = 0.0;
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;     // every block read them before the barrier
+        if (threadIdx.x == 0) {
+            scal[S_RZ0 + (parity ^ 1)] = rz_new;
+            scal[S_RZ_LAST] = rz_new;
+            const double it = scal[S_ITERS] + 1.0;
+            scal[S_ITERS] = it;
+            scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+        }
+    }
+}
+
+static const void *step_tile_kernel_for(int bs) {
+    switch (bs) {
+        case 12: return (const void *)cg_step_tile_kernel<12>;
+        case 24: return (const void *)cg_step_tile_kernel<24>;
+        case 36: return (const void *)cg_step_tile_kernel<36>;
+        default: return nullptr;
+    }
+}
+
 __global__ void __launch_bounds__(VEC_BLOCK)
 mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) out[i] = a[i] * b[i];
@@ -548,6 +769,8 @@ struct lss_solver {
     lss::BlockPrecond *bp;
     int64_t e0, e1;          // eliminated columns [e0, e1); e0 == e1: none
     double *einv, *z, *eraw;   // eraw: rank-local N_Eg v sums (multi-rank only)
+    double *r2;              // second residual buffer of the thread-per-row step kernel (swapped with r by parity)
+    int step_rows;           // 2: cg_step_tile_kernel, 1: cg_step_rows_kernel, 0: cg_step_p_kernel
     int step_grid;           // CTAs of the cooperative step kernel
     int step_stages;         // shared-memory stages per warp for the block inverses
     size_t step_smem;
@@ -584,6 +807,7 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     if (s->einv) cudaFreeAsync(s->einv, s->stream);
     if (s->eraw) cudaFreeAsync(s->eraw, s->stream);
     if (s->z) cudaFreeAsync(s->z, s->stream);
+    if (s->r2) cudaFreeAsync(s->r2, s->stream);
     if (s->nm) lss::normal_destroy(s->nm);
     if (s->ell_col) cudaFreeAsync(s->ell_col, s->stream);
     if (s->ell_val) cudaFreeAsync(s->ell_val, s->stream);
@@ -755,9 +979,29 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
         if (s->step_smem > 48 * 1024)
             LSS_CUDA(cudaFuncSetAttribute(cg_step_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->step_smem));
         int per_sm = 0;
-        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_step_p_kernel, VEC_BLOCK, s->step_smem));
-        if (per_sm < 1) return fail(LSS_EINVAL, "solver_set_structure: %zu bytes of staging memory per CTA do not fit", s->step_smem);
-        if (per_sm > STEP_PER_SM) per_sm = STEP_PER_SM;
+        int want_rows = lss::g_opt_step_kernel;
+        if (want_rows < 0) {
+            const char *e = getenv("LSS_STEP_KERNEL");
+            want_rows = e ? atoi(e) : 2;
+        }
+        if (want_rows < 0 || want_rows > 2) want_rows = 2;
+        if (want_rows == 2 && (!s->bp || !step_tile_kernel_for(s->bp->bs))) want_rows = 1;      // block stride without an instance
+        s->step_rows = want_rows;
+        if (s->step_rows == 2) {
+            if (!s->r2) LSS_TRY(dev_alloc(&s->r2, s->n_cols, st));
+            LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_tile_kernel_for(s->bp->bs), VEC_BLOCK, 0));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > STEP3_PER_SM) per_sm = STEP3_PER_SM;
+        } else if (s->step_rows) {
+            if (!s->r2) LSS_TRY(dev_alloc(&s->r2, s->n_cols, st));
+            LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_step_rows_kernel, VEC_BLOCK, 0));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > STEP2_PER_SM) per_sm = STEP2_PER_SM;
+        } else {
+            LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_step_p_kernel, VEC_BLOCK, s->step_smem));
+            if (per_sm < 1) return fail(LSS_EINVAL, "solver_set_structure: %zu bytes of staging memory per CTA do not fit", s->step_smem);
+            if (per_sm > STEP_PER_SM) per_sm = STEP_PER_SM;
+        }
         s->step_grid = kSMs * per_sm;
     }
     s->have_weights = false;
@@ -986,8 +1230,20 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
                 const float *binv = s->bp ? s->bp->inv : nullptr;
                 double *slots = s->buf + n;
                 int n_stage = s->step_stages;
-                void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &rv, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv, &n_stage};
-                LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_p_kernel, dim3(s->step_grid), dim3(VEC_BLOCK), args, s->step_smem, st));
+                if (s->step_rows == 2) {
+                    const double *r_in = parity ? s->r2 : s->r;
+                    double *r_out = parity ? s->r : s->r2;
+                    void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &r_in, &r_out, &zv, &part, &scal, &par, &nb, &bcols, &cblk, &binv};
+                    LSS_CUDA(cudaLaunchCooperativeKernel(step_tile_kernel_for(bs), dim3(s->step_grid), dim3(VEC_BLOCK), args, 0, st));
+                } else if (s->step_rows) {
+                    const double *r_in = parity ? s->r2 : s->r;
+                    double *r_out = parity ? s->r : s->r2;
+                    void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &r_in, &r_out, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv};
+                    LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_rows_kernel, dim3(s->step_grid), dim3(VEC_BLOCK), args, 0, st));
+                } else {
+                    void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &rv, &zv, &part, &scal, &par, &nb, &bs, &bcols, &cblk, &binv, &n_stage};
+                    LSS_CUDA(cudaLaunchCooperativeKernel((void *)cg_step_p_kernel, dim3(s->step_grid), dim3(VEC_BLOCK), args, s->step_smem, st));
+                }
                 ++lss::g_launches;
                 s->launches += 1;
                 s->q_clean = true;
@@ -1072,7 +1328,14 @@ extern "C" int lss_solver_info(lss_solver_t *s, int64_t *info_h) {
     info_h[5] = s->e1 - s->e0;
     info_h[6] = 0;
     // non-zeros the CG product streams per application (the rows of an eliminated trailing block are left out)
-    info_h[7] = s->nm ? ((s->e1 > s->e0 && s->e1 == s->n_cols && s->nm->part_rows == s->e0) ? s->nm->part_nnz : s->nm->nnz) : 0;
+    info_h[7] = 0;
+    if (s->nm) {
+        const bool part = s->e1 > s->e0 && s->e1 == s->n_cols;
+        if (part && lss::normal_product_variant() == 10 && s->nm->tma_plan.tile_row && s->nm->tma_plan.n_rows == s->e0) info_h[7] = s->nm->tma_nnz;
+        else if (part && s->nm->c8_part_rows == s->e0 && lss::normal_product_variant() >= 7) info_h[7] = s->nm->c8_part_nnz;
+        else if (part && s->nm->part_rows == s->e0) info_h[7] = s->nm->part_nnz;
+        else info_h[7] = s->nm->nnz;
+    }
     if (s->bp) {
         unsigned int nb = 0;
         cudaMemcpyAsync(&nb, s->bp->n_bad, sizeof(nb), cudaMemcpyDeviceToHost, s->stream);

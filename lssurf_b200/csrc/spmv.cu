@@ -351,6 +351,552 @@ int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *ind
     return LSS_OK;
 }
 
+// ============================================================================ products for the explicit normal matrix
+// The explicit normal matrix has long, uneven rows (mean 80, 0..277 entries for the 10^7-point workload) whose column
+// sets overlap heavily between neighbouring rows (neighbouring grid nodes).  The generic nnz-tiled kernel above spends
+// its L1 wavefronts on staging products through shared memory and on gathers of 32 consecutive non-zeros of ONE row
+// (ncu: l1tex 71-77 %, DRAM 50-60 %).  Two kernels specialised for this shape, selected by lss_set_option
+// ("normal_product") / LSS_N_PRODUCT:
+//
+//   rows    G lanes per row, everything in registers: each lane loads up to U (column, value) pairs of its row with
+//           streaming loads, gathers x, folds with G-wide shuffles and stores y[row] -- no shared memory, no atomics,
+//           no dependence on y's previous contents.
+//   stream  persistent CTAs; the matrix stream (values + column indices of one 1024-entry tile) is copied into a
+//           STAGES-deep shared-memory ring with cp.async (L2 evict-first), so the bytes in flight live in shared
+//           memory instead of registers (STAGES x 12 KB per CTA, several CTAs per SM); rows are then reduced straight
+//           from the ring by groups of g lanes which issue the gathers themselves (neighbouring rows side by side in
+//           a warp: their gathers hit the same lines).  Rows cut by a tile boundary are completed with RED atomics,
+//           so y must hold zeros there (same contract as spmv_launch_atomic).
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int src_bytes, uint64_t pol) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(sa), "l"(gmem), "r"(src_bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int G, int U>
+__global__ void __launch_bounds__(256)
+spmv_rows_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ data,
+                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ stop, double *__restrict__ dot_slots) {
+    if (stop && *stop != 0.0) return;
+    const uint64_t once = l2_policy_evict_first();
+    const int gl = threadIdx.x & (G - 1);
+    const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+    int b = 0, e = 0;
+    if (row < n_rows) {
+        b = __ldg(indptr + row);
+        e = __ldg(indptr + row + 1);
+    }
+    double acc = 0.0;
+    for (int k0 = b; k0 < e; k0 += G * U) {
+        int col[U];
+        double val[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int k = k0 + j * G + gl;
+            const bool in = k < e;
+            col[j] = in ? ldg_stream(indices + k, once) : -1;
+            val[j] = in ? ldg_stream(data + k, once) : 0.0;
+        }
+        double xg[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) xg[j] = col[j] >= 0 ? __ldg(x + col[j]) : 0.0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) acc += val[j] * xg[j];
+    }
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    double dot = 0.0;
+    if (row < n_rows && gl == 0) {
+        y[row] = acc;
+        if (dot_slots) dot = acc * __ldg(x + row);
+    }
+    if (dot_slots) {
+        dot = warp_sum(dot);
+        if (lane_id() == 0 && dot != 0.0) atomicAdd(dot_slots + ((blockIdx.x * 8u + (threadIdx.x >> 5)) & 255u), dot);
+    }
+}
+
+template <int BLOCK, int TILE, int STAGES>
+__global__ void __launch_bounds__(BLOCK)
+spmv_stream_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__restrict__ indptr, const int *__restrict__ indices,
+                   const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
+                   const int *__restrict__ tile_bounds, const double *__restrict__ stop, double *__restrict__ dot_slots) {
+    extern __shared__ __align__(16) unsigned char ring[];          // stage s: [TILE doubles][TILE ints]
+    constexpr int STAGE_BYTES = TILE * 12;
+    if (stop && *stop != 0.0) return;
+    const uint64_t once = l2_policy_evict_first();
+    auto issue = [&](int tile, int stage) {
+        if (tile < n_tiles) {
+            const int64_t k0 = (int64_t)tile * TILE;
+            double *sval = reinterpret_cast<double *>(ring + (size_t)stage * STAGE_BYTES);
+            int *scol = reinterpret_cast<int *>(ring + (size_t)stage * STAGE_BYTES + TILE * 8);
+            for (int c = threadIdx.x; c < TILE / 2; c += BLOCK) {          // 16 bytes = 2 values
+                const int64_t k = k0 + 2 * c;
+                const int64_t left = nnz - k;
+                const int nb = left >= 2 ? 16 : (left > 0 ? 8 : 0);
+                cp_async16_zfill(sval + 2 * c, nb ? (const void *)(data + k) : (const void *)data, nb, once);
+            }
+            for (int c = threadIdx.x; c < TILE / 4; c += BLOCK) {          // 16 bytes = 4 column indices
+                const int64_t k = k0 + 4 * c;
+                const int64_t left = nnz - k;
+                const int nb = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
+                cp_async16_zfill(scol + 4 * c, nb ? (const void *)(indices + k) : (const void *)indices, nb, once);
+            }
+        }
+        cp_async_commit_group();                                           // one group per call, empty or not
+    };
+    int t = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(t + s * (int)gridDim.x, s);
+    double dot = 0.0;
+    for (int i = 0; t < n_tiles; ++i, t += gridDim.x) {
+        issue(t + (STAGES - 1) * (int)gridDim.x, (i + STAGES - 1) % STAGES);   // the stage tile i - 1 was reduced from
+        cp_async_wait_group<STAGES - 1>();                                 // this thread's copies of tile i have landed
+        __syncthreads();                                                   // ... and everybody else's
+        const int stage = i % STAGES;
+        const double *sval = reinterpret_cast<const double *>(ring + (size_t)stage * STAGE_BYTES);
+        const int *scol = reinterpret_cast<const int *>(ring + (size_t)stage * STAGE_BYTES + TILE * 8);
+        const int64_t k0 = (int64_t)t * TILE;
+        const int64_t k1 = (k0 + TILE < nnz) ? k0 + TILE : nnz;
+        const int64_t r_lo = tile_bounds[2 * t], r_hi = tile_bounds[2 * t + 1];
+        const bool has_carry = (int64_t)indptr[r_lo] < k0;                 // r_lo started in an earlier tile
+        const int64_t first = r_lo + (has_carry ? 1 : 0);
+        const int64_t n_virtual = (r_hi - first) + 1;                      // virtual row 0 is the carry-in
+        int g = 1;
+        while (g < 32 && n_virtual * (2 * g) <= BLOCK) g <<= 1;
+        const int gl = threadIdx.x & (g - 1), rows_per_pass = BLOCK / g;
+        for (int64_t base = 0; base < n_virtual; base += rows_per_pass) {
+            const int64_t v = base + threadIdx.x / g;
+            const bool valid = v < n_virtual && !(v == 0 && !has_carry);
+            int64_t b = 0, e = 0;
+            const int64_t rr = v == 0 ? r_lo : first + v - 1;
+            if (valid) {
+                b = v == 0 ? k0 : (int64_t)indptr[rr];
+                e = indptr[rr + 1];
+            }
+            const bool open = e > k1;                                      // continues in the next tile
+            if (open) e = k1;
+            const double xr = (dot_slots && valid && gl == 0) ? __ldg(x + rr) : 0.0;
+            int k = (int)(b - k0) + gl;
+            const int kend = (int)(e - k0);
+            double a0 = 0.0, a1 = 0.0;
+            for (; k + 3 * g < kend; k += 4 * g) {
+                const int c0 = scol[k], c1 = scol[k + g], c2 = scol[k + 2 * g], c3 = scol[k + 3 * g];
+                const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+                a0 += sval[k] * x0;
+                a1 += sval[k + g] * x1;
+                a0 += sval[k + 2 * g] * x2;
+                a1 += sval[k + 3 * g] * x3;
+            }
+            for (; k < kend; k += g) a0 += sval[k] * __ldg(x + scol[k]);
+            double acc = a0 + a1;
+            for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (valid && gl == 0) {
+                if (v == 0 || open) atomicAdd(y + rr, acc);
+                else y[rr] = acc;
+                dot += acc * xr;
+            }
+        }
+        __syncthreads();                                                   // the stage is free for the copy issued next
+    }
+    cp_async_wait_group<0>();
+    if (dot_slots) {
+        dot = warp_sum(dot);
+        if (lane_id() == 0 && dot != 0.0) atomicAdd(dot_slots + ((blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5)) & 255u), dot);
+    }
+}
+
+//   chunk8  the product the solver uses by default.  The two kernels above (and the nnz-tiled one) start every row or
+//           tile with a chain of dependent loads (tile bounds -> row pointers -> matrix stream -> gather), so their
+//           bytes in flight are only outstanding for about half of the time (measured: 0.55-0.61 of the HBM peak for
+//           all of them, whatever the register / shared-memory budget).  Here the row structure is taken out of the
+//           address computation altogether: a padded copy of N keeps every row in chunks of 8 entries (zero padding,
+//           +4 %; one row id per chunk), so the address of every matrix load depends on the thread index only.  A warp
+//           owns 4U consecutive chunks: U perfectly coalesced loads of 32 (column, value) pairs per lane are issued
+//           back to back, then the gathers, then 8-lane sums; chunks of the same row inside one load are merged with
+//           two more shuffles and the sum is added to y[row] with one RED (y must hold zeros).
+template <int U>
+__global__ void __launch_bounds__(256)
+spmv_chunk8_kernel(int64_t n_chunks, const int *__restrict__ chunk_row, const int *__restrict__ cols, const double *__restrict__ vals,
+                   const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ stop, double *__restrict__ dot_slots) {
+    static_assert(4 * U <= 32, "one lane per chunk row id");
+    const unsigned lane = lane_id();
+    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t c0 = warp * (4 * U);
+    if (c0 >= n_chunks) return;
+    const uint64_t once = l2_policy_evict_first();
+    int col[U];
+    double val[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t c = c0 + 4 * u + (lane >> 3);
+        const int64_t s = (c0 + 4 * u) * 8 + lane;
+        const bool in = c < n_chunks;
+        col[u] = in ? ldg_stream(cols + s, once) : -1;
+        val[u] = in ? ldg_stream(vals + s, once) : 0.0;
+    }
+    const int my_row = ((int)lane < 4 * U && c0 + lane < n_chunks) ? __ldg(chunk_row + c0 + lane) : -1;
+    const double stop_v = stop ? *reinterpret_cast<const volatile double *>(stop) : 0.0;
+    const double my_xr = (dot_slots && my_row >= 0) ? __ldg(x + my_row) : 0.0;       // x[row] for the x . (A x) by-product
+    // ptxas is free to sink the (read-only) value loads below the gathers, where they would sit behind the wait for the
+    // column loads: make the gather base depend on every value (a NaN pattern no matrix entry holds), so all 2U matrix
+    // loads are issued before the first wait
+    int dep = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) dep |= (__double2hiint(val[u]) == (int)0xffffffffu) ? 1 : 0;
+    const double *xd = x + dep;
+    double xg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) xg[u] = col[u] >= 0 ? __ldg(xd + col[u]) : 0.0;
+    if (stop_v != 0.0) return;
+    double dot = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        double p = val[u] * xg[u];
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        p += __shfl_xor_sync(0xffffffffu, p, 4);
+        const int r = __shfl_sync(0xffffffffu, my_row, 4 * u + (int)(lane >> 3));
+        const double xr = __shfl_sync(0xffffffffu, my_xr, 4 * u + (int)(lane >> 3));
+        // chunk rows are non-decreasing: merge the sums of equal rows (groups 0|1, 2|3, then 0|2)
+        double o = __shfl_xor_sync(0xffffffffu, p, 8);
+        int ro = __shfl_xor_sync(0xffffffffu, r, 8);
+        int dead = 0;
+        if (ro == r) {
+            if (lane & 8u) dead = 1; else p += o;
+        }
+        o = __shfl_xor_sync(0xffffffffu, p, 16);
+        ro = __shfl_xor_sync(0xffffffffu, r, 16);
+        const int odead = __shfl_xor_sync(0xffffffffu, dead, 16);
+        if (ro == r && !dead && !odead) {
+            if (lane & 16u) dead = 1; else p += o;
+        }
+        if (!dead && (lane & 7u) == 0u && r >= 0) {
+            atomicAdd(y + r, p);
+            dot += p * xr;
+        }
+    }
+    if (dot_slots) {
+        dot = warp_sum(dot);
+        if (lane == 0 && dot != 0.0) atomicAdd(dot_slots + ((unsigned)warp & 255u), dot);
+    }
+}
+
+int spmv_launch_chunk8(int variant, int64_t n_chunks, const int32_t *chunk_row, const int32_t *cols, const double *vals, const double *x,
+                       double *y, const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots) {
+    if (n_chunks <= 0) return LSS_OK;
+    if (variant == 7) {
+        spmv_chunk8_kernel<4><<<ceil_div(ceil_div(n_chunks, 16), 8), 256, 0, stream>>>(n_chunks, chunk_row, cols, vals, x, y, stop, dot_slots);
+    } else if (variant == 9) {
+        spmv_chunk8_kernel<8><<<ceil_div(ceil_div(n_chunks, 32), 8), 256, 0, stream>>>(n_chunks, chunk_row, cols, vals, x, y, stop, dot_slots);
+    } else {
+        spmv_chunk8_kernel<6><<<ceil_div(ceil_div(n_chunks, 24), 8), 256, 0, stream>>>(n_chunks, chunk_row, cols, vals, x, y, stop, dot_slots);
+    }
+    LSS_LAUNCH_CHECK();
+    if (launches) *launches += 1;
+    return LSS_OK;
+}
+
+//   tma     row-aligned tiles streamed by the TMA engine.  Tile t holds the rows whose first entry lies in
+//           [1024 t, 1024 (t + 1)), so no row is cut (plain stores: y needs no clearing, no atomics, deterministic) and
+//           a tile's values, column indices and row pointers are three contiguous byte ranges.  One thread per CTA
+//           issues them as 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a STAGES-deep shared-memory
+//           ring, several tiles ahead: the stream costs no registers and no LSU wavefronts, and the descriptors of
+//           the tile after next are prefetched so that no load address waits on another load.  Consumers wait on the
+//           stage's mbarrier and reduce rows straight from shared memory with g lanes per row (neighbouring rows side
+//           by side in a warp: their gathers share lines), one shuffle fold per row.
+constexpr int TMA_TILE = 1024, TMA_RP_CAP = 132, TMA_HEAD = 512;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+// tile_row[t] = first row whose entries start at or after 1024 t (tile_row[n_tiles] = n_rows), tile_k[t] = indptr[tile_row[t]];
+// *max_span = largest number of entries a stage must hold (from the 4-aligned start of the tile)
+__global__ void __launch_bounds__(256)
+spmv_tma_plan_kernel(int64_t n_rows, const int *__restrict__ indptr, int n_tiles, int *__restrict__ tile_row, int *__restrict__ tile_k) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    const int r = t == n_tiles ? (int)n_rows : (int)lower_bound_i32(indptr, n_rows, (int64_t)t * TMA_TILE);
+    tile_row[t] = r;
+    tile_k[t] = indptr[r];
+}
+__global__ void __launch_bounds__(256)
+spmv_tma_span_kernel(int n_tiles, const int *__restrict__ tile_k, int *__restrict__ max_span) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    atomicMax(max_span, tile_k[t + 1] - (tile_k[t] & ~3));
+}
+
+template <int BLOCK, int STAGES>
+__global__ void __launch_bounds__(BLOCK)
+spmv_tma_kernel(int64_t n_rows, int n_tiles, int cap, const int *__restrict__ indptr, const int *__restrict__ indices,
+                const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y, const int *__restrict__ tile_row,
+                const int *__restrict__ tile_k, const double *__restrict__ stop, double *__restrict__ dot_slots) {
+    extern __shared__ __align__(128) unsigned char tma_ring[];
+    unsigned char *ring = tma_ring;
+    // [STAGES mbarriers | STAGES x 8 descriptor ints | STAGES x { cap doubles | cap ints | TMA_RP_CAP ints }]
+    static_assert(STAGES <= 8, "header layout");
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(ring);          // [0, 64): mbarriers
+    int *desc = reinterpret_cast<int *>(ring + 64);                                    // [64, 320): 8 ints per stage
+    unsigned char *stages = ring + TMA_HEAD;
+    const size_t stage_bytes = (size_t)cap * 12 + TMA_RP_CAP * 4;
+    if (stop && *stop != 0.0) return;
+    const uint64_t once = l2_policy_evict_first();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // thread 0 only: descriptor of the next tile to issue, loaded one iteration before it is needed
+    int d_row0 = 0, d_row1 = 0, d_k0 = 0, d_k1 = 0;
+    auto load_desc = [&](int tile) {
+        if (tile < n_tiles) {
+            d_row0 = __ldg(tile_row + tile);
+            d_row1 = __ldg(tile_row + tile + 1);
+            d_k0 = __ldg(tile_k + tile);
+            d_k1 = __ldg(tile_k + tile + 1);
+        }
+    };
+    auto issue = [&](int tile, int stage) {          // thread 0; uses the descriptor registers
+        if (tile >= n_tiles) return;
+        unsigned char *base = stages + (size_t)stage * stage_bytes;
+        const int k0a = d_k0 & ~3, nk = d_k1 - k0a;
+        const int r0a = d_row0 & ~3;
+        int nrp = d_row1 - r0a + 1;
+        if (nrp > TMA_RP_CAP) nrp = TMA_RP_CAP;
+        const unsigned b_val = (unsigned)((nk + 1) & ~1) * 8u, b_col = (unsigned)((nk + 3) & ~3) * 4u, b_rp = (unsigned)((nrp + 3) & ~3) * 4u;
+        int *dd = desc + stage * 8;
+        dd[0] = d_row0; dd[1] = d_row1; dd[2] = k0a; dd[3] = r0a;
+        mbar_arrive_expect_tx(full + stage, b_val + b_col + b_rp);
+        if (b_val) bulk_g2s(base, data + k0a, b_val, full + stage, once);
+        if (b_col) bulk_g2s(base + (size_t)cap * 8, indices + k0a, b_col, full + stage, once);
+        bulk_g2s(base + (size_t)cap * 12, indptr + r0a, b_rp, full + stage, once);
+    };
+    const int t0 = blockIdx.x, dt = gridDim.x;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            load_desc(t0 + s * dt);
+            issue(t0 + s * dt, s);
+        }
+        load_desc(t0 + (STAGES - 1) * dt);
+    }
+    double dot = 0.0;
+    int i = 0;
+    for (int t = t0; t < n_tiles; t += dt, ++i) {
+        const int stage = i % STAGES;
+        if (threadIdx.x == 0) {
+            issue(t + (STAGES - 1) * dt, (i + STAGES - 1) % STAGES);       // the stage tile i - 1 was reduced from
+            load_desc(t + STAGES * dt);
+        }
+        const unsigned parity = (unsigned)(i / STAGES) & 1u;
+        while (!mbar_try_wait(full + stage, parity)) {}
+        const unsigned char *base = stages + (size_t)stage * stage_bytes;
+        const double *sval = reinterpret_cast<const double *>(base);
+        const int *scol = reinterpret_cast<const int *>(base + (size_t)cap * 8);
+        const int *srp = reinterpret_cast<const int *>(base + (size_t)cap * 12);
+        const int *dd = desc + stage * 8;
+        const int row0 = dd[0], row1 = dd[1], k0a = dd[2], rp_off = row0 - dd[3];
+        const int nr = row1 - row0;
+        int g = 1;
+        while (g < 32 && nr * (2 * g) <= BLOCK) g <<= 1;
+        const int gl = threadIdx.x & (g - 1), n_groups = BLOCK / g;
+        for (int rr = threadIdx.x / g; rr < nr; rr += n_groups) {       // rr is uniform inside a group; g divides 32
+            const int row = row0 + rr;
+            const int j = rr + rp_off;
+            const int b = (j < TMA_RP_CAP ? srp[j] : __ldg(indptr + row)) - k0a;
+            const int e = (j + 1 < TMA_RP_CAP ? srp[j + 1] : __ldg(indptr + row + 1)) - k0a;
+            const double xr = (dot_slots && gl == 0) ? __ldg(x + row) : 0.0;
+            // all gathers of a row are issued in ONE round (rows of up to 12 g entries): a second round would wait for
+            // the first one's products, and the rounds of a tile are what its CTA's time consists of
+            constexpr int UG = 12;
+            double acc = 0.0;
+            for (int k = b + gl; k < e; k += UG * g) {
+                // branch-free: slots past the row's end re-read the lane's first entry with a zero value
+                int c[UG];
+                double v[UG];
+#pragma unroll
+                for (int j = 0; j < UG; ++j) {
+                    const bool in = k + j * g < e;
+                    const int idx = in ? k + j * g : k;
+                    c[j] = scol[idx];
+                    v[j] = sval[idx];
+                    if (!in) v[j] = 0.0;
+                }
+                double xv[UG];
+#pragma unroll
+                for (int j = 0; j < UG; ++j) xv[j] = __ldg(x + c[j]);
+                // ptxas would otherwise put product j (which waits for gather j) in front of gather j + 1: the running
+                // sum is made to depend on every gathered word (a NaN pattern x never holds), so all gathers are issued
+                // before the first product
+                int dep = 0;
+#pragma unroll
+                for (int j = 0; j < UG; ++j) dep |= (__double2hiint(xv[j]) == (int)0xffffffffu) ? 1 : 0;
+                acc = __hiloint2double(__double2hiint(acc) ^ dep, __double2loint(acc));
+#pragma unroll
+                for (int j = 0; j < UG; ++j) acc += v[j] * xv[j];
+            }
+            // fold inside the group: groups are aligned power-of-two lane ranges; rows of one warp may have
+            // different trip counts, so name the participating lanes explicitly
+            const unsigned lane = lane_id();
+            const unsigned gmask = g == 32 ? 0xffffffffu : (((1u << g) - 1u) << (lane & ~(unsigned)(g - 1)));
+            for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+            if (gl == 0) {
+                y[row] = acc;
+                dot += acc * xr;
+            }
+        }
+        __syncthreads();                                                   // the stage is free for the copy issued next
+    }
+    if (dot_slots) {
+        dot = warp_sum(dot);
+        if (lane_id() == 0 && dot != 0.0) atomicAdd(dot_slots + ((blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5)) & 255u), dot);
+    }
+}
+
+int spmv_tma_plan_create(SpmvTmaPlan *plan, int64_t n_rows, const int32_t *indptr, int64_t nnz, cudaStream_t stream) {
+    plan->n_rows = n_rows;
+    plan->n_tiles = (int)(nnz / TMA_TILE) + 1;
+    plan->stream = stream;
+    plan->cap = 0;
+    Scratch mx;
+    LSS_CUDA(mx.alloc(sizeof(int), stream));
+    LSS_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), stream));
+    LSS_CUDA(cudaMallocAsync((void **)&plan->tile_row, sizeof(int) * (plan->n_tiles + 1), stream));
+    LSS_CUDA(cudaMallocAsync((void **)&plan->tile_k, sizeof(int) * (plan->n_tiles + 1), stream));
+    spmv_tma_plan_kernel<<<ceil_div(plan->n_tiles + 1, 256), 256, 0, stream>>>(n_rows, indptr, plan->n_tiles, plan->tile_row, plan->tile_k);
+    LSS_LAUNCH_CHECK();
+    spmv_tma_span_kernel<<<ceil_div(plan->n_tiles, 256), 256, 0, stream>>>(plan->n_tiles, plan->tile_k, mx.as<int>());
+    LSS_LAUNCH_CHECK();
+    int span = 0;
+    LSS_CUDA(cudaMemcpyAsync(&span, mx.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    LSS_CUDA(cudaStreamSynchronize(stream));
+    plan->cap = (span + 15) / 16 * 16 + 16;
+    return LSS_OK;
+}
+
+void spmv_tma_plan_destroy(SpmvTmaPlan *plan) {
+    if (plan->tile_row) cudaFreeAsync(plan->tile_row, plan->stream);
+    if (plan->tile_k) cudaFreeAsync(plan->tile_k, plan->stream);
+    plan->tile_row = plan->tile_k = nullptr;
+}
+
+constexpr int TMA_BLOCK = 128, TMA_MAX_CAP = 2304;
+static int tma_stages() {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("LSS_TMA_STAGES");
+        v = e ? atoi(e) : 2;
+        if (v < 2 || v > 4) v = 2;
+    }
+    return v;
+}
+bool spmv_tma_fits(const SpmvTmaPlan *plan) { return plan->tile_row && plan->cap > 0 && plan->cap <= TMA_MAX_CAP; }
+
+// y = A x over the rows of the plan (every row is written; rows of the arrays must be readable 16 bytes past their end)
+int spmv_launch_tma(const SpmvTmaPlan *plan, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
+                    const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots) {
+    if (plan->n_rows <= 0) return LSS_OK;
+    const int S = tma_stages();
+    const size_t smem = TMA_HEAD + (size_t)S * ((size_t)plan->cap * 12 + TMA_RP_CAP * 4);
+    const void *fn = S == 2 ? (const void *)spmv_tma_kernel<TMA_BLOCK, 2> : S == 3 ? (const void *)spmv_tma_kernel<TMA_BLOCK, 3>
+                                                                                   : (const void *)spmv_tma_kernel<TMA_BLOCK, 4>;
+    static size_t attr_for = 0;
+    static int per_sm = 0;
+    if (attr_for != smem) {
+        LSS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TMA_BLOCK, smem));
+        if (per_sm < 1) return fail(LSS_EINVAL, "spmv_tma_kernel: %zu bytes of shared memory do not fit", smem);
+        attr_for = smem;
+    }
+    const int grid = plan->n_tiles < kSMs * per_sm ? plan->n_tiles : kSMs * per_sm;
+    int64_t n_rows = plan->n_rows;
+    int n_tiles = plan->n_tiles, cap = plan->cap;
+    const int *tr = plan->tile_row, *tk = plan->tile_k;
+    void *args[] = {&n_rows, &n_tiles, &cap, &indptr, &indices, &data, &x, &y, &tr, &tk, &stop, &dot_slots};
+    LSS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(TMA_BLOCK), args, smem, stream));
+    LSS_LAUNCH_CHECK();
+    if (launches) *launches += 1;
+    return LSS_OK;
+}
+
+static int g_normal_product = -1;
+int normal_product_variant() {
+    if (g_normal_product < 0) {
+        const char *e = getenv("LSS_N_PRODUCT");
+        g_normal_product = e ? atoi(e) : 0;     // measured on the 10^7-point workload (profiles/README.md): none of 1..10 beats the tiled kernel yet
+        if (g_normal_product < 0 || g_normal_product > 10) g_normal_product = 0;
+    }
+    return g_normal_product;
+}
+void set_normal_product_variant(int v) { g_normal_product = (v < 0 || v > 10) ? 0 : v; }
+
+template <int BLOCK, int TILE, int STAGES>
+static int launch_stream(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
+                         int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, double *dot_slots) {
+    constexpr size_t smem = (size_t)STAGES * TILE * 12;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (smem > 48 * 1024)
+            LSS_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<BLOCK, TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_stream_kernel<BLOCK, TILE, STAGES>, BLOCK, smem));
+        if (per_sm < 1) { per_sm = 0; return fail(LSS_EINVAL, "spmv_stream_kernel: %zu bytes of shared memory do not fit", smem); }
+    }
+    const int n_tiles = ceil_div(nnz, TILE);
+    const int grid = n_tiles < kSMs * per_sm ? n_tiles : kSMs * per_sm;
+    spmv_stream_kernel<BLOCK, TILE, STAGES><<<grid, BLOCK, smem, stream>>>(n_rows, nnz, n_tiles, indptr, indices, data, x, y, plan->bounds, stop,
+                                                                           dot_slots);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+// y (+)= A x for the explicit normal matrix, one launch; y must hold zeros (see above).  variant: normal_product_variant()
+int spmv_launch_normal(int variant, int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x,
+                       double *y, int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches,
+                       double *dot_slots) {
+    if (n_rows <= 0 || nnz == 0) return LSS_OK;
+    if (variant == 1 || variant == 5 || variant == 6) {
+        if (variant == 1) {
+            spmv_rows_kernel<16, 8><<<ceil_div(n_rows * 16, 256), 256, 0, stream>>>(n_rows, indptr, indices, data, x, y, stop, dot_slots);
+        } else if (variant == 5) {
+            spmv_rows_kernel<8, 12><<<ceil_div(n_rows * 8, 256), 256, 0, stream>>>(n_rows, indptr, indices, data, x, y, stop, dot_slots);
+        } else {
+            spmv_rows_kernel<32, 4><<<ceil_div(n_rows * 32, 256), 256, 0, stream>>>(n_rows, indptr, indices, data, x, y, stop, dot_slots);
+        }
+        LSS_LAUNCH_CHECK();
+        if (launches) *launches += 1;
+        return LSS_OK;
+    }
+    if (variant >= 2 && variant <= 4) {
+        if (!plan || !plan->bounds || plan->tile != 1024) return fail(LSS_EINVAL, "spmv_launch_normal: needs a plan with 1024-entry tiles");
+        int rc;
+        if (variant == 2) rc = launch_stream<128, 1024, 4>(n_rows, indptr, indices, data, x, y, nnz, plan, stop, stream, dot_slots);
+        else if (variant == 3) rc = launch_stream<128, 1024, 6>(n_rows, indptr, indices, data, x, y, nnz, plan, stop, stream, dot_slots);
+        else rc = launch_stream<256, 1024, 4>(n_rows, indptr, indices, data, x, y, nnz, plan, stop, stream, dot_slots);
+        if (rc == LSS_OK && launches) *launches += 1;
+        return rc;
+    }
+    return spmv_launch_atomic(n_rows, indptr, indices, data, x, y, nnz, plan, stop, stream, launches, dot_slots);
+}
+
 // ============================================================================ ELL (fixed row length) product
 // The data block G has the same number of entries in every row (2^2 z0 corners + 2^3 dz corners + bias columns),
 // so it is also kept column-major ("ELL"): entry k of row r at [k * n_pad + r].  One thread per row then reads
@@ -516,7 +1062,7 @@ int ell_normal_launch(int mode, int64_t n_rows, int64_t n_pad, int K, const int3
 
 using namespace lss;
 
-namespace lss { int g_opt_explicit_normal = -1; }
+namespace lss { int g_opt_explicit_normal = -1; int g_opt_step_kernel = -1; }
 
 extern "C" int lss_set_option(const char *name, int32_t value) {
     if (name && strcmp(name, "explicit_normal") == 0) {
@@ -526,6 +1072,16 @@ extern "C" int lss_set_option(const char *name, int32_t value) {
     if (name && strcmp(name, "spmv_variant") == 0) {
         if (value < 0 || value >= kNumShapes) return fail(LSS_EINVAL, "spmv_variant must be in [0, %d)", kNumShapes);
         g_variant = value;
+        return LSS_OK;
+    }
+    if (name && strcmp(name, "normal_product") == 0) {
+        if (value < 0 || value > 10) return fail(LSS_EINVAL, "normal_product must be in [0, 10]");
+        lss::set_normal_product_variant(value);
+        return LSS_OK;
+    }
+    if (name && strcmp(name, "step_kernel") == 0) {
+        if (value < 0 || value > 2) return fail(LSS_EINVAL, "step_kernel must be 0, 1 or 2");
+        lss::g_opt_step_kernel = value;
         return LSS_OK;
     }
     return fail(LSS_EINVAL, "unknown option %s", name ? name : "(null)");

@@ -387,6 +387,30 @@ def test_operator_forms_and_preconditioners_agree(L):
     assert its['structured'] < 0.7 * its['jacobi']
 
 
+def test_normal_product_and_step_kernel_variants_agree(L):
+    """Every product kernel for the explicit normal matrix (nnz-tiled, row-per-lane-group, cp.async stream ring, padded
+    chunks of 8, TMA-streamed row-aligned tiles) and every CG vector-step kernel (warp per block, thread per block row, CTA tile) give the same fit: same masks, solutions equal to solver tolerance."""
+    from lssurf_b200 import synthetic
+    pts, kw = synthetic.icesat2_tracks(n=150_000, width=2.e4, seed=7)
+    out = {}
+    try:
+        for prod, step in ((0, 0), (0, 1), (1, 2), (2, 2), (5, 1), (8, 2), (10, 2), (10, 0)):
+            L._cabi.set_option('normal_product', prod)
+            L._cabi.set_option('step_kernel', step)
+            out[(prod, step)] = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, **kw)
+            assert out[(prod, step)]['timing']['pcg'][0]['form'] == 'explicit_normal'
+    finally:
+        L._cabi.set_option('normal_product', 0)
+        L._cabi.set_option('step_kernel', 2)
+    ref = out[(0, 0)]
+    its0 = sum(p['iterations'] for p in ref['timing']['pcg'])
+    for key, o in out.items():
+        assert rel_l2(o['m']['all'], ref['m']['all']) < 1e-9, key
+        assert np.array_equal(o['data'].three_sigma_edit, ref['data'].three_sigma_edit), key
+        its = sum(p['iterations'] for p in o['timing']['pcg'])
+        assert abs(its - its0) <= 0.05 * its0 + 5, (key, its, its0)
+
+
 def test_large_scale_properties(L):
     """Full-size properties (cfg 3 shapes, 1e6 points) that need no oracle: row sums of the interpolation
     matrix are exactly 1 up to rounding, CSR is canonical, G^T products are adjoint, the solve reduces the residual."""
