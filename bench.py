@@ -264,6 +264,7 @@ def run_b200(a):
                               'atomic carries, p.q by-product)',
                     'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peak_src,
                     'traffic': traffic, 'bytes_per_launch': {'N': b_dom}, 'launch_ms': {'N': ms_dom},
+                    'launch_ms_samples': n_apply, 'launch_ms_sampling': 'CUDA event pairs on the solver stream around every 4th CG iteration of the timed steps',
                     'nnz_N': nnzN, 'nnz_streamed_per_product': nnzP, 'nnz_A': nnz,
                     'csr_pair_equivalent': {'bytes': b_two, 'gbs': b_two / (ms_dom / 1e3) / 1e9,
                                             'note': 'bytes the A / A^T two-product form of the same operator would stream, '

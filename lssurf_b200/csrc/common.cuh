@@ -168,8 +168,15 @@ struct SpmvTmaPlan {
     int64_t n_rows;
     int n_tiles, cap;          // cap: entries a ring stage must hold
     int *tile_row, *tile_k;    // [n_tiles + 1]
+    // dictionary form (variant 11): per tile the sorted distinct columns and 16-bit positions in them per entry
+    unsigned short *lcol;
+    int *dict, *dict_n;
+    int dstride, dcap, cap8;
     cudaStream_t stream;
 };
+int spmv_tma_plan_add_dict(SpmvTmaPlan *plan, const int32_t *indices, int64_t nnz);
+int spmv_launch_tmad(const SpmvTmaPlan *plan, const int32_t *indptr, const double *data, const double *x, double *y, const double *stop,
+                     cudaStream_t stream, int64_t *launches, double *dot_slots = nullptr);
 int spmv_tma_plan_create(SpmvTmaPlan *plan, int64_t n_rows, const int32_t *indptr, int64_t nnz, cudaStream_t stream);
 void spmv_tma_plan_destroy(SpmvTmaPlan *plan);
 bool spmv_tma_fits(const SpmvTmaPlan *plan);

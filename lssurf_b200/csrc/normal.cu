@@ -11,8 +11,9 @@
 //       (reference epoch) are left out of N altogether.
 //   numeric  (per outer iteration)   N += sum_r (w_new[r] - w_cur[r]) a_r a_r^T over the rows whose weight changed:
 //       a full pass the first time, afterwards only the rows the 3-sigma edit switched on or off.  One warp works
-//       on one row at a time: 32 lanes take the K*K pairs, find the slot of (c_i, c_j) by binary search in row c_i
-//       of the pattern, and issue one RED.ADD.F64.
+//       on a 32-row chunk: the K*K pair products of consecutive rows with identical columns (points of one track in
+//       one grid cell) are summed in registers, then 32 lanes find the slots of (c_i, c_j) by binary search in row
+//       c_i of the pattern and issue one RED.ADD.F64 per pair and run.
 //   product   the nnz-tiled CSR kernel of spmv.cu (deterministic, no atomics).
 #include "common.cuh"
 
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) normal_fill_i32_kernel(int *p, int64_t n,
 }
 
 // N += sum_r (w_new[r] - w_cur[r]) a_r a_r^T ; w_cur <- w_new.  Warp per 32-row chunk, rows staged in shared memory,
-// one row at a time spread over the lanes (pair e = i * K + j on lane e mod 32).
+// pairs spread over the lanes (pair e = i * K + j on lane e mod 32).
 __global__ void __launch_bounds__(NU_WARPS * 32)
 normal_update_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict__ ell_col, const double *__restrict__ ell_val,
                      const unsigned char *__restrict__ fixed, const double *__restrict__ w_new, double *__restrict__ w_cur,
@@ -131,15 +132,23 @@ normal_update_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict
             }
         }
         __syncwarp();
-        while (act) {
-            const int src = __ffs(act) - 1;
-            act &= act - 1u;
-            const double dws = __shfl_sync(0xffffffffu, dw, src);
-            for (int e = (int)lane; e < KK; e += 32) {
+        // Rows are stored in grid-cell order, so consecutive rows mostly hold the SAME columns (points of one track in one
+        // cell): their K x K products are summed in registers and the pattern is searched once per run, not per row.
+        constexpr int T = (NK_MAX * NK_MAX + 31) / 32;
+        double accp[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) accp[t] = 0.0;
+        int cur = -1;
+        auto flush = [&](int rep) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int e = (int)lane + 32 * t;
+                const double val = accp[t];
+                accp[t] = 0.0;
+                if (e >= KK || val == 0.0) continue;
                 const int i = e / K, j = e - i * K;
-                const int ci = sc[w][src][i], cj = sc[w][src][j];
+                const int ci = sc[w][rep][i], cj = sc[w][rep][j];
                 if (ci < 0 || cj < 0) continue;
-                const double val = dws * sv[w][src][i] * sv[w][src][j];
                 int lo = __ldg(indptr + ci), hi = __ldg(indptr + ci + 1);
                 const int end = hi;
                 while (lo < hi) {
@@ -149,7 +158,30 @@ normal_update_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict
                 if (lo < end && __ldg(indices + lo) == cj) atomicAdd(data + lo, val);
                 else atomicAdd(n_missing, 1ull);     // cannot happen with a pattern built from the same rows
             }
+        };
+        while (act) {
+            const int src = __ffs(act) - 1;
+            act &= act - 1u;
+            bool same = false;
+            if (cur >= 0) {
+                const int eq = ((int)lane < K) ? (sc[w][src][lane] == sc[w][cur][lane]) : 1;
+                same = __all_sync(0xffffffffu, eq) != 0;
+            }
+            if (!same) {
+                if (cur >= 0) flush(cur);
+                cur = src;
+            }
+            const double dws = __shfl_sync(0xffffffffu, dw, src);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int e = (int)lane + 32 * t;
+                if (e < KK) {
+                    const int i = e / K, j = e - i * K;
+                    accp[t] += dws * sv[w][src][i] * sv[w][src][j];
+                }
+            }
         }
+        if (cur >= 0) flush(cur);
         __syncwarp();
     }
 }
@@ -376,7 +408,7 @@ int normal_apply_fast(NormalMatrix *m, int64_t n_rows, const double *x, double *
         return fail(LSS_EINVAL, "normal matrix product: the single-launch kernel needs the default spmv_variant (1024-entry tiles)");
     if (!y_is_zero) LSS_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * m->n_cols, m->stream));
     int variant = normal_product_variant();
-    if (variant == 10 && m->nnz > 0) {
+    if (variant >= 10 && variant <= 11 && m->nnz > 0) {
         const int64_t rows = n_rows < m->n_cols ? n_rows : m->n_cols;
         if (!m->tma_plan.tile_row || m->tma_plan.n_rows != rows) {
             spmv_tma_plan_destroy(&m->tma_plan);
@@ -385,6 +417,10 @@ int normal_apply_fast(NormalMatrix *m, int64_t n_rows, const double *x, double *
             LSS_CUDA(cudaStreamSynchronize(m->stream));
             m->tma_nnz = nz;
             LSS_TRY(spmv_tma_plan_create(&m->tma_plan, rows, m->indptr, nz, m->stream));
+        }
+        if (variant == 11 && spmv_tma_fits(&m->tma_plan)) {
+            LSS_TRY(spmv_tma_plan_add_dict(&m->tma_plan, m->indices, m->tma_nnz));
+            return spmv_launch_tmad(&m->tma_plan, m->indptr, m->data, x, y, stop, m->stream, launches, dot_slots);
         }
         if (spmv_tma_fits(&m->tma_plan))
             return spmv_launch_tma(&m->tma_plan, m->indptr, m->indices, m->data, x, y, stop, m->stream, launches, dot_slots);

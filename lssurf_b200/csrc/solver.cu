@@ -1010,6 +1010,7 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
 
 // q(buf[0:n]) = A^T (w .* (A v)), partials of v.q appended at buf[n:], summed over ranks.
 constexpr int kBatch = 16;   // CG iterations enqueued between two looks at the convergence flag
+constexpr int kProfEvery = 4; // with lss_solver_set_profile: timing events around every 4th iteration (events cost ~10 us of stream time each)
 
 static int apply_normal(lss_solver *s, const double *v, bool with_dot, const double *stop, int prof_slot = -1) {
     cudaStream_t st = s->stream;
@@ -1203,7 +1204,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     auto harvest = [&](int sl) {     // the batch's completion event has been waited for: its timing events are final
         // iterations enqueued after convergence are no-ops on the device: leave them out of the averages
         const int real = (int)s->host_scal[sl * S_COUNT + S_ITERS] - base_it[sl];
-        for (int k = 0; k < in_slot[sl] && k < real && s->profile; ++k) {
+        for (int k = 0; k < in_slot[sl] && k < real && s->profile; k += kProfEvery) {
             float a = 0.f, b = 0.f;
             const int e = 4 * (sl * kBatch + k);
             float c = 0.f;
@@ -1221,7 +1222,8 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
         // enqueue one batch, then look at the flag the PREVIOUS batch left behind
         const int todo = (max_iter - issued) < batch ? (max_iter - issued) : batch;
         for (int k = 0; k < todo; ++k) {
-            LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity, slot * kBatch + k));
+            const bool prof_k = s->profile && (k % kProfEvery) == 0;      // event pairs around every kProfEvery-th iteration only
+            LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity, prof_k ? slot * kBatch + k : -1));
             if (structured) {
                 double *qv = s->buf, *minv = s->minv, *pv = s->p, *rv = s->r, *zv = s->z, *part = s->part2, *scal = s->scal;
                 int64_t nn = n;
@@ -1274,7 +1276,7 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
                 LSS_LAUNCH_CHECK();
                 s->launches += 2;
             }
-            if (s->profile) LSS_CUDA(cudaEventRecord((*s->prof_events)[4 * (slot * kBatch + k) + 3], st));   // after the vector step
+            if (prof_k) LSS_CUDA(cudaEventRecord((*s->prof_events)[4 * (slot * kBatch + k) + 3], st));   // after the vector step
             parity ^= 1;
         }
         base_it[slot] = issued;
@@ -1331,7 +1333,7 @@ extern "C" int lss_solver_info(lss_solver_t *s, int64_t *info_h) {
     info_h[7] = 0;
     if (s->nm) {
         const bool part = s->e1 > s->e0 && s->e1 == s->n_cols;
-        if (part && lss::normal_product_variant() == 10 && s->nm->tma_plan.tile_row && s->nm->tma_plan.n_rows == s->e0) info_h[7] = s->nm->tma_nnz;
+        if (part && lss::normal_product_variant() >= 10 && s->nm->tma_plan.tile_row && s->nm->tma_plan.n_rows == s->e0) info_h[7] = s->nm->tma_nnz;
         else if (part && s->nm->c8_part_rows == s->e0 && lss::normal_product_variant() >= 7) info_h[7] = s->nm->c8_part_nnz;
         else if (part && s->nm->part_rows == s->e0) info_h[7] = s->nm->part_nnz;
         else info_h[7] = s->nm->nnz;

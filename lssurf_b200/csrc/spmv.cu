@@ -353,28 +353,19 @@ int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *ind
 
 // ============================================================================ products for the explicit normal matrix
 // The explicit normal matrix has long, uneven rows (mean 80, 0..277 entries for the 10^7-point workload) whose column
-// sets overlap heavily between neighbouring rows (neighbouring grid nodes).  The generic nnz-tiled kernel above spends
-// its L1 wavefronts on staging products through shared memory and on gathers of 32 consecutive non-zeros of ONE row
-// (ncu: l1tex 71-77 %, DRAM 50-60 %).  Two kernels specialised for this shape, selected by lss_set_option
-// ("normal_product") / LSS_N_PRODUCT:
+// sets overlap heavily between neighbouring rows (neighbouring grid nodes).  The nnz-tiled kernel above (variant 0) is
+// still the one the solver uses: 0.092 ms per product, 0.61 of the measured HBM peak.  The kernels below are the
+// alternatives tried in round 1, all parity-tested (tests/test_gpu_parity.py) and selectable with
+// lss_set_option("normal_product", v) / LSS_N_PRODUCT for profiling; profiles/README.md has their timings and what ncu
+// says limits each of them (none is HBM-bound: L1 wavefronts of the gathers, issue slots, or per-tile latency chains).
 //
-//   rows    G lanes per row, everything in registers: each lane loads up to U (column, value) pairs of its row with
-//           streaming loads, gathers x, folds with G-wide shuffles and stores y[row] -- no shared memory, no atomics,
-//           no dependence on y's previous contents.
-//   stream  persistent CTAs; the matrix stream (values + column indices of one 1024-entry tile) is copied into a
-//           STAGES-deep shared-memory ring with cp.async (L2 evict-first), so the bytes in flight live in shared
-//           memory instead of registers (STAGES x 12 KB per CTA, several CTAs per SM); rows are then reduced straight
-//           from the ring by groups of g lanes which issue the gathers themselves (neighbouring rows side by side in
-//           a warp: their gathers hit the same lines).  Rows cut by a tile boundary are completed with RED atomics,
-//           so y must hold zeros there (same contract as spmv_launch_atomic).
-__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int src_bytes, uint64_t pol) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(sa), "l"(gmem), "r"(src_bytes), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
+//   1, 5, 6  rows    G lanes per row, everything in registers: each lane loads up to U (column, value) pairs of its row
+//                    with streaming loads, gathers x, folds with G-wide shuffles and stores y[row].
+//   7, 8, 9  chunk8  padded copy of N in chunks of 8 entries with one row id per chunk: no load address depends on a
+//                    row pointer; 8-lane sums merged across equal rows, one RED per (warp load, row).
+//   10       tma     row-aligned tiles streamed into a shared-memory ring by TMA bulk copies, rows reduced from the ring.
+//   11       tmad    tma with a per-tile column dictionary: x is gathered once per distinct column of a tile, the row
+//                    sums run from shared memory only, 10.3 instead of 12 bytes per entry.
 template <int G, int U>
 __global__ void __launch_bounds__(256)
 spmv_rows_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ data,
@@ -418,100 +409,8 @@ spmv_rows_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__re
     }
 }
 
-template <int BLOCK, int TILE, int STAGES>
-__global__ void __launch_bounds__(BLOCK)
-spmv_stream_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__restrict__ indptr, const int *__restrict__ indices,
-                   const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
-                   const int *__restrict__ tile_bounds, const double *__restrict__ stop, double *__restrict__ dot_slots) {
-    extern __shared__ __align__(16) unsigned char ring[];          // stage s: [TILE doubles][TILE ints]
-    constexpr int STAGE_BYTES = TILE * 12;
-    if (stop && *stop != 0.0) return;
-    const uint64_t once = l2_policy_evict_first();
-    auto issue = [&](int tile, int stage) {
-        if (tile < n_tiles) {
-            const int64_t k0 = (int64_t)tile * TILE;
-            double *sval = reinterpret_cast<double *>(ring + (size_t)stage * STAGE_BYTES);
-            int *scol = reinterpret_cast<int *>(ring + (size_t)stage * STAGE_BYTES + TILE * 8);
-            for (int c = threadIdx.x; c < TILE / 2; c += BLOCK) {          // 16 bytes = 2 values
-                const int64_t k = k0 + 2 * c;
-                const int64_t left = nnz - k;
-                const int nb = left >= 2 ? 16 : (left > 0 ? 8 : 0);
-                cp_async16_zfill(sval + 2 * c, nb ? (const void *)(data + k) : (const void *)data, nb, once);
-            }
-            for (int c = threadIdx.x; c < TILE / 4; c += BLOCK) {          // 16 bytes = 4 column indices
-                const int64_t k = k0 + 4 * c;
-                const int64_t left = nnz - k;
-                const int nb = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
-                cp_async16_zfill(scol + 4 * c, nb ? (const void *)(indices + k) : (const void *)indices, nb, once);
-            }
-        }
-        cp_async_commit_group();                                           // one group per call, empty or not
-    };
-    int t = blockIdx.x;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(t + s * (int)gridDim.x, s);
-    double dot = 0.0;
-    for (int i = 0; t < n_tiles; ++i, t += gridDim.x) {
-        issue(t + (STAGES - 1) * (int)gridDim.x, (i + STAGES - 1) % STAGES);   // the stage tile i - 1 was reduced from
-        cp_async_wait_group<STAGES - 1>();                                 // this thread's copies of tile i have landed
-        __syncthreads();                                                   // ... and everybody else's
-        const int stage = i % STAGES;
-        const double *sval = reinterpret_cast<const double *>(ring + (size_t)stage * STAGE_BYTES);
-        const int *scol = reinterpret_cast<const int *>(ring + (size_t)stage * STAGE_BYTES + TILE * 8);
-        const int64_t k0 = (int64_t)t * TILE;
-        const int64_t k1 = (k0 + TILE < nnz) ? k0 + TILE : nnz;
-        const int64_t r_lo = tile_bounds[2 * t], r_hi = tile_bounds[2 * t + 1];
-        const bool has_carry = (int64_t)indptr[r_lo] < k0;                 // r_lo started in an earlier tile
-        const int64_t first = r_lo + (has_carry ? 1 : 0);
-        const int64_t n_virtual = (r_hi - first) + 1;                      // virtual row 0 is the carry-in
-        int g = 1;
-        while (g < 32 && n_virtual * (2 * g) <= BLOCK) g <<= 1;
-        const int gl = threadIdx.x & (g - 1), rows_per_pass = BLOCK / g;
-        for (int64_t base = 0; base < n_virtual; base += rows_per_pass) {
-            const int64_t v = base + threadIdx.x / g;
-            const bool valid = v < n_virtual && !(v == 0 && !has_carry);
-            int64_t b = 0, e = 0;
-            const int64_t rr = v == 0 ? r_lo : first + v - 1;
-            if (valid) {
-                b = v == 0 ? k0 : (int64_t)indptr[rr];
-                e = indptr[rr + 1];
-            }
-            const bool open = e > k1;                                      // continues in the next tile
-            if (open) e = k1;
-            const double xr = (dot_slots && valid && gl == 0) ? __ldg(x + rr) : 0.0;
-            int k = (int)(b - k0) + gl;
-            const int kend = (int)(e - k0);
-            double a0 = 0.0, a1 = 0.0;
-            for (; k + 3 * g < kend; k += 4 * g) {
-                const int c0 = scol[k], c1 = scol[k + g], c2 = scol[k + 2 * g], c3 = scol[k + 3 * g];
-                const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-                a0 += sval[k] * x0;
-                a1 += sval[k + g] * x1;
-                a0 += sval[k + 2 * g] * x2;
-                a1 += sval[k + 3 * g] * x3;
-            }
-            for (; k < kend; k += g) a0 += sval[k] * __ldg(x + scol[k]);
-            double acc = a0 + a1;
-            for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (valid && gl == 0) {
-                if (v == 0 || open) atomicAdd(y + rr, acc);
-                else y[rr] = acc;
-                dot += acc * xr;
-            }
-        }
-        __syncthreads();                                                   // the stage is free for the copy issued next
-    }
-    cp_async_wait_group<0>();
-    if (dot_slots) {
-        dot = warp_sum(dot);
-        if (lane_id() == 0 && dot != 0.0) atomicAdd(dot_slots + ((blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5)) & 255u), dot);
-    }
-}
-
-//   chunk8  the product the solver uses by default.  The two kernels above (and the nnz-tiled one) start every row or
-//           tile with a chain of dependent loads (tile bounds -> row pointers -> matrix stream -> gather), so their
-//           bytes in flight are only outstanding for about half of the time (measured: 0.55-0.61 of the HBM peak for
-//           all of them, whatever the register / shared-memory budget).  Here the row structure is taken out of the
+//   chunk8  The row kernels above (and the nnz-tiled one) start every row or tile with a chain of dependent loads
+//           (tile bounds -> row pointers -> matrix stream -> gather).  Here the row structure is taken out of the
 //           address computation altogether: a padded copy of N keeps every row in chunks of 8 entries (zero padding,
 //           +4 %; one row id per chunk), so the address of every matrix load depends on the thread index only.  A warp
 //           owns 4U consecutive chunks: U perfectly coalesced loads of 32 (column, value) pairs per lane are issued
@@ -777,6 +676,8 @@ int spmv_tma_plan_create(SpmvTmaPlan *plan, int64_t n_rows, const int32_t *indpt
     plan->n_tiles = (int)(nnz / TMA_TILE) + 1;
     plan->stream = stream;
     plan->cap = 0;
+    plan->lcol = nullptr;
+    plan->dict = plan->dict_n = nullptr;
     Scratch mx;
     LSS_CUDA(mx.alloc(sizeof(int), stream));
     LSS_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), stream));
@@ -796,7 +697,11 @@ int spmv_tma_plan_create(SpmvTmaPlan *plan, int64_t n_rows, const int32_t *indpt
 void spmv_tma_plan_destroy(SpmvTmaPlan *plan) {
     if (plan->tile_row) cudaFreeAsync(plan->tile_row, plan->stream);
     if (plan->tile_k) cudaFreeAsync(plan->tile_k, plan->stream);
-    plan->tile_row = plan->tile_k = nullptr;
+    if (plan->lcol) cudaFreeAsync(plan->lcol, plan->stream);
+    if (plan->dict) cudaFreeAsync(plan->dict, plan->stream);
+    if (plan->dict_n) cudaFreeAsync(plan->dict_n, plan->stream);
+    plan->tile_row = plan->tile_k = plan->dict = plan->dict_n = nullptr;
+    plan->lcol = nullptr;
 }
 
 constexpr int TMA_BLOCK = 128, TMA_MAX_CAP = 2304;
@@ -805,7 +710,7 @@ static int tma_stages() {
     if (v == 0) {
         const char *e = getenv("LSS_TMA_STAGES");
         v = e ? atoi(e) : 2;
-        if (v < 2 || v > 4) v = 2;
+        if (v < 2 || v > 5) v = 2;
     }
     return v;
 }
@@ -815,7 +720,8 @@ bool spmv_tma_fits(const SpmvTmaPlan *plan) { return plan->tile_row && plan->cap
 int spmv_launch_tma(const SpmvTmaPlan *plan, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
                     const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots) {
     if (plan->n_rows <= 0) return LSS_OK;
-    const int S = tma_stages();
+    int S = tma_stages();
+    if (S > 4) S = 4;
     const size_t smem = TMA_HEAD + (size_t)S * ((size_t)plan->cap * 12 + TMA_RP_CAP * 4);
     const void *fn = S == 2 ? (const void *)spmv_tma_kernel<TMA_BLOCK, 2> : S == 3 ? (const void *)spmv_tma_kernel<TMA_BLOCK, 3>
                                                                                    : (const void *)spmv_tma_kernel<TMA_BLOCK, 4>;
@@ -838,35 +744,281 @@ int spmv_launch_tma(const SpmvTmaPlan *plan, const int32_t *indptr, const int32_
     return LSS_OK;
 }
 
+//   tmad    "tma" with a per-tile column dictionary.  The gathers are what every kernel above pays for (8.7 L1 lines per
+//           32 entries of a row, every x entry fetched ~4 times per tile by neighbouring rows).  Once per pattern each
+//           tile's distinct columns are sorted into a dictionary (~300 for 13 neighbouring rows) and the column indices
+//           are rewritten as 16-bit positions in it.  Per tile the TMA engine then brings values (8 B), local indices
+//           (2 B) and the dictionary; the CTA gathers x ONCE per distinct column into shared memory and the row sums
+//           run entirely from shared memory.  10.3 instead of 12 bytes per entry from HBM, ~2.5x fewer L1 wavefronts.
+__global__ void __launch_bounds__(256)
+spmv_tmad_build_kernel(int n_tiles, const int *__restrict__ tile_k, const int *__restrict__ indices, int dstride, int *__restrict__ dict,
+                       int *__restrict__ dict_n, unsigned short *__restrict__ lcol, int *__restrict__ dict_max) {
+    constexpr int PMAX = 4096;
+    __shared__ int keys[PMAX];
+    __shared__ int uniq[PMAX / 2 + 512];
+    __shared__ int wsum[8];
+    __shared__ int total_s;
+    const int t = blockIdx.x;
+    const int k0 = tile_k[t], n = tile_k[t + 1] - k0;
+    int P = 256;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += 256) keys[i] = i < n ? indices[k0 + i] : 0x7fffffff;
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < P; i += 256) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if (up ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+        }
+    __syncthreads();
+    // compaction of the run heads: thread j owns the contiguous slice [j * chunk, (j + 1) * chunk)
+    const int chunk = P / 256;
+    const int lo = threadIdx.x * chunk;
+    int cnt = 0;
+    for (int i = lo; i < lo + chunk; ++i) cnt += (keys[i] != 0x7fffffff && (i == 0 || keys[i] != keys[i - 1])) ? 1 : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += v;
+    }
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += wsum[w];
+    if (threadIdx.x == 255) total_s = base + incl;
+    int pos = base + incl - cnt;
+    for (int i = lo; i < lo + chunk; ++i)
+        if (keys[i] != 0x7fffffff && (i == 0 || keys[i] != keys[i - 1])) uniq[pos++] = keys[i];
+    __syncthreads();
+    const int nd = total_s;
+    if (threadIdx.x == 0) {
+        dict_n[t] = nd;
+        atomicMax(dict_max, nd);
+    }
+    int *out = dict + (size_t)t * dstride;
+    const int nd4 = (nd + 3) & ~3;
+    for (int i = threadIdx.x; i < nd4 && i < dstride; i += 256) out[i] = uniq[i < nd ? i : nd - 1];
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int c = indices[k0 + i];
+        int a = 0, b = nd;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (uniq[mid] < c) a = mid + 1; else b = mid;
+        }
+        lcol[k0 + i] = (unsigned short)a;
+    }
+}
+
+template <int BLOCK, int STAGES>
+__global__ void __launch_bounds__(BLOCK)
+spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, const int *__restrict__ indptr,
+                 const unsigned short *__restrict__ lcol, const double *__restrict__ data, const int *__restrict__ dict,
+                 const int *__restrict__ dict_n, const double *__restrict__ x, double *__restrict__ y, const int *__restrict__ tile_row,
+                 const int *__restrict__ tile_k, const double *__restrict__ stop, double *__restrict__ dot_slots) {
+    extern __shared__ __align__(128) unsigned char tmad_ring[];
+    static_assert(STAGES <= 8, "header layout");
+    // [0, 64) mbarriers | [64, 320) 8 descriptor ints per stage | xs: dcap doubles | STAGES x { cap doubles | cap u16 | dcap ints | RP ints }
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(tmad_ring);
+    int *desc = reinterpret_cast<int *>(tmad_ring + 64);
+    double *xs = reinterpret_cast<double *>(tmad_ring + TMA_HEAD);
+    unsigned char *stages = tmad_ring + TMA_HEAD + (size_t)dcap * 16;       // two x copies: tile i and tile i + 1
+    const size_t stage_bytes = (size_t)cap * 10 + (size_t)dcap * 4 + TMA_RP_CAP * 4;
+    if (stop && *stop != 0.0) return;
+    const uint64_t once = l2_policy_evict_first();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int d_row0 = 0, d_row1 = 0, d_k0 = 0, d_k1 = 0, d_nd = 0;
+    auto load_desc = [&](int tile) {
+        if (tile < n_tiles) {
+            d_row0 = __ldg(tile_row + tile);
+            d_row1 = __ldg(tile_row + tile + 1);
+            d_k0 = __ldg(tile_k + tile);
+            d_k1 = __ldg(tile_k + tile + 1);
+            d_nd = __ldg(dict_n + tile);
+        }
+    };
+    auto issue = [&](int tile, int stage) {          // thread 0; uses the descriptor registers
+        if (tile >= n_tiles) return;
+        unsigned char *base = stages + (size_t)stage * stage_bytes;
+        const int k0a = d_k0 & ~7, nk = d_k1 - k0a;
+        const int r0a = d_row0 & ~3;
+        int nrp = d_row1 - r0a + 1;
+        if (nrp > TMA_RP_CAP) nrp = TMA_RP_CAP;
+        const unsigned b_val = (unsigned)((nk + 1) & ~1) * 8u, b_col = (unsigned)((nk + 7) & ~7) * 2u, b_rp = (unsigned)((nrp + 3) & ~3) * 4u;
+        const unsigned b_dict = (unsigned)((d_nd + 3) & ~3) * 4u;
+        int *dd = desc + stage * 8;
+        dd[0] = d_row0; dd[1] = d_row1; dd[2] = k0a; dd[3] = r0a; dd[4] = d_nd;
+        mbar_arrive_expect_tx(full + stage, b_val + b_col + b_rp + b_dict);
+        if (b_val) bulk_g2s(base, data + k0a, b_val, full + stage, once);
+        if (b_col) bulk_g2s(base + (size_t)cap * 8, lcol + k0a, b_col, full + stage, once);
+        if (b_dict) bulk_g2s(base + (size_t)cap * 10, dict + (size_t)tile * dstride, b_dict, full + stage, once);
+        bulk_g2s(base + (size_t)cap * 10 + (size_t)dcap * 4, indptr + r0a, b_rp, full + stage, once);
+    };
+    static_assert(STAGES >= 3, "tile i is reduced while the dictionary of tile i + 1 is gathered and tile i + 2 is in flight");
+    constexpr int DREG = 8;                               // dictionary entries gathered per thread (dcap <= DREG * BLOCK)
+    const int t0 = blockIdx.x, dt = gridDim.x;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            load_desc(t0 + s * dt);
+            issue(t0 + s * dt, s);
+        }
+        load_desc(t0 + (STAGES - 1) * dt);
+    }
+    // x at the distinct columns of tile 0
+    if (t0 < n_tiles) {
+        while (!mbar_try_wait(full, 0u)) {}
+        const int *sdict = reinterpret_cast<const int *>(stages + (size_t)cap * 10);
+        const int nd = desc[4];
+        for (int j = threadIdx.x; j < nd; j += BLOCK) xs[j] = __ldg(x + sdict[j]);
+    }
+    __syncthreads();
+    double dot = 0.0;
+    int i = 0;
+    for (int t = t0; t < n_tiles; t += dt, ++i) {
+        const int stage = i % STAGES;
+        if (threadIdx.x == 0) {
+            issue(t + (STAGES - 1) * dt, (i + STAGES - 1) % STAGES);        // the stage tile i - 1 was reduced from
+            load_desc(t + STAGES * dt);
+        }
+        // gathers for the NEXT tile's dictionary are issued now and land while this tile's rows are reduced
+        double xn[DREG];
+        int nd_next = 0;
+        if (t + dt < n_tiles) {
+            const int sn = (i + 1) % STAGES;
+            while (!mbar_try_wait(full + sn, (unsigned)((i + 1) / STAGES) & 1u)) {}
+            const int *sdict = reinterpret_cast<const int *>(stages + (size_t)sn * stage_bytes + (size_t)cap * 10);
+            nd_next = desc[sn * 8 + 4];
+#pragma unroll
+            for (int u = 0; u < DREG; ++u) {
+                const int j = threadIdx.x + u * BLOCK;
+                xn[u] = j < nd_next ? __ldg(x + sdict[j]) : 0.0;
+            }
+        }
+        const double *xsc = xs + (size_t)(i & 1) * dcap;
+        const unsigned char *base = stages + (size_t)stage * stage_bytes;
+        const double *sval = reinterpret_cast<const double *>(base);
+        const unsigned short *slc = reinterpret_cast<const unsigned short *>(base + (size_t)cap * 8);
+        const int *srp = reinterpret_cast<const int *>(base + (size_t)cap * 10 + (size_t)dcap * 4);
+        const int *dd = desc + stage * 8;
+        const int row0 = dd[0], row1 = dd[1], k0a = dd[2], rp_off = row0 - dd[3];
+        const int nr = row1 - row0;
+        int g = 1;
+        while (g < 32 && nr * (2 * g) <= BLOCK) g <<= 1;
+        const int gl = threadIdx.x & (g - 1), n_groups = BLOCK / g;
+        for (int rr = threadIdx.x / g; rr < nr; rr += n_groups) {
+            const int row = row0 + rr;
+            const int j = rr + rp_off;
+            const int b = (j < TMA_RP_CAP ? srp[j] : __ldg(indptr + row)) - k0a;
+            const int e = (j + 1 < TMA_RP_CAP ? srp[j + 1] : __ldg(indptr + row + 1)) - k0a;
+            const double xr = (dot_slots && gl == 0) ? __ldg(x + row) : 0.0;
+            double a0 = 0.0, a1 = 0.0;
+            int k = b + gl;
+            for (; k + 3 * g < e; k += 4 * g) {
+                const int c0 = slc[k], c1 = slc[k + g], c2 = slc[k + 2 * g], c3 = slc[k + 3 * g];
+                a0 += sval[k] * xsc[c0];
+                a1 += sval[k + g] * xsc[c1];
+                a0 += sval[k + 2 * g] * xsc[c2];
+                a1 += sval[k + 3 * g] * xsc[c3];
+            }
+            for (; k < e; k += g) a0 += sval[k] * xsc[slc[k]];
+            double acc = a0 + a1;
+            const unsigned lane = lane_id();
+            const unsigned gmask = g == 32 ? 0xffffffffu : (((1u << g) - 1u) << (lane & ~(unsigned)(g - 1)));
+            for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+            if (gl == 0) {
+                y[row] = acc;
+                dot += acc * xr;
+            }
+        }
+        if (nd_next > 0) {
+            double *xnext = xs + (size_t)((i + 1) & 1) * dcap;
+#pragma unroll
+            for (int u = 0; u < DREG; ++u) {
+                const int j = threadIdx.x + u * BLOCK;
+                if (j < nd_next) xnext[j] = xn[u];
+            }
+        }
+        __syncthreads();                                                   // stage i and its x copy are free, the next copy is complete
+    }
+    if (dot_slots) {
+        dot = warp_sum(dot);
+        if (lane_id() == 0 && dot != 0.0) atomicAdd(dot_slots + ((blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5)) & 255u), dot);
+    }
+}
+
+// adds the dictionary form to a plan (indices: the CSR column indices of the planned rows)
+int spmv_tma_plan_add_dict(SpmvTmaPlan *plan, const int32_t *indices, int64_t nnz) {
+    cudaStream_t stream = plan->stream;
+    if (plan->lcol || !spmv_tma_fits(plan)) return LSS_OK;
+    plan->dstride = (plan->cap + 3) & ~3;
+    Scratch mx;
+    LSS_CUDA(mx.alloc(sizeof(int), stream));
+    LSS_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), stream));
+    LSS_CUDA(cudaMallocAsync((void **)&plan->lcol, sizeof(unsigned short) * ((size_t)nnz + 16), stream));
+    LSS_CUDA(cudaMallocAsync((void **)&plan->dict, sizeof(int) * ((size_t)plan->n_tiles * plan->dstride + 16), stream));
+    LSS_CUDA(cudaMallocAsync((void **)&plan->dict_n, sizeof(int) * ((size_t)plan->n_tiles + 1), stream));
+    spmv_tmad_build_kernel<<<plan->n_tiles, 256, 0, stream>>>(plan->n_tiles, plan->tile_k, indices, plan->dstride, plan->dict, plan->dict_n,
+                                                              plan->lcol, mx.as<int>());
+    LSS_LAUNCH_CHECK();
+    int dmax = 0;
+    LSS_CUDA(cudaMemcpyAsync(&dmax, mx.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    LSS_CUDA(cudaStreamSynchronize(stream));
+    plan->dcap = ((dmax + 3) & ~3) + 4;
+    // entries counted from the 8-aligned start of a tile: the stage capacity may need 4 more than the 4-aligned span
+    plan->cap8 = plan->cap + 16;
+    return LSS_OK;
+}
+
+int spmv_launch_tmad(const SpmvTmaPlan *plan, const int32_t *indptr, const double *data, const double *x, double *y, const double *stop,
+                     cudaStream_t stream, int64_t *launches, double *dot_slots) {
+    if (plan->n_rows <= 0) return LSS_OK;
+    int S = tma_stages();
+    if (S < 3) S = 3;
+    if (plan->dcap > 8 * TMA_BLOCK) return fail(LSS_EINVAL, "spmv_tmad_kernel: %d distinct columns in a tile", plan->dcap);
+    const size_t smem = TMA_HEAD + (size_t)plan->dcap * 16 + (size_t)S * ((size_t)plan->cap8 * 10 + (size_t)plan->dcap * 4 + TMA_RP_CAP * 4);
+    const void *fn = S == 3 ? (const void *)spmv_tmad_kernel<TMA_BLOCK, 3> : S == 4 ? (const void *)spmv_tmad_kernel<TMA_BLOCK, 4>
+                                                                                   : (const void *)spmv_tmad_kernel<TMA_BLOCK, 5>;
+    static size_t attr_for = 0;
+    static int per_sm = 0;
+    if (attr_for != smem) {
+        LSS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TMA_BLOCK, smem));
+        if (per_sm < 1) return fail(LSS_EINVAL, "spmv_tmad_kernel: %zu bytes of shared memory do not fit", smem);
+        attr_for = smem;
+    }
+    const int grid = plan->n_tiles < kSMs * per_sm ? plan->n_tiles : kSMs * per_sm;
+    int64_t n_rows = plan->n_rows;
+    int n_tiles = plan->n_tiles, cap = plan->cap8, dcap = plan->dcap, dstride = plan->dstride;
+    const int *tr = plan->tile_row, *tk = plan->tile_k, *dict = plan->dict, *dn = plan->dict_n;
+    const unsigned short *lc = plan->lcol;
+    void *args[] = {&n_rows, &n_tiles, &cap, &dcap, &dstride, &indptr, &lc, &data, &dict, &dn, &x, &y, &tr, &tk, &stop, &dot_slots};
+    LSS_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(TMA_BLOCK), args, smem, stream));
+    LSS_LAUNCH_CHECK();
+    if (launches) *launches += 1;
+    return LSS_OK;
+}
+
 static int g_normal_product = -1;
 int normal_product_variant() {
     if (g_normal_product < 0) {
         const char *e = getenv("LSS_N_PRODUCT");
         g_normal_product = e ? atoi(e) : 0;     // measured on the 10^7-point workload (profiles/README.md): none of 1..10 beats the tiled kernel yet
-        if (g_normal_product < 0 || g_normal_product > 10) g_normal_product = 0;
+        if (g_normal_product < 0 || g_normal_product > 11) g_normal_product = 0;
     }
     return g_normal_product;
 }
-void set_normal_product_variant(int v) { g_normal_product = (v < 0 || v > 10) ? 0 : v; }
-
-template <int BLOCK, int TILE, int STAGES>
-static int launch_stream(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
-                         int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, double *dot_slots) {
-    constexpr size_t smem = (size_t)STAGES * TILE * 12;
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        if (smem > 48 * 1024)
-            LSS_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<BLOCK, TILE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_stream_kernel<BLOCK, TILE, STAGES>, BLOCK, smem));
-        if (per_sm < 1) { per_sm = 0; return fail(LSS_EINVAL, "spmv_stream_kernel: %zu bytes of shared memory do not fit", smem); }
-    }
-    const int n_tiles = ceil_div(nnz, TILE);
-    const int grid = n_tiles < kSMs * per_sm ? n_tiles : kSMs * per_sm;
-    spmv_stream_kernel<BLOCK, TILE, STAGES><<<grid, BLOCK, smem, stream>>>(n_rows, nnz, n_tiles, indptr, indices, data, x, y, plan->bounds, stop,
-                                                                           dot_slots);
-    LSS_LAUNCH_CHECK();
-    return LSS_OK;
-}
+void set_normal_product_variant(int v) { g_normal_product = (v < 0 || v > 11) ? 0 : v; }
 
 // y (+)= A x for the explicit normal matrix, one launch; y must hold zeros (see above).  variant: normal_product_variant()
 int spmv_launch_normal(int variant, int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x,
@@ -884,15 +1036,6 @@ int spmv_launch_normal(int variant, int64_t n_rows, const int32_t *indptr, const
         LSS_LAUNCH_CHECK();
         if (launches) *launches += 1;
         return LSS_OK;
-    }
-    if (variant >= 2 && variant <= 4) {
-        if (!plan || !plan->bounds || plan->tile != 1024) return fail(LSS_EINVAL, "spmv_launch_normal: needs a plan with 1024-entry tiles");
-        int rc;
-        if (variant == 2) rc = launch_stream<128, 1024, 4>(n_rows, indptr, indices, data, x, y, nnz, plan, stop, stream, dot_slots);
-        else if (variant == 3) rc = launch_stream<128, 1024, 6>(n_rows, indptr, indices, data, x, y, nnz, plan, stop, stream, dot_slots);
-        else rc = launch_stream<256, 1024, 4>(n_rows, indptr, indices, data, x, y, nnz, plan, stop, stream, dot_slots);
-        if (rc == LSS_OK && launches) *launches += 1;
-        return rc;
     }
     return spmv_launch_atomic(n_rows, indptr, indices, data, x, y, nnz, plan, stop, stream, launches, dot_slots);
 }
@@ -1075,7 +1218,7 @@ extern "C" int lss_set_option(const char *name, int32_t value) {
         return LSS_OK;
     }
     if (name && strcmp(name, "normal_product") == 0) {
-        if (value < 0 || value > 10) return fail(LSS_EINVAL, "normal_product must be in [0, 10]");
+        if (value < 0 || value > 11) return fail(LSS_EINVAL, "normal_product must be in [0, 11]");
         lss::set_normal_product_variant(value);
         return LSS_OK;
     }

@@ -469,8 +469,14 @@ class lin_op(object):
             mask = self.grid.mask
         if mask is None:
             return np.ones_like(self.ind0, dtype=float)
-        if mask_scale is None and mask.dtype == bool and mask.all():
-            return np.ones(int(self.N_eq), dtype=bool)            # default all-True mask: nothing to sample
+        if mask.dtype == bool and mask.all():                      # default all-True mask: nothing to sample
+            if mask_scale is None:
+                return np.ones(int(self.N_eq), dtype=bool)
+            val = 0.0
+            for key, scale in mask_scale.items():                  # same outcome as the sampling loop below: last matching key wins
+                if key == True:                                    # noqa: E712  (1 and True both select the unmasked nodes)
+                    val = scale
+            return np.full(int(self.N_eq), val, dtype=float)
         local = self.ind0 - self.grid.col_0
         if len(self.grid.shape) > len(mask.shape):
             full = np.unravel_index(local, self.grid.shape)

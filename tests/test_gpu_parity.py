@@ -388,13 +388,13 @@ def test_operator_forms_and_preconditioners_agree(L):
 
 
 def test_normal_product_and_step_kernel_variants_agree(L):
-    """Every product kernel for the explicit normal matrix (nnz-tiled, row-per-lane-group, cp.async stream ring, padded
-    chunks of 8, TMA-streamed row-aligned tiles) and every CG vector-step kernel (warp per block, thread per block row, CTA tile) give the same fit: same masks, solutions equal to solver tolerance."""
+    """Every product kernel for the explicit normal matrix (nnz-tiled, row-per-lane-group, padded
+    chunks of 8, TMA-streamed row-aligned tiles with and without per-tile column dictionaries) and every CG vector-step kernel (warp per block, thread per block row, CTA tile) give the same fit: same masks, solutions equal to solver tolerance."""
     from lssurf_b200 import synthetic
     pts, kw = synthetic.icesat2_tracks(n=150_000, width=2.e4, seed=7)
     out = {}
     try:
-        for prod, step in ((0, 0), (0, 1), (1, 2), (2, 2), (5, 1), (8, 2), (10, 2), (10, 0)):
+        for prod, step in ((0, 0), (0, 1), (1, 2), (5, 1), (8, 2), (10, 2), (11, 2), (11, 0)):
             L._cabi.set_option('normal_product', prod)
             L._cabi.set_option('step_kernel', step)
             out[(prod, step)] = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, **kw)

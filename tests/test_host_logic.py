@@ -140,3 +140,21 @@ def test_grid_structure_partition():
         assert np.all(np.abs(z0.ctrs[0][iy] - dz.ctrs[0][jy]) <= dz.delta[0] / 2)
         assert np.all(np.abs(z0.ctrs[1][ix] - dz.ctrs[1][jx]) <= dz.delta[1] / 2)
     assert grid_structure({'z0': z0}, fixed) is None                  # no dz grid: scalar Jacobi
+
+
+def test_mask_for_ind0_all_true_fast_path_matches_sampling():
+    """The all-True shortcut of lin_op.mask_for_ind0 returns what sampling the mask node by node returns
+    (LSsurf/lin_op.py:633-667), for the default mask_scale, a permuted one and keys written as booleans."""
+    from lssurf_b200.lin_op import lin_op
+    g = fd_grid([[0., 10.], [0., 20.]], [1., 2.], col_0=5)
+    op = lin_op(g, name='probe')
+    op.ind0 = g.col_0 + np.array([0, 3, 17, 120, 64])
+    op.N_eq = 5
+    partial = g.mask.copy()
+    partial[0, 0] = False                                # forces the sampling path; node 0 is masked
+    for ms in ({0: 10, 1: 1}, {1: 3.5, 0: 2.}, {True: 7., False: 9.}, {0: 4.}):
+        fast = op.mask_for_ind0(ms)
+        slow = op.mask_for_ind0(ms, mask=partial)
+        assert fast.dtype == float and np.array_equal(fast[1:], slow[1:])
+        assert slow[0] == ms.get(0, 0.0)
+    assert op.mask_for_ind0(None).dtype == bool and op.mask_for_ind0(None).all()

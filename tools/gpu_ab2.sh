@@ -3,6 +3,5 @@ show() { tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); s
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests -m gpu -x -q -k "variants_agree" > gpurun_out/ab2_test.log 2>&1; tail -15 gpurun_out/ab2_test.log
 B="timeout 200 python bench.py --steps 1 --warmup 1 --skip-e2e --no-cpu-baseline"
-LSS_N_PRODUCT=10 LSS_TMA_STAGES=2 LSS_STEP_KERNEL=2 $B 2>&1 | show tma2_tile
-LSS_N_PRODUCT=10 LSS_TMA_STAGES=3 LSS_STEP_KERNEL=2 $B 2>&1 | show tma3_tile
-LSS_N_PRODUCT=10 LSS_TMA_STAGES=4 LSS_STEP_KERNEL=2 $B 2>&1 | show tma4_tile
+LSS_N_PRODUCT=12 LSS_STEP_KERNEL=2 $B 2>&1 | show dictrows_tile
+LSS_N_PRODUCT=0 LSS_STEP_KERNEL=2 $B 2>&1 | show old_tile
