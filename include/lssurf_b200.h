@@ -141,7 +141,11 @@ int lss_spmv_planned(lss_spmv_plan_t *plan, int64_t n_rows, const int32_t *indpt
 
 /* Tuning knobs.  "spmv_variant": CTA shape of the CSR product kernel (index into a fixed table of
  * (threads, non-zeros per thread) pairs); affects speed only, never results.  "explicit_normal" (default 1):
- * lss_solver_create_blocks forms N = A^T W A explicitly (see lss_normal_create) instead of applying A twice. */
+ * lss_solver_create_blocks forms N = A^T W A explicitly (see lss_normal_create) instead of applying A twice.
+ * "normal_product" (default 0, 0..11): kernel of the CG product q = N p -- 0 nnz-tiled, 1/5/6 register rows, 7..9 padded
+ * chunks of 8, 10 TMA bulk-copy ring, 11 TMA ring + per-tile column dictionary (profiles/product_variants_r01.md).
+ * "step_kernel" (default 2): CG vector step -- 0 warp per preconditioner block, 1 thread per block row, 2 CTA tile.
+ * Both change speed and the order of floating-point sums only. */
 int lss_set_option(const char *name, int32_t value);
 
 /* ------------------------------------------------------------------ explicit normal matrix */
