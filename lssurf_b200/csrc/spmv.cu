@@ -815,7 +815,7 @@ spmv_tmad_build_kernel(int n_tiles, const int *__restrict__ tile_k, const int *_
     }
 }
 
-template <int BLOCK, int STAGES>
+template <int BLOCK, int STAGES, bool PIPE>
 __global__ void __launch_bounds__(BLOCK)
 spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, const int *__restrict__ indptr,
                  const unsigned short *__restrict__ lcol, const double *__restrict__ data, const int *__restrict__ dict,
@@ -823,11 +823,13 @@ spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, co
                  const int *__restrict__ tile_k, const double *__restrict__ stop, double *__restrict__ dot_slots) {
     extern __shared__ __align__(128) unsigned char tmad_ring[];
     static_assert(STAGES <= 8, "header layout");
-    // [0, 64) mbarriers | [64, 320) 8 descriptor ints per stage | xs: dcap doubles | STAGES x { cap doubles | cap u16 | dcap ints | RP ints }
+    static_assert(!PIPE || STAGES >= 3, "PIPE: tile i is reduced while the dictionary of tile i + 1 is gathered and tile i + 2 is in flight");
+    // [0, 64) mbarriers | [64, 320) 8 descriptor ints per stage | xs: 1 (2 with PIPE) x dcap doubles |
+    // STAGES x { cap doubles | cap u16 | dcap ints | RP ints }
     unsigned long long *full = reinterpret_cast<unsigned long long *>(tmad_ring);
     int *desc = reinterpret_cast<int *>(tmad_ring + 64);
     double *xs = reinterpret_cast<double *>(tmad_ring + TMA_HEAD);
-    unsigned char *stages = tmad_ring + TMA_HEAD + (size_t)dcap * 16;       // two x copies: tile i and tile i + 1
+    unsigned char *stages = tmad_ring + TMA_HEAD + (size_t)dcap * (PIPE ? 16 : 8);
     const size_t stage_bytes = (size_t)cap * 10 + (size_t)dcap * 4 + TMA_RP_CAP * 4;
     if (stop && *stop != 0.0) return;
     const uint64_t once = l2_policy_evict_first();
@@ -857,15 +859,14 @@ spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, co
         const unsigned b_val = (unsigned)((nk + 1) & ~1) * 8u, b_col = (unsigned)((nk + 7) & ~7) * 2u, b_rp = (unsigned)((nrp + 3) & ~3) * 4u;
         const unsigned b_dict = (unsigned)((d_nd + 3) & ~3) * 4u;
         int *dd = desc + stage * 8;
-        dd[0] = d_row0; dd[1] = d_row1; dd[2] = k0a; dd[3] = r0a; dd[4] = d_nd;
+        dd[0] = d_row0; dd[1] = d_row1; dd[2] = k0a; dd[3] = r0a; dd[4] = d_nd; dd[5] = d_k0 - k0a; dd[6] = nk;
         mbar_arrive_expect_tx(full + stage, b_val + b_col + b_rp + b_dict);
         if (b_val) bulk_g2s(base, data + k0a, b_val, full + stage, once);
         if (b_col) bulk_g2s(base + (size_t)cap * 8, lcol + k0a, b_col, full + stage, once);
         if (b_dict) bulk_g2s(base + (size_t)cap * 10, dict + (size_t)tile * dstride, b_dict, full + stage, once);
         bulk_g2s(base + (size_t)cap * 10 + (size_t)dcap * 4, indptr + r0a, b_rp, full + stage, once);
     };
-    static_assert(STAGES >= 3, "tile i is reduced while the dictionary of tile i + 1 is gathered and tile i + 2 is in flight");
-    constexpr int DREG = 8;                               // dictionary entries gathered per thread (dcap <= DREG * BLOCK)
+    constexpr int DREG = 8;                               // PIPE: dictionary entries gathered per thread (dcap <= DREG * BLOCK)
     const int t0 = blockIdx.x, dt = gridDim.x;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -875,14 +876,15 @@ spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, co
         }
         load_desc(t0 + (STAGES - 1) * dt);
     }
-    // x at the distinct columns of tile 0
-    if (t0 < n_tiles) {
-        while (!mbar_try_wait(full, 0u)) {}
-        const int *sdict = reinterpret_cast<const int *>(stages + (size_t)cap * 10);
-        const int nd = desc[4];
-        for (int j = threadIdx.x; j < nd; j += BLOCK) xs[j] = __ldg(x + sdict[j]);
+    if (PIPE) {                                           // x at the distinct columns of tile 0
+        if (t0 < n_tiles) {
+            while (!mbar_try_wait(full, 0u)) {}
+            const int *sdict = reinterpret_cast<const int *>(stages + (size_t)cap * 10);
+            const int nd = desc[4];
+            for (int j = threadIdx.x; j < nd; j += BLOCK) xs[j] = __ldg(x + sdict[j]);
+        }
+        __syncthreads();
     }
-    __syncthreads();
     double dot = 0.0;
     int i = 0;
     for (int t = t0; t < n_tiles; t += dt, ++i) {
@@ -891,27 +893,52 @@ spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, co
             issue(t + (STAGES - 1) * dt, (i + STAGES - 1) % STAGES);        // the stage tile i - 1 was reduced from
             load_desc(t + STAGES * dt);
         }
-        // gathers for the NEXT tile's dictionary are issued now and land while this tile's rows are reduced
-        double xn[DREG];
-        int nd_next = 0;
-        if (t + dt < n_tiles) {
-            const int sn = (i + 1) % STAGES;
-            while (!mbar_try_wait(full + sn, (unsigned)((i + 1) / STAGES) & 1u)) {}
-            const int *sdict = reinterpret_cast<const int *>(stages + (size_t)sn * stage_bytes + (size_t)cap * 10);
-            nd_next = desc[sn * 8 + 4];
-#pragma unroll
-            for (int u = 0; u < DREG; ++u) {
-                const int j = threadIdx.x + u * BLOCK;
-                xn[u] = j < nd_next ? __ldg(x + sdict[j]) : 0.0;
-            }
-        }
-        const double *xsc = xs + (size_t)(i & 1) * dcap;
-        const unsigned char *base = stages + (size_t)stage * stage_bytes;
-        const double *sval = reinterpret_cast<const double *>(base);
+        unsigned char *base = stages + (size_t)stage * stage_bytes;
+        double *sval = reinterpret_cast<double *>(base);
         const unsigned short *slc = reinterpret_cast<const unsigned short *>(base + (size_t)cap * 8);
         const int *srp = reinterpret_cast<const int *>(base + (size_t)cap * 10 + (size_t)dcap * 4);
         const int *dd = desc + stage * 8;
-        const int row0 = dd[0], row1 = dd[1], k0a = dd[2], rp_off = row0 - dd[3];
+        double xn[DREG];
+        int nd_next = 0;
+        const double *xsc = xs;
+        if (PIPE) {
+            // gathers for the NEXT tile's dictionary are issued now and land while this tile is reduced
+            if (t + dt < n_tiles) {
+                const int sn = (i + 1) % STAGES;
+                while (!mbar_try_wait(full + sn, (unsigned)((i + 1) / STAGES) & 1u)) {}
+                const int *sdict = reinterpret_cast<const int *>(stages + (size_t)sn * stage_bytes + (size_t)cap * 10);
+                nd_next = desc[sn * 8 + 4];
+#pragma unroll
+                for (int u = 0; u < DREG; ++u) {
+                    const int j = threadIdx.x + u * BLOCK;
+                    xn[u] = j < nd_next ? __ldg(x + sdict[j]) : 0.0;
+                }
+            }
+            xsc = xs + (size_t)(i & 1) * dcap;
+        } else {
+            while (!mbar_try_wait(full + stage, (unsigned)(i / STAGES) & 1u)) {}
+            const int *sdict = reinterpret_cast<const int *>(base + (size_t)cap * 10);
+            const int nd = dd[4];
+            for (int j = threadIdx.x; j < nd; j += BLOCK) xs[j] = __ldg(x + sdict[j]);     // x once per distinct column of the tile
+            __syncthreads();
+        }
+        const int row0 = dd[0], row1 = dd[1], k0a = dd[2], rp_off = row0 - dd[3], off0 = dd[5], span = dd[6];
+        // phase A, one thread per entry: products in place of the values (conflict-free strided shared-memory accesses)
+        {
+            int k = off0 + threadIdx.x;
+            for (; k + 3 * BLOCK < span; k += 4 * BLOCK) {                   // four independent load chains in flight
+                const int c0 = slc[k], c1 = slc[k + BLOCK], c2 = slc[k + 2 * BLOCK], c3 = slc[k + 3 * BLOCK];
+                const double v0 = sval[k], v1 = sval[k + BLOCK], v2 = sval[k + 2 * BLOCK], v3 = sval[k + 3 * BLOCK];
+                const double x0 = xsc[c0], x1 = xsc[c1], x2 = xsc[c2], x3 = xsc[c3];
+                sval[k] = v0 * x0;
+                sval[k + BLOCK] = v1 * x1;
+                sval[k + 2 * BLOCK] = v2 * x2;
+                sval[k + 3 * BLOCK] = v3 * x3;
+            }
+            for (; k < span; k += BLOCK) sval[k] *= xsc[slc[k]];
+        }
+        __syncthreads();
+        // phase B, g lanes per row: sums of the staged products
         const int nr = row1 - row0;
         int g = 1;
         while (g < 32 && nr * (2 * g) <= BLOCK) g <<= 1;
@@ -924,14 +951,11 @@ spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, co
             const double xr = (dot_slots && gl == 0) ? __ldg(x + row) : 0.0;
             double a0 = 0.0, a1 = 0.0;
             int k = b + gl;
-            for (; k + 3 * g < e; k += 4 * g) {
-                const int c0 = slc[k], c1 = slc[k + g], c2 = slc[k + 2 * g], c3 = slc[k + 3 * g];
-                a0 += sval[k] * xsc[c0];
-                a1 += sval[k + g] * xsc[c1];
-                a0 += sval[k + 2 * g] * xsc[c2];
-                a1 += sval[k + 3 * g] * xsc[c3];
+            for (; k + g < e; k += 2 * g) {
+                a0 += sval[k];
+                a1 += sval[k + g];
             }
-            for (; k < e; k += g) a0 += sval[k] * xsc[slc[k]];
+            if (k < e) a0 += sval[k];
             double acc = a0 + a1;
             const unsigned lane = lane_id();
             const unsigned gmask = g == 32 ? 0xffffffffu : (((1u << g) - 1u) << (lane & ~(unsigned)(g - 1)));
@@ -941,7 +965,7 @@ spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, co
                 dot += acc * xr;
             }
         }
-        if (nd_next > 0) {
+        if (PIPE && nd_next > 0) {
             double *xnext = xs + (size_t)((i + 1) & 1) * dcap;
 #pragma unroll
             for (int u = 0; u < DREG; ++u) {
@@ -949,7 +973,9 @@ spmv_tmad_kernel(int64_t n_rows, int n_tiles, int cap, int dcap, int dstride, co
                 if (j < nd_next) xnext[j] = xn[u];
             }
         }
-        __syncthreads();                                                   // stage i and its x copy are free, the next copy is complete
+        // the products were written through the generic proxy into a buffer the TMA engine (async proxy) refills next
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();                                                   // stage i (and its x copy) are free
     }
     if (dot_slots) {
         dot = warp_sum(dot);
@@ -983,12 +1009,14 @@ int spmv_tma_plan_add_dict(SpmvTmaPlan *plan, const int32_t *indices, int64_t nn
 int spmv_launch_tmad(const SpmvTmaPlan *plan, const int32_t *indptr, const double *data, const double *x, double *y, const double *stop,
                      cudaStream_t stream, int64_t *launches, double *dot_slots) {
     if (plan->n_rows <= 0) return LSS_OK;
-    int S = tma_stages();
-    if (S < 3) S = 3;
+    const int S = tma_stages();                  // 2: dictionary gather inside the tile's own iteration; 3..5: pipelined one tile ahead
+    const bool pipe = S >= 3;
     if (plan->dcap > 8 * TMA_BLOCK) return fail(LSS_EINVAL, "spmv_tmad_kernel: %d distinct columns in a tile", plan->dcap);
-    const size_t smem = TMA_HEAD + (size_t)plan->dcap * 16 + (size_t)S * ((size_t)plan->cap8 * 10 + (size_t)plan->dcap * 4 + TMA_RP_CAP * 4);
-    const void *fn = S == 3 ? (const void *)spmv_tmad_kernel<TMA_BLOCK, 3> : S == 4 ? (const void *)spmv_tmad_kernel<TMA_BLOCK, 4>
-                                                                                   : (const void *)spmv_tmad_kernel<TMA_BLOCK, 5>;
+    const size_t smem = TMA_HEAD + (size_t)plan->dcap * (pipe ? 16 : 8) +
+                        (size_t)S * ((size_t)plan->cap8 * 10 + (size_t)plan->dcap * 4 + TMA_RP_CAP * 4);
+    const void *fn = S == 2 ? (const void *)spmv_tmad_kernel<TMA_BLOCK, 2, false>
+                   : S == 3 ? (const void *)spmv_tmad_kernel<TMA_BLOCK, 3, true>
+                   : S == 4 ? (const void *)spmv_tmad_kernel<TMA_BLOCK, 4, true> : (const void *)spmv_tmad_kernel<TMA_BLOCK, 5, true>;
     static size_t attr_for = 0;
     static int per_sm = 0;
     if (attr_for != smem) {
