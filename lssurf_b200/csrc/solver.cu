@@ -950,14 +950,29 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
     if (s->bp && !getenv("LSS_NO_L2_WINDOW")) {
         // keep the block inverses (re-read every CG iteration, ~50 MB at 10^4 blocks) in the persisting part of L2
         // while the normal matrix streams through the rest
+        // device limits are queried once per process and the carve-out is only set when it changes: cudaGetDeviceProperties
+        // and cudaDeviceSetLimit cost up to 10^2 ms on some hosts, and a solver is created per smooth_fit call
+        static int prop_dev = -1, max_persist = 0, max_window = 0;
+        static size_t carve_set = 0;
         int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        if (cudaGetDevice(&dev) == cudaSuccess && dev != prop_dev) {
+            max_persist = max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            prop_dev = dev;
+            carve_set = 0;
+        }
+        if (max_persist > 0 && max_window > 0) {
             const size_t bytes = sizeof(float) * (size_t)s->bp->n_blocks * s->bp->bs * s->bp->bs;
             size_t carve = bytes + (8u << 20);
-            if (carve > (size_t)prop.persistingL2CacheMaxSize) carve = prop.persistingL2CacheMaxSize;
-            size_t win = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+            if (carve > (size_t)max_persist) carve = (size_t)max_persist;
+            size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+            bool carve_ok = carve_set == carve;
+            if (!carve_ok && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                carve_set = carve;
+                carve_ok = true;
+            }
+            if (carve_ok) {
                 cudaStreamAttrValue attr;
                 memset(&attr, 0, sizeof(attr));
                 attr.accessPolicyWindow.base_ptr = s->bp->inv;
