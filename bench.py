@@ -197,10 +197,11 @@ def run_b200(a):
         return L.smooth_fit(data=D, VERBOSE=False, dist=dist_arg, profile_spmv=profile, time_stages=stages, **kw)
 
     # ---- warm-up (device-resident steps, plus one host-input step)
+    S = None
     for _ in range(a.warmup):
-        fit(dev, False)
+        S = fit(dev, False)           # held like in the timed loops: the previous result is still alive while the next fit runs
     if not a.skip_e2e:
-        fit(host, False)
+        S = fit(host, False)
     barrier()
 
     sampler = ClockSampler(torch.cuda.current_device())
