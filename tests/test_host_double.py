@@ -1,0 +1,46 @@
+"""CPU tier: the package's HOST logic (lin_op bookkeeping, smooth_fit assembly, edit loop control flow, parse_model)
+driven end to end against the reference fixtures, with the C-ABI wrappers replaced by the test double in
+tests/host_double.py (oracle arithmetic on CPU tensors).  The kernels are NOT under test here -- that is the
+`-m gpu` tier's job, through the real library."""
+import numpy as np
+import pytest
+
+import lssurf_b200 as L
+from tests import host_double
+from tests.util import FIT_CASES, csr_digest, digest, load_case, rel_l2
+
+
+@pytest.fixture()
+def double():
+    with host_double.installed():
+        yield
+
+
+def make_data(pts):
+    return L.point_data.data().from_dict({k: np.array(v) for k, v in pts.items()})
+
+
+@pytest.mark.parametrize('name', FIT_CASES)
+def test_host_logic_against_reference_fixture(double, name):
+    fx, pts, kw = load_case(name)
+    fo = L.smooth_fit(data=make_data(pts), VERBOSE=False, return_fit_objects=True, **kw)
+    G, C = fo['G_data'].toCSR(), fo['Gc'].toCSR()
+    assert G.shape == tuple(fx['G_shape']) and C.shape == tuple(fx['C_shape'])
+    assert csr_digest(G) == str(fx['G_digest']) and csr_digest(C) == str(fx['C_digest'])
+    assert digest(np.asarray(fo['Ec'], dtype=float)) == str(fx['Ec_digest'])
+    want_toc = {s.split(':')[0]: int(s.split(':')[1]) for s in fx['toc_rows']}
+    assert {k: len(np.unique(v)) for k, v in fo['Gc'].TOC['rows'].items()} == want_toc
+    hist = []
+    S = L.smooth_fit(data=make_data(pts), VERBOSE=False, history=hist, sort_points=False, **kw)
+    assert len(S['timing']['pcg']) == int(fx['n_outer'])
+    for k, packed in enumerate(fx['masks']):
+        assert np.array_equal(hist[k]['mask_out'], packed), f'mask after iteration {k}'
+    assert np.array_equal(np.packbits(S['data'].three_sigma_edit), fx['in_TSE'])
+    assert rel_l2(S['m']['all'], fx['m0']) < 1e-8
+    assert np.max(np.abs(S['data'].z_est - fx['z_est'])) < 1e-6
+    assert S['m']['z0'].z0.shape == tuple(S['grids']['z0'].shape)
+
+
+def test_double_is_removed_afterwards():
+    from lssurf_b200 import _cabi
+    assert _cabi.interp_coo.__module__ == 'lssurf_b200._cabi' and _cabi.device.__module__ == 'lssurf_b200._cabi'
