@@ -24,11 +24,13 @@ import torch
 
 from . import _cabi
 from .bias_functions import assign_bias_ID, setup_bias_fit, parse_biases
-from .calc_sigma_extra import sigma_extra_device
+from .calc_sigma_extra import sigma_extra_device, sigma_extra_on_grid_device
 from .constraint_functions import setup_smoothness_constraints, build_reference_epoch_matrix
+from .data_slope_bias import data_slope_bias
 from .grid_functions import setup_grids, setup_averaging_ops
 from .lin_op import lin_op, DeviceCSR
 from .point_data import data as point_data, grid_data
+from .setup_sensor_grid_bias import setup_sensor_grid_bias, parse_sensor_bias_grids
 from .solver import NormalSolver, grid_structure
 
 REQUIRED = ('data', 'W', 'ctr', 'spacing', 'E_RMS')
@@ -50,8 +52,7 @@ DEFAULTS = {
     'time_stages': False, 'sort_points': True,
 }
 
-_UNSUPPORTED = ('compute_E', 'mask_file', 'mask_update_function', 'sigma_extra_bin_spacing', 'prior_args',
-                'prior_edge_args', 'data_slope_sensors', 'sensor_grid_bias_params', 'lagrangian_coords',
+_UNSUPPORTED = ('compute_E', 'mask_file', 'mask_update_function', 'prior_args', 'prior_edge_args', 'lagrangian_coords',
                 'constraint_scaling_maps', 'avg_masks', 'z0_average_scale', 'DEM_tol')
 
 
@@ -245,7 +246,15 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         st.mark('it:residual')
         if last_iteration:
             break
-        sigma_extra, se_values = sigma_extra_device(r_data, sigma, in_TSE_d, groups, comm, out=sigma_extra)
+        if args.get('sigma_extra_bin_spacing') is None:
+            sigma_extra, se_values = sigma_extra_device(r_data, sigma, in_TSE_d, groups, comm, out=sigma_extra)
+        else:
+            # spatially varying sigma_extra on overlapping bins (smooth_fit.py:154-158)
+            if comm is not None:
+                raise NotImplementedError('sigma_extra_bin_spacing is single-GPU only')
+            sigma_extra, se_values = sigma_extra_on_grid_device(
+                _field_dev(data, 'x'), _field_dev(data, 'y'), r_data, sigma, in_TSE_d, groups,
+                spacing=args['sigma_extra_bin_spacing'], sigma_extra_max=args.get('sigma_extra_max'))
         st.mark('it:sigma_extra')
         in_TSE_last = in_TSE_d
         in_TSE_d, est = _cabi.edit_mask(r_data, sigma, sigma_extra, 3.0, comm)
@@ -350,7 +359,7 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
         _bias_statistics(m['bias'], f['bias_ID'], r, tse, len(bias_model['bias_ID_dict']), dist)
     m['all'] = m0
     m['extent'] = np.concatenate((z0g.bds[1], z0g.bds[0]))
-    m['sensor_bias_grids'] = {}
+    m['sensor_bias_grids'] = parse_sensor_bias_grids(m0, G_data, grids)
     m['jitter_bias_grids'] = {}
     # constraint residuals: scaled (chi^2) and unscaled (RMS) per family
     n_cols = m0.size
@@ -535,7 +544,8 @@ def smooth_fit(**kwargs):
     order = None
     if (args['sort_points'] and os.environ.get('LSS_SORT_POINTS', '1') != '0' and not args['return_fit_objects'] and args['bias_nsigma_edit'] is None
             and args['bias_edit_vals'] is None and 'editable' not in data.fields and args['sigma_extra_masks'] is None
-            and n_all > 1):
+            and args['data_slope_sensors'] is None and args['sensor_grid_bias_params'] is None
+            and args['sigma_extra_bin_spacing'] is None and n_all > 1):
         order = _cabi.spatial_order(grids['z0'].as_struct(), grids['dz'].as_struct(), [y_d, x_d, t_d])
         y_d, x_d, t_d, z_d, s_d = (a[order].contiguous() for a in (y_d, x_d, t_d, z_d, s_d))
         tse_d = None if tse_d is None else tse_d[order].contiguous()
@@ -600,6 +610,26 @@ def smooth_fit(**kwargs):
             if tse_d is None:
                 tse_d = torch.ones(n_all, dtype=f64, device=z_d.device)
             tse_d[torch.isin(bias_id_d, _cabi.to_dev(np.asarray(bad, dtype=np.int32)))] = 0.
+    row_range = None if whole else (lo, hi)
+    # per-sensor planar slope biases (smooth_fit.py:515-525)
+    if args['data_slope_sensors'] is not None and len(args['data_slope_sensors']) > 0:
+        sensors = np.asarray(args['data_slope_sensors'])
+        args['data_slope_sensors'] = sensors[np.isin(sensors, np.asarray(data.sensor))]
+        if len(args['data_slope_sensors']) > 0:
+            bias_model['E_slope_bias'] = args['E_slope_bias']
+            G_slope_bias, Gc_slope_bias, bias_model = data_slope_bias(
+                data, bias_model, sensors=args['data_slope_sensors'], col_0=G_data.col_N, E_rms_bias=args['E_slope_bias'],
+                _row_range=row_range)
+            if G_slope_bias is not None:
+                G_data.add(G_slope_bias)
+                constraint_op_list.append(Gc_slope_bias)
+    # gridded per-sensor biases (smooth_fit.py:527-572); the jitter / stripe variants need a DEM file (GDAL): out of scope
+    if args['sensor_grid_bias_params'] is not None:
+        for params in args['sensor_grid_bias_params']:
+            if any('jitter' in k or 'stripe' in k for k in params):
+                raise NotImplementedError('jitter_* / stripe_* sensor grid biases need DEM files (GDAL): out of scope')
+            if len(params) and 'spacing' in params:
+                setup_sensor_grid_bias(data, grids, G_data, constraint_op_list, _row_range=row_range, **params)
     for op in constraint_op_list:
         if op.prior is None:
             op.prior = np.zeros_like(op.expected)

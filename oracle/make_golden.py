@@ -215,18 +215,102 @@ def case_lowlevel(write):
         np.savez_compressed(os.path.join(GOLDEN, 'lowlevel.npz'), **fx)
 
 
+def case_widened(name, pts, kw, write):
+    """Cases for the SURVEY section 8(f) rows (sensor grid bias, slope bias, gridded sigma_extra): the fixture is taken
+    from the reference run alone (the oracle does not restate these host-level compositions; the product is compared
+    with the reference outputs directly).  Same fixture keys as case_fit."""
+    print(f'== {name}: {pts["x"].size} points (reference outputs only)')
+    L = H.load()
+    import sparseqr
+    SF = H.smooth_fit_module()
+    D = H.point_data(**pts)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        fo = L.smooth_fit(data=D.copy(), VERBOSE=False, return_fit_objects=True, **kw)
+    G_ref, C_ref = fo['G_data'].toCSR(), fo['Gc'].toCSR()
+    trace, solves = [], []
+    orig_se, orig_grid, orig_solve = SF.calc_sigma_extra, SF.calc_sigma_extra_on_grid, sparseqr.solve
+
+    def tap(r, sigma, mask, sigma_extra_masks=None):
+        out = orig_se(r, sigma, mask, sigma_extra_masks)
+        trace.append(dict(mask_in=mask.copy(), sigma_extra=out.copy()))
+        return out
+
+    def tap_grid(x, y, r, sigma, mask, **k):
+        out = orig_grid(x, y, r, sigma, mask, **k)
+        trace.append(dict(mask_in=mask.copy(), sigma_extra=out.copy()))
+        return out
+
+    def count_solve(*a, **k):
+        solves.append(1)
+        return orig_solve(*a, **k)
+    SF.calc_sigma_extra, SF.calc_sigma_extra_on_grid, sparseqr.solve = tap, tap_grid, count_solve
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            out = L.smooth_fit(data=D.copy(), VERBOSE=False, **kw)
+    finally:
+        SF.calc_sigma_extra, SF.calc_sigma_extra_on_grid, sparseqr.solve = orig_se, orig_grid, orig_solve
+    tse_ref = np.asarray(out['data'].three_sigma_edit, dtype=bool)
+    n = int(out['valid_data'].size) if out['data'].size == out['valid_data'].size else int(out['data'].size)
+    masks = [np.packbits(trace[k + 1]['mask_in']) for k in range(len(trace) - 1)] + [np.packbits(tse_ref)]
+    m_ref = out['m']['all']
+    print(f'   G {G_ref.shape} nnz={G_ref.nnz}  Gc {C_ref.shape} nnz={C_ref.nnz}  solves={len(solves)}'
+          f'  in_TSE={int(tse_ref.sum())}  cols: {sorted(fo["G_data"].TOC["cols"])}')
+    if write:
+        fx = dict(G_digest=csr_digest(G_ref), C_digest=csr_digest(C_ref), Ec_digest=digest(np.asarray(fo['Ec'], dtype=float)),
+                  G_shape=np.array(G_ref.shape), C_shape=np.array(C_ref.shape), G_nnz=G_ref.nnz, C_nnz=C_ref.nnz, m0=m_ref,
+                  z_est=np.asarray(out['data'].z_est), in_TSE=np.packbits(tse_ref), n_data=n,
+                  sigma_extra=np.array([float(np.median(t['sigma_extra'])) for t in trace]),
+                  sigma_extra_final=np.asarray(out['data'].sigma_extra, dtype=float), masks=np.array(masks),
+                  n_outer=len(solves), kw=repr(kw),
+                  toc_rows=np.array([f'{k}:{len(np.unique(v))}' for k, v in fo['Gc'].TOC['rows'].items()]),
+                  toc_cols=np.array([f'{k}:{int(np.min(v))}:{int(np.max(v))}' for k, v in fo['G_data'].TOC['cols'].items()]))
+        for key, g in out['m'].get('sensor_bias_grids', {}).items():
+            fx['grid_' + key] = np.asarray(g.z)
+        sb = out['m'].get('slope_bias', {})
+        if sb:
+            fx['slope_bias'] = np.array([[k, v['slope_x'], v['slope_y']] for k, v in sb.items()], dtype=float)
+        fx.update({'in_' + k: v for k, v in pts.items()})
+        np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **fx)
+
+
+def widened_inputs():
+    """Seeded inputs of the two section-8(f) cases."""
+    pts, kw = S.icesat2_tracks(n=8000, width=1.2e4, seed=5, t_span=3.)
+    rng = np.random.default_rng(11)
+    sensor = (pts['BP'] == 2).astype(float)                 # one beam pair is a second 'sensor'
+    pts['sensor'] = sensor
+    pts['z'] = pts['z'] + sensor * (0.2 * np.sin(pts['x'] / 3000.) + 1e-5 * pts['x'] - 2e-5 * pts['y'])
+    kw_a = dict(kw, data_slope_sensors=np.array([1.]), E_slope_bias=0.01,
+                sensor_grid_bias_params=[{'sensor': 1., 'spacing': 3000., 'expected_rms': 0.2, 'expected_rms_grad2': 1e-7}])
+    ptu, kwu = S.uniform_3d(n=6000, width=1.2e4, seed=4)
+    ptu['z'] = ptu['z'] + rng.normal(0, 1., ptu['x'].size) * 0.3 * (ptu['x'] > 0)     # noisier eastern half
+    kw_b = dict(kwu, sigma_extra_bin_spacing=4000., sigma_extra_max=5.)
+    return (pts, kw_a), (ptu, kw_b)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--check', action='store_true')
+    ap.add_argument('--only-widened', action='store_true')
     a = ap.parse_args()
     write = not a.check
     os.makedirs(GOLDEN, exist_ok=True)
+    if a.only_widened:
+        (pa, ka), (pb, kb) = widened_inputs()
+        case_widened('tracks_sensor_slope', pa, ka, write)
+        case_widened('uniform_sigma_grid', pb, kb, write)
+        return
     case_lowlevel(write)
     case_fit('strip_nb', *S.notebook_strip(), write)
     case_fit('strip_outliers', *S.notebook_strip(outliers=True, seed=0), write)
     case_fit('uniform3d_small', *S.uniform_3d(n=6000, width=1.2e4, seed=1), write)
     pts, kw = S.icesat2_tracks(n=8000, width=1.2e4, seed=2, t_span=3.)
     case_fit('tracks_bias_small', pts, kw, write)
+    (pa, ka), (pb, kb) = widened_inputs()
+    case_widened('tracks_sensor_slope', pa, ka, write)
+    case_widened('uniform_sigma_grid', pb, kb, write)
     print('all cases: oracle == reference')
 
 

@@ -1,0 +1,54 @@
+"""GPU tier, SURVEY section 8(f) rows: per-sensor gridded bias, per-sensor slope bias and gridded sigma_extra, through the
+real C ABI, against fixtures taken from the UNMODIFIED reference (oracle/make_golden.py::case_widened).  Same bars as
+the hot path: CSR of G_data / Gc bit-exact, identical edit mask after every outer iteration, model within 1e-6."""
+import numpy as np
+import pytest
+
+from tests.test_host_double import check_widened_outputs
+from tests.util import WIDENED_CASES, csr_digest, digest, load_case, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def L():
+    import lssurf_b200
+    lssurf_b200._cabi.lib()          # fails loudly if the .so or the GPU is missing
+    return lssurf_b200
+
+
+@pytest.mark.parametrize('name', WIDENED_CASES)
+def test_widened_fit_against_reference_fixture(L, name):
+    fx, pts, kw = load_case(name)
+    D = L.point_data.data().from_dict(pts)
+    fo = L.smooth_fit(data=D.copy(), VERBOSE=False, return_fit_objects=True, **kw)
+    G, C = fo['G_data'].toCSR(), fo['Gc'].toCSR()
+    assert G.shape == tuple(fx['G_shape']) and C.shape == tuple(fx['C_shape'])
+    assert csr_digest(G) == str(fx['G_digest']) and csr_digest(C) == str(fx['C_digest'])
+    assert digest(np.asarray(fo['Ec'], dtype=float)) == str(fx['Ec_digest'])
+    want_toc = {s.split(':')[0]: int(s.split(':')[1]) for s in fx['toc_rows']}
+    assert {k: len(np.unique(v)) for k, v in fo['Gc'].TOC['rows'].items()} == want_toc
+    hist = []
+    S = L.smooth_fit(data=D.copy(), VERBOSE=False, history=hist, **kw)
+    assert len(S['timing']['pcg']) == int(fx['n_outer'])
+    for k, packed in enumerate(fx['masks']):
+        assert np.array_equal(hist[k]['mask_out'], packed), f'mask after iteration {k}'
+    assert np.array_equal(np.packbits(S['data'].three_sigma_edit), fx['in_TSE'])
+    assert rel_l2(S['m']['all'], fx['m0']) < 1e-6            # north-star tolerance
+    assert np.max(np.abs(S['data'].z_est - fx['z_est'])) < 1e-5
+    check_widened_outputs(fx, S)
+
+
+def test_calc_sigma_extra_on_grid_numpy_api(L):
+    """Reference signature, NumPy in / out: constant noise -> one value everywhere; a noisier half -> larger values there."""
+    from lssurf_b200.calc_sigma_extra import calc_sigma_extra_on_grid
+    rng = np.random.default_rng(3)
+    n = 40_000
+    x, y = rng.uniform(-2e4, 2e4, n), rng.uniform(-2e4, 2e4, n)
+    sigma = np.full(n, 0.1)
+    r = rng.normal(0, 0.1, n) + rng.normal(0, 0.5, n) * (x > 0)
+    se = calc_sigma_extra_on_grid(x, y, r, sigma, np.ones(n, dtype=bool), spacing=1.e4)
+    assert se.shape == (n,) and np.all(np.isfinite(se))
+    assert np.median(se[x > 1.2e4]) > 0.3 and np.median(se[x < -1.2e4]) < 0.05
+    capped = calc_sigma_extra_on_grid(x, y, r, sigma, np.ones(n, dtype=bool), spacing=1.e4, sigma_extra_max=0.2)
+    assert capped.max() <= 0.2 + 1e-12

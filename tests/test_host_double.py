@@ -7,7 +7,7 @@ import pytest
 
 import lssurf_b200 as L
 from tests import host_double
-from tests.util import FIT_CASES, csr_digest, digest, load_case, rel_l2
+from tests.util import FIT_CASES, WIDENED_CASES, csr_digest, digest, load_case, rel_l2
 
 
 @pytest.fixture()
@@ -20,7 +20,7 @@ def make_data(pts):
     return L.point_data.data().from_dict({k: np.array(v) for k, v in pts.items()})
 
 
-@pytest.mark.parametrize('name', FIT_CASES)
+@pytest.mark.parametrize('name', FIT_CASES + WIDENED_CASES)
 def test_host_logic_against_reference_fixture(double, name):
     fx, pts, kw = load_case(name)
     fo = L.smooth_fit(data=make_data(pts), VERBOSE=False, return_fit_objects=True, **kw)
@@ -39,6 +39,24 @@ def test_host_logic_against_reference_fixture(double, name):
     assert rel_l2(S['m']['all'], fx['m0']) < 1e-8
     assert np.max(np.abs(S['data'].z_est - fx['z_est'])) < 1e-6
     assert S['m']['z0'].z0.shape == tuple(S['grids']['z0'].shape)
+    check_widened_outputs(fx, S)
+
+
+def check_widened_outputs(fx, S):
+    """Outputs only the section-8(f) fixtures hold: column ranges, sensor bias grids, slope biases, per-point sigma_extra."""
+    if 'toc_cols' in fx.files:
+        want = {s.split(':')[0]: (int(s.split(':')[1]), int(s.split(':')[2])) for s in fx['toc_cols']}
+        got = {k: (int(np.min(v)), int(np.max(v))) for k, v in S['TOC']['cols'].items()}      # Gc's table; the fixture holds G_data's
+        assert all(got[k] == v for k, v in want.items() if k in got) and 'z0' in got
+    for key in (k for k in fx.files if k.startswith('grid_')):
+        got = S['m']['sensor_bias_grids'][key[5:]].z
+        assert got.shape == fx[key].shape and np.max(np.abs(got - fx[key])) < 1e-6 * max(1., np.max(np.abs(fx[key])))
+    if 'slope_bias' in fx.files:
+        for sensor, sx, sy in fx['slope_bias']:
+            got = S['m']['slope_bias'][sensor]
+            assert abs(got['slope_x'] - sx) < 1e-6 * max(1., abs(sx)) and abs(got['slope_y'] - sy) < 1e-6 * max(1., abs(sy))
+    if 'sigma_extra_final' in fx.files:
+        assert np.max(np.abs(S['data'].sigma_extra - fx['sigma_extra_final'])) < 2e-5
 
 
 def test_double_is_removed_afterwards():
