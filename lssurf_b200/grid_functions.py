@@ -100,9 +100,20 @@ def setup_grids(args):
     return grids, bds
 
 
+def sym_range(N, ni, offset=0.5):
+    """Indices spaced ``ni`` apart, symmetric about the centre of an ``N``-node axis (grid_functions.py:177-185)."""
+    out = np.arange((ni * offset), (N / 2), (ni))
+    if offset == 0:
+        out = np.r_[-out[-1:0:-1], out] + int(np.floor(N / 2))
+    else:
+        out = np.r_[-out[-1::-1], out] + int(np.floor(N / 2))
+    return np.floor(out[np.abs(out - N / 2) <= N / 2 - ni / 2]).astype(int)
+
+
 def setup_averaging_ops(grid, col_N, args, cell_area=None):
-    """Un-averaged dz/dt operators per lag (grid_functions.py:187-214, no 3-D mask).  The block
-    averages (``avg_scales``) are next-tier (SURVEY.md section 8(f) #2)."""
+    """dz/dt operators per lag and, with ``avg_scales``, block averages of dz and of dz/dt at each scale
+    (grid_functions.py:187-313, branch without a 3-D mask).  Every operator is a stencil template applied at the coarse
+    centres (``lss_stencil_coo``) scaled by the cell areas and normalised row by row (device gathers / one SpMV)."""
     ops = {}
     if args.get('dzdt_lags') is not None:
         for lag in args['dzdt_lags']:
@@ -111,6 +122,34 @@ def setup_averaging_ops(grid, col_N, args, cell_area=None):
             op.dst_grid.cell_area = grid.cell_area
             op.normalize_by_unit_product()
             ops[name] = op
-    if args.get('avg_scales'):
-        raise NotImplementedError('avg_scales block averages are next-tier (SURVEY.md section 8(f) #2)')
+    if not args.get('avg_scales') or args.get('dzdt_lags') is None:      # grid_functions.py:217-220
+        return ops
+    if getattr(grid, 'mask_3d', None) is not None:
+        raise NotImplementedError('averaging operators with a 3-D mask are outside the hot-path scope')
+    N_grid = [ctrs.size for ctrs in grid.ctrs]
+    for scale in args['avg_scales']:
+        this_name = 'avg_dz_' + str(int(scale)) + 'm'
+        kernel_N = np.floor(np.array([scale / dd for dd in grid.delta[0:2]] + [1])).astype(int)
+        # the largest scale is centred on the middle of the grid, the others on odd multiples of half their size
+        offset = 0 if scale == np.max(args['avg_scales']) else 0.5
+        grid_ctr_subs = [sym_range(N_grid[0], kernel_N[0], offset=offset), sym_range(N_grid[1], kernel_N[1], offset=offset),
+                         np.arange(grid.shape[2], dtype=int)]
+        sub0s = np.meshgrid(*grid_ctr_subs, indexing='ij')
+        op = lin_op(grid, name=this_name, col_N=col_N).sum_to_grid3(kernel_N + 1, sub0s=sub0s, taper=True)
+        op.apply_mask(mask=cell_area)
+        if cell_area is not None:
+            op.normalize_by_unit_product()
+        else:
+            op.v /= (kernel_N[0] * kernel_N[1])
+        op.dst_grid.cell_area = sum_cell_area(grid, op.dst_grid, sub0s=sub0s, cell_area_f=cell_area)
+        ops[this_name] = op
+        for lag in args['dzdt_lags']:
+            dz_name = 'avg_dzdt_' + str(int(scale)) + 'm' + '_lag' + str(lag)
+            op = lin_op(grid, name=this_name, col_N=col_N)
+            op.sum_to_grid3(kernel_N + 1, sub0s=sub0s, lag=lag, taper=True).apply_2d_mask(mask=cell_area)
+            if cell_area is not None:
+                op.normalize_by_unit_product(wt=2 / (lag * grid.delta[2]))
+            else:
+                op.v /= (kernel_N[0] * kernel_N[1])
+            ops[dz_name] = op
     return ops

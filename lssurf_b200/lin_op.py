@@ -491,6 +491,88 @@ class lin_op(object):
             out[sampled == key] = scale
         return out
 
+    def sum_to_grid3(self, kernel_size, sub0s=None, lag=None, taper=True, valid_equations_only=True, dims=None):
+        """Rows that add up the values around output grid points, optionally as a lagged time difference
+        (lin_op.py:404-488): a box (or edge-tapered box) template handed to ``diff_op`` at the centre nodes ``sub0s``;
+        the destination grid is then the coarse grid of those centres."""
+        kernel_size = np.asarray(kernel_size)
+        half_kernel = np.floor((kernel_size - 1) / 2).astype(int) if taper else np.floor(kernel_size / 2).astype(int)
+        if dims is None:
+            dims = range(len(self.grid.shape))
+        n_dims = len(dims)
+        if sub0s is None:
+            if taper:
+                if valid_equations_only:
+                    sub0s = np.meshgrid(*[np.arange(half_kernel[ii] + 1, self.grid.shape[ii], kernel_size[ii] - 1, dtype=int)
+                                          for ii in dims], indexing='ij')
+                else:
+                    sub0s = np.meshgrid(*[np.arange(0, self.grid.shape[ii] + 1, kernel_size[ii] - 1, dtype=int) for ii in dims],
+                                        indexing='ij')
+            else:
+                sub0s = np.meshgrid(*[np.arange(half_kernel[ii], self.grid.shape[ii], kernel_size[ii], dtype=int) for ii in dims],
+                                    indexing='ij')
+        ind0 = self.grid.global_ind(sub0s[0:n_dims])
+        if np.mod(kernel_size[0] / 2, 1) == 0:               # even kernel: centres fall between nodes
+            di, dj = np.meshgrid(np.arange(-half_kernel[0], half_kernel[0]), np.arange(-half_kernel[1], half_kernel[1]),
+                                 indexing='ij')
+            grid_shift = [-self.grid.delta[0] / 2, -self.grid.delta[1] / 2, 0][0:n_dims]
+        else:
+            di, dj = np.meshgrid(np.arange(-half_kernel[0], half_kernel[0] + 1), np.arange(-half_kernel[1], half_kernel[1] + 1),
+                                 indexing='ij')
+            grid_shift = [0, 0, 0][0:n_dims]
+        wt0 = np.ones(kernel_size[0:2], dtype=float)
+        if taper:
+            for ii in [0, -1]:
+                wt0[ii, :] /= 2
+                wt0[:, ii] /= 2
+        wt0 = wt0.ravel()
+        if lag is None:
+            delta_subs = [di.ravel(), dj.ravel(), np.zeros_like(di.ravel())]
+            wt = wt0
+            grid_shift = [0, 0, 0]
+        else:
+            delta_subs = [np.concatenate([di.ravel(), di.ravel()]), np.concatenate([dj.ravel(), dj.ravel()]),
+                          np.concatenate([np.zeros_like(di.ravel(), dtype=int), np.zeros_like(di.ravel(), dtype=int) + lag])]
+            wt = np.concatenate([-wt0, wt0]) / (lag * self.grid.delta[2])
+            grid_shift[2] = 0.5 * lag * self.grid.delta[2]
+        n_grid_dims = len(self.grid.shape)
+        self.diff_op(delta_subs[:n_grid_dims], wt.astype(float), which_nodes=ind0, valid_equations_only=valid_equations_only)
+        kernel_out = (np.maximum(1, kernel_size - 1) if taper else kernel_size)[:n_grid_dims]
+        self.update_dst_grid(grid_shift[:n_grid_dims], kernel_out)
+        return self
+
+    def apply_mask(self, mask=None, row_N=None, time_step_overlap=1):
+        """Multiply every entry by the mask value at its column's grid node (lin_op.py:693-732).  The reference walks
+        the CSR rows in Python; here the canonical CSR is formed on the device and its values are scaled by one gather.
+        Like the reference the operator is left as the flat triplets of that CSR (explicit zeros where the mask is 0)."""
+        if time_step_overlap > 1:
+            raise NotImplementedError('time_step_overlap > 1 belongs to the 3-D mask path (out of scope)')
+        if mask is None:
+            mask = self.grid.mask
+        return self._scale_by_mask(np.asarray(mask), self._csr_device(row_N=row_N, col_N=self.col_N))
+
+    def apply_2d_mask(self, mask=None):
+        """Same with a mask over the first two grid dimensions (lin_op.py:669-691)."""
+        if mask is None:
+            mask = self.grid.mask
+        mask = np.asarray(mask)
+        if mask.ndim != 2:
+            raise ValueError('apply_2d_mask needs a 2-D mask')
+        return self._scale_by_mask(mask, self._csr_device())
+
+    def _scale_by_mask(self, mask, csr):
+        shape = [int(n) for n in self.grid.shape]
+        if list(mask.shape) != shape[:mask.ndim]:
+            raise ValueError('mask shape %s does not match grid shape %s' % (mask.shape, tuple(shape)))
+        trailing = int(np.prod(shape[mask.ndim:])) if mask.ndim < len(shape) else 1
+        local = csr.indices.long() - int(self.grid.col_0)
+        m_d = _cabi.to_dev(np.ascontiguousarray(mask, dtype=float).ravel(), torch.float64)
+        counts = (csr.indptr[1:] - csr.indptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(csr.shape[0], device=counts.device, dtype=torch.int32), counts)
+        vals = csr.data * m_d[torch.div(local, trailing, rounding_mode='floor')]
+        self._set_device(rows.contiguous(), csr.indices.contiguous(), vals.contiguous())
+        return self
+
     def normalize_by_unit_product(self, wt=1):
         """Scale each row so that sum(|v|) == wt (lin_op.py:311-321)."""
         unit = lin_op(col_N=self.col_N)

@@ -462,8 +462,6 @@ def smooth_fit(**kwargs):
     for key in _UNSUPPORTED:
         if args[key]:
             raise NotImplementedError(f'smooth_fit keyword {key!r} is outside the GPU hot-path scope of lssurf_b200')
-    if args['avg_scales']:
-        raise NotImplementedError("smooth_fit keyword 'avg_scales' is next-tier (SURVEY.md section 8(f))")
     dist = args['dist']
     verbose = args['VERBOSE'] and (dist is None or dist.rank == 0)
     args['VERBOSE'] = verbose

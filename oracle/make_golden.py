@@ -33,6 +33,7 @@ from oracle import ref_harness as H        # noqa: E402
 from lssurf_b200 import synthetic as S     # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales']
 
 
 def digest(*arrays):
@@ -268,6 +269,11 @@ def case_widened(name, pts, kw, write):
                   toc_cols=np.array([f'{k}:{int(np.min(v))}:{int(np.max(v))}' for k, v in fo['G_data'].TOC['cols'].items()]))
         for key, g in out['m'].get('sensor_bias_grids', {}).items():
             fx['grid_' + key] = np.asarray(g.z)
+        for key, g in out['m'].items():                      # dz/dt and block-average grids (setup_averaging_ops)
+            if key.startswith(('avg_', 'dzdt_')):
+                fx['avgop_' + key] = np.asarray(getattr(g, key), dtype=float)
+                if getattr(g, 'cell_area', None) is not None:
+                    fx['avgarea_' + key] = np.asarray(g.cell_area, dtype=float)
         sb = out['m'].get('slope_bias', {})
         if sb:
             fx['slope_bias'] = np.array([[k, v['slope_x'], v['slope_y']] for k, v in sb.items()], dtype=float)
@@ -287,20 +293,23 @@ def widened_inputs():
     ptu, kwu = S.uniform_3d(n=6000, width=1.2e4, seed=4)
     ptu['z'] = ptu['z'] + rng.normal(0, 1., ptu['x'].size) * 0.3 * (ptu['x'] > 0)     # noisier eastern half
     kw_b = dict(kwu, sigma_extra_bin_spacing=4000., sigma_extra_max=5.)
-    return (pts, kw_a), (ptu, kw_b)
+    ptc, kwc = S.uniform_3d(n=6000, width=1.2e4, seed=6)
+    kw_c = dict(kwc, dzdt_lags=[1, 4], avg_scales=[2000., 4000.], max_iterations=3)
+    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--check', action='store_true')
     ap.add_argument('--only-widened', action='store_true')
+    ap.add_argument('--case', default=None)
     a = ap.parse_args()
     write = not a.check
     os.makedirs(GOLDEN, exist_ok=True)
     if a.only_widened:
-        (pa, ka), (pb, kb) = widened_inputs()
-        case_widened('tracks_sensor_slope', pa, ka, write)
-        case_widened('uniform_sigma_grid', pb, kb, write)
+        for name, (p_, k_) in zip(WIDENED, widened_inputs()):
+            if a.case in (None, name):
+                case_widened(name, p_, k_, write)
         return
     case_lowlevel(write)
     case_fit('strip_nb', *S.notebook_strip(), write)
@@ -308,9 +317,8 @@ def main():
     case_fit('uniform3d_small', *S.uniform_3d(n=6000, width=1.2e4, seed=1), write)
     pts, kw = S.icesat2_tracks(n=8000, width=1.2e4, seed=2, t_span=3.)
     case_fit('tracks_bias_small', pts, kw, write)
-    (pa, ka), (pb, kb) = widened_inputs()
-    case_widened('tracks_sensor_slope', pa, ka, write)
-    case_widened('uniform_sigma_grid', pb, kb, write)
+    for name, (p_, k_) in zip(WIDENED, widened_inputs()):
+        case_widened(name, p_, k_, write)
     print('all cases: oracle == reference')
 
 

@@ -55,6 +55,13 @@ def check_widened_outputs(fx, S):
         for sensor, sx, sy in fx['slope_bias']:
             got = S['m']['slope_bias'][sensor]
             assert abs(got['slope_x'] - sx) < 1e-6 * max(1., abs(sx)) and abs(got['slope_y'] - sy) < 1e-6 * max(1., abs(sy))
+    for key in (k for k in fx.files if k.startswith('avgop_')):       # dz/dt and block-average grids
+        name = key[6:]
+        got, want = np.asarray(getattr(S['m'][name], name)), fx[key]
+        assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.nanmax(np.abs(got - want)) < 1e-6 * max(1., np.nanmax(np.abs(want))), name
+        if 'avgarea_' + name in fx.files:
+            assert np.allclose(S['m'][name].cell_area, fx['avgarea_' + name], rtol=1e-12, atol=0), name
     if 'sigma_extra_final' in fx.files:
         assert np.max(np.abs(S['data'].sigma_extra - fx['sigma_extra_final'])) < 2e-5
 
