@@ -110,6 +110,24 @@ def sym_range(N, ni, offset=0.5):
     return np.floor(out[np.abs(out - N / 2) <= N / 2 - ni / 2]).astype(int)
 
 
+def setup_z0_avg(grids, col_N, args):
+    """Operator that averages z0 to ``z0_average_scale`` (grid_functions.py:187-209): tapered box sums centred every
+    kernel_N nodes (edge boxes truncated, not dropped), weighted by the z0 cell areas, rows normalised to unit sum."""
+    if 'z0_average_scale' not in args or args['z0_average_scale'] is None:
+        return {}
+    scale = args['z0_average_scale']
+    this_name = 'avg_z0_' + str(int(scale)) + 'm'
+    kernel_N = np.floor(np.array([scale / dd for dd in grids['z0'].delta[0:2]])).astype(int)
+    N_grid = [ctrs.size for ctrs in grids['z0'].ctrs]
+    grid_ctr_subs = [np.arange(0, N_grid[dim] + 1, kernel_N[dim]) for dim in [0, 1]]
+    sub0s = np.meshgrid(*grid_ctr_subs, indexing='ij')
+    op = lin_op(grids['z0'], name=this_name, col_N=col_N).sum_to_grid3(kernel_N + 1, sub0s=sub0s, taper=True,
+                                                                       valid_equations_only=False)
+    op.apply_mask(grids['z0'].cell_area)
+    op.normalize_by_unit_product()
+    return {this_name: op}
+
+
 def setup_averaging_ops(grid, col_N, args, cell_area=None):
     """dz/dt operators per lag and, with ``avg_scales``, block averages of dz and of dz/dt at each scale
     (grid_functions.py:187-313, branch without a 3-D mask).  Every operator is a stencil template applied at the coarse

@@ -27,7 +27,7 @@ from .bias_functions import assign_bias_ID, setup_bias_fit, parse_biases
 from .calc_sigma_extra import sigma_extra_device, sigma_extra_on_grid_device
 from .constraint_functions import setup_smoothness_constraints, build_reference_epoch_matrix
 from .data_slope_bias import data_slope_bias
-from .grid_functions import setup_grids, setup_averaging_ops
+from .grid_functions import setup_grids, setup_averaging_ops, setup_z0_avg
 from .lin_op import lin_op, DeviceCSR
 from .point_data import data as point_data, grid_data
 from .setup_sensor_grid_bias import setup_sensor_grid_bias, parse_sensor_bias_grids
@@ -53,7 +53,7 @@ DEFAULTS = {
 }
 
 _UNSUPPORTED = ('compute_E', 'mask_file', 'mask_update_function', 'prior_args', 'prior_edge_args', 'lagrangian_coords',
-                'constraint_scaling_maps', 'avg_masks', 'z0_average_scale', 'DEM_tol')
+                'constraint_scaling_maps', 'avg_masks', 'DEM_tol')
 
 
 class _Stages(object):
@@ -611,8 +611,12 @@ def smooth_fit(**kwargs):
     row_range = None if whole else (lo, hi)
     # per-sensor planar slope biases (smooth_fit.py:515-525)
     if args['data_slope_sensors'] is not None and len(args['data_slope_sensors']) > 0:
+        if args['bias_params'] is None:
+            # the reference fails at the very end here (parse_biases adds lists to None, bias_functions.py:131)
+            raise ValueError('data_slope_sensors needs bias_params (parse_biases reports the slopes with the biases)')
         sensors = np.asarray(args['data_slope_sensors'])
-        args['data_slope_sensors'] = sensors[np.isin(sensors, np.asarray(data.sensor))]
+        sensor_of = data.sensor
+        args['data_slope_sensors'] = sensors[np.isin(sensors, _cabi.to_host(sensor_of) if isinstance(sensor_of, torch.Tensor) else np.asarray(sensor_of))]
         if len(args['data_slope_sensors']) > 0:
             bias_model['E_slope_bias'] = args['E_slope_bias']
             G_slope_bias, Gc_slope_bias, bias_model = data_slope_bias(
@@ -695,6 +699,7 @@ def smooth_fit(**kwargs):
         data.assign({'sigma_extra': sigma_extra_all})
         data.assign({'z_est': np.reshape(z_est_all, data.shape)})
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
+        averaging_ops.update(setup_z0_avg(grids, grids['dz'].col_N, args))
         dev_fields = {'z': z_loc, 'sigma': s_loc, 'z_est': z_est_d, 'three_sigma_edit': tse_out_d, 'sigma_extra': se_d,
                       'bias_ID': None if bias_id_d is None else bias_id_d[lo:hi]}
         stages.mark('outputs_d2h')
@@ -703,6 +708,7 @@ def smooth_fit(**kwargs):
         stages.mark('parse_model')
     else:
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
+        averaging_ops.update(setup_z0_avg(grids, grids['dz'].col_N, args))
     stages.mark('epilogue')
     return {'m': m, 'E': E, 'data': data, 'grids': grids, 'valid_data': valid_data, 'TOC': Gc.TOC, 'R': R, 'RMS': RMS,
             'timing': timing, 'E_RMS': args['E_RMS'], 'dzdt_lags': args['dzdt_lags']}

@@ -294,7 +294,7 @@ def widened_inputs():
     ptu['z'] = ptu['z'] + rng.normal(0, 1., ptu['x'].size) * 0.3 * (ptu['x'] > 0)     # noisier eastern half
     kw_b = dict(kwu, sigma_extra_bin_spacing=4000., sigma_extra_max=5.)
     ptc, kwc = S.uniform_3d(n=6000, width=1.2e4, seed=6)
-    kw_c = dict(kwc, dzdt_lags=[1, 4], avg_scales=[2000., 4000.], max_iterations=3)
+    kw_c = dict(kwc, dzdt_lags=[1, 4], avg_scales=[2000., 4000.], z0_average_scale=2000., max_iterations=3)
     return (pts, kw_a), (ptu, kw_b), (ptc, kw_c)
 
 
