@@ -528,7 +528,9 @@ def smooth_fit(**kwargs):
     bias_id_d = None
     if args['bias_params'] is not None:
         if args['bias_filter'] is not None:
-            raise NotImplementedError('bias_filter is outside the GPU hot-path scope')
+            # the filter returns a container whose parameter fields define the bias groups (bias_functions.py:53-57)
+            data_filt = args['bias_filter'](data)
+            extra_d.update({p: _field_dev(data_filt, p) for p in args['bias_params']})
         bias_id_d, bias_model = _assign_bias_ID_device(extra_d, args['bias_params'], extra_d['sigma_corr'])
         data.assign({'bias_ID': _cabi.to_host(bias_id_d).astype(float)})
         if args['bias_nsigma_edit']:

@@ -69,3 +69,19 @@ def check_widened_outputs(fx, S):
 def test_double_is_removed_afterwards():
     from lssurf_b200 import _cabi
     assert _cabi.interp_coo.__module__ == 'lssurf_b200._cabi' and _cabi.device.__module__ == 'lssurf_b200._cabi'
+
+
+def test_bias_filter_groups_like_the_filtered_parameters(double):
+    """bias_filter (bias_functions.py:53-57): a filter that blanks `cycle` gives one bias per rgt -- the same operator
+    as a fit whose data carry a constant cycle."""
+    fx, pts, kw = load_case('tracks_bias_small')
+
+    def per_track(D):
+        out = D.copy()
+        out.assign({'cycle': np.zeros_like(np.asarray(D.cycle))})
+        return out
+    a = L.smooth_fit(data=make_data(pts), VERBOSE=False, return_fit_objects=True, bias_filter=per_track, **kw)
+    b = L.smooth_fit(data=make_data(dict(pts, cycle=np.zeros_like(pts['cycle']))), VERBOSE=False, return_fit_objects=True, **kw)
+    assert csr_digest(a['G_data'].toCSR()) == csr_digest(b['G_data'].toCSR())
+    assert csr_digest(a['Gc'].toCSR()) == csr_digest(b['Gc'].toCSR()) and np.array_equal(a['Ec'], b['Ec'])
+    assert a['G_data'].shape[1] < int(fx['G_shape'][1])          # fewer bias columns than one per (rgt, cycle)

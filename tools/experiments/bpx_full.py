@@ -94,7 +94,11 @@ for c in (2, 4, 8, 16, 32):
     Nc = (PT @ Ngg @ P).tocsr()
     levels[c] = (P, PT, batched_block_jacobi(Nc, cy, cx), Nc)
     print('level %2dx: %d coarse unknowns (%.0fs)' % (c, P.shape[1], time.time() - t0), flush=True)
-for use, exact in (((2, 4, 8, 16), 32), ((2, 4, 8), 16), ((2, 4, 8, 16), None)):
+configs = (((2, 4, 8, 16), 32), ((2, 4, 8), 16), ((2, 4, 8, 16), None))
+if len(sys.argv) > 3:       # e.g. "-:16;-:32;-:8;2,4:8"  (levels with block-Jacobi : level solved exactly)
+    configs = [(tuple(int(v) for v in a.split(',') if v != '-'), int(b) if b != '-' else None)
+               for a, b in (c.split(':') for c in sys.argv[3].split(';'))]
+for use, exact in configs:
     lus = None
     if exact:
         Pe, PeT = levels[exact][0], levels[exact][1]
