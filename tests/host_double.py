@@ -155,16 +155,27 @@ def csr_rmatvec(indptr, indices, data, u, n_rows, n_cols):
     return torch.from_numpy(A.T @ _np(u))
 
 
+def _all_ranks(a):
+    """Rows of every rank in rank order (what the library's histogram all-reduce makes the quantiles see)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return a
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, np.asarray(a))
+    return np.concatenate(parts)
+
+
 def rde(r, sigma=None, mask=None, s1=0.0, comm=None):
-    x = _np(r).astype(float)
+    x = _all_ranks(_np(r).astype(float))
     if sigma is not None:
-        x = x / np.sqrt(s1 * s1 + _np(sigma) ** 2)
+        x = x / np.sqrt(s1 * s1 + _all_ranks(_np(sigma)) ** 2)
     if mask is not None:
-        x = x[_np(mask).astype(bool)]
+        x = x[_all_ranks(_np(mask)).astype(bool)]
     return float(O.rde(x)), int(x.size)
 
 
 def sigma_extra(r, sigma, mask, comm=None):
+    r, sigma, mask = _all_ranks(_np(r)), _all_ranks(_np(sigma)), _all_ranks(_np(mask))
     m = _np(mask).astype(bool)
     if m.sum() < 10:
         return 0.0, 0
@@ -176,8 +187,9 @@ def edit_mask(r, sigma, sigma_extra_t, n_sigma=3.0, comm=None, out=None):
     rr, sg, se = _np(r), _np(sigma), _np(sigma_extra_t)
     ratio = np.abs(rr / np.sqrt(sg ** 2 + se ** 2))
     m = ratio < n_sigma
-    st = dict(count=int(m.sum()), min_sigma=float(sg[m].min()) if m.any() else np.inf,
-              near_threshold=int(np.sum(np.abs(ratio - n_sigma) < 1e-6)))
+    m_all, sg_all = _all_ranks(m), _all_ranks(sg)
+    st = dict(count=int(m_all.sum()), min_sigma=float(sg_all[m_all].min()) if m_all.any() else np.inf,
+              near_threshold=int(np.sum(np.abs(_all_ranks(ratio) - n_sigma) < 1e-6)))
     return torch.from_numpy(m.astype(np.uint8)), st
 
 
@@ -191,6 +203,8 @@ class NormalSolver(object):
     def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None, G_local=None, stages=None):
         self.G = O.csr_matrix(_np(G.indptr), _np(G.indices), _np(G.data), G.shape)
         self.C = O.csr_matrix(_np(Cn.indptr), _np(Cn.indices), _np(Cn.data), Cn.shape)
+        Gl = G if G_local is None else G_local              # replicated solve: residuals over this rank's rows only
+        self.G_local = O.csr_matrix(_np(Gl.indptr), _np(Gl.indices), _np(Gl.data), Gl.shape)
         self.z, self.prior, self.sigma, self.Ec = _np(z), _np(prior), _np(sigma), _np(Ec)
         self.n_cols = G.shape[1]
         free = np.ones(self.n_cols, dtype=bool)
@@ -219,7 +233,7 @@ class NormalSolver(object):
         return self.x
 
     def residual(self, x, z, out=None):
-        r = torch.from_numpy(self.z - self.G @ _np(x))
+        r = torch.from_numpy(_np(z) - self.G_local @ _np(x))
         if out is not None:
             out.copy_(r)
             return out
@@ -244,7 +258,16 @@ def installed():
     me = sys.modules[__name__]
     saved = {n: getattr(_cabi, n) for n in _CABI_NAMES}
     saved_solver = sf.NormalSolver
+    from lssurf_b200.parallel import DistContext
+    saved_reduce = DistContext.allreduce_sum
+
+    def allreduce_sum(self, t):            # the library's NCCL all-reduce, over the CPU process group
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.all_reduce(t)
+        return t
     try:
+        DistContext.allreduce_sum = allreduce_sum
         for n in _CABI_NAMES:
             setattr(_cabi, n, getattr(me, n))
         sf.NormalSolver = NormalSolver
@@ -253,3 +276,4 @@ def installed():
         for n, f in saved.items():
             setattr(_cabi, n, f)
         sf.NormalSolver = saved_solver
+        DistContext.allreduce_sum = saved_reduce
