@@ -298,6 +298,41 @@ def widened_inputs():
     return (pts, kw_a), (ptu, kw_b), (ptc, kw_c)
 
 
+def grid_bias_inputs():
+    rng = np.random.default_rng(21)
+    n = 3000
+    x, y, t = rng.uniform(-6e3, 6e3, n), rng.uniform(-6e3, 6e3, n), rng.uniform(-1.5, 1.5, n)
+    cov = np.sin(x / 2000.) + 0.1 * rng.standard_normal(n)
+    return dict(x=x, y=y, time=t, z=np.zeros(n), sigma=np.ones(n), cov=cov)
+
+
+def case_grid_bias(write):
+    """setup_grid_bias at the operator level (it is not reachable through smooth_fit in the reference either,
+    smooth_fit.py:488-490): G_data = z0 + dz interpolation rows + the covariate-scaled bias grid, curvature and magnitude
+    constraint rows.  Digests of the reference operators only."""
+    print('== grid_bias (reference outputs only)')
+    L = H.load()
+    pts = grid_bias_inputs()
+    D = H.point_data(**pts)
+    z0 = L.fd_grid([[-6e3, 6e3], [-6e3, 6e3]], [500., 500.], name='z0')
+    dz = L.fd_grid([[-6e3, 6e3], [-6e3, 6e3], [-1.5, 1.5]], [1000., 1000., 0.25], name='dz', col_0=z0.N_nodes)
+    grids = {'z0': z0, 'dz': dz}
+    G = L.lin_op(z0, name='interp_z').interp_mtx(D.coords()[0:2])
+    G.add(L.lin_op(dz, name='interp_dz').interp_mtx(D.coords()))
+    ops = []
+    bg = L.fd_grid([[-6e3, 6e3], [-6e3, 6e3]], [2000., 2000.], name='cov_bias')
+    L.setup_grid_bias(D, G, ops, grids, param='cov', grid=bg, expected_rms=0.1, expected_value=0., expected_rms_grad=1e-3)
+    Gc = L.lin_op(None, name='constraints').vstack(ops)
+    fx = dict(G_digest=csr_digest(G.toCSR()), G_shape=np.array(G.toCSR().shape), C_digest=csr_digest(Gc.toCSR()),
+              C_shape=np.array(Gc.toCSR().shape), expected=np.concatenate([op.expected for op in ops]),
+              names=np.array([op.name for op in ops]), col_range=np.array([bg.col_0, bg.col_N]),
+              toc_rows=np.array([f'{k}:{len(np.unique(v))}' for k, v in Gc.TOC['rows'].items()]))
+    fx.update({'in_' + k: v for k, v in pts.items()})
+    print(f'   G {tuple(fx["G_shape"])}  Gc {tuple(fx["C_shape"])}  ops {list(fx["names"])}  cols {fx["col_range"]}')
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN, 'grid_bias.npz'), **fx)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--check', action='store_true')
@@ -310,6 +345,8 @@ def main():
         for name, (p_, k_) in zip(WIDENED, widened_inputs()):
             if a.case in (None, name):
                 case_widened(name, p_, k_, write)
+        if a.case in (None, 'grid_bias'):
+            case_grid_bias(write)
         return
     case_lowlevel(write)
     case_fit('strip_nb', *S.notebook_strip(), write)
@@ -319,6 +356,7 @@ def main():
     case_fit('tracks_bias_small', pts, kw, write)
     for name, (p_, k_) in zip(WIDENED, widened_inputs()):
         case_widened(name, p_, k_, write)
+    case_grid_bias(write)
     print('all cases: oracle == reference')
 
 

@@ -69,3 +69,9 @@ def test_bias_filter_groups_like_the_filtered_parameters(L):
     assert csr_digest(a['G_data'].toCSR()) == csr_digest(b['G_data'].toCSR())
     assert csr_digest(a['Gc'].toCSR()) == csr_digest(b['Gc'].toCSR()) and np.array_equal(a['Ec'], b['Ec'])
     assert a['G_data'].shape[1] < int(fx['G_shape'][1])
+
+
+def test_setup_grid_bias_operators(L):
+    """setup_grid_bias (setup_grid_bias.py:4-43) at the operator level against the reference digests."""
+    from tests.test_host_double import check_grid_bias, grid_bias_operators
+    check_grid_bias(*grid_bias_operators(L))

@@ -2,12 +2,14 @@
 driven end to end against the reference fixtures, with the C-ABI wrappers replaced by the test double in
 tests/host_double.py (oracle arithmetic on CPU tensors).  The kernels are NOT under test here -- that is the
 `-m gpu` tier's job, through the real library."""
+import os
+
 import numpy as np
 import pytest
 
 import lssurf_b200 as L
 from tests import host_double
-from tests.util import FIT_CASES, WIDENED_CASES, csr_digest, digest, load_case, rel_l2
+from tests.util import FIT_CASES, GOLDEN, WIDENED_CASES, csr_digest, digest, load_case, rel_l2
 
 
 @pytest.fixture()
@@ -117,3 +119,34 @@ def test_two_rank_row_sharding_reproduces_the_fixture(name, tmp_path):
         assert np.max(np.abs(r['z_est'] - fx['z_est'])) < 1e-6 and np.nansum(r['count']) > 0
         assert r['n_edited'].sum() == int(np.unpackbits(fx['in_TSE'])[:int(fx['n_data'])].sum())
     assert np.array_equal(res[0]['m0'], res[1]['m0'])          # both ranks hold the same model, bit for bit
+
+
+def grid_bias_operators(Lp):
+    """The operator-level set-up of the grid_bias fixture (oracle/make_golden.py::case_grid_bias) with the package."""
+    fx = np.load(os.path.join(GOLDEN, 'grid_bias.npz'), allow_pickle=False)
+    pts = {k[3:]: fx[k] for k in fx.files if k.startswith('in_')}
+    D = Lp.point_data.data().from_dict(pts)
+    z0 = Lp.fd_grid([[-6e3, 6e3], [-6e3, 6e3]], [500., 500.], name='z0')
+    dz = Lp.fd_grid([[-6e3, 6e3], [-6e3, 6e3], [-1.5, 1.5]], [1000., 1000., 0.25], name='dz', col_0=z0.N_nodes)
+    grids = {'z0': z0, 'dz': dz}
+    G = Lp.lin_op(z0, name='interp_z').interp_mtx(D.coords()[0:2])
+    G.add(Lp.lin_op(dz, name='interp_dz').interp_mtx(D.coords()))
+    ops = []
+    bg = Lp.fd_grid([[-6e3, 6e3], [-6e3, 6e3]], [2000., 2000.], name='cov_bias')
+    Lp.setup_grid_bias(D, G, ops, grids, param='cov', grid=bg, expected_rms=0.1, expected_value=0., expected_rms_grad=1e-3)
+    Gc = Lp.lin_op(None, name='constraints').vstack(ops)
+    return fx, G, Gc, ops, bg, grids
+
+
+def check_grid_bias(fx, G, Gc, ops, bg, grids):
+    assert csr_digest(G.toCSR()) == str(fx['G_digest']) and G.toCSR().shape == tuple(fx['G_shape'])
+    assert csr_digest(Gc.toCSR()) == str(fx['C_digest']) and Gc.toCSR().shape == tuple(fx['C_shape'])
+    assert np.array_equal(np.concatenate([op.expected for op in ops]), fx['expected'])
+    assert [op.name for op in ops] == [str(s) for s in fx['names']] and [bg.col_0, bg.col_N] == fx['col_range'].tolist()
+    assert {k: len(np.unique(v)) for k, v in Gc.TOC['rows'].items()} == {s.split(':')[0]: int(s.split(':')[1]) for s in fx['toc_rows']}
+    assert grids['cov_bias'] is bg
+
+
+def test_setup_grid_bias_operators(double):
+    """setup_grid_bias (setup_grid_bias.py:4-43) at the operator level against the reference digests."""
+    check_grid_bias(*grid_bias_operators(L))
