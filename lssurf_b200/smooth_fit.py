@@ -265,7 +265,7 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
                                         mask_out=np.packbits(in_TSE_d.cpu().numpy()), count=est['count'],
                                         near_threshold=est['near_threshold'], pcg=dict(solver.last)))
         bias_editing_changed = _edit_by_bias(data, m0, in_TSE_d, iteration, bias_model, args)
-        recount = bias_editing_changed
+        recount = args['bias_nsigma_edit'] is not None      # flagged biases drop their data from the mask on every pass
         if editable is not None:
             in_TSE_d = torch.where(editable, in_TSE_d, in_TSE_original)
             recount = True
@@ -273,6 +273,8 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
             sel = in_TSE_d.bool()
             est['count'] = int(sel.sum().item())
             est['min_sigma'] = float(sigma[sel].min().item()) if est['count'] else np.inf
+            if args.get('history') is not None:  # the mask that goes into the next solve (after bias editing / `editable`)
+                args['history'][-1]['mask_next'] = np.packbits(in_TSE_d.cpu().numpy())
         if est['count'] == 0:
             if args['VERBOSE']:
                 print("Edited data empty, returning")

@@ -33,7 +33,7 @@ from oracle import ref_harness as H        # noqa: E402
 from lssurf_b200 import synthetic as S     # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales']
+WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable']
 
 
 def digest(*arrays):
@@ -295,7 +295,24 @@ def widened_inputs():
     kw_b = dict(kwu, sigma_extra_bin_spacing=4000., sigma_extra_max=5.)
     ptc, kwc = S.uniform_3d(n=6000, width=1.2e4, seed=6)
     kw_c = dict(kwc, dzdt_lags=[1, 4], avg_scales=[2000., 4000.], z0_average_scale=2000., max_iterations=3)
-    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c)
+    # edit-loop options: bias editing, pre-edited biases, relaxed last pass
+    ptd, kwd = S.icesat2_tracks(n=8000, width=1.2e4, seed=8, t_span=3.)
+    inside = np.abs(ptd['time']) < 1.4                     # the fit only sees the epochs inside t_span
+    ids = np.unique(np.c_[ptd['rgt'], ptd['cycle']][inside], axis=0)
+    big, pre = ids[len(ids) // 3], ids[len(ids) // 2]
+    ptd['z'] = ptd['z'] + 3.0 * ((ptd['rgt'] == big[0]) & (ptd['cycle'] == big[1]))        # one implausible bias
+    ptd['three_sigma_edit'] = np.ones_like(ptd['z'])       # bias_edit_vals writes into it (smooth_fit.py:508)
+    kw_d = dict(kwd, bias_nsigma_edit=6., bias_nsigma_iteration=1, sigma_extra_relax=True,
+                bias_edit_vals={'rgt': [float(pre[0])], 'cycle': [float(pre[1])]})
+    # sigma_extra per group, points that may not be edited, and an initial edit mask
+    pte, kwe = S.uniform_3d(n=6000, width=1.2e4, seed=9)
+    grp = (rng.random(pte['x'].size) < 0.4).astype(float)
+    pte['sensor'] = grp
+    pte['z'] = pte['z'] + grp * rng.normal(0, 0.4, grp.size)
+    pte['editable'] = (rng.random(grp.size) < 0.9).astype(float)
+    pte['three_sigma_edit'] = (rng.random(grp.size) < 0.98).astype(float)
+    kw_e = dict(kwe, sigma_extra_keys={'quiet': {'sensor': [0.]}, 'noisy': {'sensor': [1.]}})
+    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e)
 
 
 def grid_bias_inputs():
