@@ -75,3 +75,9 @@ def test_setup_grid_bias_operators(L):
     """setup_grid_bias (setup_grid_bias.py:4-43) at the operator level against the reference digests."""
     from tests.test_host_double import check_grid_bias, grid_bias_operators
     check_grid_bias(*grid_bias_operators(L))
+
+
+def test_iterate_fit_reference_signature(L):
+    """iterate_fit with the reference's own argument list (smooth_fit.py:100-101), NumPy in / NumPy out."""
+    from tests.test_host_double import iterate_fit_like_a_reference_caller
+    iterate_fit_like_a_reference_caller(L)

@@ -150,3 +150,35 @@ def check_grid_bias(fx, G, Gc, ops, bg, grids):
 def test_setup_grid_bias_operators(double):
     """setup_grid_bias (setup_grid_bias.py:4-43) at the operator level against the reference digests."""
     check_grid_bias(*grid_bias_operators(L))
+
+
+def iterate_fit_like_a_reference_caller(Lp, name='uniform3d_small'):
+    """The narrow seam (smooth_fit.py:100-210) driven the way the reference's smooth_fit drives it: operators from
+    return_fit_objects, NumPy rhs / TCinv / Ip_c built by the caller, NumPy arrays back."""
+    import scipy.sparse as sp
+    from lssurf_b200.constraint_functions import build_reference_epoch_matrix
+    from lssurf_b200.smooth_fit import DEFAULTS
+    fx, pts, kw = load_case(name)
+    fo = Lp.smooth_fit(data=Lp.point_data.data().from_dict(pts), VERBOSE=False, return_fit_objects=True, **kw)
+    data, G_data, Gc, grids = fo['data'], fo['G_data'], fo['Gc'], fo['grids']
+    N_eq = G_data.N_eq + Gc.N_eq
+    TCinv = sp.dia_matrix((1. / np.concatenate((fo['Ed'], fo['Ec'])), 0), shape=(N_eq, N_eq))       # smooth_fit.py:613
+    rhs = np.zeros(N_eq)
+    rhs[0:data.size] = data.z.ravel()                                                                # :616-617
+    Ip_c = build_reference_epoch_matrix(G_data, Gc, grids, kw['reference_epoch'])
+    args = dict(DEFAULTS, **kw)
+    args.update(VERBOSE=False)
+    timing = {}
+    m0, sigma_extra, in_TSE, rs_data = Lp.iterate_fit(data, None, rhs, TCinv, G_data, Gc, np.ones(data.size, dtype=bool), Ip_c,
+                                                      timing, args, grids)
+    assert isinstance(m0, np.ndarray) and isinstance(sigma_extra, np.ndarray) and in_TSE.dtype == bool
+    assert rs_data.shape == (data.size,) and sigma_extra.shape == (data.size,)
+    assert np.array_equal(np.packbits(in_TSE), fx['in_TSE']) and rel_l2(m0, fx['m0']) < 1e-6
+    assert abs(np.median(sigma_extra) - fx['sigma_extra'][-1]) < 2e-5
+    r = (data.z - G_data.toCSR().dot(m0)) / data.sigma                                               # :146-147
+    assert np.max(np.abs(rs_data - r)) < 1e-9
+    assert 'sparseqr_solve' in timing
+
+
+def test_iterate_fit_reference_signature(double):
+    iterate_fit_like_a_reference_caller(L)
