@@ -1,0 +1,137 @@
+"""Differential check of the package's HOST logic against the unmodified reference on small random configurations
+(build container only: needs /root/reference; the kernels are replaced by tests/host_double.py, so this exercises the
+Python mirror of the reference interface -- keyword handling, operator bookkeeping, edit-loop control flow).
+    python tools/diff_fuzz.py [n_cases=12] [seed=0]"""
+import os, sys, warnings
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as H
+from tests import host_double
+from tests.util import csr_digest
+import lssurf_b200 as L
+
+
+def one_case(rng, k):
+    n = int(rng.integers(300, 2500))
+    W = float(rng.choice([6e3, 8e3, 1.2e4]))
+    t_span = float(rng.choice([1., 2., 3.]))
+    x, y, t = rng.uniform(-W / 2 * 1.05, W / 2 * 1.05, n), rng.uniform(-W / 2, W / 2, n), rng.uniform(-t_span / 2 * 1.1, t_span / 2 * 1.1, n)
+    z = 30 * np.sin(x / 3000.) * np.cos(y / 2500.) + t * (1 + x / W) + rng.normal(0, 0.1, n)
+    bad = rng.random(n) < 0.05
+    z[bad] += rng.normal(0, 10, int(bad.sum()))
+    if rng.random() < 0.3:
+        z[rng.integers(0, n, 3)] = np.nan
+    pts = dict(x=x, y=y, time=t, z=z, sigma=rng.choice([0.1, 0.2], n))
+    E = {'d2z0_dx2': 0.02, 'dz0_dx': 50, 'd3z_dx2dt': 3e-4, 'd2z_dxdt': 0.75, 'd2z_dt2': 5000}
+    for key in list(E):
+        if rng.random() < 0.2:
+            E[key] = None if rng.random() < 0.5 else E[key] * 3
+    dt = float(rng.choice([0.25, 0.5]))
+    n_ep = int(round(t_span / dt))
+    kw = dict(W={'x': W, 'y': W, 't': t_span}, ctr={'x': 0., 'y': 0., 't': 0.},
+              spacing={'z0': float(rng.choice([250., 500.])), 'dz': 1000., 'dt': dt}, E_RMS=E,
+              reference_epoch=int(rng.integers(0, n_ep + 1)), max_iterations=int(rng.choice([1, 2, 4, 10])))
+    if rng.random() < 0.5:
+        pts.update(rgt=rng.integers(0, 6, n).astype(float), cycle=rng.integers(0, 3, n).astype(float), sigma_corr=np.full(n, 0.05))
+        if rng.random() < 0.3:
+            pts['cycle'][rng.integers(0, n, 5)] = np.nan
+        kw['bias_params'] = ['rgt', 'cycle']
+    if rng.random() < 0.3:
+        kw['dzdt_lags'] = [1, 2]
+    if rng.random() < 0.3:
+        kw['sigma_extra_relax'] = True
+    if rng.random() < 0.3:
+        kw['min_iterations'] = int(rng.integers(0, 4))
+        kw['converge_tol_dz'] = float(rng.choice([0.01, 0.05, 1.0]))
+    # SURVEY section 8(f) rows and edit-loop options
+    if rng.random() < 0.6:
+        pts['sensor'] = (rng.random(n) < 0.4).astype(float)
+        if rng.random() < 0.5:
+            kw['sensor_grid_bias_params'] = [{'sensor': 1., 'spacing': float(rng.choice([2000., 3000.])), 'expected_rms': 0.2,
+                                              'expected_rms_grad2': 1e-7}]
+        if 'bias_params' in kw and rng.random() < 0.5:
+            kw['data_slope_sensors'] = np.array([1.])
+        if rng.random() < 0.4:
+            kw['sigma_extra_keys'] = {'a': {'sensor': [0.]}, 'b': {'sensor': [1.]}}
+    if rng.random() < 0.3:
+        pts['editable'] = (rng.random(n) < 0.9).astype(float)
+    if rng.random() < 0.3:
+        pts['three_sigma_edit'] = (rng.random(n) < 0.97).astype(float)
+    if rng.random() < 0.3 and 'sigma_extra_keys' not in kw:
+        kw['sigma_extra_bin_spacing'] = float(rng.choice([2000., 4000.]))
+        if rng.random() < 0.5:
+            kw['sigma_extra_max'] = 1.0
+    if 'dzdt_lags' in kw and rng.random() < 0.6:
+        kw['avg_scales'] = [2000., 4000.] if rng.random() < 0.5 else [2000.]
+        if rng.random() < 0.5:
+            kw['z0_average_scale'] = 1000.
+    if 'bias_params' in kw and rng.random() < 0.3:
+        kw['bias_nsigma_edit'] = float(rng.choice([3., 6.]))
+        kw['bias_nsigma_iteration'] = int(rng.integers(0, 3))
+    return pts, kw
+
+
+def main():
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    R = H.load()
+    bad = 0
+    for k in range(n_cases):
+        pts, kw = one_case(rng, k)
+        tag = 'case %d: n=%d %s' % (k, pts['x'].size, {a: b for a, b in kw.items() if a not in ('W', 'ctr')})
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            try:
+                fo_r = R.smooth_fit(data=H.point_data(**pts), VERBOSE=False, return_fit_objects=True, **kw)
+                S_r = R.smooth_fit(data=H.point_data(**pts), VERBOSE=False, **kw)
+                err_r = None
+            except Exception as e:          # noqa: BLE001
+                err_r = type(e).__name__
+            with host_double.installed():
+                try:
+                    fo_p = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, return_fit_objects=True, **kw)
+                    S_p = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, sort_points=False, **kw)
+                    Gp, Cp = fo_p['G_data'].toCSR(), fo_p['Gc'].toCSR()
+                    err_p = None
+                except Exception as e:      # noqa: BLE001
+                    err_p = type(e).__name__
+        if err_r or err_p:
+            ok = err_r == err_p
+            print(('ok   ' if ok else 'DIFF ') + tag + '  errors: reference %s, package %s' % (err_r, err_p))
+            bad += not ok
+            continue
+        checks = dict(G=csr_digest(fo_r['G_data'].toCSR()) == csr_digest(Gp), Gc=csr_digest(fo_r['Gc'].toCSR()) == csr_digest(Cp),
+                      Ec=np.array_equal(np.asarray(fo_r['Ec'], dtype=float), np.asarray(fo_p['Ec'], dtype=float)),
+                      valid=np.array_equal(S_r['valid_data'], S_p['valid_data']),
+                      mask=np.array_equal(np.asarray(S_r['data'].three_sigma_edit, dtype=bool), np.asarray(S_p['data'].three_sigma_edit, dtype=bool)),
+                      m0=np.linalg.norm(S_r['m']['all'] - S_p['m']['all']) <= 1e-8 * np.linalg.norm(S_r['m']['all']),
+                      keys=set(S_r['m'].keys()) == set(S_p['m'].keys()),
+                      R=all(abs(S_r['R'][q] - S_p['R'][q]) <= 1e-6 * abs(S_r['R'][q]) + 1e-12 for q in S_r['R']) and set(S_r['R']) == set(S_p['R']),
+                      RMS=all(abs(S_r['RMS'][q] - S_p['RMS'][q]) <= 1e-6 * abs(S_r['RMS'][q]) + 1e-12 for q in S_r['RMS']))
+        for key in ('z0', 'dz'):
+            for f in ('count', 'misfit_rms', 'misfit_scaled_rms'):
+                a, b = getattr(S_r['m'][key], f), getattr(S_p['m'][key], f)
+                checks['%s.%s' % (key, f)] = np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a, b, rtol=1e-6, atol=1e-9, equal_nan=True)
+        for key in S_r['m']:
+            if key.startswith(('dzdt_', 'avg_')):
+                checks[key] = np.allclose(getattr(S_r['m'][key], key), getattr(S_p['m'][key], key), rtol=1e-6, atol=1e-9, equal_nan=True)
+        if 'bias' in S_r['m']:
+            for f in ('val', 'N_raw', 'N_edited', 'rms_data_raw', 'rms_data_edited', 'expected'):
+                checks['bias.' + f] = np.allclose(np.asarray(S_r['m']['bias'][f], dtype=float), np.asarray(S_p['m']['bias'][f], dtype=float),
+                                                  rtol=1e-6, atol=1e-8, equal_nan=True)
+        for key, gr in S_r['m'].get('sensor_bias_grids', {}).items():
+            checks['grid.' + key] = key in S_p['m']['sensor_bias_grids'] and np.allclose(gr.z, S_p['m']['sensor_bias_grids'][key].z, rtol=1e-6, atol=1e-8)
+        if S_r['m'].get('slope_bias'):
+            checks['slope'] = all(abs(v['slope_x'] - S_p['m']['slope_bias'][q]['slope_x']) < 1e-8 and
+                                  abs(v['slope_y'] - S_p['m']['slope_bias'][q]['slope_y']) < 1e-8 for q, v in S_r['m']['slope_bias'].items())
+        checks['sigma_extra'] = np.allclose(np.asarray(S_r['data'].sigma_extra, dtype=float), S_p['data'].sigma_extra, rtol=0, atol=2e-5)
+        failed = [c for c, v in checks.items() if not v]
+        print(('ok   ' if not failed else 'DIFF ') + tag + ('' if not failed else '  FAILED: %s' % failed))
+        bad += bool(failed)
+    print('%d of %d cases differ' % (bad, n_cases))
+    return bad
+
+
+if __name__ == '__main__':
+    sys.exit(1 if main() else 0)
