@@ -17,6 +17,35 @@ def L():
     return lssurf_b200
 
 
+def test_bias_filter_groups_like_the_filtered_parameters(L):
+    """bias_filter (bias_functions.py:53-57): a filter that blanks `cycle` gives one bias per rgt -- the same operator
+    as a fit whose data carry a constant cycle."""
+    fx, pts, kw = load_case('tracks_bias_small')
+
+    def per_track(D):
+        out = D.copy()
+        out.assign({'cycle': np.zeros_like(np.asarray(D.cycle))})
+        return out
+    a = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, return_fit_objects=True, bias_filter=per_track, **kw)
+    b = L.smooth_fit(data=L.point_data.data().from_dict(dict(pts, cycle=np.zeros_like(pts['cycle']))), VERBOSE=False,
+                     return_fit_objects=True, **kw)
+    assert csr_digest(a['G_data'].toCSR()) == csr_digest(b['G_data'].toCSR())
+    assert csr_digest(a['Gc'].toCSR()) == csr_digest(b['Gc'].toCSR()) and np.array_equal(a['Ec'], b['Ec'])
+    assert a['G_data'].shape[1] < int(fx['G_shape'][1])
+
+
+def test_setup_grid_bias_operators(L):
+    """setup_grid_bias (setup_grid_bias.py:4-43) at the operator level against the reference digests."""
+    from tests.test_host_double import check_grid_bias, grid_bias_operators
+    check_grid_bias(*grid_bias_operators(L))
+
+
+def test_iterate_fit_reference_signature(L):
+    """iterate_fit with the reference's own argument list (smooth_fit.py:100-101), NumPy in / NumPy out."""
+    from tests.test_host_double import iterate_fit_like_a_reference_caller
+    iterate_fit_like_a_reference_caller(L)
+
+
 @pytest.mark.parametrize('name', WIDENED_CASES)
 def test_widened_fit_against_reference_fixture(L, name):
     fx, pts, kw = load_case(name)
@@ -52,32 +81,3 @@ def test_calc_sigma_extra_on_grid_numpy_api(L):
     assert np.median(se[x > 1.2e4]) > 0.3 and np.median(se[x < -1.2e4]) < 0.05
     capped = calc_sigma_extra_on_grid(x, y, r, sigma, np.ones(n, dtype=bool), spacing=1.e4, sigma_extra_max=0.2)
     assert capped.max() <= 0.2 + 1e-12
-
-
-def test_bias_filter_groups_like_the_filtered_parameters(L):
-    """bias_filter (bias_functions.py:53-57): a filter that blanks `cycle` gives one bias per rgt -- the same operator
-    as a fit whose data carry a constant cycle."""
-    fx, pts, kw = load_case('tracks_bias_small')
-
-    def per_track(D):
-        out = D.copy()
-        out.assign({'cycle': np.zeros_like(np.asarray(D.cycle))})
-        return out
-    a = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, return_fit_objects=True, bias_filter=per_track, **kw)
-    b = L.smooth_fit(data=L.point_data.data().from_dict(dict(pts, cycle=np.zeros_like(pts['cycle']))), VERBOSE=False,
-                     return_fit_objects=True, **kw)
-    assert csr_digest(a['G_data'].toCSR()) == csr_digest(b['G_data'].toCSR())
-    assert csr_digest(a['Gc'].toCSR()) == csr_digest(b['Gc'].toCSR()) and np.array_equal(a['Ec'], b['Ec'])
-    assert a['G_data'].shape[1] < int(fx['G_shape'][1])
-
-
-def test_setup_grid_bias_operators(L):
-    """setup_grid_bias (setup_grid_bias.py:4-43) at the operator level against the reference digests."""
-    from tests.test_host_double import check_grid_bias, grid_bias_operators
-    check_grid_bias(*grid_bias_operators(L))
-
-
-def test_iterate_fit_reference_signature(L):
-    """iterate_fit with the reference's own argument list (smooth_fit.py:100-101), NumPy in / NumPy out."""
-    from tests.test_host_double import iterate_fit_like_a_reference_caller
-    iterate_fit_like_a_reference_caller(L)
