@@ -138,6 +138,13 @@ def to_dev(a, dtype=None):
     return t.contiguous()
 
 
+def true_div(t, s):
+    """``t / s`` for a Python scalar ``s`` with IEEE division on every element.  torch's CUDA ``tensor / scalar``
+    multiplies by the rounded reciprocal instead (last-bit differences from NumPy); a 0-dim device divisor takes the
+    exact path, which is what bit-exact parity with the reference's NumPy arithmetic needs."""
+    return torch.div(t, torch.tensor(s, dtype=t.dtype, device=t.device))
+
+
 class _PinnedPool(object):
     """Page-locked host blocks handed out as NumPy arrays and taken back when the array is garbage collected.
     Two blocks are created the first time a size is asked for: a caller that still holds the previous fit's outputs

@@ -58,7 +58,7 @@ def sigma_extra_on_grid_device(x, y, r, sigma, mask, group_masks=None, spacing=1
         L_avg = 2 * spacing
     half = L_avg / 2
     out, values = sigma_extra_device(r, sigma, mask, group_masks)
-    ix, iy = torch.round(x / spacing), torch.round(y / spacing)
+    ix, iy = torch.round(_cabi.true_div(x, float(spacing))), torch.round(_cabi.true_div(y, float(spacing)))
     ix0, iy0 = float(ix.min().item()), float(iy.min().item())
     ny = int(iy.max().item() - iy0) + 1
     keys = torch.unique(((ix - ix0) * ny + (iy - iy0)).to(torch.int64)).cpu().numpy()
@@ -75,7 +75,7 @@ def sigma_extra_on_grid_device(x, y, r, sigma, mask, group_masks=None, spacing=1
         this, _ = sigma_extra_device(r[idx].contiguous(), sigma[idx].contiguous(), m_sub, g_sub)
         if sigma_extra_max is not None:
             this = torch.clamp(this, max=sigma_extra_max)
-        W = (1 - dx[idx] / half) * (1 - dy[idx] / half)
+        W = (1 - _cabi.true_div(dx[idx], float(half))) * (1 - _cabi.true_div(dy[idx], float(half)))
         sum_W_sigma[idx] += W * this
         sum_W[idx] += W
     out = torch.where(sum_W > 0, sum_W_sigma / sum_W, out)

@@ -41,7 +41,7 @@ def data_slope_bias(data, bias_model, col_0=0, sensors=[], op_name='data_slope',
             delta = _cabi.to_dev(full[mine], torch.float64)
             rr.append(rows_d)
             cc.append(torch.full_like(rows_d, int(col_0 + d_col_1 * 2 + d_col_2)))
-            vv.append((delta - float(mean)) / rescale)
+            vv.append(_cabi.true_div(delta - float(mean), float(rescale)))
     G_bias = lin_op(col_0=col_0, col_N=col_N, name=op_name)
     G_bias._set_device(torch.cat(rr).contiguous(), torch.cat(cc).contiguous(), torch.cat(vv).contiguous())
     ii = np.arange(col_0, col_N, dtype=int)
