@@ -20,7 +20,8 @@ def setup_grid_bias(data, G_data, constraint_op_list, grids, name=None, param=No
     grid.col_0 = G_data.col_N
     grid.col_N = grid.col_0 + grid.N_nodes
     op = lin_op(grid=grid, name=name).interp_mtx(data.coords()[0:2])
-    scale = _cabi.to_dev(np.asarray(getattr(data, param), dtype=float), torch.float64)
+    field = getattr(data, param)                     # NumPy array, or a tensor when the caller keeps its fields on the device
+    scale = _cabi.to_dev(field if isinstance(field, torch.Tensor) else np.asarray(field, dtype=float), torch.float64)
     r, c, v = op._device('r'), op._device('c'), op._device('v')
     op._set_device(r, c, (v * scale[r.long()]).contiguous())
     G_data.add(op)
