@@ -58,7 +58,10 @@ def sigma_extra_on_grid_device(x, y, r, sigma, mask, group_masks=None, spacing=1
         L_avg = 2 * spacing
     half = L_avg / 2
     out, values = sigma_extra_device(r, sigma, mask, group_masks)
-    ix, iy = torch.round(_cabi.true_div(x, float(spacing))), torch.round(_cabi.true_div(y, float(spacing)))
+    # the reference rounds the COMPLEX quotient (x + 1j * y) / spacing (calc_sigma_extra.py:86); NumPy's complex division by
+    # a real divisor multiplies both parts by 1 / spacing, so the bin index is round(x * (1 / spacing)), not round(x / spacing)
+    inv_spacing = 1.0 / float(spacing)
+    ix, iy = torch.round(x * inv_spacing), torch.round(y * inv_spacing)
     ix0, iy0 = float(ix.min().item()), float(iy.min().item())
     ny = int(iy.max().item() - iy0) + 1
     keys = torch.unique(((ix - ix0) * ny + (iy - iy0)).to(torch.int64)).cpu().numpy()

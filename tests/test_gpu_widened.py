@@ -81,3 +81,13 @@ def test_calc_sigma_extra_on_grid_numpy_api(L):
     assert np.median(se[x > 1.2e4]) > 0.3 and np.median(se[x < -1.2e4]) < 0.05
     capped = calc_sigma_extra_on_grid(x, y, r, sigma, np.ones(n, dtype=bool), spacing=1.e4, sigma_extra_max=0.2)
     assert capped.max() <= 0.2 + 1e-12
+
+
+def test_true_div_is_ieee_division(L):
+    """`tensor / python_scalar` on CUDA multiplies by the rounded reciprocal; `_cabi.true_div` must give NumPy's bits
+    (data_slope_bias.py:47 divides by 1000, calc_sigma_extra.py:73-74 by the bin spacing)."""
+    rng = np.random.default_rng(11)
+    x = rng.normal(0, 3e4, 200_000)
+    for s in (1000., 1.e4, 3., 2.5e3):
+        got = L._cabi.to_host(L._cabi.true_div(L._cabi.to_dev(x), s))
+        assert np.array_equal(got, x / s)
