@@ -24,6 +24,21 @@ def _np(t):
     return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
+_I32, _I64, _F64, _U8 = torch.int32, torch.int64, torch.float64, torch.uint8
+
+
+def _arg(t, dtype, what):
+    """What the real wrappers demand of a pointer argument: `_cabi.ptr` asserts a contiguous tensor, and the C ABI reads
+    the memory with a fixed element type (include/lssurf_b200.h) -- a tensor of another dtype would be reinterpreted
+    silently on the GPU, so the double rejects it here."""
+    if t is None:
+        return None
+    assert isinstance(t, torch.Tensor), f'{what}: the C ABI takes device tensors, got {type(t).__name__}'
+    assert t.is_contiguous(), f'{what}: expected a contiguous tensor'
+    assert t.dtype == dtype, f'{what}: the C ABI reads {dtype}, got {t.dtype}'
+    return t
+
+
 def _geom(g):
     nd = int(g.ndim)
     return dict(name='', ndim=nd, shape=np.array([g.shape[d] for d in range(nd)], dtype=np.int64),
@@ -49,6 +64,8 @@ def to_host(t):
 
 def interp_coo(g, pts, row_0=0):
     go = _geom(g)
+    for p in pts[:go['ndim']]:
+        _arg(p, _F64, 'interp_coo pts')
     P = [_np(p).astype(float) for p in pts[:go['ndim']]]
     n, nc = P[0].size, 1 << go['ndim']
     ok = O.points_in_grid(go, P)
@@ -89,17 +106,21 @@ def stencil_coo(g, offsets, coeffs, row_0=0, valid_only=True):
 
 
 def coo_extent(rows, vals):
+    _arg(rows, _I32, 'coo_extent rows'), _arg(vals, _F64, 'coo_extent vals')
     r, v = _np(rows).ravel(), _np(vals).ravel()
     nz = v != 0
     return (int(r[nz].max()) if nz.any() else -1), int(nz.sum())
 
 
 def coo_to_csr(rows, cols, vals, n_rows, n_cols):
+    _arg(rows, _I32, 'coo_to_csr rows'), _arg(cols, _I32, 'coo_to_csr cols'), _arg(vals, _F64, 'coo_to_csr vals')
+    assert rows.numel() == cols.numel() == vals.numel()
     indptr, indices, data, _ = O.coo_to_csr(_np(rows), _np(cols), _np(vals), n_rows=int(n_rows), n_cols=int(n_cols))
     return torch.from_numpy(indptr), torch.from_numpy(indices), torch.from_numpy(data)
 
 
 def csr_transpose(indptr, indices, data, n_rows, n_cols):
+    _arg(indptr, _I32, 'csr_transpose indptr'), _arg(indices, _I32, 'csr_transpose indices'), _arg(data, _F64, 'csr_transpose data')
     T = O.csr_matrix(_np(indptr), _np(indices), _np(data), (n_rows, n_cols)).T.tocsr()
     T.sort_indices()
     return (torch.from_numpy(T.indptr.astype(np.int32)), torch.from_numpy(T.indices.astype(np.int32)),
@@ -107,6 +128,7 @@ def csr_transpose(indptr, indices, data, n_rows, n_cols):
 
 
 def dense_rank(x, nan_value=-9999.0, max_unique=1 << 20):
+    _arg(x, _F64, 'dense_rank x')
     a = _np(x).astype(float)
     a = np.where(np.isnan(a), nan_value, a)
     u, inv = np.unique(a, return_inverse=True)
@@ -114,6 +136,7 @@ def dense_rank(x, nan_value=-9999.0, max_unique=1 << 20):
 
 
 def group_median(ids, vals, n_groups):
+    _arg(ids, _I32, 'group_median ids'), _arg(vals, _F64, 'group_median vals')
     i, v = _np(ids).astype(np.int64), _np(vals).astype(float)
     out = np.full(int(n_groups), np.nan)
     for k in range(int(n_groups)):
@@ -124,6 +147,8 @@ def group_median(ids, vals, n_groups):
 
 
 def _spmv(indptr, indices, data, x, n_rows, mode, s):
+    _arg(indptr, _I32, 'spmv indptr'), _arg(indices, _I32, 'spmv indices'), _arg(data, _F64, 'spmv data')
+    _arg(x, _F64, 'spmv x'), _arg(s, _F64, 'spmv s')
     A = O.csr_matrix(_np(indptr), _np(indices), _np(data), (int(n_rows), int(_np(x).size)))
     y = A @ _np(x)
     if mode == 1:
@@ -134,6 +159,7 @@ def _spmv(indptr, indices, data, x, n_rows, mode, s):
 
 
 def spmv(indptr, indices, data, x, n_rows, n_cols, mode=0, s=None, out=None):
+    _arg(out, _F64, 'spmv out')
     y = torch.from_numpy(_spmv(indptr, indices, data, x, n_rows, mode, s))
     if out is not None:
         out.copy_(y)
@@ -151,6 +177,7 @@ def spmv_planned(plan, indptr, indices, data, x, n_rows, mode=0, s=None, out=Non
 
 
 def csr_rmatvec(indptr, indices, data, u, n_rows, n_cols):
+    _arg(indptr, _I32, 'rmatvec indptr'), _arg(indices, _I32, 'rmatvec indices'), _arg(data, _F64, 'rmatvec data'), _arg(u, _F64, 'rmatvec u')
     A = O.csr_matrix(_np(indptr), _np(indices), _np(data), (int(n_rows), int(n_cols)))
     return torch.from_numpy(A.T @ _np(u))
 
@@ -166,6 +193,7 @@ def _all_ranks(a):
 
 
 def rde(r, sigma=None, mask=None, s1=0.0, comm=None):
+    _arg(r, _F64, 'rde r'), _arg(sigma, _F64, 'rde sigma'), _arg(mask, _U8, 'rde mask')
     x = _all_ranks(_np(r).astype(float))
     if sigma is not None:
         x = x / np.sqrt(s1 * s1 + _all_ranks(_np(sigma)) ** 2)
@@ -175,6 +203,7 @@ def rde(r, sigma=None, mask=None, s1=0.0, comm=None):
 
 
 def sigma_extra(r, sigma, mask, comm=None):
+    _arg(r, _F64, 'sigma_extra r'), _arg(sigma, _F64, 'sigma_extra sigma'), _arg(mask, _U8, 'sigma_extra mask')
     r, sigma, mask = _all_ranks(_np(r)), _all_ranks(_np(sigma)), _all_ranks(_np(mask))
     m = _np(mask).astype(bool)
     if m.sum() < 10:
@@ -184,6 +213,7 @@ def sigma_extra(r, sigma, mask, comm=None):
 
 
 def edit_mask(r, sigma, sigma_extra_t, n_sigma=3.0, comm=None, out=None):
+    _arg(r, _F64, 'edit_mask r'), _arg(sigma, _F64, 'edit_mask sigma'), _arg(sigma_extra_t, _F64, 'edit_mask sigma_extra')
     rr, sg, se = _np(r), _np(sigma), _np(sigma_extra_t)
     ratio = np.abs(rr / np.sqrt(sg ** 2 + se ** 2))
     m = ratio < n_sigma
@@ -201,6 +231,10 @@ class NormalSolver(object):
     """Stand-in for the solver handle: same constructor / methods, direct CPU solve of the same weighted system."""
 
     def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None, G_local=None, stages=None):
+        for A in (G, Cn) + (() if G_local is None else (G_local,)):
+            _arg(A.indptr, _I32, 'solver indptr'), _arg(A.indices, _I32, 'solver indices'), _arg(A.data, _F64, 'solver data')
+        for v, what in ((z, 'z'), (prior, 'prior'), (sigma, 'sigma'), (Ec, 'Ec')):
+            _arg(v, _F64, 'solver ' + what)
         self.G = O.csr_matrix(_np(G.indptr), _np(G.indices), _np(G.data), G.shape)
         self.C = O.csr_matrix(_np(Cn.indptr), _np(Cn.indices), _np(Cn.data), Cn.shape)
         Gl = G if G_local is None else G_local              # replicated solve: residuals over this rank's rows only
@@ -215,6 +249,7 @@ class NormalSolver(object):
         self.x = torch.zeros(self.n_cols, dtype=torch.float64)
 
     def set_rows(self, in_TSE, sigma_extra=None):
+        _arg(in_TSE, _U8, 'data_weights mask'), _arg(sigma_extra, _F64, 'data_weights sigma_extra')
         self.rows = _np(in_TSE).astype(bool)
         self.E = self.sigma if sigma_extra is None else np.sqrt(self.sigma ** 2 + _np(sigma_extra) ** 2)
 
@@ -233,6 +268,7 @@ class NormalSolver(object):
         return self.x
 
     def residual(self, x, z, out=None):
+        _arg(x, _F64, 'residual x'), _arg(z, _F64, 'residual z'), _arg(out, _F64, 'residual out')
         r = torch.from_numpy(_np(z) - self.G_local @ _np(x))
         if out is not None:
             out.copy_(r)
@@ -260,6 +296,10 @@ def installed():
     saved_solver = sf.NormalSolver
     from lssurf_b200.parallel import DistContext
     saved_reduce = DistContext.allreduce_sum
+    saved_array = torch.Tensor.__array__
+
+    def no_implicit_numpy(self, *a, **k):  # a CUDA tensor cannot be handed to NumPy; make CPU tensors behave the same
+        raise TypeError("host double: implicit tensor -> NumPy conversion (fails on a CUDA tensor); use _cabi.to_host / .cpu()")
 
     def allreduce_sum(self, t):            # the library's NCCL all-reduce, over the CPU process group
         import torch.distributed as dist
@@ -268,6 +308,7 @@ def installed():
         return t
     try:
         DistContext.allreduce_sum = allreduce_sum
+        torch.Tensor.__array__ = no_implicit_numpy
         for n in _CABI_NAMES:
             setattr(_cabi, n, getattr(me, n))
         sf.NormalSolver = NormalSolver
@@ -277,3 +318,4 @@ def installed():
             setattr(_cabi, n, f)
         sf.NormalSolver = saved_solver
         DistContext.allreduce_sum = saved_reduce
+        torch.Tensor.__array__ = saved_array
