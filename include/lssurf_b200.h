@@ -228,6 +228,17 @@ int lss_solver_info(lss_solver_t *solver, int64_t *info_h);
  *     per CG iteration. */
 int lss_solver_set_structure(lss_solver_t *solver, int32_t n_blocks, const int32_t *block_ptr, const int32_t *block_cols,
                              int32_t max_block, int64_t elim_begin, int64_t elim_end);
+/* Optional coarse level for the block-Jacobi preconditioner (two-level, additive): M^-1 = M_BJ^-1 + P S_c^-1 P^T with
+ * S_c = P^T S P the Galerkin projection of the (Schur-complement) operator the CG runs on, formed densely on the device
+ * and inverted exactly (n_coarse <= 1024).  Call after lss_solver_set_structure with blocks, before
+ * lss_solver_set_weights; ignored by the forms without a block preconditioner.  P interpolates every fine column
+ * from at most 4 coarse unknowns: cp_idx[n_cols][4] (-1 = none) / cp_w[n_cols][4] (float); the same P transposed as
+ * CSR by coarse row: pt_ptr[n_coarse + 1], pt_col[nnz_p], pt_w[nnz_p] (entries of one row in a fixed order: the
+ * restriction is a deterministic gather).  All device arrays, copied.  refresh != 0: S_c is rebuilt with every
+ * lss_solver_set_weights; 0: built once from the first weights (still a valid preconditioner afterwards).
+ * The reference's direct QR solve (smooth_fit.py:142) has no counterpart; this only changes the iteration count. */
+int lss_solver_set_coarse(lss_solver_t *solver, int32_t n_coarse, const int32_t *cp_idx, const float *cp_w,
+                          const int32_t *pt_ptr, const int32_t *pt_col, const float *pt_w, int64_t nnz_p, int32_t refresh);
 /* Row weights w (length n_rows): 1/sigma^2 for selected data rows, 0 for edited rows, 1/E_c^2 for
  * constraint rows.  Recomputes the right-hand side A^T W b and the Jacobi diagonal. */
 int lss_solver_set_weights(lss_solver_t *solver, const double *w);

@@ -65,6 +65,7 @@ SIGNATURES = {
     'lss_solver_stats': [_vp, _pf64],
     'lss_solver_info': [_vp, _pi64],
     'lss_solver_set_structure': [_vp, _i32, _vp, _vp, _i32, _i64, _i64],
+    'lss_solver_set_coarse': [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32],
     'lss_normal_create': [C.POINTER(_vp), _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _pi64, _vp],
     'lss_normal_update': [_vp, _vp],
     'lss_normal_export': [_vp, _vp, _vp, _vp],

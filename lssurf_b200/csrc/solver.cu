@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "precond.cuh"
+#include "coarse.cuh"
 
 namespace lss {
 
@@ -694,6 +695,225 @@ static const void *step_tile_kernel_for(int bs) {
     }
 }
 
+// Two-level form of the tile step (step_kernel = 3, the default when a coarse space is attached, lss_solver_set_coarse):
+// z = M_BJ^-1 r + P S_c^-1 P^T r.  Phases, separated by grid barriers:
+//   B   as cg_step_tile_kernel: alpha, x, r, z_BJ (to z), partials of r . z_BJ
+//   C1  r_c = P^T r as a gather over P^T stored by coarse row (deterministic; every coarse row is split over `chunks` warps)
+//   C2  z_c = S_c^-1 r_c: one warp per coarse row of the dense inverse (a few MB, L2 resident), r_c . z_c partials
+//   D   r.z = r.z_BJ + r_c.z_c, beta, p = z_BJ + P z_c + beta p; q and the p.q slots cleared
+struct CoarseArgs {
+    int n_c, chunks;
+    const int *pt_ptr, *pt_col;
+    const float *pt_w;
+    const double *inv;
+    const int4 *cp_idx;
+    const float4 *cp_w;
+    double *rc_part, *zc_part;
+    int dbg;
+};
+
+template <int BS>
+__global__ void __launch_bounds__(VEC_BLOCK, STEP3_PER_SM)
+cg_step_ml_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots, const double *__restrict__ minv, double *__restrict__ p,
+                  double *__restrict__ x, const double *r_in, double *r_out, double *z,
+                  double *part, double *__restrict__ scal, int parity, int n_blocks, const int *__restrict__ bcols,
+                  const int *__restrict__ col_block, const float *__restrict__ binv, CoarseArgs ca) {
+    constexpr int NBLK = VEC_BLOCK / BS, ROWS = NBLK * BS;
+    __shared__ double sm[VEC_BLOCK / 32];
+    __shared__ double rs[ROWS], qs[ROWS];
+    __shared__ double cs[CS_MAX];
+    if (scal[S_DONE0 + parity] != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
+        return;
+    }
+    cgx::grid_group grid = cgx::this_grid();
+    const int64_t tid = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x, nth = (int64_t)gridDim.x * VEC_BLOCK;
+    static_assert(PQ_SLOTS == VEC_BLOCK, "one p.q slot per thread");
+    const double slot_v = pq_slots[threadIdx.x];
+    const double rz_old = scal[S_RZ0 + parity];
+    const int n_groups = (n_blocks + NBLK - 1) / NBLK;
+    const int bl = threadIdx.x / BS, l = threadIdx.x - bl * BS;
+    double alpha = 0.0, v = 0.0;
+    bool have_alpha = false;
+    auto get_alpha = [&]() {
+        double pq = block_sum(slot_v, sm);
+        if (threadIdx.x == 0) sm[0] = pq;
+        __syncthreads();
+        pq = sm[0];
+        __syncthreads();
+        alpha = pq > 0.0 ? rz_old / pq : 0.0;
+        have_alpha = true;
+    };
+    // ---- phase B
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int b = g * NBLK + bl;
+        const bool active = threadIdx.x < ROWS && b < n_blocks;
+        float sv[BS];
+        int c = -1;
+        if (active) {
+            const float *S = binv + (size_t)b * BS * BS + l;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) sv[j] = __ldg(S + j * BS);
+            c = __ldg(bcols + (size_t)b * BS + l);
+        } else {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) sv[j] = 0.f;
+        }
+        double r_own = 0.0, q_own = 0.0, p_own = 0.0, x_own = 0.0;
+        if (c >= 0) {
+            r_own = r_in[c];
+            q_own = q[c];
+            p_own = p[c];
+            x_own = x[c];
+        }
+        if (threadIdx.x < ROWS) {
+            rs[threadIdx.x] = r_own;
+            qs[threadIdx.x] = q_own;
+        }
+        __syncthreads();
+        double zr = 0.0, zq = 0.0;
+        const double *rb = rs + bl * BS, *qb = qs + bl * BS;
+        if (threadIdx.x < ROWS) {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+                const double sj = (double)sv[j];
+                zr += sj * rb[j];
+                zq += sj * qb[j];
+            }
+        }
+        if (!have_alpha) get_alpha();
+        else __syncthreads();
+        if (c >= 0) {
+            const double zl = zr - alpha * zq;
+            const double rl = r_own - alpha * q_own;
+            x[c] = x_own + alpha * p_own;
+            r_out[c] = rl;
+            z[c] = zl;
+            v += rl * zl;
+        }
+    }
+    if (!have_alpha) get_alpha();
+    for (int64_t i = tid; i < n; i += nth) {
+        if (col_block && col_block[i] >= 0) continue;
+        x[i] += alpha * p[i];
+        const double ri = r_in[i] - alpha * q[i];
+        r_out[i] = ri;
+        const double zi = minv[i] * ri;
+        z[i] = zi;
+        v += ri * zi;
+    }
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    grid.sync();
+    // ---- phase C1: partial restrictions
+    const int n_c = ca.n_c, chunks = ca.chunks;
+    {
+        const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5);
+        for (int w = warp; w < n_c * chunks && !(ca.dbg & 1); w += n_warps) {
+            const int m = w % n_c, ch = w / n_c;
+            const int kb = ca.pt_ptr[m], len = ca.pt_ptr[m + 1] - kb;
+            const int per = (len + chunks - 1) / chunks;
+            const int k0 = kb + ch * per, k1 = min(kb + len, k0 + per);
+            double acc = 0.0;
+            int k = k0 + (int)lane_id();
+            for (; k + 96 < k1; k += 128) {            // four independent gathers in flight per lane
+                const int c0 = __ldg(ca.pt_col + k), c1 = __ldg(ca.pt_col + k + 32), c2 = __ldg(ca.pt_col + k + 64), c3 = __ldg(ca.pt_col + k + 96);
+                const float w0 = __ldg(ca.pt_w + k), w1 = __ldg(ca.pt_w + k + 32), w2 = __ldg(ca.pt_w + k + 64), w3 = __ldg(ca.pt_w + k + 96);
+                const double r0 = r_out[c0], r1 = r_out[c1], r2 = r_out[c2], r3 = r_out[c3];
+                acc += ((double)w0 * r0 + (double)w1 * r1) + ((double)w2 * r2 + (double)w3 * r3);
+            }
+            for (; k < k1; k += 32) acc += (double)__ldg(ca.pt_w + k) * r_out[__ldg(ca.pt_col + k)];
+            acc = warp_sum(acc);
+            if (lane_id() == 0) ca.rc_part[(size_t)ch * n_c + m] = acc;
+        }
+    }
+    if (!(ca.dbg & 8)) grid.sync();
+    // ---- phase C2: z_c = S_c^-1 r_c, every row of the inverse split over `chunks` warps
+    for (int m = threadIdx.x; m < n_c; m += VEC_BLOCK) {
+        double a = 0.0;
+        for (int ch = 0; ch < chunks; ++ch) a += ca.rc_part[(size_t)ch * n_c + m];
+        cs[m] = a;
+    }
+    __syncthreads();
+    {
+        const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5);
+        const int per = ((n_c + chunks - 1) / chunks + 31) & ~31;
+        for (int w = warp; w < n_c * chunks && !(ca.dbg & 2); w += n_warps) {
+            const int m = w % n_c, ch = w / n_c;
+            const double *row = ca.inv + (size_t)m * n_c;
+            const int j0 = ch * per, j1 = min(n_c, j0 + per);
+            double acc = 0.0;
+            int j = j0 + (int)lane_id();
+            for (; j + 96 < j1; j += 128) {            // four independent loads in flight per lane
+                const double a0 = __ldg(row + j), a1 = __ldg(row + j + 32), a2 = __ldg(row + j + 64), a3 = __ldg(row + j + 96);
+                acc += (a0 * cs[j] + a1 * cs[j + 32]) + (a2 * cs[j + 64] + a3 * cs[j + 96]);
+            }
+            for (; j < j1; j += 32) acc += __ldg(row + j) * cs[j];
+            acc = warp_sum(acc);
+            if (lane_id() == 0) ca.zc_part[(size_t)ch * n_c + m] = acc;
+        }
+    }
+    if (!(ca.dbg & 8)) grid.sync();
+    // ---- phase D
+    double rz_new = sum_partials(part, (int)gridDim.x, sm);
+    double rczc = 0.0;
+    double zreg[(CS_MAX + VEC_BLOCK - 1) / VEC_BLOCK];
+#pragma unroll
+    for (int u = 0; u < (CS_MAX + VEC_BLOCK - 1) / VEC_BLOCK; ++u) {
+        const int m = threadIdx.x + u * VEC_BLOCK;
+        double a = 0.0;
+        if (m < n_c) {
+            for (int ch = 0; ch < chunks; ++ch) a += ca.zc_part[(size_t)ch * n_c + m];
+            rczc += cs[m] * a;
+        }
+        zreg[u] = a;
+    }
+    rczc = block_sum(rczc, sm);                 // identical in every CTA: same values, same order
+    if (threadIdx.x == 0) sm[0] = rczc;
+    __syncthreads();
+    rz_new += sm[0];
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < (CS_MAX + VEC_BLOCK - 1) / VEC_BLOCK; ++u) {
+        const int m = threadIdx.x + u * VEC_BLOCK;
+        if (m < n_c) cs[m] = zreg[u];
+    }
+    __syncthreads();
+    const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
+    for (int64_t i = tid; i < n; i += nth) {
+        double zi = z[i];
+        const int4 pi = __ldg(ca.cp_idx + i);
+        if (!(ca.dbg & 4) && (pi.x >= 0 || pi.y >= 0 || pi.z >= 0 || pi.w >= 0)) {
+            const float4 w = __ldg(ca.cp_w + i);
+            if (pi.x >= 0) zi += (double)w.x * cs[pi.x];
+            if (pi.y >= 0) zi += (double)w.y * cs[pi.y];
+            if (pi.z >= 0) zi += (double)w.z * cs[pi.z];
+            if (pi.w >= 0) zi += (double)w.w * cs[pi.w];
+        }
+        p[i] = zi + beta * p[i];
+        q[i] = 0.0;
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;
+        if (threadIdx.x == 0) {
+            scal[S_RZ0 + (parity ^ 1)] = rz_new;
+            scal[S_RZ_LAST] = rz_new;
+            const double it = scal[S_ITERS] + 1.0;
+            scal[S_ITERS] = it;
+            scal[S_DONE0 + (parity ^ 1)] = (rz_new <= scal[S_TOL2] || it >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+        }
+    }
+}
+
+static const void *step_ml_kernel_for(int bs) {
+    switch (bs) {
+        case 12: return (const void *)cg_step_ml_kernel<12>;
+        case 24: return (const void *)cg_step_ml_kernel<24>;
+        case 36: return (const void *)cg_step_ml_kernel<36>;
+        default: return nullptr;
+    }
+}
+
 __global__ void __launch_bounds__(VEC_BLOCK)
 mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) out[i] = a[i] * b[i];
@@ -775,6 +995,10 @@ struct lss_solver {
     int step_stages;         // shared-memory stages per warp for the block inverses
     size_t step_smem;
     bool l2_window;          // an L2 persisting window on the preconditioner blocks is installed on the stream
+    lss::CoarseSpace *cs;    // coarse level of the two-level preconditioner (lss_solver_set_coarse); null: block-Jacobi alone
+    int cs_refresh;          // 1: S_c rebuilt with every weight change, 0: built with the first weights of the solver only
+    bool cs_built;
+    int step_ml_grid;
 };
 
 
@@ -804,6 +1028,7 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
         cudaGetLastError();
     }
     if (s->bp) lss::block_precond_destroy(s->bp);
+    if (s->cs) lss::coarse_destroy(s->cs);
     if (s->einv) cudaFreeAsync(s->einv, s->stream);
     if (s->eraw) cudaFreeAsync(s->eraw, s->stream);
     if (s->z) cudaFreeAsync(s->z, s->stream);
@@ -1108,9 +1333,30 @@ static int elim_slave(lss_solver *s, double *v, const double *c, const double *s
 
 // z = M^-1 r for the structured form
 static int apply_precond(lss_solver *s, const double *r, double *z) {
-    if (s->bp) return block_precond_apply(s->bp, s->n_cols, r, s->minv, z, s->stream);
+    if (s->bp) {
+        LSS_TRY(block_precond_apply(s->bp, s->n_cols, r, s->minv, z, s->stream));
+        if (s->cs && s->cs->ready) LSS_TRY(coarse_apply_add(s->cs, r, z));
+        return LSS_OK;
+    }
     mul_kernel<<<VEC_GRID, VEC_BLOCK, 0, s->stream>>>(s->n_cols, s->minv, r, z);
     LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_set_coarse(lss_solver_t *s, int32_t n_coarse, const int32_t *cp_idx, const float *cp_w, const int32_t *pt_ptr,
+                                     const int32_t *pt_col, const float *pt_w, int64_t nnz_p, int32_t refresh) {
+    if (!s) return fail(LSS_EINVAL, "solver_set_coarse: null solver");
+    if (!s->nm || !s->bp || s->step_rows != 2) return LSS_OK;     // needs the explicit-normal form with the tile step kernel
+    if (s->cs) { lss::coarse_destroy(s->cs); s->cs = nullptr; }
+    LSS_TRY(coarse_create(&s->cs, s->n_cols, n_coarse, cp_idx, cp_w, pt_ptr, pt_col, pt_w, nnz_p, (int)(s->e1 - s->e0), s->stream));
+    int per_sm = 0;
+    LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_ml_kernel_for(s->bp->bs), VEC_BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > STEP3_PER_SM) per_sm = STEP3_PER_SM;
+    s->step_ml_grid = kSMs * per_sm;
+    s->cs_refresh = refresh;
+    s->cs_built = false;
+    s->have_weights = false;
     return LSS_OK;
 }
 
@@ -1158,6 +1404,14 @@ extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
         if (s->e1 > s->e0) {
             elim_setup_kernel<<<ceil_div(s->e1 - s->e0, 256), 256, 0, st>>>(s->e0, s->e1, s->diag, s->einv, s->minv);
             LSS_LAUNCH_CHECK();
+        }
+        if (s->cs && s->bp && (s->cs_refresh || !s->cs_built)) {
+            // Galerkin coarse operator of the Schur complement for the current weights, inverted densely
+            const int64_t rows = (s->e1 > s->e0 && s->e1 == s->n_cols) ? s->e0 : s->n_cols;
+            LSS_TRY(coarse_factor(s->cs, rows, s->nm->indptr, s->nm->indices, s->nm->data, s->e0, s->e1, s->einv, s->comm));
+            s->cs_built = true;
+        }
+        if (s->e1 > s->e0) {
             LSS_CUDA(cudaMemsetAsync(s->p, 0, sizeof(double) * n, st));
             LSS_TRY(elim_slave(s, s->p, s->g, nullptr));
             LSS_TRY(normal_apply(s->nm, s->p, s->buf, nullptr, nullptr));
@@ -1247,7 +1501,22 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
                 const float *binv = s->bp ? s->bp->inv : nullptr;
                 double *slots = s->buf + n;
                 int n_stage = s->step_stages;
-                if (s->step_rows == 2) {
+                if (s->step_rows == 2 && s->cs && s->cs->ready) {
+                    const double *r_in = parity ? s->r2 : s->r;
+                    double *r_out = parity ? s->r : s->r2;
+                    lss::CoarseSpace *c = s->cs;
+                    CoarseArgs ca;
+                    ca.n_c = c->n_c;
+                    ca.chunks = (s->step_ml_grid * (VEC_BLOCK / 32)) / c->n_c;
+                    if (ca.chunks < 1) ca.chunks = 1;
+                    if (ca.chunks > CS_CHUNKS_MAX) ca.chunks = CS_CHUNKS_MAX;
+                    ca.pt_ptr = c->pt_ptr; ca.pt_col = c->pt_col; ca.pt_w = c->pt_w; ca.inv = c->inv;
+                    ca.cp_idx = reinterpret_cast<const int4 *>(c->cp_idx); ca.cp_w = reinterpret_cast<const float4 *>(c->cp_w);
+                    ca.rc_part = c->rc_part; ca.zc_part = c->zc_part;
+                    { static int dbg = -1; if (dbg < 0) { const char *e = getenv("LSS_ML_DEBUG"); dbg = e ? atoi(e) : 0; } ca.dbg = dbg; }
+                    void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &r_in, &r_out, &zv, &part, &scal, &par, &nb, &bcols, &cblk, &binv, &ca};
+                    LSS_CUDA(cudaLaunchCooperativeKernel(step_ml_kernel_for(bs), dim3(s->step_ml_grid), dim3(VEC_BLOCK), args, 0, st));
+                } else if (s->step_rows == 2) {
                     const double *r_in = parity ? s->r2 : s->r;
                     double *r_out = parity ? s->r : s->r2;
                     void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &r_in, &r_out, &zv, &part, &scal, &par, &nb, &bcols, &cblk, &binv};

@@ -31,7 +31,7 @@ from .grid_functions import setup_grids, setup_averaging_ops, setup_z0_avg
 from .lin_op import lin_op, DeviceCSR
 from .point_data import data as point_data, grid_data
 from .setup_sensor_grid_bias import setup_sensor_grid_bias, parse_sensor_bias_grids
-from .solver import NormalSolver, grid_structure
+from .solver import NormalSolver, grid_structure, coarse_structure
 
 REQUIRED = ('data', 'W', 'ctr', 'spacing', 'E_RMS')
 
@@ -174,6 +174,14 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
     st = _Stages(bool(args.get('time_stages')), timing.setdefault('stages', {}))
     st.mark('it:prep')
     structure = grid_structure(grids, fixed_cols, bias_cols=G_data.TOC['cols'].get('data_bias')) if isinstance(grids, dict) else None
+    if structure is not None and 'block_ptr' in structure and os.environ.get('LSS_COARSE', '1') != '0':
+        # two-level preconditioner: exact solve on a coarse bilinear space on top of block-Jacobi (pays off once the
+        # domain is many dz cells across; LSS_COARSE_MIN_BLOCKS moves the threshold, LSS_COARSE=0 switches it off)
+        if structure['block_ptr'].size - 1 >= int(os.environ.get('LSS_COARSE_MIN_BLOCKS', '2000')):
+            cs = coarse_structure(grids, fixed_cols, n_cols)
+            if cs is not None:
+                structure['coarse'] = cs
+                structure['coarse_refresh'] = int(os.environ.get('LSS_COARSE_REFRESH', '0'))
     if replicate:
         # replicated solve: every rank gets all assembled rows once and runs the same PCG with no collective inside the
         # iteration; per-point work (residuals, sigma_extra, edit masks) stays on the rank's own rows

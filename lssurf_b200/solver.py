@@ -98,6 +98,74 @@ def grid_structure(grids, fixed_cols, bias_cols=None, max_block=64):
     return out or None
 
 
+def _coarse_1d(nf, c):
+    """Bilinear coarsening of a line of nf nodes by the factor c (every c-th node plus the last one): per fine node the
+    lower / upper coarse parent and the weight of the upper one (0 where the fine node is a coarse node)."""
+    coarse = np.unique(np.r_[np.arange(0, nf, c), nf - 1])
+    i = np.arange(nf)
+    lo = np.searchsorted(coarse, i, side='right') - 1
+    hi = np.minimum(lo + 1, coarse.size - 1)
+    span = np.maximum(coarse[hi] - coarse[lo], 1)
+    w = np.where(coarse[lo] == i, 0., (i - coarse[lo]) / span)
+    return coarse.size, lo.astype(np.int64), hi.astype(np.int64), w.astype(np.float64)
+
+
+def coarse_structure(grids, fixed_cols, n_cols, max_coarse=1024):
+    """Coarse space of the two-level preconditioner (``lss_solver_set_coarse``): bilinear functions of (y, x) on a grid
+    c times coarser than z0 / dz (same factor for both, every epoch of dz kept), c the smallest power of two that
+    leaves at most ``max_coarse`` coarse unknowns.  Returns device tensors: per fine column its <= 4 parents and
+    weights (``cp_idx`` int32 [n_cols, 4], -1 = none; ``cp_w`` float32) and P^T as CSR by coarse row.
+    Fixed columns (reference epoch) and columns outside the two grids have no parents."""
+    z0, dz = grids.get('z0'), grids.get('dz')
+    if z0 is None or dz is None or len(z0.shape) != 2 or len(dz.shape) != 3:
+        return None
+    ny0, nx0 = (int(v) for v in z0.shape)
+    ny, nx, nt = (int(v) for v in dz.shape)
+    c = 2
+    while True:
+        n_c = _coarse_1d(ny0, c)[0] * _coarse_1d(nx0, c)[0] + _coarse_1d(ny, c)[0] * _coarse_1d(nx, c)[0] * nt
+        if n_c <= max_coarse:
+            break
+        c *= 2
+        if c > 4 * max(ny0, nx0, ny, nx):
+            return None
+    dev = _cabi.device()
+    idx = torch.full((n_cols, 4), -1, dtype=torch.int32, device=dev)
+    wts = torch.zeros((n_cols, 4), dtype=torch.float32, device=dev)
+
+    def fill(col_0, shp, nt_, base):
+        cy, ly, hy, wy = _coarse_1d(shp[0], c)
+        cx, lx, hx, wx = _coarse_1d(shp[1], c)
+        ly, hy, lx, hx = (torch.from_numpy(a).to(dev) for a in (ly, hy, lx, hx))
+        wy, wx = torch.from_numpy(wy).to(dev), torch.from_numpy(wx).to(dev)
+        k = torch.arange(shp[0] * shp[1] * nt_, device=dev)
+        node, t = k // nt_, k % nt_
+        iy, ix = node // shp[1], node % shp[1]
+        cols = slice(col_0, col_0 + k.numel())
+        for s_, (py, px, w_) in enumerate(((ly[iy], lx[ix], (1 - wy[iy]) * (1 - wx[ix])), (ly[iy], hx[ix], (1 - wy[iy]) * wx[ix]),
+                                           (hy[iy], lx[ix], wy[iy] * (1 - wx[ix])), (hy[iy], hx[ix], wy[iy] * wx[ix]))):
+            ci = base + (py * cx + px) * nt_ + t
+            idx[cols, s_] = torch.where(w_ > 0, ci, torch.full_like(ci, -1)).to(torch.int32)
+            wts[cols, s_] = w_.to(torch.float32)
+        return base + cy * cx * nt_
+
+    base = fill(int(z0.col_0), (ny0, nx0), 1, 0)
+    n_c = fill(int(dz.col_0), (ny, nx), nt, base)
+    if len(fixed_cols):
+        fc = _cabi.to_dev(np.asarray(fixed_cols, dtype=np.int64), torch.int64)
+        idx[fc] = -1
+        wts[fc] = 0
+    flat = idx.reshape(-1)
+    sel = torch.nonzero(flat >= 0).reshape(-1)
+    order = torch.argsort(flat[sel], stable=True)
+    ent = sel[order]
+    counts = torch.bincount(flat[ent].to(torch.int64), minlength=n_c)
+    pt_ptr = torch.zeros(n_c + 1, dtype=torch.int32, device=dev)
+    pt_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    return dict(n_c=int(n_c), factor=c, cp_idx=idx.contiguous(), cp_w=wts.contiguous(), pt_ptr=pt_ptr,
+                pt_col=(ent // 4).to(torch.int32).contiguous(), pt_w=wts.reshape(-1)[ent].contiguous())
+
+
 class NormalSolver(object):
     def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None, G_local=None, stages=None):
         """G: DeviceCSR of this rank's data rows; Cn: DeviceCSR of this rank's constraint rows;
@@ -157,7 +225,7 @@ class NormalSolver(object):
         _cabi.check(L.lss_solver_info(self.handle, info))
         self.form = ('csr_pair', 'fused_ell', 'explicit_normal')[int(info[0])]
         self.nnz_N, self.n_pairs = int(info[1]), int(info[2])
-        self.n_blocks = self.n_elim = 0
+        self.n_blocks = self.n_elim = self.n_coarse = 0
         if structure is not None and self.form == 'explicit_normal' and not os.environ.get('LSS_NO_STRUCTURE'):
             bp, bc = structure.get('block_ptr'), structure.get('block_cols')
             e0, e1 = structure.get('elim', (0, 0))
@@ -174,6 +242,13 @@ class NormalSolver(object):
             _cabi.check(rc)
             _cabi.check(L.lss_solver_info(self.handle, info))
             self.n_blocks, self.n_elim = int(info[4]), int(info[5])
+            cs = structure.get('coarse')
+            if cs is not None and self.n_blocks > 0:
+                self._coarse = cs          # keeps the device tensors alive until the copies inside the library are made
+                _cabi.check(L.lss_solver_set_coarse(self.handle, cs['n_c'], _cabi.ptr(cs['cp_idx']), _cabi.ptr(cs['cp_w']),
+                                                    _cabi.ptr(cs['pt_ptr']), _cabi.ptr(cs['pt_col']), _cabi.ptr(cs['pt_w']),
+                                                    int(cs['pt_col'].numel()), int(structure.get('coarse_refresh', 1))))
+                self.n_coarse = cs['n_c']
 
     def set_rows(self, in_TSE, sigma_extra=None):
         """Select data rows (uint8 mask) and, on the relaxed last pass, inflate their errors."""
@@ -197,7 +272,7 @@ class NormalSolver(object):
                          launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused, all_ell=self.all_ell,
                          n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz,
                          form=self.form, nnz_N=self.nnz_N, n_cols=self.n_cols, precond_blocks=self.n_blocks, eliminated=self.n_elim,
-                         nnz_product=int(info[7]), bad_blocks=int(info[6]))
+                         nnz_product=int(info[7]), bad_blocks=int(info[6]), coarse=self.n_coarse)
         return self.x
 
     def residual(self, x, z, out=None):

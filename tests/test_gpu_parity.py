@@ -411,6 +411,34 @@ def test_normal_product_and_step_kernel_variants_agree(L):
         assert abs(its - its0) <= 0.05 * its0 + 5, (key, its, its0)
 
 
+def test_two_level_preconditioner_agrees_with_block_jacobi(L, monkeypatch):
+    """The coarse level (lss_solver_set_coarse: Galerkin Schur operator on a bilinear coarse space, dense inverse,
+    fused into the CG step kernel) only changes the iteration count: same masks after every iteration, same solution
+    to solver tolerance, for a coarse operator frozen at the first weights (default) and for one rebuilt with every mask, with and without bias elimination."""
+    from lssurf_b200 import synthetic
+    for gen, n, width in ((synthetic.icesat2_tracks, 300_000, 3.e4), (synthetic.uniform_3d, 200_000, 3.e4)):
+        pts, kw = gen(n=n, width=width, seed=11)
+        out = {}
+        for key, env in (('bj', {'LSS_COARSE': '0'}), ('ml', {'LSS_COARSE': '1', 'LSS_COARSE_MIN_BLOCKS': '1'}),
+                         ('ml_refresh', {'LSS_COARSE': '1', 'LSS_COARSE_MIN_BLOCKS': '1', 'LSS_COARSE_REFRESH': '1'})):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            hist = []
+            out[key] = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, history=hist, **kw)
+            out[key]['hist'] = hist
+            for k in env:
+                monkeypatch.delenv(k)
+        assert out['bj']['timing']['pcg'][0]['coarse'] == 0 and out['ml']['timing']['pcg'][0]['coarse'] > 0
+        its = {k: sum(p['iterations'] for p in o['timing']['pcg']) for k, o in out.items()}
+        print(gen.__name__, 'CG iterations', its, 'coarse unknowns', out['ml']['timing']['pcg'][0]['coarse'])
+        for key in ('ml', 'ml_refresh'):
+            assert rel_l2(out[key]['m']['all'], out['bj']['m']['all']) < 1e-9, key
+            assert len(out[key]['hist']) == len(out['bj']['hist'])
+            for a, b in zip(out[key]['hist'], out['bj']['hist']):
+                assert np.array_equal(a['mask_out'], b['mask_out']), key
+            assert its[key] < 1.25 * its['bj'], (key, its)      # the coarse level pays off on large domains only (bench workload: -60 %)
+
+
 def test_large_scale_properties(L):
     """Full-size properties (cfg 3 shapes, 1e6 points) that need no oracle: row sums of the interpolation
     matrix are exactly 1 up to rounding, CSR is canonical, G^T products are adjoint, the solve reduces the residual."""
