@@ -148,6 +148,18 @@ int lss_spmv_planned(lss_spmv_plan_t *plan, int64_t n_rows, const int32_t *indpt
  * Both change speed and the order of floating-point sums only. */
 int lss_set_option(const char *name, int32_t value);
 
+/* lin_op.toCSR (lin_op.py:745-753) for operators whose triplets come in row-regular blocks -- the sum of interpolation
+ * operators and per-row bias entries smooth_fit builds for its data rows (smooth_fit.py:461-513): block b holds k_h[b]
+ * entries for EVERY row (row-major, cols_h[b] / vals_h[b] are host arrays of device pointers, 1..8 blocks).  Row r of the
+ * result takes its entries block after block with zero values dropped (toCSR drops them, lin_op.py:748); that is the
+ * canonical CSR whenever the kept columns of each row ascend strictly, which holds for np.mgrid corner order on grids
+ * with ascending column ranges.  No sort: two streaming passes.  *unordered_h receives the number of rows that are
+ * not ascending (or hold a column >= n_cols); when it is not 0 nothing is written and the caller uses lss_coo_to_csr.
+ * indices / data need room for n_rows * sum(k_h) entries. */
+int lss_blocks_to_csr(int64_t n_rows, int64_t n_cols, int32_t n_blocks, const int32_t *k_h, const int32_t *const *cols_h,
+                      const double *const *vals_h, int32_t *indptr, int32_t *indices, double *data, int64_t *nnz_out_h,
+                      int64_t *unordered_h, void *stream);
+
 /* ------------------------------------------------------------------ explicit normal matrix */
 
 /* N = A^T diag(w) A for a matrix A whose rows hold at most row_len <= 16 entries (canonical CSR in; the interpolation

@@ -41,6 +41,7 @@ SIGNATURES = {
     'lss_stencil_coo': [C.POINTER(lss_grid_t), _i32, _pi32, _pf64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     'lss_coo_extent': [_i64, _vp, _vp, _pi64, _pi64, _vp],
     'lss_coo_to_csr': [_i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _pi64, _vp],
+    'lss_blocks_to_csr': [_i64, _i64, _i32, _pi32, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _pi64, _pi64, _vp],
     'lss_csr_transpose': [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     'lss_cell_keys': [C.POINTER(lss_grid_t), C.POINTER(lss_grid_t), C.POINTER(_vp), _i64, _vp, _pi32, _vp],
     'lss_argsort_u64': [_i64, _vp, _i32, _vp, _vp],
@@ -260,6 +261,28 @@ def coo_to_csr(rows, cols, vals, n_rows, n_cols):
                            C.byref(out), stream()))
     k = out.value
     return indptr, indices[:k].clone() if k < nnz else indices[:k], data[:k].clone() if k < nnz else data[:k]
+
+
+def blocks_to_csr(blocks, n_rows, n_cols):
+    """Canonical CSR of row-regular COO blocks [(cols[n_rows, k], vals[n_rows, k]), ...] without a sort
+    (``lss_blocks_to_csr``); None when some row is not in ascending column order (the caller sorts instead)."""
+    L = lib()
+    nb = len(blocks)
+    ks = (C.c_int32 * nb)(*[int(c.shape[1]) for c, _ in blocks])
+    cols = (_vp * nb)(*[c.data_ptr() for c, _ in blocks])
+    vals = (_vp * nb)(*[v.data_ptr() for _, v in blocks])
+    cap = int(n_rows) * sum(int(c.shape[1]) for c, _ in blocks)
+    dev = device()
+    indptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    data = torch.empty(max(cap, 1), dtype=torch.float64, device=dev)
+    nnz, bad = C.c_int64(0), C.c_int64(0)
+    check(L.lss_blocks_to_csr(int(n_rows), int(n_cols), nb, ks, cols, vals, ptr(indptr), ptr(indices), ptr(data), C.byref(nnz),
+                              C.byref(bad), stream()))
+    if bad.value:
+        return None
+    k = nnz.value
+    return indptr, (indices[:k].clone() if k < cap else indices), (data[:k].clone() if k < cap else data)
 
 
 def csr_transpose(indptr, indices, data, n_rows, n_cols):

@@ -12,6 +12,7 @@
 // it is bit-identical to NumPy's) followed by a one-block kernel that picks each target's bin.
 // When points are sharded over GPUs the histograms are summed with one NCCL all-reduce per pass.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -48,10 +49,12 @@ __device__ __forceinline__ double scaled_value(const double *__restrict__ r, con
 }
 
 // Count of selected finite values (pass 0 only) and per-slot digit histograms of the current pass.
+// With `keys` the population is the candidate array keys[0 .. *n_keys) (already order-preserving images) instead of r / sigma / mask.
 __global__ void __launch_bounds__(SEL_BLOCK)
 select_hist_kernel(const double *__restrict__ r, const double *__restrict__ sigma, const unsigned char *__restrict__ mask,
                    double s1sq, int64_t n, int pass, const SelectState *__restrict__ state,
-                   unsigned long long *__restrict__ hist /*[SEL_MAX][SEL_BINS]*/, unsigned long long *__restrict__ count) {
+                   unsigned long long *__restrict__ hist /*[SEL_MAX][SEL_BINS]*/, unsigned long long *__restrict__ count,
+                   const unsigned long long *__restrict__ keys = nullptr, const unsigned long long *__restrict__ n_keys = nullptr) {
     __shared__ unsigned int h[SEL_MAX][SEL_BINS];
     __shared__ unsigned long long sp[SEL_MAX];
     __shared__ int ns;
@@ -61,12 +64,13 @@ select_hist_kernel(const double *__restrict__ r, const double *__restrict__ sigm
     __syncthreads();
     const int shift = 56 - 8 * pass;
     unsigned long long cnt = 0;
+    if (keys) n = (int64_t)*n_keys;
     // warp-uniform trip count so that the match below always sees the full warp
     for (int64_t i0 = (int64_t)blockIdx.x * SEL_BLOCK + (threadIdx.x & ~31); i0 < n; i0 += (int64_t)gridDim.x * SEL_BLOCK) {
         const int64_t i = i0 + lane_id();
-        bool use = i < n && (!mask || mask[i]);
+        bool use = i < n && (keys || !mask || mask[i]);
         double v = 0.0;
-        if (use) {
+        if (use && !keys) {
             v = scaled_value(r, sigma, s1sq, i);
             use = isfinite(v);   // RDE drops non-finite values (RDE.py:12)
         }
@@ -74,7 +78,7 @@ select_hist_kernel(const double *__restrict__ r, const double *__restrict__ sigm
         unsigned int digit = 0;
         if (use) {
             ++cnt;
-            const unsigned long long k = f64_key(v);
+            const unsigned long long k = keys ? keys[i] : f64_key(v);
             digit = (unsigned int)(k >> shift) & 0xffu;
             if (pass == 0) slot = 0;
             else {
@@ -93,7 +97,7 @@ select_hist_kernel(const double *__restrict__ r, const double *__restrict__ sigm
         const unsigned int c = (&h[0][0])[i];
         if (c) atomicAdd(&hist[i], (unsigned long long)c);
     }
-    if (pass == 0) {
+    if (pass == 0 && !keys) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane_id() == 0 && cnt) atomicAdd(count, cnt);
@@ -243,17 +247,134 @@ data_weights_kernel(const double *__restrict__ sigma, const double *__restrict__
     }
 }
 
+
+// ---- two-pass candidate selection --------------------------------------------------------------
+// A full 8-pass radix select streams all points eight times per RDE evaluation.  Instead: ONE pass builds a histogram
+// over a monotone, magnitude-resolving binning of the values (sign, 32 binary exponents around 1, 6 mantissa bits:
+// 4098 bins, ~0.4 % of a normal sample per bin near the 16th / 84th percentiles); a second pass appends the keys of the
+// points inside the (at most 4) bins that hold the target ranks to a candidate array; the exact 8-pass select then runs
+// on the candidates (~10^-2 of the points) with ranks taken relative to them.  Binning is monotone in the value, so
+// every point outside the target bins is on a known side of every target: the result is the same order statistic.
+constexpr int BIN_EXP_LO = -20, BIN_EXP_N = 32, BIN_MANT_BITS = 6;
+constexpr int BIN_HALF = BIN_EXP_N << BIN_MANT_BITS;          // 2048 magnitude classes per sign
+constexpr int BIN_COUNT = 2 * BIN_HALF + 2;                   // negatives (descending magnitude), tiny-, tiny+, positives
+
+__device__ __forceinline__ int value_bin(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    const bool neg = (u >> 63) != 0;
+    const int e = (int)((u >> 52) & 0x7ff) - 1023 - BIN_EXP_LO;              // 0 .. BIN_EXP_N - 1 inside the resolved range
+    int mag;                                                                 // -1: tiny, 0 .. BIN_HALF - 1
+    if (e < 0) mag = -1;
+    else if (e >= BIN_EXP_N) mag = BIN_HALF - 1;
+    else mag = (e << BIN_MANT_BITS) | (int)((u >> (52 - BIN_MANT_BITS)) & ((1u << BIN_MANT_BITS) - 1));
+    return neg ? (BIN_HALF - 1 - mag) : (BIN_HALF + 2 + mag);                // tiny-: BIN_HALF, tiny+: BIN_HALF + 1
+}
+
+struct BinPlan {
+    int n_bins;                    // distinct target bins (ascending)
+    int bins[SEL_MAX];
+};
+
+__global__ void __launch_bounds__(SEL_BLOCK)
+select_binhist_kernel(const double *__restrict__ r, const double *__restrict__ sigma, const unsigned char *__restrict__ mask,
+                      double s1sq, int64_t n, unsigned long long *__restrict__ hist /*[BIN_COUNT]*/, unsigned long long *__restrict__ count) {
+    __shared__ unsigned int h[BIN_COUNT];
+    for (int i = threadIdx.x; i < BIN_COUNT; i += SEL_BLOCK) h[i] = 0;
+    __syncthreads();
+    unsigned long long cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * SEL_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * SEL_BLOCK) {
+        if (mask && !mask[i]) continue;
+        const double v = scaled_value(r, sigma, s1sq, i);
+        if (!isfinite(v)) continue;
+        ++cnt;
+        atomicAdd(&h[value_bin(v)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BIN_COUNT; i += SEL_BLOCK) {
+        const unsigned int c = h[i];
+        if (c) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane_id() == 0 && cnt) atomicAdd(count, cnt);
+}
+
+// One block: bins of the target ranks; ranks become ranks inside the union of the target bins; clears the
+// candidate counter and the 8-bit histograms of the exact select that follows.
+__global__ void __launch_bounds__(SEL_BLOCK)
+select_binplan_kernel(SelectState *__restrict__ state, const unsigned long long *__restrict__ hist, BinPlan *__restrict__ bp,
+                      unsigned long long *__restrict__ n_cand, unsigned long long *__restrict__ hist8) {
+    __shared__ unsigned long long start[BIN_COUNT + 1];
+    for (int i = threadIdx.x; i < SEL_MAX * SEL_BINS; i += SEL_BLOCK) hist8[i] = 0;
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int b = 0; b < BIN_COUNT; ++b) { start[b] = acc; acc += hist[b]; }
+        start[BIN_COUNT] = acc;
+        const int nt = state->n_targets;
+        int nb = 0;
+        unsigned long long before = 0;          // candidates in target bins below the current one
+        for (int t = 0; t < nt; ++t) {          // target ranks ascend (0.16 pair, then 0.84 pair)
+            const unsigned long long rk = state->rank[t];
+            int lo = 0, hi = BIN_COUNT;         // last bin with start <= rk
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (start[mid] <= rk) lo = mid; else hi = mid; }
+            while (lo + 1 < BIN_COUNT && start[lo + 1] <= rk) ++lo;
+            if (nb == 0 || bp->bins[nb - 1] != lo) {
+                if (nb > 0) before += hist[bp->bins[nb - 1]];
+                bp->bins[nb++] = lo;
+            }
+            state->rank[t] = rk - start[lo] + before;
+        }
+        bp->n_bins = nb;
+        *n_cand = 0;
+    }
+}
+
+__global__ void __launch_bounds__(SEL_BLOCK)
+select_compact_kernel(const double *__restrict__ r, const double *__restrict__ sigma, const unsigned char *__restrict__ mask,
+                      double s1sq, int64_t n, const BinPlan *__restrict__ bp, unsigned long long *__restrict__ cand,
+                      unsigned long long *__restrict__ n_cand) {
+    const int nb = bp->n_bins;
+    int tb[SEL_MAX];
+#pragma unroll
+    for (int t = 0; t < SEL_MAX; ++t) tb[t] = t < nb ? bp->bins[t] : -1;
+    for (int64_t i0 = (int64_t)blockIdx.x * SEL_BLOCK + (threadIdx.x & ~31); i0 < n; i0 += (int64_t)gridDim.x * SEL_BLOCK) {
+        const int64_t i = i0 + lane_id();
+        bool take = false;
+        double v = 0.0;
+        if (i < n && (!mask || mask[i])) {
+            v = scaled_value(r, sigma, s1sq, i);
+            if (isfinite(v)) {
+                const int b = value_bin(v);
+                take = (b == tb[0]) | (b == tb[1]) | (b == tb[2]) | (b == tb[3]);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane_id() == 0) base = atomicAdd(n_cand, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (take) cand[base + __popc(m & ((1u << lane_id()) - 1u))] = f64_key(v);
+        }
+    }
+}
+
 struct RdeWork {
-    Scratch state, plan, hist, count, out;
+    Scratch state, plan, hist, count, out, binhist, binplan, cand, n_cand;
+    int64_t cand_cap = 0;
     int init(cudaStream_t st) {
         LSS_CUDA(state.alloc(sizeof(SelectState), st));
         LSS_CUDA(plan.alloc(sizeof(RdePlan), st));
         LSS_CUDA(hist.alloc(sizeof(unsigned long long) * SEL_MAX * SEL_BINS, st));
         LSS_CUDA(count.alloc(sizeof(unsigned long long), st));
         LSS_CUDA(out.alloc(sizeof(double) * 2, st));
+        LSS_CUDA(binhist.alloc(sizeof(unsigned long long) * BIN_COUNT, st));
+        LSS_CUDA(binplan.alloc(sizeof(BinPlan), st));
+        LSS_CUDA(n_cand.alloc(sizeof(unsigned long long), st));
         return LSS_OK;
     }
 };
+
+constexpr int64_t kCandidateMin = 1 << 16;    // below this many points the plain 8-pass select is as fast
 
 // One RDE evaluation; result (rde, n) copied to the host and the stream synchronised.
 static int rde_eval(RdeWork &wk, const double *r, const double *sigma, const unsigned char *mask, double s1sq, int64_t n,
@@ -262,20 +383,55 @@ static int rde_eval(RdeWork &wk, const double *r, const double *sigma, const uns
     LSS_CUDA(cudaMemsetAsync(wk.count.p, 0, sizeof(unsigned long long), st));
     LSS_CUDA(cudaMemsetAsync(wk.state.p, 0, sizeof(SelectState), st));
     const int grid = stride_grid(n, SEL_BLOCK, 8);
-    for (int pass = 0; pass < 8; ++pass) {
-        if (n > 0) {
-            select_hist_kernel<<<grid, SEL_BLOCK, 0, st>>>(r, sigma, mask, s1sq, n, pass, wk.state.as<SelectState>(),
-                                                           wk.hist.as<unsigned long long>(), wk.count.as<unsigned long long>());
-            LSS_LAUNCH_CHECK();
+    static int two_pass = -1;
+    if (two_pass < 0) two_pass = getenv("LSS_SELECT_FULL") ? 0 : 1;
+    // with several ranks the choice must not depend on the rank's own point count (the collectives have to match)
+    if (two_pass && (n >= kCandidateMin || (comm && comm->n_ranks > 1))) {
+        if (wk.cand_cap < n) {
+            if (wk.cand.p) { cudaFreeAsync(wk.cand.p, st); wk.cand.p = nullptr; }
+            LSS_CUDA(wk.cand.alloc(sizeof(unsigned long long) * (size_t)n, st));
+            wk.cand_cap = n;
         }
-        LSS_TRY(comm_allreduce(comm, wk.hist.p, SEL_MAX * SEL_BINS, 2, 0, st));
-        if (pass == 0) {
-            LSS_TRY(comm_allreduce(comm, wk.count.p, 1, 2, 0, st));
-            select_plan_kernel<<<1, 32, 0, st>>>(wk.count.as<unsigned long long>(), wk.state.as<SelectState>(), wk.plan.as<RdePlan>());
-            LSS_LAUNCH_CHECK();
-        }
-        select_step_kernel<<<1, SEL_BINS, 0, st>>>(wk.state.as<SelectState>(), wk.hist.as<unsigned long long>());
+        LSS_CUDA(cudaMemsetAsync(wk.binhist.p, 0, sizeof(unsigned long long) * BIN_COUNT, st));
+        select_binhist_kernel<<<grid, SEL_BLOCK, 0, st>>>(r, sigma, mask, s1sq, n, wk.binhist.as<unsigned long long>(),
+                                                          wk.count.as<unsigned long long>());
         LSS_LAUNCH_CHECK();
+        LSS_TRY(comm_allreduce(comm, wk.binhist.p, BIN_COUNT, 2, 0, st));
+        LSS_TRY(comm_allreduce(comm, wk.count.p, 1, 2, 0, st));
+        select_plan_kernel<<<1, 32, 0, st>>>(wk.count.as<unsigned long long>(), wk.state.as<SelectState>(), wk.plan.as<RdePlan>());
+        LSS_LAUNCH_CHECK();
+        select_binplan_kernel<<<1, SEL_BLOCK, 0, st>>>(wk.state.as<SelectState>(), wk.binhist.as<unsigned long long>(), wk.binplan.as<BinPlan>(),
+                                                       wk.n_cand.as<unsigned long long>(), wk.hist.as<unsigned long long>());
+        LSS_LAUNCH_CHECK();
+        select_compact_kernel<<<grid, SEL_BLOCK, 0, st>>>(r, sigma, mask, s1sq, n, wk.binplan.as<BinPlan>(), wk.cand.as<unsigned long long>(),
+                                                          wk.n_cand.as<unsigned long long>());
+        LSS_LAUNCH_CHECK();
+        const int cgrid = 2 * kSMs;          // the candidate count stays on the device
+        for (int pass = 0; pass < 8; ++pass) {
+            select_hist_kernel<<<cgrid, SEL_BLOCK, 0, st>>>(nullptr, nullptr, nullptr, 0.0, 0, pass, wk.state.as<SelectState>(),
+                                                            wk.hist.as<unsigned long long>(), wk.count.as<unsigned long long>(),
+                                                            wk.cand.as<unsigned long long>(), wk.n_cand.as<unsigned long long>());
+            LSS_LAUNCH_CHECK();
+            LSS_TRY(comm_allreduce(comm, wk.hist.p, SEL_MAX * SEL_BINS, 2, 0, st));
+            select_step_kernel<<<1, SEL_BINS, 0, st>>>(wk.state.as<SelectState>(), wk.hist.as<unsigned long long>());
+            LSS_LAUNCH_CHECK();
+        }
+    } else {
+        for (int pass = 0; pass < 8; ++pass) {
+            if (n > 0) {
+                select_hist_kernel<<<grid, SEL_BLOCK, 0, st>>>(r, sigma, mask, s1sq, n, pass, wk.state.as<SelectState>(),
+                                                               wk.hist.as<unsigned long long>(), wk.count.as<unsigned long long>());
+                LSS_LAUNCH_CHECK();
+            }
+            LSS_TRY(comm_allreduce(comm, wk.hist.p, SEL_MAX * SEL_BINS, 2, 0, st));
+            if (pass == 0) {
+                LSS_TRY(comm_allreduce(comm, wk.count.p, 1, 2, 0, st));
+                select_plan_kernel<<<1, 32, 0, st>>>(wk.count.as<unsigned long long>(), wk.state.as<SelectState>(), wk.plan.as<RdePlan>());
+                LSS_LAUNCH_CHECK();
+            }
+            select_step_kernel<<<1, SEL_BINS, 0, st>>>(wk.state.as<SelectState>(), wk.hist.as<unsigned long long>());
+            LSS_LAUNCH_CHECK();
+        }
     }
     select_finish_kernel<<<1, 32, 0, st>>>(wk.state.as<SelectState>(), wk.plan.as<RdePlan>(), wk.out.as<double>());
     LSS_LAUNCH_CHECK();

@@ -4,6 +4,9 @@
 // and csr.T / tocsc used for G^T products (LSsurf/smooth_fit.py:142, 339-345).  All of it is
 // HBM-bound integer work: coalesced tile loads, warp-aggregated shared-memory histograms
 // (__match_any_sync), stable warp-level multi-split ranking, no global atomics on the data path.
+#include <stdlib.h>
+#include <math.h>
+
 #include "common.cuh"
 
 namespace lss {
@@ -388,9 +391,202 @@ group_median_kernel(const uint64_t *__restrict__ id_keys, const uint32_t *__rest
     out[g] = (m & 1) ? a : (a + b) / 2.0;                                   // np.median: mean of the two middle values
 }
 
+
+// ---- fast paths: small-integer dense ranks, groups of equal values, row-regular COO blocks ----------------------
+
+// stats[0] = min, stats[1] = max of the order keys of x (NaN -> nan_value, -0 -> +0); stats[2] != 0 when some value is
+// not an integer (or not finite): the counting path below does not apply then.
+__global__ void __launch_bounds__(256)
+int_range_kernel(const double *__restrict__ x, int64_t n, double nan_value, unsigned long long *__restrict__ stats) {
+    unsigned long long mn = ~0ull, mx = 0ull;
+    unsigned int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (v != v) v = nan_value;
+        if (v == 0.0) v = 0.0;
+        if (!(v == floor(v)) || !(fabs(v) < 4.0e15)) { bad = 1; continue; }
+        const unsigned long long k = f64_sort_key(v);
+        mn = k < mn ? k : mn;
+        mx = k > mx ? k : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane_id() == 0) {
+        if (mn != ~0ull) { atomicMin(stats, mn); atomicMax(stats + 1, mx); }
+        if (bad) atomicOr(stats + 2, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+int_presence_kernel(const double *__restrict__ x, int64_t n, double nan_value, double lo, uint32_t *__restrict__ present) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (v != v) v = nan_value;
+        present[(int64_t)(v - lo)] = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+int_rank_kernel(const double *__restrict__ x, int64_t n, double nan_value, double lo, const uint32_t *__restrict__ pos, int *__restrict__ rank) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (v != v) v = nan_value;
+        rank[i] = (int)pos[(int64_t)(v - lo)];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+int_unique_kernel(int64_t n_bins, double lo, const uint32_t *__restrict__ present, const uint32_t *__restrict__ pos, double *__restrict__ uniq) {
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x)
+        if (present[b]) uniq[pos[b]] = lo + (double)b;
+}
+
+// per-group minimum / maximum order key (warp-aggregated: neighbouring points mostly share their group); flag[0] != 0
+// when a NaN was met or an id is out of range
+__global__ void __launch_bounds__(256)
+group_minmax_kernel(const int *__restrict__ ids, const double *__restrict__ vals, int64_t n, int n_groups,
+                    unsigned long long *__restrict__ gmin, unsigned long long *__restrict__ gmax, unsigned int *__restrict__ flag) {
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + lane_id();
+        int g = -1;
+        unsigned long long k = 0;
+        if (i < n) {
+            g = ids[i];
+            const double v = vals[i];
+            if (v != v || g < 0 || g >= n_groups) { atomicOr(flag, 1u); g = -1; }
+            else k = f64_sort_key(v == 0.0 ? 0.0 : v);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, g);
+        unsigned long long mn = k, mx = k;
+        // reduce over the peer set with shuffles from each peer lane
+        for (unsigned m = peers; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const unsigned long long ko = __shfl_sync(peers, k, src);
+            mn = ko < mn ? ko : mn;
+            mx = ko > mx ? ko : mx;
+        }
+        if (g >= 0 && lane_id() == (unsigned)(__ffs(peers) - 1)) {
+            atomicMin(gmin + g, mn);
+            atomicMax(gmax + g, mx);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+group_const_kernel(int n_groups, const unsigned long long *__restrict__ gmin, const unsigned long long *__restrict__ gmax,
+                   double *__restrict__ out, unsigned int *__restrict__ flag) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const unsigned long long a = gmin[g], b = gmax[g];
+    if (a == ~0ull && b == 0ull) { out[g] = nan(""); return; }          // empty group: nanmedian of nothing
+    if (a != b) { atomicOr(flag, 2u); return; }
+    const unsigned long long u = (a >> 63) ? (a & 0x7fffffffffffffffull) : ~a;
+    out[g] = __longlong_as_double((long long)u);
+}
+
+// Row-regular COO blocks -> canonical CSR without sorting.  Block b holds k[b] entries per row, row-major; the rows of
+// the result take their entries block after block, zero values dropped.  This is already canonical when the kept
+// columns of every row ascend strictly (interpolation corners in np.mgrid order, one grid after the other): rows that
+// violate it are counted in *unordered and the caller falls back to the sort.
+constexpr int BLK_MAX = 8;
+struct CooBlocks {
+    int n_blocks;
+    int k[BLK_MAX];
+    const int *cols[BLK_MAX];
+    const double *vals[BLK_MAX];
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+blocks_rows_kernel(int64_t n_rows, int64_t n_cols, CooBlocks B, uint32_t *__restrict__ counts, const int *__restrict__ indptr,
+                   int *__restrict__ indices, double *__restrict__ data, unsigned long long *__restrict__ unordered) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    int cnt = 0, prev = -1;
+    bool bad = false;
+    int64_t o = FILL ? indptr[r] : 0;
+    for (int b = 0; b < B.n_blocks; ++b) {
+        const int k = B.k[b];
+        const int *c = B.cols[b] + r * k;
+        const double *v = B.vals[b] + r * k;
+        for (int j = 0; j < k; ++j) {
+            const double val = v[j];
+            if (val == 0.0) continue;
+            const int col = c[j];
+            if (FILL) {
+                indices[o] = col;
+                data[o] = val;
+                ++o;
+            } else {
+                if (col <= prev || col >= n_cols) bad = true;
+                prev = col;
+                ++cnt;
+            }
+        }
+    }
+    if (!FILL) {
+        counts[r] = (uint32_t)cnt;
+        if (bad) atomicAdd(unordered, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(256) set_last_kernel(int *__restrict__ indptr, int64_t n_rows, const uint32_t *__restrict__ total) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) indptr[n_rows] = (int)*total;
+}
+
 }  // namespace lss
 
 using namespace lss;
+
+extern "C" int lss_blocks_to_csr(int64_t n_rows, int64_t n_cols, int32_t n_blocks, const int32_t *k_h, const int32_t *const *cols_h,
+                                 const double *const *vals_h, int32_t *indptr, int32_t *indices, double *data, int64_t *nnz_out_h,
+                                 int64_t *unordered_h, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_blocks < 1 || n_blocks > BLK_MAX || n_rows < 0 || !k_h || !cols_h || !vals_h || !nnz_out_h || !unordered_h)
+        return fail(LSS_EINVAL, "blocks_to_csr: bad arguments (1..%d blocks)", BLK_MAX);
+    CooBlocks B;
+    memset(&B, 0, sizeof(B));
+    B.n_blocks = n_blocks;
+    int64_t per_row = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        if (k_h[b] < 1 || k_h[b] > 64) return fail(LSS_EINVAL, "blocks_to_csr: %d entries per row in block %d", k_h[b], b);
+        B.k[b] = k_h[b]; B.cols[b] = cols_h[b]; B.vals[b] = vals_h[b];
+        per_row += k_h[b];
+    }
+    if (per_row * n_rows >= (1ll << 31)) return fail(LSS_ERANGE, "blocks_to_csr: exceeds int32 index range");
+    *nnz_out_h = 0;
+    *unordered_h = 0;
+    if (n_rows == 0) {
+        LSS_CUDA(cudaMemsetAsync(indptr, 0, sizeof(int), st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+        return LSS_OK;
+    }
+    Scratch counts, acc;
+    LSS_CUDA(counts.alloc(sizeof(uint32_t) * n_rows, st));
+    LSS_CUDA(acc.alloc(2 * sizeof(unsigned long long), st));
+    LSS_CUDA(cudaMemsetAsync(acc.p, 0, 2 * sizeof(unsigned long long), st));
+    const int grid = ceil_div(n_rows, 256);
+    blocks_rows_kernel<false><<<grid, 256, 0, st>>>(n_rows, n_cols, B, counts.as<uint32_t>(), nullptr, nullptr, nullptr, acc.as<unsigned long long>());
+    LSS_LAUNCH_CHECK();
+    uint32_t *total = reinterpret_cast<uint32_t *>(acc.as<unsigned long long>() + 1);
+    LSS_TRY(exclusive_scan_u32(counts.as<uint32_t>(), reinterpret_cast<uint32_t *>(indptr), n_rows, total, st));
+    set_last_kernel<<<1, 32, 0, st>>>(indptr, n_rows, total);
+    LSS_LAUNCH_CHECK();
+    unsigned long long h[2] = {0, 0};
+    LSS_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    LSS_CUDA(cudaStreamSynchronize(st));
+    *unordered_h = (int64_t)h[0];
+    if (h[0]) return LSS_OK;                  // not canonical by construction: the caller sorts
+    blocks_rows_kernel<true><<<grid, 256, 0, st>>>(n_rows, n_cols, B, nullptr, indptr, indices, data, nullptr);
+    LSS_LAUNCH_CHECK();
+    *nnz_out_h = (int64_t)(uint32_t)h[1];
+    return LSS_OK;
+}
 
 extern "C" int lss_coo_to_csr(int64_t nnz, const int32_t *rows, const int32_t *cols, const double *vals, int64_t n_rows,
                               int64_t n_cols, int32_t *indptr, int32_t *indices, double *data, int64_t *nnz_out_h,
@@ -498,6 +694,49 @@ extern "C" int lss_dense_rank_f64(const double *x, int64_t n, double nan_value, 
     if (n >= (1ll << 31)) return fail(LSS_ERANGE, "dense_rank: exceeds int32 index range");
     if (n_unique_h) *n_unique_h = 0;
     if (n == 0) return LSS_OK;
+    {
+        // small-integer values (track / cycle numbers, combined ranks): presence table + scan instead of a 64-bit sort
+        Scratch stats;
+        LSS_CUDA(stats.alloc(3 * sizeof(unsigned long long), st));
+        const unsigned long long init[3] = {~0ull, 0ull, 0ull};
+        LSS_CUDA(cudaMemcpyAsync(stats.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        int_range_kernel<<<stride_grid(n, 256), 256, 0, st>>>(x, n, nan_value, stats.as<unsigned long long>());
+        LSS_LAUNCH_CHECK();
+        unsigned long long h[3];
+        LSS_CUDA(cudaMemcpyAsync(h, stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+        auto decode = [](unsigned long long k) { unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k; double d; memcpy(&d, &u, sizeof(d)); return d; };
+        if (h[2] == 0 && h[0] != ~0ull && !getenv("LSS_RANK_SORT")) {
+            const double lo = decode(h[0]), hi = decode(h[1]);
+            const double span = hi - lo;
+            if (span >= 0 && span < (double)(1 << 22)) {
+                const int64_t n_bins = (int64_t)span + 1;
+                Scratch present, pos, tot, uq;
+                LSS_CUDA(present.alloc(sizeof(uint32_t) * n_bins, st));
+                LSS_CUDA(pos.alloc(sizeof(uint32_t) * n_bins, st));
+                LSS_CUDA(tot.alloc(sizeof(uint32_t), st));
+                LSS_CUDA(uq.alloc(sizeof(double) * n_bins, st));
+                LSS_CUDA(cudaMemsetAsync(present.p, 0, sizeof(uint32_t) * n_bins, st));
+                int_presence_kernel<<<stride_grid(n, 256), 256, 0, st>>>(x, n, nan_value, lo, present.as<uint32_t>());
+                LSS_LAUNCH_CHECK();
+                LSS_TRY(exclusive_scan_u32(present.as<uint32_t>(), pos.as<uint32_t>(), n_bins, tot.as<uint32_t>(), st));
+                int_rank_kernel<<<stride_grid(n, 256), 256, 0, st>>>(x, n, nan_value, lo, pos.as<uint32_t>(), rank);
+                LSS_LAUNCH_CHECK();
+                int_unique_kernel<<<stride_grid(n_bins, 256), 256, 0, st>>>(n_bins, lo, present.as<uint32_t>(), pos.as<uint32_t>(), uq.as<double>());
+                LSS_LAUNCH_CHECK();
+                uint32_t nu = 0;
+                LSS_CUDA(cudaMemcpyAsync(&nu, tot.p, sizeof(nu), cudaMemcpyDeviceToHost, st));
+                LSS_CUDA(cudaStreamSynchronize(st));
+                if (n_unique_h) *n_unique_h = nu;
+                if (unique_h) {
+                    if ((int64_t)nu > unique_cap) return fail(LSS_EINVAL, "dense_rank: %u unique values exceed the capacity %lld", nu, (long long)unique_cap);
+                    LSS_CUDA(cudaMemcpyAsync(unique_h, uq.p, sizeof(double) * nu, cudaMemcpyDeviceToHost, st));
+                    LSS_CUDA(cudaStreamSynchronize(st));
+                }
+                return LSS_OK;
+            }
+        }
+    }
     Scratch ka, kb, va, vb, flags, uniq, tot;
     LSS_CUDA(ka.alloc(sizeof(uint64_t) * n, st));
     LSS_CUDA(kb.alloc(sizeof(uint64_t) * n, st));
@@ -539,6 +778,26 @@ extern "C" int lss_group_median(const int32_t *ids, const double *vals, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
     if (n >= (1ll << 31)) return fail(LSS_ERANGE, "group_median: exceeds int32 index range");
     if (n_groups <= 0) return LSS_OK;
+    if (n > 0 && !getenv("LSS_RANK_SORT")) {
+        // every group holds one distinct value (a constant sigma_corr per track, say): its median is that value
+        Scratch gmin, gmax, flag;
+        LSS_CUDA(gmin.alloc(sizeof(unsigned long long) * n_groups, st));
+        LSS_CUDA(gmax.alloc(sizeof(unsigned long long) * n_groups, st));
+        LSS_CUDA(flag.alloc(sizeof(unsigned int), st));
+        LSS_CUDA(cudaMemsetAsync(gmin.p, 0xff, sizeof(unsigned long long) * n_groups, st));
+        LSS_CUDA(cudaMemsetAsync(gmax.p, 0, sizeof(unsigned long long) * n_groups, st));
+        LSS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(unsigned int), st));
+        group_minmax_kernel<<<stride_grid(n, 256), 256, 0, st>>>(ids, vals, n, n_groups, gmin.as<unsigned long long>(), gmax.as<unsigned long long>(),
+                                                                flag.as<unsigned int>());
+        LSS_LAUNCH_CHECK();
+        group_const_kernel<<<ceil_div(n_groups, 256), 256, 0, st>>>(n_groups, gmin.as<unsigned long long>(), gmax.as<unsigned long long>(), out,
+                                                                   flag.as<unsigned int>());
+        LSS_LAUNCH_CHECK();
+        unsigned int f = 0;
+        LSS_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(f), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+        if (f == 0) return LSS_OK;
+    }
     Scratch ka, kb, va, vb;
     LSS_CUDA(ka.alloc(sizeof(uint64_t) * (n + 1), st));
     LSS_CUDA(kb.alloc(sizeof(uint64_t) * (n + 1), st));

@@ -34,6 +34,26 @@ def _index_array(rows):
     return np.array(rows, dtype='int')
 
 
+def _join_rows(parts):
+    """Concatenation of TOC row lists; consecutive ranges merge into one range."""
+    if not parts:
+        return np.array([], dtype=int)
+    if all(isinstance(p, range) and p.step == 1 for p in parts):
+        nonempty = [p for p in parts if len(p)]
+        if not nonempty:
+            return range(0)
+        if all(a.stop == b.start for a, b in zip(nonempty[:-1], nonempty[1:])):
+            return range(nonempty[0].start, nonempty[-1].stop)
+    return np.concatenate([_index_array(p).ravel() for p in parts])
+
+
+def rows_of(rows):
+    """An index usable on NumPy arrays / tensors for a TOC row list: a slice for contiguous ranges."""
+    if isinstance(rows, range) and rows.step == 1:
+        return slice(rows.start, rows.stop)
+    return _index_array(rows)
+
+
 def _union_of_columns(arrays):
     """np.unique(np.concatenate(arrays)); column lists are almost always contiguous ranges, whose union is merged
     as intervals instead of sorting millions of integers."""
@@ -130,6 +150,7 @@ class lin_op(object):
         self._host = {'r': np.array([], dtype=int), 'c': np.array([], dtype=int), 'v': np.array([], dtype=float)}
         self._dev = {'r': None, 'c': None, 'v': None}
         self._csr_cache = {}
+        self._blocks = None       # row-regular form [(cols[n, k], vals[n, k]), ...] when every row holds the same entries block by block
         self._ind0 = np.zeros([0], dtype=int)      # or a list of parts: ('arange', n) / ndarray, joined on demand
         self.TOC = {'rows': dict(), 'cols': dict()}
         self.grid = grid
@@ -167,12 +188,14 @@ class lin_op(object):
             self._host[f] = t.cpu().numpy().astype(_HOST_DTYPE[f])
             self._dev[f] = None            # the host copy may now be edited in place: it is authoritative
             self._csr_cache = {}
+            self._blocks = None
         return self._host[f]
 
     def _set_host(self, f, value):
         self._host[f] = value
         self._dev[f] = None
         self._csr_cache = {}
+        self._blocks = None
 
     r = property(lambda self: self._get_host('r'), lambda self, v: self._set_host('r', v))
     c = property(lambda self: self._get_host('c'), lambda self, v: self._set_host('c', v))
@@ -187,10 +210,11 @@ class lin_op(object):
             return torch.empty(0, dtype=_DEV_DTYPE[f], device=_cabi.device())
         return _cabi.to_dev(np.asarray(h), _DEV_DTYPE[f])
 
-    def _set_device(self, r, c, v):
+    def _set_device(self, r, c, v, blocks=None):
         self._dev = {'r': r, 'c': c, 'v': v}
         self._host = {'r': None, 'c': None, 'v': None}
         self._csr_cache = {}
+        self._blocks = blocks
 
     def _on_device(self):
         return all(self._dev[f] is not None for f in _FIELDS)
@@ -248,7 +272,7 @@ class lin_op(object):
             keep = valid.bool()
             rows, cols, vals = rows[keep].contiguous(), cols[keep].contiguous(), vals[keep].contiguous()
         n_pts = n_in - n_bad
-        self._set_device(rows, cols, vals)
+        self._set_device(rows, cols, vals, blocks=[(cols, vals)] if n_bad == 0 and cols.dim() == 2 else None)
         self._valid_pts = valid if n_bad > 0 else None
         self.N_eq = n_pts
         self._ind0 = [('arange', n_pts)]                       # np.arange(n_pts), materialised on access
@@ -289,7 +313,7 @@ class lin_op(object):
         self._update_shape()
         return self
 
-    def data_bias(self, ind=None, val=None, col=None, DOF=None, _toc=None):
+    def data_bias(self, ind=None, val=None, col=None, DOF=None, _toc=None, _regular=False):
         """One entry per listed row: picks (or adds) a single model parameter (lin_op.py:504-522)."""
         if col is None:
             col = self.col_N
@@ -304,7 +328,9 @@ class lin_op(object):
             val_d = torch.ones(ind_d.shape, dtype=torch.float64, device=dev)
         else:
             val_d = _cabi.to_dev(np.asarray(val).ravel(), torch.float64) if not isinstance(val, torch.Tensor) else val
-        self._set_device(ind_d.contiguous(), col_d.contiguous(), val_d.contiguous())
+        col_d, val_d = col_d.contiguous(), val_d.contiguous()
+        # _regular: the caller guarantees ind == arange(n): one entry per row, in row order
+        self._set_device(ind_d.contiguous(), col_d, val_d, blocks=[(col_d.reshape(-1, 1), val_d.reshape(-1, 1))] if _regular else None)
         if _toc is not None:       # caller already knows the distinct rows / columns (avoids sorting 1e7 indices)
             self.TOC['rows'], self.TOC['cols'] = {self.name: _toc[0]}, {self.name: _toc[1]}
         else:
@@ -385,7 +411,10 @@ class lin_op(object):
                 self.add(this_op)
             return self
         if self._on_device() and op._on_device():
-            self._set_device(*[torch.cat((self._dev[f].reshape(-1), op._dev[f].reshape(-1))) for f in _FIELDS])
+            blocks = None
+            if self._blocks and op._blocks and self._blocks[0][0].shape[0] == op._blocks[0][0].shape[0]:
+                blocks = self._blocks + op._blocks
+            self._set_device(*[torch.cat((self._dev[f].reshape(-1), op._dev[f].reshape(-1))) for f in _FIELDS], blocks=blocks)
         else:
             for f in _FIELDS:
                 self._set_host(f, np.append(getattr(self, f), getattr(op, f)))
@@ -441,11 +470,16 @@ class lin_op(object):
             label = candidate
             shifted = []
             for key, rows in op.TOC['rows'].items():
-                these = _index_array(rows) + next_row
+                # contiguous row lists stay `range` objects (no 8 bytes per row on the host for 2e6 constraint rows);
+                # index arrays with them through rows_of()
+                if isinstance(rows, range) and rows.step == 1:
+                    these = range(rows.start + next_row, rows.stop + next_row)
+                else:
+                    these = _index_array(rows) + next_row
                 self.TOC['rows'][key] = these
-                shifted.append(these.ravel())
+                shifted.append(these)
             if label not in self.TOC['rows']:
-                self.TOC['rows'][label] = np.concatenate(shifted) if shifted else np.array([], dtype=int)
+                self.TOC['rows'][label] = _join_rows(shifted)
             next_row += op.N_eq
         self.N_eq = next_row
         if on_dev:
@@ -458,7 +492,7 @@ class lin_op(object):
             self.expected = np.concatenate(expected)
         self._ind0 = [p for op in ops for p in op._ind0_parts()]        # joined on demand
         if self.name is not None and len(self.name) > 0:
-            self.TOC['rows'][self.name] = np.arange(0, next_row)
+            self.TOC['rows'][self.name] = range(0, next_row)
         self._update_shape()
         return self
 
@@ -636,7 +670,12 @@ class lin_op(object):
         key = (int(row_N), int(col_N))
         if cacheable and key in self._csr_cache:
             return self._csr_cache[key]
-        indptr, indices, data = _cabi.coo_to_csr(r, c, v, int(row_N), int(col_N))
+        res = None
+        if cacheable and self._blocks and len(self._blocks) <= 8 and int(self._blocks[0][0].shape[0]) == int(row_N):
+            res = _cabi.blocks_to_csr(self._blocks, int(row_N), int(col_N))      # row-regular blocks: no sort
+        if res is None:
+            res = _cabi.coo_to_csr(r, c, v, int(row_N), int(col_N))
+        indptr, indices, data = res
         out = DeviceCSR(indptr, indices, data, key)
         if cacheable:
             self._csr_cache[key] = out

@@ -28,7 +28,7 @@ from .calc_sigma_extra import sigma_extra_device, sigma_extra_on_grid_device
 from .constraint_functions import setup_smoothness_constraints, build_reference_epoch_matrix
 from .data_slope_bias import data_slope_bias
 from .grid_functions import setup_grids, setup_averaging_ops, setup_z0_avg
-from .lin_op import lin_op, DeviceCSR
+from .lin_op import lin_op, DeviceCSR, rows_of
 from .point_data import data as point_data, grid_data
 from .setup_sensor_grid_bias import setup_sensor_grid_bias, parse_sensor_bias_grids
 from .solver import NormalSolver, grid_structure, coarse_structure
@@ -346,7 +346,7 @@ def _bias_statistics(b_dict, bias_id, r, tse, n_bias, dist):
         b_dict[key_rms] = [float(v) if c > 0 else np.nan for v, c in zip(std.cpu().numpy(), n_all.cpu().numpy())]
 
 
-def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args, dist=None):
+def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args, dist=None, stages=None):
     """Reshape the solution into grids and compute per-node data counts / misfits, bias statistics and the
     constraint residual summaries (smooth_fit.py:276-352).  ``dev_fields`` holds this rank's per-point
     device arrays (z, sigma, z_est, three_sigma_edit, sigma_extra, bias_ID).  The G^T products run on the GPU
@@ -361,12 +361,15 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
         fields = {coord: ctr for coord, ctr in zip(op.dst_grid.coords, op.dst_grid.ctrs)}
         fields.update({'cell_area': op.dst_grid.cell_area, key: op.grid_prod(m0)})
         m[key] = grid_data().from_dict(fields)
+    mark = stages.mark if stages is not None else (lambda name: None)
+    mark('pm:grids')
     f = dev_fields
     tse = f['three_sigma_edit'].bool()
     r = f['z'] - f['z_est']
     if len(bias_model.keys()) > 0:
         m['bias'], m['slope_bias'] = parse_biases(m0, bias_model, args['bias_params'])
         _bias_statistics(m['bias'], f['bias_ID'], r, tse, len(bias_model['bias_ID_dict']), dist)
+    mark('pm:bias_stats')
     m['all'] = m0
     m['extent'] = np.concatenate((z0g.bds[1], z0g.bds[0]))
     m['sensor_bias_grids'] = parse_sensor_bias_grids(m0, G_data, grids)
@@ -378,8 +381,9 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
     rc = ru / Ec
     for eq_type in ['d2z_dt2', 'grad2_z0', 'grad2_dzdt', 'grad2_PS']:
         if eq_type in Gc.TOC['rows']:
-            R[eq_type] = np.sum(rc[Gc.TOC['rows'][eq_type]] ** 2)
-            RMS[eq_type] = np.sqrt(np.mean(ru[Gc.TOC['rows'][eq_type]] ** 2))
+            R[eq_type] = np.sum(rc[rows_of(Gc.TOC['rows'][eq_type])] ** 2)
+            RMS[eq_type] = np.sqrt(np.mean(ru[rows_of(Gc.TOC['rows'][eq_type])] ** 2))
+    mark('pm:constraint_residuals')
     # data counts and misfit maps: G^T applied to the edited-in indicator, r^2 and scaled r^2
     r_in = torch.where(tse, r, torch.zeros_like(r))
     if args['sigma_extra_relax']:
@@ -399,6 +403,7 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
         with np.errstate(invalid='ignore'):
             for key in ('misfit_scaled_rms', 'misfit_rms'):
                 m[ff].assign({key: np.sqrt(sums[key][cols].reshape(grids[ff].shape) / count)})
+    mark('pm:count_misfit')
     # chi^2 and RMS of the edited-in data residuals (smooth_fit.py:676-678)
     tot = torch.stack([(rs * rs).sum(), (r_in * r_in).sum(), tse.sum().to(torch.float64)])
     tot = (tot if dist is None else dist.allreduce_sum(tot)).cpu().numpy()
@@ -573,7 +578,7 @@ def smooth_fit(**kwargs):
     if rz is not None and whole:
         # all points valid: the validity pass already produced the interpolation triplets
         for op, res, g in ((op_z0, rz, grids['z0']), (op_dz, rd, grids['dz'])):
-            op._set_device(res[0], res[1], res[2])
+            op._set_device(res[0], res[1], res[2], blocks=[(res[1], res[2])] if res[1].dim() == 2 else None)
             op.N_eq = n_all
             op._ind0 = [('arange', n_all)]
             op.TOC['rows'] = {op.name: range(n_all)}
@@ -601,7 +606,7 @@ def smooth_fit(**kwargs):
         ids_loc = bias_id_d[lo:hi]
         G_bias = lin_op(name='data_bias', col_0=col_0, col_N=col_N).data_bias(
             torch.arange(hi - lo, dtype=torch.int32, device=ids_loc.device), col=(ids_loc + int(col_0)).contiguous(),
-            _toc=(np.arange(hi - lo, dtype=int), np.arange(col_0, col_N, dtype=int)))
+            _toc=(range(hi - lo), np.arange(col_0, col_N, dtype=int)), _regular=True)
         ii = np.arange(n_bias, dtype=int)
         Gc_bias = lin_op(name='constraint_data_bias', col_0=col_0, col_N=col_N).data_bias(ii, col=col_0 + ii)
         for key in bias_model['bias_ID_dict']:
@@ -644,6 +649,7 @@ def smooth_fit(**kwargs):
                 raise NotImplementedError('jitter_* / stripe_* sensor grid biases need DEM files (GDAL): out of scope')
             if len(params) and 'spacing' in params:
                 setup_sensor_grid_bias(data, grids, G_data, constraint_op_list, _row_range=row_range, **params)
+    no_priors = all(op.prior is None for op in constraint_op_list)      # the default: every constraint pulls towards zero
     for op in constraint_op_list:
         if op.prior is None:
             op.prior = np.zeros_like(op.expected)
@@ -651,16 +657,24 @@ def smooth_fit(**kwargs):
     stages.mark('c:bias_ops')
     Gc = lin_op(None, name='constraints').vstack(constraint_op_list)
     stages.mark('c:vstack')
-    Ec = np.zeros(Gc.N_eq)
-    for op in constraint_op_list:
-        Ec[Gc.TOC['rows'][op.name]] = op.expected
+    names = [op.name for op in constraint_op_list]
+    if len(set(names)) == len(names) and sum(int(op.N_eq) for op in constraint_op_list) == int(Gc.N_eq) \
+            and all(np.size(op.expected) == op.N_eq for op in constraint_op_list):
+        Ec = np.concatenate([np.asarray(op.expected, dtype=float).ravel() for op in constraint_op_list])    # rows are stacked in list order
+    else:
+        Ec = np.zeros(Gc.N_eq)
+        for op in constraint_op_list:
+            Ec[rows_of(Gc.TOC['rows'][op.name])] = op.expected
     if bool((s_loc == 0).any().item()):
         raise ValueError('zero value found in data sigma')
-    if np.any(Ec == 0):
+    if Ec.size and Ec.min() <= 0 and np.any(Ec == 0):
         raise ValueError('zero value found in constraint sigma')
     # TCinv and rhs stay on the device for the data rows (iterate_fit accepts tensors or NumPy)
-    TCinv = DiagonalOp(torch.cat((1. / s_loc, _cabi.to_dev(1. / Ec, f64))))
-    rhs = torch.cat((z_loc, _cabi.to_dev(np.concatenate([op.prior for op in constraint_op_list]), f64)))
+    TCinv = DiagonalOp(torch.cat((1. / s_loc, 1. / _cabi.to_dev(Ec, f64))))
+    if no_priors:
+        rhs = torch.cat((z_loc, torch.zeros(int(Gc.N_eq), dtype=f64, device=z_loc.device)))
+    else:
+        rhs = torch.cat((z_loc, _cabi.to_dev(np.concatenate([op.prior for op in constraint_op_list]), f64)))
     stages.mark('c:Ec_rhs')
     Ip_c = build_reference_epoch_matrix(G_data, Gc, grids, args['reference_epoch'])
     stages.mark('c:Ip_c')
@@ -716,7 +730,7 @@ def smooth_fit(**kwargs):
                       'bias_ID': None if bias_id_d is None else bias_id_d[lo:hi]}
         stages.mark('outputs_d2h')
         parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args,
-                    dist=dist if (dist is not None and dist.world > 1) else None)
+                    dist=dist if (dist is not None and dist.world > 1) else None, stages=stages)
         stages.mark('parse_model')
     else:
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)

@@ -119,6 +119,23 @@ def coo_to_csr(rows, cols, vals, n_rows, n_cols):
     return torch.from_numpy(indptr), torch.from_numpy(indices), torch.from_numpy(data)
 
 
+def blocks_to_csr(blocks, n_rows, n_cols):
+    """lss_blocks_to_csr: rows take their entries block after block, zeros dropped; None unless every row ascends."""
+    for c, v in blocks:
+        _arg(c, _I32, 'blocks_to_csr cols'), _arg(v, _F64, 'blocks_to_csr vals')
+        assert c.shape == v.shape and c.dim() == 2 and c.shape[0] == n_rows
+    cols = np.concatenate([_np(c) for c, _ in blocks], axis=1)
+    vals = np.concatenate([_np(v) for _, v in blocks], axis=1)
+    keep = vals != 0
+    big = np.where(keep, cols, -1).astype(np.int64)
+    run = np.maximum.accumulate(big, axis=1)
+    prev = np.concatenate([np.full((cols.shape[0], 1), -1, dtype=np.int64), run[:, :-1]], axis=1)
+    if np.any(keep & ((cols <= prev) | (cols >= n_cols))):
+        return None
+    indptr = np.concatenate([[0], np.cumsum(keep.sum(axis=1))]).astype(np.int32)
+    return torch.from_numpy(indptr), torch.from_numpy(cols[keep].astype(np.int32)), torch.from_numpy(vals[keep].astype(float))
+
+
 def csr_transpose(indptr, indices, data, n_rows, n_cols):
     _arg(indptr, _I32, 'csr_transpose indptr'), _arg(indices, _I32, 'csr_transpose indices'), _arg(data, _F64, 'csr_transpose data')
     T = O.csr_matrix(_np(indptr), _np(indices), _np(data), (n_rows, n_cols)).T.tocsr()
@@ -279,7 +296,7 @@ class NormalSolver(object):
         pass
 
 
-_CABI_NAMES = ('device', 'to_dev', 'to_host', 'interp_coo', 'stencil_coo', 'coo_extent', 'coo_to_csr', 'csr_transpose',
+_CABI_NAMES = ('device', 'to_dev', 'to_host', 'interp_coo', 'stencil_coo', 'coo_extent', 'coo_to_csr', 'blocks_to_csr', 'csr_transpose',
                'dense_rank', 'group_median', 'spmv', 'SpmvPlan', 'spmv_planned', 'csr_rmatvec', 'rde', 'sigma_extra',
                'edit_mask', 'spatial_order')
 

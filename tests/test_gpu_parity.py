@@ -224,6 +224,72 @@ def test_rde_and_sigma_extra_known_answers(L):
     assert np.max(np.abs(got - want)) < 1e-12
 
 
+def test_sort_free_fast_paths_match_the_sorting_paths(L, monkeypatch):
+    """Row-regular COO blocks -> CSR without a sort, small-integer dense ranks by presence table, medians of constant
+    groups by min == max: each equals the general sorting path bit for bit (and falls back to it when it must)."""
+    _c = L._cabi
+    rng = np.random.default_rng(31)
+    n = 50_000
+    # interpolation-like blocks: ascending columns per row, some exact zeros, two grids + one bias column per row
+    c1 = np.sort(rng.choice(1000, (n, 4)), axis=1).astype(np.int32); c1 += np.arange(4, dtype=np.int32) * 1000
+    c2 = (4000 + np.sort(rng.choice(500, (n, 8)), axis=1) + np.arange(8) * 500).astype(np.int32)
+    c3 = (8000 + rng.integers(0, 50, (n, 1))).astype(np.int32)
+    v1, v2, v3 = rng.normal(size=(n, 4)), rng.normal(size=(n, 8)), np.ones((n, 1))
+    v1[rng.random((n, 4)) < 0.2] = 0.0
+    v2[::7] = 0.0
+    blocks = [(_c.to_dev(c, torch.int32), _c.to_dev(v)) for c, v in ((c1, v1), (c2, v2), (c3, v3))]
+    got = _c.blocks_to_csr(blocks, n, 8050)
+    rows = np.repeat(np.arange(n, dtype=np.int32), 13)
+    cols = np.concatenate([c1, c2, c3], axis=1).ravel(); vals = np.concatenate([v1, v2, v3], axis=1).ravel()
+    want = _c.coo_to_csr(_c.to_dev(rows, torch.int32), _c.to_dev(cols, torch.int32), _c.to_dev(vals), n, 8050)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    c1[17, 0], c1[17, 1] = c1[17, 1], c1[17, 0]                       # one row out of order -> the caller must sort
+    v1[17, :2] = 1.0
+    assert _c.blocks_to_csr([(_c.to_dev(c1, torch.int32), _c.to_dev(v1))] + blocks[1:], n, 8050) is None
+    assert _c.blocks_to_csr(blocks, n, 8049) is None                  # column outside the matrix
+    # dense ranks of integer-valued doubles (with NaN -> -9999 and -0.0)
+    x = rng.integers(-40, 1400, 300_000).astype(float); x[::11] = np.nan; x[5] = -0.0
+    xd = _c.to_dev(x)
+    r_fast, u_fast = _c.dense_rank(xd)
+    monkeypatch.setenv('LSS_RANK_SORT', '1')
+    r_sort, u_sort = _c.dense_rank(xd)
+    assert torch.equal(r_fast, r_sort) and np.array_equal(u_fast, u_sort)
+    # group medians: constant groups (fast) and mixed groups (fallback), an empty group in both
+    ids = rng.integers(0, 40, 200_000).astype(np.int32); ids[ids == 13] = 12
+    const = 0.01 * (1 + ids.astype(float))
+    m_sort_c = _c.group_median(_c.to_dev(ids, torch.int32), _c.to_dev(const), 40).cpu().numpy()
+    mixed = const.copy(); mixed[ids == 3] = rng.normal(size=int((ids == 3).sum()))
+    m_sort_m = _c.group_median(_c.to_dev(ids, torch.int32), _c.to_dev(mixed), 40).cpu().numpy()
+    monkeypatch.delenv('LSS_RANK_SORT')
+    m_fast_c = _c.group_median(_c.to_dev(ids, torch.int32), _c.to_dev(const), 40).cpu().numpy()
+    m_fast_m = _c.group_median(_c.to_dev(ids, torch.int32), _c.to_dev(mixed), 40).cpu().numpy()
+    assert np.array_equal(m_fast_c, m_sort_c, equal_nan=True) and np.array_equal(m_fast_m, m_sort_m, equal_nan=True)
+    assert np.isnan(m_fast_c[13]) and m_fast_c[5] == 0.06
+
+
+def test_rde_candidate_selection_is_exact(L):
+    """Above 2^16 points one RDE evaluation is a binned histogram pass + a compaction pass + an exact select over the
+    candidates: the order statistics (and the interpolation between them) stay bit-identical to NumPy's sort for
+    heavy tails, huge / tiny magnitudes, ties, masks, per-point sigmas and degenerate inputs."""
+    rng = np.random.default_rng(21)
+    _c = L._cabi
+    n = 400_000
+    cases = {'normal': rng.normal(0, 1, n), 'heavy': rng.standard_t(1.5, n) * 1e3, 'tiny': rng.normal(0, 1e-9, n),
+             'huge': rng.normal(0, 1e7, n), 'ties': np.round(rng.normal(0, 2, n)), 'constant': np.full(n, 0.25),
+             'one_sided': np.abs(rng.normal(0, 1, n)), 'mixed_zero': np.where(rng.random(n) < 0.7, 0.0, rng.normal(0, 1, n))}
+    for name, v in cases.items():
+        assert L.RDE(v) == O.rde(v), name
+    r = rng.normal(0, 1, n); sg = rng.uniform(0.05, 2.0, n); m = rng.random(n) < 0.9
+    for s1 in (0.0, 0.37, 5.0):
+        got, n_used = _c.rde(_c.to_dev(r), _c.to_dev(sg), _c.to_dev(m.astype(np.uint8), torch.uint8), s1)
+        want = O.rde((r / np.sqrt(s1 ** 2 + sg ** 2))[m])
+        assert got == want and n_used == int(m.sum()), s1
+    got = L.calc_sigma_extra(r * 3, sg, m)
+    want = O.sigma_extra(r * 3, sg, m)
+    assert np.max(np.abs(got - want)) < 1e-12
+
+
 def test_edit_mask_kernel(L):
     rng = np.random.default_rng(15)
     n = 100_000
