@@ -190,6 +190,8 @@ def run_b200(a):
     dev = {f: host[f].cuda(non_blocking=True) for f in fields}
     h2d = sum(host[f].numel() * 8 for f in fields)
     dist_arg = dist if world > 1 else None
+    if world == 1 and os.environ.get('LSS_SHARD_SINGLE'):       # diagnostics: the row-sharded solver with a local mailbox
+        dist_arg = parallel.single_rank_context()
 
     def fit(inputs, profile, stages=False):
         D = L.point_data.data().from_dict({f: (inputs[f] if isinstance(inputs[f], torch.Tensor) and inputs[f].is_cuda

@@ -189,6 +189,14 @@ int lss_comm_unique_id(char *id_h);
 int lss_comm_create(lss_comm_t **comm, const char *id_h, int32_t rank, int32_t n_ranks);
 int lss_comm_destroy(lss_comm_t *comm);
 int lss_comm_allreduce_f64(lss_comm_t *comm, double *buf, int64_t n, void *stream); /* in-place sum */
+/* Peer-to-peer mailbox for the row-sharded PCG (lss_solver_create_sharded): every rank allocates `bytes` of device memory
+ * (zeroed) and gets a 64-byte CUDA IPC handle for it; the handles of all ranks, concatenated in rank order (any host
+ * transport), are then opened so that kernels of this rank can store straight into the peers' boxes over NVLink.
+ * With one rank the box is local and handles_h may be NULL.  lss_comm_box_bytes: size of the open box (0: none). */
+#define LSS_IPC_HANDLE_BYTES 64
+int lss_comm_box_alloc(lss_comm_t *comm, int64_t bytes, char *handle_h);
+int lss_comm_box_open(lss_comm_t *comm, const char *handles_h);
+int lss_comm_box_bytes(lss_comm_t *comm, int64_t *bytes_h);
 
 /* ------------------------------------------------------------------ normal-equation PCG solve */
 
@@ -220,6 +228,23 @@ int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, int64_t n_co
                              const int32_t *ct_indptr, const int32_t *ct_indices, const double *ct_data,
                              const double *rhs, const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm,
                              void *stream);
+/* Row-sharded form for the GPUs of one node (one process per GPU): rank k owns a contiguous range of preconditioner
+ * blocks [block_lo, block_hi) of the structure given later to lss_solver_set_structure -- the rows of A^T W A at their
+ * columns, the block inverses, the matching entries of x and of the residual -- while the search direction p is
+ * replicated.  A = [G_ext; C] holds every row that touches an own column: the rank's own points
+ * (rows [own_row_lo, own_row_hi)), halo copies of neighbouring ranks' points around them, and all constraint rows
+ * (rows [con_row_lo, n_rows)); owned_cols[n_cols] flags the own columns (device).  Per CG iteration there is NO
+ * collective: the local product q_own = N_own p is followed by one kernel that exchanges the p.q partials, the own
+ * slice of z = M^-1 r, the partial coarse restriction and the partial bias coupling with plain stores into the peers'
+ * mailboxes over NVLink (lss_comm_box_open) behind sequence-numbered flags.  NCCL (the communicator's all-reduce) is used
+ * only in lss_solver_set_weights and at the start / end of a solve.  [elim_begin, elim_end) must be the range later
+ * given to lss_solver_set_structure.  x handed to lss_solver_solve must be complete on every rank and comes back
+ * complete and bit-identical on every rank.  Works with one rank too (the mailbox is then local). */
+int lss_solver_create_sharded(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, int32_t row_len, const int32_t *indptr,
+                              const int32_t *indices, const double *data, const double *rhs, const int32_t *fixed_cols,
+                              int64_t n_fixed, const uint8_t *owned_cols, int32_t block_lo, int32_t block_hi,
+                              int64_t own_row_lo, int64_t own_row_hi, int64_t con_row_lo, int64_t elim_begin, int64_t elim_end,
+                              lss_comm_t *comm, void *stream);
 /* Which operator form the solver uses and its size: info_h[0] = 0 generic CSR pair (A, A^T), 1 fused ELL pass,
  * 2 explicit normal matrix; info_h[1] = nnz of the explicit normal matrix (0 otherwise); info_h[2] = column pairs
  * sorted by its symbolic phase; info_h[3] = rows of A held in ELL form; info_h[4] = preconditioner blocks;

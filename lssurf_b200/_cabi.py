@@ -57,9 +57,13 @@ SIGNATURES = {
     'lss_comm_create': [C.POINTER(_vp), C.c_char_p, _i32, _i32],
     'lss_comm_destroy': [_vp],
     'lss_comm_allreduce_f64': [_vp, _vp, _i64, _vp],
+    'lss_comm_box_alloc': [_vp, _i64, C.c_char_p],
+    'lss_comm_box_open': [_vp, C.c_char_p],
+    'lss_comm_box_bytes': [_vp, _pi64],
     'lss_solver_create': [C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     'lss_solver_destroy': [_vp],
     'lss_solver_create_blocks': [C.POINTER(_vp), _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    'lss_solver_create_sharded': [C.POINTER(_vp), _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _vp, _vp],
     'lss_solver_set_weights': [_vp, _vp],
     'lss_solver_solve': [_vp, _vp, _f64, _i32, _pi32, _pf64],
     'lss_solver_set_profile': [_vp, _i32],
@@ -297,7 +301,7 @@ def csr_transpose(indptr, indices, data, n_rows, n_cols):
     return t_indptr, t_indices[:nnz], t_data[:nnz]
 
 
-def spatial_order(fine, coarse, pts):
+def spatial_order(fine, coarse, pts, return_keys=False):
     """Permutation (int64 CUDA tensor) that sorts points by (coarse cell, fine cell, time cell)."""
     L = lib()
     n = int(pts[0].numel())
@@ -306,7 +310,10 @@ def spatial_order(fine, coarse, pts):
     parr = (C.c_void_p * nd)(*[p.data_ptr() for p in pts[:nd]])
     bits = C.c_int32(0)
     check(L.lss_cell_keys(C.byref(fine), C.byref(coarse), parr, n, ptr(keys), C.byref(bits), stream()))
-    return argsort_u64(keys, bits.value).to(torch.int64)
+    order = argsort_u64(keys, bits.value).to(torch.int64)
+    if return_keys:
+        return order, keys
+    return order
 
 
 def argsort_u64(keys, key_bits):

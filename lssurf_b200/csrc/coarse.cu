@@ -12,7 +12,7 @@ namespace cgx = cooperative_groups;
 __global__ void __launch_bounds__(256)
 galerkin_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ data,
                 const int4 *__restrict__ cp_idx, const float4 *__restrict__ cp_w, int n_c, int64_t e0, int64_t e1, int n_e,
-                double *__restrict__ A, double *__restrict__ B) {
+                double *__restrict__ A, double *__restrict__ B, int only_b) {
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const unsigned lane = lane_id();
     for (int64_t i = warp; i < n_rows; i += n_warps) {
@@ -32,6 +32,7 @@ galerkin_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__res
                     if (pa[a] >= 0) atomicAdd(B + (size_t)pa[a] * n_e + (j - e0), wa[a] * v);
                 continue;
             }
+            if (only_b) continue;
             const int4 pj = __ldg(cp_idx + j);
             const float4 wj = __ldg(cp_w + j);
             const int pb[4] = {pj.x, pj.y, pj.z, pj.w};
@@ -113,6 +114,14 @@ gj_inverse_kernel(int n, double *X, double *Y, int *bad) {
     }
 }
 
+// Bt[e][m] = B[m][e]
+__global__ void __launch_bounds__(256) transpose_kernel(int n_c, int n_e, const double *__restrict__ B, double *__restrict__ Bt) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_c * n_e) return;
+    const int e = (int)(t / n_c), m = (int)(t - (int64_t)e * n_c);
+    Bt[t] = B[(size_t)m * n_e + e];
+}
+
 // out = (in + in^T) / 2
 __global__ void __launch_bounds__(256) symmetrise_kernel(int n, const double *__restrict__ in, double *__restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,7 +173,7 @@ coarse_prolong_add_kernel(int64_t n_cols, const int4 *__restrict__ cp_idx, const
 int coarse_destroy(CoarseSpace *cs) {
     if (!cs) return LSS_OK;
     cudaStream_t st = cs->stream;
-    void *ptrs[] = {cs->cp_idx, cs->cp_w, cs->pt_ptr, cs->pt_col, cs->pt_w, cs->A, cs->A2, cs->B, cs->rc_part, cs->zc_part, cs->rc, cs->zc, cs->rczc, cs->bad};
+    void *ptrs[] = {cs->cp_idx, cs->cp_w, cs->pt_ptr, cs->pt_col, cs->pt_w, cs->A, cs->A2, cs->B, cs->Bt, cs->rc_part, cs->zc_part, cs->rc, cs->zc, cs->rczc, cs->bad};
     for (void *p : ptrs)
         if (p) cudaFreeAsync(p, st);
     delete cs;
@@ -188,6 +197,7 @@ int coarse_create(CoarseSpace **out, int64_t n_cols, int n_c, const int32_t *cp_
               cudaMallocAsync((void **)&cs->A, sizeof(double) * nn, st) == cudaSuccess &&
               cudaMallocAsync((void **)&cs->A2, sizeof(double) * nn, st) == cudaSuccess &&
               cudaMallocAsync((void **)&cs->B, sizeof(double) * (size_t)n_c * (n_e > 0 ? n_e : 1), st) == cudaSuccess &&
+              cudaMallocAsync((void **)&cs->Bt, sizeof(double) * (size_t)n_c * (n_e > 0 ? n_e : 1), st) == cudaSuccess &&
               cudaMallocAsync((void **)&cs->rc_part, sizeof(double) * CS_CHUNKS_MAX * n_c, st) == cudaSuccess &&
               cudaMallocAsync((void **)&cs->zc_part, sizeof(double) * CS_CHUNKS_MAX * n_c, st) == cudaSuccess &&
               cudaMallocAsync((void **)&cs->rc, sizeof(double) * n_c, st) == cudaSuccess &&
@@ -220,7 +230,7 @@ int coarse_factor(CoarseSpace *cs, int64_t n_rows, const int32_t *indptr, const 
     LSS_CUDA(cudaMemsetAsync(cs->bad, 0, sizeof(int), st));
     galerkin_kernel<<<stride_grid(n_rows * 32, 256, 16), 256, 0, st>>>(n_rows, indptr, indices, data, reinterpret_cast<const int4 *>(cs->cp_idx),
                                                                        reinterpret_cast<const float4 *>(cs->cp_w), n, e0, e1, n_e > 0 ? n_e : 1,
-                                                                       cs->A, cs->B);
+                                                                       cs->A, cs->B, 0);
     LSS_LAUNCH_CHECK();
     LSS_TRY(comm_allreduce(comm, cs->A, (int64_t)nn, 0, 0, st));
     if (n_e > 0) {
@@ -252,11 +262,29 @@ int coarse_factor(CoarseSpace *cs, int64_t n_rows, const int32_t *indptr, const 
     return LSS_OK;
 }
 
-int coarse_apply_add(CoarseSpace *cs, const double *r, double *z) {
+// B = P^T N_gE (and its transpose) for the CURRENT values of N, summed over ranks: the row-sharded CG needs it exactly
+// for T^T (P z_c) even when S_c itself is kept from the first weights.
+int coarse_update_b(CoarseSpace *cs, int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, int64_t e0,
+                    int64_t e1, lss_comm *comm) {
+    cudaStream_t st = cs->stream;
+    const int n = cs->n_c, n_e = (int)(e1 - e0);
+    if (n_e <= 0) return LSS_OK;
+    LSS_CUDA(cudaMemsetAsync(cs->B, 0, sizeof(double) * (size_t)n * n_e, st));
+    galerkin_kernel<<<stride_grid(n_rows * 32, 256, 16), 256, 0, st>>>(n_rows, indptr, indices, data, reinterpret_cast<const int4 *>(cs->cp_idx),
+                                                                       reinterpret_cast<const float4 *>(cs->cp_w), n, e0, e1, n_e, cs->A, cs->B, 1);
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(comm_allreduce(comm, cs->B, (int64_t)n * n_e, 0, 0, st));
+    transpose_kernel<<<ceil_div((int64_t)n * n_e, 256), 256, 0, st>>>(n, n_e, cs->B, cs->Bt);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+int coarse_apply_add(CoarseSpace *cs, const double *r, double *z, lss_comm *comm) {
     cudaStream_t st = cs->stream;
     const int n = cs->n_c;
     coarse_restrict_kernel<<<ceil_div((int64_t)n * 32, 256), 256, 0, st>>>(n, cs->pt_ptr, cs->pt_col, cs->pt_w, r, cs->rc);
     LSS_LAUNCH_CHECK();
+    LSS_TRY(comm_allreduce(comm, cs->rc, n, 0, 0, st));       // row-sharded ranks hold P^T at their own columns only
     coarse_matvec_kernel<<<ceil_div((int64_t)n * 32, 256), 256, 0, st>>>(n, cs->inv, cs->rc, cs->zc);
     LSS_LAUNCH_CHECK();
     coarse_prolong_add_kernel<<<stride_grid(cs->n_cols, 256), 256, 0, st>>>(cs->n_cols, reinterpret_cast<const int4 *>(cs->cp_idx),

@@ -27,7 +27,7 @@ struct CoarseSpace {
     float *pt_w;                  // ... and weights
     double *A, *A2;               // [n_c][n_c] Galerkin matrix / Gauss-Jordan ping-pong; the inverse ends in `inv`
     double *inv;                  // -> A or A2
-    double *B;                    // [n_c][n_e] P^T N_gE
+    double *B, *Bt;               // [n_c][n_e] P^T N_gE and its transpose [n_e][n_c]
     double *rc_part, *zc_part;    // [CS_CHUNKS_MAX][n_c] partial restrictions / partial coarse solutions of the step kernel
     double *rc, *zc, *rczc;       // [n_c]
     int *bad;                     // device flag: a pivot was not positive
@@ -45,7 +45,9 @@ int coarse_destroy(CoarseSpace *cs);
 // einv = 1 / N_EE), summed over ranks, then inverted.  Leaves cs->ready false when S_c is not positive definite.
 int coarse_factor(CoarseSpace *cs, int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, int64_t e0,
                   int64_t e1, const double *einv, lss_comm *comm);
+int coarse_update_b(CoarseSpace *cs, int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, int64_t e0,
+                    int64_t e1, lss_comm *comm);
 // z += P S_c^-1 P^T r   (stand-alone kernels for the set-up path; the CG step kernel has its own fused phases)
-int coarse_apply_add(CoarseSpace *cs, const double *r, double *z);
+int coarse_apply_add(CoarseSpace *cs, const double *r, double *z, lss_comm *comm = nullptr);
 
 }  // namespace lss

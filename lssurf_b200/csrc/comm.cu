@@ -73,7 +73,8 @@ extern "C" int lss_comm_unique_id(char *id_h) {
 
 extern "C" int lss_comm_create(lss_comm_t **comm, const char *id_h, int32_t rank, int32_t n_ranks) {
     if (!comm || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(LSS_EINVAL, "comm_create: bad rank/n_ranks");
-    lss_comm *c = new lss_comm{nullptr, rank, n_ranks};
+    lss_comm *c = new lss_comm();
+    c->nccl = nullptr; c->rank = rank; c->n_ranks = n_ranks;
     if (n_ranks > 1) {
         int rc = load_nccl();
         if (rc != LSS_OK) { delete c; return rc; }
@@ -88,8 +89,58 @@ extern "C" int lss_comm_create(lss_comm_t **comm, const char *id_h, int32_t rank
     return LSS_OK;
 }
 
+// ---- peer-to-peer mailbox over CUDA IPC ---------------------------------------------------------------------------
+extern "C" int lss_comm_box_alloc(lss_comm_t *comm, int64_t bytes, char *handle_h) {
+    if (!comm || bytes <= 0 || !handle_h) return fail(LSS_EINVAL, "comm_box_alloc: bad arguments");
+    if (comm->n_ranks > LSS_MAX_RANKS) return fail(LSS_EINVAL, "comm_box_alloc: at most %d ranks", LSS_MAX_RANKS);
+    if (comm->box_local) return fail(LSS_EINVAL, "comm_box_alloc: the mailbox exists already");
+    // plain cudaMalloc (not the stream-ordered pool): IPC handles need a dedicated allocation
+    LSS_CUDA(cudaMalloc(&comm->box_local, (size_t)bytes));
+    LSS_CUDA(cudaMemset(comm->box_local, 0, (size_t)bytes));
+    LSS_CUDA(cudaDeviceSynchronize());
+    comm->box_bytes = (size_t)bytes;
+    cudaIpcMemHandle_t h;
+    memset(handle_h, 0, LSS_IPC_HANDLE_BYTES);
+    if (comm->n_ranks > 1) {
+        LSS_CUDA(cudaIpcGetMemHandle(&h, comm->box_local));
+        static_assert(sizeof(h) <= LSS_IPC_HANDLE_BYTES, "IPC handle size");
+        memcpy(handle_h, &h, sizeof(h));
+    }
+    return LSS_OK;
+}
+
+extern "C" int lss_comm_box_open(lss_comm_t *comm, const char *handles_h) {
+    if (!comm || !comm->box_local) return fail(LSS_EINVAL, "comm_box_open: call lss_comm_box_alloc first");
+    for (int r = 0; r < comm->n_ranks; ++r) {
+        if (r == comm->rank) { comm->box_peer[r] = comm->box_local; continue; }
+        if (!handles_h) return fail(LSS_EINVAL, "comm_box_open: null handles");
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles_h + (size_t)r * LSS_IPC_HANDLE_BYTES, sizeof(h));
+        cudaError_t e = cudaIpcOpenMemHandle(&comm->box_peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LSS_ECUDA, "comm_box_open: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+    }
+    comm->box_open = true;
+    return LSS_OK;
+}
+
+extern "C" int lss_comm_box_bytes(lss_comm_t *comm, int64_t *bytes_h) {
+    if (!bytes_h) return fail(LSS_EINVAL, "comm_box_bytes: null output");
+    *bytes_h = comm && comm->box_open ? (int64_t)comm->box_bytes : 0;
+    return LSS_OK;
+}
+
 extern "C" int lss_comm_destroy(lss_comm_t *comm) {
     if (!comm) return LSS_OK;
+    if (comm->box_local) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < comm->n_ranks; ++r)
+            if (r != comm->rank && comm->box_peer[r]) cudaIpcCloseMemHandle(comm->box_peer[r]);
+        cudaFree(comm->box_local);
+        comm->box_local = nullptr;
+    }
     if (comm->nccl && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)comm->nccl);
     delete comm;
     return LSS_OK;

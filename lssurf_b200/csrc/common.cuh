@@ -216,6 +216,8 @@ struct NormalMatrix {
     SpmvTmaPlan tma_plan;      // built at the first fast product for the row count it is asked for
     int64_t tma_nnz;           // entries of the rows the plan covers
     SpmvPlan plan;
+    const unsigned char *owned;   // row-sharded N: flags of this rank's own columns (borrowed; null: all rows)
+    int64_t own_e0, own_e1;       // eliminated block whose rows keep their entries at own columns
     SpmvPlan plan_part;        // plan of the leading rows [0, part_rows) (an eliminated trailing block is left out of the product)
     int64_t part_rows, part_nnz;
     cudaStream_t stream;
@@ -223,7 +225,8 @@ struct NormalMatrix {
 extern int g_opt_step_kernel;       // -1: unset (environment LSS_STEP_KERNEL decides, default 2), 0: warp per block, 1: thread per block row, 2: CTA tile
 extern int g_opt_explicit_normal;   // -1: unset (environment LSS_NO_EXPLICIT_N decides), 0 / 1: lss_set_option
 int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val,
-                  int64_t n_cols, const unsigned char *fixed, cudaStream_t stream);
+                  int64_t n_cols, const unsigned char *fixed, cudaStream_t stream, const unsigned char *owned = nullptr,
+                  int64_t own_e0 = 0, int64_t own_e1 = 0);
 int normal_destroy(NormalMatrix *m);
 int normal_update(NormalMatrix *m, const double *w);                 // N += A^T diag(w - w_cur) A ; w_cur <- w
 int normal_diag(NormalMatrix *m, double *diag);
@@ -235,9 +238,17 @@ int normal_apply_fast(NormalMatrix *m, int64_t n_rows, const double *x, double *
 }  // namespace lss
 
 // NCCL communicator wrapper (comm.cu)
+constexpr int LSS_MAX_RANKS = 8;
 struct lss_comm {
     void *nccl;  // ncclComm_t
     int rank, n_ranks;
+    // peer-to-peer mailbox (comm.cu: lss_comm_box_*): one cudaMalloc'ed block per rank, mapped into every other rank of the
+    // node through CUDA IPC; kernels exchange data with plain stores over NVLink and sequence-numbered flags
+    void *box_local = nullptr;
+    void *box_peer[LSS_MAX_RANKS] = {};      // box of rank r as seen from this process (box_peer[rank] == box_local)
+    size_t box_bytes = 0;
+    unsigned long long seq = 16;             // next free sequence number (monotonic over the life of the communicator)
+    bool box_open = false;
 };
 namespace lss {
 int comm_allreduce(lss_comm *c, void *buf, int64_t n, int dtype /*0 f64, 1 i64, 2 u64*/, int op /*0 sum,1 min,2 max*/,

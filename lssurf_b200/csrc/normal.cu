@@ -26,27 +26,51 @@ __device__ __forceinline__ bool entry_valid(int c, double v, const unsigned char
     return v != 0.0 && !(fixed && fixed[c]);
 }
 
+// Row-sharded N (one rank of several): only the rows of this rank's own columns are kept, plus, in the rows of the
+// eliminated block E = [e0, e1), the entries at own columns (N_E,own: what the rank needs for its share of N_Eg v).
+struct OwnFilter {
+    const unsigned char *owned;      // null: keep everything
+    int64_t e0, e1;
+};
+__device__ __forceinline__ bool pair_kept(const OwnFilter &f, int ci, int cj) {
+    if (!f.owned) return true;
+    return f.owned[ci] || (ci >= f.e0 && ci < f.e1 && f.owned[cj]);
+}
+
 // counts[r] = number of column pairs row r contributes that row r - 1 does not
 __global__ void __launch_bounds__(256)
 normal_pair_count_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict__ ell_col, const double *__restrict__ ell_val,
-                         const unsigned char *__restrict__ fixed, uint32_t *__restrict__ counts) {
+                         const unsigned char *__restrict__ fixed, uint32_t *__restrict__ counts, OwnFilter flt) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     int nv = 0, ns = 0;
+    int c[NK_MAX];
+    unsigned valid = 0, same = 0;
     for (int k = 0; k < K; ++k) {
-        const int c = ell_col[(int64_t)k * n_pad + r];
+        c[k] = ell_col[(int64_t)k * n_pad + r];
         const double v = ell_val[(int64_t)k * n_pad + r];
-        if (!entry_valid(c, v, fixed)) continue;
+        if (!entry_valid(c[k], v, fixed)) continue;
         ++nv;
-        if (r > 0 && ell_col[(int64_t)k * n_pad + r - 1] == c && ell_val[(int64_t)k * n_pad + r - 1] != 0.0) ++ns;
+        valid |= 1u << k;
+        if (r > 0 && ell_col[(int64_t)k * n_pad + r - 1] == c[k] && ell_val[(int64_t)k * n_pad + r - 1] != 0.0) { ++ns; same |= 1u << k; }
     }
-    counts[r] = (uint32_t)(nv * nv - ns * ns);
+    if (!flt.owned) { counts[r] = (uint32_t)(nv * nv - ns * ns); return; }
+    int n = 0;
+    for (int i = 0; i < K; ++i) {
+        if (!((valid >> i) & 1u)) continue;
+        for (int j = 0; j < K; ++j) {
+            if (!((valid >> j) & 1u)) continue;
+            if ((same >> i) & (same >> j) & 1u) continue;
+            if (pair_kept(flt, c[i], c[j])) ++n;
+        }
+    }
+    counts[r] = (uint32_t)n;
 }
 
 __global__ void __launch_bounds__(256)
 normal_pair_emit_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict__ ell_col, const double *__restrict__ ell_val,
                         const unsigned char *__restrict__ fixed, const uint32_t *__restrict__ offsets, int cbits,
-                        uint64_t *__restrict__ keys) {
+                        uint64_t *__restrict__ keys, OwnFilter flt) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     int c[NK_MAX];
@@ -64,6 +88,7 @@ normal_pair_emit_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restr
         for (int j = 0; j < K; ++j) {
             if (!((valid >> j) & 1u)) continue;
             if ((same >> i) & (same >> j) & 1u) continue;
+            if (!pair_kept(flt, c[i], c[j])) continue;
             *out++ = ((uint64_t)(uint32_t)c[i] << cbits) | (uint64_t)(uint32_t)c[j];
         }
     }
@@ -106,7 +131,7 @@ __global__ void __launch_bounds__(NU_WARPS * 32)
 normal_update_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict__ ell_col, const double *__restrict__ ell_val,
                      const unsigned char *__restrict__ fixed, const double *__restrict__ w_new, double *__restrict__ w_cur,
                      const int *__restrict__ indptr, const int *__restrict__ indices, double *__restrict__ data,
-                     unsigned long long *__restrict__ n_missing) {
+                     unsigned long long *__restrict__ n_missing, OwnFilter flt) {
     __shared__ int sc[NU_WARPS][32][NK_MAX];
     __shared__ double sv[NU_WARPS][32][NK_MAX];
     const int w = threadIdx.x >> 5;
@@ -149,6 +174,7 @@ normal_update_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict
                 const int i = e / K, j = e - i * K;
                 const int ci = sc[w][rep][i], cj = sc[w][rep][j];
                 if (ci < 0 || cj < 0) continue;
+                if (!pair_kept(flt, ci, cj)) continue;
                 int lo = __ldg(indptr + ci), hi = __ldg(indptr + ci + 1);
                 const int end = hi;
                 while (lo < hi) {
@@ -292,7 +318,7 @@ int normal_destroy(NormalMatrix *m) {
 }
 
 int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col, const double *ell_val,
-                  int64_t n_cols, const unsigned char *fixed, cudaStream_t st) {
+                  int64_t n_cols, const unsigned char *fixed, cudaStream_t st, const unsigned char *owned, int64_t own_e0, int64_t own_e1) {
     if (K < 1 || K > NK_MAX) return fail(LSS_EINVAL, "normal matrix: row length %d not in 1..%d", K, NK_MAX);
     if (n_cols >= (1ll << 31)) return fail(LSS_ERANGE, "normal matrix: too many columns");
     NormalMatrix *m = new NormalMatrix();
@@ -302,6 +328,8 @@ int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, cons
     m->part_rows = -1;
     m->c8_part_rows = -1;
     m->c8_dirty = true;
+    m->owned = owned; m->own_e0 = own_e0; m->own_e1 = own_e1;
+    const OwnFilter flt{owned, own_e0, own_e1};
     Scratch::configure_pool();
     int rc = LSS_OK;
     auto bail = [&](int code) { normal_destroy(m); return code; };
@@ -316,7 +344,7 @@ int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, cons
         Scratch counts, tot;
         if (counts.alloc(sizeof(uint32_t) * n_rows, st) != cudaSuccess || tot.alloc(2 * sizeof(uint32_t), st) != cudaSuccess)
             return bail(fail(LSS_ECUDA, "normal matrix: scratch allocation failed"));
-        normal_pair_count_kernel<<<ceil_div(n_rows, 256), 256, 0, st>>>(n_rows, n_pad, K, ell_col, ell_val, fixed, counts.as<uint32_t>());
+        normal_pair_count_kernel<<<ceil_div(n_rows, 256), 256, 0, st>>>(n_rows, n_pad, K, ell_col, ell_val, fixed, counts.as<uint32_t>(), flt);
         ++g_launches;
         if (cudaGetLastError() != cudaSuccess) return bail(fail(LSS_ECUDA, "normal matrix: launch failed"));
         // 64-bit total first: the 32-bit scan below would wrap silently
@@ -343,7 +371,7 @@ int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, cons
                 va.alloc(sizeof(uint32_t) * np, st) != cudaSuccess || vb.alloc(sizeof(uint32_t) * np, st) != cudaSuccess)
                 return bail(fail(LSS_ECUDA, "normal matrix: %.1f GB of sort scratch not available", 24e-9 * (double)np));
             normal_pair_emit_kernel<<<ceil_div(n_rows, 256), 256, 0, st>>>(n_rows, n_pad, K, ell_col, ell_val, fixed, counts.as<uint32_t>(), cbits,
-                                                                           ka.as<uint64_t>());
+                                                                           ka.as<uint64_t>(), flt);
             ++g_launches;
             uint64_t *ks;
             uint32_t *vs;
@@ -387,7 +415,7 @@ int normal_update(NormalMatrix *m, const double *w) {
     const int64_t cap = (int64_t)kSMs * 16;
     const int grid = (int)(need < cap ? need : cap);
     normal_update_kernel<<<grid, NU_WARPS * 32, 0, m->stream>>>(m->n_rows, m->n_pad, m->K, m->ell_col, m->ell_val, m->fixed, w, m->w_cur,
-                                                                m->indptr, m->indices, m->data, m->missing);
+                                                                m->indptr, m->indices, m->data, m->missing, OwnFilter{m->owned, m->own_e0, m->own_e1});
     LSS_LAUNCH_CHECK();
     return LSS_OK;
 }

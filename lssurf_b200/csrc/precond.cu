@@ -20,8 +20,8 @@ bp_index_kernel(int n_blocks, int bs, const int *__restrict__ ptr, const int *__
 __global__ void __launch_bounds__(256)
 bp_gather_kernel(int n_blocks, int bs, const int *__restrict__ ptr, const int *__restrict__ cols, const int *__restrict__ col_block,
                  const int *__restrict__ col_local, const int *__restrict__ n_indptr, const int *__restrict__ n_indices,
-                 const double *__restrict__ n_data, double *__restrict__ dense) {
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                 const double *__restrict__ n_data, double *__restrict__ dense, int b_first) {
+    const int b = b_first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (b >= n_blocks) return;
     const unsigned lane = lane_id();
     double *D = dense + (size_t)b * bs * bs;
@@ -42,9 +42,9 @@ bp_gather_kernel(int n_blocks, int bs, const int *__restrict__ ptr, const int *_
 // Not positive definite (or non-finite) -> inverse of the diagonal.  The result is symmetrised and rounded to fp32.
 __global__ void __launch_bounds__(32)
 bp_invert_kernel(int n_blocks, int bs, const int *__restrict__ ptr, const double *__restrict__ dense, float *__restrict__ inv,
-                 unsigned int *__restrict__ n_bad) {
+                 unsigned int *__restrict__ n_bad, int b_first) {
     extern __shared__ double sh[];      // [bs][bs + 1] work + [bs] original diagonal
-    const int b = blockIdx.x;
+    const int b = b_first + blockIdx.x;
     if (b >= n_blocks) return;
     const int ld = bs + 1;
     double *B = sh, *dg = sh + bs * ld;
@@ -94,11 +94,11 @@ bp_invert_kernel(int n_blocks, int bs, const int *__restrict__ ptr, const double
 __global__ void __launch_bounds__(256)
 bp_apply_kernel(int n_blocks, int bs, const int *__restrict__ ptr, const int *__restrict__ cols, const int *__restrict__ col_block,
                 const float *__restrict__ inv, int64_t n_cols, const double *__restrict__ r, const double *__restrict__ minv,
-                double *__restrict__ z) {
+                double *__restrict__ z, int b_first) {
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const unsigned lane = lane_id();
     const uint64_t keep = l2_policy_evict_last();
-    for (int b = gw; b < n_blocks; b += nw) {
+    for (int b = b_first + gw; b < n_blocks; b += nw) {
         const int b0 = ptr[b], m = ptr[b + 1] - b0;
         const int c0 = (int)lane < m ? cols[b0 + lane] : -1, c1 = (int)lane + 32 < m ? cols[b0 + 32 + lane] : -1;
         const double r0 = c0 >= 0 ? r[c0] : 0.0, r1 = c1 >= 0 ? r[c1] : 0.0;
@@ -160,11 +160,14 @@ int block_precond_create(BlockPrecond **out, int64_t n_cols, int n_blocks, const
     return LSS_OK;
 }
 
-int block_precond_factor(BlockPrecond *bp, const NormalMatrix *nm, lss_comm *comm) {
+int block_precond_factor(BlockPrecond *bp, const NormalMatrix *nm, lss_comm *comm, int b_lo, int b_hi) {
     cudaStream_t st = bp->stream;
-    const int grid = ceil_div((int64_t)bp->n_blocks * 32, 256);
-    bp_gather_kernel<<<grid, 256, 0, st>>>(bp->n_blocks, bp->bs, bp->ptr, bp->cols, bp->col_block, bp->col_local, nm->indptr, nm->indices,
-                                           nm->data, bp->dense);
+    if (b_hi < 0) b_hi = bp->n_blocks;          // blocks [b_lo, b_hi): a rank of a row-sharded N factors its own blocks only
+    const int nb = b_hi - b_lo;
+    if (nb <= 0) return LSS_OK;
+    const int grid = ceil_div((int64_t)nb * 32, 256);
+    bp_gather_kernel<<<grid, 256, 0, st>>>(b_hi, bp->bs, bp->ptr, bp->cols, bp->col_block, bp->col_local, nm->indptr, nm->indices,
+                                           nm->data, bp->dense, b_lo);
     LSS_LAUNCH_CHECK();
     LSS_TRY(comm_allreduce(comm, bp->dense, (int64_t)bp->n_blocks * bp->bs * bp->bs, 0, 0, st));
     const size_t smem = sizeof(double) * ((size_t)bp->bs * (bp->bs + 1) + bp->bs);
@@ -173,13 +176,15 @@ int block_precond_factor(BlockPrecond *bp, const NormalMatrix *nm, lss_comm *com
         LSS_CUDA(cudaFuncSetAttribute(bp_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    bp_invert_kernel<<<bp->n_blocks, 32, smem, st>>>(bp->n_blocks, bp->bs, bp->ptr, bp->dense, bp->inv, bp->n_bad);
+    bp_invert_kernel<<<nb, 32, smem, st>>>(b_hi, bp->bs, bp->ptr, bp->dense, bp->inv, bp->n_bad, b_lo);
     LSS_LAUNCH_CHECK();
     return LSS_OK;
 }
 
-int block_precond_apply(const BlockPrecond *bp, int64_t n_cols, const double *r, const double *minv, double *z, cudaStream_t st) {
-    bp_apply_kernel<<<2 * kSMs, 256, 0, st>>>(bp->n_blocks, bp->bs, bp->ptr, bp->cols, bp->col_block, bp->inv, n_cols, r, minv, z);
+int block_precond_apply(const BlockPrecond *bp, int64_t n_cols, const double *r, const double *minv, double *z, cudaStream_t st, int b_lo,
+                        int b_hi) {
+    if (b_hi < 0) b_hi = bp->n_blocks;
+    bp_apply_kernel<<<2 * kSMs, 256, 0, st>>>(b_hi, bp->bs, bp->ptr, bp->cols, bp->col_block, bp->inv, n_cols, r, minv, z, b_lo);
     LSS_LAUNCH_CHECK();
     return LSS_OK;
 }

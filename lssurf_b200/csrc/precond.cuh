@@ -26,9 +26,10 @@ int block_precond_create(BlockPrecond **out, int64_t n_cols, int n_blocks, const
                          int max_size, cudaStream_t stream);
 int block_precond_destroy(BlockPrecond *bp);
 // gather the diagonal blocks from N, sum over ranks, invert
-int block_precond_factor(BlockPrecond *bp, const NormalMatrix *nm, lss_comm *comm);
+int block_precond_factor(BlockPrecond *bp, const NormalMatrix *nm, lss_comm *comm, int b_lo = 0, int b_hi = -1);
 // z = M^-1 r for all columns (blocks: exact block inverse; others: z = minv .* r)
-int block_precond_apply(const BlockPrecond *bp, int64_t n_cols, const double *r, const double *minv, double *z, cudaStream_t stream);
+int block_precond_apply(const BlockPrecond *bp, int64_t n_cols, const double *r, const double *minv, double *z, cudaStream_t stream,
+                        int b_lo = 0, int b_hi = -1);
 
 // Warp-cooperative z = Binv r over one block.  Lane l holds members l and l + 32 (r0, r1) and receives z for the same
 // members.  The stored block is bs x bs with zero padding and symmetric, so nothing depends on the member count and

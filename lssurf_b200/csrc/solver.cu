@@ -35,7 +35,7 @@ constexpr int VEC_GRID = 2 * kSMs;  // fixed: the per-block partial sums have a 
 // S_RZ0/1 and S_DONE0/1 are double-buffered by iteration parity: kernels of iteration k read slot k&1 and only
 // block 0 of the last kernel of the iteration writes slot (k+1)&1, so no block can observe a value written
 // by a sibling block of the same launch.
-enum { S_RZ0 = 0, S_RZ1 = 1, S_BNORM = 2, S_TOL2 = 3, S_DONE0 = 4, S_DONE1 = 5, S_ITERS = 6, S_MAXIT = 7, S_RZ_LAST = 8, S_COUNT = 10 };
+enum { S_RZ0 = 0, S_RZ1 = 1, S_BNORM = 2, S_TOL2 = 3, S_DONE0 = 4, S_DONE1 = 5, S_ITERS = 6, S_MAXIT = 7, S_RZ_LAST = 8, S_COUNT = 10 };   // slot 9: S_ERR (row-sharded step)
 
 __device__ __forceinline__ double block_sum(double v, double *sm /*[VEC_BLOCK/32]*/) {
     v = warp_sum(v);
@@ -914,6 +914,387 @@ static const void *step_ml_kernel_for(int bs) {
     }
 }
 
+
+// ---- row-sharded N over the GPUs of one node: the CG step with peer-to-peer exchanges -------------------------------
+// Every rank owns a contiguous range of preconditioner blocks: the rows of N at their columns, the block inverses, the
+// matching entries of x and r.  p is replicated.  One iteration = the local product q_own = N_own p (same kernel as on
+// one GPU) + this kernel, which talks to the peers through the mailbox (comm.cu) with plain stores over NVLink:
+//   A   p.q: every rank stores its partial into every box, flags it, and sums the P partials in rank order
+//   B   own blocks: x, r, z_BJ; z_BJ goes straight into every peer's packed z buffer (coalesced 8-byte stores)
+//   C1  own part of the restriction r_c,k = P_k^T r and of the bias coupling t_k = N_E,own z_BJ
+//   X   packet [r.z_BJ partial | r_c,k | t_k] -> every box, flag; wait for the P packets; sum in rank order
+//   C2  z_c = S_c^-1 r_c (replicated, spread over the CTAs)
+//   D   beta, p = z_BJ + P z_c + beta p for ALL columns from the packed z of all ranks;
+//       u = T^T p carried along: u <- sum_k t_k + B^T z_c + beta u, p_E = -N_EE^-1 u
+// All ranks form every scalar from the same numbers in the same order: alpha, beta and the stop flag are bit-identical
+// everywhere, so no rank can leave the loop alone.  A wait that exceeds ~4 s sets S_ERR and every later wait is skipped.
+constexpr int S_ERR = 9;
+struct ShardArgs {
+    int rank, n_ranks, blk_lo, blk_hi;
+    unsigned long long seq;                 // sequence base of this solve; iteration k uses seq + 2k + 1 (A) and seq + 2k + 2 (X)
+    unsigned long long *box[LSS_MAX_RANKS]; // the mailboxes (box[rank] is local)
+    long long off_fa, off_da, off_fb, off_db, off_z;   // word offsets of flagsA / dataA / flagsB / dataB / packed z
+    int LB;                                 // words per packet: 1 + n_c + n_e (padded)
+    long long ZP;                           // words of one packed z buffer: n_blocks * BS
+    int n_e;
+    long long e0;
+    const int *n_indptr, *n_indices;        // rows of E of the local N: entries at own columns
+    const double *n_data;
+    const double *einv, *Bt;
+    double *u_e, *tk;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_box(const double *p) { return __ldcg(p); }     // written by a peer: L2 is the coherence point
+
+// thread t < n waits until flags[t] >= want; gives up after ~4 s (another rank died) and raises S_ERR
+__device__ __forceinline__ void wait_flags(const unsigned long long *flags, int n, unsigned long long want, double *scal) {
+    if ((int)threadIdx.x < n) {
+        const volatile double *err = scal + S_ERR;
+        if (*err == 0.0) {
+            const long long t0 = clock64();
+            unsigned int spins = 0;
+            while (ld_acquire_sys(flags + threadIdx.x) < want) {
+                if ((++spins & 1023u) == 0) {
+                    if (*err != 0.0) break;
+                    if (clock64() - t0 > 8000000000ll) { scal[S_ERR] = 1.0; __threadfence(); break; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int BS>
+__global__ void __launch_bounds__(VEC_BLOCK, STEP3_PER_SM)
+cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_slots, const double *__restrict__ minv, double *__restrict__ p,
+                     double *__restrict__ x, const double *r_in, double *r_out, double *z,
+                     double *part, double *__restrict__ scal, int parity, int n_blocks, const int *__restrict__ bcols,
+                     const float *__restrict__ binv, CoarseArgs ca, ShardArgs sa) {
+    constexpr int NBLK = VEC_BLOCK / BS, ROWS = NBLK * BS;
+    __shared__ double sm[VEC_BLOCK / 32];
+    __shared__ double rs[ROWS], qs[ROWS];
+    __shared__ double cs[CS_MAX];
+    if (scal[S_DONE0 + parity] != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
+        return;
+    }
+    cgx::grid_group grid = cgx::this_grid();
+    const int64_t tid = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x, nth = (int64_t)gridDim.x * VEC_BLOCK;
+    const int P = sa.n_ranks, me = sa.rank;
+    const unsigned long long it = (unsigned long long)scal[S_ITERS];
+    const int par = (int)(it & 1ull);
+    const unsigned long long seq_a = sa.seq + 2ull * it + 1ull, seq_x = seq_a + 1ull;
+    unsigned long long *mine = sa.box[me];
+    static_assert(PQ_SLOTS == VEC_BLOCK, "one p.q slot per thread");
+    const double slot_v = pq_slots[threadIdx.x];
+    const double rz_old = scal[S_RZ0 + parity];
+    const int n_own = sa.blk_hi - sa.blk_lo;
+    const int n_groups = (n_own + NBLK - 1) / NBLK;
+    const int bl = threadIdx.x / BS, l = threadIdx.x - bl * BS;
+    double alpha = 0.0, v = 0.0;
+    bool have_alpha = false;
+    // ---- phase A (folded behind the first block's loads): p.q over all ranks
+    auto get_alpha = [&]() {
+        double pq = block_sum(slot_v, sm);
+        if (threadIdx.x == 0) sm[0] = pq;
+        __syncthreads();
+        pq = sm[0];
+        __syncthreads();
+        if (blockIdx.x == 0 && (int)threadIdx.x < P) {          // one thread per peer: data, then the flag, in program order
+            unsigned long long *peer = sa.box[threadIdx.x];
+            reinterpret_cast<double *>(peer + sa.off_da)[par * P + me] = pq;
+            st_release_sys(peer + sa.off_fa + par * P + me, seq_a);
+        }
+        wait_flags(mine + sa.off_fa + par * P, P, seq_a, scal);
+        double tot = 0.0;
+        const double *da = reinterpret_cast<const double *>(mine + sa.off_da) + par * P;
+        for (int t = 0; t < P; ++t) tot += ld_box(da + t);
+        alpha = tot > 0.0 ? rz_old / tot : 0.0;
+        have_alpha = true;
+    };
+    // ---- phase B: own blocks
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int b = sa.blk_lo + g * NBLK + bl;
+        const bool active = threadIdx.x < ROWS && b < sa.blk_hi;
+        float sv[BS];
+        int c = -1;
+        if (active) {
+            const float *S = binv + (size_t)b * BS * BS + l;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) sv[j] = __ldg(S + j * BS);
+            c = __ldg(bcols + (size_t)b * BS + l);
+        } else {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) sv[j] = 0.f;
+        }
+        double r_own = 0.0, q_own = 0.0, p_own = 0.0, x_own = 0.0;
+        if (c >= 0) {
+            r_own = r_in[c];
+            q_own = q[c];
+            p_own = p[c];
+            x_own = x[c];
+        }
+        if (threadIdx.x < ROWS) {
+            rs[threadIdx.x] = r_own;
+            qs[threadIdx.x] = q_own;
+        }
+        __syncthreads();
+        double zr = 0.0, zq = 0.0;
+        const double *rb = rs + bl * BS, *qb = qs + bl * BS;
+        if (threadIdx.x < ROWS) {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+                const double sj = (double)sv[j];
+                zr += sj * rb[j];
+                zq += sj * qb[j];
+            }
+        }
+        if (!have_alpha) get_alpha();
+        else __syncthreads();
+        if (active) {
+            double zl = 0.0;
+            if (c >= 0) {
+                zl = zr - alpha * zq;
+                const double rl = r_own - alpha * q_own;
+                x[c] = x_own + alpha * p_own;
+                r_out[c] = rl;
+                z[c] = zl;
+                v += rl * zl;
+            }
+            const long long zi = sa.off_z + (long long)par * sa.ZP + (long long)b * BS + l;
+            for (int t = 0; t < P; ++t) reinterpret_cast<double *>(sa.box[t])[zi] = zl;      // coalesced over the CTA's blocks
+        }
+    }
+    if (!have_alpha) get_alpha();
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    __threadfence_system();                                     // the z stores are visible system-wide before any flag below
+    grid.sync();
+    // ---- phase C1: own part of the restriction and of N_E,own z
+    const int n_c = ca.n_c, chunks = ca.chunks;
+    {
+        const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5);
+        const int n_work = n_c * chunks + sa.n_e;
+        for (int w = warp; w < n_work; w += n_warps) {
+            double acc = 0.0;
+            if (w < n_c * chunks) {
+                const int m = w % n_c, ch = w / n_c;
+                const int kb = ca.pt_ptr[m], len = ca.pt_ptr[m + 1] - kb;
+                const int per = (len + chunks - 1) / chunks;
+                const int k0 = kb + ch * per, k1 = min(kb + len, k0 + per);
+                for (int k = k0 + (int)lane_id(); k < k1; k += 32) acc += (double)__ldg(ca.pt_w + k) * r_out[__ldg(ca.pt_col + k)];
+                acc = warp_sum(acc);
+                if (lane_id() == 0) ca.rc_part[(size_t)ch * n_c + m] = acc;
+            } else {
+                const int e = w - n_c * chunks;
+                const long long row = sa.e0 + e;
+                for (int k = sa.n_indptr[row] + (int)lane_id(); k < sa.n_indptr[row + 1]; k += 32) {
+                    const int j = __ldg(sa.n_indices + k);
+                    if (j < sa.e0 || j >= sa.e0 + sa.n_e) acc += __ldg(sa.n_data + k) * z[j];
+                }
+                acc = warp_sum(acc);
+                if (lane_id() == 0) sa.tk[e] = acc;
+            }
+        }
+    }
+    grid.sync();
+    // ---- exchange X: packet [r.z_BJ | r_c,k | t_k] to every rank (CTA t serves peer t)
+    if ((int)blockIdx.x < P) {
+        double *dst = reinterpret_cast<double *>(sa.box[blockIdx.x] + sa.off_db) + (size_t)(par * P + me) * sa.LB;
+        const double rzk = sum_partials(part, (int)gridDim.x, sm);
+        if (threadIdx.x == 0) dst[0] = rzk;
+        for (int m = threadIdx.x; m < n_c; m += VEC_BLOCK) {
+            double a = 0.0;
+            for (int ch = 0; ch < chunks; ++ch) a += ca.rc_part[(size_t)ch * n_c + m];
+            dst[1 + m] = a;
+        }
+        for (int e = threadIdx.x; e < sa.n_e; e += VEC_BLOCK) dst[1 + n_c + e] = sa.tk[e];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(sa.box[blockIdx.x] + sa.off_fb + par * P + me, seq_x);
+    }
+    wait_flags(mine + sa.off_fb + par * P, P, seq_x, scal);
+    const double *db = reinterpret_cast<const double *>(mine + sa.off_db) + (size_t)par * P * sa.LB;
+    double rz_new = 0.0;
+    for (int t = 0; t < P; ++t) rz_new += ld_box(db + (size_t)t * sa.LB);
+    for (int m = threadIdx.x; m < n_c; m += VEC_BLOCK) {
+        double a = 0.0;
+        for (int t = 0; t < P; ++t) a += ld_box(db + (size_t)t * sa.LB + 1 + m);
+        cs[m] = a;
+    }
+    __syncthreads();
+    // ---- phase C2: z_c = S_c^-1 r_c
+    {
+        const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5);
+        const int per = ((n_c + chunks - 1) / chunks + 31) & ~31;
+        for (int w = warp; w < n_c * chunks; w += n_warps) {
+            const int m = w % n_c, ch = w / n_c;
+            const double *row = ca.inv + (size_t)m * n_c;
+            const int j0 = ch * per, j1 = min(n_c, j0 + per);
+            double acc = 0.0;
+            int j = j0 + (int)lane_id();
+            for (; j + 96 < j1; j += 128) {
+                const double a0 = __ldg(row + j), a1 = __ldg(row + j + 32), a2 = __ldg(row + j + 64), a3 = __ldg(row + j + 96);
+                acc += (a0 * cs[j] + a1 * cs[j + 32]) + (a2 * cs[j + 64] + a3 * cs[j + 96]);
+            }
+            for (; j < j1; j += 32) acc += __ldg(row + j) * cs[j];
+            acc = warp_sum(acc);
+            if (lane_id() == 0) ca.zc_part[(size_t)ch * n_c + m] = acc;
+        }
+    }
+    grid.sync();
+    // ---- phase D
+    double rczc = 0.0;
+    double zreg[(CS_MAX + VEC_BLOCK - 1) / VEC_BLOCK];
+#pragma unroll
+    for (int u = 0; u < (CS_MAX + VEC_BLOCK - 1) / VEC_BLOCK; ++u) {
+        const int m = threadIdx.x + u * VEC_BLOCK;
+        double a = 0.0;
+        if (m < n_c) {
+            for (int ch = 0; ch < chunks; ++ch) a += ca.zc_part[(size_t)ch * n_c + m];
+            rczc += cs[m] * a;
+        }
+        zreg[u] = a;
+    }
+    rczc = block_sum(rczc, sm);
+    if (threadIdx.x == 0) sm[0] = rczc;
+    __syncthreads();
+    rz_new += sm[0];
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < (CS_MAX + VEC_BLOCK - 1) / VEC_BLOCK; ++u) {
+        const int m = threadIdx.x + u * VEC_BLOCK;
+        if (m < n_c) cs[m] = zreg[u];
+    }
+    __syncthreads();
+    const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
+    // p over ALL blocks from the packed z of their owners
+    {
+        const double *zp = reinterpret_cast<const double *>(mine + sa.off_z) + (size_t)par * sa.ZP;
+        const int64_t total = (int64_t)n_blocks * BS;
+        for (int64_t k = tid; k < total; k += nth) {
+            const int c = __ldg(bcols + k);
+            if (c < 0) continue;
+            double zi = ld_box(zp + k);
+            if (n_c > 0) {
+                const int4 pi = __ldg(ca.cp_idx + c);
+                const float4 w = __ldg(ca.cp_w + c);
+                if (pi.x >= 0) zi += (double)w.x * cs[pi.x];
+                if (pi.y >= 0) zi += (double)w.y * cs[pi.y];
+                if (pi.z >= 0) zi += (double)w.z * cs[pi.z];
+                if (pi.w >= 0) zi += (double)w.w * cs[pi.w];
+            }
+            p[c] = zi + beta * p[c];
+        }
+    }
+    for (int64_t i = tid; i < n; i += nth) q[i] = 0.0;
+    // the eliminated block: u = T^T p by linearity, p_E = -N_EE^-1 u (one warp per bias column)
+    {
+        const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5);
+        for (int e = warp; e < sa.n_e; e += n_warps) {
+            double acc = 0.0;
+            if (n_c > 0) {
+                const double *row = sa.Bt + (size_t)e * n_c;
+                for (int m = (int)lane_id(); m < n_c; m += 32) acc += __ldg(row + m) * cs[m];
+                acc = warp_sum(acc);
+            }
+            if (lane_id() == 0) {
+                double t = 0.0;
+                for (int r = 0; r < P; ++r) t += ld_box(db + (size_t)r * sa.LB + 1 + n_c + e);
+                const double un = t + acc + beta * sa.u_e[e];
+                sa.u_e[e] = un;
+                p[sa.e0 + e] = -sa.einv[e] * un;
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;
+        if (threadIdx.x == 0) {
+            scal[S_RZ0 + (parity ^ 1)] = rz_new;
+            scal[S_RZ_LAST] = rz_new;
+            const double itn = scal[S_ITERS] + 1.0;
+            scal[S_ITERS] = itn;
+            const bool err = *reinterpret_cast<volatile double *>(scal + S_ERR) != 0.0;
+            scal[S_DONE0 + (parity ^ 1)] = (err || rz_new <= scal[S_TOL2] || itn >= scal[S_MAXIT] || !(rz_new == rz_new)) ? 1.0 : 0.0;
+        }
+    }
+}
+
+static const void *step_shard_kernel_for(int bs) {
+    switch (bs) {
+        case 12: return (const void *)cg_step_shard_kernel<12>;
+        case 24: return (const void *)cg_step_shard_kernel<24>;
+        case 36: return (const void *)cg_step_shard_kernel<36>;
+        default: return nullptr;
+    }
+}
+
+// v[i] = 0 unless column i is this rank's own (or, with keep_e, inside the eliminated block)
+__global__ void __launch_bounds__(VEC_BLOCK)
+mask_own_kernel(int64_t n, const unsigned char *__restrict__ owned, int64_t e0, int64_t e1, int keep_e, double *__restrict__ v) {
+    for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) {
+        const bool in_e = i >= e0 && i < e1;
+        if (!(owned[i] || (in_e && keep_e))) v[i] = 0.0;
+    }
+}
+
+// Diagonal and right-hand side of the eliminated block from this rank's OWN rows (halo copies of other ranks' points
+// are left out; the constraint rows are counted by the caller on one rank only):
+// esum[e] += w a^2, esum[n_e + e] += w a b for every entry a of row r at column e0 + e.
+__global__ void __launch_bounds__(256)
+own_bias_sums_kernel(int64_t row_lo, int64_t row_hi, int64_t n_pad, int K, const int *__restrict__ ell_col, const double *__restrict__ ell_val,
+                     const double *__restrict__ w, const double *__restrict__ b, int64_t e0, int n_e, double *__restrict__ esum) {
+    for (int64_t r0 = row_lo + (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); r0 < row_hi; r0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = r0 + lane_id();
+        const bool in = r < row_hi;
+        const double wr = in ? w[r] : 0.0, br = in ? b[r] : 0.0;
+        for (int k = 0; k < K; ++k) {
+            int e = -1;
+            double a = 0.0;
+            if (in) {
+                const int c = ell_col[(int64_t)k * n_pad + r];
+                a = ell_val[(int64_t)k * n_pad + r];
+                if (a != 0.0 && c >= e0 && c < e0 + n_e) e = (int)(c - e0);
+            }
+            if (__ballot_sync(0xffffffffu, e >= 0) == 0u) continue;
+            // neighbouring points mostly share their bias column: one RED per distinct column and warp
+            const unsigned peers = __match_any_sync(0xffffffffu, e);
+            double d = wr * a * a, g = wr * a * br;
+            double ds = 0.0, gs = 0.0;
+            for (unsigned m = peers; m; m &= m - 1) {
+                const int src = __ffs(m) - 1;
+                ds += __shfl_sync(peers, d, src);
+                gs += __shfl_sync(peers, g, src);
+            }
+            if (e >= 0 && lane_id() == (unsigned)(__ffs(peers) - 1)) {
+                atomicAdd(esum + e, ds);
+                atomicAdd(esum + n_e + e, gs);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+set_block_kernel(int64_t e0, int n_e, const double *__restrict__ esum, double *__restrict__ diag, double *__restrict__ g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_e) { diag[e0 + e] = esum[e]; g[e0 + e] = esum[n_e + e]; }
+}
+
+// out_E = scale * einv .* c_E (scale -1: p_E = -N_EE^-1 u; +1 with c = g: the E part of N^-1-eliminated right-hand side)
+__global__ void __launch_bounds__(256)
+elim_scale_kernel(int64_t e0, int n_e, const double *__restrict__ einv, const double *__restrict__ c, double scale, double *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_e) out[e0 + e] = scale * einv[e] * c[e];
+}
+
 __global__ void __launch_bounds__(VEC_BLOCK)
 mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * VEC_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * VEC_BLOCK) out[i] = a[i] * b[i];
@@ -999,6 +1380,14 @@ struct lss_solver {
     int cs_refresh;          // 1: S_c rebuilt with every weight change, 0: built with the first weights of the solver only
     bool cs_built;
     int step_ml_grid;
+    // row-sharded N over the ranks of one node (lss_solver_create_sharded): p exchanged through the P2P mailbox
+    bool shard;
+    lss_comm *pc;            // communicator with an open mailbox; NCCL only in set-up / start / end of a solve (`comm` stays null)
+    unsigned char *owned;    // [n_cols] flags of this rank's own columns
+    int blk_lo, blk_hi;      // its preconditioner blocks
+    int64_t own_row_lo, own_row_hi, con_row_lo;   // own data rows and first constraint row inside the ELL block
+    double *u_e, *tk, *esum; // T^T p carried through the iterations, this rank's N_E,own z, [2 n_e] set-up sums
+    int step_sh_grid;
 };
 
 
@@ -1029,6 +1418,10 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     }
     if (s->bp) lss::block_precond_destroy(s->bp);
     if (s->cs) lss::coarse_destroy(s->cs);
+    if (s->owned) cudaFreeAsync(s->owned, s->stream);
+    if (s->u_e) cudaFreeAsync(s->u_e, s->stream);
+    if (s->tk) cudaFreeAsync(s->tk, s->stream);
+    if (s->esum) cudaFreeAsync(s->esum, s->stream);
     if (s->einv) cudaFreeAsync(s->einv, s->stream);
     if (s->eraw) cudaFreeAsync(s->eraw, s->stream);
     if (s->z) cudaFreeAsync(s->z, s->stream);
@@ -1104,17 +1497,32 @@ extern "C" int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t 
     return LSS_OK;
 }
 
-extern "C" int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, int64_t n_con, int64_t n_cols, int32_t row_len,
-                                        const int32_t *g_indptr, const int32_t *g_indices, const double *g_data,
-                                        const int32_t *c_indptr, const int32_t *c_indices, const double *c_data,
-                                        const int32_t *ct_indptr, const int32_t *ct_indices, const double *ct_data,
-                                        const double *rhs, const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm,
-                                        void *stream) {
+struct ShardSpec {
+    const uint8_t *owned_cols;     // device [n_cols]
+    int32_t block_lo, block_hi;
+    int64_t own_row_lo, own_row_hi, con_row_lo, elim_begin, elim_end;
+    lss_comm *pc;
+};
+
+static int create_blocks_impl(lss_solver_t **solver, int64_t n_data, int64_t n_con, int64_t n_cols, int32_t row_len,
+                              const int32_t *g_indptr, const int32_t *g_indices, const double *g_data,
+                              const int32_t *c_indptr, const int32_t *c_indices, const double *c_data,
+                              const int32_t *ct_indptr, const int32_t *ct_indices, const double *ct_data,
+                              const double *rhs, const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm,
+                              void *stream, const ShardSpec *sh) {
     if (!solver || n_data < 0 || n_con < 0 || n_cols <= 0) return fail(LSS_EINVAL, "solver_create_blocks: bad sizes");
     if (n_data > 0 && (row_len < 1 || row_len > 16)) return fail(LSS_EINVAL, "solver_create_blocks: data rows must hold 1..16 entries");
     lss_solver *s = new lss_solver();
     int rc = solver_init_common(s, n_data + n_con, n_cols, rhs, fixed_cols, n_fixed, comm, stream);
     cudaStream_t st = s->stream;
+    if (sh && rc == LSS_OK) {
+        s->shard = true;
+        s->pc = sh->pc;
+        s->blk_lo = sh->block_lo; s->blk_hi = sh->block_hi;
+        s->own_row_lo = sh->own_row_lo; s->own_row_hi = sh->own_row_hi; s->con_row_lo = sh->con_row_lo;
+        if (cudaMallocAsync((void **)&s->owned, (size_t)n_cols, st) != cudaSuccess) rc = fail(LSS_ECUDA, "solver_create_sharded: cudaMallocAsync failed");
+        else cudaMemcpyAsync(s->owned, sh->owned_cols, (size_t)n_cols, cudaMemcpyDeviceToDevice, st);
+    }
     s->blocks = true;
     s->n_data = n_data; s->n_con = n_con;
     s->c_indptr = c_indptr; s->c_indices = c_indices; s->c_data = c_data;
@@ -1135,15 +1543,40 @@ extern "C" int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, i
         int want = lss::g_opt_explicit_normal;
         if (want < 0) want = getenv("LSS_NO_EXPLICIT_N") ? 0 : 1;
         if (want) {
-            rc = normal_create(&s->nm, n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, n_cols, s->fixed, st);
-            if (rc == LSS_ERANGE) { s->nm = nullptr; rc = LSS_OK; }   // too many column pairs for the 32-bit sort: fused ELL form
+            rc = normal_create(&s->nm, n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, n_cols, s->fixed, st, s->owned,
+                               sh ? sh->elim_begin : 0, sh ? sh->elim_end : 0);
+            if (rc == LSS_ERANGE && !sh) { s->nm = nullptr; rc = LSS_OK; }   // too many column pairs for the 32-bit sort: fused ELL form
         }
     }
+    if (rc == LSS_OK && sh && !s->nm) rc = fail(LSS_EINVAL, "solver_create_sharded: needs the explicit-normal form (all rows <= 16 entries in one block)");
     if (rc == LSS_OK && n_con > 0) rc = spmv_plan_create(&s->plan_c, n_con, c_indptr, s->c_nnz, st);
     if (rc == LSS_OK && n_con > 0) rc = spmv_plan_create(&s->plan_ct, n_cols, ct_indptr, s->c_nnz, st);
     if (rc != LSS_OK) { lss_solver_destroy(s); return rc; }
     *solver = s;
     return LSS_OK;
+}
+
+extern "C" int lss_solver_create_blocks(lss_solver_t **solver, int64_t n_data, int64_t n_con, int64_t n_cols, int32_t row_len,
+                                        const int32_t *g_indptr, const int32_t *g_indices, const double *g_data,
+                                        const int32_t *c_indptr, const int32_t *c_indices, const double *c_data,
+                                        const int32_t *ct_indptr, const int32_t *ct_indices, const double *ct_data,
+                                        const double *rhs, const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm,
+                                        void *stream) {
+    return create_blocks_impl(solver, n_data, n_con, n_cols, row_len, g_indptr, g_indices, g_data, c_indptr, c_indices, c_data, ct_indptr,
+                              ct_indices, ct_data, rhs, fixed_cols, n_fixed, comm, stream, nullptr);
+}
+
+extern "C" int lss_solver_create_sharded(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, int32_t row_len, const int32_t *indptr,
+                                         const int32_t *indices, const double *data, const double *rhs, const int32_t *fixed_cols,
+                                         int64_t n_fixed, const uint8_t *owned_cols, int32_t block_lo, int32_t block_hi,
+                                         int64_t own_row_lo, int64_t own_row_hi, int64_t con_row_lo, int64_t elim_begin, int64_t elim_end,
+                                         lss_comm_t *comm, void *stream) {
+    if (!comm || !comm->box_open) return fail(LSS_EINVAL, "solver_create_sharded: the communicator needs an open mailbox (lss_comm_box_open)");
+    if (!owned_cols || block_hi < block_lo || own_row_lo < 0 || own_row_hi < own_row_lo || con_row_lo < own_row_hi || con_row_lo > n_rows)
+        return fail(LSS_EINVAL, "solver_create_sharded: bad ownership arguments");
+    ShardSpec sh{owned_cols, block_lo, block_hi, own_row_lo, own_row_hi, con_row_lo, elim_begin, elim_end, comm};
+    return create_blocks_impl(solver, n_rows, 0, n_cols, row_len, indptr, indices, data, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                              rhs, fixed_cols, n_fixed, nullptr, stream, &sh);
 }
 
 extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const int32_t *block_ptr, const int32_t *block_cols,
@@ -1169,7 +1602,12 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
                             (long long)elim_begin, (long long)elim_end, nb);
         s->e0 = elim_begin; s->e1 = elim_end;
         LSS_TRY(dev_alloc(&s->einv, elim_end - elim_begin, st));
-        if (multi) LSS_TRY(dev_alloc(&s->eraw, elim_end - elim_begin, st));
+        if (multi || s->shard) LSS_TRY(dev_alloc(&s->eraw, elim_end - elim_begin, st));
+        if (s->shard) {
+            LSS_TRY(dev_alloc(&s->u_e, elim_end - elim_begin, st));
+            LSS_TRY(dev_alloc(&s->tk, elim_end - elim_begin, st));
+            LSS_TRY(dev_alloc(&s->esum, 2 * (elim_end - elim_begin), st));
+        }
     }
     if (n_blocks > 0) LSS_TRY(block_precond_create(&s->bp, s->n_cols, n_blocks, block_ptr, block_cols, max_block, st));
     if (s->bp && !getenv("LSS_NO_L2_WINDOW")) {
@@ -1243,6 +1681,16 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
             if (per_sm > STEP_PER_SM) per_sm = STEP_PER_SM;
         }
         s->step_grid = kSMs * per_sm;
+    }
+    if (s->shard) {
+        if (!s->bp || s->step_rows != 2 || !step_shard_kernel_for(s->bp->bs))
+            return fail(LSS_EINVAL, "solver_set_structure: the row-sharded solver needs preconditioner blocks of 12, 24 or 36 unknowns");
+        if (s->blk_hi > s->bp->n_blocks) return fail(LSS_EINVAL, "solver_set_structure: own block range outside the blocks");
+        int per_sm = 0;
+        LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_shard_kernel_for(s->bp->bs), VEC_BLOCK, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > STEP3_PER_SM) per_sm = STEP3_PER_SM;
+        s->step_sh_grid = kSMs * per_sm;
     }
     s->have_weights = false;
     return LSS_OK;
@@ -1354,14 +1802,252 @@ extern "C" int lss_solver_set_coarse(lss_solver_t *s, int32_t n_coarse, const in
     if (per_sm < 1) per_sm = 1;
     if (per_sm > STEP3_PER_SM) per_sm = STEP3_PER_SM;
     s->step_ml_grid = kSMs * per_sm;
+    if (s->shard) s->step_ml_grid = s->step_sh_grid;
     s->cs_refresh = refresh;
     s->cs_built = false;
     s->have_weights = false;
     return LSS_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ row-sharded solver
+namespace {
+
+// z = M^-1 r on this rank's columns (own blocks exactly, coarse level through an all-reduce of the partial restriction);
+// every other entry of z is zero.  Set-up / solve start only: the iterations use the fused step kernel.
+int shard_precond(lss_solver *s, const double *r, double *z) {
+    cudaStream_t st = s->stream;
+    LSS_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * s->n_cols, st));
+    LSS_TRY(block_precond_apply(s->bp, s->n_cols, r, s->minv, z, st, s->blk_lo, s->blk_hi));
+    if (s->cs && s->cs->ready) LSS_TRY(coarse_apply_add(s->cs, r, z, s->pc));
+    mask_own_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(s->n_cols, s->owned, s->e0, s->e1, 0, z);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+// v_E = N_EE^-1 (c_E - N_Eg v_g) with the column sums completed over the ranks; the raw sums (N_Eg v_g) stay in s->eraw
+int shard_slave(lss_solver *s, double *v, const double *c) {
+    cudaStream_t st = s->stream;
+    const int n_e = (int)(s->e1 - s->e0);
+    if (n_e <= 0) return LSS_OK;
+    elim_solve_kernel<<<n_e, ELIM_BLOCK, 0, st>>>(s->e0, s->e1, s->nm->indptr, s->nm->indices, s->nm->data, v, c, s->einv, v, nullptr, s->eraw);
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(comm_allreduce(s->pc, s->eraw, n_e, 0, 0, st));
+    elim_finish_kernel<<<ceil_div(n_e, 256), 256, 0, st>>>(s->e0, s->e1, s->eraw, c, s->einv, v, nullptr);
+    LSS_LAUNCH_CHECK();
+    return LSS_OK;
+}
+
+int shard_set_weights(lss_solver *s, const double *w) {
+    cudaStream_t st = s->stream;
+    const int64_t n = s->n_cols;
+    const int n_e = (int)(s->e1 - s->e0);
+    if (!s->bp || !s->z) return fail(LSS_EINVAL, "solver_set_weights: the row-sharded solver needs lss_solver_set_structure with blocks first");
+    if (s->n_rows > 0) {
+        LSS_CUDA(cudaMemcpyAsync(s->w, w, sizeof(double) * s->n_rows, cudaMemcpyDeviceToDevice, st));
+        mul_kernel<<<stride_grid(s->n_rows, VEC_BLOCK), VEC_BLOCK, 0, st>>>(s->n_rows, s->w, s->rhs, s->u);
+        LSS_LAUNCH_CHECK();
+    }
+    // right-hand side and N at the own columns: every row touching them is held by this rank (own points + halo copies)
+    LSS_CUDA(cudaMemsetAsync(s->g, 0, sizeof(double) * n, st));
+    LSS_TRY(ell_normal_launch(1, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, s->rhs, s->g, nullptr, nullptr, st));
+    LSS_TRY(normal_update(s->nm, s->w));
+    LSS_TRY(normal_diag(s->nm, s->diag));
+    if (n_e > 0) {
+        // eliminated block: diagonal and right-hand side from OWN rows only (+ the constraint rows on rank 0), summed over ranks
+        LSS_CUDA(cudaMemsetAsync(s->esum, 0, sizeof(double) * 2 * n_e, st));
+        if (s->own_row_hi > s->own_row_lo) {
+            own_bias_sums_kernel<<<stride_grid(s->own_row_hi - s->own_row_lo, 256), 256, 0, st>>>(s->own_row_lo, s->own_row_hi, s->ell_pad, s->ell_k,
+                                                                                              s->ell_col, s->ell_val, s->w, s->rhs, s->e0, n_e, s->esum);
+            LSS_LAUNCH_CHECK();
+        }
+        if (s->pc->rank == 0 && s->n_rows > s->con_row_lo) {
+            own_bias_sums_kernel<<<stride_grid(s->n_rows - s->con_row_lo, 256), 256, 0, st>>>(s->con_row_lo, s->n_rows, s->ell_pad, s->ell_k, s->ell_col,
+                                                                                          s->ell_val, s->w, s->rhs, s->e0, n_e, s->esum);
+            LSS_LAUNCH_CHECK();
+        }
+        LSS_TRY(comm_allreduce(s->pc, s->esum, 2 * n_e, 0, 0, st));
+        set_block_kernel<<<ceil_div(n_e, 256), 256, 0, st>>>(s->e0, n_e, s->esum, s->diag, s->g);
+        LSS_LAUNCH_CHECK();
+    }
+    mask_own_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->owned, s->e0, s->e1, 1, s->g);
+    LSS_LAUNCH_CHECK();
+    jacobi_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->diag, s->fixed, s->g, s->minv, s->part2);
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(block_precond_factor(s->bp, s->nm, nullptr, s->blk_lo, s->blk_hi));
+    if (n_e > 0) {
+        elim_setup_kernel<<<ceil_div(n_e, 256), 256, 0, st>>>(s->e0, s->e1, s->diag, s->einv, s->minv);
+        LSS_LAUNCH_CHECK();
+    }
+    const int64_t rows = (n_e > 0 && s->e1 == n) ? s->e0 : n;
+    if (s->cs) {
+        if (s->cs_refresh || !s->cs_built) {
+            LSS_TRY(coarse_factor(s->cs, rows, s->nm->indptr, s->nm->indices, s->nm->data, s->e0, s->e1, s->einv, s->pc));
+            s->cs_built = true;
+        }
+        // T^T P for the CURRENT weights (the iteration carries T^T p along by linearity and needs it exactly)
+        LSS_TRY(coarse_update_b(s->cs, rows, s->nm->indptr, s->nm->indices, s->nm->data, s->e0, s->e1, s->pc));
+    }
+    // right-hand side of the Schur system on the own rows: g' = g_g - N_gE N_EE^-1 g_E
+    const double *gq = nullptr;
+    if (n_e > 0) {
+        LSS_CUDA(cudaMemsetAsync(s->p, 0, sizeof(double) * n, st));
+        elim_scale_kernel<<<ceil_div(n_e, 256), 256, 0, st>>>(s->e0, n_e, s->einv, s->g + s->e0, 1.0, s->p);
+        LSS_LAUNCH_CHECK();
+        LSS_TRY(normal_apply(s->nm, s->p, s->buf, nullptr, nullptr));
+        gq = s->buf;
+    }
+    resid_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->g, gq, s->fixed, s->e0, s->e1, nullptr, s->r);
+    LSS_LAUNCH_CHECK();
+    mask_own_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->owned, s->e0, s->e1, 0, s->r);
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(shard_precond(s, s->r, s->z));
+    init_p_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->r, s->z, nullptr, s->part2);
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(comm_allreduce(s->pc, s->part2, VEC_GRID, 0, 0, st));
+    cg_scalar_kernel<<<1, VEC_BLOCK, 0, st>>>(s->part2, VEC_GRID, s->scal, S_BNORM, 0.0, 0);
+    LSS_LAUNCH_CHECK();
+    s->have_weights = true;
+    return LSS_OK;
+}
+
+int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t *iters_h, double *relres_h) {
+    cudaStream_t st = s->stream;
+    const int64_t n = s->n_cols;
+    const int n_e = (int)(s->e1 - s->e0);
+    lss_comm *pc = s->pc;
+    const int P = pc->n_ranks;
+    s->launches = 0;
+    s->n_apply = 0;
+    s->ms_a = s->ms_at = s->ms_step = 0.0;
+    s->n_prof = 0;
+    // mailbox layout (8-byte words)
+    const int n_c = (s->cs && s->cs->ready) ? s->cs->n_c : 0;
+    const int bs = s->bp->bs;
+    ShardArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.rank = pc->rank; sa.n_ranks = P; sa.blk_lo = s->blk_lo; sa.blk_hi = s->blk_hi;
+    sa.LB = (1 + n_c + n_e + 3) & ~3;
+    sa.ZP = (long long)s->bp->n_blocks * bs;
+    sa.off_fa = 0; sa.off_da = 2 * P; sa.off_fb = 4 * P; sa.off_db = (6 * P + 7) & ~7;
+    sa.off_z = (sa.off_db + 2ll * P * sa.LB + 7) & ~7ll;
+    const size_t need = sizeof(double) * (size_t)(sa.off_z + 2 * sa.ZP);
+    if (need > pc->box_bytes) return fail(LSS_EINVAL, "solver_solve: the mailbox holds %zu bytes, the exchange needs %zu", pc->box_bytes, need);
+    for (int r = 0; r < P; ++r) sa.box[r] = reinterpret_cast<unsigned long long *>(pc->box_peer[r]);
+    sa.seq = pc->seq;
+    pc->seq += 2ull * (unsigned long long)(max_iter > 0 ? max_iter : 0) + 8ull;      // the same on every rank: all call solve with the same arguments
+    sa.n_e = n_e; sa.e0 = s->e0;
+    sa.n_indptr = s->nm->indptr; sa.n_indices = s->nm->indices; sa.n_data = s->nm->data;
+    sa.einv = s->einv; sa.Bt = s->cs ? s->cs->Bt : nullptr; sa.u_e = s->u_e; sa.tk = s->tk;
+    CoarseArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.n_c = n_c;
+    if (n_c > 0) {
+        lss::CoarseSpace *c = s->cs;
+        ca.chunks = (s->step_sh_grid * (VEC_BLOCK / 32)) / (n_c + n_e);
+        if (ca.chunks < 1) ca.chunks = 1;
+        if (ca.chunks > CS_CHUNKS_MAX) ca.chunks = CS_CHUNKS_MAX;
+        ca.pt_ptr = c->pt_ptr; ca.pt_col = c->pt_col; ca.pt_w = c->pt_w; ca.inv = c->inv;
+        ca.cp_idx = reinterpret_cast<const int4 *>(c->cp_idx); ca.cp_w = reinterpret_cast<const float4 *>(c->cp_w);
+        ca.rc_part = c->rc_part; ca.zc_part = c->zc_part;
+    } else {
+        ca.chunks = 1;
+    }
+    LSS_CUDA(cudaEventRecord(s->ev0, st));
+    s->q_clean = false;
+    LSS_CUDA(cudaMemsetAsync(s->scal + S_ERR, 0, sizeof(double), st));
+    // ---- start: r = g' - S x_g on the own rows (x is complete on every rank), z, p = z everywhere, r.z, T^T p
+    zero_fixed_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->fixed, x);
+    LSS_LAUNCH_CHECK();
+    if (n_e > 0) LSS_TRY(shard_slave(s, x, s->g));
+    LSS_TRY(apply_normal(s, x, false, nullptr));
+    resid_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->g, s->buf, s->fixed, s->e0, s->e1, x, s->r);
+    LSS_LAUNCH_CHECK();
+    mask_own_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->owned, s->e0, s->e1, 0, s->r);
+    LSS_LAUNCH_CHECK();
+    LSS_CUDA(cudaMemcpyAsync(s->r2, s->r, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    LSS_TRY(shard_precond(s, s->r, s->z));
+    init_p_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->r, s->z, s->p, s->part2);
+    LSS_LAUNCH_CHECK();
+    LSS_TRY(comm_allreduce(pc, s->part2, VEC_GRID, 0, 0, st));
+    LSS_TRY(comm_allreduce(pc, s->p, n, 0, 0, st));                  // zero-padded own parts: the sum is the complete direction
+    if (n_e > 0) {
+        LSS_TRY(shard_slave(s, s->p, nullptr));                      // p_E = -N_EE^-1 N_Eg p_g
+        LSS_CUDA(cudaMemcpyAsync(s->u_e, s->eraw, sizeof(double) * n_e, cudaMemcpyDeviceToDevice, st));
+    }
+    cg_scalar_kernel<<<1, VEC_BLOCK, 0, st>>>(s->part2, VEC_GRID, s->scal, S_RZ0, rtol, max_iter);
+    LSS_LAUNCH_CHECK();
+    s->launches += 8;
+    const void *kern = step_shard_kernel_for(bs);
+    int issued = 0, parity = 0, slot = 0;
+    bool done = false;
+    bool pending[2] = {false, false};
+    while (!done) {
+        const int todo = (max_iter - issued) < kBatch ? (max_iter - issued) : kBatch;
+        for (int k = 0; k < todo; ++k) {
+            LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity));
+            double *qv = s->buf, *minv = s->minv, *pv = s->p, *zv = s->z, *part = s->part2, *scal = s->scal, *slots = s->buf + n;
+            int64_t nn = n;
+            int par = parity, nb = s->bp->n_blocks;
+            const int *bcols = s->bp->cols_pad;
+            const float *binv = s->bp->inv;
+            const double *r_in = parity ? s->r2 : s->r;
+            double *r_out = parity ? s->r : s->r2;
+            void *args[] = {&nn, &qv, &slots, &minv, &pv, &x, &r_in, &r_out, &zv, &part, &scal, &par, &nb, &bcols, &binv, &ca, &sa};
+            LSS_CUDA(cudaLaunchCooperativeKernel(kern, dim3(s->step_sh_grid), dim3(VEC_BLOCK), args, 0, st));
+            ++lss::g_launches;
+            s->launches += 1;
+            s->q_clean = true;
+            parity ^= 1;
+        }
+        issued += todo;
+        LSS_CUDA(cudaMemcpyAsync(s->host_scal + slot * S_COUNT, s->scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaEventRecord(s->ev_batch[slot], st));
+        pending[slot] = true;
+        const int prev = slot ^ 1;
+        if (pending[prev]) {
+            LSS_CUDA(cudaEventSynchronize(s->ev_batch[prev]));
+            pending[prev] = false;
+            if (s->host_scal[prev * S_COUNT + S_DONE0] != 0.0 || s->host_scal[prev * S_COUNT + S_DONE1] != 0.0) done = true;
+        }
+        if (!done && (issued >= max_iter || todo == 0)) {
+            LSS_CUDA(cudaEventSynchronize(s->ev_batch[slot]));
+            pending[slot] = false;
+            done = true;
+        }
+        slot ^= 1;
+    }
+    // ---- end: back-substitution of the eliminated block, then the own parts of x become the complete x on every rank
+    if (n_e > 0) LSS_TRY(shard_slave(s, x, s->g));
+    {
+        Scratch keep;
+        if (n_e > 0) {
+            LSS_CUDA(keep.alloc(sizeof(double) * n_e, st));
+            LSS_CUDA(cudaMemcpyAsync(keep.p, x + s->e0, sizeof(double) * n_e, cudaMemcpyDeviceToDevice, st));
+        }
+        mask_own_kernel<<<VEC_GRID, VEC_BLOCK, 0, st>>>(n, s->owned, s->e0, s->e1, 0, x);
+        LSS_LAUNCH_CHECK();
+        LSS_TRY(comm_allreduce(pc, x, n, 0, 0, st));
+        if (n_e > 0) LSS_CUDA(cudaMemcpyAsync(x + s->e0, keep.p, sizeof(double) * n_e, cudaMemcpyDeviceToDevice, st));     // identical on every rank
+    }
+    LSS_CUDA(cudaMemcpyAsync(s->host_scal, s->scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
+    LSS_CUDA(cudaEventRecord(s->ev1, st));
+    LSS_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    s->ms_total = ms;
+    const double bn = s->host_scal[S_BNORM], rzl = s->host_scal[S_RZ_LAST];
+    if (iters_h) *iters_h = (int32_t)s->host_scal[S_ITERS];
+    if (relres_h) *relres_h = bn > 0.0 ? sqrt(rzl / bn) : 0.0;
+    if (s->host_scal[S_ERR] != 0.0) return fail(LSS_ENCCL, "solver_solve: a peer did not answer within the exchange time-out (row-sharded CG)");
+    return LSS_OK;
+}
+
+}  // namespace
+
 extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
     if (!s || !w) return fail(LSS_EINVAL, "solver_set_weights: null argument");
+    if (s->shard) return shard_set_weights(s, w);
     cudaStream_t st = s->stream;
     if (s->n_rows > 0) LSS_CUDA(cudaMemcpyAsync(s->w, w, sizeof(double) * s->n_rows, cudaMemcpyDeviceToDevice, st));
     // g = A^T (w .* b)  and the Jacobi diagonal diag(A^T W A)
@@ -1433,6 +2119,7 @@ extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
 extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t max_iter, int32_t *iters_h, double *relres_h) {
     if (!s || !x) return fail(LSS_EINVAL, "solver_solve: null argument");
     if (!s->have_weights) return fail(LSS_EINVAL, "solver_solve: call lss_solver_set_weights first");
+    if (s->shard) return shard_solve(s, x, rtol, max_iter, iters_h, relres_h);
     cudaStream_t st = s->stream;
     const int64_t n = s->n_cols;
     s->launches = 0;

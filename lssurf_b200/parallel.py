@@ -109,10 +109,58 @@ class DistContext(object):
         _cabi.check(_cabi.lib().lss_comm_allreduce_f64(self.comm, _cabi.ptr(t), int(t.numel()), _cabi.stream()))
         return t
 
+    def ensure_box(self, nbytes):
+        """Peer-to-peer mailbox of at least nbytes on every rank (``lss_comm_box_*``): allocated once per communicator,
+        CUDA IPC handles exchanged through torch.distributed (host transport), mapped into every rank."""
+        if self.comm is None:
+            raise _cabi.LssError('the peer-to-peer mailbox needs a communicator')
+        L = _cabi.lib()
+        have = C.c_int64(0)
+        _cabi.check(L.lss_comm_box_bytes(self.comm, C.byref(have)))
+        if have.value >= nbytes:
+            return
+        if have.value > 0:
+            raise _cabi.LssError(f'mailbox of {have.value} bytes is too small ({nbytes} needed); set LSS_BOX_BYTES before the first fit')
+        size = max(int(nbytes), int(os.environ.get('LSS_BOX_BYTES', str(32 << 20))))
+        if self.world > 1:
+            import torch.distributed as dist
+            sizes = [None] * self.world
+            dist.all_gather_object(sizes, size)
+            size = max(sizes)
+        buf = C.create_string_buffer(64)
+        _cabi.check(L.lss_comm_box_alloc(self.comm, size, buf))
+        handles = None
+        if self.world > 1:
+            import torch.distributed as dist
+            parts = [None] * self.world
+            dist.all_gather_object(parts, bytes(buf.raw))
+            handles = b''.join(parts)
+        _cabi.check(L.lss_comm_box_open(self.comm, handles))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def gather_ints(self, values):
+        """Every rank's list of integers, as a list of lists in rank order (host transport)."""
+        if self.world == 1:
+            return [list(values)]
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, [int(v) for v in values])
+        return parts
+
     def destroy(self):
         if self.comm is not None:
             _cabi.load().lss_comm_destroy(self.comm)
             self.comm = None
+
+
+def single_rank_context():
+    """A one-rank context WITH a communicator handle: lets the row-sharded solver (mailbox exchange with itself) run
+    on a single GPU, which is how its kernels are tested where only one device is available."""
+    handle = C.c_void_p(0)
+    _cabi.check(_cabi.lib().lss_comm_create(C.byref(handle), None, 0, 1))
+    return DistContext(0, 1, handle)
 
 
 def init_from_env():

@@ -169,20 +169,42 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
     st0.mark('it:G_csr(sort)')
     C_all = Gc._csr_device(col_N=n_cols, row_N=int(Gc.N_eq))
     st0.mark('it:C_csr(sort)')
+    shard = args.get('_shard')
     multi = dist is not None and dist.world > 1
-    replicate = multi and not os.environ.get('LSS_SHARDED_SOLVE')
+    replicate = multi and shard is None and not os.environ.get('LSS_SHARDED_SOLVE')
     st = _Stages(bool(args.get('time_stages')), timing.setdefault('stages', {}))
     st.mark('it:prep')
     structure = grid_structure(grids, fixed_cols, bias_cols=G_data.TOC['cols'].get('data_bias')) if isinstance(grids, dict) else None
     if structure is not None and 'block_ptr' in structure and os.environ.get('LSS_COARSE', '1') != '0':
         # two-level preconditioner: exact solve on a coarse bilinear space on top of block-Jacobi (pays off once the
         # domain is many dz cells across; LSS_COARSE_MIN_BLOCKS moves the threshold, LSS_COARSE=0 switches it off)
-        if structure['block_ptr'].size - 1 >= int(os.environ.get('LSS_COARSE_MIN_BLOCKS', '2000')):
+        if structure['block_ptr'].numel() - 1 >= int(os.environ.get('LSS_COARSE_MIN_BLOCKS', '2000')):
             cs = coarse_structure(grids, fixed_cols, n_cols)
             if cs is not None:
                 structure['coarse'] = cs
                 structure['coarse_refresh'] = int(os.environ.get('LSS_COARSE_REFRESH', '0'))
-    if replicate:
+    if shard is not None:
+        # row-sharded solve: this rank's own blocks of N (built from its own points + halo copies and all constraint rows),
+        # p exchanged with the peers inside the CG step kernel through the P2P mailbox (no collective per iteration)
+        if structure is None or 'block_ptr' not in structure or structure['block_ptr'].numel() - 1 != shard['n_blocks']:
+            raise _cabi.LssError('row-sharded solve: the preconditioner blocks do not match the dz nodes (use LSS_REPLICATED_SOLVE=1)')
+        bp_t, bc_t = structure['block_ptr'], structure['block_cols']
+        owned = torch.zeros(n_cols, dtype=torch.uint8, device=dev)
+        owned[bc_t[int(bp_t[shard['block_lo']].item()):int(bp_t[shard['block_hi']].item())].long()] = 1
+        if 'coarse' in structure:
+            structure['coarse'] = coarse_structure(grids, fixed_cols, n_cols, owned=owned)
+        n_e = (structure['elim'][1] - structure['elim'][0]) if 'elim' in structure else 0
+        n_c = structure['coarse']['n_c'] if structure.get('coarse') else 0
+        P = dist.world
+        bs = (int(structure['max_block']) + 3) // 4 * 4
+        dist.ensure_box(8 * (8 * P + 16 + 2 * P * (n_c + n_e + 8) + 2 * bs * shard['n_blocks']))
+        st.mark('it:csr')
+        solver = NormalSolver(G_csr, C_all, z, rhs_d[n_data:].contiguous(), sigma, E_all[n_data:].contiguous(), fixed_cols, dist,
+                              structure=structure, stages=st,
+                              shard=dict(owned_cols=owned, block_lo=shard['block_lo'], block_hi=shard['block_hi'], own_rows=shard['own_rows']))
+        o0, o1 = shard['own_rows']
+        solver.G_local = G_csr.row_slice(o0, o1) if (o0, o1) != (0, n_data) else G_csr
+    elif replicate:
         # replicated solve: every rank gets all assembled rows once and runs the same PCG with no collective inside the
         # iteration; per-point work (residuals, sigma_extra, edit masks) stays on the rank's own rows
         row_counts = dist.gather_counts(n_data)
@@ -219,6 +241,15 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
     if sigma_extra_masks is not None:
         groups = {k: _cabi.to_dev(np.asarray(v).astype(np.uint8), torch.uint8) for k, v in sigma_extra_masks.items()}
 
+    if shard is not None:
+        # per-point work (residuals, order statistics, masks) runs on the own rows; the solver's weights also need the
+        # masks of the halo copies, which come from their owners (all-gather of the own masks after every edit)
+        o0, o1 = shard['own_rows']
+        in_TSE_ext = in_TSE_d
+        in_TSE_d = in_TSE_ext[o0:o1].contiguous()
+        in_TSE_original = in_TSE_d.clone()
+        sigma_ext, sigma, z = sigma, sigma[o0:o1].contiguous(), z[o0:o1].contiguous()
+        n_data = o1 - o0
     sigma_extra = torch.zeros(n_data, dtype=f64, device=dev)
     r_data = torch.empty(n_data, dtype=f64, device=dev)
     dz_cols = np.asarray(Gc.TOC['cols']['dz']) if 'dz' in Gc.TOC['cols'] else np.zeros(0, dtype=int)
@@ -229,7 +260,12 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         relax = last_iteration and args['sigma_extra_relax']
         if relax and args['VERBOSE']:
             print('smooth_fit.iterate_fit: relaxing errors by sigma_extra')
-        if replicate:
+        if shard is not None:
+            se_ext = None
+            if relax:
+                se_ext = torch.full_like(sigma_ext, float(se_values.get('all', 0.)))      # one global value (no groups in this mode)
+            solver.set_rows(in_TSE_ext, se_ext)
+        elif replicate:
             solver.set_rows(dist.gather_var_device(in_TSE_d, row_counts),
                             dist.gather_var_device(sigma_extra, row_counts) if relax else None)
         else:
@@ -266,11 +302,14 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         st.mark('it:sigma_extra')
         in_TSE_last = in_TSE_d
         in_TSE_d, est = _cabi.edit_mask(r_data, sigma, sigma_extra, 3.0, comm)
+        if shard is not None:
+            full_mask = dist.gather_var_device(in_TSE_d, shard['counts'])
+            in_TSE_ext = full_mask[shard['lo_e']:shard['hi']].contiguous()
         st.mark('it:edit_mask')
         timing.setdefault('near_threshold', []).append(est['near_threshold'])
         if args.get('history') is not None:      # per-iteration tap for parity tests
             args['history'].append(dict(iteration=iteration, m0=m0.copy(), sigma_extra=dict(se_values),
-                                        mask_out=np.packbits(in_TSE_d.cpu().numpy()), count=est['count'],
+                                        mask_out=np.packbits((full_mask if shard is not None else in_TSE_d).cpu().numpy()), count=est['count'],
                                         near_threshold=est['near_threshold'], pcg=dict(solver.last)))
         bias_editing_changed = _edit_by_bias(data, m0, in_TSE_d, iteration, bias_model, args)
         recount = args['bias_nsigma_edit'] is not None      # flagged biases drop their data from the mask on every pass
@@ -390,7 +429,7 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
         rs = r_in / torch.sqrt(f['sigma'] ** 2 + f['sigma_extra'] ** 2)
     else:
         rs = r_in / f['sigma']
-    Gd = G_data._csr_device(col_N=n_cols, row_N=int(r.numel()))
+    Gd = f.get('G_rows') or G_data._csr_device(col_N=n_cols, row_N=int(r.numel()))
     sums = {}
     for key, vec in (('count', tse.to(torch.float64)), ('misfit_scaled_rms', rs * rs), ('misfit_rms', r_in * r_in)):
         full = Gd.rdot(vec.contiguous())                 # G^T vec by scatter: three products do not pay for a transpose
@@ -458,6 +497,22 @@ def _assign_bias_ID_device(fields_d, bias_params, sigma_corr_d):
         model['bias_ID_dict'][k] = {p: shown[j] for j, p in enumerate(bias_params)}
         model['E_bias'][k] = e_bias[k]
     return ids, model
+
+
+def _shard_plan(grids, cell_ids, dist):
+    """Ownership of the row-sharded solve: rank k owns the preconditioner blocks (dz nodes, row-major)
+    [k n_b / P, (k + 1) n_b / P), the points whose dz cell has its lower-left node among them, and additionally holds
+    halo copies of the points of the cell row below (every point that touches one of its columns).  ``cell_ids``: the
+    dz-cell id (= id of the cell's lower-left node) of every point in the internal (sorted) order."""
+    ny, nx, _ = (int(v) for v in grids['dz'].shape)
+    n_b = ny * nx
+    P, k = dist.world, dist.rank
+    bounds = [(r * n_b) // P for r in range(P + 1)]
+    edges = torch.tensor(bounds + [max(b - nx - 1, 0) for b in bounds[:-1]], dtype=cell_ids.dtype, device=cell_ids.device)
+    pos = torch.searchsorted(cell_ids, edges).cpu().numpy()
+    starts, halo = pos[:P + 1], pos[P + 1:]
+    return dict(block_lo=bounds[k], block_hi=bounds[k + 1], lo=int(starts[k]), hi=int(starts[k + 1]), lo_e=int(halo[k]),
+                counts=[int(starts[r + 1] - starts[r]) for r in range(P)], n_blocks=n_b)
 
 
 def smooth_fit(**kwargs):
@@ -547,7 +602,7 @@ def smooth_fit(**kwargs):
             data_filt = args['bias_filter'](data)
             extra_d.update({p: _field_dev(data_filt, p) for p in args['bias_params']})
         bias_id_d, bias_model = _assign_bias_ID_device(extra_d, args['bias_params'], extra_d['sigma_corr'])
-        data.assign({'bias_ID': _cabi.to_host(bias_id_d).astype(float)})
+        data.assign({'bias_ID': _cabi.to_host(bias_id_d.to(f64))})      # float on the device: no 10^7-element host cast
         if args['bias_nsigma_edit']:
             bias_model['bias_param_dict']['edited'] = np.zeros_like(bias_model['bias_param_dict']['ID'], dtype=bool)
 
@@ -557,18 +612,31 @@ def smooth_fit(**kwargs):
     # caller's order.  Skipped where the caller sees operator rows (return_fit_objects) or per-point host logic
     # addresses rows (bias editing, `editable`).
     order = None
+    shard = None
     if (args['sort_points'] and os.environ.get('LSS_SORT_POINTS', '1') != '0' and not args['return_fit_objects'] and args['bias_nsigma_edit'] is None
             and args['bias_edit_vals'] is None and 'editable' not in data.fields and args['sigma_extra_masks'] is None
             and args['data_slope_sensors'] is None and args['sensor_grid_bias_params'] is None
             and args['sigma_extra_bin_spacing'] is None and n_all > 1):
-        order = _cabi.spatial_order(grids['z0'].as_struct(), grids['dz'].as_struct(), [y_d, x_d, t_d])
+        order, keys = _cabi.spatial_order(grids['z0'].as_struct(), grids['dz'].as_struct(), [y_d, x_d, t_d], return_keys=True)
+        if (dist is not None and dist.comm is not None and not os.environ.get('LSS_REPLICATED_SOLVE')
+                and (dist.world > 1 or os.environ.get('LSS_SHARD_SINGLE')) and len(grids['dz'].shape) == 3 and len(grids['z0'].shape) == 2):
+            # row-sharded solve: ownership follows the dz cells, which is the leading part of the sort key
+            div = int(grids['z0'].shape[0]) * int(grids['z0'].shape[1]) * int(grids['dz'].shape[2])
+            shard = _shard_plan(grids, torch.div(keys[order], div, rounding_mode='floor'), dist)
+        del keys
         y_d, x_d, t_d, z_d, s_d = (a[order].contiguous() for a in (y_d, x_d, t_d, z_d, s_d))
         tse_d = None if tse_d is None else tse_d[order].contiguous()
         bias_id_d = None if bias_id_d is None else bias_id_d[order].contiguous()
         rz = rd = None
         stages.mark('spatial_sort')
     # ---- this rank's block of points
-    lo, hi = (0, n_all) if dist is None else dist.shard(n_all)
+    if shard is not None:
+        lo, hi = shard['lo_e'], shard['hi']          # rows assembled here: halo copies [lo_e, lo) + own points [lo, hi)
+        shard['own_rows'] = (shard['lo'] - lo, hi - lo)
+        args['_shard'] = shard
+    else:
+        lo, hi = (0, n_all) if dist is None else dist.shard(n_all)
+        args.pop('_shard', None)
     whole = (lo, hi) == (0, n_all)
     if order is not None:
         # rows are in the internal order: the loop only needs the row count from the point container
@@ -699,12 +767,22 @@ def smooth_fit(**kwargs):
         timing['iteration'] = time() - tic_iteration
         stages.mark('iterate_fit')
         # model estimate of every data point, G_data . m0 (smooth_fit.py:662); the CSR is already cached
-        z_est_d = G_data._csr_device(col_N=m0.size, row_N=hi - lo).dot(_cabi.to_dev(m0, f64))
+        G_rows = G_data._csr_device(col_N=m0.size, row_N=hi - lo)
+        z_own, s_own, ids_own = z_loc, s_loc, (None if bias_id_d is None else bias_id_d[lo:hi])
+        if shard is not None:            # results are reported for the own rows; the halo copies belong to other ranks
+            o0, o1 = shard['own_rows']
+            if (o0, o1) != (0, hi - lo):
+                G_rows = G_rows.row_slice(o0, o1)
+                z_own, s_own = z_loc[o0:o1].contiguous(), s_loc[o0:o1].contiguous()
+                ids_own = None if ids_own is None else ids_own[o0:o1].contiguous()
+        z_est_d = G_rows.dot(_cabi.to_dev(m0, f64))
         multi = dist is not None and dist.world > 1
 
         def to_caller(t):
             """device rows of this rank -> NumPy over all points in the caller's order"""
-            if multi:
+            if shard is not None:
+                t = dist.gather_var_device(t, shard['counts'])
+            elif multi:
                 t = dist.gather_rows_device(t, n_all)
             if order is not None:
                 out = torch.empty_like(t)
@@ -715,7 +793,7 @@ def smooth_fit(**kwargs):
         in_TSE_all = to_caller(tse_out_d).astype(bool)
         sigma_extra_all = to_caller(se_d)
         z_est_all = to_caller(z_est_d)
-        if args.get('history') is not None and order is not None and not multi:
+        if args.get('history') is not None and order is not None and (not multi or shard is not None):
             for h in args['history']:             # per-iteration masks were recorded in the internal order
                 mk = torch.empty(n_all, dtype=torch.uint8, device=z_d.device)
                 mk[order] = _cabi.to_dev(np.unpackbits(h['mask_out'])[:n_all])
@@ -726,8 +804,8 @@ def smooth_fit(**kwargs):
         data.assign({'z_est': np.reshape(z_est_all, data.shape)})
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
         averaging_ops.update(setup_z0_avg(grids, grids['dz'].col_N, args))
-        dev_fields = {'z': z_loc, 'sigma': s_loc, 'z_est': z_est_d, 'three_sigma_edit': tse_out_d, 'sigma_extra': se_d,
-                      'bias_ID': None if bias_id_d is None else bias_id_d[lo:hi]}
+        dev_fields = {'z': z_own, 'sigma': s_own, 'z_est': z_est_d, 'three_sigma_edit': tse_out_d, 'sigma_extra': se_d,
+                      'bias_ID': ids_own, 'G_rows': G_rows}
         stages.mark('outputs_d2h')
         parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args,
                     dist=dist if (dist is not None and dist.world > 1) else None, stages=stages)

@@ -67,30 +67,44 @@ class NormalMatrix(object):
             pass
 
 
+def _structure_device():
+    """Where the index tables of the solver structure are built: the GPU when there is one (they are handed to the C ABI
+    as device arrays); the CPU otherwise, so that the tables themselves can be checked without a device."""
+    return _cabi.device() if torch.cuda.is_available() else torch.device('cpu')
+
+
 def grid_structure(grids, fixed_cols, bias_cols=None, max_block=64):
     """Column structure handed to ``lss_solver_set_structure``: one preconditioner block per dz node (its free epochs
     plus the z0 nodes nearest to it), and the bias column range to eliminate.  ``grids``: the dict of fd_grid objects
-    smooth_fit builds (needs 'z0' with 2 and 'dz' with 3 dimensions, same extent); returns None without them."""
+    smooth_fit builds (needs 'z0' with 2 and 'dz' with 3 dimensions, same extent); returns None without them.
+    ``block_ptr`` / ``block_cols`` are int32 device tensors (built with tensor ops on the device: 4e5 columns)."""
     out = {}
     z0, dz = grids.get('z0'), grids.get('dz')
     if z0 is not None and dz is not None and len(z0.shape) == 2 and len(dz.shape) == 3:
+        dev = _structure_device()
         ny, nx, nt = [int(v) for v in dz.shape]
-        k = np.arange(int(z0.N_nodes))
-        iy, ix = np.divmod(k, int(z0.shape[1]))
-        jy = np.clip(np.floor((z0.ctrs[0][iy] - dz.ctrs[0][0]) / dz.delta[0] + 0.5), 0, ny - 1).astype(np.int64)
-        jx = np.clip(np.floor((z0.ctrs[1][ix] - dz.ctrs[1][0]) / dz.delta[1] + 0.5), 0, nx - 1).astype(np.int64)
-        cols = np.concatenate([z0.col_0 + k, dz.col_0 + np.arange(int(dz.N_nodes))])
-        blk = np.concatenate([jy * nx + jx, np.arange(int(dz.N_nodes)) // nt])
-        free = np.ones(int(cols.max()) + 1, dtype=bool)
-        free[np.asarray(fixed_cols, dtype=np.int64)] = False
+        # nearest dz node of every z0 row / column (tiny host tables), then everything per column on the device
+        jy_tab = np.clip(np.floor((z0.ctrs[0] - dz.ctrs[0][0]) / dz.delta[0] + 0.5), 0, ny - 1).astype(np.int64)
+        jx_tab = np.clip(np.floor((z0.ctrs[1] - dz.ctrs[1][0]) / dz.delta[1] + 0.5), 0, nx - 1).astype(np.int64)
+        jy_d, jx_d = torch.from_numpy(jy_tab).to(dev), torch.from_numpy(jx_tab).to(dev)
+        n0, nd = int(z0.N_nodes), int(dz.N_nodes)
+        k = torch.arange(n0, device=dev)
+        blk0 = jy_d[k // int(z0.shape[1])] * nx + jx_d[k % int(z0.shape[1])]
+        kd = torch.arange(nd, device=dev)
+        cols = torch.cat([int(z0.col_0) + k, int(dz.col_0) + kd])
+        blk = torch.cat([blk0, kd // nt])
+        free = torch.ones(int(cols.max().item()) + 1, dtype=torch.bool, device=dev)
+        if len(fixed_cols):
+            free[torch.from_numpy(np.asarray(fixed_cols, dtype=np.int64)).to(dev)] = False
         sel = free[cols]
         cols, blk = cols[sel], blk[sel]
-        order = np.argsort(blk, kind='stable')
-        counts = np.bincount(blk, minlength=ny * nx)
+        order = torch.argsort(blk, stable=True)
+        counts = torch.bincount(blk, minlength=ny * nx)
         counts = counts[counts > 0]
-        if counts.size and counts.max() <= max_block:
-            out.update(block_ptr=np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), block_cols=cols[order].astype(np.int32),
-                       max_block=int(counts.max()))
+        if counts.numel() and int(counts.max().item()) <= max_block:
+            ptr = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=dev)
+            ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            out.update(block_ptr=ptr, block_cols=cols[order].to(torch.int32).contiguous(), max_block=int(counts.max().item()))
     if bias_cols is not None and len(bias_cols) > 0:
         b = np.asarray(bias_cols, dtype=np.int64)
         if b.max() - b.min() + 1 == b.size:
@@ -110,12 +124,13 @@ def _coarse_1d(nf, c):
     return coarse.size, lo.astype(np.int64), hi.astype(np.int64), w.astype(np.float64)
 
 
-def coarse_structure(grids, fixed_cols, n_cols, max_coarse=1024):
+def coarse_structure(grids, fixed_cols, n_cols, max_coarse=1024, owned=None):
     """Coarse space of the two-level preconditioner (``lss_solver_set_coarse``): bilinear functions of (y, x) on a grid
     c times coarser than z0 / dz (same factor for both, every epoch of dz kept), c the smallest power of two that
     leaves at most ``max_coarse`` coarse unknowns.  Returns device tensors: per fine column its <= 4 parents and
     weights (``cp_idx`` int32 [n_cols, 4], -1 = none; ``cp_w`` float32) and P^T as CSR by coarse row.
-    Fixed columns (reference epoch) and columns outside the two grids have no parents."""
+    Fixed columns (reference epoch) and columns outside the two grids have no parents.  With ``owned`` (uint8 per column)
+    P^T keeps the entries at those columns only (one rank's share of the restriction)."""
     z0, dz = grids.get('z0'), grids.get('dz')
     if z0 is None or dz is None or len(z0.shape) != 2 or len(dz.shape) != 3:
         return None
@@ -129,7 +144,7 @@ def coarse_structure(grids, fixed_cols, n_cols, max_coarse=1024):
         c *= 2
         if c > 4 * max(ny0, nx0, ny, nx):
             return None
-    dev = _cabi.device()
+    dev = _structure_device()
     idx = torch.full((n_cols, 4), -1, dtype=torch.int32, device=dev)
     wts = torch.zeros((n_cols, 4), dtype=torch.float32, device=dev)
 
@@ -152,11 +167,14 @@ def coarse_structure(grids, fixed_cols, n_cols, max_coarse=1024):
     base = fill(int(z0.col_0), (ny0, nx0), 1, 0)
     n_c = fill(int(dz.col_0), (ny, nx), nt, base)
     if len(fixed_cols):
-        fc = _cabi.to_dev(np.asarray(fixed_cols, dtype=np.int64), torch.int64)
+        fc = torch.from_numpy(np.asarray(fixed_cols, dtype=np.int64)).to(dev)
         idx[fc] = -1
         wts[fc] = 0
     flat = idx.reshape(-1)
-    sel = torch.nonzero(flat >= 0).reshape(-1)
+    keep = flat >= 0
+    if owned is not None:          # a rank of the row-sharded solver restricts from its own columns only
+        keep = keep & owned.to(dev).bool().repeat_interleave(4)
+    sel = torch.nonzero(keep).reshape(-1)
     order = torch.argsort(flat[sel], stable=True)
     ent = sel[order]
     counts = torch.bincount(flat[ent].to(torch.int64), minlength=n_c)
@@ -167,7 +185,8 @@ def coarse_structure(grids, fixed_cols, n_cols, max_coarse=1024):
 
 
 class NormalSolver(object):
-    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None, G_local=None, stages=None):
+    def __init__(self, G, Cn, z, prior, sigma, Ec, fixed_cols, dist=None, fused=True, structure=None, G_local=None, stages=None,
+                 shard=None):
         """G: DeviceCSR of this rank's data rows; Cn: DeviceCSR of this rank's constraint rows;
         z / sigma: data values and errors (CUDA fp64); prior / Ec: constraint right-hand side and sigma;
         fixed_cols: columns held at zero (reference epoch)."""
@@ -187,7 +206,25 @@ class NormalSolver(object):
         con_len = int((Cn.indptr[1:] - Cn.indptr[:-1]).max().item()) if self.n_con > 0 else 0
         self.fused = bool(fused) and row_len <= 16 and not os.environ.get('LSS_NO_FUSED')
         self.all_ell = False
-        if self.fused:
+        self.shard = shard
+        if shard is not None:
+            # row-sharded N: G holds this rank's own points plus halo copies, Cn every constraint row; the rank owns the
+            # preconditioner blocks [block_lo, block_hi) and exchanges p with its peers through the P2P mailbox
+            if not (self.fused and con_len <= 16 and structure is not None and 'block_ptr' in structure):
+                raise _cabi.LssError('the row-sharded solver needs short rows and a block structure')
+            self.all_ell = True
+            self.A = DeviceCSR.vstack([G, Cn]) if self.n_con > 0 else G
+            e0, e1 = structure.get('elim', (0, 0))
+            self._owned = shard['owned_cols']
+            _cabi.check(L.lss_solver_create_sharded(
+                C.byref(self.handle), self.n_data + self.n_con, self.n_cols, max(row_len, con_len, 1), _cabi.ptr(self.A.indptr),
+                _cabi.ptr(self.A.indices), _cabi.ptr(self.A.data), _cabi.ptr(self.rhs), _cabi.ptr(self.fixed), int(self.fixed.numel()),
+                _cabi.ptr(self._owned), int(shard['block_lo']), int(shard['block_hi']), int(shard['own_rows'][0]), int(shard['own_rows'][1]),
+                int(self.n_data), int(e0), int(e1), dist.comm, _cabi.stream()))
+            self.A = None
+            if stages is not None:
+                stages.mark('it:solver_create(ELL+symbolic N)')
+        elif self.fused:
             p = _cabi.ptr
             nul = C.c_void_p(0)
             self.all_ell = con_len <= 16 and not os.environ.get('LSS_CSR_CONSTRAINTS')
@@ -231,9 +268,10 @@ class NormalSolver(object):
             e0, e1 = structure.get('elim', (0, 0))
             if os.environ.get('LSS_NO_ELIM'):
                 e0 = e1 = 0
-            nb = 0 if bp is None or os.environ.get('LSS_NO_BLOCKS') else int(bp.size) - 1
-            self._bp = _cabi.to_dev(np.asarray(bp if nb else [0], dtype=np.int32), torch.int32)
-            self._bc = _cabi.to_dev(np.asarray(bc if nb else [0], dtype=np.int32), torch.int32)
+            nb = 0 if bp is None or os.environ.get('LSS_NO_BLOCKS') else int(bp.numel()) - 1
+            zero = torch.zeros(1, dtype=torch.int32, device=z.device)
+            self._bp = _cabi.to_dev(bp, torch.int32) if nb else zero
+            self._bc = _cabi.to_dev(bc, torch.int32) if nb else zero
             rc = L.lss_solver_set_structure(self.handle, nb, _cabi.ptr(self._bp), _cabi.ptr(self._bc),
                                             int(structure.get('max_block', 1)), int(e0), int(e1))
             if rc == -1 and e1 > e0:         # LSS_EINVAL: the candidate block is not diagonal -> keep those columns in the solve

@@ -505,6 +505,36 @@ def test_two_level_preconditioner_agrees_with_block_jacobi(L, monkeypatch):
             assert its[key] < 1.25 * its['bj'], (key, its)      # the coarse level pays off on large domains only (bench workload: -60 %)
 
 
+def test_row_sharded_solver_on_one_rank_matches_the_plain_solver(L, monkeypatch):
+    """The row-sharded PCG (own blocks of N, p exchanged through the P2P mailbox inside the step kernel) run with a single
+    rank -- the mailbox is then local, every exchange goes to itself -- gives the plain solver's fit: same masks after
+    every iteration, same solution; with and without the coarse level and the eliminated bias block."""
+    from lssurf_b200 import synthetic, parallel
+    dist = parallel.single_rank_context()
+    try:
+        for gen, n, width in ((synthetic.icesat2_tracks, 200_000, 2.5e4), (synthetic.uniform_3d, 150_000, 2.5e4)):
+            pts, kw = gen(n=n, width=width, seed=17)
+            for coarse in ('0', '1'):
+                monkeypatch.setenv('LSS_COARSE', coarse)
+                monkeypatch.setenv('LSS_COARSE_MIN_BLOCKS', '1')
+                h0, h1 = [], []
+                ref = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, history=h0, **kw)
+                monkeypatch.setenv('LSS_SHARD_SINGLE', '1')
+                got = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, history=h1, dist=dist, **kw)
+                monkeypatch.delenv('LSS_SHARD_SINGLE')
+                assert rel_l2(got['m']['all'], ref['m']['all']) < 1e-9, (gen.__name__, coarse)
+                assert len(h0) == len(h1)
+                for a, b in zip(h0, h1):
+                    assert np.array_equal(a['mask_out'], b['mask_out']), (gen.__name__, coarse, a['iteration'])
+                assert np.array_equal(got['data'].three_sigma_edit, ref['data'].three_sigma_edit)
+                assert np.allclose(got['data'].z_est, ref['data'].z_est, rtol=0, atol=1e-7)
+                its = [sum(p['iterations'] for p in o['timing']['pcg']) for o in (ref, got)]
+                print(gen.__name__, 'coarse', coarse, 'CG iterations plain / sharded', its)
+                assert abs(its[0] - its[1]) <= 0.05 * its[0] + 5
+    finally:
+        dist.destroy()
+
+
 def test_large_scale_properties(L):
     """Full-size properties (cfg 3 shapes, 1e6 points) that need no oracle: row sums of the interpolation
     matrix are exactly 1 up to rounding, CSR is canonical, G^T products are adjoint, the solve reduces the residual."""

@@ -123,7 +123,7 @@ def test_grid_structure_partition():
     fixed = reference_epoch_columns(grids, 3)
     bias = np.arange(dz.col_N, dz.col_N + 7)
     st = grid_structure(grids, fixed, bias_cols=bias)
-    ptr, cols = st['block_ptr'], st['block_cols']
+    ptr, cols = st['block_ptr'].cpu().numpy(), st['block_cols'].cpu().numpy()
     assert st['elim'] == (dz.col_N, dz.col_N + 7)
     assert ptr[0] == 0 and ptr[-1] == cols.size and np.all(np.diff(ptr) > 0) and np.diff(ptr).max() == st['max_block'] <= 64
     free = np.setdiff1d(np.arange(dz.col_N), fixed)
@@ -140,6 +140,48 @@ def test_grid_structure_partition():
         assert np.all(np.abs(z0.ctrs[0][iy] - dz.ctrs[0][jy]) <= dz.delta[0] / 2)
         assert np.all(np.abs(z0.ctrs[1][ix] - dz.ctrs[1][jx]) <= dz.delta[1] / 2)
     assert grid_structure({'z0': z0}, fixed) is None                  # no dz grid: scalar Jacobi
+
+
+def test_coarse_structure_is_a_bilinear_partition_of_unity():
+    """Coarse space handed to lss_solver_set_coarse: every free grid column interpolates from <= 4 coarse unknowns with
+    weights that sum to 1 (bilinear in space, identity in time), fixed / foreign columns have no parents, P^T (CSR by
+    coarse row) holds exactly the same entries, and a fine node that is a coarse node has a single parent."""
+    from lssurf_b200.solver import coarse_structure
+    from lssurf_b200.constraint_functions import reference_epoch_columns
+    by, bx, bt = [-20000., 20000.], [-30000., 30000.], [-1., 1.]
+    z0 = fd_grid([by, bx], [250., 250.], name='z0')
+    dz = fd_grid([by, bx, bt], [1000., 1000., 0.25], name='dz', col_0=z0.N_nodes)
+    grids = {'z0': z0, 'dz': dz}
+    fixed = reference_epoch_columns(grids, 4)
+    n_cols = int(dz.col_N) + 5                                         # five bias columns behind the grids
+    cs = coarse_structure(grids, fixed, n_cols)
+    idx, w = cs['cp_idx'].cpu().numpy(), cs['cp_w'].cpu().numpy().astype(float)
+    assert cs['n_c'] <= 1024 and idx.shape == (n_cols, 4) and idx.max() < cs['n_c']
+    free = np.ones(n_cols, dtype=bool); free[fixed] = False; free[int(dz.col_N):] = False
+    assert np.all(idx[~free] == -1)
+    assert np.allclose(np.where(idx[free] >= 0, w[free], 0).sum(axis=1), 1.0, atol=1e-6)
+    assert np.all((idx[free] >= 0).sum(axis=1) >= 1)
+    # z0 and dz parents never mix; a dz column keeps its epoch
+    nz0c = idx[:int(z0.N_nodes)].max() + 1
+    assert np.all(idx[int(dz.col_0):int(dz.col_N)][idx[int(dz.col_0):int(dz.col_N)] >= 0] >= nz0c)
+    nt = int(dz.shape[2])
+    t_of = (np.arange(int(dz.N_nodes)) % nt)[:, None]
+    pd = idx[int(dz.col_0):int(dz.col_N)]
+    assert np.all(((pd - nz0c) % nt == t_of) | (pd < 0))
+    # corner node of both grids: exactly one parent with weight 1
+    assert (idx[0] >= 0).sum() == 1 and w[0][idx[0] >= 0][0] == 1.0
+    # P^T as CSR
+    ptr, col, pw = cs['pt_ptr'].cpu().numpy(), cs['pt_col'].cpu().numpy(), cs['pt_w'].cpu().numpy()
+    assert ptr[0] == 0 and ptr[-1] == col.size == int((idx >= 0).sum())
+    dense = {}
+    for c in range(n_cols):
+        for a in range(4):
+            if idx[c, a] >= 0:
+                dense[(int(idx[c, a]), c)] = np.float32(w[c, a])
+    m = 7
+    got = {(m, int(c)): np.float32(x) for c, x in zip(col[ptr[m]:ptr[m + 1]], pw[ptr[m]:ptr[m + 1]])}
+    assert got == {k: v for k, v in dense.items() if k[0] == m}
+    assert np.all(np.diff(col[ptr[m]:ptr[m + 1]]) >= 0)               # fixed entry order inside a coarse row
 
 
 def test_mask_for_ind0_all_true_fast_path_matches_sampling():
