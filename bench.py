@@ -260,8 +260,8 @@ def run_b200(a):
         nnzN = p0['nnz_N']
         nnzP = p0.get('nnz_product') or nnzN          # the rows of the eliminated bias block are not part of the CG product
         b_dom = spmv_bytes(n_cols - p0.get('eliminated', 0), n_cols, nnzP, False)
-        ms_dom = ms_at / n_apply
-        ach = b_dom / (ms_dom / 1e3) / 1e9
+        ms_dom = ms_at / max(n_apply, 1)
+        ach = b_dom / (ms_dom / 1e3) / 1e9 if ms_dom > 0 else 0.0
         b_two = spmv_bytes(p0['rows'], n_cols, nnz, True) + spmv_bytes(n_cols, p0['rows'], nnz, False)
         roofline = {'bound': 'hbm', 'kernel': 'lss::spmv_persistent_kernel<128,8,false,true> on the explicit normal matrix (q = N p, N = A^T W A; one launch, '
                               'atomic carries, p.q by-product)',
@@ -269,7 +269,7 @@ def run_b200(a):
                     'traffic': traffic, 'bytes_per_launch': {'N': b_dom}, 'launch_ms': {'N': ms_dom},
                     'launch_ms_samples': n_apply, 'launch_ms_sampling': 'CUDA event pairs on the solver stream around every 4th CG iteration of the timed steps',
                     'nnz_N': nnzN, 'nnz_streamed_per_product': nnzP, 'nnz_A': nnz,
-                    'csr_pair_equivalent': {'bytes': b_two, 'gbs': b_two / (ms_dom / 1e3) / 1e9,
+                    'csr_pair_equivalent': {'bytes': b_two, 'gbs': b_two / (ms_dom / 1e3) / 1e9 if ms_dom > 0 else None,
                                             'note': 'bytes the A / A^T two-product form of the same operator would stream, '
                                                     'divided by the time of the N product (not a bandwidth claim)'},
                     'frac_of_nominal_8TBs': ach / 8000.0}

@@ -942,6 +942,7 @@ struct ShardArgs {
     const double *n_data;
     const double *einv, *Bt;
     double *u_e, *tk;
+    unsigned long long *trace;              // LSS_SHARD_TRACE: %globaltimer of CTA 0 at the phase boundaries, [iteration % 1024][16]
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -952,6 +953,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SHARD_STAMP(k)                                                                                \
+    do {                                                                                           \
+        if (sa.trace && blockIdx.x == 0 && threadIdx.x == 0) sa.trace[(it & 1023ull) * 16 + (k)] = global_ns(); \
+    } while (0)
 __device__ __forceinline__ double ld_box(const double *p) { return __ldcg(p); }     // written by a peer: L2 is the coherence point
 
 // thread t < n waits until flags[t] >= want; gives up after ~4 s (another rank died) and raises S_ERR
@@ -994,6 +1004,7 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
     const unsigned long long seq_a = sa.seq + 2ull * it + 1ull, seq_x = seq_a + 1ull;
     unsigned long long *mine = sa.box[me];
     static_assert(PQ_SLOTS == VEC_BLOCK, "one p.q slot per thread");
+    SHARD_STAMP(0);
     const double slot_v = pq_slots[threadIdx.x];
     const double rz_old = scal[S_RZ0 + parity];
     const int n_own = sa.blk_hi - sa.blk_lo;
@@ -1019,6 +1030,7 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
         for (int t = 0; t < P; ++t) tot += ld_box(da + t);
         alpha = tot > 0.0 ? rz_old / tot : 0.0;
         have_alpha = true;
+        SHARD_STAMP(1);
     };
     // ---- phase B: own blocks
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
@@ -1076,8 +1088,11 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
     if (!have_alpha) get_alpha();
     v = block_sum(v, sm);
     if (threadIdx.x == 0) part[blockIdx.x] = v;
+    SHARD_STAMP(2);
     __threadfence_system();                                     // the z stores are visible system-wide before any flag below
+    SHARD_STAMP(3);
     grid.sync();
+    SHARD_STAMP(4);
     // ---- phase C1: own part of the restriction and of N_E,own z
     const int n_c = ca.n_c, chunks = ca.chunks;
     {
@@ -1106,6 +1121,7 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
         }
     }
     grid.sync();
+    SHARD_STAMP(5);
     // ---- exchange X: packet [r.z_BJ | r_c,k | t_k] to every rank (CTA t serves peer t)
     if ((int)blockIdx.x < P) {
         double *dst = reinterpret_cast<double *>(sa.box[blockIdx.x] + sa.off_db) + (size_t)(par * P + me) * sa.LB;
@@ -1121,7 +1137,9 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
         __syncthreads();
         if (threadIdx.x == 0) st_release_sys(sa.box[blockIdx.x] + sa.off_fb + par * P + me, seq_x);
     }
+    SHARD_STAMP(6);
     wait_flags(mine + sa.off_fb + par * P, P, seq_x, scal);
+    SHARD_STAMP(7);
     const double *db = reinterpret_cast<const double *>(mine + sa.off_db) + (size_t)par * P * sa.LB;
     double rz_new = 0.0;
     for (int t = 0; t < P; ++t) rz_new += ld_box(db + (size_t)t * sa.LB);
@@ -1150,7 +1168,9 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
             if (lane_id() == 0) ca.zc_part[(size_t)ch * n_c + m] = acc;
         }
     }
+    SHARD_STAMP(8);
     grid.sync();
+    SHARD_STAMP(9);
     // ---- phase D
     double rczc = 0.0;
     double zreg[(CS_MAX + VEC_BLOCK - 1) / VEC_BLOCK];
@@ -1215,6 +1235,7 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
             }
         }
     }
+    SHARD_STAMP(10);
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < PQ_SLOTS; i += VEC_BLOCK) pq_slots[i] = 0.0;
         if (threadIdx.x == 0) {
@@ -1939,6 +1960,12 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
     sa.n_e = n_e; sa.e0 = s->e0;
     sa.n_indptr = s->nm->indptr; sa.n_indices = s->nm->indices; sa.n_data = s->nm->data;
     sa.einv = s->einv; sa.Bt = s->cs ? s->cs->Bt : nullptr; sa.u_e = s->u_e; sa.tk = s->tk;
+    Scratch trace_buf;
+    if (getenv("LSS_SHARD_TRACE")) {
+        LSS_CUDA(trace_buf.alloc(sizeof(unsigned long long) * 1024 * 16, st));
+        LSS_CUDA(cudaMemsetAsync(trace_buf.p, 0, sizeof(unsigned long long) * 1024 * 16, st));
+        sa.trace = reinterpret_cast<unsigned long long *>(trace_buf.p);
+    }
     CoarseArgs ca;
     memset(&ca, 0, sizeof(ca));
     ca.n_c = n_c;
@@ -1982,10 +2009,27 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
     int issued = 0, parity = 0, slot = 0;
     bool done = false;
     bool pending[2] = {false, false};
+    int in_slot[2] = {0, 0}, base_it[2] = {0, 0};
+    auto harvest = [&](int sl) {     // as in lss_solver_solve: event pairs around every kProfEvery-th real iteration
+        const int real = (int)s->host_scal[sl * S_COUNT + S_ITERS] - base_it[sl];
+        for (int k = 0; k < in_slot[sl] && k < real && s->profile; k += kProfEvery) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            const int e = 4 * (sl * kBatch + k);
+            cudaEventElapsedTime(&a, (*s->prof_events)[e], (*s->prof_events)[e + 1]);
+            cudaEventElapsedTime(&b, (*s->prof_events)[e + 1], (*s->prof_events)[e + 2]);
+            cudaEventElapsedTime(&c, (*s->prof_events)[e + 2], (*s->prof_events)[e + 3]);
+            s->ms_a += a;
+            s->ms_at += b;
+            s->ms_step += c;
+            s->n_prof += 1;
+        }
+        in_slot[sl] = 0;
+    };
     while (!done) {
         const int todo = (max_iter - issued) < kBatch ? (max_iter - issued) : kBatch;
         for (int k = 0; k < todo; ++k) {
-            LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity));
+            const bool prof_k = s->profile && (k % kProfEvery) == 0;
+            LSS_TRY(apply_normal(s, s->p, true, s->scal + S_DONE0 + parity, prof_k ? slot * kBatch + k : -1));
             double *qv = s->buf, *minv = s->minv, *pv = s->p, *zv = s->z, *part = s->part2, *scal = s->scal, *slots = s->buf + n;
             int64_t nn = n;
             int par = parity, nb = s->bp->n_blocks;
@@ -1998,9 +2042,12 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
             ++lss::g_launches;
             s->launches += 1;
             s->q_clean = true;
+            if (prof_k) LSS_CUDA(cudaEventRecord((*s->prof_events)[4 * (slot * kBatch + k) + 3], st));   // after the step + exchange
             parity ^= 1;
         }
+        base_it[slot] = issued;
         issued += todo;
+        in_slot[slot] = todo;
         LSS_CUDA(cudaMemcpyAsync(s->host_scal + slot * S_COUNT, s->scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
         LSS_CUDA(cudaEventRecord(s->ev_batch[slot], st));
         pending[slot] = true;
@@ -2008,6 +2055,7 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
         if (pending[prev]) {
             LSS_CUDA(cudaEventSynchronize(s->ev_batch[prev]));
             pending[prev] = false;
+            harvest(prev);
             if (s->host_scal[prev * S_COUNT + S_DONE0] != 0.0 || s->host_scal[prev * S_COUNT + S_DONE1] != 0.0) done = true;
         }
         if (!done && (issued >= max_iter || todo == 0)) {
@@ -2036,9 +2084,30 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->ms_total = ms;
+    harvest(0);
+    harvest(1);
     const double bn = s->host_scal[S_BNORM], rzl = s->host_scal[S_RZ_LAST];
     if (iters_h) *iters_h = (int32_t)s->host_scal[S_ITERS];
     if (relres_h) *relres_h = bn > 0.0 ? sqrt(rzl / bn) : 0.0;
+    if (sa.trace) {            // diagnostics: mean time between the phase stamps of CTA 0 over the recorded iterations
+        std::vector<unsigned long long> h(1024 * 16);
+        cudaMemcpy(h.data(), sa.trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
+        const int n_it = (int)s->host_scal[S_ITERS] < 1024 ? (int)s->host_scal[S_ITERS] : 1024;
+        double acc[12] = {0};
+        int cnt = 0;
+        for (int i = 8; i + 1 < n_it; ++i) {
+            const unsigned long long *a = &h[(size_t)i * 16], *b = &h[(size_t)(i + 1) * 16];
+            if (!a[0] || !b[0] || !a[10]) continue;
+            for (int k = 0; k < 10; ++k) acc[k] += (double)(a[k + 1] - a[k]) * 1e-3;
+            acc[10] += (double)(b[0] - a[10]) * 1e-3;        // end of this step -> start of the next: the product and the launch gaps
+            ++cnt;
+        }
+        if (cnt) {
+            fprintf(stderr, "[lss shard trace rank %d] %d its, us:", pc->rank, cnt);
+            for (int k = 0; k < 11; ++k) fprintf(stderr, " %d:%.1f", k, acc[k] / cnt);
+            fprintf(stderr, "\n");
+        }
+    }
     if (s->host_scal[S_ERR] != 0.0) return fail(LSS_ENCCL, "solver_solve: a peer did not answer within the exchange time-out (row-sharded CG)");
     return LSS_OK;
 }

@@ -1,12 +1,16 @@
-"""Multi-GPU parity check (run under torchrun on N GPUs of one box; not collected by pytest).
+"""Multi-GPU parity check: one rank of an N-rank run (torchrun, or spawned by tests/test_gpu_multi.py).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
 
-Every rank runs the multi-GPU smooth_fit in both solve modes (replicated solve: rows all-gathered once, no collective
-inside CG; row-sharded solve, LSS_SHARDED_SOLVE=1: one all-reduce per CG iteration); rank 0 then repeats the fit on one
-GPU and requires the same edit masks after every outer iteration and the same model to 1e-9 relative L2 (summation
-order differs from the single-GPU order).
+Every rank runs the multi-GPU smooth_fit in its solve modes:
+  p2p         (default) row-sharded normal matrix, p exchanged inside the CG step kernel through the peer-to-peer
+              mailbox over NVLink, no collective per iteration;
+  replicated  (LSS_REPLICATED_SOLVE=1) rows all-gathered once, every rank runs the whole CG;
+  allreduce   (LSS_REPLICATED_SOLVE=1 LSS_SHARDED_SOLVE=1) row-sharded products summed by one NCCL all-reduce per iteration.
+Rank 0 then repeats the fit on one GPU and requires the same edit mask after every outer iteration and the same model
+to 1e-9 relative L2 (summation order differs from the single-GPU order).
 """
+import faulthandler
 import os
 import sys
 
@@ -17,33 +21,49 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lssurf_b200 as L                       # noqa: E402
 from lssurf_b200 import parallel, synthetic   # noqa: E402
 
+MODES = {'p2p': {}, 'replicated': {'LSS_REPLICATED_SOLVE': '1'},
+         'allreduce': {'LSS_REPLICATED_SOLVE': '1', 'LSS_SHARDED_SOLVE': '1'}}
+
 
 def main():
+    faulthandler.dump_traceback_later(int(os.environ.get('LSS_DIST_CHECK_TIMEOUT', '600')), exit=True)
     ctx = parallel.init_from_env()
-    cases = [('uniform_3d', synthetic.uniform_3d(n=200_000, width=3.e4, seed=4)),
-             ('tracks_bias', synthetic.icesat2_tracks(n=300_000, width=2.e4, seed=4))]
+    modes = [m for m in os.environ.get('LSS_DIST_CHECK_MODES', 'p2p,replicated,allreduce').split(',') if m]
+    scale = float(os.environ.get('LSS_DIST_CHECK_SCALE', '1'))
+    cases = [('uniform_3d', synthetic.uniform_3d(n=int(200_000 * scale), width=3.e4 * scale ** 0.5, seed=4)),
+             ('tracks_bias', synthetic.icesat2_tracks(n=int(300_000 * scale), width=2.e4 * scale ** 0.5, seed=4)),
+             # wide enough for the two-level preconditioner (>= 2000 dz nodes) on top of the bias elimination
+             ('tracks_bias_coarse', synthetic.icesat2_tracks(n=int(400_000 * scale), width=5.e4 * scale ** 0.5, seed=5))]
     ok = True
-    for name, (pts, kw), mode in [(c[0], c[1], m) for c in cases for m in ('replicated', 'sharded')]:
-        hist = []
-        if mode == 'sharded':
-            os.environ['LSS_SHARDED_SOLVE'] = '1'
-        else:
-            os.environ.pop('LSS_SHARDED_SOLVE', None)
-        S = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, dist=ctx if ctx.world > 1 else None,
-                         history=hist, **kw)
-        name = name + '/' + mode
-        if ctx.rank == 0:
-            hist1 = []
-            S1 = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, history=hist1, **kw)
+    single = {}
+    for name, (pts, kw) in cases:
+        for mode in modes:
+            for k in ('LSS_REPLICATED_SOLVE', 'LSS_SHARDED_SOLVE'):
+                os.environ.pop(k, None)
+            os.environ.update(MODES[mode])
+            hist = []
+            S = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, dist=ctx if ctx.world > 1 else None,
+                             history=hist, **kw)
+            if ctx.rank != 0:
+                continue
+            if name not in single:
+                hist1 = []
+                S1 = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, history=hist1, **kw)
+                single[name] = (S1, hist1)
+            S1, hist1 = single[name]
             rel = float(np.linalg.norm(S['m']['all'] - S1['m']['all']) / np.linalg.norm(S1['m']['all']))
             same_final = bool(np.array_equal(S['data'].three_sigma_edit, S1['data'].three_sigma_edit))
             same_count = [h['count'] for h in hist] == [h['count'] for h in hist1]
+            same_masks = len(hist) == len(hist1) and all(np.array_equal(a['mask_out'], b['mask_out']) for a, b in zip(hist, hist1)) \
+                if mode == 'p2p' else same_count          # the other modes record rank-local masks
             dz_est = float(np.max(np.abs(S['data'].z_est - S1['data'].z_est)))
             cnt = float(np.nanmax(np.abs(S['m']['z0'].count - S1['m']['z0'].count)))
-            print(f'[dist_check] {name}: world={ctx.world} rel-L2(m0)={rel:.2e} masks identical={same_final} '
-                  f'per-iteration counts equal={same_count} max|dz_est|={dz_est:.2e} count-map diff={cnt} '
+            mis = float(np.nanmax(np.abs(S['m']['dz'].misfit_rms - S1['m']['dz'].misfit_rms)))
+            print(f'[dist_check] {name}/{mode}: world={ctx.world} rel-L2(m0)={rel:.2e} final mask identical={same_final} '
+                  f'masks identical per iteration={same_masks} counts equal={same_count} max|dz_est|={dz_est:.2e} '
+                  f'count-map diff={cnt} misfit-map diff={mis:.1e} coarse={hist[0]["pcg"].get("coarse")} '
                   f'its={[h["pcg"]["iterations"] for h in hist]} vs {[h["pcg"]["iterations"] for h in hist1]}', flush=True)
-            ok = ok and rel < 1e-9 and same_final and same_count and cnt < 1e-9
+            ok = ok and rel < 1e-9 and same_final and same_count and same_masks and cnt < 1e-9 and mis < 1e-8
     import torch.distributed as td
     if ctx.world > 1:
         td.barrier()
