@@ -154,7 +154,8 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
 
 int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
                        int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches,
-                       double *dot_slots = nullptr);   // y pre-zeroed; dot_slots[256] += partial sums of x . (A x)
+                       double *dot_slots = nullptr,    // y pre-zeroed; dot_slots[256] += partial sums of x . (A x)
+                       const int32_t *row_ids = nullptr);   // compacted row list: row r of the CSR is row row_ids[r] of y and x
 
 // Products specialised for the explicit normal matrix (long overlapping rows); variant 0 is spmv_launch_atomic.
 int normal_product_variant();
@@ -220,6 +221,10 @@ struct NormalMatrix {
     int64_t own_e0, own_e1;       // eliminated block whose rows keep their entries at own columns
     SpmvPlan plan_part;        // plan of the leading rows [0, part_rows) (an eliminated trailing block is left out of the product)
     int64_t part_rows, part_nnz;
+    // row-sharded N: most rows are empty (columns of other ranks); the product runs over the compacted list of non-empty rows
+    int32_t *cp_indptr, *cp_rows;
+    int64_t cp_n, cp_nnz, cp_for_rows;
+    SpmvPlan plan_cp;
     cudaStream_t stream;
 };
 extern int g_opt_step_kernel;       // -1: unset (environment LSS_STEP_KERNEL decides, default 2), 0: warp per block, 1: thread per block row, 2: CTA tile

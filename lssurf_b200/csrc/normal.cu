@@ -15,6 +15,8 @@
 //       one grid cell) are summed in registers, then 32 lanes find the slots of (c_i, c_j) by binary search in row
 //       c_i of the pattern and issue one RED.ADD.F64 per pair and run.
 //   product   the nnz-tiled CSR kernel of spmv.cu (deterministic, no atomics).
+#include <vector>
+
 #include "common.cuh"
 
 namespace lss {
@@ -313,6 +315,9 @@ int normal_destroy(NormalMatrix *m) {
     spmv_tma_plan_destroy(&m->tma_plan);
     spmv_plan_destroy(&m->plan);
     spmv_plan_destroy(&m->plan_part);
+    if (m->cp_indptr) cudaFreeAsync(m->cp_indptr, st);
+    if (m->cp_rows) cudaFreeAsync(m->cp_rows, st);
+    spmv_plan_destroy(&m->plan_cp);
     delete m;
     return LSS_OK;
 }
@@ -327,6 +332,7 @@ int normal_create(NormalMatrix **out, int64_t n_rows, int64_t n_pad, int K, cons
     m->ell_col = ell_col; m->ell_val = ell_val; m->fixed = fixed; m->stream = st;
     m->part_rows = -1;
     m->c8_part_rows = -1;
+    m->cp_for_rows = -1;
     m->c8_dirty = true;
     m->owned = owned; m->own_e0 = own_e0; m->own_e1 = own_e1;
     const OwnFilter flt{owned, own_e0, own_e1};
@@ -435,6 +441,35 @@ int normal_apply_fast(NormalMatrix *m, int64_t n_rows, const double *x, double *
     if (m->plan.n_tiles > 0 && m->plan.tile != 1024)
         return fail(LSS_EINVAL, "normal matrix product: the single-launch kernel needs the default spmv_variant (1024-entry tiles)");
     if (!y_is_zero) LSS_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * m->n_cols, m->stream));
+    if (m->owned) {
+        // row-sharded N: a tile of the nnz-tiled kernel would walk the long runs of empty rows between the owned column ranges
+        // one by one, so the product runs over the compacted list of non-empty rows (built once: the pattern is fixed)
+        const int64_t rows = n_rows < m->n_cols ? n_rows : m->n_cols;
+        if (m->cp_for_rows != rows) {
+            std::vector<int32_t> h(rows + 1), hp, hr;
+            LSS_CUDA(cudaMemcpyAsync(h.data(), m->indptr, sizeof(int32_t) * (rows + 1), cudaMemcpyDeviceToHost, m->stream));
+            LSS_CUDA(cudaStreamSynchronize(m->stream));
+            hp.reserve(rows / 2 + 2);
+            hr.reserve(rows / 2 + 2);
+            for (int64_t r = 0; r < rows; ++r)
+                if (h[r + 1] > h[r]) { hp.push_back(h[r]); hr.push_back((int32_t)r); }
+            hp.push_back(h[rows]);
+            if (m->cp_indptr) cudaFreeAsync(m->cp_indptr, m->stream);
+            if (m->cp_rows) cudaFreeAsync(m->cp_rows, m->stream);
+            spmv_plan_destroy(&m->plan_cp);
+            m->cp_n = (int64_t)hr.size();
+            m->cp_nnz = h[rows];
+            LSS_CUDA(cudaMallocAsync((void **)&m->cp_indptr, sizeof(int32_t) * hp.size(), m->stream));
+            LSS_CUDA(cudaMallocAsync((void **)&m->cp_rows, sizeof(int32_t) * (hr.size() + 1), m->stream));
+            LSS_CUDA(cudaMemcpyAsync(m->cp_indptr, hp.data(), sizeof(int32_t) * hp.size(), cudaMemcpyHostToDevice, m->stream));
+            if (!hr.empty()) LSS_CUDA(cudaMemcpyAsync(m->cp_rows, hr.data(), sizeof(int32_t) * hr.size(), cudaMemcpyHostToDevice, m->stream));
+            LSS_CUDA(cudaStreamSynchronize(m->stream));           // the host vectors go out of scope
+            if (m->cp_n > 0) LSS_TRY(spmv_plan_create(&m->plan_cp, m->cp_n, m->cp_indptr, m->cp_nnz, m->stream));
+            m->cp_for_rows = rows;
+        }
+        return spmv_launch_atomic(m->cp_n, m->cp_indptr, m->indices, m->data, x, y, m->cp_nnz, &m->plan_cp, stop, m->stream, launches, dot_slots,
+                                  m->cp_rows);
+    }
     int variant = normal_product_variant();
     if (variant >= 10 && variant <= 11 && m->nnz > 0) {
         const int64_t rows = n_rows < m->n_cols ? n_rows : m->n_cols;

@@ -929,6 +929,8 @@ static const void *step_ml_kernel_for(int bs) {
 // All ranks form every scalar from the same numbers in the same order: alpha, beta and the stop flag are bit-identical
 // everywhere, so no rank can leave the loop alone.  A wait that exceeds ~4 s sets S_ERR and every later wait is skipped.
 constexpr int S_ERR = 9;
+constexpr int SHARD_NS = 8;                // slices the exchange packet is sent in (one CTA and one flag per peer and slice)
+constexpr int SHARD_ECH_MAX = 32;           // pieces per row of N_E in phase C1
 struct ShardArgs {
     int rank, n_ranks, blk_lo, blk_hi;
     unsigned long long seq;                 // sequence base of this solve; iteration k uses seq + 2k + 1 (A) and seq + 2k + 2 (X)
@@ -936,12 +938,20 @@ struct ShardArgs {
     long long off_fa, off_da, off_fb, off_db, off_z;   // word offsets of flagsA / dataA / flagsB / dataB / packed z
     int LB;                                 // words per packet: 1 + n_c + n_e (padded)
     long long ZP;                           // words of one packed z buffer: n_blocks * BS
-    int n_e;
+    int n_e, ech;                           // eliminated columns; pieces every row of N_E is cut into (phase C1)
     long long e0;
     const int *n_indptr, *n_indices;        // rows of E of the local N: entries at own columns
     const double *n_data;
     const double *einv, *Bt;
     double *u_e, *tk;
+    // phase C1 as flat entry lists (row key per entry): restriction entries [0, n_fr), rows of N_E [kE0, kE0 + n_fe)
+    const int *fr_key;                      // coarse row of every entry of P^T (own columns)
+    const int *fe_key;                      // n_c + bias row of every entry of the rows of N_E
+    int n_fr, n_fe;
+    long long kE0;
+    double *tgt;                            // [n_c + n_e] sums of phase C1 (cleared in phase D for the next iteration)
+    const int *dlist;                       // phase D: packed-z slots of the columns this rank needs p at (null: all)
+    int n_dlist;
     unsigned long long *trace;              // LSS_SHARD_TRACE: %globaltimer of CTA 0 at the phase boundaries, [iteration % 1024][16]
 };
 
@@ -1089,56 +1099,89 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
     v = block_sum(v, sm);
     if (threadIdx.x == 0) part[blockIdx.x] = v;
     SHARD_STAMP(2);
-    __threadfence_system();                                     // the z stores are visible system-wide before any flag below
     SHARD_STAMP(3);
     grid.sync();
     SHARD_STAMP(4);
-    // ---- phase C1: own part of the restriction and of N_E,own z
+    // ---- phase C1: own part of the restriction r_c,k = P_k^T r and of t_k = N_E,own z.  Both are sums over flat entry lists
+    // sorted by row: every warp takes 128 consecutive entries at a time (4 independent loads per lane, then 4 gathers), folds
+    // equal rows with a segmented warp scan and adds one value per (warp, row) to tgt with a RED.
     const int n_c = ca.n_c, chunks = ca.chunks;
+    const unsigned long long tc0 = sa.trace ? global_ns() : 0ull;
     {
-        const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5);
-        const int n_work = n_c * chunks + sa.n_e;
-        for (int w = warp; w < n_work; w += n_warps) {
-            double acc = 0.0;
-            if (w < n_c * chunks) {
-                const int m = w % n_c, ch = w / n_c;
-                const int kb = ca.pt_ptr[m], len = ca.pt_ptr[m + 1] - kb;
-                const int per = (len + chunks - 1) / chunks;
-                const int k0 = kb + ch * per, k1 = min(kb + len, k0 + per);
-                for (int k = k0 + (int)lane_id(); k < k1; k += 32) acc += (double)__ldg(ca.pt_w + k) * r_out[__ldg(ca.pt_col + k)];
-                acc = warp_sum(acc);
-                if (lane_id() == 0) ca.rc_part[(size_t)ch * n_c + m] = acc;
-            } else {
-                const int e = w - n_c * chunks;
-                const long long row = sa.e0 + e;
-                for (int k = sa.n_indptr[row] + (int)lane_id(); k < sa.n_indptr[row + 1]; k += 32) {
-                    const int j = __ldg(sa.n_indices + k);
-                    if (j < sa.e0 || j >= sa.e0 + sa.n_e) acc += __ldg(sa.n_data + k) * z[j];
-                }
-                acc = warp_sum(acc);
-                if (lane_id() == 0) sa.tk[e] = acc;
+        const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5), lane = (int)lane_id();
+        auto seg_add = [&](int key, double val) {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v2 = __shfl_up_sync(0xffffffffu, val, o);
+                const int k2 = __shfl_up_sync(0xffffffffu, key, o);
+                if (lane >= o && k2 == key) val += v2;
             }
+            const int kn = __shfl_down_sync(0xffffffffu, key, 1);
+            if (key >= 0 && (lane == 31 || kn != key)) atomicAdd(sa.tgt + key, val);
+        };
+        for (int base = warp * 128; base < sa.n_fr; base += n_warps * 128) {
+            int key[4], col[4];
+            float wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = base + 32 * j + lane;
+                const bool in = k < sa.n_fr;
+                key[j] = in ? __ldg(sa.fr_key + k) : -1;
+                col[j] = in ? __ldg(ca.pt_col + k) : 0;
+                wv[j] = in ? __ldg(ca.pt_w + k) : 0.f;
+            }
+            double val[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) val[j] = key[j] >= 0 ? (double)wv[j] * r_out[col[j]] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) seg_add(key[j], val[j]);
         }
+        const long long e_lo = sa.e0, e_hi = sa.e0 + sa.n_e;
+        for (int base = warp * 128; base < sa.n_fe; base += n_warps * 128) {
+            int key[4], col[4];
+            double av[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = base + 32 * j + lane;
+                const bool in = k < sa.n_fe;
+                key[j] = in ? __ldg(sa.fe_key + k) : -1;
+                col[j] = in ? __ldg(sa.n_indices + sa.kE0 + k) : 0;
+                av[j] = in ? __ldg(sa.n_data + sa.kE0 + k) : 0.0;
+            }
+            double val[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) val[j] = (key[j] >= 0 && (col[j] < e_lo || col[j] >= e_hi)) ? av[j] * z[col[j]] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) seg_add(key[j], val[j]);
+        }
+    }
+    const unsigned long long tc1 = sa.trace ? global_ns() : 0ull;
+    __threadfence_system();          // this thread's z stores of phase B (long acknowledged by now) are visible system-wide before any flag below
+    if (sa.trace && threadIdx.x == 0) {         // slowest CTA of the phase: work, then fence
+        atomicMax(sa.trace + (it & 1023ull) * 16 + 11, tc1 - tc0);
+        atomicMax(sa.trace + (it & 1023ull) * 16 + 12, global_ns() - tc1);
     }
     grid.sync();
     SHARD_STAMP(5);
-    // ---- exchange X: packet [r.z_BJ | r_c,k | t_k] to every rank (CTA t serves peer t)
-    if ((int)blockIdx.x < P) {
-        double *dst = reinterpret_cast<double *>(sa.box[blockIdx.x] + sa.off_db) + (size_t)(par * P + me) * sa.LB;
-        const double rzk = sum_partials(part, (int)gridDim.x, sm);
-        if (threadIdx.x == 0) dst[0] = rzk;
-        for (int m = threadIdx.x; m < n_c; m += VEC_BLOCK) {
-            double a = 0.0;
-            for (int ch = 0; ch < chunks; ++ch) a += ca.rc_part[(size_t)ch * n_c + m];
-            dst[1 + m] = a;
+    // ---- exchange X: packet [r.z_BJ | r_c,k | t_k] to every rank, in SHARD_NS slices (CTA b serves peer b % P, slice b / P)
+    if ((int)blockIdx.x < P * SHARD_NS) {
+        const int peer = (int)blockIdx.x % P, sl = (int)blockIdx.x / P;
+        double *dst = reinterpret_cast<double *>(sa.box[peer] + sa.off_db) + (size_t)(par * P + me) * sa.LB;
+        const int used = 1 + n_c + sa.n_e, per_s = (used + SHARD_NS - 1) / SHARD_NS;
+        const int i0 = sl * per_s, i1 = min(used, i0 + per_s);
+        if (sl == 0) {
+            const double rzk = sum_partials(part, (int)gridDim.x, sm);
+            if (threadIdx.x == 0) dst[0] = rzk;
         }
-        for (int e = threadIdx.x; e < sa.n_e; e += VEC_BLOCK) dst[1 + n_c + e] = sa.tk[e];
+        for (int i = max(i0, 1) + (int)threadIdx.x; i < i1; i += VEC_BLOCK) {
+            dst[i] = __ldcg(sa.tgt + (i - 1));        // written with REDs (L2) by all CTAs before the grid barrier
+        }
         __threadfence_system();
         __syncthreads();
-        if (threadIdx.x == 0) st_release_sys(sa.box[blockIdx.x] + sa.off_fb + par * P + me, seq_x);
+        if (threadIdx.x == 0) st_release_sys(sa.box[peer] + sa.off_fb + (par * P + me) * SHARD_NS + sl, seq_x);
     }
     SHARD_STAMP(6);
-    wait_flags(mine + sa.off_fb + par * P, P, seq_x, scal);
+    wait_flags(mine + sa.off_fb + par * P * SHARD_NS, P * SHARD_NS, seq_x, scal);
     SHARD_STAMP(7);
     const double *db = reinterpret_cast<const double *>(mine + sa.off_db) + (size_t)par * P * sa.LB;
     double rz_new = 0.0;
@@ -1196,11 +1239,12 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
     }
     __syncthreads();
     const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
-    // p over ALL blocks from the packed z of their owners
+    // p from the packed z of the owners, at the columns this rank's rows of N reference (the rest of p is never read here)
     {
         const double *zp = reinterpret_cast<const double *>(mine + sa.off_z) + (size_t)par * sa.ZP;
-        const int64_t total = (int64_t)n_blocks * BS;
-        for (int64_t k = tid; k < total; k += nth) {
+        const int64_t total = sa.dlist ? (int64_t)sa.n_dlist : (int64_t)n_blocks * BS;
+        for (int64_t i = tid; i < total; i += nth) {
+            const int64_t k = sa.dlist ? (int64_t)__ldg(sa.dlist + i) : i;
             const int c = __ldg(bcols + k);
             if (c < 0) continue;
             double zi = ld_box(zp + k);
@@ -1216,6 +1260,7 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
         }
     }
     for (int64_t i = tid; i < n; i += nth) q[i] = 0.0;
+    for (int64_t i = tid; i < n_c + sa.n_e; i += nth) sa.tgt[i] = 0.0;      // for phase C1 of the next iteration
     // the eliminated block: u = T^T p by linearity, p_E = -N_EE^-1 u (one warp per bias column)
     {
         const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5);
@@ -1256,6 +1301,14 @@ static const void *step_shard_kernel_for(int bs) {
         case 36: return (const void *)cg_step_shard_kernel<36>;
         default: return nullptr;
     }
+}
+
+// out[k - base] = key0 + r for every entry k of row r of a CSR pointer array (one warp per row)
+__global__ void __launch_bounds__(256)
+expand_rows_kernel(int n_rows, const int *__restrict__ ptr, int base, int key0, int *__restrict__ out) {
+    const int r = (int)(((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5);
+    if (r >= n_rows) return;
+    for (int k = ptr[r] + (int)lane_id(); k < ptr[r + 1]; k += 32) out[k - base] = key0 + r;
 }
 
 // v[i] = 0 unless column i is this rank's own (or, with keep_e, inside the eliminated block)
@@ -1408,6 +1461,12 @@ struct lss_solver {
     int blk_lo, blk_hi;      // its preconditioner blocks
     int64_t own_row_lo, own_row_hi, con_row_lo;   // own data rows and first constraint row inside the ELL block
     double *u_e, *tk, *esum; // T^T p carried through the iterations, this rank's N_E,own z, [2 n_e] set-up sums
+    int32_t *fr_key = nullptr, *fe_key = nullptr;   // row keys of the flat entry lists of phase C1 (row-sharded step)
+    int n_fr = 0, n_fe = 0;
+    int64_t kE0 = 0;
+    double *tgt = nullptr;
+    int32_t *dlist = nullptr; // slots of the packed z buffer whose columns this rank's rows of N reference (own + halo): the only entries of p it keeps current
+    int n_dlist = 0;
     int step_sh_grid;
 };
 
@@ -1442,6 +1501,10 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     if (s->owned) cudaFreeAsync(s->owned, s->stream);
     if (s->u_e) cudaFreeAsync(s->u_e, s->stream);
     if (s->tk) cudaFreeAsync(s->tk, s->stream);
+    if (s->dlist) cudaFreeAsync(s->dlist, s->stream);
+    if (s->fr_key) cudaFreeAsync(s->fr_key, s->stream);
+    if (s->fe_key) cudaFreeAsync(s->fe_key, s->stream);
+    if (s->tgt) cudaFreeAsync(s->tgt, s->stream);
     if (s->esum) cudaFreeAsync(s->esum, s->stream);
     if (s->einv) cudaFreeAsync(s->einv, s->stream);
     if (s->eraw) cudaFreeAsync(s->eraw, s->stream);
@@ -1626,7 +1689,7 @@ extern "C" int lss_solver_set_structure(lss_solver_t *s, int32_t n_blocks, const
         if (multi || s->shard) LSS_TRY(dev_alloc(&s->eraw, elim_end - elim_begin, st));
         if (s->shard) {
             LSS_TRY(dev_alloc(&s->u_e, elim_end - elim_begin, st));
-            LSS_TRY(dev_alloc(&s->tk, elim_end - elim_begin, st));
+            LSS_TRY(dev_alloc(&s->tk, (elim_end - elim_begin) * SHARD_ECH_MAX, st));
             LSS_TRY(dev_alloc(&s->esum, 2 * (elim_end - elim_begin), st));
         }
     }
@@ -1817,6 +1880,10 @@ extern "C" int lss_solver_set_coarse(lss_solver_t *s, int32_t n_coarse, const in
     if (!s) return fail(LSS_EINVAL, "solver_set_coarse: null solver");
     if (!s->nm || !s->bp || s->step_rows != 2) return LSS_OK;     // needs the explicit-normal form with the tile step kernel
     if (s->cs) { lss::coarse_destroy(s->cs); s->cs = nullptr; }
+    // the flat lists of the row-sharded step follow the coarse space: rebuilt at the next solve
+    if (s->fr_key) { cudaFreeAsync(s->fr_key, s->stream); s->fr_key = nullptr; }
+    if (s->fe_key) { cudaFreeAsync(s->fe_key, s->stream); s->fe_key = nullptr; }
+    if (s->tgt) { cudaFreeAsync(s->tgt, s->stream); s->tgt = nullptr; }
     LSS_TRY(coarse_create(&s->cs, s->n_cols, n_coarse, cp_idx, cp_w, pt_ptr, pt_col, pt_w, nnz_p, (int)(s->e1 - s->e0), s->stream));
     int per_sm = 0;
     LSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_ml_kernel_for(s->bp->bs), VEC_BLOCK, 0));
@@ -1950,7 +2017,7 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
     sa.rank = pc->rank; sa.n_ranks = P; sa.blk_lo = s->blk_lo; sa.blk_hi = s->blk_hi;
     sa.LB = (1 + n_c + n_e + 3) & ~3;
     sa.ZP = (long long)s->bp->n_blocks * bs;
-    sa.off_fa = 0; sa.off_da = 2 * P; sa.off_fb = 4 * P; sa.off_db = (6 * P + 7) & ~7;
+    sa.off_fa = 0; sa.off_da = 2 * P; sa.off_fb = 4 * P; sa.off_db = (4 * P + 2 * P * SHARD_NS + 7) & ~7;
     sa.off_z = (sa.off_db + 2ll * P * sa.LB + 7) & ~7ll;
     const size_t need = sizeof(double) * (size_t)(sa.off_z + 2 * sa.ZP);
     if (need > pc->box_bytes) return fail(LSS_EINVAL, "solver_solve: the mailbox holds %zu bytes, the exchange needs %zu", pc->box_bytes, need);
@@ -1958,6 +2025,13 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
     sa.seq = pc->seq;
     pc->seq += 2ull * (unsigned long long)(max_iter > 0 ? max_iter : 0) + 8ull;      // the same on every rank: all call solve with the same arguments
     sa.n_e = n_e; sa.e0 = s->e0;
+    sa.ech = 1;
+    if (n_e > 0) {
+        const int n_warps = s->step_sh_grid * (VEC_BLOCK / 32);
+        sa.ech = (2 * n_warps + n_e - 1) / n_e;
+        if (sa.ech < 1) sa.ech = 1;
+        if (sa.ech > SHARD_ECH_MAX) sa.ech = SHARD_ECH_MAX;
+    }
     sa.n_indptr = s->nm->indptr; sa.n_indices = s->nm->indices; sa.n_data = s->nm->data;
     sa.einv = s->einv; sa.Bt = s->cs ? s->cs->Bt : nullptr; sa.u_e = s->u_e; sa.tk = s->tk;
     Scratch trace_buf;
@@ -1966,12 +2040,54 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
         LSS_CUDA(cudaMemsetAsync(trace_buf.p, 0, sizeof(unsigned long long) * 1024 * 16, st));
         sa.trace = reinterpret_cast<unsigned long long *>(trace_buf.p);
     }
+    if (!s->dlist && P > 1 && !getenv("LSS_SHARD_FULL_P")) {
+        // columns referenced by the local rows of N -> slots of the packed z buffer (once per solver: the pattern is fixed)
+        const int64_t slots_all = (int64_t)s->bp->n_blocks * bs;
+        std::vector<int32_t> h_idx(s->nm->nnz > 0 ? s->nm->nnz : 1), h_cols(slots_all);
+        LSS_CUDA(cudaMemcpyAsync(h_idx.data(), s->nm->indices, sizeof(int32_t) * s->nm->nnz, cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaMemcpyAsync(h_cols.data(), s->bp->cols_pad, sizeof(int32_t) * slots_all, cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+        std::vector<unsigned char> need(n, 0);
+        for (int64_t k = 0; k < s->nm->nnz; ++k) need[h_idx[k]] = 1;
+        std::vector<int32_t> dl;
+        dl.reserve(slots_all / P * 2);
+        for (int64_t k = 0; k < slots_all; ++k)
+            if (h_cols[k] >= 0 && need[h_cols[k]]) dl.push_back((int32_t)k);
+        s->n_dlist = (int)dl.size();
+        LSS_CUDA(cudaMallocAsync((void **)&s->dlist, sizeof(int32_t) * (dl.size() + 1), st));
+        if (!dl.empty()) LSS_CUDA(cudaMemcpyAsync(s->dlist, dl.data(), sizeof(int32_t) * dl.size(), cudaMemcpyHostToDevice, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+    }
+    sa.dlist = s->dlist; sa.n_dlist = s->n_dlist;
+    if (!s->tgt) {
+        // flat entry lists of phase C1: a row key per entry of P^T (own columns) and of the rows of N_E (once per solver)
+        LSS_CUDA(cudaMallocAsync((void **)&s->tgt, sizeof(double) * (size_t)(n_c + n_e + 1), st));
+        if (n_c > 0) {
+            s->n_fr = (int)s->cs->nnz_p;
+            LSS_CUDA(cudaMallocAsync((void **)&s->fr_key, sizeof(int32_t) * (size_t)(s->n_fr + 1), st));
+            expand_rows_kernel<<<ceil_div((int64_t)n_c * 32, 256), 256, 0, st>>>(n_c, s->cs->pt_ptr, 0, 0, s->fr_key);
+            LSS_LAUNCH_CHECK();
+        }
+        if (n_e > 0) {
+            int32_t be[2] = {0, 0};
+            LSS_CUDA(cudaMemcpyAsync(&be[0], s->nm->indptr + s->e0, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            LSS_CUDA(cudaMemcpyAsync(&be[1], s->nm->indptr + s->e1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            LSS_CUDA(cudaStreamSynchronize(st));
+            s->kE0 = be[0];
+            s->n_fe = be[1] - be[0];
+            LSS_CUDA(cudaMallocAsync((void **)&s->fe_key, sizeof(int32_t) * (size_t)(s->n_fe + 1), st));
+            expand_rows_kernel<<<ceil_div((int64_t)n_e * 32, 256), 256, 0, st>>>(n_e, s->nm->indptr + s->e0, be[0], n_c, s->fe_key);
+            LSS_LAUNCH_CHECK();
+        }
+    }
+    LSS_CUDA(cudaMemsetAsync(s->tgt, 0, sizeof(double) * (size_t)(n_c + n_e + 1), st));
+    sa.fr_key = s->fr_key; sa.fe_key = s->fe_key; sa.n_fr = n_c > 0 ? s->n_fr : 0; sa.n_fe = n_e > 0 ? s->n_fe : 0; sa.kE0 = s->kE0; sa.tgt = s->tgt;
     CoarseArgs ca;
     memset(&ca, 0, sizeof(ca));
     ca.n_c = n_c;
     if (n_c > 0) {
         lss::CoarseSpace *c = s->cs;
-        ca.chunks = (s->step_sh_grid * (VEC_BLOCK / 32)) / (n_c + n_e);
+        ca.chunks = (s->step_sh_grid * (VEC_BLOCK / 32)) / n_c;
         if (ca.chunks < 1) ca.chunks = 1;
         if (ca.chunks > CS_CHUNKS_MAX) ca.chunks = CS_CHUNKS_MAX;
         ca.pt_ptr = c->pt_ptr; ca.pt_col = c->pt_col; ca.pt_w = c->pt_w; ca.inv = c->inv;
@@ -2093,18 +2209,20 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
         std::vector<unsigned long long> h(1024 * 16);
         cudaMemcpy(h.data(), sa.trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
         const int n_it = (int)s->host_scal[S_ITERS] < 1024 ? (int)s->host_scal[S_ITERS] : 1024;
-        double acc[12] = {0};
+        double acc[13] = {0};
         int cnt = 0;
         for (int i = 8; i + 1 < n_it; ++i) {
             const unsigned long long *a = &h[(size_t)i * 16], *b = &h[(size_t)(i + 1) * 16];
             if (!a[0] || !b[0] || !a[10]) continue;
             for (int k = 0; k < 10; ++k) acc[k] += (double)(a[k + 1] - a[k]) * 1e-3;
+            acc[11] += (double)a[11] * 1e-3;
+            acc[12] += (double)a[12] * 1e-3;
             acc[10] += (double)(b[0] - a[10]) * 1e-3;        // end of this step -> start of the next: the product and the launch gaps
             ++cnt;
         }
         if (cnt) {
             fprintf(stderr, "[lss shard trace rank %d] %d its, us:", pc->rank, cnt);
-            for (int k = 0; k < 11; ++k) fprintf(stderr, " %d:%.1f", k, acc[k] / cnt);
+            for (int k = 0; k < 13; ++k) fprintf(stderr, " %d:%.1f", k, acc[k] / cnt);
             fprintf(stderr, "\n");
         }
     }
@@ -2373,7 +2491,8 @@ extern "C" int lss_solver_info(lss_solver_t *s, int64_t *info_h) {
     info_h[7] = 0;
     if (s->nm) {
         const bool part = s->e1 > s->e0 && s->e1 == s->n_cols;
-        if (part && lss::normal_product_variant() >= 10 && s->nm->tma_plan.tile_row && s->nm->tma_plan.n_rows == s->e0) info_h[7] = s->nm->tma_nnz;
+        if (s->nm->owned && s->nm->cp_for_rows >= 0) info_h[7] = s->nm->cp_nnz;
+        else if (part && lss::normal_product_variant() >= 10 && s->nm->tma_plan.tile_row && s->nm->tma_plan.n_rows == s->e0) info_h[7] = s->nm->tma_nnz;
         else if (part && s->nm->c8_part_rows == s->e0 && lss::normal_product_variant() >= 7) info_h[7] = s->nm->c8_part_nnz;
         else if (part && s->nm->part_rows == s->e0) info_h[7] = s->nm->part_nnz;
         else info_h[7] = s->nm->nnz;

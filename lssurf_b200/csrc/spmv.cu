@@ -75,7 +75,9 @@ template <int BLOCK, bool ATOMIC = false>
 __device__ __forceinline__ void reduce_rows(const double *__restrict__ prod, int tile, int64_t k0, int64_t k1, int64_t r_lo, int64_t r_hi,
                                             const int *__restrict__ indptr, double *__restrict__ y, int mode,
                                             const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row,
-                                            const double *__restrict__ xdot = nullptr, double *__restrict__ dot_slots = nullptr) {
+                                            const double *__restrict__ xdot = nullptr, double *__restrict__ dot_slots = nullptr,
+                                            const int *__restrict__ row_ids = nullptr) {
+    // row_ids (ATOMIC only): the CSR holds a compacted list of rows, row r of it is row row_ids[r] of y / x
     double dot = 0.0;      // ATOMIC only: this thread's share of x . (A x), summed per warp into dot_slots
     // carry-in: the row that started in an earlier tile and still has entries here
     const bool has_carry = (int64_t)indptr[r_lo] < k0;                // r_lo itself started in an earlier tile
@@ -103,14 +105,15 @@ __device__ __forceinline__ void reduce_rows(const double *__restrict__ prod, int
         }
         const bool open = e > k1;   // continues in the next tile
         if (open) e = k1;
-        const double xr = (ATOMIC && xdot && valid && gl == 0) ? __ldg(xdot + rr) : 0.0;   // in flight during the sum
+        const int64_t ro = (ATOMIC && row_ids && valid && gl == 0) ? (int64_t)__ldg(row_ids + rr) : rr;
+        const double xr = (ATOMIC && xdot && valid && gl == 0) ? __ldg(xdot + ro) : 0.0;   // in flight during the sum
         double acc = 0.0;
         for (int64_t k = b - k0 + gl; k < e - k0; k += g) acc += prod[k];
         for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (valid && gl == 0) {
             if (ATOMIC) {
-                if (v == 0 || open) atomicAdd(y + rr, acc);
-                else y[rr] = acc;
+                if (v == 0 || open) atomicAdd(y + ro, acc);
+                else y[ro] = acc;
                 dot += acc * xr;
             } else if (v == 0) carry_val[tile] = acc;
             else y[r] = open ? acc : epilogue(acc, mode, s, r);
@@ -164,7 +167,8 @@ __global__ void __launch_bounds__(BLOCK)
 spmv_persistent_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__restrict__ indptr, const int *__restrict__ indices,
                        const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y, int mode,
                        const double *__restrict__ s, double *__restrict__ carry_val, int *__restrict__ carry_row,
-                       const int *__restrict__ tile_bounds, const double *__restrict__ stop, double *__restrict__ dot_slots = nullptr) {
+                       const int *__restrict__ tile_bounds, const double *__restrict__ stop, double *__restrict__ dot_slots = nullptr,
+                       const int *__restrict__ row_ids = nullptr) {
     constexpr int TILE = BLOCK * IPT;
     __shared__ double prod_s[DBUF ? 2 : 1][TILE];
     if (stop && *stop != 0.0) return;
@@ -198,7 +202,7 @@ spmv_persistent_kernel(int64_t n_rows, int64_t nnz, int n_tiles, const int *__re
         const int nt = t + gridDim.x;
         if (nt < n_tiles) fetch(nt);            // in flight during the barrier and the row reduction below
         __syncthreads();
-        reduce_rows<BLOCK, ATOMIC>(prod, t, k0, k1, r_lo, r_hi, indptr, y, mode, s, carry_val, carry_row, dot_slots ? x : nullptr, dot_slots);
+        reduce_rows<BLOCK, ATOMIC>(prod, t, k0, k1, r_lo, r_hi, indptr, y, mode, s, carry_val, carry_row, dot_slots ? x : nullptr, dot_slots, row_ids);
         if (DBUF) buf ^= 1; else __syncthreads();
     }
 }
@@ -333,7 +337,8 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
 // the persistent kernel with atomic carries.  Used for the explicit normal matrix inside CG, where the vector step
 // that consumes q clears it for the next product.
 int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
-                       int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots) {
+                       int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots,
+                       const int32_t *row_ids) {
     if (n_rows <= 0 || nnz == 0) return LSS_OK;
     constexpr int BLOCK = 128, IPT = 8;
     if (!plan || !plan->bounds || plan->tile != BLOCK * IPT) return fail(LSS_EINVAL, "spmv_launch_atomic: needs a plan with %d-entry tiles", BLOCK * IPT);
@@ -345,7 +350,7 @@ int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *ind
     }
     const int grid = n_tiles < kSMs * per_sm ? n_tiles : kSMs * per_sm;
     spmv_persistent_kernel<BLOCK, IPT, false, true><<<grid, BLOCK, 0, stream>>>(n_rows, nnz, n_tiles, indptr, indices, data, x, y, LSS_SPMV_PLAIN,
-                                                                                nullptr, nullptr, nullptr, plan->bounds, stop, dot_slots);
+                                                                                nullptr, nullptr, nullptr, plan->bounds, stop, dot_slots, row_ids);
     LSS_LAUNCH_CHECK();
     if (launches) *launches += 1;
     return LSS_OK;
