@@ -935,7 +935,7 @@ struct ShardArgs {
     int rank, n_ranks, blk_lo, blk_hi;
     unsigned long long seq;                 // sequence base of this solve; iteration k uses seq + 2k + 1 (A) and seq + 2k + 2 (X)
     unsigned long long *box[LSS_MAX_RANKS]; // the mailboxes (box[rank] is local)
-    long long off_fa, off_da, off_fb, off_db, off_z;   // word offsets of flagsA / dataA / flagsB / dataB / packed z
+    long long off_lla, off_zf, off_llx, off_z;          // word offsets: p.q cells / z-complete flags / packet cells / packed z
     int LB;                                 // words per packet: 1 + n_c + n_e (padded)
     long long ZP;                           // words of one packed z buffer: n_blocks * BS
     int n_e, ech;                           // eliminated columns; pieces every row of N_E is cut into (phase C1)
@@ -950,6 +950,7 @@ struct ShardArgs {
     int n_fr, n_fe;
     long long kE0;
     double *tgt;                            // [n_c + n_e] sums of phase C1 (cleared in phase D for the next iteration)
+    const unsigned char *blk_peers;         // per own block: bit t set when rank t references one of its columns (null: all ranks)
     const int *dlist;                       // phase D: packed-z slots of the columns this rank needs p at (null: all)
     int n_dlist;
     unsigned long long *trace;              // LSS_SHARD_TRACE: %globaltimer of CTA 0 at the phase boundaries, [iteration % 1024][16]
@@ -973,6 +974,63 @@ __device__ __forceinline__ unsigned long long global_ns() {
         if (sa.trace && blockIdx.x == 0 && threadIdx.x == 0) sa.trace[(it & 1023ull) * 16 + (k)] = global_ns(); \
     } while (0)
 __device__ __forceinline__ double ld_box(const double *p) { return __ldcg(p); }     // written by a peer: L2 is the coherence point
+
+// "LL" cells (the protocol NCCL uses for small messages): a double travels as two 8-byte words, each carrying 32 data bits and
+// the 32-bit sequence number of the exchange, written with ONE 16-byte store.  The receiver polls the cell until both words
+// show the expected sequence: no separate flag, no fence between data and flag, one NVLink crossing per exchange.
+__device__ __forceinline__ void ll_store(unsigned long long *cell, double v, unsigned int seq32) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), hi = (unsigned long long)seq32 << 32;
+    const unsigned long long w0 = hi | (b & 0xffffffffull), w1 = hi | (b >> 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(w0), "l"(w1) : "memory");
+}
+// returns the value once it has arrived; gives up after ~4 s (a peer died): raises S_ERR and returns 0
+__device__ __forceinline__ double ll_wait(const unsigned long long *cell, unsigned int seq32, double *scal) {
+    unsigned long long w0, w1;
+    unsigned int spins = 0;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(cell) : "memory");
+        if ((unsigned int)(w0 >> 32) == seq32 && (unsigned int)(w1 >> 32) == seq32) break;
+        if ((++spins & 255u) == 0) {
+            if (*reinterpret_cast<const volatile double *>(scal + 9) != 0.0) return 0.0;       // S_ERR
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 8000000000ll) { scal[9] = 1.0; __threadfence(); return 0.0; }
+        }
+    }
+    return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+}
+
+// sum over the ranks (in rank order) of the cells cell0 + t * stride: all loads of a round are issued together, only the
+// cells that have not arrived are polled again
+__device__ __forceinline__ double ll_wait_sum(const unsigned long long *cell0, size_t stride, int P, unsigned int seq32, double *scal) {
+    double v[LSS_MAX_RANKS];
+    unsigned int pending = (1u << P) - 1u, spins = 0;
+    long long t0 = 0;
+#pragma unroll
+    for (int t = 0; t < LSS_MAX_RANKS; ++t) v[t] = 0.0;
+    while (pending) {
+        unsigned long long w0[LSS_MAX_RANKS], w1[LSS_MAX_RANKS];
+#pragma unroll
+        for (int t = 0; t < LSS_MAX_RANKS; ++t)
+            if (pending & (1u << t))
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[t]), "=l"(w1[t]) : "l"(cell0 + t * stride) : "memory");
+#pragma unroll
+        for (int t = 0; t < LSS_MAX_RANKS; ++t)
+            if ((pending & (1u << t)) && (unsigned int)(w0[t] >> 32) == seq32 && (unsigned int)(w1[t] >> 32) == seq32) {
+                v[t] = __longlong_as_double((long long)((w1[t] << 32) | (w0[t] & 0xffffffffull)));
+                pending &= ~(1u << t);
+            }
+        if (pending && (++spins & 255u) == 0) {
+            if (*reinterpret_cast<const volatile double *>(scal + 9) != 0.0) break;       // S_ERR
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 8000000000ll) { scal[9] = 1.0; __threadfence(); break; }
+        }
+    }
+    double a = 0.0;
+#pragma unroll
+    for (int t = 0; t < LSS_MAX_RANKS; ++t) a += v[t];
+    return a;
+}
 
 // thread t < n waits until flags[t] >= want; gives up after ~4 s (another rank died) and raises S_ERR
 __device__ __forceinline__ void wait_flags(const unsigned long long *flags, int n, unsigned long long want, double *scal) {
@@ -1002,6 +1060,7 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
     __shared__ double sm[VEC_BLOCK / 32];
     __shared__ double rs[ROWS], qs[ROWS];
     __shared__ double cs[CS_MAX];
+    __shared__ double llv[LSS_MAX_RANKS];
     if (scal[S_DONE0 + parity] != 0.0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE0 + (parity ^ 1)] = 1.0;
         return;
@@ -1012,6 +1071,7 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
     const unsigned long long it = (unsigned long long)scal[S_ITERS];
     const int par = (int)(it & 1ull);
     const unsigned long long seq_a = sa.seq + 2ull * it + 1ull, seq_x = seq_a + 1ull;
+    const unsigned int seq32_a = (unsigned int)seq_a, seq32_x = (unsigned int)seq_x;
     unsigned long long *mine = sa.box[me];
     static_assert(PQ_SLOTS == VEC_BLOCK, "one p.q slot per thread");
     SHARD_STAMP(0);
@@ -1029,15 +1089,12 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
         __syncthreads();
         pq = sm[0];
         __syncthreads();
-        if (blockIdx.x == 0 && (int)threadIdx.x < P) {          // one thread per peer: data, then the flag, in program order
-            unsigned long long *peer = sa.box[threadIdx.x];
-            reinterpret_cast<double *>(peer + sa.off_da)[par * P + me] = pq;
-            st_release_sys(peer + sa.off_fa + par * P + me, seq_a);
-        }
-        wait_flags(mine + sa.off_fa + par * P, P, seq_a, scal);
+        if (blockIdx.x == 0 && (int)threadIdx.x < P)            // one thread per peer: value and sequence number in one store
+            ll_store(sa.box[threadIdx.x] + sa.off_lla + 2 * (par * P + me), pq, seq32_a);
+        if ((int)threadIdx.x < P) llv[threadIdx.x] = ll_wait(mine + sa.off_lla + 2 * (par * P + threadIdx.x), seq32_a, scal);
+        __syncthreads();
         double tot = 0.0;
-        const double *da = reinterpret_cast<const double *>(mine + sa.off_da) + par * P;
-        for (int t = 0; t < P; ++t) tot += ld_box(da + t);
+        for (int t = 0; t < P; ++t) tot += llv[t];        // rank order: the same sum on every rank
         alpha = tot > 0.0 ? rz_old / tot : 0.0;
         have_alpha = true;
         SHARD_STAMP(1);
@@ -1091,8 +1148,12 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
                 z[c] = zl;
                 v += rl * zl;
             }
-            const long long zi = sa.off_z + (long long)par * sa.ZP + (long long)b * BS + l;
-            for (int t = 0; t < P; ++t) reinterpret_cast<double *>(sa.box[t])[zi] = zl;      // coalesced over the CTA's blocks
+            // z of the own blocks goes to the ranks that reference them, as LL cells (16-byte stores, coalesced over the CTA's
+            // blocks): no fence and no flag are needed before the peers may read them
+            const long long zi = sa.off_z + 2 * ((long long)par * sa.ZP + (long long)b * BS + l);
+            const unsigned int peers = sa.blk_peers ? ((unsigned int)__ldg(sa.blk_peers + (b - sa.blk_lo)) | (1u << me)) : 0xffffffffu;
+            for (int t = 0; t < P; ++t)
+                if (peers & (1u << t)) ll_store(sa.box[t] + zi, zl, seq32_x);
         }
     }
     if (!have_alpha) get_alpha();
@@ -1156,42 +1217,36 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
         }
     }
     const unsigned long long tc1 = sa.trace ? global_ns() : 0ull;
-    __threadfence_system();          // this thread's z stores of phase B (long acknowledged by now) are visible system-wide before any flag below
     if (sa.trace && threadIdx.x == 0) {         // slowest CTA of the phase: work, then fence
         atomicMax(sa.trace + (it & 1023ull) * 16 + 11, tc1 - tc0);
         atomicMax(sa.trace + (it & 1023ull) * 16 + 12, global_ns() - tc1);
     }
     grid.sync();
     SHARD_STAMP(5);
-    // ---- exchange X: packet [r.z_BJ | r_c,k | t_k] to every rank, in SHARD_NS slices (CTA b serves peer b % P, slice b / P)
+    // ---- exchange X: packet [r.z_BJ | r_c,k | t_k] to every rank as LL cells, in SHARD_NS slices (CTA b serves peer b % P,
+    // slice b / P)
     if ((int)blockIdx.x < P * SHARD_NS) {
         const int peer = (int)blockIdx.x % P, sl = (int)blockIdx.x / P;
-        double *dst = reinterpret_cast<double *>(sa.box[peer] + sa.off_db) + (size_t)(par * P + me) * sa.LB;
+        unsigned long long *dst = sa.box[peer] + sa.off_llx + 2 * (size_t)(par * P + me) * sa.LB;
         const int used = 1 + n_c + sa.n_e, per_s = (used + SHARD_NS - 1) / SHARD_NS;
         const int i0 = sl * per_s, i1 = min(used, i0 + per_s);
         if (sl == 0) {
             const double rzk = sum_partials(part, (int)gridDim.x, sm);
-            if (threadIdx.x == 0) dst[0] = rzk;
+            if (threadIdx.x == 0) ll_store(dst, rzk, seq32_x);
         }
-        for (int i = max(i0, 1) + (int)threadIdx.x; i < i1; i += VEC_BLOCK) {
-            dst[i] = __ldcg(sa.tgt + (i - 1));        // written with REDs (L2) by all CTAs before the grid barrier
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_sys(sa.box[peer] + sa.off_fb + (par * P + me) * SHARD_NS + sl, seq_x);
+        for (int i = max(i0, 1) + (int)threadIdx.x; i < i1; i += VEC_BLOCK)
+            ll_store(dst + 2 * (size_t)i, __ldcg(sa.tgt + (i - 1)), seq32_x);     // tgt: written with REDs (L2) before the grid barrier
     }
     SHARD_STAMP(6);
-    wait_flags(mine + sa.off_fb + par * P * SHARD_NS, P * SHARD_NS, seq_x, scal);
-    SHARD_STAMP(7);
-    const double *db = reinterpret_cast<const double *>(mine + sa.off_db) + (size_t)par * P * sa.LB;
-    double rz_new = 0.0;
-    for (int t = 0; t < P; ++t) rz_new += ld_box(db + (size_t)t * sa.LB);
+    const unsigned long long *db = mine + sa.off_llx + 2 * (size_t)par * P * sa.LB;
+    if ((int)threadIdx.x < P) llv[threadIdx.x] = ll_wait(db + 2 * (size_t)threadIdx.x * sa.LB, seq32_x, scal);
     for (int m = threadIdx.x; m < n_c; m += VEC_BLOCK) {
-        double a = 0.0;
-        for (int t = 0; t < P; ++t) a += ld_box(db + (size_t)t * sa.LB + 1 + m);
-        cs[m] = a;
+        cs[m] = ll_wait_sum(db + 2 * (size_t)(1 + m), 2 * (size_t)sa.LB, P, seq32_x, scal);
     }
     __syncthreads();
+    SHARD_STAMP(7);
+    double rz_new = 0.0;
+    for (int t = 0; t < P; ++t) rz_new += llv[t];
     // ---- phase C2: z_c = S_c^-1 r_c
     {
         const int warp = (int)(tid >> 5), n_warps = (int)(nth >> 5);
@@ -1241,13 +1296,13 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
     const double beta = rz_old > 0.0 ? rz_new / rz_old : 0.0;
     // p from the packed z of the owners, at the columns this rank's rows of N reference (the rest of p is never read here)
     {
-        const double *zp = reinterpret_cast<const double *>(mine + sa.off_z) + (size_t)par * sa.ZP;
+        const unsigned long long *zp = mine + sa.off_z + 2 * (size_t)par * sa.ZP;      // LL cells, sent in phase B of this iteration
         const int64_t total = sa.dlist ? (int64_t)sa.n_dlist : (int64_t)n_blocks * BS;
         for (int64_t i = tid; i < total; i += nth) {
             const int64_t k = sa.dlist ? (int64_t)__ldg(sa.dlist + i) : i;
             const int c = __ldg(bcols + k);
             if (c < 0) continue;
-            double zi = ld_box(zp + k);
+            double zi = ll_wait(zp + 2 * k, seq32_x, scal);
             if (n_c > 0) {
                 const int4 pi = __ldg(ca.cp_idx + c);
                 const float4 w = __ldg(ca.cp_w + c);
@@ -1272,8 +1327,7 @@ cg_step_shard_kernel(int64_t n, double *__restrict__ q, double *__restrict__ pq_
                 acc = warp_sum(acc);
             }
             if (lane_id() == 0) {
-                double t = 0.0;
-                for (int r = 0; r < P; ++r) t += ld_box(db + (size_t)r * sa.LB + 1 + n_c + e);
+                const double t = ll_wait_sum(db + 2 * (size_t)(1 + n_c + e), 2 * (size_t)sa.LB, P, seq32_x, scal);
                 const double un = t + acc + beta * sa.u_e[e];
                 sa.u_e[e] = un;
                 p[sa.e0 + e] = -sa.einv[e] * un;
@@ -1301,6 +1355,53 @@ static const void *step_shard_kernel_for(int bs) {
         case 36: return (const void *)cg_step_shard_kernel<36>;
         default: return nullptr;
     }
+}
+
+// row-sharded step, set-up: need[c] = 1 for every column the local rows of N reference; bit (owner of c) set in the mask of the
+// preconditioner block of every own row that references c (block b belongs to the rank r with floor(r n_b / P) <= b < floor((r + 1) n_b / P))
+__global__ void __launch_bounds__(256)
+shard_need_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__restrict__ indices, const int *__restrict__ col_block, int n_b, int P,
+                  int blk_lo, int blk_hi, unsigned char *__restrict__ need, unsigned int *__restrict__ blk_mask) {
+    const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    const int b_row = col_block[r];
+    const bool own_row = b_row >= blk_lo && b_row < blk_hi;
+    unsigned int mask = 0;
+    for (int k = indptr[r] + (int)lane_id(); k < indptr[r + 1]; k += 32) {
+        const int c = indices[k];
+        need[c] = 1;
+        const int b = col_block[c];
+        if (own_row && b >= 0) {
+            int t = (int)(((long long)b * P) / n_b);
+            while (t + 1 < P && (int)(((long long)(t + 1) * n_b) / P) <= b) ++t;
+            while (t > 0 && (int)(((long long)t * n_b) / P) > b) --t;
+            mask |= 1u << t;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+    if (own_row && lane_id() == 0 && mask) atomicOr(blk_mask + (b_row - blk_lo), mask);
+}
+
+// slots of the packed z buffer whose column is needed, appended in (roughly) ascending order: one append per warp
+__global__ void __launch_bounds__(256)
+shard_dlist_kernel(int64_t n_slots, const int *__restrict__ cols_pad, const unsigned char *__restrict__ need, int *__restrict__ dlist,
+                   int *__restrict__ counter) {
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int c = k < n_slots ? cols_pad[k] : -1;
+    const bool keep = c >= 0 && need[c];
+    const unsigned int m = __ballot_sync(0xffffffffu, keep);
+    if (!m) return;
+    int base = 0;
+    if (lane_id() == 0) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) dlist[base + __popc(m & ((1u << lane_id()) - 1u))] = (int)k;
+}
+
+__global__ void __launch_bounds__(256)
+narrow_mask_kernel(int n, const unsigned int *__restrict__ in, unsigned char *__restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = (unsigned char)(in[i] & 0xffu);
 }
 
 // out[k - base] = key0 + r for every entry k of row r of a CSR pointer array (one warp per row)
@@ -1465,6 +1566,7 @@ struct lss_solver {
     int n_fr = 0, n_fe = 0;
     int64_t kE0 = 0;
     double *tgt = nullptr;
+    unsigned char *blk_peers = nullptr;   // per own block: ranks that reference it
     int32_t *dlist = nullptr; // slots of the packed z buffer whose columns this rank's rows of N reference (own + halo): the only entries of p it keeps current
     int n_dlist = 0;
     int step_sh_grid;
@@ -1502,6 +1604,7 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     if (s->u_e) cudaFreeAsync(s->u_e, s->stream);
     if (s->tk) cudaFreeAsync(s->tk, s->stream);
     if (s->dlist) cudaFreeAsync(s->dlist, s->stream);
+    if (s->blk_peers) cudaFreeAsync(s->blk_peers, s->stream);
     if (s->fr_key) cudaFreeAsync(s->fr_key, s->stream);
     if (s->fe_key) cudaFreeAsync(s->fe_key, s->stream);
     if (s->tgt) cudaFreeAsync(s->tgt, s->stream);
@@ -2017,9 +2120,9 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
     sa.rank = pc->rank; sa.n_ranks = P; sa.blk_lo = s->blk_lo; sa.blk_hi = s->blk_hi;
     sa.LB = (1 + n_c + n_e + 3) & ~3;
     sa.ZP = (long long)s->bp->n_blocks * bs;
-    sa.off_fa = 0; sa.off_da = 2 * P; sa.off_fb = 4 * P; sa.off_db = (4 * P + 2 * P * SHARD_NS + 7) & ~7;
-    sa.off_z = (sa.off_db + 2ll * P * sa.LB + 7) & ~7ll;
-    const size_t need = sizeof(double) * (size_t)(sa.off_z + 2 * sa.ZP);
+    sa.off_lla = 0; sa.off_zf = 4 * P; sa.off_llx = (6 * P + 7) & ~7;
+    sa.off_z = (sa.off_llx + 4ll * P * sa.LB + 7) & ~7ll;
+    const size_t need = sizeof(double) * (size_t)(sa.off_z + 4 * sa.ZP);
     if (need > pc->box_bytes) return fail(LSS_EINVAL, "solver_solve: the mailbox holds %zu bytes, the exchange needs %zu", pc->box_bytes, need);
     for (int r = 0; r < P; ++r) sa.box[r] = reinterpret_cast<unsigned long long *>(pc->box_peer[r]);
     sa.seq = pc->seq;
@@ -2041,23 +2144,32 @@ int shard_solve(lss_solver *s, double *x, double rtol, int32_t max_iter, int32_t
         sa.trace = reinterpret_cast<unsigned long long *>(trace_buf.p);
     }
     if (!s->dlist && P > 1 && !getenv("LSS_SHARD_FULL_P")) {
-        // columns referenced by the local rows of N -> slots of the packed z buffer (once per solver: the pattern is fixed)
+        // columns referenced by the local rows of N -> slots of the packed z buffer this rank reads in phase D; per own block the
+        // ranks that reference it (they get its z in phase B).  Once per solver: the pattern is fixed.
         const int64_t slots_all = (int64_t)s->bp->n_blocks * bs;
-        std::vector<int32_t> h_idx(s->nm->nnz > 0 ? s->nm->nnz : 1), h_cols(slots_all);
-        LSS_CUDA(cudaMemcpyAsync(h_idx.data(), s->nm->indices, sizeof(int32_t) * s->nm->nnz, cudaMemcpyDeviceToHost, st));
-        LSS_CUDA(cudaMemcpyAsync(h_cols.data(), s->bp->cols_pad, sizeof(int32_t) * slots_all, cudaMemcpyDeviceToHost, st));
-        LSS_CUDA(cudaStreamSynchronize(st));
-        std::vector<unsigned char> need(n, 0);
-        for (int64_t k = 0; k < s->nm->nnz; ++k) need[h_idx[k]] = 1;
-        std::vector<int32_t> dl;
-        dl.reserve(slots_all / P * 2);
-        for (int64_t k = 0; k < slots_all; ++k)
-            if (h_cols[k] >= 0 && need[h_cols[k]]) dl.push_back((int32_t)k);
-        s->n_dlist = (int)dl.size();
-        LSS_CUDA(cudaMallocAsync((void **)&s->dlist, sizeof(int32_t) * (dl.size() + 1), st));
-        if (!dl.empty()) LSS_CUDA(cudaMemcpyAsync(s->dlist, dl.data(), sizeof(int32_t) * dl.size(), cudaMemcpyHostToDevice, st));
+        const int n_own = s->blk_hi - s->blk_lo;
+        if (s->blk_lo != (int)(((long long)pc->rank * s->bp->n_blocks) / P) || s->blk_hi != (int)(((long long)(pc->rank + 1) * s->bp->n_blocks) / P))
+            return fail(LSS_EINVAL, "solver_solve: the row-sharded step expects the blocks split evenly in rank order");
+        Scratch need, mask32, counter;
+        LSS_CUDA(need.alloc((size_t)n, st));
+        LSS_CUDA(mask32.alloc(sizeof(unsigned int) * (size_t)(n_own + 1), st));
+        LSS_CUDA(counter.alloc(sizeof(int), st));
+        LSS_CUDA(cudaMemsetAsync(need.p, 0, (size_t)n, st));
+        LSS_CUDA(cudaMemsetAsync(mask32.p, 0, sizeof(unsigned int) * (size_t)(n_own + 1), st));
+        LSS_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(int), st));
+        shard_need_kernel<<<ceil_div(n * 32, 256), 256, 0, st>>>(n, s->nm->indptr, s->nm->indices, s->bp->col_block, s->bp->n_blocks, P, s->blk_lo,
+                                                               s->blk_hi, need.as<unsigned char>(), mask32.as<unsigned int>());
+        LSS_LAUNCH_CHECK();
+        LSS_CUDA(cudaMallocAsync((void **)&s->dlist, sizeof(int32_t) * (size_t)(slots_all + 1), st));
+        shard_dlist_kernel<<<ceil_div(slots_all, 256), 256, 0, st>>>(slots_all, s->bp->cols_pad, need.as<unsigned char>(), s->dlist, counter.as<int>());
+        LSS_LAUNCH_CHECK();
+        LSS_CUDA(cudaMallocAsync((void **)&s->blk_peers, (size_t)(n_own + 1), st));
+        narrow_mask_kernel<<<ceil_div(n_own, 256), 256, 0, st>>>(n_own, mask32.as<unsigned int>(), s->blk_peers);
+        LSS_LAUNCH_CHECK();
+        LSS_CUDA(cudaMemcpyAsync(&s->n_dlist, counter.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         LSS_CUDA(cudaStreamSynchronize(st));
     }
+    sa.blk_peers = s->dlist ? s->blk_peers : nullptr;
     sa.dlist = s->dlist; sa.n_dlist = s->n_dlist;
     if (!s->tgt) {
         // flat entry lists of phase C1: a row key per entry of P^T (own columns) and of the rows of N_E (once per solver)

@@ -197,7 +197,7 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         n_c = structure['coarse']['n_c'] if structure.get('coarse') else 0
         P = dist.world
         bs = (int(structure['max_block']) + 3) // 4 * 4
-        dist.ensure_box(8 * (32 * P + 64 + 2 * P * (n_c + n_e + 8) + 2 * bs * shard['n_blocks']))
+        dist.ensure_box(8 * (32 * P + 64 + 4 * P * (n_c + n_e + 8) + 4 * bs * shard['n_blocks']))
         st.mark('it:csr')
         solver = NormalSolver(G_csr, C_all, z, rhs_d[n_data:].contiguous(), sigma, E_all[n_data:].contiguous(), fixed_cols, dist,
                               structure=structure, stages=st,
