@@ -119,6 +119,7 @@ int lss_group_median(const int32_t *ids, const double *vals, int64_t n, int32_t 
 #define LSS_SPMV_PLAIN 0     /* y = A x                                                        */
 #define LSS_SPMV_SCALE 1     /* y = s .* (A x)        (row weights, smooth_fit.py:129, 142)     */
 #define LSS_SPMV_RESIDUAL 2  /* y = s - A x           (r_data = z - G m0, smooth_fit.py:146)    */
+#define LSS_SPMV_ACCUM 3     /* y += A x with atomics (internal: products that share y)         */
 
 /* scipy csr_matvec replacement (smooth_fit.py:142, 146, 326-345).  nnz-balanced tiles, deterministic
  * (no atomics).  `s` is read only for modes 1 and 2.  rows [row_begin, row_end) only. */
@@ -276,6 +277,33 @@ int lss_solver_set_structure(lss_solver_t *solver, int32_t n_blocks, const int32
  * The reference's direct QR solve (smooth_fit.py:142) has no counterpart; this only changes the iteration count. */
 int lss_solver_set_coarse(lss_solver_t *solver, int32_t n_coarse, const int32_t *cp_idx, const float *cp_w,
                           const int32_t *pt_ptr, const int32_t *pt_col, const float *pt_w, int64_t nnz_p, int32_t refresh);
+/* Grid-structured storage of N for the CG product (explicit-normal form on one GPU; optional).  The reference's solve
+ * (sparseqr.solve, smooth_fit.py:142) has no counterpart: this only changes how q = N p is computed.  On the z0(y, x) +
+ * dz(y, x, t) unknowns that setup_grids builds (grid_functions.py:26-134) almost all of N is regular: z0 node x dz node
+ * pairs hold one value per epoch, dz node x dz node pairs are banded in time, z0 x z0 is a fixed set of (dy, dx) offsets.
+ * These families are stored without column indices (z0-dz pairs once for both triangles) and the rest as a CSR remainder.
+ * lss_solver_export_pattern copies the pattern of N out (indptr[n_cols + 1], indices[nnz], device arrays);
+ * lssurf_b200/structured.py builds the tables from it; lss_solver_set_structured hands them over.  All pointers are device
+ * arrays that must stay valid for the life of the solver (borrowed).  Values are taken from N through `map` after every
+ * lss_solver_set_weights.  Layout of the value buffer (doubles; nt = epochs per dz node, nn = dz nodes, n0 = z0 nodes); node
+ * blocks and pair records are multiples of 16 bytes so that each travels as one bulk copy:
+ *   node block a at [a * node_len]:   [((band + 1) * dd_stride + j) * nt + t]   N[(a, t), (b_j, t + band)], band = -1..1
+ *                                     [3 * dd_stride * nt ...]                  the neighbour ids b_j = dd_b[a * dd_stride + j]
+ *                                                                               as int32, two per double (-1: slot not used)
+ *                                     [self_off + (band + 2) * nt + t]          N[(a, t), (a, t + band)], band = -2..2,
+ *                                                                               self_off = 3 * dd_stride * nt + (dd_stride + 1) / 2
+ *   pair record at [zd_base + pair * rec_len]:  [t] N[k, (a, t)], [nt] = k = zd_k[pair] as int64; the pairs of dz node a
+ *                                     are [zd_ptr[a], zd_ptr[a + 1]) (at most max_pairs <= 8 * (256 / nt))
+ *   [zz_base + (d * n0 + i)]          N[z0 i, z0 i + zz_off[d]] */
+typedef struct {
+    int32_t nt, nn, n0, n_diag, dd_stride, node_len, rec_len, max_pairs, n_zd, rem_n_rows;
+    int64_t z0_col0, dz_col0, rows, nnz, n_vals, zd_base, zz_base, rem_nnz;
+    const int32_t *map;                       /* [nnz] slot of every CSR entry of the leading rows, -1: not stored here */
+    const int32_t *dd_b, *zd_ptr, *zd_k, *zz_off;
+    const int32_t *rem_src, *rem_rows, *rem_indptr, *rem_indices;   /* remainder: CSR over rem_n_rows non-empty rows */
+} lss_structured_t;
+int lss_solver_export_pattern(lss_solver_t *solver, int32_t *indptr, int32_t *indices);
+int lss_solver_set_structured(lss_solver_t *solver, const lss_structured_t *desc);
 /* Row weights w (length n_rows): 1/sigma^2 for selected data rows, 0 for edited rows, 1/E_c^2 for
  * constraint rows.  Recomputes the right-hand side A^T W b and the Jacobi diagonal. */
 int lss_solver_set_weights(lss_solver_t *solver, const double *w);

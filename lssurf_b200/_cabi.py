@@ -27,6 +27,13 @@ class lss_grid_t(C.Structure):
                 ('hi', C.c_double * 3), ('delta', C.c_double * 3), ('col_0', C.c_int64)]
 
 
+class lss_structured_t(C.Structure):
+    """Tables of the grid-structured normal-matrix layout (include/lssurf_b200.h; built by lssurf_b200/structured.py)."""
+    _fields_ = [(k, C.c_int32) for k in ('nt', 'nn', 'n0', 'n_diag', 'dd_stride', 'node_len', 'rec_len', 'max_pairs', 'n_zd', 'rem_n_rows')] + \
+               [(k, C.c_int64) for k in ('z0_col0', 'dz_col0', 'rows', 'nnz', 'n_vals', 'zd_base', 'zz_base', 'rem_nnz')] + \
+               [(k, C.c_void_p) for k in ('map', 'dd_b', 'zd_ptr', 'zd_k', 'zz_off', 'rem_src', 'rem_rows', 'rem_indptr', 'rem_indices')]
+
+
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 _pi64, _pi32, _pf64 = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)
 
@@ -71,6 +78,8 @@ SIGNATURES = {
     'lss_solver_info': [_vp, _pi64],
     'lss_solver_set_structure': [_vp, _i32, _vp, _vp, _i32, _i64, _i64],
     'lss_solver_set_coarse': [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32],
+    'lss_solver_export_pattern': [_vp, _vp, _vp],
+    'lss_solver_set_structured': [_vp, C.POINTER(lss_structured_t)],
     'lss_normal_create': [C.POINTER(_vp), _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _pi64, _vp],
     'lss_normal_update': [_vp, _vp],
     'lss_normal_export': [_vp, _vp, _vp, _vp],

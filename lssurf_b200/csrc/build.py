@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ['assembly.cu', 'sort.cu', 'spmv.cu', 'comm.cu', 'normal.cu', 'precond.cu', 'coarse.cu', 'solver.cu', 'robust.cu']
+SOURCES = ['assembly.cu', 'sort.cu', 'spmv.cu', 'comm.cu', 'normal.cu', 'precond.cu', 'coarse.cu', 'structured.cu', 'solver.cu', 'robust.cu']
 LIB = os.path.join(PKG, 'liblssurf_b200.so')
 NVCC_FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default']
@@ -21,7 +21,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, f) for f in SOURCES + ['common.cuh', 'precond.cuh', 'coarse.cuh']] + \
+    deps = [os.path.join(HERE, f) for f in SOURCES + ['common.cuh', 'precond.cuh', 'coarse.cuh', 'structured.cuh']] + \
            [os.path.join(os.path.dirname(PKG), 'include', 'lssurf_b200.h')]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -155,7 +155,8 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
 int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
                        int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches,
                        double *dot_slots = nullptr,    // y pre-zeroed; dot_slots[256] += partial sums of x . (A x)
-                       const int32_t *row_ids = nullptr);   // compacted row list: row r of the CSR is row row_ids[r] of y and x
+                       const int32_t *row_ids = nullptr,    // compacted row list: row r of the CSR is row row_ids[r] of y and x
+                       bool accumulate = false);            // every row is added with an atomic (y is shared with another product)
 
 // Products specialised for the explicit normal matrix (long overlapping rows); variant 0 is spmv_launch_atomic.
 int normal_product_variant();

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "precond.cuh"
 #include "coarse.cuh"
+#include "structured.cuh"
 
 namespace lss {
 
@@ -1566,6 +1567,7 @@ struct lss_solver {
     int n_fr = 0, n_fe = 0;
     int64_t kE0 = 0;
     double *tgt = nullptr;
+    lss::StructuredN *sn = nullptr;        // grid-structured copy of N for the CG product (lss_solver_set_structured)
     unsigned char *blk_peers = nullptr;   // per own block: ranks that reference it
     int32_t *dlist = nullptr; // slots of the packed z buffer whose columns this rank's rows of N reference (own + halo): the only entries of p it keeps current
     int n_dlist = 0;
@@ -1603,6 +1605,7 @@ extern "C" int lss_solver_destroy(lss_solver_t *s) {
     if (s->owned) cudaFreeAsync(s->owned, s->stream);
     if (s->u_e) cudaFreeAsync(s->u_e, s->stream);
     if (s->tk) cudaFreeAsync(s->tk, s->stream);
+    if (s->sn) lss::structured_destroy(s->sn);
     if (s->dlist) cudaFreeAsync(s->dlist, s->stream);
     if (s->blk_peers) cudaFreeAsync(s->blk_peers, s->stream);
     if (s->fr_key) cudaFreeAsync(s->fr_key, s->stream);
@@ -1908,6 +1911,10 @@ static int apply_normal(lss_solver *s, const double *v, bool with_dot, const dou
         const int64_t rows = (s->e1 > s->e0 && s->e1 == s->n_cols) ? s->e0 : s->n_cols;
         double *slots = (s->z && with_dot) ? s->buf + s->n_cols : nullptr;      // p.q by-product for the structured step kernel
         if (slots && !s->q_clean) LSS_CUDA(cudaMemsetAsync(slots, 0, sizeof(double) * PQ_SLOTS, st));
+        if (s->sn && s->sn->d.rows == rows) {
+            if (!s->q_clean) LSS_CUDA(cudaMemsetAsync(s->buf, 0, sizeof(double) * s->n_cols, st));
+            LSS_TRY(lss::structured_apply(s->sn, v, s->buf, stop, &s->launches, slots));
+        } else
         LSS_TRY(normal_apply_fast(s->nm, rows, v, s->buf, s->q_clean, stop, &s->launches, slots));
         s->q_clean = false;
     } else if (s->blocks) {
@@ -2368,6 +2375,7 @@ extern "C" int lss_solver_set_weights(lss_solver_t *s, const double *w) {
         LSS_TRY(ell_normal_launch(1, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, s->rhs, s->g, nullptr, nullptr, st));
         if (s->nm) {
             LSS_TRY(normal_update(s->nm, s->w));       // N += A^T diag(w - w_prev) A : only rows whose weight changed
+            if (s->sn) LSS_TRY(lss::structured_refresh(s->sn, s->nm->data));
             LSS_TRY(normal_diag(s->nm, s->diag));
         } else {
             LSS_TRY(ell_normal_launch(2, s->n_data, s->ell_pad, s->ell_k, s->ell_col, s->ell_val, nullptr, s->w, nullptr, s->diag, nullptr, nullptr, st));
@@ -2584,6 +2592,24 @@ extern "C" int lss_solver_solve(lss_solver_t *s, double *x, double rtol, int32_t
     return LSS_OK;
 }
 
+extern "C" int lss_solver_export_pattern(lss_solver_t *s, int32_t *indptr, int32_t *indices) {
+    if (!s || !indptr || !indices) return fail(LSS_EINVAL, "solver_export_pattern: null argument");
+    if (!s->nm) return fail(LSS_EINVAL, "solver_export_pattern: the solver holds no explicit normal matrix");
+    LSS_CUDA(cudaMemcpyAsync(indptr, s->nm->indptr, sizeof(int32_t) * (s->n_cols + 1), cudaMemcpyDeviceToDevice, s->stream));
+    LSS_CUDA(cudaMemcpyAsync(indices, s->nm->indices, sizeof(int32_t) * s->nm->nnz, cudaMemcpyDeviceToDevice, s->stream));
+    return LSS_OK;
+}
+
+extern "C" int lss_solver_set_structured(lss_solver_t *s, const lss_structured_t *desc) {
+    if (!s || !desc) return fail(LSS_EINVAL, "solver_set_structured: null argument");
+    if (!s->nm || s->shard) return fail(LSS_EINVAL, "solver_set_structured: needs the explicit-normal form on one GPU");
+    if (desc->rows > s->n_cols || desc->nnz > s->nm->nnz) return fail(LSS_EINVAL, "solver_set_structured: the tables do not match N");
+    if (s->sn) { lss::structured_destroy(s->sn); s->sn = nullptr; }
+    LSS_TRY(lss::structured_create(&s->sn, desc, s->stream));
+    if (s->have_weights) LSS_TRY(lss::structured_refresh(s->sn, s->nm->data));
+    return LSS_OK;
+}
+
 extern "C" int lss_solver_set_profile(lss_solver_t *s, int32_t on) {
     if (!s) return fail(LSS_EINVAL, "solver_set_profile: null solver");
     s->profile = on != 0;
@@ -2603,7 +2629,8 @@ extern "C" int lss_solver_info(lss_solver_t *s, int64_t *info_h) {
     info_h[7] = 0;
     if (s->nm) {
         const bool part = s->e1 > s->e0 && s->e1 == s->n_cols;
-        if (s->nm->owned && s->nm->cp_for_rows >= 0) info_h[7] = s->nm->cp_nnz;
+        if (s->sn) info_h[7] = s->sn->d.nnz;
+        else if (s->nm->owned && s->nm->cp_for_rows >= 0) info_h[7] = s->nm->cp_nnz;
         else if (part && lss::normal_product_variant() >= 10 && s->nm->tma_plan.tile_row && s->nm->tma_plan.n_rows == s->e0) info_h[7] = s->nm->tma_nnz;
         else if (part && s->nm->c8_part_rows == s->e0 && lss::normal_product_variant() >= 7) info_h[7] = s->nm->c8_part_nnz;
         else if (part && s->nm->part_rows == s->e0) info_h[7] = s->nm->part_nnz;

@@ -112,7 +112,7 @@ __device__ __forceinline__ void reduce_rows(const double *__restrict__ prod, int
         for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (valid && gl == 0) {
             if (ATOMIC) {
-                if (v == 0 || open) atomicAdd(y + ro, acc);
+                if (v == 0 || open || mode == LSS_SPMV_ACCUM) atomicAdd(y + ro, acc);
                 else y[ro] = acc;
                 dot += acc * xr;
             } else if (v == 0) carry_val[tile] = acc;
@@ -338,7 +338,7 @@ int spmv_launch(int64_t n_rows, const int32_t *indptr, const int32_t *indices, c
 // that consumes q clears it for the next product.
 int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y,
                        int64_t nnz, const SpmvPlan *plan, const double *stop, cudaStream_t stream, int64_t *launches, double *dot_slots,
-                       const int32_t *row_ids) {
+                       const int32_t *row_ids, bool accumulate) {
     if (n_rows <= 0 || nnz == 0) return LSS_OK;
     constexpr int BLOCK = 128, IPT = 8;
     if (!plan || !plan->bounds || plan->tile != BLOCK * IPT) return fail(LSS_EINVAL, "spmv_launch_atomic: needs a plan with %d-entry tiles", BLOCK * IPT);
@@ -349,7 +349,8 @@ int spmv_launch_atomic(int64_t n_rows, const int32_t *indptr, const int32_t *ind
         if (per_sm < 1) per_sm = 1;
     }
     const int grid = n_tiles < kSMs * per_sm ? n_tiles : kSMs * per_sm;
-    spmv_persistent_kernel<BLOCK, IPT, false, true><<<grid, BLOCK, 0, stream>>>(n_rows, nnz, n_tiles, indptr, indices, data, x, y, LSS_SPMV_PLAIN,
+    spmv_persistent_kernel<BLOCK, IPT, false, true><<<grid, BLOCK, 0, stream>>>(n_rows, nnz, n_tiles, indptr, indices, data, x, y,
+                                                                                accumulate ? LSS_SPMV_ACCUM : LSS_SPMV_PLAIN,
                                                                                 nullptr, nullptr, nullptr, plan->bounds, stop, dot_slots, row_ids);
     LSS_LAUNCH_CHECK();
     if (launches) *launches += 1;

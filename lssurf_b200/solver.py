@@ -20,7 +20,7 @@ import os
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, structured
 from .lin_op import DeviceCSR
 
 
@@ -105,6 +105,7 @@ def grid_structure(grids, fixed_cols, bias_cols=None, max_block=64):
             ptr = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=dev)
             ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
             out.update(block_ptr=ptr, block_cols=cols[order].to(torch.int32).contiguous(), max_block=int(counts.max().item()))
+        out['grids_desc'] = (int(z0.col_0), tuple(int(v) for v in z0.shape), int(dz.col_0), tuple(int(v) for v in dz.shape))
     if bias_cols is not None and len(bias_cols) > 0:
         b = np.asarray(bias_cols, dtype=np.int64)
         if b.max() - b.min() + 1 == b.size:
@@ -287,6 +288,34 @@ class NormalSolver(object):
                                                     _cabi.ptr(cs['pt_ptr']), _cabi.ptr(cs['pt_col']), _cabi.ptr(cs['pt_w']),
                                                     int(cs['pt_col'].numel()), int(structure.get('coarse_refresh', 1))))
                 self.n_coarse = cs['n_c']
+            self.structured = None
+            gd = structure.get('grids_desc')
+            # opt-in (LSS_STRUCTURED_N=1): 0.073 ms instead of 0.092 ms per product on the bench workload, but the tables cost
+            # ~12 ms per fit to build, and the kernel is still issue-bound (profiles/structured_product_r02.md)
+            if gd is not None and os.environ.get('LSS_STRUCTURED_N', '0') == '1' and shard is None:
+                self._set_structured(gd, int(e0) if (e1 > e0 and e1 == self.n_cols) else self.n_cols)
+
+    def _set_structured(self, gd, rows):
+        """Grid-structured copy of N for the CG product (structured.py): tables from the exported pattern, handed to the
+        library, which fills the values after every numeric update.  Skipped when the layout does not apply."""
+        L = _cabi.lib()
+        dev = self.x.device
+        indptr = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
+        indices = torch.empty(max(self.nnz_N, 1), dtype=torch.int32, device=dev)
+        _cabi.check(L.lss_solver_export_pattern(self.handle, _cabi.ptr(indptr), _cabi.ptr(indices)))
+        st = structured.build(indptr, indices, rows, *gd)
+        del indptr, indices
+        if st is None:
+            return
+        d = _cabi.lss_structured_t()
+        for k in ('nt', 'nn', 'n0', 'n_diag', 'dd_stride', 'node_len', 'rec_len', 'max_pairs', 'n_zd', 'z0_col0', 'dz_col0', 'rows', 'nnz', 'n_vals', 'zd_base', 'zz_base'):
+            setattr(d, k, int(st[k]))
+        d.rem_n_rows, d.rem_nnz = int(st['rem_rows'].numel()), int(st['rem_src'].numel())
+        for k in ('map', 'dd_b', 'zd_ptr', 'zd_k', 'zz_off', 'rem_src', 'rem_rows', 'rem_indptr', 'rem_indices'):
+            setattr(d, k, st[k].data_ptr() if st[k].numel() else None)
+        _cabi.check(L.lss_solver_set_structured(self.handle, C.byref(d)))
+        self.structured = st          # the library borrows the tables: they live as long as the solver
+        self.structured_bytes = structured.product_bytes(st)
 
     def set_rows(self, in_TSE, sigma_extra=None):
         """Select data rows (uint8 mask) and, on the relaxed last pass, inflate their errors."""
@@ -310,7 +339,8 @@ class NormalSolver(object):
                          launches=int(st[4]), nnz=int(st[5]), rows=self.n_data + self.n_con, fused=self.fused, all_ell=self.all_ell,
                          n_data=self.n_data, n_con=self.n_con, nnz_G=self.G.nnz, nnz_C=self.C.nnz,
                          form=self.form, nnz_N=self.nnz_N, n_cols=self.n_cols, precond_blocks=self.n_blocks, eliminated=self.n_elim,
-                         nnz_product=int(info[7]), bad_blocks=int(info[6]), coarse=self.n_coarse)
+                         nnz_product=int(info[7]), bad_blocks=int(info[6]), coarse=self.n_coarse,
+                         structured_bytes=getattr(self, 'structured_bytes', 0) if getattr(self, 'structured', None) is not None else 0)
         return self.x
 
     def residual(self, x, z, out=None):

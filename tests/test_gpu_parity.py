@@ -505,6 +505,31 @@ def test_two_level_preconditioner_agrees_with_block_jacobi(L, monkeypatch):
             assert its[key] < 1.25 * its['bj'], (key, its)      # the coarse level pays off on large domains only (bench workload: -60 %)
 
 
+def test_structured_normal_product_agrees_with_the_csr_product(L, monkeypatch):
+    """The grid-structured layout of N (lss_solver_set_structured: z0-dz pairs stored once for both triangles, banded dz-dz
+    blocks, z0-z0 diagonals, CSR remainder) only changes how q = N p is computed: same masks after every iteration, same
+    solution to solver tolerance as the CSR product; with the eliminated bias block (remainder = bias coupling) and without."""
+    from lssurf_b200 import synthetic
+    for gen, n, width in ((synthetic.icesat2_tracks, 300_000, 3.e4), (synthetic.uniform_3d, 200_000, 3.e4)):
+        pts, kw = gen(n=n, width=width, seed=23)
+        out = {}
+        for key in ('0', '1'):
+            monkeypatch.setenv('LSS_STRUCTURED_N', key)
+            hist = []
+            out[key] = L.smooth_fit(data=make_data(L, pts), VERBOSE=False, history=hist, **kw)
+            out[key]['hist'] = hist
+        monkeypatch.delenv('LSS_STRUCTURED_N')
+        assert out['0']['timing']['pcg'][0]['structured_bytes'] == 0 and out['1']['timing']['pcg'][0]['structured_bytes'] > 0
+        assert out['1']['timing']['pcg'][0]['structured_bytes'] < 0.8 * 12 * out['0']['timing']['pcg'][0]['nnz_product']
+        assert rel_l2(out['1']['m']['all'], out['0']['m']['all']) < 1e-9
+        assert len(out['1']['hist']) == len(out['0']['hist'])
+        for a, b in zip(out['1']['hist'], out['0']['hist']):
+            assert np.array_equal(a['mask_out'], b['mask_out']), a['iteration']
+        its = [sum(p['iterations'] for p in out[k]['timing']['pcg']) for k in ('0', '1')]
+        print(gen.__name__, 'CG iterations csr / structured', its)
+        assert abs(its[0] - its[1]) <= 0.05 * its[0] + 5
+
+
 def test_row_sharded_solver_on_one_rank_matches_the_plain_solver(L, monkeypatch):
     """The row-sharded PCG (own blocks of N, p exchanged through the P2P mailbox inside the step kernel) run with a single
     rank -- the mailbox is then local, every exchange goes to itself -- gives the plain solver's fit: same masks after
