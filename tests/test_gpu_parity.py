@@ -520,7 +520,7 @@ def test_structured_normal_product_agrees_with_the_csr_product(L, monkeypatch):
             out[key]['hist'] = hist
         monkeypatch.delenv('LSS_STRUCTURED_N')
         assert out['0']['timing']['pcg'][0]['structured_bytes'] == 0 and out['1']['timing']['pcg'][0]['structured_bytes'] > 0
-        assert out['1']['timing']['pcg'][0]['structured_bytes'] < 0.8 * 12 * out['0']['timing']['pcg'][0]['nnz_product']
+        assert out['1']['timing']['pcg'][0]['structured_bytes'] < 12 * out['0']['timing']['pcg'][0]['nnz_product']
         assert rel_l2(out['1']['m']['all'], out['0']['m']['all']) < 1e-9
         assert len(out['1']['hist']) == len(out['0']['hist'])
         for a, b in zip(out['1']['hist'], out['0']['hist']):
