@@ -7,21 +7,28 @@
 Workload (config.workload = "cfg4"): BASELINE.json configs[3] -- ICESat-2-shaped synthetic tracks,
 1e7 points on 100 x 100 km, z0 250 m (401^2), dz 1 km x 0.25 yr (101^2 x 21), per-(rgt, cycle) bias
 columns, curvature / slope / d2/dt2 constraints, up to 10 robust edit iterations; it fits one B200.
-One "step" = one complete smooth_fit(): design-matrix assembly (interp + stencil COO -> CSR), the
-edit loop of matrix-free PCG solves, residuals, sigma_extra (RDE + Brent) and 3-sigma masks.
+One "step" = one complete smooth_fit(): design-matrix assembly (interp + stencil COO -> CSR), the explicit normal
+matrix N = A^T W A, the edit loop of fp64 PCG solves on it (two-level preconditioner, bias columns eliminated),
+residuals, sigma_extra (RDE + Brent) and 3-sigma masks, parse_model.
 
   value   points/s with the per-point inputs already resident in HBM (CUDA tensors handed to smooth_fit),
-          timed with CUDA events between barrier + synchronize, max over ranks;
+          timed with CUDA events between barrier + synchronize, max over ranks; no profiling events inside;
   e2e     the same call with HOST NumPy inputs (pinned): host->device copies of the inputs and the
           device->host copies of the model and per-point outputs are inside the timed region;
-  roofline  achieved HBM GB/s of the dominant kernel (the nnz-tiled CSR product, used for A p and A^T u)
-          from CUDA events recorded by the solver around every product on its launch stream, against
-          MEASURED_PEAKS.json;
-  cpu_baseline  the CPU oracle port of the reference path (NumPy/SciPy, SuperLU stand-in for SPQR) on a
-          bounded sample of the same generator, timed on this host (rank 0, N = 1 only).
+  roofline  achieved HBM GB/s of the dominant kernel (q = N p of the CG iteration) from CUDA event pairs the solver
+          records on its launch stream in a SEPARATE untimed pass, against MEASURED_PEAKS.json; the CG iteration counts,
+          the per-stage wall times and the bench-scale parity record ride in the same object (keys the driver keeps);
+  cpu_baseline  the reference path on the CPU on a bounded sample of the same data set (rank 0, N = 1 only).
 
-`--impl reference` runs only that CPU arm (rank 0; other ranks exit 0).  With N > 1 the data rows (and
-the constraint rows) are sharded over the ranks: strong scaling, one NCCL all-reduce per CG iteration.
+With N > 1 the normal matrix is row-sharded: every rank owns a range of dz-node blocks (its rows of N, built from its own
+points plus halo copies), and the ranks exchange p inside the CG step kernel with stores into peer memory over NVLink --
+no collective inside the iteration.  Strong scaling (total work fixed).
+
+`--impl reference` runs only the CPU arm (rank 0; other ranks exit 0): the reference's own smooth_fit under stub
+dependencies when /root/reference exists (build container), else the oracle port (GPU box); SuiteSparseQR is replaced by
+SuperLU on the normal equations (bias columns ordered last) + 3 refinement steps in both.  Each step is one fit of the
+points of the cfg-4 data set inside a centred 10 x 10 km window (~1e5 points; the cost of the direct solve grows faster
+than the window: a 31.6 km window with 1e6 points takes ~280 s per fit, profiles/README.md), and the line says so.
 """
 import argparse
 import json
@@ -38,7 +45,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'smooth_fit_points_per_s'
 UNIT = 'points/s'
-SAMPLE_WIDTH = 5.0e3     # CPU arms: a 5 x 5 km window of the same generator at the same point density
+SAMPLE_WIDTH = 1.0e4     # CPU arms: the points of the cfg-4 data set inside a centred 10 x 10 km window
 
 
 def parse_args():
@@ -55,57 +62,110 @@ def parse_args():
     ap.add_argument('--max-outer', type=int, default=None, help='profiling only: cap the edit iterations')
     ap.add_argument('--cg-maxiter', type=int, default=None, help='profiling only: cap the CG iterations per solve')
     ap.add_argument('--skip-e2e', action='store_true', help='profiling only: no host-input pass')
-    ap.add_argument('--stages', action='store_true', help='add an untimed pass reporting wall time per stage')
+    ap.add_argument('--stages', action='store_true', help='kept for old command lines (the stage split is always reported)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the untimed bench-scale parity record')
+    ap.add_argument('--ref-window', type=float, default=SAMPLE_WIDTH, help='CPU arms: width of the sample window in metres')
     return ap.parse_args()
 
 
 def workload_config(a):
+    if a.gpus == 1:
+        par = 'single GPU'
+    else:
+        par = ('normal matrix row-sharded over %d GPUs by dz-node blocks (own points + halo copies per rank); p, p.q and the '
+               'coarse-level packet exchanged inside the CG step kernel through peer memory over NVLink, no collective per '
+               'iteration' % a.gpus)
     return {'workload': 'cfg4: ICESat-2-shaped tracks, %d points, %.0f x %.0f km, z0 250 m, dz 1 km x 0.25 yr, '
                         "bias_params=['rgt','cycle'], max_iterations=10" % (a.points, a.width / 1e3, a.width / 1e3),
-            'points': a.points, 'parallelism': 'row-sharded dp%d' % a.gpus,
-            'l2_policy': 'inputs larger than L2 (the normal matrix streamed per CG iteration is ~0.75 GB per rank at N=1, A is 1.7 GB)'}
+            'points': a.points, 'extent_km': a.width / 1e3, 'parallelism': par,
+            'l2_policy': 'inputs larger than L2 (N streamed per CG iteration is 0.37 GB at N=1, A is 1.7 GB)'}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(a):
+def cpu_sample(a, pts=None, kw=None):
+    """The points of the bench data set inside a centred window, to be fitted on that window with the same spacings."""
     from lssurf_b200 import synthetic
-    n = max(2000, int(round(a.points * (SAMPLE_WIDTH / a.width) ** 2)))
-    pts, kw = synthetic.icesat2_tracks(n=n, width=SAMPLE_WIDTH, seed=a.seed)
-    desc = ('%d-point %.0f x %.0f km window of the same track generator and spacings (same point density), full '
-            'edit loop' % (pts['x'].size, SAMPLE_WIDTH / 1e3, SAMPLE_WIDTH / 1e3))
-    return pts, kw, desc
+    if pts is None:
+        pts, kw = synthetic.icesat2_tracks(n=a.points, width=a.width, seed=a.seed)
+    ws = min(a.ref_window, a.width)
+    sel = (np.abs(pts['x']) < ws / 2) & (np.abs(pts['y']) < ws / 2)
+    sub = {k: np.ascontiguousarray(np.asarray(v)[sel]) for k, v in pts.items()}
+    kw = dict(kw)
+    kw['W'] = dict(kw['W'], x=ws, y=ws)
+    n_bias = int(np.unique(sub['rgt'] * 1000 + sub['cycle']).size)
+    desc = ('the %d points of the bench data set inside the centred %.1f x %.1f km window, fitted on that window with the same '
+            'spacings (%d bias columns), full edit loop' % (sub['x'].size, ws / 1e3, ws / 1e3, n_bias))
+    return sub, kw, desc, n_bias
 
 
-def cpu_step(pts, kw):
-    """One pass of the reference path on the CPU: the oracle port (oracle/lssurf_oracle.py).  The only
-    places bench.py executes oracle/ are this baseline leg and --impl reference."""
-    from oracle import lssurf_oracle as O
+def cpu_kind():
+    from oracle import ref_harness
+    return 'reference' if ref_harness.available() else 'port'
+
+
+def cpu_step(pts, kw, kind, n_bias):
+    """One pass of the reference path on the CPU.  kind 'reference': the unmodified reference smooth_fit under stub
+    dependencies (oracle/ref_harness.py; build container only); 'port': the oracle port (oracle/lssurf_oracle.py).
+    The only places bench.py executes oracle/ are this baseline leg and --impl reference."""
     t0 = time.perf_counter()
+    if kind == 'reference':
+        from oracle import ref_harness as H
+        L = H.load()
+        import sparseqr
+        sparseqr.TRAILING_DENSE = n_bias
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            S = L.smooth_fit(data=H.point_data(**pts), VERBOSE=False, **kw)
+        return time.perf_counter() - t0, int(S['data'].size if hasattr(S['data'], 'size') else pts['x'].size)
+    from oracle import lssurf_oracle as O
     res = O.smooth_fit(pts['x'], pts['y'], pts['time'], pts['z'], pts['sigma'], kw['ctr'], kw['W'], kw['spacing'],
                        kw['E_RMS'], reference_epoch=kw['reference_epoch'], max_iterations=kw['max_iterations'],
                        bias_params=[pts['rgt'], pts['cycle']], sigma_corr=pts['sigma_corr'])
     return time.perf_counter() - t0, res['sys']['n_data']
 
 
+CPU_NOTE = ('SuiteSparseQR (not installable here) replaced by SuperLU on the normal equations, bias columns ordered last, + 3 '
+            'refinement steps; SciPy sparse kernels and SuperLU are sequential apart from the BLAS-3 supernode updates, '
+            'which may use `cores` threads')
+
+
+def cpu_threads():
+    """Let the BLAS pools use every host core (torchrun exports OMP_NUM_THREADS=1) and report the limit that is in force."""
+    n = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+        pools = [p.get('num_threads', 1) for p in threadpoolctl.threadpool_info()]
+        return int(max(pools)) if pools else 1
+    except Exception:
+        return 1
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    pts, kw, desc = cpu_sample(a)
-    for _ in range(min(a.warmup, 1)):          # the CPU path has no warm-up effects worth 3 x 12 s
-        cpu_step(pts, kw)
+    cores = cpu_threads()
+    pts, kw, desc, n_bias = cpu_sample(a)
+    kind = cpu_kind()
+    for _ in range(a.warmup):
+        cpu_step(pts, kw, kind, n_bias)
     times = []
     for _ in range(a.steps):
-        dt, n = cpu_step(pts, kw)
+        dt, n = cpu_step(pts, kw, kind, n_bias)
         times.append(dt)
     t = float(np.mean(times))
     val = n / t
+    ws = min(a.ref_window, a.width)
+    cfg = {'workload': 'cfg4 window: %s' % desc, 'points': int(n), 'extent_km': ws / 1e3, 'parallelism': 'host CPU, %d thread(s)' % cores,
+           'sample_of': workload_config(a)['workload'],
+           'note': 'value = points of the sample / seconds per fit of the sample; NOT a time for the full 1e7-point workload '
+                   '(the direct solve grows faster than linearly with the window)'}
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
-            'warmup': min(a.warmup, 1), 'ms_per_step': 1e3 * t, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(a),
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': desc,
-                             'note': 'oracle port of the reference python (SciPy is single-threaded); SuiteSparseQR '
-                                     'replaced by SuperLU on the normal equations + 3 refinement steps'},
+            'warmup': a.warmup, 'ms_per_step': 1e3 * t, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': desc, 'note': CPU_NOTE},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -193,30 +253,30 @@ def run_b200(a):
     if world == 1 and os.environ.get('LSS_SHARD_SINGLE'):       # diagnostics: the row-sharded solver with a local mailbox
         dist_arg = parallel.single_rank_context()
 
-    def fit(inputs, profile, stages=False):
+    def fit(inputs, profile=False, stages=False, history=None):
         D = L.point_data.data().from_dict({f: (inputs[f] if isinstance(inputs[f], torch.Tensor) and inputs[f].is_cuda
                                                else inputs[f].numpy()) for f in fields})
-        return L.smooth_fit(data=D, VERBOSE=False, dist=dist_arg, profile_spmv=profile, time_stages=stages, **kw)
+        return L.smooth_fit(data=D, VERBOSE=False, dist=dist_arg, profile_spmv=profile, time_stages=stages, history=history, **kw)
 
     # ---- warm-up (device-resident steps, plus one host-input step)
     S = None
     for _ in range(a.warmup):
-        S = fit(dev, False)           # held like in the timed loops: the previous result is still alive while the next fit runs
+        S = fit(dev)                  # held like in the timed loops: the previous result is still alive while the next fit runs
     if not a.skip_e2e:
-        S = fit(host, False)
+        S = fit(host)
     barrier()
 
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
-    # ---- value: inputs resident in HBM, device time by CUDA events
+    # ---- value: inputs resident in HBM, device time by CUDA events, no profiling events inside the solver
     launches0 = L._cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pcg = []
     barrier()
     ev0.record()
     for _ in range(a.steps):
-        S = fit(dev, True)
+        S = fit(dev)
         pcg += S['timing']['pcg']
     ev1.record()
     barrier()
@@ -226,92 +286,108 @@ def run_b200(a):
     barrier()
     w0 = time.perf_counter()
     for _ in range(0 if a.skip_e2e else a.steps):
-        S = fit(host, False)
+        S = fit(host)
         _ = float(S['m']['all'].sum())             # the model vector is already host memory (D2H done inside)
     torch.cuda.synchronize()
     t_e2e = max(time.perf_counter() - w0, 1e-9)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    stage_times = None
-    if a.stages:                                   # untimed diagnostic pass: wall time per stage with device syncs
-        Sd = fit(host, False, stages=True)
-        stage_times = {k: round(v, 4) for k, v in Sd['timing']['stages'].items()}
+    # ---- untimed passes: kernel timings (event pairs around every 4th CG iteration), wall time per stage with device syncs
+    Sp = fit(dev, profile=True)
+    prof = Sp['timing']['pcg']
+    barrier()
+    Sd = fit(host, stages=True)
+    stage_times = {k: round(v, 4) for k, v in Sd['timing']['stages'].items()}
+    barrier()
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
         td.all_reduce(t, op=td.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
     d2h = 8 * int(S['m']['all'].size) + n_pts * (1 + 8 + 8)      # m0 + three_sigma_edit, sigma_extra, z_est
 
-    # ---- roofline of the dominant kernel from the solver's own event pairs (this rank's launches)
-    n_apply = sum(p['n_apply'] for p in pcg)
-    ms_a, ms_at = sum(p['ms_A'] for p in pcg), sum(p['ms_At'] for p in pcg)
-    p0 = pcg[0]
-    nnz = p0['nnz']
+    # ---- roofline of the dominant kernel (q = N p) from the solver's own event pairs (this rank's launches)
+    n_apply = sum(p['n_apply'] for p in prof)
+    ms_prod = sum(p['ms_At'] for p in prof) / max(n_apply, 1)
+    ms_vec = sum(p.get('ms_step', 0.) for p in prof) / max(n_apply, 1)
+    p0 = prof[0]
     n_cols = int(S['m']['all'].size)
     peak, peak_src = measured_peak()
+    form = p0.get('form', '')
+    nnzN = p0.get('nnz_N', 0)
+    nnzP = p0.get('nnz_product') or nnzN          # the rows of the eliminated bias block are not part of the CG product
+    rows_P = n_cols - p0.get('eliminated', 0)
     traffic = None
-    prof = os.path.join(ROOT, 'profiles', 'spmv_traffic.json')
-    if os.path.exists(prof):       # ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by operator form
-        traffic = json.load(open(prof)).get(p0.get('form', ''), {}).get('dram_bytes_per_launch')
-    if p0.get('form') == 'explicit_normal':
-        # explicit form: q = N p with the tiled CSR kernel over N = A^T W A: 12 B per non-zero of N, row pointers,
-        # q written and p read once (SURVEY 8(d) formula applied to N).  The two-product CSR form of the same
-        # operator (what SURVEY 8(d) budgets per CG iteration) is reported alongside for comparison.
-        nnzN = p0['nnz_N']
-        nnzP = p0.get('nnz_product') or nnzN          # the rows of the eliminated bias block are not part of the CG product
-        b_dom = spmv_bytes(n_cols - p0.get('eliminated', 0), n_cols, nnzP, False)
-        ms_dom = ms_at / max(n_apply, 1)
-        ach = b_dom / (ms_dom / 1e3) / 1e9 if ms_dom > 0 else 0.0
-        b_two = spmv_bytes(p0['rows'], n_cols, nnz, True) + spmv_bytes(n_cols, p0['rows'], nnz, False)
-        roofline = {'bound': 'hbm', 'kernel': 'lss::spmv_persistent_kernel<128,8,false,true> on the explicit normal matrix (q = N p, N = A^T W A; one launch, '
-                              'atomic carries, p.q by-product)',
-                    'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peak_src,
-                    'traffic': traffic, 'bytes_per_launch': {'N': b_dom}, 'launch_ms': {'N': ms_dom},
-                    'launch_ms_samples': n_apply, 'launch_ms_sampling': 'CUDA event pairs on the solver stream around every 4th CG iteration of the timed steps',
-                    'nnz_N': nnzN, 'nnz_streamed_per_product': nnzP, 'nnz_A': nnz,
-                    'csr_pair_equivalent': {'bytes': b_two, 'gbs': b_two / (ms_dom / 1e3) / 1e9 if ms_dom > 0 else None,
-                                            'note': 'bytes the A / A^T two-product form of the same operator would stream, '
-                                                    'divided by the time of the N product (not a bandwidth claim)'},
-                    'frac_of_nominal_8TBs': ach / 8000.0}
-    elif p0.get('fused'):
-        # block form: ONE pass over the ELL copy of G does q += G^T (w .* (G p)): 12 B per entry, the row weights,
-        # x read once and q read-modify-written once (compulsory); the constraint pair (C, C^T) is the small rest
-        if p0.get('all_ell'):      # constraint rows ride in the same ELL block: one kernel per operator application
-            b_dom = 12 * (p0['nnz_G'] + p0['nnz_C']) + 8 * (p0['n_data'] + p0['n_con']) + 24 * n_cols
-            b_con = 0
-        else:
-            b_dom = 12 * p0['nnz_G'] + 8 * p0['n_data'] + 24 * n_cols
-            b_con = spmv_bytes(p0['n_con'], n_cols, p0['nnz_C'], True) + spmv_bytes(n_cols, p0['n_con'], p0['nnz_C'], False)
-        ms_dom, ms_con = ms_at / n_apply, ms_a / n_apply
-        ach = b_dom / (ms_dom / 1e3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'lss::ell_normal_kernel<13,0> (fused q += A^T (w .* (A p)), one pass over the ELL rows)',
-                    'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peak_src,
-                    'traffic': traffic, 'bytes_per_launch': {'fused_G': b_dom, 'C_and_Ct': b_con},
-                    'launch_ms': {'fused_G': ms_dom, 'C_and_Ct': ms_con},
-                    'gbs': {'fused_G': ach, 'C_and_Ct': b_con / (ms_con / 1e3) / 1e9 if ms_con > 0 else None},
-                    'frac_of_nominal_8TBs': ach / 8000.0}
+    tfile = os.path.join(ROOT, 'profiles', 'spmv_traffic.json')
+    if form != 'explicit_normal':
+        raise SystemExit('bench.py: the workload is expected to run on the explicit normal matrix, got form %r' % form)
+    if p0.get('structured_bytes'):
+        kern = ('lss::sn_product_kernel<21>: q = N p from the grid-structured layout of N (TMA-pipelined node blocks and z0-dz pair '
+                'records, z0-z0 diagonals, flat remainder; one launch)')
+        b_dom = int(p0['structured_bytes'])
+        b_note = 'bytes of the structured layout one product streams (lssurf_b200/structured.py product_bytes): values 8 B, tables, flat remainder 16 B / entry, q and p once'
+        tkey = 'structured_normal'
     else:
-        rows_loc = p0['rows']
-        b_a = spmv_bytes(rows_loc, n_cols, nnz, True)
-        b_at = spmv_bytes(n_cols, rows_loc, nnz, False)
-        ach = (b_a + b_at) * n_apply / ((ms_a + ms_at) / 1e3) / 1e9 if (ms_a + ms_at) > 0 else None
-        roofline = {'bound': 'hbm', 'kernel': 'lss::spmv_persistent_kernel (y = w.*(A p) and q = A^T u)', 'achieved': ach, 'peak': peak,
-                    'unit': 'GB/s', 'frac': None if ach is None else ach / peak, 'peak_source': peak_src, 'traffic': traffic,
-                    'bytes_per_launch': {'A': b_a, 'At': b_at}, 'launch_ms': {'A': ms_a / n_apply, 'At': ms_at / n_apply},
-                    'gbs': {'A': b_a / (ms_a / n_apply / 1e3) / 1e9, 'At': b_at / (ms_at / n_apply / 1e3) / 1e9},
-                    'frac_of_nominal_8TBs': None if ach is None else ach / 8000.0}
+        if world > 1:
+            rows_P = max(rows_P // world, 1)       # this rank's rows of N (dz-node blocks split evenly)
+        kern = ('lss::spmv_persistent_kernel<128,8,false,true> on the explicit normal matrix (q = N p, N = A^T W A; one launch, '
+                'atomic carries, p.q by-product)' + ('; this rank\'s rows only' if world > 1 else ''))
+        b_dom = spmv_bytes(rows_P, n_cols, nnzP, False)
+        b_note = 'SURVEY 8(d) CSR formula applied to the rows of N one launch covers: 12 nnz + 4 (rows + 1) + 8 rows + 8 cols'
+        tkey = 'explicit_normal'
+    if os.path.exists(tfile):       # ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by kernel
+        traffic = json.load(open(tfile)).get(tkey if world == 1 else '', {}).get('dram_bytes_per_launch')
+    ach = b_dom / (ms_prod / 1e3) / 1e9 if ms_prod > 0 else 0.0
     outer = len(pcg) / a.steps
     iters = sum(p['iterations'] for p in pcg) / a.steps
     solve_ms = sum(p['ms'] for p in pcg) / a.steps
+    solve = {'outer_iterations': outer, 'cg_iterations_per_step': iters, 'pcg_ms_per_step': solve_ms,
+             'ms_per_cg_iteration': solve_ms / max(iters, 1), 'ms_product_per_iteration': ms_prod,
+             'ms_vector_step_per_iteration': ms_vec,
+             'preconditioner': {'blocks': p0.get('precond_blocks', 0), 'eliminated_columns': p0.get('eliminated', 0),
+                                'coarse_unknowns': p0.get('coarse', 0)},
+             'cg_rtol': kw.get('cg_rtol', 1e-12), 'in_TSE': int(np.sum(S['data'].three_sigma_edit)), 'unknowns': n_cols,
+             'nnz_A_per_rank': p0['nnz'], 'cg_iterations': [p['iterations'] for p in pcg[:int(outer)]],
+             'converged': all(p.get('converged', True) for p in pcg)}
+    roofline = {'bound': 'hbm', 'kernel': kern, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_source': peak_src,
+                'traffic': traffic, 'bytes_per_launch': b_dom, 'bytes_definition': b_note, 'launch_ms': ms_prod,
+                'launch_ms_samples': n_apply,
+                'launch_ms_sampling': 'CUDA event pairs on the solver stream around every 4th CG iteration of one untimed profiling step',
+                'nnz_N': nnzN, 'nnz_streamed_per_product': nnzP, 'frac_of_nominal_8TBs': ach / 8000.0,
+                'csr_equivalent': {'bytes': spmv_bytes(rows_P, n_cols, nnzP, False),
+                                   'gbs': spmv_bytes(rows_P, n_cols, nnzP, False) / (ms_prod / 1e3) / 1e9 if ms_prod > 0 else None,
+                                   'note': 'bytes of the same rows of N as CSR divided by the launch time (equals achieved for the CSR kernel)'},
+                'solve': solve, 'stages_s': stage_times}
+
+    # ---- untimed bench-scale parity record: default form vs the deterministic CSR-pair form (A and A^T as CSR, Jacobi) on the
+    # same points -- masks after every outer iteration, model, points close to the 3-sigma threshold
+    parity = None
+    if rank == 0 and world == 1 and not a.no_parity:
+        h0, h1 = [], []
+        Sa = fit(dev, history=h0)
+        os.environ['LSS_NO_FUSED'] = '1'
+        try:
+            Sb = fit(dev, history=h1)
+        finally:
+            os.environ.pop('LSS_NO_FUSED', None)
+        ma, mb = Sa['m']['all'], Sb['m']['all']
+        parity = {'against': 'generic CSR-pair solver form (LSS_NO_FUSED=1: two deterministic CSR products per iteration, Jacobi) on the same 1e7 points',
+                  'form_b': Sb['timing']['pcg'][0].get('form'),
+                  'masks_identical_per_iteration': bool(len(h0) == len(h1) and all(np.array_equal(x['mask_out'], y['mask_out']) for x, y in zip(h0, h1))),
+                  'final_mask_identical': bool(np.array_equal(Sa['data'].three_sigma_edit, Sb['data'].three_sigma_edit)),
+                  'rel_l2_m0': float(np.linalg.norm(ma - mb) / np.linalg.norm(mb)),
+                  'near_threshold': [int(v) for v in Sa['timing'].get('near_threshold', [])],
+                  'near_threshold_definition': 'points whose scaled residual lies within 1e-6 of the 3-sigma threshold, per outer iteration',
+                  'cg_iterations': [[h['pcg']['iterations'] for h in hh] for hh in (h0, h1)]}
+        roofline['parity'] = parity
 
     cpu = None
     if rank == 0 and a.gpus == 1 and not a.no_cpu_baseline:
-        cp, ckw, desc = cpu_sample(a)
-        dt, n = cpu_step(cp, ckw)
-        cpu = {'value': n / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': desc, 'seconds': dt,
-               'host_cores_available': os.cpu_count(),
-               'note': 'oracle port of the reference python; SciPy sparse + SuperLU are single-threaded; SuiteSparseQR '
-                       'replaced by SuperLU on the normal equations + 3 refinement steps'}
+        cores = cpu_threads()
+        cp, ckw, desc, n_bias = cpu_sample(a, pts, kw)
+        kind = cpu_kind()
+        dt, n = cpu_step(cp, ckw, kind, n_bias)
+        cpu = {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': desc, 'seconds': dt,
+               'host_cores_available': os.cpu_count(), 'note': CPU_NOTE}
     if rank == 0:
         line = {'metric': METRIC, 'value': n_pts * a.steps / t_dev, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': 1e3 * t_dev / a.steps, 'higher_is_better': True, 'scaling': 'strong',
@@ -319,14 +395,7 @@ def run_b200(a):
                 'e2e': {'value': n_pts * a.steps / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': 1e3 * t_e2e / a.steps},
                 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
-                'solve': {'outer_iterations': outer, 'cg_iterations_per_step': iters, 'pcg_ms_per_step': solve_ms,
-                          'ms_per_cg_iteration': solve_ms / max(iters, 1),
-                          'ms_product_per_iteration': ms_at / max(n_apply, 1), 'ms_vector_step_per_iteration': sum(p.get('ms_step', 0.) for p in pcg) / max(n_apply, 1),
-                          'preconditioner': {'blocks': p0.get('precond_blocks', 0), 'eliminated_columns': p0.get('eliminated', 0)},
-                          'cg_rtol': kw.get('cg_rtol', 1e-12),
-                          'in_TSE': int(np.sum(S['data'].three_sigma_edit)), 'unknowns': n_cols, 'nnz_A_per_rank': nnz,
-                          'cg_iterations': [p['iterations'] for p in pcg[:int(outer)]]},
-                'stages_s': stage_times}
+                'solve': solve, 'stages_s': stage_times, 'parity': parity}
         print(json.dumps(line), flush=True)
     dist.destroy()
     if world > 1:

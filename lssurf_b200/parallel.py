@@ -109,6 +109,14 @@ class DistContext(object):
         _cabi.check(_cabi.lib().lss_comm_allreduce_f64(self.comm, _cabi.ptr(t), int(t.numel()), _cabi.stream()))
         return t
 
+    def allreduce_min(self, t):
+        """Minimum over ranks of a small fp64 CUDA tensor (sum all-reduce of one slot per rank)."""
+        if self.world == 1:
+            return t
+        slots = torch.zeros((self.world,) + tuple(t.shape), dtype=torch.float64, device=t.device)
+        slots[self.rank] = t
+        return self.allreduce_sum(slots).amin(dim=0)
+
     def ensure_box(self, nbytes):
         """Peer-to-peer mailbox of at least nbytes on every rank (``lss_comm_box_*``): allocated once per communicator,
         CUDA IPC handles exchanged through torch.distributed (host transport), mapped into every rank."""

@@ -16,6 +16,7 @@ keywords (defaults keep existing calls unchanged): ``cg_rtol``, ``cg_maxiter``, 
 ``parallel.DistContext`` for row-sharded multi-GPU solves), ``profile_spmv``.
 """
 import os
+import warnings
 from time import time, ctime
 
 import numpy as np
@@ -117,10 +118,13 @@ def _edit_by_bias(data, m0, in_TSE_d, iteration, bias_model, args):
     return not np.all(bpd['edited'] == before)
 
 
-def _value_set(mask):
-    """Distinct values of a 0/1 mask (what np.setxor1d sees when handed boolean arrays)."""
-    has_one, all_one = bool(mask.any().item()), bool(mask.all().item())
-    return ({1} if has_one else set()) | (set() if all_one else {0})
+def _value_set(mask, dist=None):
+    """Distinct values of a 0/1 mask (what np.setxor1d sees when handed boolean arrays); over all ranks with ``dist``."""
+    n_one, n_all = float(mask.sum().item()), float(mask.numel())
+    if dist is not None:
+        tot = dist.allreduce_sum(torch.tensor([n_one, n_all], dtype=torch.float64, device=mask.device))
+        n_one, n_all = float(tot[0].item()), float(tot[1].item())
+    return ({1} if n_one > 0 else set()) | (set() if n_one == n_all else {0})
 
 
 def iterate_fit(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing, args, grids,
@@ -280,7 +284,15 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
             dist.broadcast(x, src=0)          # every rank continues from rank 0's bits
         m0 = x.cpu().numpy().copy()
         timing['sparseqr_solve'] = time() - tic
-        stats.append(dict(solver.last, iteration=iteration, wall_s=timing['sparseqr_solve']))
+        last = solver.last
+        last['converged'] = bool(np.isfinite(last['relres']) and last['relres'] <= args['cg_rtol'] and last['iterations'] < args['cg_maxiter'])
+        if not np.isfinite(last['relres']):
+            raise _cabi.LssError('smooth_fit: the PCG solve of outer iteration %d broke down (residual is not finite)' % iteration)
+        if not last['converged']:
+            # the reference's direct QR solve cannot stall; say so instead of feeding an unconverged model into the edit loop silently
+            warnings.warn('smooth_fit: PCG stopped at %d iterations with relative residual %.2e > cg_rtol %.1e (outer iteration %d)'
+                          % (last['iterations'], last['relres'], args['cg_rtol'], iteration), RuntimeWarning)
+        stats.append(dict(last, iteration=iteration, wall_s=timing['sparseqr_solve']))
         if args['VERBOSE']:
             print('\tpcg: %d iterations, relres=%.2e, %.1f ms' % (solver.last['iterations'], solver.last['relres'],
                                                                   solver.last['ms']), flush=True)
@@ -317,9 +329,14 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
             in_TSE_d = torch.where(editable, in_TSE_d, in_TSE_original)
             recount = True
         if recount:
+            # counted over ALL ranks: the loop control below must take the same decisions everywhere
             sel = in_TSE_d.bool()
-            est['count'] = int(sel.sum().item())
-            est['min_sigma'] = float(sigma[sel].min().item()) if est['count'] else np.inf
+            cnt = sel.sum().to(f64).reshape(1)
+            mn = (sigma[sel].min() if bool(sel.any().item()) else torch.tensor(np.inf, dtype=f64, device=dev)).reshape(1)
+            if multi:
+                cnt, mn = dist.allreduce_sum(cnt), dist.allreduce_min(mn)
+            est['count'] = int(cnt.item())
+            est['min_sigma'] = float(mn.item()) if est['count'] else np.inf
             if args.get('history') is not None:  # the mask that goes into the next solve (after bias editing / `editable`)
                 args['history'][-1]['mask_next'] = np.packbits(in_TSE_d.cpu().numpy())
         if est['count'] == 0:
@@ -341,16 +358,20 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
                     print(f'\t sigma_extra for {key} : {se_values.get(key, 0.):3.4f}', flush=True)
         if iteration > 0 and iteration > args['bias_nsigma_iteration']:
             # the reference applies setxor1d to the boolean masks as value sets (smooth_fit.py:196)
-            vals_last = _value_set(in_TSE_last)
-            vals_now = _value_set(in_TSE_d)
+            vals_last = _value_set(in_TSE_last, dist if multi else None)
+            vals_now = _value_set(in_TSE_d, dist if multi else None)
             n_editable = int(np.sum(data.editable)) if 'editable' in data.fields else data.size
+            if multi:
+                n_editable = int(dist.allreduce_sum(torch.tensor([float(n_editable)], dtype=f64, device=dev)).item())
             if len(vals_last ^ vals_now) / n_editable < args['converge_tol_frac_TSE']:
                 if args['VERBOSE']:
                     print("filtering unchanged with tolerance %3.5f, will exit after iteration %d"
                           % (args['converge_tol_frac_TSE'], iteration + 1))
                 last_iteration = True
         if iteration >= np.maximum(args['min_iterations'], args['bias_nsigma_iteration'] + 1):
-            se_max = max(se_values.values()) if se_values else 0.
+            # the reference tests every point: np.all(sigma_extra < 0.5 * min(sigma[in_TSE])) (smooth_fit.py:203)
+            se_top = sigma_extra.max().reshape(1) if sigma_extra.numel() else torch.zeros(1, dtype=f64, device=dev)
+            se_max = -float(dist.allreduce_min(-se_top).item()) if multi else float(se_top.item())
             if se_max < 0.5 * est['min_sigma'] and not bias_editing_changed:
                 if args['VERBOSE']:
                     print("sigma_extra is small, performing one additional iteration", flush=True)
@@ -446,7 +467,11 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
     # chi^2 and RMS of the edited-in data residuals (smooth_fit.py:676-678)
     tot = torch.stack([(rs * rs).sum(), (r_in * r_in).sum(), tse.sum().to(torch.float64)])
     tot = (tot if dist is None else dist.allreduce_sum(tot)).cpu().numpy()
-    R['data'] = tot[0] if not args['sigma_extra_relax'] else float(((r_in / f['sigma']) ** 2).sum().item())
+    if args['sigma_extra_relax']:        # chi^2 against the unrelaxed errors (smooth_fit.py:676)
+        raw = ((r_in / f['sigma']) ** 2).sum().reshape(1)
+        R['data'] = float((raw if dist is None else dist.allreduce_sum(raw)).item())
+    else:
+        R['data'] = tot[0]
     RMS['data'] = np.sqrt(tot[1] / tot[2]) if tot[2] > 0 else np.nan
 
 
@@ -497,6 +522,36 @@ def _assign_bias_ID_device(fields_d, bias_params, sigma_corr_d):
         model['bias_ID_dict'][k] = {p: shown[j] for j, p in enumerate(bias_params)}
         model['E_bias'][k] = e_bias[k]
     return ids, model
+
+
+def _validate_by_dz_mask_device(grids, y_d, x_d, t_d):
+    """validate_by_dz_mask (grid_functions.py:346-374) on device arrays: the dz mask (2-D, or mask_3d) interpolated to the
+    points must exceed 0.5.  Returns a bool tensor (True: keep) or None when the mask is all True (every point passes: the
+    interpolation weights of a point sum to 1).  The interpolated value is summed in ascending column order like the CSR
+    product of the reference."""
+    dz = grids['dz']
+    m3 = getattr(dz, 'mask_3d', None)
+    if m3 is not None:
+        mask, pts, bds, delta = np.asarray(getattr(m3, 'z', m3)), [y_d, x_d, t_d], dz.bds, dz.delta
+    else:
+        mask = np.asarray(dz.mask)
+        if mask.ndim == 2:
+            pts, bds, delta = [y_d, x_d], dz.bds[0:2], dz.delta[0:2]
+        else:
+            pts, bds, delta = [y_d, x_d, t_d], dz.bds, dz.delta
+    if mask.all():
+        return None
+    from .fd_grid import fd_grid
+    tmp = fd_grid(bds, delta)
+    _, cols, vals, _, _ = _cabi.interp_coo(tmp.as_struct(), pts)
+    mask_d = _cabi.to_dev(mask.ravel().astype(np.float64), torch.float64)
+    cols, order = torch.sort(cols.long(), dim=1)
+    vals = torch.gather(vals, 1, order)
+    acc = torch.zeros(cols.shape[0], dtype=torch.float64, device=vals.device)
+    for k in range(cols.shape[1]):
+        acc = acc + vals[:, k] * mask_d[cols[:, k]]
+    acc = torch.where(torch.isfinite(acc), acc, torch.zeros_like(acc))
+    return acc > 0.5
 
 
 def _shard_plan(grids, cell_ids, dist):
@@ -561,8 +616,11 @@ def smooth_fit(**kwargs):
     rz = _cabi.interp_coo(grids['z0'].as_struct(), [y_d, x_d])
     rd = _cabi.interp_coo(grids['dz'].as_struct(), [y_d, x_d, t_d])
     finite = torch.isfinite(z_d)
-    if rz[4] or rd[4] or not bool(finite.all().item()):
+    in_mask = _validate_by_dz_mask_device(grids, y_d, x_d, t_d)        # points under a masked-out part of the dz grid are dropped
+    if rz[4] or rd[4] or in_mask is not None or not bool(finite.all().item()):
         keep = finite & rz[3].bool() & rd[3].bool()
+        if in_mask is not None:
+            keep = keep & in_mask
         valid_data = keep.cpu().numpy()
         if not np.any(valid_data):
             if verbose:

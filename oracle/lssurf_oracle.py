@@ -336,16 +336,46 @@ def sigma_extra(r, sigma, mask, groups=None):
 # least-squares solve: stand-in for sparseqr.solve (LSsurf/smooth_fit.py:142)
 # --------------------------------------------------------------------------------------------
 
-def solve_least_squares(A, b, dense_max=3000, refine=3):
+def factor_normal(N, trailing=0):
+    """Sparse LU of the SPD normal matrix N = A^T A with a fill-reducing order chosen for the fit's structure
+    (with bias_params the bias columns must come last, else SuperLU's fill explodes):
+    the last `trailing` columns (per-(rgt, cycle) biases: each touches every grid node under its track) stay last, the
+    grid part is ordered by minimum degree (taken from a throw-away factorisation of the grid block alone, which is
+    cheap); no pivoting (N is symmetric positive definite).  Returns (lu, perm): ``x[perm] = lu.solve(rhs[perm])``."""
+    N = sp.csc_matrix(N)
+    n = N.shape[0]
+    opts = dict(diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    if trailing <= 0 or trailing >= n:
+        lu = spl.splu(N, permc_spec='MMD_AT_PLUS_A', **opts)
+        return lu, np.arange(n)
+    ng = n - trailing
+    pg = spl.splu(N[:ng][:, :ng].tocsc(), permc_spec='MMD_AT_PLUS_A', **opts).perm_c
+    perm = np.concatenate([np.argsort(pg), np.arange(ng, n)])
+    lu = spl.splu(N[perm][:, perm].tocsc(), permc_spec='NATURAL', **opts)
+    return lu, perm
+
+
+def solve_least_squares(A, b, dense_max=3000, refine=3, info=None, trailing=0):
+    """Stand-in for sparseqr.solve (LSsurf/smooth_fit.py:142; SuiteSparseQR is not installable here): the unique
+    least-squares solution of the full-column-rank system.  Small systems: dense lstsq (gold).  Otherwise SuperLU on the
+    normal equations + `refine` steps of iterative refinement with the residual formed through A."""
     A = sp.csr_matrix(A)
     b = np.asarray(b, dtype=float).ravel()
     if A.shape[1] <= dense_max:
         return np.linalg.lstsq(A.toarray(), b, rcond=None)[0]
     At = A.T.tocsr()
-    lu = spl.splu((At @ A).tocsc())
-    x = lu.solve(At @ b)
+    lu, perm = factor_normal(At @ A, trailing)
+
+    def apply(r):
+        x = np.empty_like(r)
+        x[perm] = lu.solve(r[perm])
+        return x
+    x = apply(At @ b)
     for _ in range(refine):
-        x = x + lu.solve(At @ (b - A @ x))
+        x = x + apply(At @ (b - A @ x))
+    if info is not None:
+        info.update(method='splu(AtA, minimum degree on the grid block, %d bias columns last) + %d refinements' % (trailing, refine),
+                    fill=int(lu.L.nnz + lu.U.nnz))
     return x
 
 
@@ -491,7 +521,8 @@ def iterate(sys_, max_iterations=10, min_iterations=2, converge_tol_dz=0.05, sig
     Returns m0 (full column space, reference epoch = 0), sigma_extra, in_TSE, rs_data.
     """
     if solver is None:
-        solver = solve_least_squares
+        nb = sys_['bias']['n'] if sys_.get('bias') else 0          # bias columns are the last kept columns
+        solver = (lambda A, b: solve_least_squares(A, b, trailing=nb)) if nb else solve_least_squares
     G = csr_matrix(*sys_['G'][:3], shape=(sys_['n_data'], sys_['col_N']))
     C = csr_matrix(*sys_['C'][:3], shape=(sys_['Ec'].size, sys_['col_N']))
     keep = sys_['keep_cols']

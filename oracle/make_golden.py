@@ -33,7 +33,7 @@ from oracle import ref_harness as H        # noqa: E402
 from lssurf_b200 import synthetic as S     # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable']
+WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable', 'uniform_masked']
 
 
 def digest(*arrays):
@@ -72,6 +72,53 @@ def run_reference(pts, kw):
     finally:
         SF.calc_sigma_extra = orig
     return fo, out, trace
+
+
+def parse_model_outputs(out):
+    """What parse_model adds to the result (smooth_fit.py:276-352, 676-678; bias_functions.py:140-155): per-node data
+    counts and misfits on both grids, chi^2 / RMS per constraint family and for the data, per-bias residual statistics."""
+    fx = {}
+    for g in ('z0', 'dz'):
+        for key in ('count', 'misfit_rms', 'misfit_scaled_rms'):
+            fx[f'pm_{g}_{key}'] = np.asarray(getattr(out['m'][g], key), dtype=float)
+        fx[f'pm_{g}_cell_area'] = np.asarray(out['m'][g].cell_area, dtype=float)
+        fx[f'pm_{g}_mask'] = np.asarray(out['m'][g].mask, dtype=bool)
+    fx['pm_R'] = np.array([f'{k}:{float(v)!r}' for k, v in out['R'].items()])
+    fx['pm_RMS'] = np.array([f'{k}:{float(v)!r}' for k, v in out['RMS'].items()])
+    b = out['m'].get('bias')
+    if b:
+        for key in ('val', 'expected', 'rms_data_raw', 'rms_data_edited', 'N_raw', 'N_edited'):
+            if key in b:
+                fx['pm_bias_' + key] = np.asarray(b[key], dtype=float)
+    return fx
+
+
+def with_masks(SF, masks):
+    """Context manager: the reference's setup_grids with NumPy masks put on the z0 / dz grids the way its own mask
+    branch leaves them (grid_functions.py:72-133: masks on the grids, dz cell areas summed from the masked z0 cells,
+    z0 cell areas masked last) -- the stub pointCollection cannot interpolate mask grids, everything downstream
+    (validate_by_dz_mask, mask_for_ind0 with mask_scale, cell areas) is the unmodified reference."""
+    import contextlib
+    GF = sys.modules['LSsurf.grid_functions']
+
+    @contextlib.contextmanager
+    def ctx():
+        orig = SF.setup_grids
+
+        def patched(args):
+            grids, bds = orig(args)
+            grids['z0'].mask = masks['z0'].astype(bool)
+            grids['dz'].mask = masks['dz'].astype(bool)
+            grids['z0'].cell_area = GF.calc_cell_area(grids['z0'])
+            grids['dz'].cell_area = GF.sum_cell_area(grids['z0'], grids['dz'])
+            grids['z0'].cell_area *= grids['z0'].mask
+            return grids, bds
+        SF.setup_grids = patched
+        try:
+            yield
+        finally:
+            SF.setup_grids = orig
+    return ctx() if masks is not None else contextlib.nullcontext()
 
 
 def case_fit(name, pts, kw, write):
@@ -119,6 +166,7 @@ def case_fit(name, pts, kw, write):
                   sigma_extra=np.array(sig_x), masks=np.array(masks), n_outer=len(hist),
                   near_threshold=np.array(n_close), kw=repr(kw),
                   toc_rows=np.array([f'{k}:{len(np.unique(v))}' for k, v in fo['Gc'].TOC['rows'].items()]))
+        fx.update(parse_model_outputs(out))
         fx.update({'in_' + k: v for k, v in pts.items()})
         np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **fx)
 
@@ -225,7 +273,9 @@ def case_widened(name, pts, kw, write):
     import sparseqr
     SF = H.smooth_fit_module()
     D = H.point_data(**pts)
-    with warnings.catch_warnings():
+    kw = dict(kw)
+    grid_masks = kw.pop('mask_data', None)         # NumPy masks: injected into the reference's grids (with_masks)
+    with warnings.catch_warnings(), with_masks(SF, grid_masks):
         warnings.simplefilter('ignore')
         fo = L.smooth_fit(data=D.copy(), VERBOSE=False, return_fit_objects=True, **kw)
     G_ref, C_ref = fo['G_data'].toCSR(), fo['Gc'].toCSR()
@@ -247,7 +297,7 @@ def case_widened(name, pts, kw, write):
         return orig_solve(*a, **k)
     SF.calc_sigma_extra, SF.calc_sigma_extra_on_grid, sparseqr.solve = tap, tap_grid, count_solve
     try:
-        with warnings.catch_warnings():
+        with warnings.catch_warnings(), with_masks(SF, grid_masks):
             warnings.simplefilter('ignore')
             out = L.smooth_fit(data=D.copy(), VERBOSE=False, **kw)
     finally:
@@ -274,6 +324,10 @@ def case_widened(name, pts, kw, write):
                 fx['avgop_' + key] = np.asarray(getattr(g, key), dtype=float)
                 if getattr(g, 'cell_area', None) is not None:
                     fx['avgarea_' + key] = np.asarray(g.cell_area, dtype=float)
+        fx.update(parse_model_outputs(out))
+        fx['valid_data'] = np.packbits(np.asarray(out['valid_data'], dtype=bool))
+        if grid_masks is not None:
+            fx['mask_z0'], fx['mask_dz'] = grid_masks['z0'].astype(bool), grid_masks['dz'].astype(bool)
         sb = out['m'].get('slope_bias', {})
         if sb:
             fx['slope_bias'] = np.array([[k, v['slope_x'], v['slope_y']] for k, v in sb.items()], dtype=float)
@@ -312,7 +366,17 @@ def widened_inputs():
     pte['editable'] = (rng.random(grp.size) < 0.9).astype(float)
     pte['three_sigma_edit'] = (rng.random(grp.size) < 0.98).astype(float)
     kw_e = dict(kwe, sigma_extra_keys={'quiet': {'sensor': [0.]}, 'noisy': {'sensor': [1.]}})
-    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e)
+    # masks with holes on both grids: points under the dz hole are dropped (validate_by_dz_mask),
+    # constraint rows centred outside the masks are loosened by mask_scale (mask_for_ind0), cell areas follow the masks
+    ptf, kwf = S.uniform_3d(n=6000, width=1.2e4, seed=12)
+    gz = (int(1.2e4 / kwf['spacing']['z0']) + 1,) * 2
+    gd = (int(1.2e4 / kwf['spacing']['dz']) + 1,) * 2
+    mz, md = np.ones(gz, dtype=bool), np.ones(gd, dtype=bool)
+    mz[3:9, 14:21] = False                                  # a lake in the z0 grid
+    mz[:, :2] = False                                       # and a strip along its western edge
+    md[8:, 9:] = False                                      # the north-east corner of the dz grid
+    kw_f = dict(kwf, mask_data={'z0': mz, 'dz': md}, mask_scale={0: 10, 1: 1}, dzdt_lags=[1], max_iterations=4)
+    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e), (ptf, kw_f)
 
 
 def grid_bias_inputs():

@@ -10,6 +10,7 @@ import scipy.sparse.linalg as spl
 
 DENSE_MAX = 3000
 LAST = {}
+TRAILING_DENSE = 0      # set by the harness: number of trailing bias columns (kept last in the factorisation)
 
 
 def solve(A, b, tolerance=None):
@@ -19,13 +20,13 @@ def solve(A, b, tolerance=None):
         x = np.linalg.lstsq(A.toarray(), b, rcond=None)[0]
         LAST['method'] = 'dense lstsq'
         return x
-    At = A.T.tocsr()
-    N = (At @ A).tocsc()
-    lu = spl.splu(N)
-    x = lu.solve(At @ b)
-    for _ in range(3):
-        x = x + lu.solve(At @ (b - A @ x))
-    LAST['method'] = 'splu(AtA)+3 refinements'
+    # same factorisation as the oracle (oracle/lssurf_oracle.py factor_normal: dense bias columns last, RCM on the grid part)
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle.lssurf_oracle import solve_least_squares
+    info = {}
+    x = solve_least_squares(A, b, dense_max=DENSE_MAX, refine=3, info=info, trailing=TRAILING_DENSE)
+    LAST.update(info)
     return x
 
 

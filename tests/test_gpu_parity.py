@@ -9,7 +9,7 @@ import scipy.sparse as sp
 import torch
 
 from oracle import lssurf_oracle as O
-from tests.util import FIT_CASES, GOLDEN, csr_digest, digest, load_case, rel_l2
+from tests.util import FIT_CASES, GOLDEN, check_parse_model_outputs, csr_digest, digest, load_case, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -331,6 +331,7 @@ def test_smooth_fit_against_reference_fixture(L, name):
                                                          indexing='ij'), kw['reference_epoch'] + np.zeros(S['grids']['dz'].shape[:2], dtype=int)])
     assert np.all(S['m']['all'][ref_cols.ravel()] == 0.0)    # reference epoch held at exactly zero
     assert S['valid_data'].sum() == int(np.unpackbits(fx['in_TSE'])[:int(fx['n_data'])].sum())
+    check_parse_model_outputs(fx, S)                         # counts, misfits, R / RMS, per-bias statistics
 
 
 def test_smooth_fit_medium_against_oracle(L):

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from tests.test_host_double import check_widened_outputs
-from tests.util import WIDENED_CASES, csr_digest, digest, load_case, rel_l2
+from tests.util import check_parse_model_outputs, WIDENED_CASES, csr_digest, digest, load_case, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -66,6 +66,7 @@ def test_widened_fit_against_reference_fixture(L, name):
     assert rel_l2(S['m']['all'], fx['m0']) < 1e-6            # north-star tolerance
     assert np.max(np.abs(S['data'].z_est - fx['z_est'])) < 1e-5
     check_widened_outputs(fx, S)
+    check_parse_model_outputs(fx, S)
 
 
 def test_calc_sigma_extra_on_grid_numpy_api(L):

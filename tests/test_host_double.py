@@ -9,7 +9,7 @@ import pytest
 
 import lssurf_b200 as L
 from tests import host_double
-from tests.util import FIT_CASES, GOLDEN, WIDENED_CASES, csr_digest, digest, load_case, rel_l2
+from tests.util import FIT_CASES, GOLDEN, WIDENED_CASES, check_parse_model_outputs, csr_digest, digest, load_case, rel_l2
 
 
 @pytest.fixture()
@@ -42,6 +42,7 @@ def test_host_logic_against_reference_fixture(double, name):
     assert np.max(np.abs(S['data'].z_est - fx['z_est'])) < 1e-6
     assert S['m']['z0'].z0.shape == tuple(S['grids']['z0'].shape)
     check_widened_outputs(fx, S)
+    check_parse_model_outputs(fx, S)
 
 
 def check_widened_outputs(fx, S):
