@@ -14,6 +14,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <cmath>
+
 #include "common.cuh"
 
 namespace lss {
@@ -443,6 +445,40 @@ static int rde_eval(RdeWork &wk, const double *r, const double *sigma, const uns
     return LSS_OK;
 }
 
+// min / max of sigma over the selected points with a finite residual (out[0] = min, out[1] = max; initialised to +-inf)
+__global__ void __launch_bounds__(SEL_BLOCK)
+sigma_range_kernel(const double *__restrict__ r, const double *__restrict__ sigma, const unsigned char *__restrict__ mask, int64_t n,
+                   double *__restrict__ out) {
+    double lo = INFINITY, hi = -INFINITY;
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * SEL_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * SEL_BLOCK) {
+        if (mask && !mask[i]) continue;
+        if (!isfinite(r[i])) continue;
+        const double sg = sigma[i];
+        if (!(sg == sg)) bad = true;
+        lo = fmin(lo, sg);
+        hi = fmax(hi, sg);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (__any_sync(0xffffffffu, bad)) { lo = -INFINITY; hi = INFINITY; }      // a NaN sigma: never "constant"
+    if (lane_id() == 0) {
+        // fp64 min / max through the ordered integer image of the value
+        atomicMin(reinterpret_cast<unsigned long long *>(out), f64_key(lo));
+        atomicMax(reinterpret_cast<unsigned long long *>(out) + 1, f64_key(hi));
+    }
+}
+
+static double host_key_f64(unsigned long long k) {
+    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double v;
+    memcpy(&v, &u, sizeof(v));
+    return v;
+}
+
 // libm pow through a volatile exponent: NumPy evaluates scalar `x**2` with pow(), which is not always
 // the correctly rounded x*x; the compiler must not fold it.
 static double py_square(double x) {
@@ -479,10 +515,72 @@ extern "C" int lss_sigma_extra(const double *r, const double *sigma, const uint8
     if (n_used < 10) return LSS_OK;
     if (!(sigma_hat == sigma_hat) || isinf(sigma_hat)) return LSS_OK;   // scipy raises -> reference swallows, keeps 0
     int nfev = 0, rc = LSS_OK;
+    // Constant sigma over the selected points (one value per sensor / data set is common): x = r / sqrt(s1^2 + sigma^2) is then
+    // a monotone image of r for every s1, so its order statistics are the SAME elements the evaluation above selected from r.
+    // Every further RDE costs four divisions on the host -- with the operations and roundings of the device code -- instead
+    // of passes over the points.  (One range pass over sigma decides; any spread, NaN or non-positive value keeps the general path.)
+    bool const_sigma = false;
+    double sg_const = 0.0, rv[SEL_MAX] = {0, 0, 0, 0};
+    RdePlan plan_h;
+    memset(&plan_h, 0, sizeof(plan_h));
+    if (!getenv("LSS_SIGMA_EXTRA_GENERAL")) {
+        Scratch range;
+        LSS_CUDA(range.alloc(sizeof(unsigned long long) * 2, st));
+        const unsigned long long init[2] = {~0ull, 0ull};
+        LSS_CUDA(cudaMemcpyAsync(range.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        sigma_range_kernel<<<stride_grid(n, SEL_BLOCK, 8), SEL_BLOCK, 0, st>>>(r, sigma, mask, n, range.as<double>());
+        LSS_LAUNCH_CHECK();
+        unsigned long long keys[2];
+        SelectState st_h;
+        LSS_CUDA(cudaMemcpyAsync(keys, range.p, sizeof(keys), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaMemcpyAsync(&st_h, wk.state.p, sizeof(st_h), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaMemcpyAsync(&plan_h, wk.plan.p, sizeof(plan_h), cudaMemcpyDeviceToHost, st));
+        LSS_CUDA(cudaStreamSynchronize(st));
+        double lo = host_key_f64(keys[0]), hi = host_key_f64(keys[1]);
+        if (comm && comm->n_ranks > 1) {           // the same decision on every rank
+            Scratch mm;
+            LSS_CUDA(mm.alloc(sizeof(double) * 2, st));
+            const double v[2] = {lo, -hi};
+            LSS_CUDA(cudaMemcpyAsync(mm.p, v, sizeof(v), cudaMemcpyHostToDevice, st));
+            LSS_TRY(comm_allreduce(comm, mm.p, 2, 0, 1, st));
+            double w[2];
+            LSS_CUDA(cudaMemcpyAsync(w, mm.p, sizeof(w), cudaMemcpyDeviceToHost, st));
+            LSS_CUDA(cudaStreamSynchronize(st));
+            lo = w[0]; hi = -w[1];
+        }
+        if (lo == hi && lo > 0.0 && std::isfinite(lo) && plan_h.n >= 2) {
+            const_sigma = true;
+            sg_const = lo;
+            for (int t = 0; t < SEL_MAX && t < plan_h.n_targets; ++t) rv[t] = host_key_f64(st_h.prefix[t]);
+        }
+    }
+    auto rde_const = [&](double s1sq) -> double {
+        // scaled_value() and select_finish_kernel on the host: every operation rounded on its own (volatile: no contraction)
+        volatile double sq = sg_const * sg_const;
+        volatile double sum = s1sq + sq;
+        volatile double c = sqrt(sum);
+        double q[2];
+        for (int k = 0; k < 2; ++k) {
+            volatile double lo = rv[plan_h.lo_idx[k]] / c;
+            if (plan_h.clamp[k]) { q[k] = lo; continue; }
+            volatile double hi = rv[plan_h.hi_idx[k]] / c;
+            volatile double d = hi - lo;
+            volatile double slope = d / 1.0;
+            volatile double prod = slope * plan_h.frac[k];
+            volatile double qq = prod + lo;
+            q[k] = qq;
+        }
+        volatile double diff = q[1] - q[0];
+        return diff / 2.0;
+    };
     auto f = [&](double s1) -> double {
         double v = 0.0;
-        int e = rde_eval(wk, r, sigma, mask, py_square(s1), n, comm, &v, nullptr, st);
-        if (e != LSS_OK) rc = e;
+        if (const_sigma) {
+            v = rde_const(py_square(s1));
+        } else {
+            int e = rde_eval(wk, r, sigma, mask, py_square(s1), n, comm, &v, nullptr, st);
+            if (e != LSS_OK) rc = e;
+        }
         ++nfev;
         return py_square(v - 1.0);
     };

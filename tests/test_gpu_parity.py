@@ -224,6 +224,33 @@ def test_rde_and_sigma_extra_known_answers(L):
     assert np.max(np.abs(got - want)) < 1e-12
 
 
+def test_sigma_extra_constant_sigma_path_is_bit_identical(L, monkeypatch):
+    """With one sigma for all selected points the scaled residuals keep the order of the residuals for every trial value,
+    so lss_sigma_extra evaluates RDE from the four order statistics it selected once (host arithmetic with the device's
+    roundings).  Same bits and same number of Brent evaluations as the general path (a select over all points per
+    evaluation); a single deviating sigma -- inside or outside the mask -- is handled, NaN residuals are skipped."""
+    rng = np.random.default_rng(31)
+    for n in (37, 5000, 300_001):
+        r = rng.standard_t(3, n) * 0.7
+        r[rng.random(n) < 0.001] = np.nan
+        r_in = np.where(np.isfinite(r), r, 0.)
+        msk = rng.random(n) < 0.9
+        for sg in (np.full(n, 0.05), np.full(n, 3.0)):
+            monkeypatch.delenv('LSS_SIGMA_EXTRA_GENERAL', raising=False)
+            fast = L.calc_sigma_extra(r_in, sg, msk)
+            monkeypatch.setenv('LSS_SIGMA_EXTRA_GENERAL', '1')
+            slow = L.calc_sigma_extra(r_in, sg, msk)
+            monkeypatch.delenv('LSS_SIGMA_EXTRA_GENERAL')
+            assert np.array_equal(fast, slow), (n, sg[0])
+            assert abs(fast[0] - O.sigma_extra(r_in, sg, msk)[0]) < 1e-12
+        sg = np.full(n, 0.05)
+        out = np.flatnonzero(~msk)[0]
+        sg[out] = 7.0                                 # outside the mask: still constant where it counts
+        assert np.array_equal(L.calc_sigma_extra(r_in, sg, msk), L.calc_sigma_extra(r_in, np.full(n, 0.05), msk))
+        sg[np.flatnonzero(msk)[3]] = 0.0500001        # inside: the general path must take over
+        assert abs(L.calc_sigma_extra(r_in, sg, msk)[0] - O.sigma_extra(r_in, sg, msk)[0]) < 1e-12
+
+
 def test_sort_free_fast_paths_match_the_sorting_paths(L, monkeypatch):
     """Row-regular COO blocks -> CSR without a sort, small-integer dense ranks by presence table, medians of constant
     groups by min == max: each equals the general sorting path bit for bit (and falls back to it when it must)."""
