@@ -21,7 +21,7 @@
 
 namespace lss {
 
-constexpr int NK_MAX = 16;          // longest ELL row (lss_solver_create_blocks checks)
+constexpr int NK_MAX = 24;          // longest ELL row (lss_solver_create_blocks checks): 4 z0 + 8 dz + bias + slope + sensor-grid columns
 constexpr int NU_WARPS = 4;         // warps per CTA of the numeric kernel
 
 __device__ __forceinline__ bool entry_valid(int c, double v, const unsigned char *__restrict__ fixed) {
@@ -128,14 +128,16 @@ __global__ void __launch_bounds__(256) normal_fill_i32_kernel(int *p, int64_t n,
 }
 
 // N += sum_r (w_new[r] - w_cur[r]) a_r a_r^T ; w_cur <- w_new.  Warp per 32-row chunk, rows staged in shared memory,
-// pairs spread over the lanes (pair e = i * K + j on lane e mod 32).
+// pairs spread over the lanes (pair e = i * K + j on lane e mod 32).  KM: compile-time bound of K (16 for plain fits: fewer
+// pair registers per lane; 24 for rows with slope / sensor-grid columns).
+template <int KM>
 __global__ void __launch_bounds__(NU_WARPS * 32)
 normal_update_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict__ ell_col, const double *__restrict__ ell_val,
                      const unsigned char *__restrict__ fixed, const double *__restrict__ w_new, double *__restrict__ w_cur,
                      const int *__restrict__ indptr, const int *__restrict__ indices, double *__restrict__ data,
                      unsigned long long *__restrict__ n_missing, OwnFilter flt) {
-    __shared__ int sc[NU_WARPS][32][NK_MAX];
-    __shared__ double sv[NU_WARPS][32][NK_MAX];
+    __shared__ int sc[NU_WARPS][32][KM];
+    __shared__ double sv[NU_WARPS][32][KM];
     const int w = threadIdx.x >> 5;
     const unsigned lane = lane_id();
     const int64_t n_chunks = (n_rows + 31) >> 5;
@@ -161,7 +163,7 @@ normal_update_kernel(int64_t n_rows, int64_t n_pad, int K, const int *__restrict
         __syncwarp();
         // Rows are stored in grid-cell order, so consecutive rows mostly hold the SAME columns (points of one track in one
         // cell): their K x K products are summed in registers and the pattern is searched once per run, not per row.
-        constexpr int T = (NK_MAX * NK_MAX + 31) / 32;
+        constexpr int T = (KM * KM + 31) / 32;
         double accp[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) accp[t] = 0.0;
@@ -420,7 +422,7 @@ int normal_update(NormalMatrix *m, const double *w) {
     int64_t need = (n_chunks + NU_WARPS - 1) / NU_WARPS;
     const int64_t cap = (int64_t)kSMs * 16;
     const int grid = (int)(need < cap ? need : cap);
-    normal_update_kernel<<<grid, NU_WARPS * 32, 0, m->stream>>>(m->n_rows, m->n_pad, m->K, m->ell_col, m->ell_val, m->fixed, w, m->w_cur,
+    (m->K <= 16 ? normal_update_kernel<16> : normal_update_kernel<24>)<<<grid, NU_WARPS * 32, 0, m->stream>>>(m->n_rows, m->n_pad, m->K, m->ell_col, m->ell_val, m->fixed, w, m->w_cur,
                                                                 m->indptr, m->indices, m->data, m->missing, OwnFilter{m->owned, m->own_e0, m->own_e1});
     LSS_LAUNCH_CHECK();
     return LSS_OK;

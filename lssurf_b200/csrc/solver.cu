@@ -1701,7 +1701,7 @@ static int create_blocks_impl(lss_solver_t **solver, int64_t n_data, int64_t n_c
                               const double *rhs, const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm,
                               void *stream, const ShardSpec *sh) {
     if (!solver || n_data < 0 || n_con < 0 || n_cols <= 0) return fail(LSS_EINVAL, "solver_create_blocks: bad sizes");
-    if (n_data > 0 && (row_len < 1 || row_len > 16)) return fail(LSS_EINVAL, "solver_create_blocks: data rows must hold 1..16 entries");
+    if (n_data > 0 && (row_len < 1 || row_len > 24)) return fail(LSS_EINVAL, "solver_create_blocks: data rows must hold 1..24 entries");
     lss_solver *s = new lss_solver();
     int rc = solver_init_common(s, n_data + n_con, n_cols, rhs, fixed_cols, n_fixed, comm, stream);
     cudaStream_t st = s->stream;
@@ -1738,7 +1738,7 @@ static int create_blocks_impl(lss_solver_t **solver, int64_t n_data, int64_t n_c
             if (rc == LSS_ERANGE && !sh) { s->nm = nullptr; rc = LSS_OK; }   // too many column pairs for the 32-bit sort: fused ELL form
         }
     }
-    if (rc == LSS_OK && sh && !s->nm) rc = fail(LSS_EINVAL, "solver_create_sharded: needs the explicit-normal form (all rows <= 16 entries in one block)");
+    if (rc == LSS_OK && sh && !s->nm) rc = fail(LSS_EINVAL, "solver_create_sharded: needs the explicit-normal form (all rows <= 24 entries in one block)");
     if (rc == LSS_OK && n_con > 0) rc = spmv_plan_create(&s->plan_c, n_con, c_indptr, s->c_nnz, st);
     if (rc == LSS_OK && n_con > 0) rc = spmv_plan_create(&s->plan_ct, n_cols, ct_indptr, s->c_nnz, st);
     if (rc != LSS_OK) { lss_solver_destroy(s); return rc; }

@@ -1208,7 +1208,8 @@ int ell_spmv_launch(int64_t n_rows, int64_t n_pad, int K, const int32_t *ell_col
     switch (K) {
         LSS_ELL_CASE(1) LSS_ELL_CASE(2) LSS_ELL_CASE(3) LSS_ELL_CASE(4) LSS_ELL_CASE(5) LSS_ELL_CASE(6) LSS_ELL_CASE(7) LSS_ELL_CASE(8)
         LSS_ELL_CASE(9) LSS_ELL_CASE(10) LSS_ELL_CASE(11) LSS_ELL_CASE(12) LSS_ELL_CASE(13) LSS_ELL_CASE(14) LSS_ELL_CASE(15) LSS_ELL_CASE(16)
-        default: return fail(LSS_EINVAL, "ELL product: row length %d not in 1..16", K);
+        LSS_ELL_CASE(17) LSS_ELL_CASE(18) LSS_ELL_CASE(19) LSS_ELL_CASE(20) LSS_ELL_CASE(21) LSS_ELL_CASE(22) LSS_ELL_CASE(23) LSS_ELL_CASE(24)
+        default: return fail(LSS_EINVAL, "ELL product: row length %d not in 1..24", K);
     }
 #undef LSS_ELL_CASE
     LSS_LAUNCH_CHECK();
@@ -1228,7 +1229,8 @@ int ell_normal_launch(int mode, int64_t n_rows, int64_t n_pad, int K, const int3
     switch (K) {
         LSS_ELLN_CASE(1) LSS_ELLN_CASE(2) LSS_ELLN_CASE(3) LSS_ELLN_CASE(4) LSS_ELLN_CASE(5) LSS_ELLN_CASE(6) LSS_ELLN_CASE(7) LSS_ELLN_CASE(8)
         LSS_ELLN_CASE(9) LSS_ELLN_CASE(10) LSS_ELLN_CASE(11) LSS_ELLN_CASE(12) LSS_ELLN_CASE(13) LSS_ELLN_CASE(14) LSS_ELLN_CASE(15) LSS_ELLN_CASE(16)
-        default: return fail(LSS_EINVAL, "ELL product: row length %d not in 1..16", K);
+        LSS_ELLN_CASE(17) LSS_ELLN_CASE(18) LSS_ELLN_CASE(19) LSS_ELLN_CASE(20) LSS_ELLN_CASE(21) LSS_ELLN_CASE(22) LSS_ELLN_CASE(23) LSS_ELLN_CASE(24)
+        default: return fail(LSS_EINVAL, "ELL product: row length %d not in 1..24", K);
     }
 #undef LSS_ELLN_CASE
     LSS_LAUNCH_CHECK();

@@ -8,7 +8,7 @@ Three forms (include/lssurf_b200.h):
   * explicit normal matrix (default): N = A^T W A is formed on the device from the ELL rows of A = [G; C] (it has fewer
     non-zeros than A) and CG multiplies by it with one gather product per iteration; N is updated incrementally when
     the edit mask changes (``LSS_NO_EXPLICIT_N=1`` or ``lss_set_option('explicit_normal', 0)`` selects the next form);
-  * block form (default when every data row holds <= 16 entries, which is always the case for interpolation rows):
+  * block form (default when every data row holds <= 24 entries: interpolation rows with bias, slope and sensor-grid columns):
     G as an ELL copy applied by the fused ``q += G^T (w .* (G p))`` kernel, the constraint rows as a CSR pair
     (C, C^T) -- one pass over G per CG iteration, no transpose of G;
   * generic form: A = [G; C] and an explicit A^T as CSR, two tiled CSR products per iteration (deterministic;
@@ -205,13 +205,13 @@ class NormalSolver(object):
         comm = dist.comm if dist is not None else None
         row_len = int((G.indptr[1:] - G.indptr[:-1]).max().item()) if self.n_data > 0 else 1
         con_len = int((Cn.indptr[1:] - Cn.indptr[:-1]).max().item()) if self.n_con > 0 else 0
-        self.fused = bool(fused) and row_len <= 16 and not os.environ.get('LSS_NO_FUSED')
+        self.fused = bool(fused) and row_len <= 24 and not os.environ.get('LSS_NO_FUSED')
         self.all_ell = False
         self.shard = shard
         if shard is not None:
             # row-sharded N: G holds this rank's own points plus halo copies, Cn every constraint row; the rank owns the
             # preconditioner blocks [block_lo, block_hi) and exchanges p with its peers through the P2P mailbox
-            if not (self.fused and con_len <= 16 and structure is not None and 'block_ptr' in structure):
+            if not (self.fused and con_len <= 24 and structure is not None and 'block_ptr' in structure):
                 raise _cabi.LssError('the row-sharded solver needs short rows and a block structure')
             self.all_ell = True
             self.A = DeviceCSR.vstack([G, Cn]) if self.n_con > 0 else G
@@ -228,7 +228,7 @@ class NormalSolver(object):
         elif self.fused:
             p = _cabi.ptr
             nul = C.c_void_p(0)
-            self.all_ell = con_len <= 16 and not os.environ.get('LSS_CSR_CONSTRAINTS')
+            self.all_ell = con_len <= 24 and not os.environ.get('LSS_CSR_CONSTRAINTS')
             if self.all_ell:
                 # constraint stencils are short rows too (<= 9 entries): one ELL block [G; C], one kernel per product
                 self.A = DeviceCSR.vstack([G, Cn]) if self.n_con > 0 else G
