@@ -30,6 +30,7 @@ from .constraint_functions import setup_smoothness_constraints, build_reference_
 from .data_slope_bias import data_slope_bias
 from .grid_functions import setup_grids, setup_averaging_ops, setup_z0_avg
 from .lin_op import lin_op, DeviceCSR, rows_of
+from .match_priors import match_prior_dz
 from .point_data import data as point_data, grid_data
 from .setup_sensor_grid_bias import setup_sensor_grid_bias, parse_sensor_bias_grids
 from .solver import NormalSolver, grid_structure, coarse_structure
@@ -53,8 +54,8 @@ DEFAULTS = {
     'time_stages': False, 'sort_points': True,
 }
 
-_UNSUPPORTED = ('compute_E', 'mask_file', 'mask_update_function', 'prior_args', 'prior_edge_args', 'lagrangian_coords',
-                'constraint_scaling_maps', 'avg_masks', 'DEM_tol')
+_UNSUPPORTED = ('compute_E', 'mask_file', 'mask_update_function', 'prior_edge_args', 'lagrangian_coords',
+                'constraint_scaling_maps', 'avg_masks')
 
 
 class _Stages(object):
@@ -256,6 +257,7 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         n_data = o1 - o0
     sigma_extra = torch.zeros(n_data, dtype=f64, device=dev)
     r_data = torch.empty(n_data, dtype=f64, device=dev)
+    dem_d = None
     dz_cols = np.asarray(Gc.TOC['cols']['dz']) if 'dz' in Gc.TOC['cols'] else np.zeros(0, dtype=int)
     last_iteration = (args['max_iterations'] <= 1)
     m0 = np.zeros(n_cols)
@@ -327,6 +329,16 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
         recount = args['bias_nsigma_edit'] is not None      # flagged biases drop their data from the mask on every pass
         if editable is not None:
             in_TSE_d = torch.where(editable, in_TSE_d, in_TSE_original)
+            recount = True
+        if args['DEM_tol'] is not None:
+            # check_data_against_DEM (smooth_fit.py:31-37): selected points must stay within DEM_tol of the DEM once the
+            # fitted height change (everything but z0) is taken out
+            if dem_d is None:
+                dem_d = _field_dev(data, 'DEM')
+            m1 = m0.copy()
+            m1[np.asarray(G_data.TOC['cols']['z0'])] = 0
+            r_dem = solver.residual(_cabi.to_dev(m1, f64), z) - dem_d
+            in_TSE_d = (in_TSE_d.bool() & (r_dem.abs() < args['DEM_tol'])).to(torch.uint8)
             recount = True
         if recount:
             # counted over ALL ranks: the loop control below must take the same decisions everywhere
@@ -672,7 +684,7 @@ def smooth_fit(**kwargs):
     order = None
     shard = None
     if (args['sort_points'] and os.environ.get('LSS_SORT_POINTS', '1') != '0' and not args['return_fit_objects'] and args['bias_nsigma_edit'] is None
-            and args['bias_edit_vals'] is None and 'editable' not in data.fields and args['sigma_extra_masks'] is None
+            and args['bias_edit_vals'] is None and 'editable' not in data.fields and args['sigma_extra_masks'] is None and args['DEM_tol'] is None
             and args['data_slope_sensors'] is None and args['sensor_grid_bias_params'] is None
             and args['sigma_extra_bin_spacing'] is None and n_all > 1):
         order, keys = _cabi.spatial_order(grids['z0'].as_struct(), grids['dz'].as_struct(), [y_d, x_d, t_d], return_keys=True)
@@ -775,6 +787,9 @@ def smooth_fit(**kwargs):
                 raise NotImplementedError('jitter_* / stripe_* sensor grid biases need DEM files (GDAL): out of scope')
             if len(params) and 'spacing' in params:
                 setup_sensor_grid_bias(data, grids, G_data, constraint_op_list, _row_range=row_range, **params)
+    # prior constraints from an existing dz model (smooth_fit.py:575-576; in-memory data sets only)
+    if args['prior_args'] is not None:
+        constraint_op_list += match_prior_dz(grids, **args['prior_args'])
     no_priors = all(op.prior is None for op in constraint_op_list)      # the default: every constraint pulls towards zero
     for op in constraint_op_list:
         if op.prior is None:

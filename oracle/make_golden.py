@@ -33,7 +33,7 @@ from oracle import ref_harness as H        # noqa: E402
 from lssurf_b200 import synthetic as S     # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable', 'uniform_masked']
+WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable', 'uniform_masked', 'uniform_prior_dem']
 
 
 def digest(*arrays):
@@ -275,6 +275,15 @@ def case_widened(name, pts, kw, write):
     D = H.point_data(**pts)
     kw = dict(kw)
     grid_masks = kw.pop('mask_data', None)         # NumPy masks: injected into the reference's grids (with_masks)
+    prior = kw.pop('prior_args', None)             # in-memory prior points: handed to the reference's make_prior_op
+    if prior is not None:
+        MP = sys.modules['LSsurf.match_priors']
+
+        def prior_ops(grids, **_):
+            return [MP.make_prior_op(grids, H.point_data(**d), 'prior_%d' % k, ref_time=prior['ref_epoch'], sigma_scale=prior['sigma_scale'])
+                    for k, d in enumerate(prior['dzs'])]
+        kw['prior_args'] = {}
+        SF.match_prior_dz = prior_ops
     with warnings.catch_warnings(), with_masks(SF, grid_masks):
         warnings.simplefilter('ignore')
         fo = L.smooth_fit(data=D.copy(), VERBOSE=False, return_fit_objects=True, **kw)
@@ -328,6 +337,13 @@ def case_widened(name, pts, kw, write):
         fx['valid_data'] = np.packbits(np.asarray(out['valid_data'], dtype=bool))
         if grid_masks is not None:
             fx['mask_z0'], fx['mask_dz'] = grid_masks['z0'].astype(bool), grid_masks['dz'].astype(bool)
+        if prior is not None:
+            kw.pop('prior_args')
+            fx['kw'] = repr(kw)
+            fx['prior_meta'] = np.array([prior['ref_epoch'], prior['sigma_scale'], len(prior['dzs'])], dtype=float)
+            for k, d in enumerate(prior['dzs']):
+                for f, v in d.items():
+                    fx[f'prior{k}_{f}'] = np.asarray(v, dtype=float)
         sb = out['m'].get('slope_bias', {})
         if sb:
             fx['slope_bias'] = np.array([[k, v['slope_x'], v['slope_y']] for k, v in sb.items()], dtype=float)
@@ -376,7 +392,18 @@ def widened_inputs():
     mz[:, :2] = False                                       # and a strip along its western edge
     md[8:, 9:] = False                                      # the north-east corner of the dz grid
     kw_f = dict(kwf, mask_data={'z0': mz, 'dz': md}, mask_scale={0: 10, 1: 1}, dzdt_lags=[1], max_iterations=4)
-    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e), (ptf, kw_f)
+    # prior constraints from an existing dz model (match_priors.make_prior_op: interpolation at t minus interpolation at the
+    # reference time, non-zero prior values in the right-hand side) and the DEM check of the edit loop (DEM_tol)
+    ptg, kwg = S.uniform_3d(n=6000, width=1.2e4, seed=13)
+    ptg['DEM'] = 100. * np.cos(2 * np.pi * ptg['x'] / 2.e4) * np.sin(2 * np.pi * ptg['y'] / 3.e4) + rng.normal(0, 0.5, ptg['x'].size)
+    far = rng.random(ptg['x'].size) < 0.02
+    ptg['DEM'][far] += 40.                                  # DEM blunders: those points fail the check
+    npr = 150
+    px, py = rng.uniform(-5.5e3, 5.5e3, npr), rng.uniform(-5.5e3, 5.5e3, npr)
+    pt = rng.choice([-1.5, -0.75, 0., 0.75, 1.5], npr)       # the reference-time rows (t = 0) are dropped by make_prior_op
+    prior_pts = dict(x=px, y=py, t=pt, dz=pt * (1. + np.cos(2 * np.pi * px / 4.e4)) + rng.normal(0, 0.02, npr), sigma_dz=np.full(npr, 0.05))
+    kw_g = dict(kwg, DEM_tol=10., prior_args=dict(dzs=[prior_pts], ref_epoch=0., sigma_scale=2.), max_iterations=5)
+    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e), (ptf, kw_f), (ptg, kw_g)
 
 
 def grid_bias_inputs():
@@ -414,6 +441,31 @@ def case_grid_bias(write):
         np.savez_compressed(os.path.join(GOLDEN, 'grid_bias.npz'), **fx)
 
 
+def case_notebook_solves(write):
+    """BASELINE.json configs[0..1] at the one-line seam sparseqr.solve(A, b): the systems of tests/notebook_cases.py built
+    with the unmodified reference classes, solved by the stub sparseqr (SuperLU on the normal equations + refinement).
+    The fixture holds the digest of every scaled system and its solution (every 4th node of the 401 x 401 grids)."""
+    print('== notebook solves (cfg 1b, cfg 2)')
+    L = H.load()
+    import sparseqr
+    from tests import notebook_cases
+    systems = notebook_cases.build(L, lambda d: H.point_data(**d))
+    fx = {}
+    for name, (A, b, shape) in systems.items():
+        x = sparseqr.solve(A, b)
+        r = A @ x - b
+        g = A.T @ r
+        print(f'   {name}: A {A.shape} nnz={A.nnz}  |A^T r| / |A^T b| = {np.linalg.norm(g) / np.linalg.norm(A.T @ b):.1e}  {sparseqr.LAST.get("method")}')
+        step = 4 if shape[0] > 200 else 1
+        fx[name + '_A'] = csr_digest(A)
+        fx[name + '_b'] = digest(np.asarray(b, dtype=float))
+        fx[name + '_x'] = x.reshape(shape)[::step, ::step].copy()
+        fx[name + '_step'] = step
+        fx[name + '_norm'] = float(np.linalg.norm(x))
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN, 'notebook_solves.npz'), **fx)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--check', action='store_true')
@@ -428,6 +480,8 @@ def main():
                 case_widened(name, p_, k_, write)
         if a.case in (None, 'grid_bias'):
             case_grid_bias(write)
+        if a.case in (None, 'notebook_solves'):
+            case_notebook_solves(write)
         return
     case_lowlevel(write)
     case_fit('strip_nb', *S.notebook_strip(), write)
@@ -438,6 +492,7 @@ def main():
     for name, (p_, k_) in zip(WIDENED, widened_inputs()):
         case_widened(name, p_, k_, write)
     case_grid_bias(write)
+    case_notebook_solves(write)
     print('all cases: oracle == reference')
 
 

@@ -92,3 +92,28 @@ def test_true_div_is_ieee_division(L):
     for s in (1000., 1.e4, 3., 2.5e3):
         got = L._cabi.to_host(L._cabi.true_div(L._cabi.to_dev(x), s))
         assert np.array_equal(got, x / s)
+
+
+def test_solve_is_a_drop_in_for_sparseqr_solve(L):
+    """lssurf_b200.solve(A, b) at the one-line seam of the reference (sparseqr.solve, smooth_fit.py:142; aniso notebook cells
+    6, 13, 20; BASELINE.json configs[0..1]): the systems are bit-identical to the reference's, the solutions agree with its
+    direct solve to 1e-6 relative L2 (north-star tolerance)."""
+    from tests import notebook_cases
+    from tests.util import GOLDEN
+    fx = np.load(f'{GOLDEN}/notebook_solves.npz')
+    systems = notebook_cases.build(L, lambda d: L.point_data.data().from_dict(d))
+    for name, (A, b, shape) in systems.items():
+        assert csr_digest(A) == str(fx[name + '_A']) and digest(np.asarray(b, dtype=float)) == str(fx[name + '_b']), name
+        info = {}
+        x = L.solve(A, b, info=info)
+        step = int(fx[name + '_step'])
+        got, want = x.reshape(shape)[::step, ::step], fx[name + '_x']
+        rel = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        print(name, info, 'rel-L2 %.2e' % rel)
+        assert info['converged'] and rel < 1e-6, (name, rel, info)
+        assert abs(np.linalg.norm(x) - float(fx[name + '_norm'])) < 1e-6 * float(fx[name + '_norm'])
+    # other accepted inputs: COO, a lin_op; a wrong right-hand side length is refused
+    A, b, shape = systems['cfg1b']
+    assert rel_l2(L.solve(A.tocoo(), b), L.solve(A, b)) < 1e-9
+    with pytest.raises(ValueError):
+        L.solve(A, b[:-1])

@@ -183,3 +183,16 @@ def iterate_fit_like_a_reference_caller(Lp, name='uniform3d_small'):
 
 def test_iterate_fit_reference_signature(double):
     iterate_fit_like_a_reference_caller(L)
+
+
+def test_notebook_systems_are_bit_identical(double):
+    """BASELINE.json configs[0..1] at the low-level API (fd_grid / lin_op.interp_mtx / grad2 / one / diff_op with mutated .v /
+    add / vstack / toCSR, notebooks/smooth_fit_demo_aniso.ipynb): the scaled systems handed to solve(A, b) have the digests of
+    the ones the unmodified reference builds (tests/notebook_cases.py, oracle/make_golden.py::case_notebook_solves)."""
+    from tests import notebook_cases
+    fx = np.load(f'{GOLDEN}/notebook_solves.npz')
+    systems = notebook_cases.build(L, make_data)
+    assert set(systems) == {'cfg1b', 'cfg2_iso', 'cfg2_aniso', 'cfg2_circle'}
+    for name, (A, b, shape) in systems.items():
+        assert csr_digest(A) == str(fx[name + '_A']), name
+        assert digest(np.asarray(b, dtype=float)) == str(fx[name + '_b']), name

@@ -30,6 +30,12 @@ def load_case(name):
     kw.pop('mask_data', None)
     if 'mask_z0' in fx.files:            # NumPy masks of the z0 / dz grids (oracle/make_golden.py::with_masks)
         kw['mask_data'] = {'z0': fx['mask_z0'], 'dz': fx['mask_dz']}
+    if 'prior_meta' in fx.files:         # in-memory prior points of match_priors.match_prior_dz
+        ref_epoch, sigma_scale, n_sets = fx['prior_meta']
+        dzs = []
+        for k in range(int(n_sets)):
+            dzs.append({f[len(f'prior{k}_'):]: fx[f] for f in fx.files if f.startswith(f'prior{k}_')})
+        kw['prior_args'] = dict(dzs=dzs, ref_epoch=float(ref_epoch), sigma_scale=float(sigma_scale))
     return fx, pts, kw
 
 
@@ -40,7 +46,7 @@ def rel_l2(a, b):
 FIT_CASES = ['strip_nb', 'strip_outliers', 'uniform3d_small', 'tracks_bias_small']
 # fixtures taken from the reference run alone (oracle/make_golden.py::case_widened)
 WIDENED_CASES = ['uniform_avg_scales', 'uniform_groups_editable', 'tracks_bias_edit', 'uniform_sigma_grid', 'tracks_sensor_slope',
-                 'uniform_masked']
+                 'uniform_masked', 'uniform_prior_dem']
 
 
 def check_parse_model_outputs(fx, S):
