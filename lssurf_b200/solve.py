@@ -29,7 +29,7 @@ def _device_csr(A):
                      _cabi.to_dev(M.data.astype(np.float64), torch.float64), M.shape)
 
 
-def solve(A, b, tolerance=None, rtol=1e-12, maxiter=100000, x0=None, info=None):
+def solve(A, b, tolerance=None, rtol=1e-12, maxiter=1000000, x0=None, info=None):
     """x = argmin |A x - b|.  A: scipy.sparse matrix (any format), ``lin_op`` or ``DeviceCSR``; b: array of A.shape[0]
     values.  ``tolerance`` is accepted for signature compatibility with sparseqr.solve (a rank tolerance there) and
     ignored; ``rtol`` is the PCG stopping tolerance sqrt(r^T M^-1 r / b^T M^-1 b).  Columns without entries come back as
@@ -56,6 +56,10 @@ def solve(A, b, tolerance=None, rtol=1e-12, maxiter=100000, x0=None, info=None):
         s.close()
     if not np.isfinite(last['relres']):
         raise _cabi.LssError('solve: the PCG iteration broke down (residual is not finite)')
+    if not last['relres'] <= rtol:
+        import warnings
+        warnings.warn('solve: PCG stopped at %d iterations with relative residual %.2e > rtol %.1e' % (last['iterations'], last['relres'], rtol),
+                      RuntimeWarning)
     if info is not None:
         info.update(iterations=last['iterations'], relres=last['relres'], form=last['form'],
                     converged=bool(last['relres'] <= rtol))
