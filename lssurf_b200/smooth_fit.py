@@ -54,7 +54,7 @@ DEFAULTS = {
     'time_stages': False, 'sort_points': True,
 }
 
-_UNSUPPORTED = ('compute_E', 'mask_file', 'mask_update_function', 'prior_edge_args', 'lagrangian_coords',
+_UNSUPPORTED = ('mask_file', 'mask_update_function', 'prior_edge_args', 'lagrangian_coords',
                 'constraint_scaling_maps', 'avg_masks')
 
 
@@ -883,6 +883,18 @@ def smooth_fit(**kwargs):
         parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args,
                     dist=dist if (dist is not None and dist.world > 1) else None, stages=stages)
         stages.mark('parse_model')
+        if args['compute_E']:
+            # error propagation (smooth_fit.py:689-712): data errors inflated by sigma_extra, edited rows out
+            if dist is not None and dist.world > 1:
+                raise NotImplementedError('compute_E runs on one GPU')
+            from .propagate_errors import covariance_dense, calc_and_parse_errors
+            w_e = torch.cat((tse_out_d.to(f64) / (s_loc * s_loc + se_d * se_d), 1. / _cabi.to_dev(Ec, f64) ** 2))
+            fixed = np.setdiff1d(np.arange(m0.size), np.asarray(Ip_c.free_cols)) if not sp.issparse(Ip_c) else \
+                np.setdiff1d(np.arange(m0.size), np.unique(Ip_c.tocoo().row))
+            cov = covariance_dense(G_rows, Gc._csr_device(col_N=m0.size, row_N=int(Gc.N_eq)), w_e, fixed)
+            calc_and_parse_errors(E, cov, grids, G_data, Gc, averaging_ops, bias_model, args['bias_params'])
+            del cov
+            stages.mark('compute_E')
     else:
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
         averaging_ops.update(setup_z0_avg(grids, grids['dz'].col_N, args))

@@ -441,6 +441,42 @@ def case_grid_bias(write):
         np.savez_compressed(os.path.join(GOLDEN, 'grid_bias.npz'), **fx)
 
 
+def compute_E_inputs():
+    """A fit small enough for the dense QR / triangular-inverse stand-ins (about 1 300 unknowns): repeat tracks with
+    per-(rgt, cycle) biases, dz/dt at two lags and block averages, so every branch of calc_and_parse_errors is taken."""
+    pts, kw = S.icesat2_tracks(n=4000, width=6.e3, seed=17, t_span=3.)
+    return pts, dict(kw, compute_E=True, dzdt_lags=[1, 4], avg_scales=[2000.], max_iterations=4)
+
+
+def case_compute_E(write):
+    """Error propagation (smooth_fit.py:212-274, 689-712, lin_op.py:540-553) from the reference run alone:
+    sparseqr.rz and LSsurf.inv_tr_upper are dense stand-ins (oracle/ref_stubs/sparseqr, oracle/ref_harness), everything
+    else -- the rebuilt TCinv with sigma_extra, Ip_r, the row norms of Rinv, grid_error of every averaging operator,
+    parse_biases of the errors -- is the unmodified reference."""
+    pts, kw = compute_E_inputs()
+    print(f'== compute_E: {pts["x"].size} points (reference outputs only)')
+    L = H.load()
+    D = H.point_data(**pts)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out = L.smooth_fit(data=D.copy(), VERBOSE=False, **kw)
+    E = out['E']
+    fx = dict(m0=out['m']['all'], in_TSE=np.packbits(np.asarray(out['data'].three_sigma_edit, dtype=bool)),
+              sigma_extra_final=np.asarray(out['data'].sigma_extra, dtype=float), kw=repr(kw))
+    for key, g in E.items():
+        if key in ('sigma_bias', 'sigma_slope_bias'):
+            continue
+        fx['E_' + key] = np.asarray(getattr(g, key), dtype=float)
+    sb = E.get('sigma_bias')
+    if sb:
+        fx['E_sigma_bias_val'] = np.asarray(sb['val'], dtype=float)
+    print('   E keys:', sorted(E), ' sigma_z0 median %.4f  sigma_dz median %.4f' %
+          (np.nanmedian(fx['E_sigma_z0']), np.nanmedian(fx['E_sigma_dz'])))
+    fx.update({'in_' + k: v for k, v in pts.items()})
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN, 'compute_E.npz'), **fx)
+
+
 def case_notebook_solves(write):
     """BASELINE.json configs[0..1] at the one-line seam sparseqr.solve(A, b): the systems of tests/notebook_cases.py built
     with the unmodified reference classes, solved by the stub sparseqr (SuperLU on the normal equations + refinement).
@@ -482,6 +518,8 @@ def main():
             case_grid_bias(write)
         if a.case in (None, 'notebook_solves'):
             case_notebook_solves(write)
+        if a.case in (None, 'compute_E'):
+            case_compute_E(write)
         return
     case_lowlevel(write)
     case_fit('strip_nb', *S.notebook_strip(), write)
@@ -493,6 +531,7 @@ def main():
         case_widened(name, p_, k_, write)
     case_grid_bias(write)
     case_notebook_solves(write)
+    case_compute_E(write)
     print('all cases: oracle == reference')
 
 

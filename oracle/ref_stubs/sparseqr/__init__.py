@@ -30,5 +30,13 @@ def solve(A, b, tolerance=None):
     return x
 
 
-def rz(*a, **kw):
-    raise NotImplementedError('sparseqr.rz (compute_E path) is out of scope')
+def rz(A, b, tolerance=None):
+    """Stand-in for PySPQR's ``rz`` (Q-less QR: returns Z = Q^T b, R, the column permutation and the rank) as the
+    reference's error propagation calls it (LSsurf/smooth_fit.py:219).  Dense Householder QR without column pivoting
+    (LAPACK through NumPy), so the permutation is the identity; only for the small systems of the compute_E fixture."""
+    A = sp.csr_matrix(A)
+    if A.shape[1] > DENSE_MAX:
+        raise NotImplementedError('sparseqr.rz stand-in: dense QR only (%d columns)' % A.shape[1])
+    b = np.asarray(b.todense() if sp.issparse(b) else b, dtype=float).reshape(A.shape[0], -1)
+    Q, R = np.linalg.qr(A.toarray(), mode='reduced')
+    return Q.T @ b, sp.coo_matrix(np.triu(R)), np.arange(A.shape[1]), A.shape[1]

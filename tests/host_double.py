@@ -296,6 +296,33 @@ class NormalSolver(object):
         pass
 
 
+class NormalMatrix(object):
+    """Stand-in for lssurf_b200.solver.NormalMatrix (lss_normal_*): N = A^T diag(w) A with SciPy, the rows and columns of
+    the fixed unknowns left empty like the device matrix."""
+
+    def __init__(self, A, fixed_cols=None):
+        _arg(A.indptr, _I32, 'normal indptr'), _arg(A.indices, _I32, 'normal indices'), _arg(A.data, _F64, 'normal data')
+        self.A = O.csr_matrix(_np(A.indptr), _np(A.indices), _np(A.data), A.shape)
+        self.n_cols = A.shape[1]
+        self.keep = np.ones(self.n_cols)
+        self.keep[np.asarray(fixed_cols if fixed_cols is not None else [], dtype=np.int64)] = 0.
+
+    def update(self, w):
+        import scipy.sparse as sp
+        _arg(w, _F64, 'normal weights')
+        K = sp.diags(self.keep)
+        self.N = (K @ (self.A.T @ sp.diags(_np(w)) @ self.A) @ K).tocsr()
+        self.N.eliminate_zeros()
+        self.N.sort_indices()
+
+    def export(self):
+        return (torch.from_numpy(self.N.indptr.astype(np.int32)), torch.from_numpy(self.N.indices.astype(np.int32)),
+                torch.from_numpy(self.N.data.astype(np.float64)))
+
+    def close(self):
+        pass
+
+
 _CABI_NAMES = ('device', 'to_dev', 'to_host', 'interp_coo', 'stencil_coo', 'coo_extent', 'coo_to_csr', 'blocks_to_csr', 'csr_transpose',
                'dense_rank', 'group_median', 'spmv', 'SpmvPlan', 'spmv_planned', 'csr_rmatvec', 'rde', 'sigma_extra',
                'edit_mask', 'spatial_order')
@@ -311,6 +338,8 @@ def installed():
     me = sys.modules[__name__]
     saved = {n: getattr(_cabi, n) for n in _CABI_NAMES}
     saved_solver = sf.NormalSolver
+    import lssurf_b200.propagate_errors as pe
+    saved_normal = pe.NormalMatrix
     from lssurf_b200.parallel import DistContext
     saved_reduce = DistContext.allreduce_sum
     saved_array = torch.Tensor.__array__
@@ -329,10 +358,12 @@ def installed():
         for n in _CABI_NAMES:
             setattr(_cabi, n, getattr(me, n))
         sf.NormalSolver = NormalSolver
+        pe.NormalMatrix = NormalMatrix
         yield
     finally:
         for n, f in saved.items():
             setattr(_cabi, n, f)
         sf.NormalSolver = saved_solver
+        pe.NormalMatrix = saved_normal
         DistContext.allreduce_sum = saved_reduce
         torch.Tensor.__array__ = saved_array

@@ -69,6 +69,14 @@ def test_widened_fit_against_reference_fixture(L, name):
     check_parse_model_outputs(fx, S)
 
 
+def test_compute_E_against_reference_fixture(L):
+    """Error propagation: per-node, per-operator and per-bias errors from the covariance of the device
+    normal matrix against the reference's R^-1 row norms."""
+    from tests.test_host_double import check_compute_E
+    S = check_compute_E(L)
+    assert 'compute_E' not in S['timing'] or S['timing']['compute_E'] >= 0
+
+
 def test_calc_sigma_extra_on_grid_numpy_api(L):
     """Reference signature, NumPy in / out: constant noise -> one value everywhere; a noisier half -> larger values there."""
     from lssurf_b200.calc_sigma_extra import calc_sigma_extra_on_grid

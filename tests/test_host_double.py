@@ -69,6 +69,31 @@ def check_widened_outputs(fx, S):
         assert np.max(np.abs(S['data'].sigma_extra - fx['sigma_extra_final'])) < 2e-5
 
 
+def check_compute_E(Lp, **extra):
+    """compute_E against the reference run (oracle/make_golden.py::case_compute_E; smooth_fit.py:212-274, 689-712,
+    lin_op.py:540-553).  The reference reads errors off the rows of R^-1 with entries below 1e-5 dropped, the package off
+    the exact covariance N^-1: at most n x 1e-10 (about 1e-7) of variance is missing from a reference value, and forming
+    N squares the condition number of the QR; the bar is 1e-4 relative."""
+    fx, pts, kw = load_case('compute_E')
+    S = Lp.smooth_fit(data=make_data(pts), VERBOSE=False, **dict(kw, **extra))
+    assert np.array_equal(np.packbits(S['data'].three_sigma_edit), fx['in_TSE'])
+    assert rel_l2(S['m']['all'], fx['m0']) < 1e-6
+    keys = [k[2:] for k in fx.files if k.startswith('E_') and k != 'E_sigma_bias_val']
+    assert set(keys) <= set(S['E']) and len(keys) == 7, (keys, sorted(S['E']))
+    for key in keys:
+        want, got = fx['E_' + key], np.asarray(getattr(S['E'][key], key), dtype=float)
+        assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want)), key
+        ok = ~np.isnan(want)
+        assert np.max(np.abs(got[ok] - want[ok]) / np.maximum(want[ok], 1e-3)) < 1e-4, key
+    want, got = fx['E_sigma_bias_val'], np.asarray(S['E']['sigma_bias']['val'], dtype=float)
+    assert got.shape == want.shape and np.max(np.abs(got - want) / want) < 1e-4
+    return S
+
+
+def test_compute_E_against_reference_fixture(double):
+    check_compute_E(L, sort_points=False)
+
+
 def test_double_is_removed_afterwards():
     from lssurf_b200 import _cabi
     assert _cabi.interp_coo.__module__ == 'lssurf_b200._cabi' and _cabi.device.__module__ == 'lssurf_b200._cabi'
