@@ -204,11 +204,14 @@ int lss_comm_box_bytes(lss_comm_t *comm, int64_t *bytes_h);
 typedef struct lss_solver lss_solver_t;
 
 /* Replaces sparseqr.solve on the row-selected, 1/sigma-scaled system (smooth_fit.py:123-142) by a
- * matrix-free fp64 preconditioned CG on (A^T W A) x = A^T W b, where A = [G; C] is this rank's block
- * of data rows stacked on its share of the constraint rows, W = diag(w), b = [z; prior].
+ * fp64 preconditioned CG on (A^T W A) x = A^T W b, where A = [G; C] is this rank's block
+ * of data rows stacked on its share of the constraint rows, W = diag(w), b = [z; prior].  This entry point is the GENERIC
+ * form (rows of any length): A and A^T as CSR, two products per iteration.  smooth_fit uses lss_solver_create_blocks /
+ * lss_solver_create_sharded below, which form the normal matrix explicitly and multiply by it once per iteration.
  * Columns listed in fixed_cols (the reference-epoch columns removed by Ip_c,
- * constraint_functions.py:128-151) are held at exactly 0.  With a communicator the products
- * A^T W (A p) and the dot products are summed over ranks with one NCCL all-reduce per iteration.
+ * constraint_functions.py:128-151) are held at exactly 0.  With a communicator (this form only) the products
+ * A^T W (A p) and the dot products are summed over ranks with one NCCL all-reduce per iteration; the row-sharded
+ * normal-matrix form (lss_solver_create_sharded) has no collective inside the iteration.
  * The solver borrows every array (the caller keeps them alive until lss_solver_destroy). */
 int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, const int32_t *indptr,
                       const int32_t *indices, const double *data, const int32_t *t_indptr,

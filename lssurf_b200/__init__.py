@@ -14,7 +14,7 @@ from .constraint_functions import setup_smoothness_constraints, build_reference_
 from .fd_grid import fd_grid                              # noqa: F401
 from .calc_sigma_extra import calc_sigma_extra_on_grid    # noqa: F401
 from .data_slope_bias import data_slope_bias              # noqa: F401
-from .grid_functions import setup_grids, sum_cell_area, calc_cell_area, setup_averaging_ops, setup_z0_avg, sym_range   # noqa: F401
+from .grid_functions import setup_grids, sum_cell_area, calc_cell_area, setup_averaging_ops, setup_z0_avg, setup_avg_mask_ops, sym_range   # noqa: F401
 from .lin_op import lin_op, fd_op, DeviceCSR              # noqa: F401
 from .match_priors import make_prior_op, match_prior_dz   # noqa: F401
 from .setup_grid_bias import setup_grid_bias              # noqa: F401

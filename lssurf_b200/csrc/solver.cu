@@ -1,4 +1,4 @@
-// Matrix-free fp64 preconditioned conjugate gradients on the normal equations.
+// fp64 preconditioned conjugate gradients on the normal equations (A^T W A) x = A^T W b.
 //
 // Replaces `sparseqr.solve(Ip_r.dot(TCinv.dot(Gcoo)), Ip_r.dot(TCinv.dot(rhs)))`
 // (LSsurf/smooth_fit.py:123-142).  The row selection Ip_r and the 1/sigma scaling TCinv are never
@@ -6,10 +6,17 @@
 // Ip_c (reference epoch, constraint_functions.py:128-151) is a zero in the preconditioner, which
 // keeps those unknowns at exactly 0.
 //
-// One CG iteration =  u = w .* (A p)      CSR product, streams A once        (spmv.cu)
-//                     q = A^T u           CSR product, streams A^T once      (spmv.cu)
-//                     [q | p.q partials]  one NCCL all-reduce when row-sharded over GPUs
-//                     x, r, z, p updates  two fused vector kernels
+// Operator forms (chosen at creation, lss_solver_info reports which):
+//   explicit normal matrix (default)  N = A^T W A built on the device (normal.cu), q = N p by ONE gather product per
+//                                     iteration (spmv.cu, or the grid-structured layout of structured.cu), then ONE
+//                                     cooperative vector-step kernel: alpha, x, r, z = (block-Jacobi + coarse level) r,
+//                                     beta, p, eliminated bias columns slaved
+//   fused ELL pass                    q += A^T (w .* (A p)) in one pass over an ELL copy of A
+//   generic CSR pair                  u = w .* (A p), q = A^T u: two deterministic CSR products (any row length)
+// Several GPUs: rows of N sharded by preconditioner blocks, every exchange of the iteration (p.q, z, coarse restriction,
+// bias coupling) done by the step kernel itself with stores into peer memory over NVLink (cg_step_shard_kernel below,
+// mailbox in comm.cu) -- no collective per iteration; the older NCCL all-reduce per iteration remains for the
+// generic forms.
 // All scalars (alpha, beta, r.z) stay on the device; the host only polls a convergence flag once
 // per batch of iterations, one batch ahead of the GPU, so the queue never drains.
 #include <math.h>

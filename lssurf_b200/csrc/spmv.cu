@@ -1,4 +1,4 @@
-// CSR products y = A x for the matrix-free normal-equation operator.
+// CSR products y = A x: the explicit normal matrix N of the CG iteration, G for residuals / parse_model, A and A^T of the generic form.
 //
 // Replaces scipy's csr_matvec behind `.dot` (LSsurf/smooth_fit.py:142, 146, 326-345).  HBM-bound:
 // the matrix (12 B per non-zero) is streamed exactly once with coalesced, L1-bypassing loads;

@@ -171,3 +171,17 @@ def setup_averaging_ops(grid, col_N, args, cell_area=None):
                 op.v /= (kernel_N[0] * kernel_N[1])
             ops[dz_name] = op
     return ops
+
+
+def setup_avg_mask_ops(grid, col_N, avg_masks, dzdt_lags):
+    """Mean of dz, and of dz/dt at every lag, over each named mask (grid_functions.py:314-325)."""
+    if avg_masks is None:
+        return {}
+    avg_ops = {}
+    for name, mask in avg_masks.items():
+        this_name = name + '_avg_dz'
+        avg_ops[this_name] = lin_op(grid, col_N=col_N, name=this_name).mean_of_mask(mask, dzdt_lag=None)
+        for lag in dzdt_lags:
+            this_name = name + f'_avg_dzdt_lag{lag}'
+            avg_ops[this_name] = lin_op(grid, col_N=col_N, name=this_name).mean_of_mask(mask, dzdt_lag=lag)
+    return avg_ops

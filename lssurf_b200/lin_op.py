@@ -621,6 +621,60 @@ class lin_op(object):
         shape = tuple(self._dev['v'].shape) if self._dev['v'] is not None else np.shape(self._host['v'])
         self._set_device(self._device('r'), self._device('c'), new_v.reshape(shape))
 
+    def mean_of_mask(self, mask, dzdt_lag=None):
+        """Weighted mean over the nodes a 2-D mask selects, one row per epoch, or the lagged rate of that mean with
+        ``dzdt_lag`` (lin_op.py:347-402).  ``mask``: anything with ``interp(x, y)`` returning its values at node
+        coordinates (the reference's pointCollection grid), or an array already on the (y, x) nodes of the grid.
+        Weights = mask x cell area, normalised; the destination grid is a single point at the weighted centroid."""
+        g = self.grid
+        if hasattr(mask, 'interp'):
+            yy, xx = np.meshgrid(g.ctrs[0], g.ctrs[1], indexing='ij')
+            w = np.array(mask.interp(xx, yy), dtype=float)
+        else:
+            w = np.array(mask, dtype=float)
+        if w.shape != tuple(g.shape[0:2]):
+            raise ValueError('mean_of_mask: mask values must sit on the (y, x) nodes of the grid')
+        w[~np.isfinite(w)] = 0
+        i0, j0 = np.nonzero(w)
+        sel = np.flatnonzero(w)
+        v0 = w.ravel()[sel] if g.cell_area is None else (w * g.cell_area).ravel()[sel]
+        v0 = v0 / v0.sum()
+        y0 = np.sum((g.bds[0][0] + i0 * g.delta[0]) * v0)
+        x0 = np.sum((g.bds[1][0] + j0 * g.delta[1]) * v0)
+        if len(g.shape) < 3:
+            # one row: the average of the grid itself
+            self._set_host('r', np.zeros_like(i0))
+            self.c = g.global_ind([i0, j0])
+            self.v = v0
+            self.N_eq = 1
+            self.col_N = int(np.max(self.c)) + 1
+            self.__update_size_and_shape__()
+            self.dst_grid = fd_grid([[y0, y0], [x0, x0]], g.delta, 0, col_N=0, srs_proj4=g.srs_proj4)
+            self.dst_ind0 = np.array([0]).astype(int)
+            return self
+        nt = int(g.shape[2])
+        if dzdt_lag is None:
+            n_out = nt
+            terms = [(0, v0)]
+            t_vals = g.ctrs[2]
+        else:
+            n_out = nt - dzdt_lag
+            terms = [(0, -v0 / dzdt_lag / g.delta[2]), (dzdt_lag, v0 / dzdt_lag / g.delta[2])]
+            t_vals = g.ctrs[-1][:-dzdt_lag] + g.delta[-1] * dzdt_lag / 2
+        rr, cc, vv = [], [], []
+        for ii in range(n_out):
+            for shift, vals in terms:
+                rr.append(np.zeros_like(i0) + ii)
+                cc.append(g.global_ind([i0, j0, np.zeros_like(i0) + ii + shift]))
+                vv.append(vals)
+        self._set_host('r', np.concatenate(rr))
+        self.c, self.v = np.concatenate(cc), np.concatenate(vv)
+        self.N_eq = int(self.r.max()) + 1
+        self.dst_grid = fd_grid([[y0, y0], [x0, x0], [t_vals[0], t_vals[-1]]], g.delta, 0, col_N=self.N_eq, srs_proj4=g.srs_proj4)
+        self.__update_size_and_shape__()
+        self.dst_ind0 = np.arange(self.N_eq, dtype=int)
+        return self
+
     def update_dst_grid(self, grid_shift, kernel_size):
         """Destination grid of an averaging / differencing operator (lin_op.py:490-502)."""
         sub0 = np.unravel_index(self.ind0 - self.grid.col_0, self.grid.shape)

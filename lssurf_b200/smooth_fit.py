@@ -5,15 +5,17 @@ Drop-in for the reference driver (LSsurf/smooth_fit.py:100-210 ``iterate_fit``, 
 The three expensive stages run on the GPU through the C ABI (include/lssurf_b200.h):
 
   assembly   lin_op.interp_mtx / diff_op / toCSR  ->  lss_interp_coo, lss_stencil_coo, lss_coo_to_csr
-  solve      sparseqr.solve on the scaled system  ->  lss_solver_* : matrix-free fp64 PCG on
-             (A^T W A) x = A^T W b, A = [G; C] resident in HBM, W = diag(in_TSE / sigma^2, 1 / E_c^2)
+  solve      sparseqr.solve on the scaled system  ->  lss_solver_* : fp64 PCG on (A^T W A) x = A^T W b with the
+             normal matrix formed explicitly on the device (one gather product + one fused vector step per iteration,
+             two-level preconditioner, bias columns eliminated), W = diag(in_TSE / sigma^2, 1 / E_c^2)
   edit loop  residual, calc_sigma_extra (RDE + Brent), 3-sigma mask  ->  lss_spmv, lss_sigma_extra,
              lss_edit_mask, all on device arrays between solves
 
 The row selection ``Ip_r`` and scaling ``TCinv`` of the reference are never materialised (they are
 the weight vector), the column selection ``Ip_c`` is a set of unknowns held at zero.  New optional
 keywords (defaults keep existing calls unchanged): ``cg_rtol``, ``cg_maxiter``, ``dist`` (a
-``parallel.DistContext`` for row-sharded multi-GPU solves), ``profile_spmv``.
+``parallel.DistContext``: rows of the normal matrix sharded over the GPUs of one node, exchanges inside the CG step kernel
+over NVLink), ``profile_spmv``; ``compute_E`` (error propagation) takes the dense-covariance path of propagate_errors.py.
 """
 import os
 import warnings
@@ -28,7 +30,7 @@ from .bias_functions import assign_bias_ID, setup_bias_fit, parse_biases
 from .calc_sigma_extra import sigma_extra_device, sigma_extra_on_grid_device
 from .constraint_functions import setup_smoothness_constraints, build_reference_epoch_matrix
 from .data_slope_bias import data_slope_bias
-from .grid_functions import setup_grids, setup_averaging_ops, setup_z0_avg
+from .grid_functions import setup_grids, setup_averaging_ops, setup_z0_avg, setup_avg_mask_ops
 from .lin_op import lin_op, DeviceCSR, rows_of
 from .match_priors import match_prior_dz
 from .point_data import data as point_data, grid_data
@@ -54,8 +56,7 @@ DEFAULTS = {
     'time_stages': False, 'sort_points': True,
 }
 
-_UNSUPPORTED = ('mask_file', 'mask_update_function', 'prior_edge_args', 'lagrangian_coords',
-                'constraint_scaling_maps', 'avg_masks')
+_UNSUPPORTED = ('mask_file', 'prior_edge_args', 'lagrangian_coords')
 
 
 class _Stages(object):
@@ -220,7 +221,8 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
                               fixed_cols, None, structure=structure, G_local=G_csr, stages=st)
         del G_full
     else:
-        # row-sharded solve: this rank's data rows + its share of the constraint rows, one all-reduce per CG iteration
+        # generic fall-back (rows too long for the normal-matrix forms): this rank's data rows + its share of the constraint rows,
+        # one NCCL all-reduce per CG iteration
         c_lo, c_hi = (0, int(Gc.N_eq)) if dist is None else dist.shard(int(Gc.N_eq))
         C_loc = C_all if (c_lo, c_hi) == (0, int(Gc.N_eq)) else C_all.row_slice(c_lo, c_hi)
         prior = rhs_d[n_data + c_lo:n_data + c_hi].contiguous()
@@ -735,7 +737,20 @@ def smooth_fit(**kwargs):
     constraint_op_list = []
     if verbose:
         print(f"smooth_fit: E_RMS={args['E_RMS']}")
-    setup_smoothness_constraints(grids, constraint_op_list, args['E_RMS'], args['mask_scale'])
+    scaling_masks = None
+    if args['constraint_scaling_maps'] is not None:
+        # per-node multipliers of the expected constraint values (smooth_fit.py:467-478): maps that can interpolate themselves
+        # (the reference's pointCollection grids) or arrays already on the (y, x) nodes of the z0 / dz grid; non-finite -> 1
+        scaling_masks = {}
+        for key, this_map in args['constraint_scaling_maps'].items():
+            g = grids['z0'] if 'z0' in key else grids['dz']
+            vals = this_map.interp(g.ctrs[1], g.ctrs[0], gridded=True) if hasattr(this_map, 'interp') else this_map
+            vals = np.array(vals, dtype=float)
+            if vals.shape != tuple(g.shape[0:2]):
+                raise ValueError(f'constraint_scaling_maps[{key!r}] must sit on the (y, x) nodes of the {g.name} grid')
+            vals[~np.isfinite(vals)] = 1.
+            scaling_masks[key] = vals
+    setup_smoothness_constraints(grids, constraint_op_list, args['E_RMS'], args['mask_scale'], scaling_masks=scaling_masks)
     stages.mark('c:smoothness_ops')
     if args['bias_params'] is not None:
         n_bias = len(bias_model['bias_ID_dict'])
@@ -875,10 +890,17 @@ def smooth_fit(**kwargs):
         data.assign({'three_sigma_edit': in_TSE_all})
         data.assign({'sigma_extra': sigma_extra_all})
         data.assign({'z_est': np.reshape(z_est_all, data.shape)})
-        averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
-        averaging_ops.update(setup_z0_avg(grids, grids['dz'].col_N, args))
         dev_fields = {'z': z_own, 'sigma': s_own, 'z_est': z_est_d, 'three_sigma_edit': tse_out_d, 'sigma_extra': se_d,
                       'bias_ID': ids_own, 'G_rows': G_rows}
+        if args['mask_update_function'] is not None:
+            # the caller's hook sees the parsed model (no averaging grids yet) and may change the grid masks / cell areas
+            # before the averaging operators are built (smooth_fit.py:664-666)
+            parse_model(m, m0, dev_fields, R, RMS, G_data, {}, Gc, Ec, grids, bias_model, args,
+                        dist=dist if (dist is not None and dist.world > 1) else None)
+            args['mask_update_function'](grids, m, args)
+        averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
+        averaging_ops.update(setup_z0_avg(grids, grids['dz'].col_N, args))
+        averaging_ops.update(setup_avg_mask_ops(grids['dz'], G_data.col_N, args['avg_masks'], args['dzdt_lags']))
         stages.mark('outputs_d2h')
         parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids, bias_model, args,
                     dist=dist if (dist is not None and dist.world > 1) else None, stages=stages)
@@ -898,6 +920,7 @@ def smooth_fit(**kwargs):
     else:
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
         averaging_ops.update(setup_z0_avg(grids, grids['dz'].col_N, args))
+        averaging_ops.update(setup_avg_mask_ops(grids['dz'], G_data.col_N, args['avg_masks'], args['dzdt_lags']))
     stages.mark('epilogue')
     return {'m': m, 'E': E, 'data': data, 'grids': grids, 'valid_data': valid_data, 'TOC': Gc.TOC, 'R': R, 'RMS': RMS,
             'timing': timing, 'E_RMS': args['E_RMS'], 'dzdt_lags': args['dzdt_lags']}

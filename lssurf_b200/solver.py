@@ -1,4 +1,4 @@
-"""Python handle on the matrix-free normal-equation PCG solver (``lss_solver_*`` in the C ABI).
+"""Python handle on the normal-equation PCG solver (``lss_solver_*`` in the C ABI).
 
 Stands in for the single line ``m0 = Ip_c.dot(sparseqr.solve(Ip_r.dot(TCinv.dot(Gcoo)), Ip_r.dot(TCinv.dot(rhs))))``
 (LSsurf/smooth_fit.py:142).  The operator stays in GPU memory for the whole edit loop; only the row-weight vector

@@ -33,7 +33,8 @@ from oracle import ref_harness as H        # noqa: E402
 from lssurf_b200 import synthetic as S     # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable', 'uniform_masked', 'uniform_prior_dem']
+WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable', 'uniform_masked', 'uniform_prior_dem',
+           'uniform_avg_masks', 'uniform_scaling_maps']
 
 
 def digest(*arrays):
@@ -276,6 +277,20 @@ def case_widened(name, pts, kw, write):
     kw = dict(kw)
     grid_masks = kw.pop('mask_data', None)         # NumPy masks: injected into the reference's grids (with_masks)
     prior = kw.pop('prior_args', None)             # in-memory prior points: handed to the reference's make_prior_op
+    avg_masks = kw.pop('avg_masks', None)          # named masks as arrays on the dz nodes; the reference asks them to interpolate
+    scaling_maps = kw.pop('constraint_scaling_maps', None)     # per-node multipliers as arrays on the z0 / dz nodes
+    if avg_masks is not None or scaling_maps is not None:
+        class NodeMask(object):                    # what lin_op.mean_of_mask needs of a pointCollection grid (lin_op.py:352-354)
+            def __init__(self, z):
+                self.z = z
+
+            def interp(self, x, y, gridded=False, **_):
+                assert (x.size, y.size)[::-1] == self.z.shape if gridded else x.shape == self.z.shape
+                return self.z.copy()
+    if avg_masks is not None:
+        kw['avg_masks'] = {k: NodeMask(np.asarray(v, dtype=float)) for k, v in avg_masks.items()}
+    if scaling_maps is not None:
+        kw['constraint_scaling_maps'] = {k: NodeMask(np.asarray(v, dtype=float)) for k, v in scaling_maps.items()}
     if prior is not None:
         MP = sys.modules['LSsurf.match_priors']
 
@@ -329,7 +344,7 @@ def case_widened(name, pts, kw, write):
         for key, g in out['m'].get('sensor_bias_grids', {}).items():
             fx['grid_' + key] = np.asarray(g.z)
         for key, g in out['m'].items():                      # dz/dt and block-average grids (setup_averaging_ops)
-            if key.startswith(('avg_', 'dzdt_')):
+            if key.startswith(('avg_', 'dzdt_')) or '_avg_dz' in key:
                 fx['avgop_' + key] = np.asarray(getattr(g, key), dtype=float)
                 if getattr(g, 'cell_area', None) is not None:
                     fx['avgarea_' + key] = np.asarray(g.cell_area, dtype=float)
@@ -337,6 +352,16 @@ def case_widened(name, pts, kw, write):
         fx['valid_data'] = np.packbits(np.asarray(out['valid_data'], dtype=bool))
         if grid_masks is not None:
             fx['mask_z0'], fx['mask_dz'] = grid_masks['z0'].astype(bool), grid_masks['dz'].astype(bool)
+        if avg_masks is not None:
+            kw.pop('avg_masks')
+            fx['kw'] = repr(kw)
+            for k, v in avg_masks.items():
+                fx['avgmask_' + k] = np.asarray(v, dtype=float)
+        if scaling_maps is not None:
+            kw.pop('constraint_scaling_maps')
+            fx['kw'] = repr(kw)
+            for k, v in scaling_maps.items():
+                fx['scalemap_' + k] = np.asarray(v, dtype=float)
         if prior is not None:
             kw.pop('prior_args')
             fx['kw'] = repr(kw)
@@ -403,7 +428,26 @@ def widened_inputs():
     pt = rng.choice([-1.5, -0.75, 0., 0.75, 1.5], npr)       # the reference-time rows (t = 0) are dropped by make_prior_op
     prior_pts = dict(x=px, y=py, t=pt, dz=pt * (1. + np.cos(2 * np.pi * px / 4.e4)) + rng.normal(0, 0.02, npr), sigma_dz=np.full(npr, 0.05))
     kw_g = dict(kwg, DEM_tol=10., prior_args=dict(dzs=[prior_pts], ref_epoch=0., sigma_scale=2.), max_iterations=5)
-    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e), (ptf, kw_f), (ptg, kw_g)
+    # means of dz and dz/dt over named masks (grid_functions.setup_avg_mask_ops, lin_op.mean_of_mask): a fractional mask
+    # with NaNs outside, weighted by the cell areas
+    pth, kwh = S.uniform_3d(n=6000, width=1.2e4, seed=14)
+    ndz = int(1.2e4 / kwh['spacing']['dz']) + 1
+    iy, ix = np.meshgrid(np.arange(ndz), np.arange(ndz), indexing='ij')
+    basin = np.clip(1.2 - np.hypot(iy - 4., ix - 7.) / 4., 0., 1.)
+    basin[:, :2] = np.nan
+    shelf = (ix >= 9).astype(float)
+    kw_h = dict(kwh, dzdt_lags=[1, 4], avg_masks={'basin': basin, 'shelf': shelf}, max_iterations=3)
+    # per-node multipliers of the expected constraint values (smooth_fit.py:467-478, constraint_functions.py:40-90): stiffer
+    # z0 curvature in the south, looser dz curvature in the east, d2z/dt2 scaled in a corner, and a 'dz' magnitude
+    # constraint on the nodes where its map is positive
+    pti, kwi = S.uniform_3d(n=6000, width=1.2e4, seed=15)
+    nz0 = int(1.2e4 / kwi['spacing']['z0']) + 1
+    m_z0 = np.ones((nz0, nz0)); m_z0[:nz0 // 2] = 0.25; m_z0[2, 3] = np.nan
+    m_d3 = np.ones((ndz, ndz)); m_d3[:, ndz // 2:] = 4.
+    m_tt = np.ones((ndz, ndz)); m_tt[:3, :3] = 0.5
+    m_dz = np.zeros((ndz, ndz)); m_dz[:2, :] = 0.05; m_dz[5, 5] = np.nan
+    kw_i = dict(kwi, constraint_scaling_maps={'d2z0_dx2': m_z0, 'd3z_dx2dt': m_d3, 'd2z_dt2': m_tt, 'dz': m_dz}, max_iterations=3)
+    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e), (ptf, kw_f), (ptg, kw_g), (pth, kw_h), (pti, kw_i)
 
 
 def grid_bias_inputs():

@@ -30,6 +30,10 @@ def load_case(name):
     kw.pop('mask_data', None)
     if 'mask_z0' in fx.files:            # NumPy masks of the z0 / dz grids (oracle/make_golden.py::with_masks)
         kw['mask_data'] = {'z0': fx['mask_z0'], 'dz': fx['mask_dz']}
+    if any(f.startswith('avgmask_') for f in fx.files):      # named averaging masks, values on the dz nodes
+        kw['avg_masks'] = {f[len('avgmask_'):]: fx[f] for f in fx.files if f.startswith('avgmask_')}
+    if any(f.startswith('scalemap_') for f in fx.files):     # constraint scaling maps, values on the z0 / dz nodes
+        kw['constraint_scaling_maps'] = {f[len('scalemap_'):]: fx[f] for f in fx.files if f.startswith('scalemap_')}
     if 'prior_meta' in fx.files:         # in-memory prior points of match_priors.match_prior_dz
         ref_epoch, sigma_scale, n_sets = fx['prior_meta']
         dzs = []
@@ -46,7 +50,7 @@ def rel_l2(a, b):
 FIT_CASES = ['strip_nb', 'strip_outliers', 'uniform3d_small', 'tracks_bias_small']
 # fixtures taken from the reference run alone (oracle/make_golden.py::case_widened)
 WIDENED_CASES = ['uniform_avg_scales', 'uniform_groups_editable', 'tracks_bias_edit', 'uniform_sigma_grid', 'tracks_sensor_slope',
-                 'uniform_masked', 'uniform_prior_dem']
+                 'uniform_masked', 'uniform_prior_dem', 'uniform_avg_masks', 'uniform_scaling_maps']
 
 
 def check_parse_model_outputs(fx, S):
