@@ -451,12 +451,22 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
     # constraint residuals: scaled (chi^2) and unscaled (RMS) per family
     n_cols = m0.size
     m0_d = _cabi.to_dev(m0, torch.float64)
-    ru = Gc._csr_device(col_N=n_cols, row_N=int(Gc.N_eq)).dot(m0_d).cpu().numpy()
-    rc = ru / Ec
-    for eq_type in ['d2z_dt2', 'grad2_z0', 'grad2_dzdt', 'grad2_PS']:
-        if eq_type in Gc.TOC['rows']:
-            R[eq_type] = np.sum(rc[rows_of(Gc.TOC['rows'][eq_type])] ** 2)
-            RMS[eq_type] = np.sqrt(np.mean(ru[rows_of(Gc.TOC['rows'][eq_type])] ** 2))
+    ru = Gc._csr_device(col_N=n_cols, row_N=int(Gc.N_eq)).dot(m0_d)
+    Ec_d = f['Ec'] if f.get('Ec') is not None else _cabi.to_dev(Ec, torch.float64)
+    rc = ru / Ec_d
+    kinds = [k for k in ['d2z_dt2', 'grad2_z0', 'grad2_dzdt', 'grad2_PS'] if k in Gc.TOC['rows']]
+    if kinds:
+        # sums stay on the device (1.5e6 constraint rows at cfg 4): one small copy for all families
+        parts = []
+        for eq_type in kinds:
+            sel = rows_of(Gc.TOC['rows'][eq_type])
+            if not isinstance(sel, slice):
+                sel = _cabi.to_dev(np.asarray(sel), torch.int64)
+            parts += [(rc[sel] ** 2).sum(), (ru[sel] ** 2).mean()]
+        parts = torch.stack(parts).cpu().numpy()
+        for k, eq_type in enumerate(kinds):
+            R[eq_type] = parts[2 * k]
+            RMS[eq_type] = np.sqrt(parts[2 * k + 1])
     mark('pm:constraint_residuals')
     # data counts and misfit maps: G^T applied to the edited-in indicator, r^2 and scaled r^2
     r_in = torch.where(tse, r, torch.zeros_like(r))
@@ -646,12 +656,12 @@ def smooth_fit(**kwargs):
         tse_d = None if tse_d is None else tse_d[keep].contiguous()
         rz = rd = None
     else:
-        valid_data = np.ones(int(z_d.numel()), dtype=bool)
+        valid_data = None                      # every point is valid: the mask is written once, from the final edit mask
         data = data_in.view() if hasattr(data_in, 'view') else data_in.copy_subset(valid_data)
     n_all = int(z_d.numel())
     if n_all == 0:
         print("\tsmooth_fit.py: after masking, no data found")
-        return _empty_result(m, E, data, grids, valid_data, timing, args)
+        return _empty_result(m, E, data, grids, np.ones(0, dtype=bool) if valid_data is None else valid_data, timing, args)
 
     stages.mark('interp+valid')
     # sigma_extra groups (smooth_fit.py:443-453)
@@ -663,7 +673,8 @@ def smooth_fit(**kwargs):
                 sel |= np.isin(getattr(data, field), vals)
             args['sigma_extra_masks'][key] = sel
     elif args['sigma_extra_masks'] is not None:
-        args['sigma_extra_masks'] = {k: np.asarray(v)[valid_data == 1] for k, v in args['sigma_extra_masks'].items()}
+        args['sigma_extra_masks'] = {k: (np.asarray(v) if valid_data is None else np.asarray(v)[valid_data == 1])
+                                     for k, v in args['sigma_extra_masks'].items()}
 
     # bias IDs are global (unique parameter combinations over ALL points), assigned before sharding
     bias_model = {}
@@ -826,7 +837,8 @@ def smooth_fit(**kwargs):
     if Ec.size and Ec.min() <= 0 and np.any(Ec == 0):
         raise ValueError('zero value found in constraint sigma')
     # TCinv and rhs stay on the device for the data rows (iterate_fit accepts tensors or NumPy)
-    TCinv = DiagonalOp(torch.cat((1. / s_loc, 1. / _cabi.to_dev(Ec, f64))))
+    Ec_d = _cabi.to_dev(Ec, f64)
+    TCinv = DiagonalOp(torch.cat((1. / s_loc, 1. / Ec_d)))
     if no_priors:
         rhs = torch.cat((z_loc, torch.zeros(int(Gc.N_eq), dtype=f64, device=z_loc.device)))
     else:
@@ -878,7 +890,8 @@ def smooth_fit(**kwargs):
                 t = out
             return _cabi.to_host(t)
 
-        in_TSE_all = to_caller(tse_out_d).astype(bool)
+        in_TSE_all = to_caller(tse_out_d)
+        in_TSE_all = in_TSE_all.view(np.bool_) if in_TSE_all.dtype == np.uint8 else in_TSE_all.astype(bool)    # 0 / 1 bytes
         sigma_extra_all = to_caller(se_d)
         z_est_all = to_caller(z_est_d)
         if args.get('history') is not None and order is not None and (not multi or shard is not None):
@@ -886,12 +899,15 @@ def smooth_fit(**kwargs):
                 mk = torch.empty(n_all, dtype=torch.uint8, device=z_d.device)
                 mk[order] = _cabi.to_dev(np.unpackbits(h['mask_out'])[:n_all])
                 h['mask_out'] = np.packbits(_cabi.to_host(mk))
-        valid_data[valid_data] = in_TSE_all
+        if valid_data is None:
+            valid_data = in_TSE_all.copy()
+        else:
+            valid_data[valid_data] = in_TSE_all
         data.assign({'three_sigma_edit': in_TSE_all})
         data.assign({'sigma_extra': sigma_extra_all})
         data.assign({'z_est': np.reshape(z_est_all, data.shape)})
         dev_fields = {'z': z_own, 'sigma': s_own, 'z_est': z_est_d, 'three_sigma_edit': tse_out_d, 'sigma_extra': se_d,
-                      'bias_ID': ids_own, 'G_rows': G_rows}
+                      'bias_ID': ids_own, 'G_rows': G_rows, 'Ec': Ec_d}
         if args['mask_update_function'] is not None:
             # the caller's hook sees the parsed model (no averaging grids yet) and may change the grid masks / cell areas
             # before the averaging operators are built (smooth_fit.py:664-666)
@@ -910,7 +926,7 @@ def smooth_fit(**kwargs):
             if dist is not None and dist.world > 1:
                 raise NotImplementedError('compute_E runs on one GPU')
             from .propagate_errors import covariance_dense, calc_and_parse_errors
-            w_e = torch.cat((tse_out_d.to(f64) / (s_loc * s_loc + se_d * se_d), 1. / _cabi.to_dev(Ec, f64) ** 2))
+            w_e = torch.cat((tse_out_d.to(f64) / (s_loc * s_loc + se_d * se_d), 1. / Ec_d ** 2))
             fixed = np.setdiff1d(np.arange(m0.size), np.asarray(Ip_c.free_cols)) if not sp.issparse(Ip_c) else \
                 np.setdiff1d(np.arange(m0.size), np.unique(Ip_c.tocoo().row))
             cov = covariance_dense(G_rows, Gc._csr_device(col_N=m0.size, row_N=int(Gc.N_eq)), w_e, fixed)
