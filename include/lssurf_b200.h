@@ -163,7 +163,7 @@ int lss_blocks_to_csr(int64_t n_rows, int64_t n_cols, int32_t n_blocks, const in
 
 /* ------------------------------------------------------------------ explicit normal matrix */
 
-/* N = A^T diag(w) A for a matrix A whose rows hold at most row_len <= 16 entries (canonical CSR in; the interpolation
+/* N = A^T diag(w) A for a matrix A whose rows hold at most row_len <= 24 entries (canonical CSR in; the interpolation
  * rows of lin_op.interp_mtx and the stencil rows of lin_op.diff_op all qualify).  This is the matrix SuiteSparseQR
  * factorises implicitly in sparseqr.solve (smooth_fit.py:142); the PCG solver multiplies by it instead.
  * lss_normal_create computes the sparsity pattern (row i of N = union of the column sets of the rows of A holding
@@ -219,7 +219,7 @@ int lss_solver_create(lss_solver_t **solver, int64_t n_rows, int64_t n_cols, con
                       const int32_t *fixed_cols, int64_t n_fixed, lss_comm_t *comm, void *stream);
 int lss_solver_destroy(lss_solver_t *solver);
 /* Block form of the same solver, the one smooth_fit uses: A = [G; C] is given as its two row blocks.
- *   G (n_data rows): every row holds at most row_len <= 16 entries (4 z0 + 8 dz corners + bias columns).  It is copied
+ *   G (n_data rows): every row holds at most row_len <= 24 entries (4 z0 + 8 dz corners + bias, slope and sensor-grid columns).  It is copied
  *     column-major (ELL) and applied by ONE fused kernel q += G^T (w .* (G p)) -- a single pass over G per CG
  *     iteration, contributions of neighbouring rows combined with warp shuffles before fp64 RED atomics -- so no
  *     transpose of G is ever built.  The CSR arrays of G are only read during this call.

@@ -1,18 +1,21 @@
-"""Row-sharded data parallelism over the GPUs of one node: one process per GPU.
+"""Data parallelism over the GPUs of one node: one process per GPU.
 
-The reference is single-process.  Here each rank owns a contiguous block of data
-rows: it assembles its rows of G and does all per-point work (residuals, order statistics, edit masks) on them.
-Two ways to run the solve:
-  * replicated solve (default): the assembled rows are all-gathered once (NCCL all-gather over NVLink, ~2 GB at 10^7
-    points), every rank forms the same normal matrix and runs the same PCG with NO collective inside the iteration
-    (one CG iteration is ~150 us of work on one B200 -- less than one 8-rank all-reduce costs); the solution is
-    broadcast from rank 0 after every solve so all ranks continue from identical bits;
-  * row-sharded solve (``LSS_SHARDED_SOLVE=1``): each rank keeps only its rows plus a 1/P share of the constraint
-    rows and the products are summed with one NCCL all-reduce (fp64) per CG iteration, issued from the C++ solver
-    loop through the communicator created here (``lss_comm_create`` -> ncclCommInitRank) -- for problems whose
-    iteration is long compared with the collective.
-torch.distributed is plumbing only: the host transport for the 128-byte NCCL unique id (any backend, gloo on CPU
-works), the all-gathers of assembled rows / masks / per-point outputs and the broadcast of the solution.
+The reference is single-process.  Here each rank owns a contiguous block of the spatially sorted
+data rows: it assembles its rows of G and does all per-point work (residuals, order statistics, edit masks) on them.
+Three ways to run the solve (smooth_fit.iterate_fit_device picks):
+  * row-sharded normal matrix (default with more than one rank on the z0 + dz grids): every rank owns a range of
+    preconditioner blocks -- its rows of N = A^T W A, built from its own points plus halo copies -- and the ranks exchange
+    p.q, their slice of z, the coarse restriction and the bias coupling from inside the CG step kernel through a
+    peer-to-peer mailbox (``ensure_box``: one device block per rank, CUDA-IPC handles opened on every peer, plain stores over
+    NVLink); no collective inside the iteration;
+  * replicated solve (``LSS_REPLICATED_SOLVE=1``): the assembled rows are all-gathered once (NCCL, ~2 GB at 10^7 points) and
+    every rank runs the same PCG; the solution is broadcast from rank 0 after every solve so all ranks continue from
+    identical bits;
+  * all-reduce solve (``LSS_SHARDED_SOLVE=1`` with the replicated mode, or rows too long for the normal-matrix forms): each
+    rank keeps its rows plus a 1/P share of the constraint rows and the products are summed with one NCCL all-reduce
+    (fp64) per CG iteration, issued from the C++ solver loop through the communicator created here.
+torch.distributed is plumbing only: the host transport for the 128-byte NCCL unique id and the IPC handles (any backend,
+gloo on CPU works), the all-gathers of masks / per-point outputs and the broadcast of the solution.
 """
 import ctypes as C
 import os
