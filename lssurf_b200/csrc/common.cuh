@@ -64,7 +64,10 @@ struct Scratch {
         if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
+            // bounded: scratch beyond this is handed back to the driver at the next synchronisation, so the library does
+            // not sit on memory PyTorch's caching allocator could use (cfg 4 keeps ~5 GB of staging alive between fits)
+            unsigned long long keep = 24ull << 30;
+            if (const char *e = getenv("LSS_POOL_KEEP_GB")) keep = (unsigned long long)atoll(e) << 30;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
         done_for = dev;
