@@ -64,6 +64,10 @@ def parse_args():
     ap.add_argument('--skip-e2e', action='store_true', help='profiling only: no host-input pass')
     ap.add_argument('--stages', action='store_true', help='kept for old command lines (the stage split is always reported)')
     ap.add_argument('--no-parity', action='store_true', help='skip the untimed bench-scale parity record')
+    ap.add_argument('--grid-bias', action='store_true',
+                    help='add the setup_grid_bias term of SURVEY 8(d) cfg 4 (10 km grid x a per-point covariate) to the timed workload; '
+                         'one GPU only (its columns belong to no preconditioner block, which the row-sharded solver needs)')
+    ap.add_argument('--no-variant', action='store_true', help='skip the untimed pass that measures the fit with the grid-bias term')
     ap.add_argument('--ref-window', type=float, default=SAMPLE_WIDTH, help='CPU arms: width of the sample window in metres')
     return ap.parse_args()
 
@@ -76,9 +80,23 @@ def workload_config(a):
                'coarse-level packet exchanged inside the CG step kernel through peer memory over NVLink, no collective per '
                'iteration' % a.gpus)
     return {'workload': 'cfg4: ICESat-2-shaped tracks, %d points, %.0f x %.0f km, z0 250 m, dz 1 km x 0.25 yr, '
-                        "bias_params=['rgt','cycle'], max_iterations=10" % (a.points, a.width / 1e3, a.width / 1e3),
+                        "bias_params=['rgt','cycle']%s, max_iterations=10" % (a.points, a.width / 1e3, a.width / 1e3,
+                                                                               ' + setup_grid_bias term (10 km grid)' if a.grid_bias else ''),
             'points': a.points, 'extent_km': a.width / 1e3, 'parallelism': par,
             'l2_policy': 'inputs larger than L2 (N streamed per CG iteration is 0.37 GB at N=1, A is 1.7 GB)'}
+
+
+def grid_bias_term(pts, width, seed):
+    """SURVEY 8(d) cfg 4's `setup_grid_bias` term: a per-point covariate (seeded N(0, 1), e.g. a signal-strength anomaly), a
+    smooth bias field proportional to it added to z, and the keyword arguments of the fit (10 km grid, expected_rms 0.1,
+    expected_rms_grad 1e-3).  Returns (cov, z_with_bias, grid bounds)."""
+    rng = np.random.default_rng(seed + 1)
+    cov = rng.standard_normal(pts['x'].size)
+    z = pts['z'] + 0.05 * np.cos(2 * np.pi * pts['x'] / 6e4) * np.sin(2 * np.pi * pts['y'] / 8e4) * cov
+    return cov, z, (-width / 2, width / 2, -width / 2, width / 2)
+
+
+GRID_BIAS = dict(spacing=1.0e4, expected_rms=0.1, expected_rms_grad=1e-3)
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
@@ -89,8 +107,14 @@ def cpu_sample(a, pts=None, kw=None):
         pts, kw = synthetic.icesat2_tracks(n=a.points, width=a.width, seed=a.seed)
     ws = min(a.ref_window, a.width)
     sel = (np.abs(pts['x']) < ws / 2) & (np.abs(pts['y']) < ws / 2)
+    if a.grid_bias and 'cov' not in pts:
+        cov, z_gb, _ = grid_bias_term(pts, a.width, a.seed)
+        pts = dict(pts, z=z_gb, cov=cov)
     sub = {k: np.ascontiguousarray(np.asarray(v)[sel]) for k, v in pts.items()}
     kw = dict(kw)
+    kw.pop('grid_bias_model_args', None)
+    if a.grid_bias:           # the same 10 km grid, cut to the window
+        kw['_grid_bias'] = dict(values=sub['cov'], bounds=(-ws / 2, ws / 2, -ws / 2, ws / 2), **GRID_BIAS)
     kw['W'] = dict(kw['W'], x=ws, y=ws)
     n_bias = int(np.unique(sub['rgt'] * 1000 + sub['cycle']).size)
     desc = ('the %d points of the bench data set inside the centred %.1f x %.1f km window, fitted on that window with the same '
@@ -98,8 +122,13 @@ def cpu_sample(a, pts=None, kw=None):
     return sub, kw, desc, n_bias
 
 
-def cpu_kind():
+def cpu_kind(a=None):
+    """'reference': the unmodified reference under stubs (build container); 'port': the oracle port (GPU box, and always for the
+    --grid-bias workload: the live reference driver has no call site for setup_grid_bias, the oracle restates the composition and
+    is pinned against the reference's own functions in oracle/make_golden.py)."""
     from oracle import ref_harness
+    if a is not None and a.grid_bias:
+        return 'port'
     return 'reference' if ref_harness.available() else 'port'
 
 
@@ -107,7 +136,11 @@ def cpu_step(pts, kw, kind, n_bias):
     """One pass of the reference path on the CPU.  kind 'reference': the unmodified reference smooth_fit under stub
     dependencies (oracle/ref_harness.py; build container only); 'port': the oracle port (oracle/lssurf_oracle.py).
     The only places bench.py executes oracle/ are this baseline leg and --impl reference."""
+    kw = dict(kw)
+    gbias = kw.pop('_grid_bias', None)
     t0 = time.perf_counter()
+    if kind == 'reference' and gbias is not None:
+        kind = 'port'             # the live reference driver has no call site for setup_grid_bias; the oracle restates the composition
     if kind == 'reference':
         from oracle import ref_harness as H
         L = H.load()
@@ -121,7 +154,7 @@ def cpu_step(pts, kw, kind, n_bias):
     from oracle import lssurf_oracle as O
     res = O.smooth_fit(pts['x'], pts['y'], pts['time'], pts['z'], pts['sigma'], kw['ctr'], kw['W'], kw['spacing'],
                        kw['E_RMS'], reference_epoch=kw['reference_epoch'], max_iterations=kw['max_iterations'],
-                       bias_params=[pts['rgt'], pts['cycle']], sigma_corr=pts['sigma_corr'])
+                       bias_params=[pts['rgt'], pts['cycle']], sigma_corr=pts['sigma_corr'], grid_bias=gbias)
     return time.perf_counter() - t0, res['sys']['n_data']
 
 
@@ -148,7 +181,7 @@ def run_reference(a):
         return
     cores = cpu_threads()
     pts, kw, desc, n_bias = cpu_sample(a)
-    kind = cpu_kind()
+    kind = cpu_kind(a)
     for _ in range(a.warmup):
         cpu_step(pts, kw, kind, n_bias)
     times = []
@@ -245,6 +278,18 @@ def run_b200(a):
         kw['cg_maxiter'] = a.cg_maxiter
     n_pts = int(pts['x'].size)
     fields = ('x', 'y', 'time', 'z', 'sigma', 'sigma_corr', 'rgt', 'cycle')
+    cov, z_gb, gb_bounds = grid_bias_term(pts, a.width, a.seed)
+
+    def grid_bias_kw():
+        g = L.fd_grid([[gb_bounds[0], gb_bounds[1]], [gb_bounds[2], gb_bounds[3]]], [GRID_BIAS['spacing']] * 2, name='cov_bias')
+        return [dict(param='cov', grid=g, expected_rms=GRID_BIAS['expected_rms'], expected_value=0.,
+                     expected_rms_grad=GRID_BIAS['expected_rms_grad'])]
+    if a.grid_bias:
+        if world > 1:
+            raise SystemExit('bench.py --grid-bias runs on one GPU')
+        pts = dict(pts, z=z_gb, cov=cov)
+        fields = fields + ('cov',)
+        kw['grid_bias_model_args'] = grid_bias_kw()
     # pinned host copies (e2e input) and device-resident copies (value input)
     host = {f: torch.from_numpy(pts[f]).pin_memory() for f in fields}
     dev = {f: host[f].cuda(non_blocking=True) for f in fields}
@@ -386,11 +431,37 @@ def run_b200(a):
                   'cg_iterations': [[h['pcg']['iterations'] for h in hh] for hh in (h0, h1)]}
         roofline['parity'] = parity
 
+    # ---- untimed variant: the same fit WITH the setup_grid_bias term of cfg 4 (the timed workload leaves it out: the reference's
+    # live smooth_fit has no call site for it and the row-sharded solver cannot own its columns), so its cost is on record
+    if rank == 0 and world == 1 and not a.grid_bias and not a.no_variant:
+        vdev = dict(dev, z=torch.from_numpy(z_gb).cuda(), cov=torch.from_numpy(cov).cuda())
+        vfields = fields + ('cov',)
+
+        def vfit():
+            D = L.point_data.data().from_dict({f: vdev[f] for f in vfields})
+            return L.smooth_fit(data=D, VERBOSE=False, **dict(kw, grid_bias_model_args=grid_bias_kw()))
+        Sv = vfit()
+        Sv = None
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        Sv = vfit()
+        torch.cuda.synchronize()
+        t_v = time.perf_counter() - w0
+        gb = Sv['m']['grid_biases']['cov_bias']
+        truth = 0.05 * np.cos(2 * np.pi * gb.x[None, :] / 6e4) * np.sin(2 * np.pi * gb.y[:, None] / 8e4)
+        roofline['grid_bias_variant'] = {
+            'what': 'one untimed fit of the same points with the setup_grid_bias term (covariate x 10 km grid, 121 columns, expected_rms 0.1, '
+                    'expected_rms_grad 1e-3; rows of 17 entries); bench.py --grid-bias times this workload',
+            'ms_per_step': 1e3 * t_v, 'cg_iterations': [p['iterations'] for p in Sv['timing']['pcg']],
+            'form': Sv['timing']['pcg'][0].get('form'), 'nnz_N': Sv['timing']['pcg'][0].get('nnz_N'),
+            'bias_field_correlation_with_truth': float(np.corrcoef(gb.cov_bias.ravel(), truth.ravel())[0, 1])}
+        Sv = vdev = None
+
     cpu = None
     if rank == 0 and a.gpus == 1 and not a.no_cpu_baseline:
         cores = cpu_threads()
         cp, ckw, desc, n_bias = cpu_sample(a, pts, kw)
-        kind = cpu_kind()
+        kind = cpu_kind(a)
         dt, n = cpu_step(cp, ckw, kind, n_bias)
         cpu = {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': desc, 'seconds': dt,
                'host_cores_available': os.cpu_count(), 'note': CPU_NOTE}

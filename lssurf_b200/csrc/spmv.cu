@@ -1116,16 +1116,47 @@ ell_spmv_kernel(int64_t n_rows, int64_t n_pad, const int *__restrict__ ell_col, 
     y[r] = epilogue(acc, mode, s, r);
 }
 
-// q += A^T u straight from the CSR rows of A (one thread per row, one RED.ADD.F64 per entry): for the handful of
-// transpose products per fit that do not justify building and storing A^T (parse_model's per-node sums).
+// q += A^T u straight from the CSR rows of A (one thread per row): for the handful of transpose products per fit that do
+// not justify building and storing A^T (parse_model's per-node sums).  The rows are sorted by grid cell, so entry k of
+// neighbouring rows usually names the same column: the warp folds runs of equal columns with a segmented shuffle scan and
+// only the tail of a run issues a RED.ADD.F64 (a bias column shared by a whole track segment, or the four nodes of a
+// 10 km bias grid under 10^5 consecutive points, would otherwise serialise thousands of atomics on one address).
 __global__ void __launch_bounds__(256)
 csr_rmatvec_kernel(int64_t n_rows, const int *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ data,
                    const double *__restrict__ u, double *__restrict__ q) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    const double ur = u[r];
-    if (ur == 0.0) return;
-    for (int k = indptr[r]; k < indptr[r + 1]; ++k) atomicAdd(q + indices[k], data[k] * ur);
+    const unsigned lane = threadIdx.x & 31u;
+    int k0 = 0, len = 0;
+    double ur = 0.0;
+    if (r < n_rows) {
+        ur = u[r];
+        if (ur != 0.0) {
+            k0 = indptr[r];
+            len = indptr[r + 1] - k0;
+        }
+    }
+    int max_len = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+    for (int k = 0; k < max_len; ++k) {
+        const bool in = k < len;
+        const int key = in ? indices[k0 + k] : -1;
+        double val = in ? data[k0 + k] * ur : 0.0;
+        const int kp = __shfl_up_sync(0xffffffffu, key, 1);
+        int head = (lane == 0u || kp != key) ? 1 : 0;          // equal columns need not be adjacent: scan inside runs only
+        const int is_head = head;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v2 = __shfl_up_sync(0xffffffffu, val, o);
+            const int h2 = __shfl_up_sync(0xffffffffu, head, o);
+            if (lane >= (unsigned)o) {
+                if (!head) val += v2;
+                head |= h2;
+            }
+        }
+        const int hn = __shfl_down_sync(0xffffffffu, is_head, 1);
+        if (key >= 0 && (lane == 31u || hn)) atomicAdd(q + key, val);
+    }
 }
 
 // Fused normal-equation product of the data block:  q += G^T (w .* (G x))  in ONE pass over the ELL copy of G.

@@ -7,23 +7,28 @@ from .lin_op import lin_op
 
 
 def setup_grid_bias(data, G_data, constraint_op_list, grids, name=None, param=None, grid=None, expected_rms=None,
-                    expected_value=None, expected_rms_grad=None):
+                    expected_value=None, expected_rms_grad=None, _pts=None, _scale=None):
     """Columns = nodes of ``grid`` appended after G_data's; entries = interpolation weights x data.<param>.
 
     Replicates the reference including its operator-precedence quirk: the curvature rows get
     ``expected = expected_rms_grad`` (the division by sqrt(cell area) applies to a zero array,
-    setup_grid_bias.py:33).
+    setup_grid_bias.py:33).  ``_pts`` / ``_scale`` (not in the reference): device arrays [y, x] and the parameter values of
+    the rows G_data holds, when smooth_fit has reordered or sharded the points (``data`` is then not consulted).
     """
     if name is None:
         name = param + '_bias'
     grids[name] = grid
     grid.col_0 = G_data.col_N
     grid.col_N = grid.col_0 + grid.N_nodes
-    op = lin_op(grid=grid, name=name).interp_mtx(data.coords()[0:2])
-    field = getattr(data, param)                     # NumPy array, or a tensor when the caller keeps its fields on the device
-    scale = _cabi.to_dev(field if isinstance(field, torch.Tensor) else np.asarray(field, dtype=float), torch.float64)
+    op = lin_op(grid=grid, name=name).interp_mtx(data.coords()[0:2] if _pts is None else _pts)
+    if _scale is None:
+        field = getattr(data, param)                 # NumPy array, or a tensor when the caller keeps its fields on the device
+        scale = _cabi.to_dev(field if isinstance(field, torch.Tensor) else np.asarray(field, dtype=float), torch.float64)
+    else:
+        scale = _scale
     r, c, v = op._device('r'), op._device('c'), op._device('v')
-    op._set_device(r, c, (v * scale[r.long()]).contiguous())
+    vs = (v * scale[r.long()]).contiguous()
+    op._set_device(r, c, vs, blocks=[(c, vs)] if op._blocks and c.dim() == 2 else None)      # still row-regular: no sort for toCSR
     G_data.add(op)
     if expected_rms_grad is not None:
         curv = lin_op(grid, name='grad2_' + name).grad2(DOF=param)

@@ -34,6 +34,7 @@ from .grid_functions import setup_grids, setup_averaging_ops, setup_z0_avg, setu
 from .lin_op import lin_op, DeviceCSR, rows_of
 from .match_priors import match_prior_dz
 from .point_data import data as point_data, grid_data
+from .setup_grid_bias import setup_grid_bias
 from .setup_sensor_grid_bias import setup_sensor_grid_bias, parse_sensor_bias_grids
 from .solver import NormalSolver, grid_structure, coarse_structure
 
@@ -49,7 +50,7 @@ DEFAULTS = {
     'data_slope_sensors': None, 'E_slope_bias': 0.01, 'E_RMS_d2x_PS_bias': None, 'E_RMS_PS_bias': None,
     'constraint_scaling_maps': None, 'error_res_scale': None, 'avg_masks': None, 'sigma_extra_masks': None,
     'bias_nsigma_edit': None, 'bias_nsigma_iteration': 2, 'bias_edit_vals': None, 'sensor_grid_bias_params': None,
-    'ancillary_data': None, 'lagrangian_coords': None, 'z0_average_scale': None, 'erode_source_mask': True,
+    'grid_bias_model_args': None, 'ancillary_data': None, 'lagrangian_coords': None, 'z0_average_scale': None, 'erode_source_mask': True,
     'VERBOSE': True, 'DEBUG': False,
     # solver controls (new; defaults chosen for 1e-6 relative-L2 parity with a direct solve)
     'cg_rtol': 1e-12, 'cg_maxiter': 50000, 'dist': None, 'profile_spmv': False, 'history': None,
@@ -448,6 +449,12 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
     m['extent'] = np.concatenate((z0g.bds[1], z0g.bds[0]))
     m['sensor_bias_grids'] = parse_sensor_bias_grids(m0, G_data, grids)
     m['jitter_bias_grids'] = {}
+    if args.get('grid_bias_model_args') is not None:            # deprecated/smooth_xytb_fit.py:303-310
+        m['grid_biases'] = {}
+        for bm in args['grid_bias_model_args']:
+            g = bm['grid']
+            m['grid_biases'][g.name] = grid_data().from_dict({'x': g.ctrs[1], 'y': g.ctrs[0],
+                                                              g.name: np.reshape(m0[g.col_0:g.col_N], g.shape)})
     # constraint residuals: scaled (chi^2) and unscaled (RMS) per family
     n_cols = m0.size
     m0_d = _cabi.to_dev(m0, torch.float64)
@@ -634,6 +641,9 @@ def smooth_fit(**kwargs):
     if args['bias_params'] is not None:
         extra_d = {p: _field_dev(data_in, p) for p in list(args['bias_params']) + ['sigma_corr']}
     tse_d = _field_dev(data_in, 'three_sigma_edit') if 'three_sigma_edit' in data_in.fields else None
+    cov_d = {}
+    if args['grid_bias_model_args'] is not None:       # the data parameters the gridded biases multiply
+        cov_d = {bm['param']: _field_dev(data_in, bm['param']) for bm in args['grid_bias_model_args']}
     stages.mark('upload')
     op_z0 = lin_op(grids['z0'], name='interp_z')
     op_dz = lin_op(grids['dz'], name='interp_dz')
@@ -653,6 +663,7 @@ def smooth_fit(**kwargs):
         data = data_in.copy_subset(valid_data)
         y_d, x_d, t_d, z_d, s_d = (a[keep].contiguous() for a in (y_d, x_d, t_d, z_d, s_d))
         extra_d = {k: v[keep].contiguous() for k, v in extra_d.items()}
+        cov_d = {k: v[keep].contiguous() for k, v in cov_d.items()}
         tse_d = None if tse_d is None else tse_d[keep].contiguous()
         rz = rd = None
     else:
@@ -701,7 +712,7 @@ def smooth_fit(**kwargs):
             and args['data_slope_sensors'] is None and args['sensor_grid_bias_params'] is None
             and args['sigma_extra_bin_spacing'] is None and n_all > 1):
         order, keys = _cabi.spatial_order(grids['z0'].as_struct(), grids['dz'].as_struct(), [y_d, x_d, t_d], return_keys=True)
-        if (dist is not None and dist.comm is not None and not os.environ.get('LSS_REPLICATED_SOLVE')
+        if (dist is not None and dist.comm is not None and not os.environ.get('LSS_REPLICATED_SOLVE') and args['grid_bias_model_args'] is None
                 and (dist.world > 1 or os.environ.get('LSS_SHARD_SINGLE')) and len(grids['dz'].shape) == 3 and len(grids['z0'].shape) == 2):
             # row-sharded solve: ownership follows the dz cells, which is the leading part of the sort key
             div = int(grids['z0'].shape[0]) * int(grids['z0'].shape[1]) * int(grids['dz'].shape[2])
@@ -710,6 +721,7 @@ def smooth_fit(**kwargs):
         y_d, x_d, t_d, z_d, s_d = (a[order].contiguous() for a in (y_d, x_d, t_d, z_d, s_d))
         tse_d = None if tse_d is None else tse_d[order].contiguous()
         bias_id_d = None if bias_id_d is None else bias_id_d[order].contiguous()
+        cov_d = {k: v[order].contiguous() for k, v in cov_d.items()}
         rz = rd = None
         stages.mark('spatial_sort')
     # ---- this rank's block of points
@@ -762,6 +774,12 @@ def smooth_fit(**kwargs):
             vals[~np.isfinite(vals)] = 1.
             scaling_masks[key] = vals
     setup_smoothness_constraints(grids, constraint_op_list, args['E_RMS'], args['mask_scale'], scaling_masks=scaling_masks)
+    # gridded biases that multiply a data parameter (setup_grid_bias.py:4-43; the live reference driver has no call site for
+    # it, smooth_fit.py:487-489 -- the keyword is the one of its predecessor, deprecated/smooth_xytb_fit.py:465-467)
+    if args['grid_bias_model_args'] is not None:
+        for bm_args in args['grid_bias_model_args']:
+            setup_grid_bias(data, G_data, constraint_op_list, grids, _pts=[y_d[lo:hi].contiguous(), x_d[lo:hi].contiguous()],
+                            _scale=cov_d[bm_args['param']][lo:hi].contiguous(), **bm_args)
     stages.mark('c:smoothness_ops')
     if args['bias_params'] is not None:
         n_bias = len(bias_model['bias_ID_dict'])

@@ -445,11 +445,14 @@ def bias_ids(params):
 
 
 def assemble(x, y, t, z, sigma, ctr, W, spacing, E_RMS, reference_epoch=0, mask_scale=None,
-             bias_params=None, sigma_corr=None):
+             bias_params=None, sigma_corr=None, grid_bias=None):
     """Everything smooth_fit builds before iterate_fit (smooth_fit.py:406-634), as plain arrays.
 
     Returns a dict with the canonical CSR of G_data and Gc (full column space), Ed, Ec, rhs,
     the kept (non reference-epoch) columns, the valid-point mask and bookkeeping.
+    ``grid_bias`` = dict(values, bounds=(y0, y1, x0, x1), spacing, expected_rms, expected_rms_grad): one gridded bias that
+    multiplies a per-point covariate (setup_grid_bias.py:4-43), placed where the reference's predecessor driver called it
+    (deprecated/smooth_xytb_fit.py:465-467): columns after dz, constraint rows after the smoothness families.
     """
     grids, _ = setup_grids(ctr, W, spacing)
     z0, dz = grids['z0'], grids['dz']
@@ -463,6 +466,25 @@ def assemble(x, y, t, z, sigma, ctr, W, spacing, E_RMS, reference_epoch=0, mask_
     vv = [v0.ravel(), v1.ravel()]
     col_N = dz['col_N']
     cons = smoothness_constraints(grids, E_RMS, mask_scale)
+    if grid_bias is not None:
+        b = grid_bias['bounds']
+        gb = grid_geometry([[b[0], b[1]], [b[2], b[3]]], grid_bias['spacing'] * np.ones(2), col_0=col_N, name='grid_bias')
+        rg, cg, vg = interp_triplets(gb, [ys, xs])
+        rr.append(rg.ravel())
+        cc.append(cg.ravel())
+        vv.append(vg.ravel() * grid_bias['values'][valid][rg.ravel()])          # setup_grid_bias.py:29
+        if grid_bias.get('expected_rms_grad') is not None:
+            for name, offs, coef in stencil_families(gb, 'grad2_z0'):
+                r_, c_, v_, i0 = stencil_triplets(gb, offs, coef)
+                # the division by sqrt(cell area) applies to a zero array in the reference (setup_grid_bias.py:33-34)
+                cons.append(dict(op='grad2_grid_bias', name=name + '_grid_bias', rows=r_, cols=c_, vals=v_, ind0=i0,
+                                 expected=grid_bias['expected_rms_grad'] + np.zeros(r_.shape[0])))
+        if grid_bias.get('expected_rms') is not None:
+            k = np.arange(gb['n_nodes'], dtype=np.int64)
+            cons.append(dict(op='mag_grid_bias', name='mag_grid_bias', rows=k[:, None], cols=(col_N + k)[:, None],
+                             vals=np.ones((k.size, 1)), ind0=np.zeros(0, dtype=np.int64),
+                             expected=grid_bias['expected_rms'] + np.zeros(k.size)))
+        col_N += gb['n_nodes']
     bias = None
     if bias_params is not None:
         ids, u = bias_ids([p[valid] for p in bias_params])
@@ -569,10 +591,10 @@ def iterate(sys_, max_iterations=10, min_iterations=2, converge_tol_dz=0.05, sig
 
 
 def smooth_fit(x, y, t, z, sigma, ctr, W, spacing, E_RMS, reference_epoch=0, max_iterations=10,
-               bias_params=None, sigma_corr=None, history=None, **kw):
+               bias_params=None, sigma_corr=None, history=None, grid_bias=None, **kw):
     """assemble + iterate; returns dict(m0, sigma_extra, in_TSE, z_est, valid, sys)."""
     s = assemble(x, y, t, z, sigma, ctr, W, spacing, E_RMS, reference_epoch,
-                 bias_params=bias_params, sigma_corr=sigma_corr)
+                 bias_params=bias_params, sigma_corr=sigma_corr, grid_bias=grid_bias)
     m0, se, tse, rs = iterate(s, max_iterations=max_iterations, history=history, **kw)
     G = csr_matrix(*s['G'][:3], shape=(s['n_data'], s['col_N']))
     return dict(m0=m0, sigma_extra=se, in_TSE=tse, rs_data=rs, z_est=G @ m0, valid=s['valid'], sys=s)

@@ -34,7 +34,7 @@ from lssurf_b200 import synthetic as S     # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable', 'uniform_masked', 'uniform_prior_dem',
-           'uniform_avg_masks', 'uniform_scaling_maps']
+           'uniform_avg_masks', 'uniform_scaling_maps', 'tracks_grid_bias']
 
 
 def digest(*arrays):
@@ -279,6 +279,20 @@ def case_widened(name, pts, kw, write):
     prior = kw.pop('prior_args', None)             # in-memory prior points: handed to the reference's make_prior_op
     avg_masks = kw.pop('avg_masks', None)          # named masks as arrays on the dz nodes; the reference asks them to interpolate
     scaling_maps = kw.pop('constraint_scaling_maps', None)     # per-node multipliers as arrays on the z0 / dz nodes
+    grid_bias = kw.pop('grid_bias_spec', None)                 # gridded bias x covariate: [param, grid bounds, spacing, rms, rms_grad]
+    orig_constraints = SF.setup_smoothness_constraints
+    if grid_bias is not None:
+        # the live reference driver has no call site for setup_grid_bias (smooth_fit.py:487-489); its predecessor called it
+        # right after the smoothness constraints (deprecated/smooth_xytb_fit.py:465-467), which is what this hook does with the
+        # driver's own data / G_data objects.  The grid object is rebuilt for every run (setup_grid_bias writes col_0 into it).
+        def constraints_then_grid_bias(grids, constraint_op_list, *a, **k):
+            orig_constraints(grids, constraint_op_list, *a, **k)
+            caller = sys._getframe(1).f_locals
+            b = grid_bias['bounds']
+            g = L.fd_grid([[b[0], b[1]], [b[2], b[3]]], [grid_bias['spacing']] * 2, name=grid_bias['param'] + '_bias')
+            L.setup_grid_bias(caller['data'], caller['G_data'], constraint_op_list, grids, param=grid_bias['param'], grid=g,
+                              expected_rms=grid_bias['expected_rms'], expected_value=0., expected_rms_grad=grid_bias['expected_rms_grad'])
+        SF.setup_smoothness_constraints = constraints_then_grid_bias
     if avg_masks is not None or scaling_maps is not None:
         class NodeMask(object):                    # what lin_op.mean_of_mask needs of a pointCollection grid (lin_op.py:352-354)
             def __init__(self, z):
@@ -326,7 +340,22 @@ def case_widened(name, pts, kw, write):
             out = L.smooth_fit(data=D.copy(), VERBOSE=False, **kw)
     finally:
         SF.calc_sigma_extra, SF.calc_sigma_extra_on_grid, sparseqr.solve = orig_se, orig_grid, orig_solve
+        SF.setup_smoothness_constraints = orig_constraints
     tse_ref = np.asarray(out['data'].three_sigma_edit, dtype=bool)
+    if grid_bias is not None:
+        # the oracle restates this composition (it is the CPU arm of the bench): pinned here bit for bit
+        res = O.smooth_fit(pts['x'], pts['y'], pts['time'], pts['z'], pts['sigma'], kw['ctr'], kw['W'], kw['spacing'], kw['E_RMS'],
+                           reference_epoch=kw['reference_epoch'], max_iterations=kw['max_iterations'],
+                           bias_params=[pts[k] for k in kw['bias_params']], sigma_corr=pts.get('sigma_corr'),
+                           grid_bias=dict(values=pts[grid_bias['param']], bounds=grid_bias['bounds'], spacing=grid_bias['spacing'],
+                                          expected_rms=grid_bias['expected_rms'], expected_rms_grad=grid_bias['expected_rms_grad']))
+        assert digest(*res['sys']['G'][:3]) == csr_digest(G_ref), 'oracle G with grid bias differs from the reference'
+        assert digest(*res['sys']['C'][:3]) == csr_digest(C_ref), 'oracle Gc with grid bias differs from the reference'
+        assert digest(res['sys']['Ec']) == digest(np.asarray(fo['Ec'], dtype=float))
+        assert np.array_equal(res['in_TSE'], tse_ref), 'oracle edit mask with grid bias differs'
+        rel = np.linalg.norm(res['m0'] - out['m']['all']) / np.linalg.norm(out['m']['all'])
+        print(f'   oracle with grid bias == reference: CSR / Ec / mask identical, rel-L2(m0) = {rel:.1e}')
+        assert rel < 1e-9
     n = int(out['valid_data'].size) if out['data'].size == out['valid_data'].size else int(out['data'].size)
     masks = [np.packbits(trace[k + 1]['mask_in']) for k in range(len(trace) - 1)] + [np.packbits(tse_ref)]
     m_ref = out['m']['all']
@@ -357,6 +386,11 @@ def case_widened(name, pts, kw, write):
             fx['kw'] = repr(kw)
             for k, v in avg_masks.items():
                 fx['avgmask_' + k] = np.asarray(v, dtype=float)
+        if grid_bias is not None:
+            fx['gridbias_param'] = grid_bias['param']
+            fx['gridbias_spec'] = np.array(list(grid_bias['bounds']) + [grid_bias['spacing'], grid_bias['expected_rms'], grid_bias['expected_rms_grad']], dtype=float)
+            c0, c1 = (int(v) for v in fo['G_data'].TOC['cols'][grid_bias['param'] + '_bias'][[0, -1]])
+            fx['gridbias_values'] = np.asarray(m_ref[c0:c1 + 1], dtype=float)
         if scaling_maps is not None:
             kw.pop('constraint_scaling_maps')
             fx['kw'] = repr(kw)
@@ -447,7 +481,14 @@ def widened_inputs():
     m_tt = np.ones((ndz, ndz)); m_tt[:3, :3] = 0.5
     m_dz = np.zeros((ndz, ndz)); m_dz[:2, :] = 0.05; m_dz[5, 5] = np.nan
     kw_i = dict(kwi, constraint_scaling_maps={'d2z0_dx2': m_z0, 'd3z_dx2dt': m_d3, 'd2z_dt2': m_tt, 'dz': m_dz}, max_iterations=3)
-    return (pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e), (ptf, kw_f), (ptg, kw_g), (pth, kw_h), (pti, kw_i)
+    # a gridded bias that multiplies a per-point covariate (setup_grid_bias.py:4-43; BASELINE configs[3]) next to the
+    # per-(rgt, cycle) biases: 17-entry rows, columns outside the z0 / dz grids and outside the eliminated block
+    ptj, kwj = S.icesat2_tracks(n=8000, width=1.2e4, seed=16, t_span=3.)
+    ptj['cov'] = np.sin(ptj['x'] / 2500.) + 0.1 * rng.standard_normal(ptj['x'].size)
+    ptj['z'] = ptj['z'] + ptj['cov'] * 0.15 * np.cos(ptj['y'] / 4000.)
+    kw_j = dict(kwj, grid_bias_spec=dict(param='cov', bounds=(-6e3, 6e3, -6e3, 6e3), spacing=3000., expected_rms=0.1, expected_rms_grad=1e-3))
+    return ((pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e), (ptf, kw_f), (ptg, kw_g), (pth, kw_h), (pti, kw_i),
+            (ptj, kw_j))
 
 
 def grid_bias_inputs():

@@ -67,6 +67,10 @@ def check_widened_outputs(fx, S):
             assert np.allclose(S['m'][name].cell_area, fx['avgarea_' + name], rtol=1e-12, atol=0), name
     if 'sigma_extra_final' in fx.files:
         assert np.max(np.abs(S['data'].sigma_extra - fx['sigma_extra_final'])) < 2e-5
+    if 'gridbias_values' in fx.files:
+        name = str(fx['gridbias_param']) + '_bias'
+        got = np.asarray(getattr(S['m']['grid_biases'][name], name)).ravel()
+        assert got.shape == fx['gridbias_values'].shape and np.max(np.abs(got - fx['gridbias_values'])) < 1e-6 * max(1., np.max(np.abs(fx['gridbias_values'])))
 
 
 def check_compute_E(Lp, **extra):

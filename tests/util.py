@@ -34,6 +34,13 @@ def load_case(name):
         kw['avg_masks'] = {f[len('avgmask_'):]: fx[f] for f in fx.files if f.startswith('avgmask_')}
     if any(f.startswith('scalemap_') for f in fx.files):     # constraint scaling maps, values on the z0 / dz nodes
         kw['constraint_scaling_maps'] = {f[len('scalemap_'):]: fx[f] for f in fx.files if f.startswith('scalemap_')}
+    if 'gridbias_spec' in fx.files:      # gridded bias x covariate (setup_grid_bias through the keyword of the deprecated driver)
+        import lssurf_b200
+        y0, y1, x0, x1, spacing, rms, rms_grad = (float(v) for v in fx['gridbias_spec'])
+        param = str(fx['gridbias_param'])
+        kw.pop('grid_bias_spec', None)
+        kw['grid_bias_model_args'] = [dict(param=param, expected_rms=rms, expected_value=0., expected_rms_grad=rms_grad,
+                                           grid=lssurf_b200.fd_grid([[y0, y1], [x0, x1]], [spacing, spacing], name=param + '_bias'))]
     if 'prior_meta' in fx.files:         # in-memory prior points of match_priors.match_prior_dz
         ref_epoch, sigma_scale, n_sets = fx['prior_meta']
         dzs = []
@@ -50,7 +57,7 @@ def rel_l2(a, b):
 FIT_CASES = ['strip_nb', 'strip_outliers', 'uniform3d_small', 'tracks_bias_small']
 # fixtures taken from the reference run alone (oracle/make_golden.py::case_widened)
 WIDENED_CASES = ['uniform_avg_scales', 'uniform_groups_editable', 'tracks_bias_edit', 'uniform_sigma_grid', 'tracks_sensor_slope',
-                 'uniform_masked', 'uniform_prior_dem', 'uniform_avg_masks', 'uniform_scaling_maps']
+                 'uniform_masked', 'uniform_prior_dem', 'uniform_avg_masks', 'uniform_scaling_maps', 'tracks_grid_bias']
 
 
 def check_parse_model_outputs(fx, S):
