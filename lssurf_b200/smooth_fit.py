@@ -311,11 +311,10 @@ def iterate_fit_device(data, Gcoo, rhs, TCinv, G_data, Gc, in_TSE, Ip_c, timing,
             sigma_extra, se_values = sigma_extra_device(r_data, sigma, in_TSE_d, groups, comm, out=sigma_extra)
         else:
             # spatially varying sigma_extra on overlapping bins (smooth_fit.py:154-158)
-            if comm is not None:
-                raise NotImplementedError('sigma_extra_bin_spacing is single-GPU only')
             sigma_extra, se_values = sigma_extra_on_grid_device(
                 _field_dev(data, 'x'), _field_dev(data, 'y'), r_data, sigma, in_TSE_d, groups,
-                spacing=args['sigma_extra_bin_spacing'], sigma_extra_max=args.get('sigma_extra_max'))
+                spacing=args['sigma_extra_bin_spacing'], sigma_extra_max=args.get('sigma_extra_max'), comm=comm,
+                dist=dist if multi else None)
         st.mark('it:sigma_extra')
         in_TSE_last = in_TSE_d
         in_TSE_d, est = _cabi.edit_mask(r_data, sigma, sigma_extra, 3.0, comm)

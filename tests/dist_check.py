@@ -34,6 +34,10 @@ def main():
              ('tracks_bias', synthetic.icesat2_tracks(n=int(300_000 * scale), width=2.e4 * scale ** 0.5, seed=4)),
              # wide enough for the two-level preconditioner (>= 2000 dz nodes) on top of the bias elimination
              ('tracks_bias_coarse', synthetic.icesat2_tracks(n=int(400_000 * scale), width=5.e4 * scale ** 0.5, seed=5))]
+    # spatially varying sigma_extra: the bins are global, every rank holds a slice of each (points stay in the caller's order)
+    pb, kb = synthetic.uniform_3d(n=int(120_000 * scale), width=2.e4 * scale ** 0.5, seed=6)
+    pb['z'] = pb['z'] + np.random.default_rng(6).normal(0, 1., pb['x'].size) * 0.3 * (pb['x'] > 0)
+    cases.append(('uniform_sigma_bins', (pb, dict(kb, sigma_extra_bin_spacing=5.e3 * scale ** 0.5, sigma_extra_max=5.))))
     ok = True
     single = {}
     for name, (pts, kw) in cases:

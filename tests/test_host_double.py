@@ -119,7 +119,7 @@ def test_bias_filter_groups_like_the_filtered_parameters(double):
     assert a['G_data'].shape[1] < int(fx['G_shape'][1])          # fewer bias columns than one per (rgt, cycle)
 
 
-@pytest.mark.parametrize('name', ['tracks_bias_small', 'tracks_sensor_slope', 'tracks_bias_edit', 'uniform_groups_editable'])
+@pytest.mark.parametrize('name', ['tracks_bias_small', 'tracks_sensor_slope', 'tracks_bias_edit', 'uniform_groups_editable', 'uniform_sigma_grid'])
 def test_two_rank_row_sharding_reproduces_the_fixture(name, tmp_path):
     """World size 2 over gloo, host double on each rank (tests/two_rank_worker.py): every rank assembles only its block of
     data rows (bias, slope and sensor-grid rows included), the replicated solve sees the gathered rows, per-point outputs
