@@ -58,8 +58,10 @@ def main():
             rel = float(np.linalg.norm(S['m']['all'] - S1['m']['all']) / np.linalg.norm(S1['m']['all']))
             same_final = bool(np.array_equal(S['data'].three_sigma_edit, S1['data'].three_sigma_edit))
             same_count = [h['count'] for h in hist] == [h['count'] for h in hist1]
-            same_masks = len(hist) == len(hist1) and all(np.array_equal(a['mask_out'], b['mask_out']) for a, b in zip(hist, hist1)) \
-                if mode == 'p2p' else same_count          # the other modes record rank-local masks
+            # the row-sharded mode records global masks; the others (and fits that cannot be row-sharded, e.g. with gridded
+            # sigma_extra) record rank-local ones, whose global counts are compared instead
+            global_masks = mode == 'p2p' and len(hist) == len(hist1) and all(a['mask_out'].size == b['mask_out'].size for a, b in zip(hist, hist1))
+            same_masks = all(np.array_equal(a['mask_out'], b['mask_out']) for a, b in zip(hist, hist1)) if global_masks else same_count
             dz_est = float(np.max(np.abs(S['data'].z_est - S1['data'].z_est)))
             cnt = float(np.nanmax(np.abs(S['m']['z0'].count - S1['m']['z0'].count)))
             mis = float(np.nanmax(np.abs(S['m']['dz'].misfit_rms - S1['m']['dz'].misfit_rms)))

@@ -9,8 +9,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 import lssurf_b200 as L
-from lssurf_b200 import synthetic
+from lssurf_b200 import synthetic, parallel
 import lssurf_b200.smooth_fit          # noqa: F401
+
+ctx = parallel.init_from_env()          # under torchrun: the row-sharded multi-GPU fit, rank 0 reports
 
 SF = sys.modules['lssurf_b200.smooth_fit']
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
@@ -30,7 +32,7 @@ class Stages(object):          # stage boundaries as host timestamps WITHOUT dev
 
 def fit():
     D = L.point_data.data().from_dict({f: dev[f] for f in fields})
-    return L.smooth_fit(data=D, VERBOSE=False, **kw)
+    return L.smooth_fit(data=D, VERBOSE=False, dist=ctx if ctx.world > 1 else None, **kw)
 
 
 S = None
@@ -43,6 +45,11 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     S = fit()
     torch.cuda.synchronize()
     t_host1 = time.perf_counter_ns()
+if ctx.rank != 0:
+    import torch.distributed as td
+    td.barrier()
+    ctx.destroy()
+    sys.exit(0)
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 print('fit wall %.1f ms, %d device events' % ((t_host1 - t_host0) / 1e6, len(ev)))
 iv = sorted((e.time_range.start, e.time_range.end, e.name) for e in ev)
@@ -78,3 +85,8 @@ for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
 # host-side stage boundaries -> which stage each gap falls in (device timestamps and perf_counter share no epoch:
 # align the first mark with the first device event of the fit, good to a few 100 us)
 print('host stage marks (ms since start):', [(nm, round((t - marks[0][1]) / 1e6, 1)) for nm, t in marks])
+
+if ctx.world > 1:
+    import torch.distributed as td
+    td.barrier()
+    ctx.destroy()
