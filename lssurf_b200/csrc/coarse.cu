@@ -1,4 +1,6 @@
 // Coarse level of the two-level preconditioner: Galerkin set-up, dense inverse, stand-alone apply (see coarse.cuh).
+#include <stdlib.h>
+
 #include <cooperative_groups.h>
 
 #include "coarse.cuh"
@@ -111,6 +113,119 @@ gj_inverse_kernel(int n, double *X, double *Y, int *bad) {
         }
         grid.sync();
         double *t = src; src = dst; dst = t;
+    }
+}
+
+// Blocked Gauss-Jordan inverse (32 x 32 blocks, no pivoting: S_c is symmetric positive definite), ping-pong like the plain
+// sweep above but ONE grid barrier per block of 32 pivots instead of one per pivot (721 unknowns: 23 barriers instead of 721,
+// 3.7 ms -> a few hundred microseconds).  Step k, with D = src[k][k]:
+//     dst[k][k] = D^-1,   dst[k][j] = D^-1 src[k][j],   dst[i][k] = -src[i][k] D^-1,   dst[i][j] = src[i][j] - src[i][k] D^-1 src[k][j].
+// Every CTA inverts the pivot block itself in shared memory (the same sweep on 32 x 32, padded with the identity in the last
+// block), so no barrier is needed between the pivot inverse and the tile updates; the tiles (i, j) are shared out over the grid.
+// After ceil(n / 32) steps the inverse is in (steps odd ? Y : X).
+constexpr int GJB = 32;
+__global__ void __launch_bounds__(256)
+gj_block_inverse_kernel(int n, double *X, double *Y, int *bad) {
+    cgx::grid_group grid = cgx::this_grid();
+    __shared__ double D[2][GJB][GJB + 1];
+    __shared__ double Ta[GJB][GJB + 1], Tb[GJB][GJB + 1];
+    __shared__ int s_bad;
+    const int nb = (n + GJB - 1) / GJB;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8 threads, rows ty + 8 u
+    double *src = X, *dst = Y;
+    for (int kb = 0; kb < nb; ++kb) {
+        const int k0 = kb * GJB, kn = min(GJB, n - k0);
+        for (int r = ty; r < GJB; r += 8)
+            D[0][r][tx] = (r < kn && tx < kn) ? src[(size_t)(k0 + r) * n + k0 + tx] : (r == tx ? 1.0 : 0.0);
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+        int cur = 0;
+        for (int p = 0; p < GJB; ++p) {
+            const double piv = D[cur][p][p];
+            if (!(piv > 0.0) || !(piv < 1e300)) {
+                if (threadIdx.x == 0) s_bad = 1;
+            } else {
+                const double ip = 1.0 / piv;
+                const double pk = D[cur][p][tx] * ip;
+                for (int r = ty; r < GJB; r += 8) {
+                    double v;
+                    if (r == p) {
+                        v = (tx == p) ? ip : pk;
+                    } else {
+                        const double f = D[cur][r][p];
+                        v = (tx == p) ? -f * ip : D[cur][r][tx] - f * pk;
+                    }
+                    D[cur ^ 1][r][tx] = v;
+                }
+            }
+            __syncthreads();
+            if (s_bad) break;               // every CTA holds the same block: the same decision everywhere
+            cur ^= 1;
+        }
+        if (s_bad) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) *bad = 1;
+            return;
+        }
+        const double (*Di)[GJB + 1] = D[cur];
+        for (int t = blockIdx.x; t < nb * nb; t += gridDim.x) {
+            const int ib = t / nb, jb = t - ib * nb;
+            const int i0 = ib * GJB, j0 = jb * GJB, in = min(GJB, n - i0), jn = min(GJB, n - j0);
+            if (ib == kb && jb == kb) {
+                for (int r = ty; r < kn; r += 8)
+                    if (tx < kn) dst[(size_t)(k0 + r) * n + k0 + tx] = Di[r][tx];
+                continue;                    // uniform per CTA: no barrier skipped by part of the block
+            }
+            // stage src[i][k] (in x kn) and src[k][j] (kn x jn), zero padded
+            for (int r = ty; r < GJB; r += 8) {
+                Ta[r][tx] = (ib != kb && r < in && tx < kn) ? src[(size_t)(i0 + r) * n + k0 + tx] : 0.0;
+                Tb[r][tx] = (jb != kb && r < kn && tx < jn) ? src[(size_t)(k0 + r) * n + j0 + tx] : 0.0;
+            }
+            __syncthreads();
+            if (ib == kb) {                  // dst[k][j] = D^-1 src[k][j]
+                for (int r = ty; r < kn; r += 8) {
+                    double acc = 0.0;
+#pragma unroll 8
+                    for (int m = 0; m < GJB; ++m) acc += Di[r][m] * Tb[m][tx];
+                    if (tx < jn) dst[(size_t)(k0 + r) * n + j0 + tx] = acc;
+                }
+            } else {
+                double tv[4];                // T = src[i][k] D^-1
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = ty + 8 * u;
+                    double acc = 0.0;
+#pragma unroll 8
+                    for (int m = 0; m < GJB; ++m) acc += Ta[r][m] * Di[m][tx];
+                    tv[u] = acc;
+                }
+                if (jb == kb) {              // dst[i][k] = -T
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = ty + 8 * u;
+                        if (r < in && tx < kn) dst[(size_t)(i0 + r) * n + k0 + tx] = -tv[u];
+                    }
+                } else {                     // dst[i][j] = src[i][j] - T src[k][j]
+                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) Ta[ty + 8 * u][tx] = tv[u];
+                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = ty + 8 * u;
+                        double acc = 0.0;
+#pragma unroll 8
+                        for (int m = 0; m < GJB; ++m) acc += Ta[r][m] * Tb[m][tx];
+                        if (r < in && tx < jn) {
+                            const size_t o = (size_t)(i0 + r) * n + j0 + tx;
+                            dst[o] = src[o] - acc;
+                        }
+                    }
+                }
+            }
+            __syncthreads();                 // Ta / Tb are restaged by the next tile
+        }
+        grid.sync();
+        double *tmp = src; src = dst; dst = tmp;
     }
 }
 
@@ -241,17 +356,28 @@ int coarse_factor(CoarseSpace *cs, int64_t n_rows, const int32_t *indptr, const 
     }
     coarse_fix_diag_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, cs->A);
     LSS_LAUNCH_CHECK();
+    const bool plain = getenv("LSS_GJ_PLAIN") != nullptr;       // the one-barrier-per-pivot sweep, kept for cross-checks
+    int steps = n;
     {
         int nn_i = n;
         double *X = cs->A, *Y = cs->A2;
         int *bad = cs->bad;
         void *args[] = {&nn_i, &X, &Y, &bad};
-        int grid = 2 * kSMs;
-        if (grid > n) grid = n;
-        LSS_CUDA(cudaLaunchCooperativeKernel((void *)gj_inverse_kernel, dim3(grid), dim3(256), args, 0, st));
+        if (plain) {
+            int grid = 2 * kSMs;
+            if (grid > n) grid = n;
+            LSS_CUDA(cudaLaunchCooperativeKernel((void *)gj_inverse_kernel, dim3(grid), dim3(256), args, 0, st));
+        } else {
+            steps = (n + GJB - 1) / GJB;
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gj_block_inverse_kernel, 256, 0);
+            int grid = kSMs * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
+            if (grid > steps * steps) grid = steps * steps;
+            LSS_CUDA(cudaLaunchCooperativeKernel((void *)gj_block_inverse_kernel, dim3(grid), dim3(256), args, 0, st));
+        }
         ++g_launches;
     }
-    double *res = (n & 1) ? cs->A2 : cs->A, *other = (n & 1) ? cs->A : cs->A2;
+    double *res = (steps & 1) ? cs->A2 : cs->A, *other = (steps & 1) ? cs->A : cs->A2;
     symmetrise_kernel<<<ceil_div((int64_t)nn, 256), 256, 0, st>>>(n, res, other);
     LSS_LAUNCH_CHECK();
     cs->inv = other;

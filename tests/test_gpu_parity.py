@@ -514,7 +514,9 @@ def test_two_level_preconditioner_agrees_with_block_jacobi(L, monkeypatch):
         pts, kw = gen(n=n, width=width, seed=11)
         out = {}
         for key, env in (('bj', {'LSS_COARSE': '0'}), ('ml', {'LSS_COARSE': '1', 'LSS_COARSE_MIN_BLOCKS': '1'}),
-                         ('ml_refresh', {'LSS_COARSE': '1', 'LSS_COARSE_MIN_BLOCKS': '1', 'LSS_COARSE_REFRESH': '1'})):
+                         ('ml_refresh', {'LSS_COARSE': '1', 'LSS_COARSE_MIN_BLOCKS': '1', 'LSS_COARSE_REFRESH': '1'}),
+                        # the coarse inverse by the plain Gauss-Jordan sweep (one grid barrier per pivot) instead of the blocked one
+                        ('ml_plain_gj', {'LSS_COARSE': '1', 'LSS_COARSE_MIN_BLOCKS': '1', 'LSS_GJ_PLAIN': '1'})):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             hist = []
@@ -525,7 +527,8 @@ def test_two_level_preconditioner_agrees_with_block_jacobi(L, monkeypatch):
         assert out['bj']['timing']['pcg'][0]['coarse'] == 0 and out['ml']['timing']['pcg'][0]['coarse'] > 0
         its = {k: sum(p['iterations'] for p in o['timing']['pcg']) for k, o in out.items()}
         print(gen.__name__, 'CG iterations', its, 'coarse unknowns', out['ml']['timing']['pcg'][0]['coarse'])
-        for key in ('ml', 'ml_refresh'):
+        assert abs(its['ml'] - its['ml_plain_gj']) <= 3, its          # the two inverses agree to rounding
+        for key in ('ml', 'ml_refresh', 'ml_plain_gj'):
             assert rel_l2(out[key]['m']['all'], out['bj']['m']['all']) < 1e-9, key
             assert len(out[key]['hist']) == len(out['bj']['hist'])
             for a, b in zip(out[key]['hist'], out['bj']['hist']):
