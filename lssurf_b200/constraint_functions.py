@@ -57,6 +57,17 @@ def setup_smoothness_constraints(grids, constraint_op_list, E_RMS, mask_scale, s
         mag_dz = lin_op(dz, name='dz_zero').one(DOF='dz', which_nodes=ind + dz.col_0)
         mag_dz.expected = e_dz[ind]
         constraint_op_list += [mag_dz]
+    if E_RMS.get('lagrangian_dz') is not None or E_RMS.get('lagrangian_dzdx') is not None:
+        lag = grids['lagrangian_dz']
+        root_area_lag = np.sqrt(lag.delta[0] * lag.delta[1])
+        if E_RMS.get('lagrangian_dz') is not None:             # magnitude of the lagrangian offsets (:95-99)
+            op = lin_op(lag, name='lagrangian_rms').one(DOF='lagrangian_dz')
+            op.expected = np.zeros(op.N_eq) + E_RMS['lagrangian_dz'] / root_area_lag
+            constraint_op_list += [op]
+        if E_RMS.get('lagrangian_dzdx') is not None:           # and of their gradient (:101-105)
+            op = lin_op(lag, name='lagrangian_rms_grad').grad(DOF='lagrangian_dz')
+            op.expected = np.zeros(op.N_eq) + E_RMS['lagrangian_dzdx'] / root_area_lag
+            constraint_op_list += [op]
     for op in constraint_op_list:
         if np.any(op.expected == 0):
             raise ValueError(f'found zero value in the expected values for {op.name}')

@@ -75,8 +75,6 @@ def setup_grids(args):
         z0_mask, dz_mask = mask_data.get('z0'), mask_data.get('dz')
     elif mask_data is not None:
         raise NotImplementedError('mask_data must be a dict {"z0": array, "dz": array} of NumPy masks')
-    if args.get('lagrangian_coords') is not None:
-        raise NotImplementedError('lagrangian_dz grids are outside the hot-path scope (SURVEY.md section 8(f))')
     srs = args.get('srs_proj4')
     erode = args.get('erode_source_mask', True)
     grids = dict()
@@ -89,6 +87,10 @@ def setup_grids(args):
                           erode_source_mask=erode)
     grids['t'] = fd_grid([bds['t']], [args['spacing']['dt']], name='t')
     grids['z0'].cell_area = calc_cell_area(grids['z0'])
+    if args.get('lagrangian_coords') is not None:
+        # a 2-D grid of height offsets in the coordinates that move with the ice (grid_functions.py:89-93)
+        grids['lagrangian_dz'] = fd_grid([bds['y'], bds['x']], [args['spacing']['lagrangian_dz'], args['spacing']['lagrangian_dz']],
+                                         name='lagrangian_dz', col_0=grids['z0'].N_nodes + grids['dz'].N_nodes, srs_proj4=srs)
     if np.any(grids['dz'].delta[0:2] >= grids['z0'].delta):
         grids['dz'].cell_area = sum_cell_area(grids['z0'], grids['dz'])
     else:

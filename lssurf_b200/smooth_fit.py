@@ -57,7 +57,7 @@ DEFAULTS = {
     'time_stages': False, 'sort_points': True,
 }
 
-_UNSUPPORTED = ('mask_file', 'prior_edge_args', 'lagrangian_coords')
+_UNSUPPORTED = ('mask_file', 'prior_edge_args')
 
 
 class _Stages(object):
@@ -431,6 +431,11 @@ def parse_model(m, m0, dev_fields, R, RMS, G_data, averaging_ops, Gc, Ec, grids,
     m['dz'] = grid_data().from_dict({'x': dzg.ctrs[1], 'y': dzg.ctrs[0], 'time': dzg.ctrs[2],
                                      'dz': np.reshape(m0[G_data.TOC['cols']['dz']], dzg.shape),
                                      'cell_area': dzg.cell_area, 'mask': dzg.mask})
+    if 'lagrangian_dz' in grids:
+        lg = grids['lagrangian_dz']
+        m['lagrangian_dz'] = grid_data().from_dict({'x': lg.ctrs[1], 'y': lg.ctrs[0],
+                                                    'dz': np.reshape(m0[G_data.TOC['cols']['lagrangian_dz']], lg.shape),
+                                                    'cell_area': lg.cell_area, 'mask': lg.mask})
     for key, op in averaging_ops.items():
         fields = {coord: ctr for coord, ctr in zip(op.dst_grid.coords, op.dst_grid.ctrs)}
         fields.update({'cell_area': op.dst_grid.cell_area, key: op.grid_prod(m0)})
@@ -708,6 +713,7 @@ def smooth_fit(**kwargs):
     shard = None
     if (args['sort_points'] and os.environ.get('LSS_SORT_POINTS', '1') != '0' and not args['return_fit_objects'] and args['bias_nsigma_edit'] is None
             and args['bias_edit_vals'] is None and 'editable' not in data.fields and args['sigma_extra_masks'] is None and args['DEM_tol'] is None
+            and args['lagrangian_coords'] is None
             and args['data_slope_sensors'] is None and args['sensor_grid_bias_params'] is None
             and args['sigma_extra_bin_spacing'] is None and n_all > 1):
         order, keys = _cabi.spatial_order(grids['z0'].as_struct(), grids['dz'].as_struct(), [y_d, x_d, t_d], return_keys=True)
@@ -753,6 +759,11 @@ def smooth_fit(**kwargs):
     G_data = op_z0
     G_data.add(op_dz)
     del rz, rd
+    if args['lagrangian_coords'] is not None:
+        # height offsets on a grid in the coordinates that move with the ice; points without such coordinates (NaN / outside)
+        # get no entry (smooth_fit.py:463-465, interp_mtx with bounds_error=False).  Rows stay in the caller's order.
+        lag_pts = [_field_dev(data, f)[lo:hi].contiguous() for f in args['lagrangian_coords']]
+        G_data.add(lin_op(grids['lagrangian_dz'], name='interp_lagrangian_dz').interp_mtx(lag_pts, bounds_error=False))
     z_loc, s_loc = z_d[lo:hi].contiguous(), s_d[lo:hi].contiguous()
 
     stages.mark('G_data')

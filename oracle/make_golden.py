@@ -34,7 +34,8 @@ from lssurf_b200 import synthetic as S     # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 WIDENED = ['tracks_sensor_slope', 'uniform_sigma_grid', 'uniform_avg_scales', 'tracks_bias_edit', 'uniform_groups_editable', 'uniform_masked', 'uniform_prior_dem',
-           'uniform_avg_masks', 'uniform_scaling_maps', 'tracks_grid_bias']
+           'uniform_avg_masks', 'uniform_scaling_maps', 'tracks_grid_bias',
+           'uniform_lagrangian']
 
 
 def digest(*arrays):
@@ -370,6 +371,8 @@ def case_widened(name, pts, kw, write):
                   n_outer=len(solves), kw=repr(kw),
                   toc_rows=np.array([f'{k}:{len(np.unique(v))}' for k, v in fo['Gc'].TOC['rows'].items()]),
                   toc_cols=np.array([f'{k}:{int(np.min(v))}:{int(np.max(v))}' for k, v in fo['G_data'].TOC['cols'].items()]))
+        if 'lagrangian_dz' in out['m']:
+            fx['lagrangian_dz'] = np.asarray(out['m']['lagrangian_dz'].dz, dtype=float)
         for key, g in out['m'].get('sensor_bias_grids', {}).items():
             fx['grid_' + key] = np.asarray(g.z)
         for key, g in out['m'].items():                      # dz/dt and block-average grids (setup_averaging_ops)
@@ -487,8 +490,18 @@ def widened_inputs():
     ptj['cov'] = np.sin(ptj['x'] / 2500.) + 0.1 * rng.standard_normal(ptj['x'].size)
     ptj['z'] = ptj['z'] + ptj['cov'] * 0.15 * np.cos(ptj['y'] / 4000.)
     kw_j = dict(kwj, grid_bias_spec=dict(param='cov', bounds=(-6e3, 6e3, -6e3, 6e3), spacing=3000., expected_rms=0.1, expected_rms_grad=1e-3))
+    # height offsets on a grid in coordinates that move with the ice (lagrangian_coords: smooth_fit.py:463-465,
+    # grid_functions.py:89-93, constraint_functions.py:95-105): two thirds of the points carry such coordinates, the
+    # rest NaN (no entry in those rows), a few fall outside the grid
+    ptk, kwk = S.uniform_3d(n=6000, width=1.2e4, seed=18)
+    has = rng.random(ptk['x'].size) < 0.66
+    ptk['x0'] = np.where(has, ptk['x'] - 150. * ptk['time'], np.nan)          # advected back to t = 0
+    ptk['y0'] = np.where(has, ptk['y'] + 60. * ptk['time'], np.nan)
+    ptk['z'] = ptk['z'] + np.where(has, 0.5 * np.sin(ptk['x0'] / 1500.) * np.cos(ptk['y0'] / 2500.), 0.)
+    kw_k = dict(kwk, lagrangian_coords=['y0', 'x0'], spacing=dict(kwk['spacing'], lagrangian_dz=1000.),
+                E_RMS=dict(kwk['E_RMS'], lagrangian_dz=50., lagrangian_dzdx=0.5), max_iterations=4)
     return ((pts, kw_a), (ptu, kw_b), (ptc, kw_c), (ptd, kw_d), (pte, kw_e), (ptf, kw_f), (ptg, kw_g), (pth, kw_h), (pti, kw_i),
-            (ptj, kw_j))
+            (ptj, kw_j), (ptk, kw_k))
 
 
 def grid_bias_inputs():

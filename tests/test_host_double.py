@@ -67,6 +67,9 @@ def check_widened_outputs(fx, S):
             assert np.allclose(S['m'][name].cell_area, fx['avgarea_' + name], rtol=1e-12, atol=0), name
     if 'sigma_extra_final' in fx.files:
         assert np.max(np.abs(S['data'].sigma_extra - fx['sigma_extra_final'])) < 2e-5
+    if 'lagrangian_dz' in fx.files:
+        got, want = np.asarray(S['m']['lagrangian_dz'].dz), fx['lagrangian_dz']
+        assert got.shape == want.shape and np.max(np.abs(got - want)) < 1e-6 * max(1., np.max(np.abs(want)))
     if 'gridbias_values' in fx.files:
         name = str(fx['gridbias_param']) + '_bias'
         got = np.asarray(getattr(S['m']['grid_biases'][name], name)).ravel()

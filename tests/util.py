@@ -57,7 +57,8 @@ def rel_l2(a, b):
 FIT_CASES = ['strip_nb', 'strip_outliers', 'uniform3d_small', 'tracks_bias_small']
 # fixtures taken from the reference run alone (oracle/make_golden.py::case_widened)
 WIDENED_CASES = ['uniform_avg_scales', 'uniform_groups_editable', 'tracks_bias_edit', 'uniform_sigma_grid', 'tracks_sensor_slope',
-                 'uniform_masked', 'uniform_prior_dem', 'uniform_avg_masks', 'uniform_scaling_maps', 'tracks_grid_bias']
+                 'uniform_masked', 'uniform_prior_dem', 'uniform_avg_masks', 'uniform_scaling_maps', 'tracks_grid_bias',
+                 'uniform_lagrangian']
 
 
 def check_parse_model_outputs(fx, S):
