@@ -83,6 +83,10 @@ def workload_config(a):
                         "bias_params=['rgt','cycle']%s, max_iterations=10" % (a.points, a.width / 1e3, a.width / 1e3,
                                                                                ' + setup_grid_bias term (10 km grid)' if a.grid_bias else ''),
             'points': a.points, 'extent_km': a.width / 1e3, 'parallelism': par,
+            'grid_bias_term': ('in the timed workload (covariate x 10 km grid)' if a.grid_bias else
+                               'not in the timed workload (no call site in the reference smooth_fit; its columns cannot be owned by one '
+                               'rank of the row-sharded solver, and the workload is the same at every GPU count); measured untimed in '
+                               'roofline.grid_bias_variant at N = 1, timed with --grid-bias'),
             'l2_policy': 'inputs larger than L2 (N streamed per CG iteration is 0.37 GB at N=1, A is 1.7 GB)'}
 
 

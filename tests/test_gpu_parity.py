@@ -189,6 +189,17 @@ def test_rmatvec_and_spatial_order(L):
     got = A.rdot(_c.to_dev(u)).cpu().numpy()
     want = M.T.dot(u)
     assert np.max(np.abs(got - want)) <= 1e-13 * np.abs(M).T.dot(np.abs(u)).max()
+    # rows that repeat a few column templates in runs AND interleaved (A B A B ...): the warp folds runs of equal columns
+    # before the atomics, and equal columns that are not adjacent must not be folded across the row in between
+    tmpl = [np.sort(rng.choice(400, 6, replace=False)) for _ in range(3)] + [np.sort(rng.choice(400, 3, replace=False))]
+    which = np.concatenate([np.repeat([0, 1, 2, 3], 37), np.tile([0, 1], 64), rng.integers(0, 4, 4000)])
+    cols = np.concatenate([tmpl[w] for w in which])
+    ptr = np.concatenate([[0], np.cumsum([tmpl[w].size for w in which])])
+    T = sp.csr_matrix((rng.normal(size=cols.size), cols.astype(np.int32), ptr.astype(np.int32)), shape=(which.size, 400))
+    B = L.DeviceCSR(_c.to_dev(T.indptr.astype(np.int32)), _c.to_dev(T.indices.astype(np.int32)), _c.to_dev(T.data), T.shape)
+    v = rng.normal(size=T.shape[0]); v[::5] = 0.
+    got, want = B.rdot(_c.to_dev(v)).cpu().numpy(), T.T.dot(v)
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.abs(T).T.dot(np.abs(v)).max()
     fine = L.fd_grid([[0., 100.], [0., 100.]], [1., 1.], name='z0')
     coarse = L.fd_grid([[0., 100.], [0., 100.], [0., 2.]], [4., 4., 0.5], name='dz')
     y, x, t = rng.uniform(0, 100, 5000), rng.uniform(0, 100, 5000), rng.uniform(0, 2, 5000)
