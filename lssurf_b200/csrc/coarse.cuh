@@ -16,7 +16,7 @@
 
 namespace lss {
 
-constexpr int CS_MAX = 1024;      // largest coarse space (the step kernel keeps r_c / z_c in shared memory)
+constexpr int CS_MAX = 1024;      // largest coarse space (the step kernel keeps r_c / z_c in shared memory); 2048 was measured: no gain
 
 struct CoarseSpace {
     int n_c;                      // coarse unknowns

@@ -125,7 +125,7 @@ def _coarse_1d(nf, c):
     return coarse.size, lo.astype(np.int64), hi.astype(np.int64), w.astype(np.float64)
 
 
-def coarse_structure(grids, fixed_cols, n_cols, max_coarse=1024, owned=None):
+def coarse_structure(grids, fixed_cols, n_cols, max_coarse=None, owned=None):
     """Coarse space of the two-level preconditioner (``lss_solver_set_coarse``): bilinear functions of (y, x) on a grid
     c times coarser than z0 / dz (same factor for both, every epoch of dz kept), c the smallest power of two that
     leaves at most ``max_coarse`` coarse unknowns.  Returns device tensors: per fine column its <= 4 parents and
@@ -135,6 +135,8 @@ def coarse_structure(grids, fixed_cols, n_cols, max_coarse=1024, owned=None):
     z0, dz = grids.get('z0'), grids.get('dz')
     if z0 is None or dz is None or len(z0.shape) != 2 or len(dz.shape) != 3:
         return None
+    if max_coarse is None:
+        max_coarse = min(int(os.environ.get('LSS_COARSE_MAX', '1024')), 1024)      # CS_MAX of the library
     ny0, nx0 = (int(v) for v in z0.shape)
     ny, nx, nt = (int(v) for v in dz.shape)
     c = 2
