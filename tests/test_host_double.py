@@ -101,6 +101,25 @@ def test_compute_E_against_reference_fixture(double):
     check_compute_E(L, sort_points=False)
 
 
+def test_mask_update_function_sees_the_parsed_model(double):
+    """mask_update_function (smooth_fit.py:664-666): called once after the edit loop with (grids, m, args), m already parsed
+    (no averaging grids yet); what it does to the grids is seen by the averaging operators built afterwards."""
+    fx, pts, kw = load_case('uniform_avg_scales')
+    seen = {}
+
+    def hook(grids, m, args):
+        seen['keys'] = sorted(m)
+        seen['dz_shape'] = m['dz'].dz.shape
+        seen['n_calls'] = seen.get('n_calls', 0) + 1
+        grids['dz'].cell_area = grids['dz'].cell_area * 2.          # doubles the areas the block averages report
+    S = L.smooth_fit(data=make_data(pts), VERBOSE=False, sort_points=False, mask_update_function=hook, **kw)
+    assert seen['n_calls'] == 1 and 'z0' in seen['keys'] and 'dz' in seen['keys'] and not any(k.startswith('avg_') for k in seen['keys'])
+    assert seen['dz_shape'] == tuple(S['grids']['dz'].shape)
+    assert rel_l2(S['m']['all'], fx['m0']) < 1e-6
+    name = [k for k in fx.files if k.startswith('avgarea_avg_dz_')][0][len('avgarea_'):]
+    assert np.allclose(S['m'][name].cell_area, 2. * fx['avgarea_' + name], rtol=1e-12)
+
+
 def test_double_is_removed_afterwards():
     from lssurf_b200 import _cabi
     assert _cabi.interp_coo.__module__ == 'lssurf_b200._cabi' and _cabi.device.__module__ == 'lssurf_b200._cabi'
