@@ -187,3 +187,47 @@ def setup_avg_mask_ops(grid, col_N, avg_masks, dzdt_lags):
             this_name = name + f'_avg_dzdt_lag{lag}'
             avg_ops[this_name] = lin_op(grid, col_N=col_N, name=this_name).mean_of_mask(mask, dzdt_lag=lag)
     return avg_ops
+
+
+def _drop_points(data, valid_data, keep):
+    """Shared tail of setup_mask / validate_by_dz_mask (grid_functions.py:341-343, 372-374): subset ``data`` in place and
+    fold the decision into the caller's valid-point mask."""
+    if not np.all(keep):
+        data.index(keep)
+        valid_data[valid_data] = keep
+
+
+def validate_by_dz_mask(data, grids, valid_data):
+    """Mark the points under masked-out dz nodes invalid (grid_functions.py:346-374): the dz mask (2-D, or ``mask_3d``)
+    interpolated to each point must exceed 0.5.  Same in-place behaviour as the reference: ``data`` is subset, ``valid_data``
+    updated.  The interpolation runs on the GPU (``lss_interp_coo``)."""
+    import torch
+    from . import _cabi
+    from .smooth_fit import _validate_by_dz_mask_device
+    y, x = (_cabi.to_dev(np.asarray(c, dtype=float), torch.float64) for c in data.coords()[0:2])
+    t = _cabi.to_dev(np.asarray(data.coords()[2], dtype=float), torch.float64) if len(data.coords()) > 2 else None
+    keep = _validate_by_dz_mask_device(grids, y, x, t)
+    if keep is not None:
+        _drop_points(data, valid_data, _cabi.to_host(keep.to(torch.uint8)).astype(bool))
+
+
+def setup_mask(data, grids, valid_data, bds, args):
+    """Mark the points where the interpolated z0 mask is zero invalid (grid_functions.py:327-343).  The reference reaches
+    this function only with ``mask_file`` (smooth_fit.py:437-438), which needs GDAL and is out of scope; with NumPy masks
+    (``mask_data``) already on the z0 grid it works the same way."""
+    import torch
+    from . import _cabi
+    if args.get('mask_file') is not None:
+        raise NotImplementedError('mask_file needs GDAL (out of scope); use mask_data with NumPy arrays')
+    z0 = grids['z0']
+    tmp = fd_grid([bds['y'], bds['x']], [args['spacing']['z0'], args['spacing']['z0']], name='z0')
+    y, x = (_cabi.to_dev(np.asarray(c, dtype=float), torch.float64) for c in data.coords()[0:2])
+    _, cols, vals, _, _ = _cabi.interp_coo(tmp.as_struct(), [y, x])
+    mask_d = _cabi.to_dev(np.asarray(z0.mask, dtype=np.float64).ravel(), torch.float64)
+    cols, order = torch.sort(cols.long(), dim=1)              # ascending columns: the summation order of the CSR product
+    vals = torch.gather(vals, 1, order)
+    acc = torch.zeros(cols.shape[0], dtype=torch.float64, device=vals.device)
+    for k in range(cols.shape[1]):
+        acc = acc + vals[:, k] * mask_d[cols[:, k]]
+    acc = torch.where(torch.isfinite(acc), acc, torch.zeros_like(acc))
+    _drop_points(data, valid_data, _cabi.to_host((acc != 0).to(torch.uint8)).astype(bool))

@@ -120,6 +120,27 @@ def test_mask_update_function_sees_the_parsed_model(double):
     assert np.allclose(S['m'][name].cell_area, 2. * fx['avgarea_' + name], rtol=1e-12)
 
 
+def test_public_mask_functions_drop_points_in_place(double):
+    """validate_by_dz_mask / setup_mask as public functions (LSsurf/__init__.py exports both; grid_functions.py:327-374): the
+    reference's in-place contract -- data subset, valid_data updated -- and its thresholds (> 0.5 of the interpolated dz mask,
+    != 0 of the interpolated z0 mask)."""
+    fx, pts, kw = load_case('uniform_masked')
+    args = dict(L.smooth_fit.__globals__['DEFAULTS'], **kw)
+    grids, bds = L.setup_grids(args)
+    for fn, extra in ((L.validate_by_dz_mask, ()), (L.setup_mask, (bds, args))):
+        D = make_data(pts)
+        valid = np.ones(D.size, dtype=bool)
+        fn(D, grids, valid, *extra)
+        assert 0 < valid.sum() < valid.size and D.size == int(valid.sum())
+        assert np.array_equal(np.asarray(D.x), pts['x'][valid])
+        g = grids['dz'] if fn is L.validate_by_dz_mask else grids['z0']
+        # a point whose four surrounding nodes are all inside the mask is kept, one whose four nodes are all outside is dropped
+        iy = np.clip(np.floor((pts['y'] - g.bds[0][0]) / g.delta[0]).astype(int), 0, g.shape[0] - 2)
+        ix = np.clip(np.floor((pts['x'] - g.bds[1][0]) / g.delta[1]).astype(int), 0, g.shape[1] - 2)
+        corners = np.stack([g.mask[iy, ix], g.mask[iy + 1, ix], g.mask[iy, ix + 1], g.mask[iy + 1, ix + 1]])
+        assert np.all(valid[corners.all(axis=0)]) and not np.any(valid[~corners.any(axis=0)])
+
+
 def test_double_is_removed_afterwards():
     from lssurf_b200 import _cabi
     assert _cabi.interp_coo.__module__ == 'lssurf_b200._cabi' and _cabi.device.__module__ == 'lssurf_b200._cabi'
