@@ -52,7 +52,7 @@ def match_prior_dz(grids, dzs=None, filenames=None, ref_epoch=0, sigma_scale=1, 
 
 
 def match_tile_edges(grids, ref_epoch, prior_dir=None, **kw):
-    """Constraints tying the edges of a tile to its already-fitted neighbours (match_priors.py:109-225).  The reference reads
+    """Constraints tying the edges of a tile to its already-fitted neighbours (match_priors.py:109-224).  The reference reads
     the neighbouring tiles from h5 files with pointCollection; that I/O is outside this package.  Build the same constraints
     from in-memory models with ``make_prior_op`` (one call per neighbour) and pass them through ``prior_args={'dzs': [...]}``."""
     raise NotImplementedError('match_tile_edges reads neighbouring tiles from h5 files (pointCollection I/O): out of scope; '
