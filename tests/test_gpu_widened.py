@@ -77,6 +77,12 @@ def test_compute_E_against_reference_fixture(L):
     assert 'compute_E' not in S['timing'] or S['timing']['compute_E'] >= 0
 
 
+def test_errors_and_early_returns_like_the_reference(L):
+    """ValueErrors, silent point drops and the no-data early return of the reference driver, on the device path."""
+    from tests.test_host_double import check_errors_and_early_returns
+    check_errors_and_early_returns(L)
+
+
 def test_calc_sigma_extra_on_grid_numpy_api(L):
     """Reference signature, NumPy in / out: constant noise -> one value everywhere; a noisier half -> larger values there."""
     from lssurf_b200.calc_sigma_extra import calc_sigma_extra_on_grid

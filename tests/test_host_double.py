@@ -141,33 +141,37 @@ def test_public_mask_functions_drop_points_in_place(double):
         assert np.all(valid[corners.all(axis=0)]) and not np.any(valid[~corners.any(axis=0)])
 
 
-def test_errors_and_early_returns_like_the_reference(double):
+def check_errors_and_early_returns(Lp, **extra):
     """The failure handling of the reference driver: ValueErrors for a missing required keyword
     (smooth_fit.py:403-405), zero data sigma (:604-605), a zero expected constraint value (constraint_functions.py:107-109) and a
     zero expected bias (bias_functions.py:112-113); points outside the grids or with a non-finite z dropped silently
     (:406, 423-425); the early return with data None and empty TOC / R / RMS when nothing is left (:427-430)."""
     fx, pts, kw = load_case('tracks_bias_small')
     with pytest.raises(ValueError):
-        L.smooth_fit(data=make_data(pts), VERBOSE=False, sort_points=False, **{k: v for k, v in kw.items() if k != 'spacing'})
+        Lp.smooth_fit(data=make_data(pts), VERBOSE=False, **extra, **{k: v for k, v in kw.items() if k != 'spacing'})
     with pytest.raises(ValueError, match='zero value found in data sigma'):
-        L.smooth_fit(data=make_data(dict(pts, sigma=np.where(np.abs(pts['time']) < 1.0, 0., pts['sigma']))), VERBOSE=False, sort_points=False, **kw)
+        Lp.smooth_fit(data=make_data(dict(pts, sigma=np.where(np.abs(pts['time']) < 1.0, 0., pts['sigma']))), VERBOSE=False, **extra, **kw)
     with pytest.raises(ValueError, match='found zero value in the expected values for d2z_dt2'):
-        L.smooth_fit(data=make_data(pts), VERBOSE=False, sort_points=False, **dict(kw, E_RMS=dict(kw['E_RMS'], d2z_dt2=0.)))
+        Lp.smooth_fit(data=make_data(pts), VERBOSE=False, **extra, **dict(kw, E_RMS=dict(kw['E_RMS'], d2z_dt2=0.)))
     with pytest.raises(ValueError, match='zero value in the expected biases'):
-        L.smooth_fit(data=make_data(dict(pts, sigma_corr=np.zeros_like(pts['sigma_corr']))), VERBOSE=False, sort_points=False, **kw)
+        Lp.smooth_fit(data=make_data(dict(pts, sigma_corr=np.zeros_like(pts['sigma_corr']))), VERBOSE=False, **extra, **kw)
     # points outside the domain / NaN heights: dropped, reported through valid_data, the rest fitted as if they were never there
     far = dict(pts)
     far['x'] = pts['x'].copy(); far['z'] = pts['z'].copy()
     far['x'][:5] += 1.e6
     far['z'][5:9] = np.nan
-    S = L.smooth_fit(data=make_data(far), VERBOSE=False, sort_points=False, max_iterations=1, **{k: v for k, v in kw.items() if k != 'max_iterations'})
+    S = Lp.smooth_fit(data=make_data(far), VERBOSE=False, **extra, max_iterations=1, **{k: v for k, v in kw.items() if k != 'max_iterations'})
     assert S['valid_data'].shape == (pts['x'].size,)
     assert not S['valid_data'][:9].any() and S['data'].size <= pts['x'].size - 9
     # nothing valid: the early return
     gone = dict(pts, x=pts['x'] + 1.e6)
-    E0 = L.smooth_fit(data=make_data(gone), VERBOSE=False, sort_points=False, **kw)
+    E0 = Lp.smooth_fit(data=make_data(gone), VERBOSE=False, **extra, **kw)
     assert E0['data'] is None and E0['TOC'] == {} and E0['R'] == {} and E0['RMS'] == {} and E0['m'] == {} and not E0['valid_data'].any()
     assert set(E0) >= {'m', 'E', 'data', 'grids', 'valid_data', 'TOC', 'R', 'RMS', 'timing', 'E_RMS'}
+
+
+def test_errors_and_early_returns_like_the_reference(double):
+    check_errors_and_early_returns(L, sort_points=False)
 
 
 def test_double_is_removed_afterwards():
