@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(256) coarse_fix_diag_kernel(int n_c, double *_
     if (m < n_c && !(A[(size_t)m * n_c + m] > 0.0)) A[(size_t)m * n_c + m] = 1.0;
 }
 
-// Gauss-Jordan inverse without pivoting (S_c is symmetric positive definite), ping-pong between two buffers so that no
-// CTA reads a row another CTA is rewriting: one grid barrier per pivot.  After n steps the inverse is in (n odd ? Y : X).
+// Plain Gauss-Jordan inverse without pivoting (S_c is symmetric positive definite), ping-pong between two buffers so that no
+// CTA reads a row another CTA is rewriting: one grid barrier per pivot.  Superseded by the blocked sweep below; kept behind
+// LSS_GJ_PLAIN=1 as its cross-check.  After n steps the inverse is in (n odd ? Y : X).
 __global__ void __launch_bounds__(256)
 gj_inverse_kernel(int n, double *X, double *Y, int *bad) {
     cgx::grid_group grid = cgx::this_grid();

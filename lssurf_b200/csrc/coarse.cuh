@@ -10,7 +10,7 @@
 // hands P in two forms: per fine column the <= 4 (parent, weight) pairs, and P^T as CSR by coarse row (so that the
 // restriction is a deterministic gather, not a scatter).  S_c is a dense n_c x n_c matrix (n_c <= 1024: a few MB that
 // stay in L2); it is formed with RED atomics over the non-zeros of N, the rank-n_E bias term is subtracted densely,
-// and the inverse comes from a cooperative Gauss-Jordan sweep (one grid barrier per pivot).
+// and the inverse comes from a cooperative blocked Gauss-Jordan sweep (32 x 32 pivot blocks, one grid barrier per block).
 #pragma once
 #include "common.cuh"
 
