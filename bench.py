@@ -78,7 +78,7 @@ def workload_config(a):
     else:
         par = ('normal matrix row-sharded over %d GPUs by dz-node blocks (own points + halo copies per rank); p, p.q and the '
                'coarse-level packet exchanged inside the CG step kernel through peer memory over NVLink, no collective per '
-               'iteration' % a.gpus)
+               'iteration; per-point outputs gathered over NVLink and copied to the host on rank 0 (gather_outputs="root")' % a.gpus)
     return {'workload': 'cfg4: ICESat-2-shaped tracks, %d points, %.0f x %.0f km, z0 250 m, dz 1 km x 0.25 yr, '
                         "bias_params=['rgt','cycle']%s, max_iterations=10" % (a.points, a.width / 1e3, a.width / 1e3,
                                                                                ' + setup_grid_bias term (10 km grid)' if a.grid_bias else ''),
@@ -305,7 +305,9 @@ def run_b200(a):
     def fit(inputs, profile=False, stages=False, history=None):
         D = L.point_data.data().from_dict({f: (inputs[f] if isinstance(inputs[f], torch.Tensor) and inputs[f].is_cuda
                                                else inputs[f].numpy()) for f in fields})
-        return L.smooth_fit(data=D, VERBOSE=False, dist=dist_arg, profile_spmv=profile, time_stages=stages, history=history, **kw)
+        # one job, one result: with several ranks the per-point outputs are gathered and copied to the host on rank 0 only
+        return L.smooth_fit(data=D, VERBOSE=False, dist=dist_arg, profile_spmv=profile, time_stages=stages, history=history,
+                            gather_outputs='root' if world > 1 else 'all', **kw)
 
     # ---- warm-up (device-resident steps, plus one host-input step)
     S = None
@@ -342,7 +344,7 @@ def run_b200(a):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     n_cols = int(S['m']['all'].size)
-    n_in_tse = int(np.sum(S['data'].three_sigma_edit))
+    n_in_tse = int(np.sum(S['data'].three_sigma_edit)) if rank == 0 else 0
     S = None                          # results of the timed loops are released: the untimed passes below must not grow the pinned pool
     # ---- untimed passes: kernel timings (event pairs around every 4th CG iteration), wall time per stage with device syncs
     Sp = fit(dev, profile=True)
@@ -359,7 +361,8 @@ def run_b200(a):
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
         td.all_reduce(t, op=td.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
-    d2h = 8 * n_cols + n_pts * (1 + 8 + 8)      # m0 + three_sigma_edit, sigma_extra, z_est
+    # m0 + three_sigma_edit, sigma_extra, z_est, bias_ID (rank 0; with several ranks the others copy m0 only)
+    d2h = 8 * n_cols + n_pts * (1 + 8 + 8 + (8 if kw.get('bias_params') else 0))
 
     # ---- roofline of the dominant kernel (q = N p) from the solver's own event pairs (this rank's launches)
     n_apply = sum(p['n_apply'] for p in prof)

@@ -15,7 +15,8 @@ The row selection ``Ip_r`` and scaling ``TCinv`` of the reference are never mate
 the weight vector), the column selection ``Ip_c`` is a set of unknowns held at zero.  New optional
 keywords (defaults keep existing calls unchanged): ``cg_rtol``, ``cg_maxiter``, ``dist`` (a
 ``parallel.DistContext``: rows of the normal matrix sharded over the GPUs of one node, exchanges inside the CG step kernel
-over NVLink), ``profile_spmv``; ``compute_E`` (error propagation) takes the dense-covariance path of propagate_errors.py.
+over NVLink), ``gather_outputs`` ('all': every rank returns the per-point outputs of all points; 'root': only rank 0 copies
+them to the host), ``profile_spmv``; ``compute_E`` (error propagation) takes the dense-covariance path of propagate_errors.py.
 """
 import os
 import warnings
@@ -55,6 +56,9 @@ DEFAULTS = {
     # solver controls (new; defaults chosen for 1e-6 relative-L2 parity with a direct solve)
     'cg_rtol': 1e-12, 'cg_maxiter': 50000, 'dist': None, 'profile_spmv': False, 'history': None,
     'time_stages': False, 'sort_points': True,
+    # several ranks: 'all' = every rank returns the per-point outputs of all points (each rank a full drop-in result),
+    # 'root' = only rank 0 copies them to the host; the other ranks return the model, grids and statistics only
+    'gather_outputs': 'all',
 }
 
 _UNSUPPORTED = ('mask_file', 'prior_edge_args')
@@ -700,7 +704,7 @@ def smooth_fit(**kwargs):
             data_filt = args['bias_filter'](data)
             extra_d.update({p: _field_dev(data_filt, p) for p in args['bias_params']})
         bias_id_d, bias_model = _assign_bias_ID_device(extra_d, args['bias_params'], extra_d['sigma_corr'])
-        data.assign({'bias_ID': _cabi.to_host(bias_id_d.to(f64))})      # float on the device: no 10^7-element host cast
+        bias_id_caller = bias_id_d                  # in the caller's order; copied to the host once the row order is known
         if args['bias_nsigma_edit']:
             bias_model['bias_param_dict']['edited'] = np.zeros_like(bias_model['bias_param_dict']['ID'], dtype=bool)
 
@@ -729,6 +733,13 @@ def smooth_fit(**kwargs):
         cov_d = {k: v[order].contiguous() for k, v in cov_d.items()}
         rz = rd = None
         stages.mark('spatial_sort')
+    if args['gather_outputs'] not in ('all', 'root'):
+        raise ValueError("gather_outputs must be 'all' or 'root'")
+    # does this rank hand per-point outputs to its caller?  (with gather_outputs='root' only rank 0 pays for the copies)
+    host_out = dist is None or dist.world == 1 or args['gather_outputs'] == 'all' or dist.rank == 0
+    if bias_id_d is not None and (host_out or order is None):        # without the internal order the edit loop reads data.bias_ID
+        data.assign({'bias_ID': _cabi.to_host(bias_id_caller.to(f64))})      # float on the device: no 10^7-element host cast
+    bias_id_caller = None
     # ---- this rank's block of points
     if shard is not None:
         lo, hi = shard['lo_e'], shard['hi']          # rows assembled here: halo copies [lo_e, lo) + own points [lo, hi)
@@ -912,6 +923,8 @@ def smooth_fit(**kwargs):
                 t = dist.gather_var_device(t, shard['counts'])
             elif multi:
                 t = dist.gather_rows_device(t, n_all)
+            if not host_out:                      # took part in the gather; the copy to the host is rank 0's
+                return None
             if order is not None:
                 out = torch.empty_like(t)
                 out[order] = t                    # undo the internal spatial ordering on the device
@@ -919,7 +932,8 @@ def smooth_fit(**kwargs):
             return _cabi.to_host(t)
 
         in_TSE_all = to_caller(tse_out_d)
-        in_TSE_all = in_TSE_all.view(np.bool_) if in_TSE_all.dtype == np.uint8 else in_TSE_all.astype(bool)    # 0 / 1 bytes
+        if host_out:
+            in_TSE_all = in_TSE_all.view(np.bool_) if in_TSE_all.dtype == np.uint8 else in_TSE_all.astype(bool)    # 0 / 1 bytes
         sigma_extra_all = to_caller(se_d)
         z_est_all = to_caller(z_est_d)
         if args.get('history') is not None and order is not None and (not multi or shard is not None):
@@ -927,13 +941,14 @@ def smooth_fit(**kwargs):
                 mk = torch.empty(n_all, dtype=torch.uint8, device=z_d.device)
                 mk[order] = _cabi.to_dev(np.unpackbits(h['mask_out'])[:n_all])
                 h['mask_out'] = np.packbits(_cabi.to_host(mk))
-        if valid_data is None:
-            valid_data = in_TSE_all.copy()
-        else:
-            valid_data[valid_data] = in_TSE_all
-        data.assign({'three_sigma_edit': in_TSE_all})
-        data.assign({'sigma_extra': sigma_extra_all})
-        data.assign({'z_est': np.reshape(z_est_all, data.shape)})
+        if host_out:
+            if valid_data is None:
+                valid_data = in_TSE_all.copy()
+            else:
+                valid_data[valid_data] = in_TSE_all
+            data.assign({'three_sigma_edit': in_TSE_all})
+            data.assign({'sigma_extra': sigma_extra_all})
+            data.assign({'z_est': np.reshape(z_est_all, data.shape)})
         dev_fields = {'z': z_own, 'sigma': s_own, 'z_est': z_est_d, 'three_sigma_edit': tse_out_d, 'sigma_extra': se_d,
                       'bias_ID': ids_own, 'G_rows': G_rows, 'Ec': Ec_d}
         if args['mask_update_function'] is not None:

@@ -228,6 +228,34 @@ def test_two_rank_row_sharding_reproduces_the_fixture(name, tmp_path):
     assert np.array_equal(res[0]['m0'], res[1]['m0'])          # both ranks hold the same model, bit for bit
 
 
+def test_two_rank_outputs_on_rank_0_only(tmp_path):
+    """gather_outputs='root': rank 0 returns what a single process returns, rank 1 the same model and node statistics but no
+    per-point outputs (it takes part in the gathers and skips the copies to the host)."""
+    import subprocess
+    import sys
+    name = 'tracks_bias_small'
+    port = str(33500 + (os.getpid() % 2000))
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'two_rank_worker.py')
+    outs = [str(tmp_path / f'rank{r}.npz') for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, worker, str(r), '2', port, name, outs[r], 'root'], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    logs = []
+    for p in procs:
+        try:
+            logs.append(p.communicate(timeout=300)[0].decode(errors='replace'))
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    assert all(p.returncode == 0 for p in procs), '\n'.join(logs)
+    fx, pts, kw = load_case(name)
+    r0, r1 = (np.load(o) for o in outs)
+    assert rel_l2(r0['m0'], fx['m0']) < 1e-8 and np.array_equal(r0['in_TSE'], fx['in_TSE'])
+    assert np.max(np.abs(r0['z_est'] - fx['z_est'])) < 1e-6
+    assert np.array_equal(r0['m0'], r1['m0']) and np.array_equal(r0['count'], r1['count'], equal_nan=True)
+    assert 'z_est' not in r1.files and r1['masks'].shape[0] == fx['masks'].shape[0]
+
+
 def grid_bias_operators(Lp):
     """The operator-level set-up of the grid_bias fixture (oracle/make_golden.py::case_grid_bias) with the package."""
     fx = np.load(os.path.join(GOLDEN, 'grid_bias.npz'), allow_pickle=False)
