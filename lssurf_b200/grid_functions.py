@@ -43,6 +43,31 @@ def _tapered_sum_op(grid, kernel_size, sub0s=None, dims=None):
     return lin_op(grid=grid).diff_op(offs, wt.ravel().astype(float), which_nodes=centres, valid_equations_only=False)
 
 
+def _tapered_box_sum_host(area, n_k, shape_c):
+    """The tapered box sums of _tapered_sum_op applied to a 2-D array, on the host: the same products added in the same
+    (ascending column) order as the CSR product of the operator, entries outside the array left out.  None when the
+    kernel or the centres fall outside the plain case (the caller builds the operator instead)."""
+    k0, k1 = int(n_k[0]), int(n_k[1])
+    if k0 < 3 or k1 < 3 or k0 % 2 == 0 or k1 % 2 == 0:
+        return None
+    ny, nx = area.shape
+    ci, cj = np.arange(0, ny + 1, k0 - 1), np.arange(0, nx + 1, k1 - 1)
+    if ci[-1] >= ny or cj[-1] >= nx or (ci.size, cj.size) != tuple(shape_c):
+        return None
+    h0, h1 = (k0 - 1) // 2, (k1 - 1) // 2
+    wt = np.ones((k0, k1))
+    for edge in [0, -1]:
+        wt[edge, :] /= 2
+        wt[:, edge] /= 2
+    pad = np.zeros((ny + 2 * h0, nx + 2 * h1))
+    pad[h0:h0 + ny, h1:h1 + nx] = area
+    out = np.zeros((ci.size, cj.size))
+    for a in range(k0):
+        for b in range(k1):
+            out += wt[a, b] * pad[ci[:, None] + a, cj[None, :] + b]
+    return out
+
+
 def sum_cell_area(grid_f, grid_c, cell_area_f=None, return_op=False, sub0s=None, taper=True):
     """Area of the (masked) fine-grid cells inside each coarse cell (grid_functions.py:136-167)."""
     if cell_area_f is None:
@@ -55,6 +80,11 @@ def sum_cell_area(grid_f, grid_c, cell_area_f=None, return_op=False, sub0s=None,
     n_k = (grid_c.delta[0:2] / grid_f.delta[0:2] + 1).astype(int)
     if cell_area_f.ndim == 3:
         n_k = np.array(list(n_k) + [1])
+    if not return_op and sub0s is None and cell_area_f.ndim == 2:
+        # a few thousand coarse cells: 25 shifted adds on the host instead of an operator, a sort and a product on the device
+        result = _tapered_box_sum_host(np.asarray(cell_area_f, dtype=float), n_k, grid_c.shape[0:2])
+        if result is not None:
+            return result
     tmp = fd_grid([grid_f.bds[d] for d in dims], deltas=grid_f.delta[dims])
     op = _tapered_sum_op(tmp, n_k, sub0s=sub0s, dims=dims)
     result = op.toCSR().dot(cell_area_f.ravel()).reshape(grid_c.shape[dims])
