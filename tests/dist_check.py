@@ -38,6 +38,9 @@ def main():
     pb, kb = synthetic.uniform_3d(n=int(120_000 * scale), width=2.e4 * scale ** 0.5, seed=6)
     pb['z'] = pb['z'] + np.random.default_rng(6).normal(0, 1., pb['x'].size) * 0.3 * (pb['x'] > 0)
     cases.append(('uniform_sigma_bins', (pb, dict(kb, sigma_extra_bin_spacing=5.e3 * scale ** 0.5, sigma_extra_max=5.))))
+    only = [c for c in os.environ.get('LSS_DIST_CHECK_CASES', '').split(',') if c]
+    if only:
+        cases = [c for c in cases if c[0] in only]
     ok = True
     single = {}
     for name, (pts, kw) in cases:
@@ -48,6 +51,19 @@ def main():
             hist = []
             S = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, dist=ctx if ctx.world > 1 else None,
                              history=hist, **kw)
+            if mode == modes[0] and name == 'tracks_bias' and ctx.world > 1:
+                # gather_outputs='root': the same fit, per-point outputs copied to the host on rank 0 only
+                Sr = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, dist=ctx, gather_outputs='root', **kw)
+                if ctx.rank == 0:
+                    rel_r = float(np.linalg.norm(Sr['m']['all'] - S['m']['all']) / np.linalg.norm(S['m']['all']))
+                    same_r = bool(np.array_equal(Sr['data'].three_sigma_edit, S['data'].three_sigma_edit))
+                    dz_r = float(np.max(np.abs(Sr['data'].z_est - S['data'].z_est)))
+                    print(f'[dist_check] {name}/{mode}: gather_outputs=root rel-L2(m0)={rel_r:.2e} final mask identical={same_r} '
+                          f'max|dz_est|={dz_r:.2e}', flush=True)
+                    ok = ok and rel_r < 1e-9 and same_r and dz_r < 1e-6
+                else:
+                    assert not any(f in Sr['data'].fields for f in ('z_est', 'sigma_extra', 'bias_ID')), 'outputs are rank 0\'s'
+                del Sr
             if ctx.rank != 0:
                 continue
             if name not in single:
