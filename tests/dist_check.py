@@ -51,7 +51,7 @@ def main():
             hist = []
             S = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, dist=ctx if ctx.world > 1 else None,
                              history=hist, **kw)
-            if mode == modes[0] and name == 'tracks_bias' and ctx.world > 1:
+            if mode == 'p2p' and name == 'tracks_bias' and ctx.world > 1:
                 # gather_outputs='root': the same fit, per-point outputs copied to the host on rank 0 only
                 Sr = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, dist=ctx, gather_outputs='root', **kw)
                 if ctx.rank == 0:
