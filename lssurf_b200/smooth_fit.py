@@ -626,6 +626,8 @@ def smooth_fit(**kwargs):
     for key in _UNSUPPORTED:
         if args[key]:
             raise NotImplementedError(f'smooth_fit keyword {key!r} is outside the GPU hot-path scope of lssurf_b200')
+    if args['gather_outputs'] not in ('all', 'root'):
+        raise ValueError("gather_outputs must be 'all' or 'root'")
     dist = args['dist']
     verbose = args['VERBOSE'] and (dist is None or dist.rank == 0)
     args['VERBOSE'] = verbose
@@ -733,8 +735,6 @@ def smooth_fit(**kwargs):
         cov_d = {k: v[order].contiguous() for k, v in cov_d.items()}
         rz = rd = None
         stages.mark('spatial_sort')
-    if args['gather_outputs'] not in ('all', 'root'):
-        raise ValueError("gather_outputs must be 'all' or 'root'")
     # does this rank hand per-point outputs to its caller?  (with gather_outputs='root' only rank 0 pays for the copies)
     host_out = dist is None or dist.world == 1 or args['gather_outputs'] == 'all' or dist.rank == 0
     if bias_id_d is not None and (host_out or order is None):        # without the internal order the edit loop reads data.bias_ID

@@ -56,7 +56,9 @@ def test_unique_by_rows_and_bias_ids():
 def test_smooth_fit_argument_errors():
     with pytest.raises(ValueError):
         smooth_fit(data=point_data().from_dict({'z': np.zeros(3)}))
-    assert DEFAULTS['max_iterations'] == 10 and DEFAULTS['mask_scale'] == {0: 10, 1: 1}
+    with pytest.raises(ValueError):          # checked before any device work
+        smooth_fit(data=point_data().from_dict({'z': np.zeros(3)}), W={}, ctr={}, spacing={}, E_RMS={}, gather_outputs='everyone')
+    assert DEFAULTS['max_iterations'] == 10 and DEFAULTS['mask_scale'] == {0: 10, 1: 1} and DEFAULTS['gather_outputs'] == 'all'
     assert DEFAULTS['converge_tol_dz'] == 0.05 and DEFAULTS['min_iterations'] == 2
 
 
