@@ -519,12 +519,21 @@ def _empty_result(m, E, data, grids, valid_data, timing, args):
             'timing': timing, 'E_RMS': args['E_RMS']}
 
 
-def _field_dev(obj, name):
-    """A per-point field as a contiguous fp64 CUDA tensor (NumPy arrays are uploaded, CUDA tensors used as is)."""
+def _field_dev(obj, name, dist=None):
+    """A per-point field as a contiguous fp64 CUDA tensor (NumPy arrays are uploaded, CUDA tensors used as is).
+    With several ranks (``dist``) every rank holds the same host array: each uploads its 1 / P of the rows and the blocks are
+    all-gathered over NVLink, so a byte crosses PCIe once per node instead of once per rank."""
     v = getattr(obj, name)
     if isinstance(v, torch.Tensor):
         return _cabi.to_dev(v.reshape(-1), torch.float64)
-    return _cabi.to_dev(np.asarray(v, dtype=float).ravel(), torch.float64)
+    v = np.asarray(v, dtype=float).ravel()
+    if dist is not None and dist.world > 1 and v.size >= int(os.environ.get('LSS_SHARED_UPLOAD_MIN', _SHARED_UPLOAD_MIN)):
+        lo, hi = dist.shard(v.size)
+        return dist.gather_rows_device(_cabi.to_dev(v[lo:hi], torch.float64), v.size)
+    return _cabi.to_dev(v, torch.float64)
+
+
+_SHARED_UPLOAD_MIN = 1 << 16      # rows; below this one copy per rank is cheaper than a collective
 
 
 def _assign_bias_ID_device(fields_d, bias_params, sigma_corr_d):
@@ -646,14 +655,14 @@ def smooth_fit(**kwargs):
     f64 = torch.float64
     if not all(f in data_in.fields for f in ('x', 'y', 'time')):
         raise ValueError('data must have x, y and time fields')
-    y_d, x_d, t_d, z_d, s_d = (_field_dev(data_in, f) for f in ('y', 'x', 'time', 'z', 'sigma'))
+    y_d, x_d, t_d, z_d, s_d = (_field_dev(data_in, f, dist) for f in ('y', 'x', 'time', 'z', 'sigma'))
     extra_d = {}
     if args['bias_params'] is not None:
-        extra_d = {p: _field_dev(data_in, p) for p in list(args['bias_params']) + ['sigma_corr']}
-    tse_d = _field_dev(data_in, 'three_sigma_edit') if 'three_sigma_edit' in data_in.fields else None
+        extra_d = {p: _field_dev(data_in, p, dist) for p in list(args['bias_params']) + ['sigma_corr']}
+    tse_d = _field_dev(data_in, 'three_sigma_edit', dist) if 'three_sigma_edit' in data_in.fields else None
     cov_d = {}
     if args['grid_bias_model_args'] is not None:       # the data parameters the gridded biases multiply
-        cov_d = {bm['param']: _field_dev(data_in, bm['param']) for bm in args['grid_bias_model_args']}
+        cov_d = {bm['param']: _field_dev(data_in, bm['param'], dist) for bm in args['grid_bias_model_args']}
     stages.mark('upload')
     op_z0 = lin_op(grids['z0'], name='interp_z')
     op_dz = lin_op(grids['dz'], name='interp_dz')

@@ -13,6 +13,8 @@ sys.path.insert(0, ROOT)
 def main():
     rank, world, port, name, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4], sys.argv[5]
     gather = sys.argv[6] if len(sys.argv) > 6 else 'all'
+    if gather == 'root':
+        os.environ['LSS_SHARED_UPLOAD_MIN'] = '0'       # also exercise the shared upload (each rank copies 1 / P of every field)
     faulthandler.dump_traceback_later(240, exit=True)          # a stuck collective must not hang the suite
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=port, RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
