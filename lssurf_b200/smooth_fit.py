@@ -892,6 +892,10 @@ def smooth_fit(**kwargs):
     else:
         rhs = torch.cat((z_loc, _cabi.to_dev(np.concatenate([op.prior for op in constraint_op_list]), f64)))
     stages.mark('c:Ec_rhs')
+    if int(G_data.col_N) != int(Gc.col_N):
+        # the reference stacks G_data on Gc at this point (smooth_fit.py:621): constraints that do not reach the last column
+        # of G_data (e.g. no dz constraint at all) make scipy's vstack fail with this message
+        raise ValueError('incompatible dimensions for axis 1')
     Ip_c = build_reference_epoch_matrix(G_data, Gc, grids, args['reference_epoch'])
     stages.mark('c:Ip_c')
     timing['setup'] = time() - tic

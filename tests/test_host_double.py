@@ -174,6 +174,15 @@ def test_errors_and_early_returns_like_the_reference(double):
     check_errors_and_early_returns(L, sort_points=False)
 
 
+def test_constraints_that_leave_out_the_dz_columns_fail_like_the_reference(double):
+    """No dz constraint at all: the constraint operator ends at the last z0 column, and the reference fails when it stacks
+    G_data on Gc (smooth_fit.py:621, scipy: 'incompatible dimensions for axis 1').  Found by tools/diff_fuzz.py (seed 777)."""
+    fx, pts, kw = load_case('uniform3d_small')
+    E = {k: v for k, v in kw['E_RMS'].items() if k in ('d2z0_dx2', 'dz0_dx')}
+    with pytest.raises(ValueError, match='incompatible dimensions for axis 1'):
+        L.smooth_fit(data=make_data(pts), VERBOSE=False, sort_points=False, **dict(kw, E_RMS=E))
+
+
 def test_double_is_removed_afterwards():
     from lssurf_b200 import _cabi
     assert _cabi.interp_coo.__module__ == 'lssurf_b200._cabi' and _cabi.device.__module__ == 'lssurf_b200._cabi'

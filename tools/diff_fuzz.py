@@ -1,7 +1,11 @@
 """Differential check of the package's HOST logic against the unmodified reference on small random configurations
 (build container only: needs /root/reference; the kernels are replaced by tests/host_double.py, so this exercises the
 Python mirror of the reference interface -- keyword handling, operator bookkeeping, edit-loop control flow).
-    python tools/diff_fuzz.py [n_cases=12] [seed=0]"""
+    python tools/diff_fuzz.py [n_cases=12] [seed=0] [widened]
+With ``widened`` every case also draws from the keywords that take in-memory grids: NumPy masks on both grids (``mask_data``,
+``mask_scale``), ``constraint_scaling_maps``, ``avg_masks``, ``prior_args``, ``DEM_tol``, ``lagrangian_coords``; the reference
+is driven through the hooks oracle/make_golden.py uses for its fixtures (masks put on the reference's grids, node arrays
+wrapped in an object that can "interpolate" itself, prior points handed to the reference's make_prior_op)."""
 import os, sys, warnings
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -72,22 +76,126 @@ def one_case(rng, k):
     return pts, kw
 
 
+def widen(rng, pts, kw):
+    """Add keywords that take in-memory grids / points to a case of one_case (package form of the arguments)."""
+    W = kw['W']['x']
+    n = pts['x'].size
+    nz0, ndz = int(W / kw['spacing']['z0']) + 1, int(W / kw['spacing']['dz']) + 1
+    for key in ('sigma_extra_bin_spacing', 'sigma_extra_max', 'sensor_grid_bias_params', 'data_slope_sensors'):
+        kw.pop(key, None)                    # keep the combinations to what the fixtures establish as supported together
+    if rng.random() < 0.5:
+        mz, md = np.ones((nz0, nz0), dtype=bool), np.ones((ndz, ndz), dtype=bool)
+        for m in (mz, md):
+            for _ in range(int(rng.integers(0, 3))):
+                a, b = sorted(rng.integers(0, m.shape[0], 2))
+                c, d = sorted(rng.integers(0, m.shape[1], 2))
+                m[a:min(b, a + m.shape[0] // 3) + 1, c:min(d, c + m.shape[1] // 3) + 1] = False
+        kw['mask_data'] = {'z0': mz, 'dz': md}
+        if rng.random() < 0.5:
+            kw['mask_scale'] = {0: float(rng.choice([3., 10., 30.])), 1: 1}
+    if rng.random() < 0.4:
+        maps = {}
+        if kw['E_RMS'].get('d2z0_dx2') is not None and rng.random() < 0.7:
+            m = np.ones((nz0, nz0)); m[:nz0 // 2] = float(rng.choice([0.25, 4.])); m[int(rng.integers(0, nz0)), int(rng.integers(0, nz0))] = np.nan
+            maps['d2z0_dx2'] = m
+        if kw['E_RMS'].get('d3z_dx2dt') is not None and rng.random() < 0.7:
+            m = np.ones((ndz, ndz)); m[:, ndz // 2:] = float(rng.choice([0.5, 4.]))
+            maps['d3z_dx2dt'] = m
+        if kw['E_RMS'].get('d2z_dt2') is not None and rng.random() < 0.5:
+            m = np.ones((ndz, ndz)); m[:3, :3] = 0.5
+            maps['d2z_dt2'] = m
+        if rng.random() < 0.4:
+            m = np.zeros((ndz, ndz)); m[:2, :] = 0.05; m[min(5, ndz - 1), min(5, ndz - 1)] = np.nan
+            maps['dz'] = m
+        if maps:
+            kw['constraint_scaling_maps'] = maps
+    if rng.random() < 0.4:
+        kw.setdefault('dzdt_lags', [1, 2])
+        iy, ix = np.meshgrid(np.arange(ndz), np.arange(ndz), indexing='ij')
+        basin = np.clip(1.2 - np.hypot(iy - ndz / 3., ix - ndz / 2.) / (ndz / 3.), 0., 1.)
+        if rng.random() < 0.5:
+            basin[:, :2] = np.nan
+        kw['avg_masks'] = {'basin': basin, 'shelf': (ix >= ndz // 2).astype(float)}
+    if rng.random() < 0.4:
+        npr = int(rng.integers(20, 120))
+        px, py = rng.uniform(-0.45 * W, 0.45 * W, npr), rng.uniform(-0.45 * W, 0.45 * W, npr)
+        half_t = kw['W']['t'] / 2
+        pt = rng.choice([-half_t / 2, 0., half_t / 2, half_t * 0.9], npr)
+        prior = dict(x=px, y=py, t=pt, dz=pt * (1. + px / W) + rng.normal(0, 0.02, npr), sigma_dz=np.full(npr, 0.05))
+        kw['prior_args'] = dict(dzs=[prior], ref_epoch=0., sigma_scale=float(rng.choice([1., 2.])))
+    if rng.random() < 0.3:
+        dem = 30 * np.sin(pts['x'] / 3000.) * np.cos(pts['y'] / 2500.) + rng.normal(0, 0.5, n)
+        dem[rng.random(n) < 0.02] += 40.
+        pts['DEM'] = dem
+        kw['DEM_tol'] = 10.
+    if rng.random() < 0.3 and 'bias_nsigma_edit' not in kw:
+        has = rng.random(n) < 0.66
+        pts['x0'] = np.where(has, pts['x'] - 150. * pts['time'], np.nan)
+        pts['y0'] = np.where(has, pts['y'] + 60. * pts['time'], np.nan)
+        kw['lagrangian_coords'] = ['y0', 'x0']
+        kw['spacing'] = dict(kw['spacing'], lagrangian_dz=1000.)
+        kw['E_RMS'] = dict(kw['E_RMS'], lagrangian_dz=50., lagrangian_dzdx=0.5)
+    return pts, kw
+
+
+class _NodeGrid(object):
+    """What the reference asks of a pointCollection grid that already sits on the nodes it is sampled at."""
+
+    def __init__(self, z):
+        self.z = z
+
+    def interp(self, x, y, gridded=False, **_):
+        return self.z.copy()
+
+
+def reference_fit(R, pts, kw, **more):
+    """The unmodified reference with the package form of the widened keywords translated by the hooks of
+    oracle/make_golden.py::case_widened."""
+    from oracle import make_golden as MG
+    SF = H.smooth_fit_module()
+    kw = dict(kw)
+    masks = kw.pop('mask_data', None)
+    prior = kw.pop('prior_args', None)
+    for key in ('avg_masks', 'constraint_scaling_maps'):
+        if kw.get(key) is not None:
+            kw[key] = {k: _NodeGrid(np.asarray(v, dtype=float)) for k, v in kw[key].items()}
+    orig_prior = SF.match_prior_dz
+    if prior is not None:
+        MP = sys.modules['LSsurf.match_priors']
+
+        def prior_ops(grids, **_):
+            return [MP.make_prior_op(grids, H.point_data(**d), 'prior_%d' % k, ref_time=prior['ref_epoch'], sigma_scale=prior['sigma_scale'])
+                    for k, d in enumerate(prior['dzs'])]
+        kw['prior_args'] = {}
+        SF.match_prior_dz = prior_ops
+    try:
+        with MG.with_masks(SF, masks):
+            return R.smooth_fit(data=H.point_data(**pts), VERBOSE=False, **more, **kw)
+    finally:
+        SF.match_prior_dz = orig_prior
+
+
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 12
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    widened = len(sys.argv) > 3 and sys.argv[3] == 'widened'
     R = H.load()
     bad = 0
     for k in range(n_cases):
         pts, kw = one_case(rng, k)
-        tag = 'case %d: n=%d %s' % (k, pts['x'].size, {a: b for a, b in kw.items() if a not in ('W', 'ctr')})
+        if widened:
+            pts, kw = widen(rng, pts, kw)
+        tag = 'case %d: n=%d %s' % (k, pts['x'].size, {a: (b if a not in ('mask_data', 'constraint_scaling_maps', 'avg_masks', 'prior_args') else sorted(b))
+                                               for a, b in kw.items() if a not in ('W', 'ctr')})
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
             try:
-                fo_r = R.smooth_fit(data=H.point_data(**pts), VERBOSE=False, return_fit_objects=True, **kw)
-                S_r = R.smooth_fit(data=H.point_data(**pts), VERBOSE=False, **kw)
+                fo_r = reference_fit(R, pts, kw, return_fit_objects=True)
+                S_r = reference_fit(R, pts, kw)
                 err_r = None
             except Exception as e:          # noqa: BLE001
                 err_r = type(e).__name__
+                msg_r = str(e)[:80]
             with host_double.installed():
                 try:
                     fo_p = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, return_fit_objects=True, **kw)
@@ -96,9 +204,11 @@ def main():
                     err_p = None
                 except Exception as e:      # noqa: BLE001
                     err_p = type(e).__name__
+                    msg_p = str(e)[:80]
         if err_r or err_p:
             ok = err_r == err_p
-            print(('ok   ' if ok else 'DIFF ') + tag + '  errors: reference %s, package %s' % (err_r, err_p))
+            print(('ok   ' if ok else 'DIFF ') + tag + '  errors: reference %s (%s), package %s (%s)' % (
+                err_r, msg_r if err_r else '', err_p, msg_p if err_p else ''))
             bad += not ok
             continue
         checks = dict(G=csr_digest(fo_r['G_data'].toCSR()) == csr_digest(Gp), Gc=csr_digest(fo_r['Gc'].toCSR()) == csr_digest(Cp),
