@@ -1,11 +1,12 @@
 """Differential check of the package's HOST logic against the unmodified reference on small random configurations
 (build container only: needs /root/reference; the kernels are replaced by tests/host_double.py, so this exercises the
 Python mirror of the reference interface -- keyword handling, operator bookkeeping, edit-loop control flow).
-    python tools/diff_fuzz.py [n_cases=12] [seed=0] [widened]
+    python tools/diff_fuzz.py [n_cases=12] [seed=0] [widened] [compute_E]
 With ``widened`` every case also draws from the keywords that take in-memory grids: NumPy masks on both grids (``mask_data``,
 ``mask_scale``), ``constraint_scaling_maps``, ``avg_masks``, ``prior_args``, ``DEM_tol``, ``lagrangian_coords``; the reference
 is driven through the hooks oracle/make_golden.py uses for its fixtures (masks put on the reference's grids, node arrays
-wrapped in an object that can "interpolate" itself, prior points handed to the reference's make_prior_op)."""
+wrapped in an object that can "interpolate" itself, prior points handed to the reference's make_prior_op).  With ``compute_E``
+half of the small cases also propagate errors (dense stand-ins for sparseqr.rz / inv_tr_upper on the reference side)."""
 import os, sys, warnings
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -73,7 +74,12 @@ def one_case(rng, k):
     if 'bias_params' in kw and rng.random() < 0.3:
         kw['bias_nsigma_edit'] = float(rng.choice([3., 6.]))
         kw['bias_nsigma_iteration'] = int(rng.integers(0, 3))
+    if COMPUTE_E and W <= 8e3 and kw['spacing']['z0'] == 500. and 'sensor_grid_bias_params' not in kw and rng.random() < 0.5:
+        kw['compute_E'] = True              # small enough for the dense QR / triangular-inverse stand-ins of the reference run
     return pts, kw
+
+
+COMPUTE_E = 'compute_E' in sys.argv[1:]
 
 
 def widen(rng, pts, kw):
@@ -178,7 +184,7 @@ def reference_fit(R, pts, kw, **more):
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 12
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-    widened = len(sys.argv) > 3 and sys.argv[3] == 'widened'
+    widened = 'widened' in sys.argv[3:]
     R = H.load()
     bad = 0
     for k in range(n_cases):
@@ -235,6 +241,13 @@ def main():
         if S_r['m'].get('slope_bias'):
             checks['slope'] = all(abs(v['slope_x'] - S_p['m']['slope_bias'][q]['slope_x']) < 1e-8 and
                                   abs(v['slope_y'] - S_p['m']['slope_bias'][q]['slope_y']) < 1e-8 for q, v in S_r['m']['slope_bias'].items())
+        for key, g in S_r['E'].items():          # error propagation: the reference drops entries of R^-1 below 1e-5, the bar is 1e-4
+            if key in ('sigma_bias', 'sigma_slope_bias'):
+                a, b = np.asarray(g.get('val', []), dtype=float), np.asarray(S_p['E'].get(key, {}).get('val', []), dtype=float)
+            else:
+                a, b = np.asarray(getattr(g, key), dtype=float), np.asarray(getattr(S_p['E'][key], key), dtype=float) if key in S_p['E'] else np.zeros(0)
+            checks['E.' + key] = a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and \
+                (not np.any(~np.isnan(a)) or np.nanmax(np.abs(a - b) / np.maximum(np.abs(a), 1e-3)) < 1e-4)
         checks['sigma_extra'] = np.allclose(np.asarray(S_r['data'].sigma_extra, dtype=float), S_p['data'].sigma_extra, rtol=0, atol=2e-5)
         failed = [c for c, v in checks.items() if not v]
         print(('ok   ' if not failed else 'DIFF ') + tag + ('' if not failed else '  FAILED: %s' % failed))
