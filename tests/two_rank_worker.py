@@ -1,5 +1,6 @@
 """One rank of the world-size-2 host-logic test (tests/test_host_double.py): gloo process group, C-ABI wrappers replaced
-by the test double, the package's own smooth_fit with this rank's DistContext.  Usage: rank world port case out.npz [gather_outputs]"""
+by the test double, the package's own smooth_fit with this rank's DistContext.  Usage: rank world port case out.npz [gather_outputs]
+(case = a fixture name, or the path of a pickled (pts, kw) pair written by tools/dist_fuzz.py)"""
 import faulthandler
 import os
 import sys
@@ -23,7 +24,12 @@ def main():
     from lssurf_b200.parallel import DistContext
     from tests import host_double
     from tests.util import load_case
-    fx, pts, kw = load_case(name)
+    if name.endswith('.pkl'):           # tools/dist_fuzz.py: a random case instead of a fixture
+        import pickle
+        with open(name, 'rb') as f:
+            pts, kw = pickle.load(f)
+    else:
+        fx, pts, kw = load_case(name)
     hist = []
     with host_double.installed():
         S = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, history=hist, sort_points=False,
@@ -31,12 +37,13 @@ def main():
     if gather == 'root' and rank != 0:
         # per-point outputs are rank 0's; this rank returns the model, the grids and the all-reduced statistics
         assert not any(f in S['data'].fields for f in ('z_est', 'sigma_extra'))
-        np.savez(out, m0=S['m']['all'], count=S['m']['z0'].count, masks=np.array([h['mask_out'] for h in hist]))
+        np.savez(out, m0=S['m']['all'], count=S['m']['z0'].count, masks=np.array([h['mask_out'] for h in hist]), n_solves=len(S['timing']['pcg']))
         dist.destroy_process_group()
         return
     n_edited = S['m']['bias']['N_edited'] if 'bias' in S['m'] else []
     np.savez(out, m0=S['m']['all'], in_TSE=np.packbits(S['data'].three_sigma_edit), masks=np.array([h['mask_out'] for h in hist]),
-             z_est=np.asarray(S['data'].z_est), count=S['m']['z0'].count, n_edited=np.asarray(n_edited, dtype=float))
+             z_est=np.asarray(S['data'].z_est), count=S['m']['z0'].count, n_edited=np.asarray(n_edited, dtype=float),
+             n_solves=len(S['timing']['pcg']))
     dist.destroy_process_group()
 
 
