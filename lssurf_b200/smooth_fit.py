@@ -993,6 +993,8 @@ def smooth_fit(**kwargs):
         averaging_ops = setup_averaging_ops(grids['dz'], grids['dz'].col_N, args, grids['dz'].cell_area)
         averaging_ops.update(setup_z0_avg(grids, grids['dz'].col_N, args))
         averaging_ops.update(setup_avg_mask_ops(grids['dz'], G_data.col_N, args['avg_masks'], args['dzdt_lags']))
+        if valid_data is None:              # no iterations: the validity mask as it stands (every point valid)
+            valid_data = np.ones(n_all, dtype=bool)
     stages.mark('epilogue')
     return {'m': m, 'E': E, 'data': data, 'grids': grids, 'valid_data': valid_data, 'TOC': Gc.TOC, 'R': R, 'RMS': RMS,
             'timing': timing, 'E_RMS': args['E_RMS'], 'dzdt_lags': args['dzdt_lags']}

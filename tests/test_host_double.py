@@ -183,6 +183,18 @@ def test_constraints_that_leave_out_the_dz_columns_fail_like_the_reference(doubl
         L.smooth_fit(data=make_data(pts), VERBOSE=False, sort_points=False, **dict(kw, E_RMS=E))
 
 
+def test_no_iterations_returns_the_validity_mask(double):
+    """max_iterations = 0 (smooth_fit.py:648-662 skipped): empty m / E / R / RMS, the operators' TOC, and valid_data as the
+    validity mask of the points.  Found by tools/diff_fuzz.py ('more' mode)."""
+    fx, pts, kw = load_case('uniform3d_small')
+    far = dict(pts, x=pts['x'].copy())
+    far['x'][:7] += 1.e6
+    for p_, n_valid in ((pts, pts['x'].size), (far, pts['x'].size - 7)):
+        S = L.smooth_fit(data=make_data(p_), VERBOSE=False, sort_points=False, **dict(kw, max_iterations=0))
+        assert S['m'] == {} and S['E'] == {} and S['R'] == {} and S['RMS'] == {} and 'cols' in S['TOC']
+        assert S['valid_data'].dtype == bool and S['valid_data'].shape == (pts['x'].size,) and S['valid_data'].sum() == n_valid
+
+
 def test_double_is_removed_afterwards():
     from lssurf_b200 import _cabi
     assert _cabi.interp_coo.__module__ == 'lssurf_b200._cabi' and _cabi.device.__module__ == 'lssurf_b200._cabi'

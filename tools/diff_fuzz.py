@@ -1,7 +1,7 @@
 """Differential check of the package's HOST logic against the unmodified reference on small random configurations
 (build container only: needs /root/reference; the kernels are replaced by tests/host_double.py, so this exercises the
 Python mirror of the reference interface -- keyword handling, operator bookkeeping, edit-loop control flow).
-    python tools/diff_fuzz.py [n_cases=12] [seed=0] [widened] [compute_E]
+    python tools/diff_fuzz.py [n_cases=12] [seed=0] [widened] [compute_E] [more]
 With ``widened`` every case also draws from the keywords that take in-memory grids: NumPy masks on both grids (``mask_data``,
 ``mask_scale``), ``constraint_scaling_maps``, ``avg_masks``, ``prior_args``, ``DEM_tol``, ``lagrangian_coords``; the reference
 is driven through the hooks oracle/make_golden.py uses for its fixtures (masks put on the reference's grids, node arrays
@@ -74,12 +74,31 @@ def one_case(rng, k):
     if 'bias_params' in kw and rng.random() < 0.3:
         kw['bias_nsigma_edit'] = float(rng.choice([3., 6.]))
         kw['bias_nsigma_iteration'] = int(rng.integers(0, 3))
+    if MORE:
+        # less common switches: a magnitude constraint on z0, pre-edited biases, the fractional-change stop rule, no
+        # iterations at all, long dz/dt lags, block averages without dz/dt lags
+        if rng.random() < 0.3 and E.get('d2z0_dx2') is not None:
+            E['z0'] = float(rng.choice([10., 100.]))
+        if 'bias_params' in kw and rng.random() < 0.3:
+            pts.setdefault('three_sigma_edit', np.ones(n))
+            kw['bias_edit_vals'] = {'rgt': [float(rng.integers(0, 6))], 'cycle': [float(rng.integers(0, 3))]}
+        if rng.random() < 0.3:
+            kw['converge_tol_frac_TSE'] = float(rng.choice([1e-3, 1e-2, 0.1]))
+        if rng.random() < 0.1:
+            kw['max_iterations'] = 0
+        if rng.random() < 0.2:
+            kw['dzdt_lags'] = [1, int(rng.integers(2, 8))]
+        if rng.random() < 0.15 and 'dzdt_lags' not in kw:
+            kw['avg_scales'] = [2000.]
+        if rng.random() < 0.2:
+            kw['sigma_extra_max'] = float(rng.choice([0.05, 1.0]))
     if COMPUTE_E and W <= 8e3 and kw['spacing']['z0'] == 500. and 'sensor_grid_bias_params' not in kw and rng.random() < 0.5:
         kw['compute_E'] = True              # small enough for the dense QR / triangular-inverse stand-ins of the reference run
     return pts, kw
 
 
 COMPUTE_E = 'compute_E' in sys.argv[1:]
+MORE = 'more' in sys.argv[1:]
 
 
 def widen(rng, pts, kw):
@@ -216,6 +235,15 @@ def main():
             print(('ok   ' if ok else 'DIFF ') + tag + '  errors: reference %s (%s), package %s (%s)' % (
                 err_r, msg_r if err_r else '', err_p, msg_p if err_p else ''))
             bad += not ok
+            continue
+        if 'all' not in S_r['m'] or 'all' not in S_p['m']:       # max_iterations = 0: no solve, nothing parsed
+            same = set(S_r['m']) == set(S_p['m']) and set(S_r) <= set(S_p) | {'dzdt_lags'} and set(S_r['E']) == set(S_p['E']) \
+                and set(S_r['R']) == set(S_p['R']) and csr_digest(fo_r['G_data'].toCSR()) == csr_digest(Gp) \
+                and csr_digest(fo_r['Gc'].toCSR()) == csr_digest(Cp) and S_p['valid_data'] is not None \
+                and np.array_equal(S_r['valid_data'], S_p['valid_data'])
+            print(('ok   ' if same else 'DIFF ') + tag + '  (no iterations: result keys %s / %s, m %s / %s)' % (
+                sorted(S_r), sorted(S_p), sorted(S_r['m']), sorted(S_p['m'])))
+            bad += not same
             continue
         checks = dict(G=csr_digest(fo_r['G_data'].toCSR()) == csr_digest(Gp), Gc=csr_digest(fo_r['Gc'].toCSR()) == csr_digest(Cp),
                       Ec=np.array_equal(np.asarray(fo_r['Ec'], dtype=float), np.asarray(fo_p['Ec'], dtype=float)),
