@@ -163,6 +163,11 @@ def widen(rng, pts, kw):
     return pts, kw
 
 
+def _close(a, b):
+    """scalars equal to 1e-6 relative; NaN (no data left) matches NaN"""
+    return (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-6 * abs(a) + 1e-12
+
+
 class _NodeGrid(object):
     """What the reference asks of a pointCollection grid that already sits on the nodes it is sampled at."""
 
@@ -251,8 +256,8 @@ def main():
                       mask=np.array_equal(np.asarray(S_r['data'].three_sigma_edit, dtype=bool), np.asarray(S_p['data'].three_sigma_edit, dtype=bool)),
                       m0=np.linalg.norm(S_r['m']['all'] - S_p['m']['all']) <= 1e-8 * np.linalg.norm(S_r['m']['all']),
                       keys=set(S_r['m'].keys()) == set(S_p['m'].keys()),
-                      R=all(abs(S_r['R'][q] - S_p['R'][q]) <= 1e-6 * abs(S_r['R'][q]) + 1e-12 for q in S_r['R']) and set(S_r['R']) == set(S_p['R']),
-                      RMS=all(abs(S_r['RMS'][q] - S_p['RMS'][q]) <= 1e-6 * abs(S_r['RMS'][q]) + 1e-12 for q in S_r['RMS']))
+                      R=set(S_r['R']) == set(S_p['R']) and all(_close(S_r['R'][q], S_p['R'][q]) for q in S_r['R']),
+                      RMS=set(S_r['RMS']) == set(S_p['RMS']) and all(_close(S_r['RMS'][q], S_p['RMS'][q]) for q in S_r['RMS']))
         for key in ('z0', 'dz'):
             for f in ('count', 'misfit_rms', 'misfit_scaled_rms'):
                 a, b = getattr(S_r['m'][key], f), getattr(S_p['m'][key], f)
