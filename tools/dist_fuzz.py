@@ -3,7 +3,7 @@ Random cases of tools/diff_fuzz.py are fitted by WORLD gloo ranks (tests/two_ran
 tests/host_double.py, every rank assembles its block of rows, the statistics are all-reduced, per-point outputs gathered) and
 by the single-process reference; every rank must return the reference's model, final edit mask, z_est and count map, and
 take the reference's number of edit iterations.
-    python tools/dist_fuzz.py [n_cases=8] [seed=0] [world=2]"""
+    python tools/dist_fuzz.py [n_cases=8] [seed=0] [world=2] [widened] [more]"""
 import os, pickle, subprocess, sys, tempfile, warnings
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +23,10 @@ def main():
     bad = n_run = 0
     for k in range(n_cases):
         pts, kw = F.one_case(rng, k)
-        tag = 'case %d: n=%d %s' % (k, pts['x'].size, {a: b for a, b in kw.items() if a not in ('W', 'ctr')})
+        if 'widened' in sys.argv[4:]:
+            pts, kw = F.widen(rng, pts, kw)
+        tag = 'case %d: n=%d %s' % (k, pts['x'].size, {a: (b if a not in ('mask_data', 'constraint_scaling_maps', 'avg_masks', 'prior_args') else sorted(b))
+                                               for a, b in kw.items() if a not in ('W', 'ctr')})
         import sparseqr                     # the stub of oracle/ref_stubs: count the reference's solves = its edit iterations
         solves, orig_solve = [], sparseqr.solve
 
@@ -34,14 +37,14 @@ def main():
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
             try:
-                S_r = R.smooth_fit(data=H.point_data(**pts), VERBOSE=False, **kw)
+                S_r = F.reference_fit(R, pts, kw)
             except Exception as e:          # noqa: BLE001 -- error behaviour is diff_fuzz.py's subject
                 print('skip ' + tag + '  (reference raises %s)' % type(e).__name__)
                 continue
             finally:
                 sparseqr.solve = orig_solve
-        if S_r['data'] is None:
-            print('skip ' + tag + '  (no valid data)')
+        if S_r['data'] is None or kw['max_iterations'] == 0:
+            print('skip ' + tag + '  (no valid data / no iterations)')
             continue
         n_run += 1
         with tempfile.TemporaryDirectory() as tmp:
