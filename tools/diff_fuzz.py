@@ -153,6 +153,12 @@ def widen(rng, pts, kw):
         dem[rng.random(n) < 0.02] += 40.
         pts['DEM'] = dem
         kw['DEM_tol'] = 10.
+    if rng.random() < 0.3 and 'bias_params' in kw and 'bias_nsigma_edit' not in kw:
+        # a gridded bias that multiplies a per-point covariate (setup_grid_bias.py:4-43; cfg 4 of the benchmark)
+        pts['cov'] = np.sin(pts['x'] / 2500.) + 0.1 * rng.standard_normal(n)
+        pts['z'] = pts['z'] + pts['cov'] * 0.15 * np.cos(pts['y'] / 4000.)
+        kw['grid_bias_spec'] = dict(param='cov', bounds=(-W / 2, W / 2, -W / 2, W / 2), spacing=float(rng.choice([2000., 3000.])),
+                                    expected_rms=0.1, expected_rms_grad=1e-3)
     if rng.random() < 0.3 and 'bias_nsigma_edit' not in kw:
         has = rng.random(n) < 0.66
         pts['x0'] = np.where(has, pts['x'] - 150. * pts['time'], np.nan)
@@ -189,6 +195,19 @@ def reference_fit(R, pts, kw, **more):
     for key in ('avg_masks', 'constraint_scaling_maps'):
         if kw.get(key) is not None:
             kw[key] = {k: _NodeGrid(np.asarray(v, dtype=float)) for k, v in kw[key].items()}
+    gb = kw.pop('grid_bias_spec', None)
+    orig_constraints = SF.setup_smoothness_constraints
+    if gb is not None:
+        # the live reference driver has no call site for setup_grid_bias (smooth_fit.py:487-489); its predecessor called it right
+        # after the smoothness constraints (deprecated/smooth_xytb_fit.py:465-467): same hook as oracle/make_golden.py
+        def constraints_then_grid_bias(grids, constraint_op_list, *a, **k):
+            orig_constraints(grids, constraint_op_list, *a, **k)
+            caller = sys._getframe(1).f_locals
+            b = gb['bounds']
+            g = R.fd_grid([[b[0], b[1]], [b[2], b[3]]], [gb['spacing']] * 2, name=gb['param'] + '_bias')
+            R.setup_grid_bias(caller['data'], caller['G_data'], constraint_op_list, grids, param=gb['param'], grid=g,
+                              expected_rms=gb['expected_rms'], expected_value=0., expected_rms_grad=gb['expected_rms_grad'])
+        SF.setup_smoothness_constraints = constraints_then_grid_bias
     orig_prior = SF.match_prior_dz
     if prior is not None:
         MP = sys.modules['LSsurf.match_priors']
@@ -203,6 +222,18 @@ def reference_fit(R, pts, kw, **more):
             return R.smooth_fit(data=H.point_data(**pts), VERBOSE=False, **more, **kw)
     finally:
         SF.match_prior_dz = orig_prior
+        SF.setup_smoothness_constraints = orig_constraints
+
+
+def package_kw(kw):
+    """The keywords as the package takes them: the grid-bias spec becomes ``grid_bias_model_args`` with an fd_grid."""
+    kw = dict(kw)
+    gb = kw.pop('grid_bias_spec', None)
+    if gb is not None:
+        b = gb['bounds']
+        kw['grid_bias_model_args'] = [dict(param=gb['param'], expected_rms=gb['expected_rms'], expected_value=0., expected_rms_grad=gb['expected_rms_grad'],
+                                           grid=L.fd_grid([[b[0], b[1]], [b[2], b[3]]], [gb['spacing']] * 2, name=gb['param'] + '_bias'))]
+    return kw
 
 
 def main():
@@ -228,8 +259,8 @@ def main():
                 msg_r = str(e)[:80]
             with host_double.installed():
                 try:
-                    fo_p = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, return_fit_objects=True, **kw)
-                    S_p = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, sort_points=False, **kw)
+                    fo_p = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, return_fit_objects=True, **package_kw(kw))
+                    S_p = L.smooth_fit(data=L.point_data.data().from_dict(pts), VERBOSE=False, sort_points=False, **package_kw(kw))
                     Gp, Cp = fo_p['G_data'].toCSR(), fo_p['Gc'].toCSR()
                     err_p = None
                 except Exception as e:      # noqa: BLE001
@@ -255,7 +286,7 @@ def main():
                       valid=np.array_equal(S_r['valid_data'], S_p['valid_data']),
                       mask=np.array_equal(np.asarray(S_r['data'].three_sigma_edit, dtype=bool), np.asarray(S_p['data'].three_sigma_edit, dtype=bool)),
                       m0=np.linalg.norm(S_r['m']['all'] - S_p['m']['all']) <= 1e-8 * np.linalg.norm(S_r['m']['all']),
-                      keys=set(S_r['m'].keys()) == set(S_p['m'].keys()),
+                      keys=set(S_r['m'].keys()) == set(S_p['m'].keys()) - {'grid_biases'},      # the reference has no parser for grid biases (m0 covers their columns)
                       R=set(S_r['R']) == set(S_p['R']) and all(_close(S_r['R'][q], S_p['R'][q]) for q in S_r['R']),
                       RMS=set(S_r['RMS']) == set(S_p['RMS']) and all(_close(S_r['RMS'][q], S_p['RMS'][q]) for q in S_r['RMS']))
         for key in ('z0', 'dz'):

@@ -50,7 +50,7 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             case = os.path.join(tmp, 'case.pkl')
             with open(case, 'wb') as f:
-                pickle.dump((pts, kw), f)
+                pickle.dump((pts, F.package_kw(kw)), f)
             port = str(34000 + (os.getpid() + 7 * k) % 2000)
             outs = [os.path.join(tmp, 'rank%d.npz' % r) for r in range(world)]
             procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), port, case, outs[r]], stdout=subprocess.PIPE,
