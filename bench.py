@@ -22,7 +22,8 @@ residuals, sigma_extra (RDE + Brent) and 3-sigma masks, parse_model.
 
 With N > 1 the normal matrix is row-sharded: every rank owns a range of dz-node blocks (its rows of N, built from its own
 points plus halo copies), and the ranks exchange p inside the CG step kernel with stores into peer memory over NVLink --
-no collective inside the iteration.  Strong scaling (total work fixed).
+no collective inside the iteration.  Strong scaling (total work fixed).  An untimed pass compares the N-GPU fit with a one-GPU fit of
+the same points on rank 0 (roofline.parity).
 
 `--impl reference` runs only the CPU arm (rank 0; other ranks exit 0): the reference's own smooth_fit under stub
 dependencies when /root/reference exists (build container), else the oracle port (GPU box); SuiteSparseQR is replaced by
@@ -357,6 +358,31 @@ def run_b200(a):
     stage_times = {k: round(v, 4) for k, v in Sd['timing']['stages'].items()}
     Sd = None
     barrier()
+    # ---- untimed multi-GPU parity record: the row-sharded fit of all ranks against a one-GPU fit of the same points on rank 0
+    # (what tests/dist_check.py checks at small sizes): masks after every outer iteration, final mask, model
+    parity_multi = None
+    if world > 1 and not a.no_parity:
+        try:
+            hm = []
+            Sm = fit(dev, history=hm)
+            if rank == 0:
+                h1 = []
+                D1 = L.point_data.data().from_dict({f: dev[f] for f in fields})
+                S1 = L.smooth_fit(data=D1, VERBOSE=False, history=h1, **kw)
+                mm, m1 = Sm['m']['all'], S1['m']['all']
+                parity_multi = {
+                    'against': 'the same fit on one GPU (rank 0, dist=None) on the same 1e7 points',
+                    'masks_identical_per_iteration': bool(len(hm) == len(h1) and all(x['mask_out'].size == y['mask_out'].size and
+                                                                                     np.array_equal(x['mask_out'], y['mask_out']) for x, y in zip(hm, h1))),
+                    'final_mask_identical': bool(np.array_equal(Sm['data'].three_sigma_edit, S1['data'].three_sigma_edit)),
+                    'rel_l2_m0': float(np.linalg.norm(mm - m1) / np.linalg.norm(m1)),
+                    'max_abs_z_est': float(np.max(np.abs(np.asarray(Sm['data'].z_est) - np.asarray(S1['data'].z_est)))),
+                    'cg_iterations': [[h['pcg']['iterations'] for h in hh] for hh in (hm, h1)]}
+                S1 = D1 = None
+            Sm = None
+        except Exception as e:       # noqa: BLE001 -- a record, not a gate: the timed numbers above stand either way
+            parity_multi = {'error': repr(e)[:300]} if rank == 0 else None
+        barrier()
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -436,6 +462,9 @@ def run_b200(a):
                   'near_threshold': [int(v) for v in Sa['timing'].get('near_threshold', [])],
                   'near_threshold_definition': 'points whose scaled residual lies within 1e-6 of the 3-sigma threshold, per outer iteration',
                   'cg_iterations': [[h['pcg']['iterations'] for h in hh] for hh in (h0, h1)]}
+        roofline['parity'] = parity
+    elif parity_multi is not None:
+        parity = parity_multi
         roofline['parity'] = parity
 
     # ---- untimed variant: the same fit WITH the setup_grid_bias term of cfg 4 (the timed workload leaves it out: the reference's
