@@ -995,6 +995,25 @@ def smooth_fit(**kwargs):
         averaging_ops.update(setup_avg_mask_ops(grids['dz'], G_data.col_N, args['avg_masks'], args['dzdt_lags']))
         if valid_data is None:              # no iterations: the validity mask as it stands (every point valid)
             valid_data = np.ones(n_all, dtype=bool)
+        if args['compute_E']:
+            # the reference propagates errors without a fit as well (smooth_fit.py:689-712): the initial edit mask and the
+            # sigma_extra the data carry; without that field it estimates one from data.z_est, which no fit has produced
+            if 'sigma_extra' not in data.fields:
+                raise AttributeError("'data' object has no attribute 'z_est'")
+            if dist is not None and dist.world > 1:
+                raise NotImplementedError('compute_E runs on one GPU')
+            from .propagate_errors import covariance_dense, calc_and_parse_errors
+            se0 = _field_dev(data, 'sigma_extra')
+            if order is not None:
+                se0 = se0[order].contiguous()
+            n_cols = int(G_data.col_N)
+            w_e = torch.cat((in_TSE.to(f64) / (s_loc * s_loc + se0 * se0), 1. / Ec_d ** 2))
+            fixed = np.setdiff1d(np.arange(n_cols), np.asarray(Ip_c.free_cols)) if not sp.issparse(Ip_c) else \
+                np.setdiff1d(np.arange(n_cols), np.unique(Ip_c.tocoo().row))
+            cov = covariance_dense(G_data._csr_device(col_N=n_cols, row_N=hi - lo), Gc._csr_device(col_N=n_cols, row_N=int(Gc.N_eq)), w_e, fixed)
+            calc_and_parse_errors(E, cov, grids, G_data, Gc, averaging_ops, bias_model, args['bias_params'])
+            del cov
+            stages.mark('compute_E')
     stages.mark('epilogue')
     return {'m': m, 'E': E, 'data': data, 'grids': grids, 'valid_data': valid_data, 'TOC': Gc.TOC, 'R': R, 'RMS': RMS,
             'timing': timing, 'E_RMS': args['E_RMS'], 'dzdt_lags': args['dzdt_lags']}
